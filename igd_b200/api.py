@@ -1,0 +1,306 @@
+"""Python binding of the igd_b200 C-ABI (include/igd_b200.h) via ctypes.
+
+Mirrors the reference's handle-based binding surface -- ``igd_py.open / search_1 / search_n /
+get_nFiles`` (``/root/reference/src_py/igd_py.pyx:21-44``) and R's ``search_nr``
+(``/root/reference/IGDr/src/igd_search.c:340-355``) -- on top of ``libigd_b200.so``.  Every search runs in
+the CUDA library; if the library or a GPU is missing the calls raise, they never fall back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libigd_b200.so")
+CLI_PATH = os.path.join(_HERE, "bin", "igd")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "igd_b200.h")
+
+
+class IGDError(RuntimeError):
+    pass
+
+
+class _HitList(C.Structure):
+    _fields_ = [("total", C.c_int64), ("n_queries", C.c_int64), ("query_off", C.POINTER(C.c_int64)),
+                ("start", C.POINTER(C.c_int32)), ("end", C.POINTER(C.c_int32)), ("file", C.POINTER(C.c_int32))]
+
+
+class _Queries(C.Structure):
+    _fields_ = [("n", C.c_int64), ("name_id", C.POINTER(C.c_int32)), ("qs", C.POINTER(C.c_int32)),
+                ("qe", C.POINTER(C.c_int32)), ("n_names", C.c_int32), ("names", C.POINTER(C.c_char_p))]
+
+
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+_u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+
+_lib = None
+
+
+def load_library():
+    """dlopen libigd_b200.so (built by ``__graft_entry__.build()`` / ``make -C igd_b200/csrc``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise IGDError(f"{LIB_PATH} is missing: build it with `make -C igd_b200/csrc` "
+                       "(igd_b200 has no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.igd_b200_open.restype = vp
+    L.igd_b200_open.argtypes = [C.c_char_p, C.c_int]
+    L.igd_b200_close.argtypes = [vp]
+    L.igd_b200_last_error.restype = C.c_char_p
+    L.igd_b200_device_count.restype = C.c_int
+    for f in ("nfiles", "nctg", "nbp", "gtype"):
+        getattr(L, "igd_b200_" + f).restype = C.c_int32
+        getattr(L, "igd_b200_" + f).argtypes = [vp]
+    for f in ("ntiles", "nrecords", "device_bytes", "launch_count"):
+        getattr(L, "igd_b200_" + f).restype = C.c_int64
+        getattr(L, "igd_b200_" + f).argtypes = [vp]
+    L.igd_b200_ntile.restype = C.c_int32
+    L.igd_b200_ntile.argtypes = [vp, C.c_int32]
+    L.igd_b200_ncnt.restype = C.c_int32
+    L.igd_b200_ncnt.argtypes = [vp, C.c_int32, C.c_int32]
+    L.igd_b200_file_nr.restype = C.c_int32
+    L.igd_b200_file_nr.argtypes = [vp, C.c_int32]
+    L.igd_b200_file_name.restype = C.c_char_p
+    L.igd_b200_file_name.argtypes = [vp, C.c_int32]
+    L.igd_b200_ctg_name.restype = C.c_char_p
+    L.igd_b200_ctg_name.argtypes = [vp, C.c_int32]
+    L.igd_b200_ctg_id.restype = C.c_int32
+    L.igd_b200_ctg_id.argtypes = [vp, C.c_char_p]
+    L.get_overlaps_n.restype = C.c_int64
+    L.get_overlaps_n.argtypes = [vp, C.c_int64, C.POINTER(C.c_char_p), _i32p, _i32p, C.c_int32, _i64p]
+    L.igd_b200_count.restype = C.c_int64
+    L.igd_b200_count.argtypes = [vp, C.c_int64, vp, vp, vp, C.c_int32, _i64p]
+    L.igd_b200_count_device.restype = C.c_int
+    L.igd_b200_count_device.argtypes = [vp, C.c_int64, vp, vp, vp, C.c_int32, vp, vp]
+    L.igd_b200_full.restype = C.c_int
+    L.igd_b200_full.argtypes = [vp, C.c_int64, _i32p, _i32p, _i32p, C.POINTER(_HitList)]
+    L.igd_b200_hitlist_free.argtypes = [C.POINTER(_HitList)]
+    L.igd_b200_hitsmap.restype = C.c_int64
+    L.igd_b200_hitsmap.argtypes = [vp, C.c_int32, _u32p]
+    L.igd_b200_read_bed.restype = C.POINTER(_Queries)
+    L.igd_b200_read_bed.argtypes = [C.c_char_p]
+    L.igd_b200_queries_free.argtypes = [C.POINTER(_Queries)]
+    L.igd_b200_resolve.argtypes = [vp, C.POINTER(_Queries), _i32p]
+    L.search.restype = C.c_int64
+    L.search.argtypes = [vp, C.c_char_p, C.c_int32, _i64p]
+    L.igd_b200_seqpare.restype = C.c_int
+    L.igd_b200_seqpare.argtypes = [vp, C.c_char_p, _f64p]
+    L.igd_b200_query_cost.restype = C.c_int
+    L.igd_b200_query_cost.argtypes = [vp, C.c_int64, _i32p, _i32p, _i32p, _i64p]
+    L.igd_b200_last_timing.argtypes = [vp, C.POINTER(C.c_float * 3)]
+    L.igd_b200_use.argtypes = [vp]
+    L.igd_b200_current.restype = vp
+    L.get_overlaps.restype = C.c_int32
+    L.get_overlaps.argtypes = [C.c_char_p, C.c_int32, C.c_int32, _i64p]
+    L.get_overlaps_v.restype = C.c_int32
+    L.get_overlaps_v.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.c_int32, _i64p]
+    L.getOverlaps.restype = C.c_int64
+    L.getOverlaps.argtypes = [C.c_char_p, _i64p]
+    L.getOverlaps_v.restype = C.c_int64
+    L.getOverlaps_v.argtypes = [C.c_char_p, _i64p, C.c_int32]
+    L.getMap.restype = C.c_int64
+    L.getMap_v.restype = C.c_int64
+    L.seqOverlaps.argtypes = [C.c_char_p, _f64p]
+    _lib = L
+    return L
+
+
+def last_error() -> str:
+    return load_library().igd_b200_last_error().decode(errors="replace")
+
+
+class QuerySet:
+    """Accepted lines of a BED(.gz) query file (parse_bed's rule, src/igd_base.c:53-72)."""
+
+    def __init__(self, path: str):
+        L = load_library()
+        p = L.igd_b200_read_bed(os.fsencode(path))
+        if not p:
+            raise FileNotFoundError(path)
+        try:
+            q = p.contents
+            self.n = int(q.n)
+            mk = lambda ptr: (np.ctypeslib.as_array(ptr, (self.n,)).copy() if self.n else np.zeros(0, np.int32))
+            self.name_id, self.qs, self.qe = mk(q.name_id), mk(q.qs), mk(q.qe)
+            self.names = [q.names[i].decode() for i in range(q.n_names)]
+        finally:
+            L.igd_b200_queries_free(p)
+
+
+class IGD:
+    """An .igd database resident in the HBM of one GPU."""
+
+    def __init__(self, igd_path: str | None = None, device: int = 0):
+        self._L = load_library()
+        self._h = None
+        if igd_path is not None:
+            self.open(igd_path, device)
+
+    # -- igd_py.open (src_py/igd_py.pyx:27-30) ---------------------------------------------------------
+    def open(self, igd_path: str, device: int = 0) -> "IGD":
+        self.close()
+        h = self._L.igd_b200_open(os.fsencode(igd_path), device)
+        if not h:
+            raise IGDError(last_error())
+        self._h = h
+        L = self._L
+        self.path = igd_path
+        self.device = device
+        self.nfiles = L.igd_b200_nfiles(h)
+        self.nctg = L.igd_b200_nctg(h)
+        self.nbp = L.igd_b200_nbp(h)
+        self.ntiles = L.igd_b200_ntiles(h)
+        self.nrecords = L.igd_b200_nrecords(h)
+        self.ctg_names = [L.igd_b200_ctg_name(h, c).decode(errors="replace") for c in range(self.nctg)]
+        self.file_names = [L.igd_b200_file_name(h, i).decode() for i in range(self.nfiles)]
+        self.file_nr = np.array([L.igd_b200_file_nr(h, i) for i in range(self.nfiles)], np.int32)
+        self._ctg = {n: i for i, n in reversed(list(enumerate(self.ctg_names)))}
+        return self
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._L.igd_b200_close(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _need(self):
+        if not self._h:
+            raise IGDError("database is not open")
+        return self._h
+
+    # -- metadata ----------------------------------------------------------------------------------
+    def get_nFiles(self) -> int:                                  # igd_py.get_nFiles
+        return self.nfiles
+
+    def ctg_id(self, name: str) -> int:
+        return self._ctg.get(name, -1)
+
+    def ntile(self, ctg: int) -> int:
+        return self._L.igd_b200_ntile(self._need(), ctg)
+
+    def device_bytes(self) -> int:
+        return self._L.igd_b200_device_bytes(self._need())
+
+    def launch_count(self) -> int:
+        return self._L.igd_b200_launch_count(self._need())
+
+    def last_timing(self):
+        t = (C.c_float * 3)()
+        self._L.igd_b200_last_timing(self._need(), C.byref(t))
+        return {"h2d_ms": t[0], "kernel_ms": t[1], "d2h_ms": t[2]}
+
+    def resolve_names(self, names) -> np.ndarray:
+        return np.array([self.ctg_id(n) for n in names], np.int32)
+
+    def resolve(self, q: QuerySet) -> np.ndarray:
+        m = self.resolve_names(q.names) if q.names else np.zeros(0, np.int32)
+        return m[q.name_id] if q.n else np.zeros(0, np.int32)
+
+    # -- count search ------------------------------------------------------------------------------
+    @staticmethod
+    def _a(x):
+        return np.ascontiguousarray(x, dtype=np.int32)
+
+    def count(self, ctg, qs, qe, v: int = 0, hits: np.ndarray | None = None):
+        """Batched count search on contig ids.  Returns (hits, overlaps found by this call)."""
+        ctg, qs, qe = self._a(ctg), self._a(qs), self._a(qe)
+        if hits is None:
+            hits = np.zeros(self.nfiles, np.int64)
+        r = self._L.igd_b200_count(self._need(), len(ctg), ctg.ctypes.data, qs.ctypes.data, qe.ctypes.data,
+                                   int(v), hits)
+        if r < 0:
+            raise IGDError(last_error())
+        return hits, int(r)
+
+    def count_ptr(self, n: int, ctg_ptr: int, qs_ptr: int, qe_ptr: int, v: int, hits: np.ndarray) -> int:
+        """Same, on raw host pointers (e.g. pinned torch tensors)."""
+        r = self._L.igd_b200_count(self._need(), n, ctg_ptr, qs_ptr, qe_ptr, int(v), hits)
+        if r < 0:
+            raise IGDError(last_error())
+        return int(r)
+
+    def get_overlaps_n(self, chrm: list[str], qs, qe, v: int = 0, hits: np.ndarray | None = None):
+        """search_nr(igdr, n, chrm, qs, qe) (IGDr/R/IGDr.R:54-57)."""
+        qs, qe = self._a(qs), self._a(qe)
+        if hits is None:
+            hits = np.zeros(self.nfiles, np.int64)
+        arr = (C.c_char_p * len(chrm))(*[c.encode() for c in chrm])
+        r = self._L.get_overlaps_n(self._need(), len(chrm), arr, qs, qe, int(v), hits)
+        if r < 0:
+            raise IGDError(last_error())
+        return hits, int(r)
+
+    def search_1(self, chrm: str, qs: int, qe: int, hits: np.ndarray | None = None, v: int = 0):
+        """igd_py.search_1 (src_py/igd_py.pyx:39-41)."""
+        return self.get_overlaps_n([chrm], [qs], [qe], v, hits)
+
+    def search_n(self, qfile: str, hits: np.ndarray | None = None, v: int = 0):
+        """igd_py.search_n (src_py/igd_py.pyx:42-44): whole query file."""
+        if hits is None:
+            hits = np.zeros(self.nfiles, np.int64)
+        r = self._L.search(self._need(), os.fsencode(qfile), int(v), hits)
+        if r < 0:
+            raise IGDError(last_error())
+        return hits, int(r)
+
+    def count_device(self, n: int, d_ctg: int, d_qs: int, d_qe: int, v: int, d_hits: int, stream: int = 0) -> None:
+        """Device-pointer form: enqueue on a CUDA stream; d_hits is uint64[nfiles], incremented."""
+        if self._L.igd_b200_count_device(self._need(), n, d_ctg, d_qs, d_qe, int(v), d_hits, stream):
+            raise IGDError(last_error())
+
+    def query_cost(self, ctg, qs, qe) -> np.ndarray:
+        ctg, qs, qe = self._a(ctg), self._a(qs), self._a(qe)
+        cost = np.zeros(len(ctg), np.int64)
+        self._L.igd_b200_query_cost(self._need(), len(ctg), ctg, qs, qe, cost)
+        return cost
+
+    # -- -f ------------------------------------------------------------------------------------------
+    def full(self, ctg, qs, qe):
+        """-> (query_off[n+1], start, end, file) in the reference's per-query order."""
+        ctg, qs, qe = self._a(ctg), self._a(qs), self._a(qe)
+        hl = _HitList()
+        if self._L.igd_b200_full(self._need(), len(ctg), ctg, qs, qe, C.byref(hl)):
+            raise IGDError(last_error())
+        try:
+            n, t = len(ctg), int(hl.total)
+            qoff = np.ctypeslib.as_array(hl.query_off, (n + 1,)).copy()
+            mk = lambda p: np.ctypeslib.as_array(p, (t,)).copy() if t else np.zeros(0, np.int32)
+            return qoff, mk(hl.start), mk(hl.end), mk(hl.file)
+        finally:
+            self._L.igd_b200_hitlist_free(C.byref(hl))
+
+    # -- -m / -s -----------------------------------------------------------------------------------------
+    def hitsmap(self, v: int = 0) -> np.ndarray:
+        hm = np.zeros((self.nfiles, self.nfiles), np.uint32)
+        if self._L.igd_b200_hitsmap(self._need(), int(v), hm.reshape(-1)) < 0:
+            raise IGDError(last_error())
+        return hm
+
+    def seqpare(self, qfile: str) -> np.ndarray:
+        sm = np.zeros(self.nfiles, np.float64)
+        if self._L.igd_b200_seqpare(self._need(), os.fsencode(qfile), sm):
+            raise IGDError(last_error())
+        return sm
+
+    # -- reference-named global-state entry points ---------------------------------------------------------
+    def use(self) -> None:
+        """Make this handle the one the reference-named symbols (get_overlaps, getOverlaps, ...) act on."""
+        self._L.igd_b200_use(self._need())

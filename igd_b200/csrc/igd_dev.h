@@ -1,0 +1,49 @@
+/* Thin C-ABI between the host C code (igd_host.c) and the CUDA layer (igd_dev.cu).
+ * Internal to libigd_b200.so; the public boundary is include/igd_b200.h. */
+#ifndef IGD_DEV_H
+#define IGD_DEV_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct igdb_dev igdb_dev;
+
+int igdb_device_count(void);
+const char *igdb_dev_error(void);       /* thread-local message of the last CUDA-layer failure */
+
+/* Device image of one database.  ntile[nctg], ncnt[sum ntile] are the header tables of the .igd file
+ * (reference layout: src/igd_base.c:408-419). */
+igdb_dev *igdb_dev_create(int device, int32_t nbp, int32_t nctg, const int32_t *ntile,
+                          const int32_t *ncnt, int32_t nfiles);
+/* stream a run of on-disk gdata_t records [rec0, rec0+nrec) (AoS, 16 B each) into the SoA image */
+int igdb_dev_upload(igdb_dev *d, int64_t rec0, int64_t nrec, const void *aos);
+/* after the last upload: per-tile dedupe start (tS) and first start */
+int igdb_dev_finalize(igdb_dev *d);
+void igdb_dev_destroy(igdb_dev *d);
+int64_t igdb_dev_bytes(const igdb_dev *d);
+int64_t igdb_dev_launches(const igdb_dev *d);
+void *igdb_dev_pinned(igdb_dev *d, size_t bytes);   /* reusable pinned staging buffer (upload) */
+
+/* count (mode_v = 0: get_overlaps control flow) / -v (mode_v = 1: get_overlaps_v control flow and the
+ * value >= v predicate).  Host buffers; hits_delta[nfiles] receives the counts of THIS call. t_ms[3] = H2D,
+ * kernels, D2H (may be NULL). */
+int igdb_dev_count_host(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_t *qs, const int32_t *qe,
+                        int mode_v, int32_t v, uint64_t *hits_delta, float *t_ms);
+/* device buffers, enqueued on stream; d_hits[nfiles] incremented */
+int igdb_dev_count_device(igdb_dev *d, int64_t n, const int32_t *d_ctg, const int32_t *d_qs,
+                          const int32_t *d_qe, int mode_v, int32_t v, uint64_t *d_hits, void *stream);
+
+/* -f: returns total (>= 0) and malloc'ed host arrays; query_off has n+1 entries */
+int64_t igdb_dev_full_host(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_t *qs, const int32_t *qe,
+                           int64_t **query_off, int32_t **start, int32_t **end, int32_t **file);
+
+/* -m */
+int64_t igdb_dev_hitsmap_host(igdb_dev *d, int32_t v, uint32_t *hitmap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,461 @@
+/* igd_b200 host side (C): .igd / _index.tsv parsing, BED query ingest, the handle-based C-ABI of
+ * include/igd_b200.h and the reference-named global-state entry points.  All searching is done by the
+ * CUDA layer (igd_dev.cu) through igd_dev.h; there is no CPU search path in this library. */
+#define _GNU_SOURCE
+#include "igd_b200.h"
+#include "igd_dev.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <zlib.h>
+
+struct igd_b200 {
+    int32_t nbp, gtype, nctg, nfiles;
+    int32_t *ntile;                 /* [nctg]            iGD_t.nTile */
+    int64_t *tbase;                 /* [nctg+1]          first global tile of each contig */
+    int32_t *ncnt;                  /* [sum ntile]       iGD_t.nCnt, flattened contig-major */
+    char (*cname)[40];              /* iGD_t.cName */
+    char **fname;                   /* info_t.fileName */
+    int32_t *fnr;                   /* info_t.nr */
+    int64_t nrec, ntiles;
+    igdb_dev *dev;
+    float t_ms[3];
+    uint64_t *delta;                /* [nfiles] per-call counts */
+};
+
+static __thread char g_err[512] = "";
+static igd_b200_t *g_current = NULL;
+
+const char *igd_b200_last_error(void) { return g_err[0] ? g_err : igdb_dev_error(); }
+int igd_b200_device_count(void) { return igdb_device_count(); }
+
+static void set_err(const char *fmt, const char *arg)
+{
+    snprintf(g_err, sizeof g_err, fmt, arg);
+}
+
+/* ---- <stem>_index.tsv: written by src/igd_create.c:96-111, read by get_fileinfo src/igd_base.c:235-267.
+ * The header line is skipped; column 2 is the file name, column 3 the number of regions. -------------- */
+static int read_index_tsv(igd_b200_t *h, const char *igd_path)
+{
+    size_t L = strlen(igd_path);
+    char *tsv = malloc(L + 16);
+    memcpy(tsv, igd_path, L + 1);
+    char *dot = strrchr(tsv, '.');
+    if (!dot) { free(tsv); return -1; }
+    strcpy(dot, "_index.tsv");
+    FILE *f = fopen(tsv, "r");
+    if (!f) { set_err("file not found:%s", tsv); free(tsv); return -1; }
+    free(tsv);
+    char buf[1024];
+    int cap = 64, n = 0;
+    h->fname = malloc(sizeof(char *) * cap);
+    h->fnr = malloc(sizeof(int32_t) * cap);
+    if (!fgets(buf, sizeof buf, f)) { fclose(f); h->nfiles = 0; return 0; }
+    while (fgets(buf, sizeof buf, f)) {
+        if (n == cap) {
+            cap *= 2;
+            h->fname = realloc(h->fname, sizeof(char *) * cap);
+            h->fnr = realloc(h->fnr, sizeof(int32_t) * cap);
+        }
+        char *save = NULL;
+        strtok_r(buf, "\t", &save);
+        char *name = strtok_r(NULL, "\t", &save);
+        char *nr = strtok_r(NULL, "\t", &save);
+        h->fname[n] = strdup(name ? name : "");
+        h->fnr[n] = nr ? (int32_t)atol(nr) : 0;
+        n++;
+    }
+    fclose(f);
+    h->nfiles = n;
+    return 0;
+}
+
+/* ---- .igd: header tables as in get_igdinfo (src/igd_base.c:269-323); payload streamed to the device.
+ * Layout (src/igd_base.c:408-458): nbp, gType, nCtg, nTile[nCtg], nCnt[sum nTile], 40-byte names, then
+ * every tile's gdata_t records, contig-major. ---------------------------------------------------------- */
+igd_b200_t *igd_b200_open(const char *igd_path, int device)
+{
+    g_err[0] = 0;
+    FILE *f = fopen(igd_path, "rb");
+    if (!f) { set_err("Can't open file %s", igd_path); return NULL; }
+    igd_b200_t *h = calloc(1, sizeof *h);
+    int32_t hd[3];
+    if (fread(hd, 4, 3, f) != 3) { set_err("%s: truncated header", igd_path); goto fail; }
+    h->nbp = hd[0], h->gtype = hd[1], h->nctg = hd[2];
+    if (h->gtype != 1) { set_err("%s: only gType 1 (gdata_t) databases are supported", igd_path); goto fail; }
+    if (h->nbp <= 0 || h->nctg < 0) { set_err("%s: corrupt header", igd_path); goto fail; }
+    int32_t m = h->nctg;
+    h->ntile = malloc(sizeof(int32_t) * (size_t)(m + 1));
+    if (m && fread(h->ntile, 4, m, f) != (size_t)m) { set_err("%s: truncated header", igd_path); goto fail; }
+    h->tbase = malloc(sizeof(int64_t) * (size_t)(m + 1));
+    h->tbase[0] = 0;
+    for (int i = 0; i < m; i++) {
+        if (h->ntile[i] < 0) { set_err("%s: corrupt header", igd_path); goto fail; }
+        h->tbase[i + 1] = h->tbase[i] + h->ntile[i];
+    }
+    h->ntiles = h->tbase[m];
+    if (h->ntiles >= 0x7fffffff) { set_err("%s: too many tiles", igd_path); goto fail; }
+    h->ncnt = malloc(sizeof(int32_t) * (size_t)(h->ntiles + 1));
+    if (h->ntiles && fread(h->ncnt, 4, h->ntiles, f) != (size_t)h->ntiles) {
+        set_err("%s: truncated header", igd_path);
+        goto fail;
+    }
+    h->cname = malloc(40 * (size_t)(m + 1));
+    if (m && fread(h->cname, 40, m, f) != (size_t)m) { set_err("%s: truncated header", igd_path); goto fail; }
+    for (int i = 0; i < m; i++) h->cname[i][39] = 0;
+    for (int64_t t = 0; t < h->ntiles; t++) {
+        if (h->ncnt[t] < 0) { set_err("%s: corrupt header", igd_path); goto fail; }
+        h->nrec += h->ncnt[t];
+    }
+    if (read_index_tsv(h, igd_path)) goto fail;
+    h->delta = calloc((size_t)h->nfiles + 1, sizeof(uint64_t));
+
+    if (igdb_device_count() <= 0) {
+        set_err("%s: no CUDA device available (igd_b200 has no CPU search path)", igd_path);
+        goto fail;
+    }
+    h->dev = igdb_dev_create(device, h->nbp, h->nctg, h->ntile, h->ncnt, h->nfiles);
+    if (!h->dev) goto fail;
+    {
+        const int64_t CH = 4 << 20;                     /* records per chunk: 64 MiB */
+        int64_t chunk = h->nrec < CH ? h->nrec : CH;
+        char *buf = chunk ? igdb_dev_pinned(h->dev, (size_t)chunk * 16) : NULL;
+        if (chunk && !buf) { set_err("%s: cannot allocate the pinned upload buffer", igd_path); goto fail; }
+        for (int64_t r = 0; r < h->nrec; r += chunk) {
+            int64_t k = h->nrec - r < chunk ? h->nrec - r : chunk;
+            if (fread(buf, 16, (size_t)k, f) != (size_t)k) { set_err("%s: truncated tile data", igd_path); goto fail; }
+            /* file indices index hits[]: reject records the reference would write out of bounds with */
+            for (int64_t i = 0; i < k; i++) {
+                int32_t idx = ((int32_t *)buf)[4 * i];
+                if (idx < 0 || idx >= h->nfiles) { set_err("%s: record with file index outside _index.tsv", igd_path); goto fail; }
+            }
+            if (igdb_dev_upload(h->dev, r, k, buf)) goto fail;
+        }
+        if (igdb_dev_finalize(h->dev)) goto fail;
+    }
+    fclose(f);
+    return h;
+fail:
+    fclose(f);
+    igd_b200_close(h);
+    return NULL;
+}
+
+void igd_b200_close(igd_b200_t *h)
+{
+    if (!h) return;
+    if (g_current == h) g_current = NULL;
+    if (h->dev) igdb_dev_destroy(h->dev);
+    if (h->fname) for (int i = 0; i < h->nfiles; i++) free(h->fname[i]);
+    free(h->fname); free(h->fnr); free(h->ntile); free(h->tbase); free(h->ncnt); free(h->cname);
+    free(h->delta); free(h);
+}
+
+int32_t igd_b200_nfiles(const igd_b200_t *h) { return h->nfiles; }
+int32_t igd_b200_nctg(const igd_b200_t *h) { return h->nctg; }
+int32_t igd_b200_nbp(const igd_b200_t *h) { return h->nbp; }
+int32_t igd_b200_gtype(const igd_b200_t *h) { return h->gtype; }
+int64_t igd_b200_ntiles(const igd_b200_t *h) { return h->ntiles; }
+int64_t igd_b200_nrecords(const igd_b200_t *h) { return h->nrec; }
+int32_t igd_b200_ntile(const igd_b200_t *h, int32_t c) { return c >= 0 && c < h->nctg ? h->ntile[c] : 0; }
+int32_t igd_b200_ncnt(const igd_b200_t *h, int32_t c, int32_t t)
+{
+    if (c < 0 || c >= h->nctg || t < 0 || t >= h->ntile[c]) return 0;
+    return h->ncnt[h->tbase[c] + t];
+}
+int32_t igd_b200_file_nr(const igd_b200_t *h, int32_t i) { return i >= 0 && i < h->nfiles ? h->fnr[i] : 0; }
+const char *igd_b200_file_name(const igd_b200_t *h, int32_t i) { return i >= 0 && i < h->nfiles ? h->fname[i] : ""; }
+const char *igd_b200_ctg_name(const igd_b200_t *h, int32_t c) { return c >= 0 && c < h->nctg ? h->cname[c] : ""; }
+int64_t igd_b200_device_bytes(const igd_b200_t *h) { return igdb_dev_bytes(h->dev); }
+int64_t igd_b200_launch_count(const igd_b200_t *h) { return igdb_dev_launches(h->dev); }
+void igd_b200_last_timing(const igd_b200_t *h, float t[3]) { t[0] = h->t_ms[0], t[1] = h->t_ms[1], t[2] = h->t_ms[2]; }
+
+/* get_id (src/igd_base.c:325-331): exact string match on the contig name */
+int32_t igd_b200_ctg_id(const igd_b200_t *h, const char *chrm)
+{
+    for (int i = 0; i < h->nctg; i++)
+        if (strcmp(h->cname[i], chrm) == 0) return i;
+    return -1;
+}
+
+/* ---- count -------------------------------------------------------------------------------------- */
+static int64_t count_mode(igd_b200_t *h, int64_t n, const int32_t *ctg, const int32_t *qs, const int32_t *qe,
+                          int mode_v, int32_t v, int64_t *hits)
+{
+    g_err[0] = 0;
+    if (n <= 0) return 0;
+    if (igdb_dev_count_host(h->dev, n, ctg, qs, qe, mode_v, v, h->delta, h->t_ms)) return -1;
+    int64_t total = 0;
+    for (int i = 0; i < h->nfiles; i++) {
+        hits[i] += (int64_t)h->delta[i];
+        total += (int64_t)h->delta[i];
+    }
+    return total;
+}
+
+/* the CLI's dispatch: the signal filter (and get_overlaps_v's control flow) only when v > 0
+ * (src/igd_search.c:1027,1045) */
+int64_t igd_b200_count(igd_b200_t *h, int64_t n, const int32_t *ctg, const int32_t *qs, const int32_t *qe,
+                       int32_t v, int64_t *hits)
+{
+    return count_mode(h, n, ctg, qs, qe, v > 0, v, hits);
+}
+
+int igd_b200_count_device(igd_b200_t *h, int64_t n, const int32_t *d_ctg, const int32_t *d_qs,
+                          const int32_t *d_qe, int32_t v, uint64_t *d_hits, void *stream)
+{
+    g_err[0] = 0;
+    return igdb_dev_count_device(h->dev, n, d_ctg, d_qs, d_qe, v > 0, v, d_hits, stream);
+}
+
+int64_t get_overlaps_n(igd_b200_t *h, int64_t n, const char *const *chrm, const int32_t *qs,
+                       const int32_t *qe, int32_t v, int64_t *hits)
+{
+    if (n <= 0) return 0;
+    int32_t *ctg = malloc(sizeof(int32_t) * (size_t)n);
+    int32_t last = -1;
+    for (int64_t i = 0; i < n; i++) {
+        if (last >= 0 && strcmp(h->cname[last], chrm[i]) == 0) ctg[i] = last;
+        else ctg[i] = last = igd_b200_ctg_id(h, chrm[i]);
+    }
+    int64_t r = igd_b200_count(h, n, ctg, qs, qe, v, hits);
+    free(ctg);
+    return r;
+}
+
+int igd_b200_full(igd_b200_t *h, int64_t n, const int32_t *ctg, const int32_t *qs, const int32_t *qe,
+                  igd_b200_hitlist *out)
+{
+    g_err[0] = 0;
+    memset(out, 0, sizeof *out);
+    out->n_queries = n;
+    out->total = igdb_dev_full_host(h->dev, n, ctg, qs, qe, &out->query_off, &out->start, &out->end, &out->file);
+    if (out->total < 0) { igd_b200_hitlist_free(out); return -1; }
+    return 0;
+}
+
+void igd_b200_hitlist_free(igd_b200_hitlist *l)
+{
+    if (!l) return;
+    free(l->query_off); free(l->start); free(l->end); free(l->file);
+    memset(l, 0, sizeof *l);
+}
+
+int64_t igd_b200_hitsmap(igd_b200_t *h, int32_t v, uint32_t *hitmap)
+{
+    g_err[0] = 0;
+    return igdb_dev_hitsmap_host(h->dev, v, hitmap);
+}
+
+/* estimated scan bytes per query: 4 * sum of nCnt over the bins the query touches */
+int igd_b200_query_cost(const igd_b200_t *h, int64_t n, const int32_t *ctg, const int32_t *qs,
+                        const int32_t *qe, int64_t *cost)
+{
+    for (int64_t i = 0; i < n; i++) {
+        int64_t c = 16;
+        int32_t k = ctg[i];
+        if (k >= 0 && k < h->nctg) {
+            int32_t n1 = qs[i] / h->nbp, n2 = (qe[i] - 1) / h->nbp, mT = h->ntile[k] - 1;
+            if (n1 >= 0 && n1 <= mT) {
+                if (n2 > mT) n2 = mT;
+                const int32_t *nc = h->ncnt + h->tbase[k];
+                for (int32_t j = n1; j <= (n2 > n1 ? n2 : n1); j++) c += 8 + 4 * (int64_t)nc[j];
+            }
+        }
+        cost[i] = c;
+    }
+    return 0;
+}
+
+/* ---- query ingest ----------------------------------------------------------------------------------
+ * parse_bed's acceptance rule (src/igd_base.c:53-72): split on tabs, contig = field 0, start/end =
+ * atol of fields 1/2, accept iff >= 3 fields, contig begins "chr" and is shorter than 40 chars, end > 0.
+ * Lines end at '\n' with one trailing '\r' dropped (src/kseq.h:127); gzopen reads plain text too. */
+static int accept_query_line(char *s, char **ctg_out, int32_t *st_out, int32_t *en_out)
+{
+    int nf = 0;
+    char *fld = s, *ctg = NULL;
+    int32_t st = -1, en = -1;
+    for (char *p = s;; p++) {
+        char ch = *p;
+        if (ch != '\t' && ch != '\0') continue;
+        *p = '\0';
+        if (nf == 0) ctg = fld;
+        else if (nf == 1) st = (int32_t)atol(fld);
+        else if (nf == 2) en = (int32_t)atol(fld);
+        nf++;
+        fld = p + 1;
+        if (ch == '\0') break;
+    }
+    *ctg_out = ctg, *st_out = st, *en_out = en;
+    return nf >= 3 && strncmp(ctg, "chr", 3) == 0 && strlen(ctg) < 40 && en > 0;
+}
+
+static void queries_push(igd_b200_queries *Q, int64_t *cap, int *ncap, int *last, char *ctg, int32_t st, int32_t en)
+{
+    int id = -1;
+    if (*last >= 0 && strcmp(Q->names[*last], ctg) == 0) id = *last;
+    else
+        for (int k = 0; k < Q->n_names; k++)
+            if (strcmp(Q->names[k], ctg) == 0) { id = k; break; }
+    if (id < 0) {
+        if (Q->n_names == *ncap) Q->names = realloc(Q->names, sizeof(char *) * (size_t)(*ncap *= 2));
+        id = Q->n_names++;
+        Q->names[id] = strdup(ctg);
+    }
+    *last = id;
+    if (Q->n == *cap) {
+        *cap *= 2;
+        Q->name_id = realloc(Q->name_id, sizeof(int32_t) * (size_t)*cap);
+        Q->qs = realloc(Q->qs, sizeof(int32_t) * (size_t)*cap);
+        Q->qe = realloc(Q->qe, sizeof(int32_t) * (size_t)*cap);
+    }
+    Q->name_id[Q->n] = id, Q->qs[Q->n] = st, Q->qe[Q->n] = en;
+    Q->n++;
+}
+
+igd_b200_queries *igd_b200_read_bed(const char *path)
+{
+    gzFile fp = gzopen(path, "r");
+    if (!fp) return NULL;
+    gzbuffer(fp, 1 << 20);
+    igd_b200_queries *Q = calloc(1, sizeof *Q);
+    int64_t cap = 4096;
+    int ncap = 64, last = -1;
+    Q->name_id = malloc(sizeof(int32_t) * (size_t)cap);
+    Q->qs = malloc(sizeof(int32_t) * (size_t)cap);
+    Q->qe = malloc(sizeof(int32_t) * (size_t)cap);
+    Q->names = malloc(sizeof(char *) * (size_t)ncap);
+    size_t lcap = 1 << 12, llen = 0;
+    char *line = malloc(lcap);
+    static const int BUFSZ = 1 << 20;
+    char *buf = malloc(BUFSZ);
+    for (;;) {
+        int got = gzread(fp, buf, BUFSZ);
+        int eof = got <= 0;
+        if (eof) got = 0;
+        char *p = buf, *end = buf + got;
+        while (p < end || (eof && llen)) {
+            char *nl = p < end ? memchr(p, '\n', (size_t)(end - p)) : NULL;
+            size_t take = nl ? (size_t)(nl - p) : (size_t)(end - p);
+            if (llen + take + 2 > lcap) {
+                while (llen + take + 2 > lcap) lcap *= 2;
+                line = realloc(line, lcap);
+            }
+            memcpy(line + llen, p, take);
+            llen += take;
+            p += take;
+            if (!nl && !eof) break;                 /* partial line: wait for more input */
+            if (nl) p++;
+            if (llen && line[llen - 1] == '\r') llen--;
+            line[llen] = '\0';
+            char *ctg;
+            int32_t st, en;
+            if (accept_query_line(line, &ctg, &st, &en)) queries_push(Q, &cap, &ncap, &last, ctg, st, en);
+            llen = 0;
+            if (!nl) break;
+        }
+        if (eof) break;
+    }
+    free(buf);
+    free(line);
+    gzclose(fp);
+    return Q;
+}
+
+void igd_b200_queries_free(igd_b200_queries *q)
+{
+    if (!q) return;
+    for (int i = 0; i < q->n_names; i++) free(q->names[i]);
+    free(q->names); free(q->name_id); free(q->qs); free(q->qe); free(q);
+}
+
+void igd_b200_resolve(const igd_b200_t *h, const igd_b200_queries *q, int32_t *out)
+{
+    int32_t *map = malloc(sizeof(int32_t) * (size_t)(q->n_names + 1));
+    for (int k = 0; k < q->n_names; k++) map[k] = igd_b200_ctg_id(h, q->names[k]);
+    for (int64_t i = 0; i < q->n; i++) out[i] = map[q->name_id[i]];
+    free(map);
+}
+
+static int64_t search_mode(igd_b200_t *h, const char *qFile, int mode_v, int32_t v, int64_t *hits)
+{
+    g_err[0] = 0;
+    igd_b200_queries *Q = igd_b200_read_bed(qFile);
+    if (!Q) return 0;                               /* unopenable query file -> 0 (src/igd_search.c:701-702) */
+    int64_t r = 0;
+    if (Q->n) {
+        int32_t *ctg = malloc(sizeof(int32_t) * (size_t)Q->n);
+        igd_b200_resolve(h, Q, ctg);
+        r = count_mode(h, Q->n, ctg, Q->qs, Q->qe, mode_v, v, hits);
+        free(ctg);
+    }
+    igd_b200_queries_free(Q);
+    return r;
+}
+
+int64_t search(igd_b200_t *h, const char *qFile, int32_t v, int64_t *hits)
+{
+    return search_mode(h, qFile, v > 0, v, hits);
+}
+
+/* ---- (2) reference-named entry points over the current handle ---------------------------------------- */
+void igd_b200_use(igd_b200_t *h) { g_current = h; }
+igd_b200_t *igd_b200_current(void) { return g_current; }
+
+/* get_overlaps always returns 0: its counter is never incremented (src/igd_search.c:461,533) */
+int32_t get_overlaps(char *chrm, int32_t qs, int32_t qe, int64_t *hits)
+{
+    if (!g_current) return 0;
+    int32_t c = igd_b200_ctg_id(g_current, chrm);
+    igd_b200_count(g_current, 1, &c, &qs, &qe, 0, hits);
+    return 0;
+}
+
+/* get_overlaps_v returns the number of hits (src/igd_search.c:653,683,693).  Called directly it applies
+ * its own control flow and value >= v for ANY v (the v > 0 dispatch lives in igd_search, :1027,:1045). */
+int32_t get_overlaps_v(char *chrm, int32_t qs, int32_t qe, int32_t v, int64_t *hits)
+{
+    if (!g_current) return 0;
+    int32_t c = igd_b200_ctg_id(g_current, chrm);
+    int64_t r = count_mode(g_current, 1, &c, &qs, &qe, 1, v, hits);
+    return r < 0 ? 0 : (int32_t)r;
+}
+
+int64_t getOverlaps(char *qFile, int64_t *hits)
+{
+    if (!g_current) return 0;
+    search(g_current, qFile, 0, hits);
+    return 0;                                       /* sum of get_overlaps' return values */
+}
+
+int64_t getOverlaps_v(char *qFile, int64_t *hits, int32_t v)
+{
+    if (!g_current) return 0;
+    int64_t r = search_mode(g_current, qFile, 1, v, hits);
+    return r < 0 ? 0 : r;
+}
+
+int64_t getMap(uint32_t **hitmap) { return getMap_v(hitmap, 0); }
+
+int64_t getMap_v(uint32_t **hitmap, int32_t v)
+{
+    if (!g_current) return 0;
+    int32_t n = g_current->nfiles;
+    uint32_t *dense = malloc(sizeof(uint32_t) * (size_t)n * (size_t)n + 4);
+    for (int i = 0; i < n; i++) memcpy(dense + (size_t)i * n, hitmap[i], sizeof(uint32_t) * (size_t)n);
+    int64_t r = igd_b200_hitsmap(g_current, v, dense);
+    if (r >= 0)
+        for (int i = 0; i < n; i++) memcpy(hitmap[i], dense + (size_t)i * n, sizeof(uint32_t) * (size_t)n);
+    free(dense);
+    return r < 0 ? 0 : r;
+}
+
+int igd_b200_seqpare(igd_b200_t *h, const char *qFile, double *sm)
+{
+    (void)h; (void)qFile; (void)sm;
+    snprintf(g_err, sizeof g_err, "Seqpare (-s) is not implemented on the device yet");
+    return -1;
+}

@@ -1,0 +1,146 @@
+/* igd_b200 -- C-ABI of the B200-native IGD batch overlap search.
+ *
+ * Plain pointers and sizes only; no CUDA or torch types.  Two groups of entry points:
+ *
+ *  (1) a handle-based, batched interface (what a new binding should call), and
+ *  (2) the reference's own global-state entry points of src/igd_search.h, with the same names,
+ *      argument meaning, return values and (absence of) error reporting, implemented over (1).
+ *
+ * Every declaration cites the reference interface it replaces (paths under databio/IGD).
+ * All searches run on the GPU; there is no CPU fallback -- a call that cannot reach a CUDA device
+ * fails (NULL / negative return, message in igd_b200_last_error()).
+ */
+#ifndef IGD_B200_H
+#define IGD_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------
+ * (1) handle-based interface
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct igd_b200 igd_b200_t;          /* replaces iGD_t*, IGDr/src/igd_base.h:71-83 */
+
+/* open_iGD (IGDr/src/igd_base.h:97) + get_igdinfo/get_fileinfo (src/igd_base.c:269-323, 235-267):
+ * parses <db>.igd and <db>_index.tsv and uploads every tile into the HBM of CUDA device `device`
+ * (CSR of tile offsets + SoA start/end/idx/value).  NULL on failure. */
+igd_b200_t *igd_b200_open(const char *igd_path, int device);
+/* close_iGD (IGDr/src/igd_base.h:124) */
+void igd_b200_close(igd_b200_t *h);
+/* message of the last failure on this thread ("" if none) */
+const char *igd_b200_last_error(void);
+/* number of visible CUDA devices (<= 0: none) */
+int igd_b200_device_count(void);
+
+/* get_nFiles / get_nCtgs / get_nbp (IGDr/src/igd_search.c:357-393) and iGD_t fields */
+int32_t igd_b200_nfiles(const igd_b200_t *h);
+int32_t igd_b200_nctg(const igd_b200_t *h);
+int32_t igd_b200_nbp(const igd_b200_t *h);
+int32_t igd_b200_gtype(const igd_b200_t *h);
+int64_t igd_b200_ntiles(const igd_b200_t *h);
+int64_t igd_b200_nrecords(const igd_b200_t *h);
+int32_t igd_b200_ntile(const igd_b200_t *h, int32_t ctg);           /* iGD_t.nTile[ctg] */
+int32_t igd_b200_ncnt(const igd_b200_t *h, int32_t ctg, int32_t tile); /* iGD_t.nCnt[ctg][tile] */
+int32_t igd_b200_file_nr(const igd_b200_t *h, int32_t i);           /* info_t.nr   src/igd_base.h:54-58 */
+const char *igd_b200_file_name(const igd_b200_t *h, int32_t i);     /* info_t.fileName */
+const char *igd_b200_ctg_name(const igd_b200_t *h, int32_t ctg);    /* iGD_t.cName[ctg] */
+/* get_id (src/igd_base.c:325-331): contig index, -1 if absent */
+int32_t igd_b200_ctg_id(const igd_b200_t *h, const char *chrm);
+/* bytes of HBM held by the database image */
+int64_t igd_b200_device_bytes(const igd_b200_t *h);
+
+/* Batched count search -- the n-query array form of search_nr (IGDr/src/igd_search.c:340-355) with the
+ * semantics of get_overlaps (v <= 0; src/igd_search.c:454-534) or get_overlaps_v (v > 0; :623-694) per
+ * query.  hits[nFiles] is caller-allocated, caller-zeroed and INCREMENTED (src/igd_search.c:925,491).
+ * Returns the number of overlaps found in this call (>= 0) or a negative error code.
+ * (The reference's own return value -- 0 for plain, the count for -v -- is what group (2) returns.) */
+int64_t get_overlaps_n(igd_b200_t *h, int64_t n, const char *const *chrm, const int32_t *qs,
+                       const int32_t *qe, int32_t v, int64_t *hits);
+/* same, contig ids already resolved with igd_b200_ctg_id (-1 = unknown chrom: contributes nothing) */
+int64_t igd_b200_count(igd_b200_t *h, int64_t n, const int32_t *ctg, const int32_t *qs,
+                       const int32_t *qe, int32_t v, int64_t *hits);
+/* same, but every buffer is a DEVICE pointer on the handle's device and the work is enqueued on
+ * `stream` (a cudaStream_t, may be NULL).  d_hits is uint64[nFiles], incremented.  Returns 0 once the
+ * work is enqueued; the caller synchronises.  This is the entry point the multi-GPU driver uses, with an
+ * NCCL allreduce of d_hits behind it. */
+int igd_b200_count_device(igd_b200_t *h, int64_t n, const int32_t *d_ctg, const int32_t *d_qs,
+                          const int32_t *d_qe, int32_t v, uint64_t *d_hits, void *stream);
+
+/* -f: the overlaps themselves, in the reference's order (get_overlaps_f1, src/igd_search.c:537-620:
+ * per query, bin n1 from the last start < qe downwards, then later bins ascending).
+ * The arrays are malloc'ed by the library and released with igd_b200_hitlist_free. */
+typedef struct {
+    int64_t total;          /* number of overlaps */
+    int64_t n_queries;
+    int64_t *query_off;     /* [n_queries + 1] : overlaps of query q are [query_off[q], query_off[q+1]) */
+    int32_t *start;         /* [total] gdata_t.start */
+    int32_t *end;           /* [total] gdata_t.end */
+    int32_t *file;          /* [total] gdata_t.idx */
+} igd_b200_hitlist;
+int igd_b200_full(igd_b200_t *h, int64_t n, const int32_t *ctg, const int32_t *qs, const int32_t *qe,
+                  igd_b200_hitlist *out);
+void igd_b200_hitlist_free(igd_b200_hitlist *l);
+
+/* -m: getMap / getMap_v (src/igd_search.c:772-886) as one dense row-major uint32[nFiles*nFiles],
+ * incremented (wraps mod 2^32 like the reference).  v > 0 selects the strict `value > v` filter.
+ * Returns the number of pairs counted or a negative error code. */
+int64_t igd_b200_hitsmap(igd_b200_t *h, int32_t v, uint32_t *hitmap);
+
+/* Query ingest: the accepted lines of a BED(.gz) file by parse_bed's rule (src/igd_base.c:53-72: >= 3
+ * tab-separated fields, contig starts with "chr", shorter than 40 chars, end > 0), read like
+ * getOverlaps does (src/igd_search.c:696-719). */
+typedef struct {
+    int64_t n;
+    int32_t *name_id;       /* [n] index into names[] (first-appearance order) */
+    int32_t *qs, *qe;       /* [n] */
+    int32_t n_names;
+    char **names;
+} igd_b200_queries;
+igd_b200_queries *igd_b200_read_bed(const char *path);      /* NULL if the file cannot be opened */
+void igd_b200_queries_free(igd_b200_queries *q);
+/* contig id per query (-1 = not in the database) */
+void igd_b200_resolve(const igd_b200_t *h, const igd_b200_queries *q, int32_t *ctg_out);
+
+/* Whole-file search -- search_n of src_py/igd_py.pyx:42-44 / getOverlaps(iGD, qFile, hits)
+ * (src_py/igd_search.c:104-128): parse qFile, count (v <= 0) or count with the signal filter (v > 0).
+ * Returns the number of overlaps, or negative on error. */
+int64_t search(igd_b200_t *h, const char *qFile, int32_t v, int64_t *hits);
+/* -s: seqOverlaps (src/igd_search.c:355-451); sm[nFiles] is overwritten.  0 on success. */
+int igd_b200_seqpare(igd_b200_t *h, const char *qFile, double *sm);
+
+/* Multi-GPU planning: cost[i] = estimated scan bytes of query i (sum over its bins of
+ * 4*nCnt); used to cut a (ctg,start)-sorted query set into contiguous, cost-balanced shards. */
+int igd_b200_query_cost(const igd_b200_t *h, int64_t n, const int32_t *ctg, const int32_t *qs,
+                        const int32_t *qe, int64_t *cost);
+
+/* timing of the last igd_b200_count / get_overlaps_n call on this handle, milliseconds (CUDA events):
+ * t[0] H2D, t[1] kernels, t[2] D2H */
+void igd_b200_last_timing(const igd_b200_t *h, float t[3]);
+/* kernel launches issued by this handle since open (for bench.py's gpu_launches) */
+int64_t igd_b200_launch_count(const igd_b200_t *h);
+
+/* ------------------------------------------------------------------------------------------------
+ * (2) the reference's global-state entry points (src/igd_search.h), operating on the handle made
+ *     current with igd_b200_use() -- the counterpart of the reference's process globals
+ *     IGD / fP / gData (src/igd.c:14-19) that igd_search() sets up (src/igd_search.c:917-925,974).
+ * ---------------------------------------------------------------------------------------------- */
+void igd_b200_use(igd_b200_t *h);
+igd_b200_t *igd_b200_current(void);
+
+int32_t get_overlaps(char *chrm, int32_t qs, int32_t qe, int64_t *hits);              /* igd_search.h:23 */
+int32_t get_overlaps_v(char *chrm, int32_t qs, int32_t qe, int32_t v, int64_t *hits); /* igd_search.h:24 */
+int64_t getOverlaps(char *qFile, int64_t *hits);                                      /* igd_search.h:27 */
+int64_t getOverlaps_v(char *qFile, int64_t *hits, int32_t v);                         /* igd_search.h:28 */
+int64_t getMap(uint32_t **hitmap);                                                    /* igd_search.h:31 */
+int64_t getMap_v(uint32_t **hitmap, int32_t v);                                       /* igd_search.h:32 */
+int32_t get_overlaps_f1(char *chrm, int32_t qs, int32_t qe);                          /* igd_search.h:36 */
+int64_t getOverlaps_f1(char *qFile);                                                  /* igd_search.h:38 */
+void seqOverlaps(char *qFile, double *sm);                                            /* igd_search.h:20 */
+int igd_search(int argc, char **argv);                                                /* igd_search.h:41 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,92 @@
+"""GPU parity: the CUDA path (through the C-ABI) against the oracle on the same seeded inputs."""
+import os
+
+import numpy as np
+import pytest
+
+from igd_b200 import synth
+from tests.conftest import SMALL_NAMES, SMALL_SIZES, make_queries
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle
+    return oracle
+
+
+@pytest.fixture(scope="module")
+def api():
+    from igd_b200 import api
+    return api
+
+
+def _queries(kind):
+    if kind == "short":
+        return make_queries(101, 20000, ("lognormal", 6.0, 1.0))
+    if kind == "fixed1k":
+        return make_queries(102, 20000, ("fixed", 1000))
+    if kind == "long":
+        return make_queries(103, 3000, ("fixed", 150000))
+    raise KeyError(kind)
+
+
+@pytest.mark.parametrize("kind", ["short", "fixed1k", "long"])
+@pytest.mark.parametrize("v", [0, 1, 500, 1000])
+def test_count_dense(dense_db, O, api, kind, v):
+    q = _queries(kind)
+    odb = O.OracleDB(dense_db)
+    g = api.IGD(dense_db)
+    want, want_ret = odb.count(q.ctg, q.start, q.end, v)
+    got, got_n = g.count(q.ctg, q.start, q.end, v)
+    assert np.array_equal(got, want)
+    assert got_n == int(want.sum())
+    g.close()
+
+
+@pytest.mark.parametrize("v", [0, 500])
+def test_count_sparse_cfg1(sparse_db, O, api, v):
+    law = ("lognormal", 6.5, 1.2)
+    q = synth.gen_intervals(synth.seed_for(1, synth.QUERY_FILE_INDEX), 10000, law)
+    odb = O.OracleDB(sparse_db)
+    g = api.IGD(sparse_db)
+    want, _ = odb.count(q.ctg, q.start, q.end, v)
+    got, _ = g.count(q.ctg, q.start, q.end, v)
+    assert want.sum() > 0
+    assert np.array_equal(got, want)
+    g.close()
+
+
+def test_hits_accumulate(dense_db, O, api):
+    q = _queries("short")
+    odb = O.OracleDB(dense_db)
+    g = api.IGD(dense_db)
+    seed = np.arange(g.nfiles, dtype=np.int64) * 7 + 3
+    want, _ = odb.count(q.ctg, q.start, q.end, 0, hits=seed.copy())
+    got, _ = g.count(q.ctg, q.start, q.end, 0, hits=seed.copy())
+    got, _ = g.count(q.ctg[:0], q.start[:0], q.end[:0], 0, hits=got)     # empty batch is a no-op
+    assert np.array_equal(got, want)
+    g.close()
+
+
+@pytest.mark.parametrize("kind", ["short", "long"])
+def test_full_dense(dense_db, O, api, kind):
+    q = _queries(kind)
+    n = 2000 if kind == "long" else 20000
+    odb = O.OracleDB(dense_db)
+    g = api.IGD(dense_db)
+    per, oq, os_, oe, of = odb.full(q.ctg[:n], q.start[:n], q.end[:n])
+    qoff, s, e, f = g.full(q.ctg[:n], q.start[:n], q.end[:n])
+    assert np.array_equal(np.diff(qoff), per)
+    # exact reference order, not just the same multiset
+    assert np.array_equal(s, os_) and np.array_equal(e, oe) and np.array_equal(f, of)
+    g.close()
+
+
+@pytest.mark.parametrize("v", [0, 500])
+def test_hitsmap_dense(dense_db, O, api, v):
+    odb = O.OracleDB(dense_db)
+    g = api.IGD(dense_db)
+    assert np.array_equal(g.hitsmap(v), odb.hitsmap(v))
+    g.close()
