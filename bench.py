@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""Benchmark of the IGD batch overlap search hot path (count mode) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2]
+
+One "step" = one pass of the hot path over the whole query batch of the workload (BASELINE.json
+configs[1] by default: 1,905 files x 50k intervals, 1M x 1 kb queries, count mode).  Prints ONE JSON line.
+
+* value  : query intervals/s, whole job, queries already resident in HBM (CUDA events, max over ranks)
+* e2e    : the same through the C-ABI call with HOST (pinned) buffers: H2D + kernels + D2H inside
+* roofline : the search kernel's algorithmic bytes (from the oracle's instrumented
+             restatement) / its CUDA-event duration, against MEASURED_PEAKS.json's HBM copy bandwidth
+* cpu_baseline : the oracle port timed on one host core on the same workload (reported, not a target)
+
+--impl reference times the unmodified reference binary (oracle/_ref/igd, all host cores, one process per
+core over line-splits of the query file) on the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from igd_b200 import synth, workloads  # noqa: E402
+
+METRIC = "query_intervals_per_s"
+UNIT = "queries/s"
+
+
+def env_int(k, d):
+    return int(os.environ.get(k, d))
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.max = index, False, [], set(), None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                     "hw_power_brake": 0x80, "sw_power_cap": 0x4}
+            while not self.stop_flag:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+                time.sleep(0.002)
+        except Exception as e:  # pragma: no cover
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max,
+                "samples": len(self.sm), "reasons": sorted(self.reasons)}
+
+
+def workload_setup(args, rank, world, barrier):
+    """DB on disk (built once by rank 0) + the query set mapped to database contig ids."""
+    workdir = args.workdir
+    if rank == 0:
+        t0 = time.time()
+        path = workloads.build_db(args.workload, workdir)
+        build_s = time.time() - t0
+    barrier()
+    path = os.path.join(workdir, args.workload + ".igd")
+    q = workloads.queries(args.workload, args.queries)
+    return path, q, (build_s if rank == 0 else 0.0)
+
+
+def oracle_leg(path, ctg, qs, qe, sample, cache_file):
+    """cpu_baseline: the oracle port on one host core; also the algorithmic-byte counters."""
+    from oracle import oracle as O
+    n = len(ctg)
+    if os.path.exists(cache_file):
+        c = json.load(open(cache_file))
+        if c.get("n") == n and c.get("sample") == sample:
+            return c
+    odb = O.OracleDB(path)
+    m = min(n, sample)
+    # a strided sample keeps the (ctg, start) distribution of the whole set
+    sel = np.arange(m) * (n // m) if m < n else np.arange(n)
+    t0 = time.perf_counter()
+    hits, _, st = odb.count(ctg[sel], qs[sel], qe[sel], 0, stats=True)
+    dt = time.perf_counter() - t0
+    scale = n / m
+    out = {"n": n, "sample": sample, "sample_n": int(m), "seconds": dt, "qps": m / dt,
+           "stats": st, "scale": scale, "hits_sample": hits.tolist(),
+           "bytes_total": st["bytes"] * scale, "hits_total": st["hits"] * scale,
+           "tile_bytes_sample": st["tile_bytes"]}
+    odb.close()
+    with open(cache_file, "w") as f:
+        json.dump(out, f)
+    return out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from igd_b200 import api
+
+    world = env_int("WORLD_SIZE", 1)
+    rank = env_int("RANK", 0)
+    local = env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the igd_b200 search path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    barrier = (lambda: dist.barrier()) if world > 1 else (lambda: None)
+    dev = torch.device("cuda", local)
+
+    path, q, build_s = workload_setup(args, rank, world, barrier)
+    t0 = time.time()
+    igd = api.IGD(path, device=local)
+    open_s = time.time() - t0
+    ctg_all = igd.resolve_names(synth.HG38_NAMES)[q.ctg].astype(np.int32)
+    qs_all, qe_all = q.start, q.end
+    n_total = len(ctg_all)
+
+    # multi-GPU: DB replicated, (ctg,start)-sorted queries cut into cost-balanced contiguous shards
+    if world > 1:
+        ctg_s, qs_s, qe_s, bounds = workloads.sort_and_shard(igd, ctg_all, qs_all, qe_all, world)
+        a, b = bounds[rank], bounds[rank + 1]
+        ctg_l, qs_l, qe_l = ctg_s[a:b], qs_s[a:b], qe_s[a:b]
+    else:
+        ctg_l, qs_l, qe_l = ctg_all, qs_all, qe_all
+    n_local = len(ctg_l)
+
+    d_ctg = torch.from_numpy(np.ascontiguousarray(ctg_l)).to(dev)
+    d_qs = torch.from_numpy(np.ascontiguousarray(qs_l)).to(dev)
+    d_qe = torch.from_numpy(np.ascontiguousarray(qe_l)).to(dev)
+    d_hits = torch.zeros(igd.nfiles, dtype=torch.int64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    # a real (non-default) stream: the library enqueues its kernels on the stream it is handed, and the
+    # CUDA events / NCCL collective below are recorded on the same one
+    side = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(side)
+    stream = side.cuda_stream
+
+    def step_device():
+        d_hits.zero_()
+        igd.count_device(n_local, d_ctg.data_ptr(), d_qs.data_ptr(), d_qe.data_ptr(), 0, d_hits.data_ptr(), stream)
+        if world > 1:
+            dist.all_reduce(d_hits)
+
+    # pinned host copies for the end-to-end path
+    h_ctg = torch.from_numpy(np.ascontiguousarray(ctg_l)).pin_memory()
+    h_qs = torch.from_numpy(np.ascontiguousarray(qs_l)).pin_memory()
+    h_qe = torch.from_numpy(np.ascontiguousarray(qe_l)).pin_memory()
+    h_hits = torch.zeros(igd.nfiles, dtype=torch.int64).pin_memory()
+    e_ctg, e_qs, e_qe = (torch.empty_like(d_ctg) for _ in range(3))
+
+    def step_e2e():
+        if world == 1:
+            # the reference-facing C-ABI call: host buffers in, hits[] out (igd_b200_count)
+            hits = np.zeros(igd.nfiles, np.int64)
+            igd.count_ptr(n_local, h_ctg.data_ptr(), h_qs.data_ptr(), h_qe.data_ptr(), 0, hits)
+            return hits
+        e_ctg.copy_(h_ctg, non_blocking=True)
+        e_qs.copy_(h_qs, non_blocking=True)
+        e_qe.copy_(h_qe, non_blocking=True)
+        d_hits.zero_()
+        igd.count_device(n_local, e_ctg.data_ptr(), e_qs.data_ptr(), e_qe.data_ptr(), 0, d_hits.data_ptr(), stream)
+        dist.all_reduce(d_hits)
+        h_hits.copy_(d_hits, non_blocking=True)
+        torch.cuda.synchronize()
+        return h_hits.numpy()
+
+    # ---- warm-up ---------------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        flush.fill_(1)
+        step_device()
+    torch.cuda.synchronize()
+    hits_dev = d_hits.cpu().numpy().copy()
+
+    # ---- timed: device-resident inputs -----------------------------------------------------------
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = igd.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kernel_ms = []
+    barrier()
+    torch.cuda.synchronize()
+    for i in range(args.steps):
+        flush.fill_(i & 0xff)               # evict the previous step's tiles from L2 (not timed)
+        ev[i][0].record()
+        step_device()
+        ev[i][1].record()
+        torch.cuda.synchronize()
+        kernel_ms.append(igd.last_search_kernel_ms())
+    barrier()
+    torch.cuda.synchronize()
+    launches = igd.launch_count() - launches0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(step_ms))
+
+    # ---- timed: end to end from host buffers --------------------------------------------------------
+    for _ in range(3):
+        hits_e2e = step_e2e()
+    barrier()
+    torch.cuda.synchronize()
+    e2e_s = 0.0
+    for i in range(args.steps):
+        flush.fill_(i & 0xff)
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        hits_e2e = step_e2e()
+        e2e_s += time.perf_counter() - t0
+    sampler.stop_flag = True
+    sampler.join()
+
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_s, float(np.mean(kernel_ms))], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_s, kmean = (float(x) for x in t.cpu())
+        ln = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(ln)
+        launches = int(ln.item())
+    else:
+        kmean = float(np.mean(kernel_ms))
+    assert np.array_equal(np.asarray(hits_e2e), hits_dev), "e2e and device-resident paths disagree"
+
+    if rank == 0:
+        ms_per_step = total_ms / args.steps
+        overlaps = int(hits_dev.sum())
+        peak, peak_src = peaks()
+        cache = os.path.join(args.workdir, f"{args.workload}.oracle_{n_total}.json")
+        orc = oracle_leg(path, ctg_all, qs_all, qe_all, args.cpu_sample, cache)
+        parity = None
+        if orc["sample_n"] == n_total:
+            parity = bool(np.array_equal(np.array(orc["hits_sample"], np.int64), hits_dev))
+        alg_bytes = orc["bytes_total"] / world          # per launch (each rank launches on its shard)
+        achieved = alg_bytes / (kmean * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(args.workload)
+        line = {
+            "metric": METRIC, "value": n_total / (ms_per_step * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32",
+            "data": "synthetic",
+            "overlaps_per_s": overlaps / (ms_per_step * 1e-3), "overlaps_per_step": overlaps,
+            "config": {"workload": f"{args.workload}: {workloads.CONFIGS[args.workload]['n_files']} files x "
+                                   f"{workloads.CONFIGS[args.workload]['per_file']} intervals (hg38, -b 14), "
+                                   f"{n_total} queries, count mode",
+                       "n_records": int(igd.nrecords), "n_tiles": int(igd.ntiles), "n_queries": n_total,
+                       "db_hbm_bytes": int(igd.device_bytes()),
+                       "l2": "256 MiB flush write between steps (untimed); DB image > 126 MB L2",
+                       "parallelism": f"db replicated, queries sharded x{world} by scan-byte prefix sum"
+                       if world > 1 else "single GPU", "db_build_s": round(build_s, 1), "db_open_s": round(open_s, 2)},
+            "e2e": {"value": n_total / (e2e_s / args.steps), "unit": UNIT, "ms_per_step": e2e_s / args.steps * 1e3,
+                    "h2d_bytes_per_step": 12 * n_total, "d2h_bytes_per_step": 8 * igd.nfiles * world,
+                    "api": "igd_b200_count (C-ABI, host buffers)" if world == 1 else
+                           "pinned H2D + igd_b200_count_device + NCCL allreduce + D2H"},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "k_search (count)", "kernel_ms": kmean,
+                         "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                         "bytes_definition": "SURVEY.md 8(d) reference scan range, oracle-instrumented"
+                                             + ("" if orc["sample_n"] == n_total else f" (scaled from a {orc['sample_n']}-query sample)")},
+            "cpu_baseline": {"value": orc["qps"], "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": f"{orc['sample_n']} of {n_total} queries of the same workload, oracle/igd_oracle.c, {orc['seconds']:.1f} s"},
+            "parity_vs_oracle": parity,
+        }
+        print(json.dumps(line), flush=True)
+    igd.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    """The reference's own CPU implementation on the box's host cores (rank 0 only)."""
+    if env_int("RANK", 0) != 0:
+        return
+    from oracle import oracle as O
+    path = workloads.build_db(args.workload, args.workdir)
+    q = workloads.queries(args.workload, args.queries)
+    n_total = len(q)
+    cores = os.cpu_count() or 1
+    n = min(n_total, args.ref_sample)
+    qdir = os.path.join(args.workdir, f"{args.workload}_refq_{n}_{cores}")
+    if not os.path.isdir(qdir):
+        os.makedirs(qdir)
+        sel = np.arange(n) * (n_total // n)
+        for c in range(cores):
+            part = sel[c::cores]
+            synth.write_bed(os.path.join(qdir, f"q{c:03d}.bed"),
+                            synth.Intervals(q.ctg[part], q.start[part], q.end[part], q.value[part]))
+    kind = "reference" if O.have_ref() else "port"
+
+    def one_step():
+        t0 = time.perf_counter()
+        if kind == "reference":
+            procs = [subprocess.Popen([O.REF_BIN, "search", path, "-q", os.path.join(qdir, f"q{c:03d}.bed")],
+                                      stdout=subprocess.DEVNULL) for c in range(cores)]
+            for p in procs:
+                p.wait()
+        else:
+            code = ("import sys; sys.path.insert(0, %r); from oracle import oracle as O; "
+                    "db=O.OracleDB(sys.argv[1]); q=O.Queries(sys.argv[2]); db.count(db.resolve(q), q.qs, q.qe)" % ROOT)
+            procs = [subprocess.Popen([sys.executable, "-c", code, path, os.path.join(qdir, f"q{c:03d}.bed")])
+                     for c in range(cores)]
+            for p in procs:
+                p.wait()
+        return time.perf_counter() - t0
+
+    for _ in range(args.warmup):
+        one_step()
+    total = sum(one_step() for _ in range(args.steps))
+    sec = total / args.steps
+    val = n / sec
+    sample = f"{n} of {n_total} queries per step, split over {cores} processes of oracle/_ref/igd search -q" \
+        if kind == "reference" else f"{n} of {n_total} queries per step, {cores} processes of the oracle port"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {workloads.CONFIGS[args.workload]['n_files']} files x "
+                                   f"{workloads.CONFIGS[args.workload]['per_file']} intervals (hg38, -b 14), "
+                                   f"{n_total} queries, count mode", "n_queries": n_total},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(workloads.CONFIGS))
+    ap.add_argument("--queries", type=int, default=None, help="override the number of queries")
+    ap.add_argument("--workdir", default=os.environ.get("IGD_B200_WORKDIR", "/tmp/igd_b200_bench"))
+    ap.add_argument("--cpu-sample", type=int, default=1_000_000, help="queries in the cpu_baseline sample")
+    ap.add_argument("--ref-sample", type=int, default=1_000_000, help="queries per step of --impl reference")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

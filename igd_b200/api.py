@@ -94,6 +94,8 @@ def load_library():
     L.igd_b200_seqpare.argtypes = [vp, C.c_char_p, _f64p]
     L.igd_b200_query_cost.restype = C.c_int
     L.igd_b200_query_cost.argtypes = [vp, C.c_int64, _i32p, _i32p, _i32p, _i64p]
+    L.igd_b200_last_search_kernel_ms.restype = C.c_float
+    L.igd_b200_last_search_kernel_ms.argtypes = [vp]
     L.igd_b200_last_timing.argtypes = [vp, C.POINTER(C.c_float * 3)]
     L.igd_b200_use.argtypes = [vp]
     L.igd_b200_current.restype = vp
@@ -201,6 +203,9 @@ class IGD:
 
     def launch_count(self) -> int:
         return self._L.igd_b200_launch_count(self._need())
+
+    def last_search_kernel_ms(self) -> float:
+        return float(self._L.igd_b200_last_search_kernel_ms(self._need()))
 
     def last_timing(self):
         t = (C.c_float * 3)()

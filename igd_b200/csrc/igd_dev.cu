@@ -452,6 +452,8 @@ struct igdb_dev {
     int64_t launches = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t kev[2] = {nullptr, nullptr};               // around the last count-mode search kernel
+    bool kev_valid = false;
     // staging / scratch (grown on demand)
     void *pinned = nullptr;
     size_t pinned_cap = 0;
@@ -548,6 +550,7 @@ int launch_search(igdb_dev *d, const SearchArgs &a, cudaStream_t st)
     const bool smem = OUT == OUT_HIST && hist_bytes <= 200 * 1024;
     const size_t shm = smem ? hist_bytes : 0;
     int per_sm = 0;
+    if (OUT == OUT_HIST) CK(cudaEventRecord(d->kev[0], st));
     if (smem) {
         auto kern = k_search<V, OUT, true>;
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
@@ -559,6 +562,10 @@ int launch_search(igdb_dev *d, const SearchArgs &a, cudaStream_t st)
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0));
         per_sm = std::max(per_sm, 1);
         kern<<<d->sm_count * per_sm, threads, 0, st>>>(a);
+    }
+    if (OUT == OUT_HIST) {
+        CK(cudaEventRecord(d->kev[1], st));
+        d->kev_valid = true;
     }
     d->launches += 1;
     CK(cudaGetLastError());
@@ -633,6 +640,8 @@ void igdb_dev_destroy(igdb_dev *d)
     if (d->h_scalar) cudaFreeHost(d->h_scalar);
     for (auto &e : d->ev)
         if (e) cudaEventDestroy(e);
+    for (auto &e : d->kev)
+        if (e) cudaEventDestroy(e);
     if (d->stream) cudaStreamDestroy(d->stream);
     delete d;
 }
@@ -645,6 +654,7 @@ static int create_impl(igdb_dev *d, const int32_t *ntile, const int32_t *ncnt)
     d->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
     for (auto &e : d->ev) CK(cudaEventCreate(&e));
+    for (auto &e : d->kev) CK(cudaEventCreate(&e));
     CK(cudaMallocHost((void **)&d->h_scalar, 64));
 
     std::vector<int32_t> tbase(d->nctg + 1, 0);
@@ -745,6 +755,15 @@ int igdb_dev_finalize(igdb_dev *d)
         d->d_stage = nullptr, d->d_stage_cap = 0;
     }
     return 0;
+}
+
+float igdb_dev_last_search_ms(igdb_dev *d)
+{
+    float ms = -1.f;
+    if (!d->kev_valid) return ms;
+    if (cudaEventSynchronize(d->kev[1]) != cudaSuccess) return ms;
+    if (cudaEventElapsedTime(&ms, d->kev[0], d->kev[1]) != cudaSuccess) return -1.f;
+    return ms;
 }
 
 int64_t igdb_dev_bytes(const igdb_dev *d) { return d->bytes; }

@@ -25,6 +25,8 @@ int igdb_dev_finalize(igdb_dev *d);
 void igdb_dev_destroy(igdb_dev *d);
 int64_t igdb_dev_bytes(const igdb_dev *d);
 int64_t igdb_dev_launches(const igdb_dev *d);
+/* device time of the last count-mode search kernel (CUDA events on its stream); < 0 if none */
+float igdb_dev_last_search_ms(igdb_dev *d);
 void *igdb_dev_pinned(igdb_dev *d, size_t bytes);   /* reusable pinned staging buffer (upload) */
 
 /* count (mode_v = 0: get_overlaps control flow) / -v (mode_v = 1: get_overlaps_v control flow and the

@@ -120,9 +120,69 @@ def write_bed_files(outdir: str, config: int, n_files: int, n_per_file: int, law
 # direct .igd writer
 # ---------------------------------------------------------------------------------------------
 
+def _expand_sort(crank, start, end, nbp, m, use_cuda=None):
+    """Replicate every interval into each bin it touches (igd_add, igd_base.c:162-172) and order the
+    copies by (contig rank, bin, start), stable in (file, line) order.  Returns (source index of every
+    record in file order, nCnt per tile, nTile per contig, total tiles).  The heavy repeat/sort runs on
+    the GPU through torch when one is present (input generation only -- not the search path)."""
+    if use_cuda is None:
+        try:
+            import torch
+            use_cuda = torch.cuda.is_available() and start.shape[0] > 2_000_000
+        except Exception:
+            use_cuda = False
+    if use_cuda:
+        import torch
+        dev = torch.device("cuda")
+        t_rank = torch.from_numpy(np.ascontiguousarray(crank)).to(dev)
+        t_s = torch.from_numpy(start).to(dev).long()
+        t_e = torch.from_numpy(end).to(dev).long()
+        n1 = t_s // nbp
+        n2 = (t_e - 1) // nbp
+        ntile = torch.zeros(m, dtype=torch.int64, device=dev)
+        ntile.scatter_reduce_(0, t_rank, n2 + 1, reduce="amax", include_self=True)
+        tile_base = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(ntile, 0)])
+        span = n2 - n1 + 1
+        src = torch.repeat_interleave(torch.arange(t_s.shape[0], device=dev), span)
+        first = torch.cumsum(span, 0) - span
+        within = torch.arange(src.shape[0], device=dev) - first[src]
+        gtile = tile_base[t_rank[src]] + n1[src] + within
+        del within, first
+        key = (gtile << 32) | t_s[src]
+        del gtile
+        key, order = torch.sort(key, stable=True)
+        src = src[order]
+        del order
+        total_tiles = int(tile_base[-1].item())
+        ncnt = torch.bincount(key >> 32, minlength=total_tiles).to(torch.int32)
+        out = (src.cpu().numpy(), ncnt.cpu().numpy(), ntile.to(torch.int32).cpu().numpy(), total_tiles)
+        del key, src
+        torch.cuda.empty_cache()
+        return out
+    n1 = start.astype(np.int64) // nbp
+    n2 = (end.astype(np.int64) - 1) // nbp
+    ntile = np.zeros(m, dtype=np.int32)
+    np.maximum.at(ntile, crank, (n2 + 1).astype(np.int32))
+    tile_base = np.concatenate([[0], np.cumsum(ntile.astype(np.int64))])
+    span = n2 - n1 + 1
+    rep = np.repeat(np.arange(len(start), dtype=np.int64), span)
+    within = np.arange(rep.shape[0], dtype=np.int64) - np.repeat(np.cumsum(span) - span, span)
+    gtile = tile_base[crank[rep]] + n1[rep] + within
+    del within
+    key = (gtile << 32) | start[rep].astype(np.int64)
+    order = np.argsort(key, kind="stable")
+    del key
+    rep = rep[order]
+    gtile = gtile[order]
+    total_tiles = int(tile_base[-1])
+    ncnt = np.bincount(gtile, minlength=total_tiles).astype(np.int32)
+    return rep, ncnt, ntile, total_tiles
+
+
 def write_igd_direct(stem: str, files: list[Intervals] | None = None, *, nbp: int = 16384,
                      names=HG38_NAMES, file_names: list[str] | None = None,
-                     gen=None, n_files: int | None = None, ctg_order: list[int] | None = None) -> dict:
+                     gen=None, n_files: int | None = None, ctg_order: list[int] | None = None,
+                     use_cuda: bool | None = None) -> dict:
     """Write ``stem + '.igd'`` and ``stem + '_index.tsv'``.
 
     ``files`` is a list of per-file interval bags, or pass ``gen(i) -> Intervals`` with ``n_files``.
@@ -159,28 +219,7 @@ def write_igd_direct(stem: str, files: list[Intervals] | None = None, *, nbp: in
     rank[np.array(ctg_order, dtype=np.int64)] = np.arange(len(ctg_order))
     m = len(ctg_order)
 
-    n1 = start // nbp
-    n2 = (end - 1) // nbp
-    ntile = np.zeros(m, dtype=np.int32)
-    np.maximum.at(ntile, rank[ctg], (n2 + 1).astype(np.int32))
-    tile_base = np.concatenate([[0], np.cumsum(ntile.astype(np.int64))])
-
-    # replicate each interval into every bin it touches (igd_base.c:162-172)
-    span = (n2 - n1 + 1).astype(np.int64)
-    rep = np.repeat(np.arange(len(start), dtype=np.int64), span)
-    within = np.arange(rep.shape[0], dtype=np.int64) - np.repeat(np.cumsum(span) - span, span)
-    gtile = tile_base[rank[ctg[rep]]] + n1[rep] + within
-    del within
-    # sort by (global tile, start); stable so equal starts keep (file, line) order
-    key = (gtile << 32) | start[rep].astype(np.int64)
-    order = np.argsort(key, kind="stable")
-    del key
-    rep = rep[order]
-    gtile = gtile[order]
-    del order
-    total_tiles = int(tile_base[-1])
-    ncnt = np.bincount(gtile, minlength=total_tiles).astype(np.int32)
-    del gtile
+    rep, ncnt, ntile, total_tiles = _expand_sort(rank[ctg], start, end, nbp, m, use_cuda)
 
     rec = np.empty((rep.shape[0], 4), dtype=np.int32)   # gdata_t {idx,start,end,value} igd_base.h:41-46
     rec[:, 0] = fidx[rep]

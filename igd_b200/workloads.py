@@ -1,0 +1,79 @@
+"""BASELINE.json's benchmark configurations as synthetic inputs.
+
+Host-side setup only: builds (and caches under a work directory) the ``.igd`` database of a named
+configuration with :func:`igd_b200.synth.write_igd_direct` and generates its query set.
+"""
+from __future__ import annotations
+
+import json
+import os
+from concurrent.futures import ProcessPoolExecutor
+
+import numpy as np
+
+from . import synth
+
+CONFIGS = {
+    # 10 files x 10k; the reference's own CPU-runnable case
+    "cfg1": dict(config=1, n_files=10, per_file=10_000, db_law=("lognormal", 6.5, 1.2),
+                 n_queries=10_000, q_law=("lognormal", 6.5, 1.2)),
+    # Roadmap-scale: 1,905 files x 50k (~1e8 intervals), 1M x 1 kb queries, count mode, 1 GPU
+    "cfg2": dict(config=2, n_files=1905, per_file=50_000, db_law=("lognormal", 6.0, 1.0),
+                 n_queries=1_000_000, q_law=("fixed", 1000)),
+    # 1e9 intervals (10k files), 10M queries, query-sharded over 1/2/4/8 GPUs
+    "cfg3": dict(config=3, n_files=10_000, per_file=100_000, db_law=("lognormal", 6.0, 1.0),
+                 n_queries=10_000_000, q_law=("fixed", 1000)),
+    # a 1/10 cut of cfg2 for smoke runs and CPU-side tests
+    "mini": dict(config=2, n_files=200, per_file=50_000, db_law=("lognormal", 6.0, 1.0),
+                 n_queries=100_000, q_law=("fixed", 1000)),
+}
+
+
+def _gen_file(args):
+    config, i, per_file, law = args
+    return synth.gen_intervals(synth.seed_for(config, i), per_file, law)
+
+
+def build_db(name: str, workdir: str, procs: int | None = None) -> str:
+    """Create (once) ``<workdir>/<name>.igd`` + ``_index.tsv``; returns the .igd path."""
+    cfg = CONFIGS[name]
+    os.makedirs(workdir, exist_ok=True)
+    stem = os.path.join(workdir, name)
+    marker = stem + ".json"
+    want = json.dumps({k: cfg[k] for k in ("config", "n_files", "per_file", "db_law")}, sort_keys=True)
+    if os.path.exists(marker) and os.path.exists(stem + ".igd") and open(marker).read() == want:
+        return stem + ".igd"
+    jobs = [(cfg["config"], i, cfg["per_file"], cfg["db_law"]) for i in range(cfg["n_files"])]
+    procs = procs or min(os.cpu_count() or 1, 16)
+    if procs > 1 and len(jobs) >= 64:
+        with ProcessPoolExecutor(procs) as ex:
+            files = list(ex.map(_gen_file, jobs, chunksize=max(1, len(jobs) // (procs * 4))))
+    else:
+        files = [_gen_file(j) for j in jobs]
+    stats = synth.write_igd_direct(stem, files)
+    with open(stem + ".stats.json", "w") as f:
+        json.dump(stats, f)
+    with open(marker, "w") as f:
+        f.write(want)
+    return stem + ".igd"
+
+
+def queries(name: str, n: int | None = None) -> synth.Intervals:
+    cfg = CONFIGS[name]
+    return synth.gen_intervals(synth.seed_for(cfg["config"], synth.QUERY_FILE_INDEX),
+                               n or cfg["n_queries"], cfg["q_law"])
+
+
+def sort_and_shard(igd, ctg: np.ndarray, qs: np.ndarray, qe: np.ndarray, n_parts: int):
+    """Sort queries by (contig id, start) and cut them into ``n_parts`` contiguous ranges balanced by the
+    prefix sum of estimated per-query scan bytes (igd_b200_query_cost).  Returns sorted arrays + bounds."""
+    order = np.lexsort((qs, ctg))
+    ctg, qs, qe = ctg[order], qs[order], qe[order]
+    cost = igd.query_cost(ctg, qs, qe)
+    cum = np.cumsum(cost)
+    total = int(cum[-1]) if len(cum) else 0
+    bounds = [0]
+    for p in range(1, n_parts):
+        bounds.append(int(np.searchsorted(cum, total * p / n_parts)))
+    bounds.append(len(ctg))
+    return ctg, qs, qe, bounds

@@ -118,6 +118,9 @@ int igd_b200_query_cost(const igd_b200_t *h, int64_t n, const int32_t *ctg, cons
 /* timing of the last igd_b200_count / get_overlaps_n call on this handle, milliseconds (CUDA events):
  * t[0] H2D, t[1] kernels, t[2] D2H */
 void igd_b200_last_timing(const igd_b200_t *h, float t[3]);
+/* device time (ms, CUDA events on the launching stream) of the search kernel of the last count call;
+ * blocks until that kernel has finished; < 0 if there was none */
+float igd_b200_last_search_kernel_ms(igd_b200_t *h);
 /* kernel launches issued by this handle since open (for bench.py's gpu_launches) */
 int64_t igd_b200_launch_count(const igd_b200_t *h);
 
