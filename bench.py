@@ -164,6 +164,7 @@ def run_ours(args):
     def step_device():
         d_hits.zero_()
         igd.count_device(n_local, d_ctg.data_ptr(), d_qs.data_ptr(), d_qe.data_ptr(), 0, d_hits.data_ptr(), stream)
+        igd.count_device_finish()
         if world > 1:
             dist.all_reduce(d_hits)
 
@@ -185,6 +186,7 @@ def run_ours(args):
         e_qe.copy_(h_qe, non_blocking=True)
         d_hits.zero_()
         igd.count_device(n_local, e_ctg.data_ptr(), e_qs.data_ptr(), e_qe.data_ptr(), 0, d_hits.data_ptr(), stream)
+        igd.count_device_finish()
         dist.all_reduce(d_hits)
         h_hits.copy_(d_hits, non_blocking=True)
         torch.cuda.synchronize()

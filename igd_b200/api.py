@@ -79,6 +79,8 @@ def load_library():
     L.igd_b200_count.argtypes = [vp, C.c_int64, vp, vp, vp, C.c_int32, _i64p]
     L.igd_b200_count_device.restype = C.c_int
     L.igd_b200_count_device.argtypes = [vp, C.c_int64, vp, vp, vp, C.c_int32, vp, vp]
+    L.igd_b200_count_device_finish.restype = C.c_int
+    L.igd_b200_count_device_finish.argtypes = [vp]
     L.igd_b200_full.restype = C.c_int
     L.igd_b200_full.argtypes = [vp, C.c_int64, _i32p, _i32p, _i32p, C.POINTER(_HitList)]
     L.igd_b200_hitlist_free.argtypes = [C.POINTER(_HitList)]
@@ -267,8 +269,13 @@ class IGD:
         return hits, int(r)
 
     def count_device(self, n: int, d_ctg: int, d_qs: int, d_qe: int, v: int, d_hits: int, stream: int = 0) -> None:
-        """Device-pointer form: enqueue on a CUDA stream; d_hits is uint64[nfiles], incremented."""
+        """Device-pointer form: enqueue on a CUDA stream; d_hits is uint64[nfiles], incremented.
+        Call :meth:`count_device_finish` before consuming d_hits."""
         if self._L.igd_b200_count_device(self._need(), n, d_ctg, d_qs, d_qe, int(v), d_hits, stream):
+            raise IGDError(last_error())
+
+    def count_device_finish(self) -> None:
+        if self._L.igd_b200_count_device_finish(self._need()):
             raise IGDError(last_error())
 
     def query_cost(self, ctg, qs, qe) -> np.ndarray:

@@ -9,13 +9,22 @@
 //                              src/igd_search.c:510-511 is a per-tile constant; computed once here)
 //                       s0   : start of the first record              (the `qe > gData[0].start` gate, :477)
 //   start/end/idx/value[P]  SoA int32 copies of gdata_t's fields (src/igd_base.h:41-46), tile-major in
-//                       the file's order (each tile sorted by start).  Pad records: start=0x7f7f7f7f,
-//                       end=0x80808080 (never overlap anything).
+//                       the file's order (each tile sorted by start).  Pad records: start=INT_MAX,
+//                       end=INT_MIN (overlap no query).
 //   tbase[nctg+1]     global tile index of each contig's tile 0.
 //
 // Query batches are turned into (query, tile) SEGMENTS -- one per non-empty, non-gated tile the reference
 // would visit for that query, first-bin-empty quirk included -- counting-sorted by tile on the device, so
-// that concurrently running warps work on neighbouring tiles whatever the order of the input.
+// that the work is organised by tile whatever the order of the input.
+//
+// Count mode (-q, -v) is TILE-CENTRIC and RECORD-STATIONARY: a warp task ("item") is 128 consecutive
+// records of one tile against up to 256 of the tile's segments.  Every lane keeps 4 records in registers
+// (one 128-bit load each of start/end/idx[/value] -- the tile is read from HBM once however many queries
+// hit it), the segments are streamed through the warp 32 at a time, pruned against the warp's
+// [min start, max end] window with one ballot, and broadcast with shuffles; a lane adds the number of
+// segments overlapping each of its records and issues ONE shared-memory atomic per record with a non-zero
+// count (hits[idx] += count), not one per overlap.  -f keeps the query-centric warp-per-segment kernel
+// because it needs the reference's per-query output order.
 #include "igd_dev.h"
 
 #include <cuda_runtime.h>
@@ -83,6 +92,12 @@ __global__ void k_transpose(const int4 *__restrict__ aos, int64_t rec0, int64_t 
     int4 r = __ldg(&aos[i]);
     int64_t dst = (int64_t)tiles[lo].off4 * 4 + (g - __ldg(&toff[lo]));
     idx[dst] = r.x, start[dst] = r.y, end[dst] = r.z, value[dst] = r.w;
+}
+
+__global__ void k_fill(int32_t *__restrict__ p, int64_t n, int32_t v)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = v;
 }
 
 // per tile: ts = #records with start < bd (bd arrives in .ts), s0 = first start
@@ -166,6 +181,22 @@ __global__ void k_seg_scatter(DbView db, int64_t n, const int32_t *__restrict__ 
 // ------------------------------------------------------------------------------------------------
 constexpr int SCAN_T = 512, SCAN_I = 8, SCAN_B = SCAN_T * SCAN_I;
 
+// two running sums scanned together: segments and work items per tile
+struct Plan {
+    unsigned long long segs, items;
+};
+__device__ __forceinline__ Plan operator+(Plan a, Plan b) { return Plan{a.segs + b.segs, a.items + b.items}; }
+__device__ __forceinline__ Plan operator-(Plan a, Plan b) { return Plan{a.segs - b.segs, a.items - b.items}; }
+__device__ __forceinline__ Plan &operator+=(Plan &a, Plan b) { a = a + b; return a; }
+
+template <class T>
+__device__ __forceinline__ T shfl_up(T v, int d) { return __shfl_up_sync(FULL, v, d); }
+template <>
+__device__ __forceinline__ Plan shfl_up<Plan>(Plan v, int d)
+{
+    return Plan{__shfl_up_sync(FULL, v.segs, d), __shfl_up_sync(FULL, v.items, d)};
+}
+
 template <class Tout>
 __device__ __forceinline__ Tout block_exclusive(Tout x, Tout *total)
 {
@@ -175,16 +206,16 @@ __device__ __forceinline__ Tout block_exclusive(Tout x, Tout *total)
     Tout inc = x;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        Tout y = __shfl_up_sync(FULL, inc, d);
+        Tout y = shfl_up<Tout>(inc, d);
         if (lane >= d) inc += y;
     }
     if (lane == 31) wsum[w] = inc;
     __syncthreads();
     if (w == 0) {
-        Tout s = lane < SCAN_T / 32 ? wsum[lane] : 0, si = s;
+        Tout s = lane < SCAN_T / 32 ? wsum[lane] : Tout{}, si = s;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            Tout y = __shfl_up_sync(FULL, si, d);
+            Tout y = shfl_up<Tout>(si, d);
             if (lane >= d) si += y;
         }
         if (lane < SCAN_T / 32) wsum[lane] = si - s;
@@ -220,10 +251,10 @@ __global__ void __launch_bounds__(SCAN_T) k_scan1(const Tin *__restrict__ in, To
 template <class Tout>
 __global__ void __launch_bounds__(SCAN_T) k_scan2(Tout *bsum, int nb)
 {
-    Tout carry = 0;
+    Tout carry = Tout{};
     for (int b0 = 0; b0 < nb; b0 += SCAN_T) {
         int i = b0 + threadIdx.x;
-        Tout x = i < nb ? bsum[i] : (Tout)0, tot;
+        Tout x = i < nb ? bsum[i] : Tout{}, tot;
         Tout ex = block_exclusive<Tout>(x, &tot);
         if (i < nb) bsum[i] = carry + ex;
         carry += tot;
@@ -244,17 +275,320 @@ __global__ void __launch_bounds__(SCAN_T) k_scan3(Tout *__restrict__ out, int64_
 }
 
 // ------------------------------------------------------------------------------------------------
-// the search kernel: one warp per segment.
+// count mode, planning.  Segments are keyed by (tile, later): cnt2[2*tile + later].  One scan over the tiles
+// yields, per tile, where its segments start (seg_off), where its later-bin segments start (seg_mid) and where
+// its work items start (item_off); a tile with s segments and n records has ceil(n/GROUP) * ceil(s/SMAX) items.
+// ------------------------------------------------------------------------------------------------
+constexpr int GROUP = 128;      // records per item: 4 per lane
+constexpr int SMAX = 256;       // segments per item (bounds the cost of one item; hot tiles get many items)
+
+struct __align__(8) CSeg {       // count-mode segment: the query's interval, nothing else
+    int32_t qs, qe;
+};
+
+template <bool V>
+__global__ void k_cseg_count(DbView db, int64_t n, const int32_t *__restrict__ ctg, const int32_t *__restrict__ qs,
+                             const int32_t *__restrict__ qe, uint32_t *__restrict__ cnt2)
+{
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    for_each_segment<V>(db, ctg[q], qs[q], qe[q],
+                        [&](int tile, bool later, int) { atomicAdd(&cnt2[2 * tile + (later ? 1 : 0)], 1u); });
+}
+
+__device__ __forceinline__ Plan plan_of_tile(const DbView &db, const uint32_t *__restrict__ cnt2, int32_t t)
+{
+    const uint2 c = __ldg(reinterpret_cast<const uint2 *>(cnt2) + t);
+    const unsigned long long s = (unsigned long long)c.x + c.y;
+    if (s == 0) return Plan{0, 0};
+    const unsigned long long g = ((unsigned long long)(uint32_t)db.tiles[t].n + GROUP - 1) / GROUP;
+    return Plan{s, g * ((s + SMAX - 1) / SMAX)};
+}
+
+__global__ void __launch_bounds__(SCAN_T) k_plan1(DbView db, const uint32_t *__restrict__ cnt2,
+                                                   Plan *__restrict__ tmp, Plan *__restrict__ bsum)
+{
+    const int32_t T = db.ntiles;
+    const int64_t base = (int64_t)blockIdx.x * SCAN_B + (int64_t)threadIdx.x * SCAN_I;
+    Plan v[SCAN_I], s = Plan{0, 0};
+#pragma unroll
+    for (int k = 0; k < SCAN_I; ++k) {
+        v[k] = base + k < T ? plan_of_tile(db, cnt2, (int32_t)(base + k)) : Plan{0, 0};
+        s += v[k];
+    }
+    Plan tot, ex = block_exclusive<Plan>(s, &tot);
+#pragma unroll
+    for (int k = 0; k < SCAN_I; ++k) {
+        if (base + k < T) tmp[base + k] = ex;
+        ex += v[k];
+    }
+    if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(SCAN_T) k_plan3(int32_t T, const uint32_t *__restrict__ cnt2,
+                                                   const Plan *__restrict__ tmp, const Plan *__restrict__ bsum, int nb,
+                                                   uint32_t *__restrict__ seg_off, uint32_t *__restrict__ seg_mid,
+                                                   uint32_t *__restrict__ item_off, unsigned long long *__restrict__ tot)
+{
+    const int64_t base = (int64_t)blockIdx.x * SCAN_B + (int64_t)threadIdx.x * SCAN_I;
+    const Plan add = bsum[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_I; ++k) {
+        const int64_t t = base + k;
+        if (t < T) {
+            const Plan p = tmp[t] + add;
+            seg_off[t] = (uint32_t)p.segs;
+            seg_mid[t] = (uint32_t)p.segs + __ldg(&cnt2[2 * t]);
+            item_off[t] = (uint32_t)p.items;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const Plan p = bsum[nb];
+        seg_off[T] = (uint32_t)p.segs, item_off[T] = (uint32_t)p.items;
+        tot[0] = p.segs, tot[1] = p.items;
+    }
+}
+
+// cnt2 is counted back down to zero here, so it is clean for the next batch.  Nothing is written when the
+// plan does not fit the scratch buffers: the host then grows them and runs the batch again.
+template <bool V>
+__global__ void k_cseg_scatter(DbView db, int64_t n, const int32_t *__restrict__ ctg, const int32_t *__restrict__ qs,
+                               const int32_t *__restrict__ qe, uint32_t *__restrict__ cnt2,
+                               const uint32_t *__restrict__ seg_off, const uint32_t *__restrict__ seg_mid,
+                               const unsigned long long *__restrict__ tot, unsigned long long seg_cap,
+                               unsigned long long item_cap, CSeg *__restrict__ segs)
+{
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n || tot[0] > seg_cap || tot[1] > item_cap) return;
+    const int s = qs[q], e = qe[q];
+    for_each_segment<V>(db, ctg[q], s, e, [&](int tile, bool later, int) {
+        const uint32_t b = later ? __ldg(&seg_mid[tile]) : __ldg(&seg_off[tile]);
+        const uint32_t pos = b + atomicSub(&cnt2[2 * tile + (later ? 1 : 0)], 1u) - 1u;
+        segs[pos] = CSeg{s, e};
+    });
+}
+
+// Work items of tile t, group-major.  An item is self-contained, so the search kernel goes from the item to
+// its records and segments without touching the tile table:
+//   x = position of the group's first record in the SoA arrays, in units of 4 records
+//   y, z = first segment, one past the last segment
+//   w = records in the group (bits 0-7, 1..128) | first record of the group that starts inside this bin
+//       (bits 8-15, 0..128: the dedupe rule of later bins) | number of first-bin segments (bits 16-31, 0..256;
+//       the later-bin segments follow them)
+__global__ void __launch_bounds__(256) k_item_fill(DbView db, const uint32_t *__restrict__ seg_off,
+                                                    const uint32_t *__restrict__ seg_mid,
+                                                    const uint32_t *__restrict__ item_off,
+                                                    const unsigned long long *__restrict__ tot,
+                                                    unsigned long long seg_cap, unsigned long long item_cap,
+                                                    int4 *__restrict__ items)
+{
+    if (tot[0] > seg_cap || tot[1] > item_cap) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < db.ntiles; t += nw) {
+        const uint32_t i0 = __ldg(&item_off[t]), ni = __ldg(&item_off[t + 1]) - i0;
+        if (ni == 0) continue;
+        const uint32_t a = __ldg(&seg_off[t]), b = __ldg(&seg_off[t + 1]), mid = __ldg(&seg_mid[t]);
+        const int4 tm = __ldg(reinterpret_cast<const int4 *>(&db.tiles[t]));
+        const uint32_t ch = (b - a + SMAX - 1) / SMAX;
+        for (uint32_t k = lane; k < ni; k += 32) {
+            const uint32_t g = k / ch, c = k - g * ch;
+            const uint32_t sa = a + c * SMAX, sb = min(sa + (uint32_t)SMAX, b);
+            const int r0 = (int)(g * GROUP);
+            const uint32_t nv = (uint32_t)min(tm.y - r0, GROUP);
+            const uint32_t tsr = (uint32_t)min(max(tm.z - r0, 0), GROUP);
+            const uint32_t nfirst = min(max(mid, sa), sb) - sa;
+            items[i0 + k] = make_int4((int)((uint32_t)tm.x + g * (GROUP / 4)), (int)sa, (int)sb,
+                                      (int)(nv | (tsr << 8) | (nfirst << 16)));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// count mode, the search kernel (see the file header).  Restates the per-record predicate of get_overlaps
+// (src/igd_search.c:489-493, 522-526: start < qe from the binary search, end > qs from the scan, and in later
+// bins i >= tS, i.e. start >= bin boundary) and get_overlaps_v (:650-653, 680-683: ... && value >= v); which
+// tiles a query reaches at all was decided when its segments were made (for_each_segment).
+// ------------------------------------------------------------------------------------------------
+struct CountArgs {
+    DbView db;
+    const int4 *items;
+    const CSeg *segs;
+    const unsigned long long *tot;      // device: {segments, items} of this batch
+    unsigned long long seg_cap, item_cap;
+    int32_t v;
+    unsigned long long *hits;
+};
+
+constexpr int IMAX = 0x7fffffff, IMIN = -0x7fffffff - 1;
+constexpr int COUNT_T = 256;            // threads per CTA of k_count_items
+
+template <bool V>
+struct ItemRegs {                       // one lane's share of an item, as loaded: 4 records + 1 segment
+    int4 d;                             // the item (see k_item_fill)
+    int4 S, E, I, VV;
+    CSeg q;
+};
+
+// Issue the loads of item r.d.  Slots past the group's records keep (IMAX, IMIN): they can match no query; so
+// do the pad records inside the tile's last block of 4 (written as (IMAX, IMIN) at upload).
+template <bool V>
+__device__ __forceinline__ void load_item(const DbView &db, const CSeg *__restrict__ segs, int lane, ItemRegs<V> &r)
+{
+    r.S = make_int4(IMAX, IMAX, IMAX, IMAX), r.E = make_int4(IMIN, IMIN, IMIN, IMIN);
+    r.I = make_int4(0, 0, 0, 0), r.VV = make_int4(0, 0, 0, 0);
+    if (lane * 4 < (r.d.w & 0xff)) {
+        const int64_t p = (int64_t)(uint32_t)r.d.x * 4 + lane * 4;
+        r.S = ldg4(db.start + p), r.E = ldg4(db.end + p), r.I = ldg4(db.idx + p);
+        if (V) r.VV = ldg4(db.value + p);
+    }
+    r.q = CSeg{IMAX, IMIN};
+    if ((uint32_t)r.d.y + lane < (uint32_t)r.d.z) r.q = segs[(uint32_t)r.d.y + lane];
+}
+
+// c += (s < qe && e > qs)
+__device__ __forceinline__ void count_if(int &c, int s, int e, int qs, int qe)
+{
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %1, %4;\n\tsetp.gt.and.s32 p, %2, %3, p;\n\t@p add.s32 %0, %0, 1;\n\t}"
+        : "+r"(c)
+        : "r"(s), "r"(e), "r"(qs), "r"(qe));
+}
+
+// the segments selected by mask m (lanes of q) against this lane's 4 records
+__device__ __forceinline__ void count_segments(unsigned m, const CSeg &q, const int (&s)[4], const int (&e)[4],
+                                               int (&c)[4])
+{
+    while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const int qs = __shfl_sync(FULL, q.qs, src), qe = __shfl_sync(FULL, q.qe, src);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) count_if(c[k], s[k], e[k], qs, qe);
+    }
+}
+
+template <bool V, bool SMEM>
+__device__ __forceinline__ void count_item(const CountArgs &a, const ItemRegs<V> &r, int lane, uint32_t hist_s)
+{
+    int s[4] = {r.S.x, r.S.y, r.S.z, r.S.w}, e[4] = {r.E.x, r.E.y, r.E.z, r.E.w};
+    const int f[4] = {r.I.x, r.I.y, r.I.z, r.I.w};
+    int c[4] = {0, 0, 0, 0};
+    if (V) {
+        const int vv[4] = {r.VV.x, r.VV.y, r.VV.z, r.VV.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (vv[k] < a.v) s[k] = IMAX;                       // filtered out by -v: matches no query
+    }
+    const int smin = min(min(s[0], s[1]), min(s[2], s[3]));
+    const int wsmin = V ? __reduce_min_sync(FULL, smin) : __shfl_sync(FULL, s[0], 0);   // sorted by start
+    const int emax = __reduce_max_sync(FULL, max(max(e[0], e[1]), max(e[2], e[3])));
+    const uint32_t A = (uint32_t)r.d.y, B = (uint32_t)r.d.z;
+    const uint32_t M = A + ((uint32_t)r.d.w >> 16);            // first-bin segments [A, M), later-bin [M, B)
+    // first-bin segments: every record of the tile is a candidate
+    if (M > A) {
+        CSeg q = r.q;
+        for (uint32_t sb = A;;) {
+            const unsigned m = __ballot_sync(FULL, sb + lane < M && q.qe > wsmin && q.qs < emax);
+            count_segments(m, q, s, e, c);
+            sb += 32;
+            if (sb >= M) break;
+            q = CSeg{IMAX, IMIN};
+            if (sb + lane < M) q = a.segs[sb + lane];
+        }
+    }
+    // later-bin segments: only records that start inside this bin (index >= tS, src/igd_search.c:510-511,522)
+    if (B > M) {
+        const int tsr = (r.d.w >> 8) & 0xff;
+        int sl[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) sl[k] = lane * 4 + k >= tsr ? s[k] : IMAX;
+        const int wslmin = __reduce_min_sync(FULL, min(min(sl[0], sl[1]), min(sl[2], sl[3])));
+        if (wslmin != IMAX) {
+            const uint32_t b0 = A + ((M - A) & ~31u);           // 32-aligned (from A) batch holding segment M
+            CSeg q = r.q;
+            for (uint32_t sb = b0;;) {
+                if (sb != A) {
+                    q = CSeg{IMAX, IMIN};
+                    if (sb + lane < B) q = a.segs[sb + lane];
+                }
+                const unsigned m =
+                    __ballot_sync(FULL, sb + lane >= M && sb + lane < B && q.qe > wslmin && q.qs < emax);
+                count_segments(m, q, sl, e, c);
+                sb += 32;
+                if (sb >= B) break;
+            }
+        }
+    }
+    // hits[idx] += count: one atomic per record that overlaps anything
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (SMEM) {
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %1, 0;\n\t@p red.shared.add.u32 [%0], %1;\n\t}"
+                         :
+                         : "r"(hist_s + 4u * (uint32_t)f[k]), "r"(c[k])
+                         : "memory");
+        } else if (c[k]) {
+            atomicAdd(&a.hits[f[k]], (unsigned long long)c[k]);
+        }
+    }
+}
+
+template <bool V, bool SMEM>
+__global__ void __launch_bounds__(COUNT_T, 3) k_count_items(const CountArgs a)
+{
+    extern __shared__ uint32_t hist[];
+    const DbView &db = a.db;
+    if (SMEM) {
+        for (int f = threadIdx.x; f < db.nfiles; f += blockDim.x) hist[f] = 0;
+        __syncthreads();
+    }
+    const uint32_t hist_s = (uint32_t)__cvta_generic_to_shared(hist);
+    const int lane = threadIdx.x & 31, W = blockDim.x >> 5;
+    const unsigned long long nseg = __ldg(&a.tot[0]), nit = __ldg(&a.tot[1]);
+    const uint32_t n_items = (nseg > a.seg_cap || nit > a.item_cap) ? 0u : (uint32_t)nit;
+    const uint32_t stride = gridDim.x * W;
+    uint32_t it = blockIdx.x * W + (threadIdx.x >> 5);
+    // Software pipeline over this warp's items, two register sets (ra, rb) alternating: while an item is
+    // evaluated, the records and first 32 segments of the next one and the descriptor of the one after it are
+    // in flight.
+    const int4 zero = make_int4(0, 0, 0, 0);
+    ItemRegs<V> ra, rb;
+    ra.d = it < n_items ? __ldg(&a.items[it]) : zero;
+    rb.d = it + stride < n_items ? __ldg(&a.items[it + stride]) : zero;
+    load_item<V>(db, a.segs, lane, ra);
+    while (it < n_items) {
+        load_item<V>(db, a.segs, lane, rb);
+        const int4 da = it + 2 * stride < n_items ? __ldg(&a.items[it + 2 * stride]) : zero;
+        count_item<V, SMEM>(a, ra, lane, hist_s);
+        ra.d = da;
+        it += stride;
+        if (it >= n_items) break;
+        load_item<V>(db, a.segs, lane, ra);
+        const int4 dbn = it + 2 * stride < n_items ? __ldg(&a.items[it + 2 * stride]) : zero;
+        count_item<V, SMEM>(a, rb, lane, hist_s);
+        rb.d = dbn;
+        it += stride;
+    }
+    if (SMEM) {
+        __syncthreads();
+        for (int f = threadIdx.x; f < db.nfiles; f += blockDim.x) {
+            const uint32_t c = hist[f];
+            if (c) atomicAdd(&a.hits[f], (unsigned long long)c);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// -f: one warp per segment, in the reference's visiting order (get_overlaps_f1, src/igd_search.c:537-620).
 //   1. 32-ary ballot search for cnt = #{start < qe} in the tile (tL = cnt-1): every round the 32 lanes
 //      probe 32 evenly spaced records and one ballot narrows the range 32x -- 2 dependent loads for a
 //      1 k-record tile instead of 10.
-//   2. scan end[tS..tL] (tS = 0 in the query's first bin, the tile's dedupe start in later bins) with
-//      128-bit loads; predicate end > qs (and value >= v).
-//   3. OUT_HIST : hits[idx]++ in a block-private shared-memory histogram, flushed once per block
-//      OUT_COUNT: per-segment hit count (first pass of -f)
+//   2. scan end[tS..tL] (tS = 0 in the query's first bin, the tile's dedupe start in later bins);
+//      predicate end > qs.
+//   3. OUT_COUNT: per-segment hit count (first pass)
 //      OUT_FILL : records written in the reference's order (descending index) at the segment's offset
 // ------------------------------------------------------------------------------------------------
-enum { OUT_HIST = 0, OUT_COUNT = 1, OUT_FILL = 2 };
+enum { OUT_COUNT = 1, OUT_FILL = 2 };
 
 __device__ __forceinline__ int warp_count_lt(const int32_t *__restrict__ s, int n, int key, int lane)
 {
@@ -277,22 +611,15 @@ struct SearchArgs {
     DbView db;
     const Seg *segs;
     const uint32_t *nsegs;          // device scalar
-    int32_t v;
-    unsigned long long *hits;       // OUT_HIST
     uint32_t *seg_hits;             // OUT_COUNT  [sid]
     const unsigned long long *seg_off;   // OUT_FILL [sid]
-    int32_t *out_s, *out_e, *out_f;      // OUT_FILL
+    int32_t *out_s, *out_e, *out_f, *out_g;     // OUT_FILL (out_g: index within the tile, may be NULL)
 };
 
-template <bool V, int OUT, bool SMEM>
+template <int OUT>
 __global__ void __launch_bounds__(512) k_search(const SearchArgs a)
 {
-    extern __shared__ uint32_t hist[];
     const DbView &db = a.db;
-    if (OUT == OUT_HIST && SMEM) {
-        for (int f = threadIdx.x; f < db.nfiles; f += blockDim.x) hist[f] = 0;
-        __syncthreads();
-    }
     const int lane = threadIdx.x & 31;
     const uint32_t nsegs = __ldg(a.nsegs);
     const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
@@ -305,35 +632,20 @@ __global__ void __launch_bounds__(512) k_search(const SearchArgs a)
         const uint32_t sid = (uint32_t)sg.w & 0x7fffffffu;
         const int hi = warp_count_lt(db.start + off, tm.y, qe, lane);        // tL + 1
         const int32_t *__restrict__ E = db.end + off;
-        const int32_t *__restrict__ Vv = db.value + off;
-        const int32_t *__restrict__ I = db.idx + off;
-        if (OUT != OUT_FILL) {
+        if (OUT == OUT_COUNT) {
             int cnt = 0;
             for (int b = (tS & ~3) + lane * 4; b < hi; b += 128) {
                 const int4 e = ldg4(E + b);
-                int4 val = make_int4(0, 0, 0, 0);
-                if (V) val = ldg4(Vv + b);
                 const int ev[4] = {e.x, e.y, e.z, e.w};
-                const int vv[4] = {val.x, val.y, val.z, val.w};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const int i = b + k;
-                    if (i >= tS && i < hi && ev[k] > qs && (!V || vv[k] >= a.v)) {
-                        if (OUT == OUT_HIST) {
-                            const int f = __ldg(&I[i]);
-                            if (SMEM) atomicAdd(&hist[f], 1u);
-                            else atomicAdd(&a.hits[f], 1ull);
-                        } else {
-                            ++cnt;
-                        }
-                    }
+                    cnt += (i >= tS) & (i < hi) & (ev[k] > qs);
                 }
             }
-            if (OUT == OUT_COUNT) {
 #pragma unroll
-                for (int d = 16; d; d >>= 1) cnt += __shfl_xor_sync(FULL, cnt, d);
-                if (lane == 0) a.seg_hits[sid] = (uint32_t)cnt;
-            }
+            for (int d = 16; d; d >>= 1) cnt += __shfl_xor_sync(FULL, cnt, d);
+            if (lane == 0) a.seg_hits[sid] = (uint32_t)cnt;
         } else {
             unsigned long long pos = __ldg(&a.seg_off[sid]);
             for (int top = hi - 1; top >= tS; top -= 32) {
@@ -349,17 +661,11 @@ __global__ void __launch_bounds__(512) k_search(const SearchArgs a)
                     const unsigned long long p = pos + __popc(b & ((1u << lane) - 1u));
                     a.out_s[p] = __ldg(&db.start[off + i]);
                     a.out_e[p] = e;
-                    a.out_f[p] = __ldg(&I[i]);
+                    a.out_f[p] = __ldg(&db.idx[off + i]);
+                    if (a.out_g) a.out_g[p] = i;
                 }
                 pos += __popc(b);
             }
-        }
-    }
-    if (OUT == OUT_HIST && SMEM) {
-        __syncthreads();
-        for (int f = threadIdx.x; f < db.nfiles; f += blockDim.x) {
-            const uint32_t c = hist[f];
-            if (c) atomicAdd(&a.hits[f], (unsigned long long)c);
         }
     }
 }
@@ -472,6 +778,26 @@ struct igdb_dev {
     int64_t segx_cap = 0;
     unsigned long long *d_hits = nullptr;                   // [nfiles]
     uint32_t *h_scalar = nullptr;                           // pinned readback
+    // count mode (tile-centric): plan scratch, segments, work items
+    uint32_t *cnt2 = nullptr, *cseg_off = nullptr, *cseg_mid = nullptr, *item_off = nullptr;   // [2T+2],[T+1],[T+1],[T+1]
+    Plan *plan_tmp = nullptr, *plan_bsum = nullptr;         // [T], [scan blocks + 1]
+    unsigned long long *plan_tot = nullptr;                 // device {segments, items} of the batch in flight
+    volatile unsigned long long *h_plan = nullptr;          // pinned copy of plan_tot
+    cudaEvent_t plan_ev = nullptr;
+    CSeg *csegs = nullptr;
+    int64_t cseg_cap = 0;
+    int4 *items = nullptr;
+    int64_t item_cap = 0;
+    int64_t db_groups = 0;                                  // sum over tiles of ceil(n / GROUP)
+    int count_grid[2] = {0, 0};                             // CTAs of k_count_items<V> (0 = not yet computed)
+    struct Pending {                                        // count batch enqueued but not yet settled
+        bool active = false, mode_v = false;
+        int64_t n = 0;
+        const int32_t *ctg = nullptr, *qs = nullptr, *qe = nullptr;
+        int32_t v = 0;
+        unsigned long long *hits = nullptr;
+        cudaStream_t st = nullptr;
+    } pending;
     DbView view() const
     {
         DbView v;
@@ -541,51 +867,34 @@ int ensure_query_cap(igdb_dev *d, int64_t n)
     return 0;
 }
 
-// search kernel launch geometry: persistent-style grid, a whole number of CTAs per SM
-template <bool V, int OUT>
+// -f kernels: persistent-style grid, a whole number of CTAs per SM
+template <int OUT>
 int launch_search(igdb_dev *d, const SearchArgs &a, cudaStream_t st)
 {
     const int threads = 512;
-    const size_t hist_bytes = (size_t)d->nfiles * sizeof(uint32_t);
-    const bool smem = OUT == OUT_HIST && hist_bytes <= 200 * 1024;
-    const size_t shm = smem ? hist_bytes : 0;
     int per_sm = 0;
-    if (OUT == OUT_HIST) CK(cudaEventRecord(d->kev[0], st));
-    if (smem) {
-        auto kern = k_search<V, OUT, true>;
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, shm));
-        per_sm = std::max(per_sm, 1);
-        kern<<<d->sm_count * per_sm, threads, shm, st>>>(a);
-    } else {
-        auto kern = k_search<V, OUT, false>;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0));
-        per_sm = std::max(per_sm, 1);
-        kern<<<d->sm_count * per_sm, threads, 0, st>>>(a);
-    }
-    if (OUT == OUT_HIST) {
-        CK(cudaEventRecord(d->kev[1], st));
-        d->kev_valid = true;
-    }
+    auto kern = k_search<OUT>;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0));
+    per_sm = std::max(per_sm, 1);
+    kern<<<d->sm_count * per_sm, threads, 0, st>>>(a);
     d->launches += 1;
     CK(cudaGetLastError());
     return 0;
 }
 
-// queries (device) -> tile-sorted segments.  Leaves the segment count in tile_off[T] and, if with_sid,
-// the per-query segment prefix in qseg_off.  One stream sync (to size the segment buffer).
-template <bool V>
+// -f: queries (device) -> tile-sorted segments.  Leaves the segment count in tile_off[T] and the per-query
+// segment prefix in qseg_off.  One stream sync (to size the segment buffer).
 int build_segments(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_t *qs, const int32_t *qe,
-                   bool with_sid, cudaStream_t st, uint32_t *nsegs_out)
+                   cudaStream_t st, uint32_t *nsegs_out)
 {
     const DbView db = d->view();
     const int thr = 256;
     const int nb = (int)((n + thr - 1) / thr);
-    k_seg_count<V><<<nb, thr, 0, st>>>(db, n, ctg, qs, qe, d->tile_cnt, with_sid ? d->nseg : nullptr);
+    k_seg_count<false><<<nb, thr, 0, st>>>(db, n, ctg, qs, qe, d->tile_cnt, d->nseg);
     d->launches += 1;
     CK(cudaGetLastError());
     if (exclusive_scan<uint32_t, uint32_t>(d, d->tile_cnt, d->tile_off, d->T, st)) return -1;
-    if (with_sid && exclusive_scan<uint32_t, uint32_t>(d, d->nseg, d->qseg_off, n, st)) return -1;
+    if (exclusive_scan<uint32_t, uint32_t>(d, d->nseg, d->qseg_off, n, st)) return -1;
     CK(cudaMemcpyAsync(d->h_scalar, d->tile_off + d->T, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const uint32_t nsegs = *d->h_scalar;
@@ -594,24 +903,124 @@ int build_segments(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_t *qs
         return -1;
     }
     if (grow(&d->segs, &d->seg_cap, (int64_t)nsegs)) return -1;
-    k_seg_scatter<V><<<nb, thr, 0, st>>>(db, n, ctg, qs, qe, d->tile_cnt, d->tile_off,
-                                          with_sid ? d->qseg_off : nullptr, d->segs);
+    k_seg_scatter<false><<<nb, thr, 0, st>>>(db, n, ctg, qs, qe, d->tile_cnt, d->tile_off, d->qseg_off, d->segs);
     d->launches += 1;
     CK(cudaGetLastError());
     *nsegs_out = nsegs;
     return 0;
 }
 
+// ---- count mode ----------------------------------------------------------------------------------
+// One batch = 7 launches on one stream with no host round trip in between: the kernels that consume the
+// plan check on the device that it fits the scratch buffers and do nothing otherwise; the host looks at
+// the plan's totals when it settles the batch and, in the rare case they did not fit (first batch of a
+// larger size), grows the buffers and runs the batch again -- or splits it when the plan itself is too big.
 template <bool V>
-int count_device_impl(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_t *qs, const int32_t *qe, int32_t v,
-                      unsigned long long *d_hits, cudaStream_t st)
+int count_geometry(igdb_dev *d, int *grid, size_t *shm, bool *smem)
 {
-    uint32_t nsegs = 0;
-    if (build_segments<V>(d, n, ctg, qs, qe, false, st, &nsegs)) return -1;
-    if (nsegs == 0) return 0;
-    SearchArgs a{};
-    a.db = d->view(), a.segs = d->segs, a.nsegs = d->tile_off + d->T, a.v = v, a.hits = d_hits;
-    return launch_search<V, OUT_HIST>(d, a, st);
+    const size_t hist_bytes = (size_t)d->nfiles * sizeof(uint32_t);
+    *smem = hist_bytes <= 200 * 1024;
+    *shm = *smem ? hist_bytes : 0;
+    if (d->count_grid[V] == 0) {
+        int per_sm = 0;
+        if (*smem) {
+            CK(cudaFuncSetAttribute(k_count_items<V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*shm));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_count_items<V, true>, COUNT_T, *shm));
+        } else {
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_count_items<V, false>, COUNT_T, 0));
+        }
+        d->count_grid[V] = d->sm_count * std::max(per_sm, 1);
+    }
+    *grid = d->count_grid[V];
+    return 0;
+}
+
+// a CTA's shared histogram is uint32: an item adds at most GROUP*SMAX = 2^15, a CTA takes at most
+// items/grid + COUNT_T/32 items, so this many items per launch cannot overflow a counter
+int64_t item_limit(const igdb_dev *d, int grid) { return ((int64_t)(1 << 17) - 64) * grid; }
+
+template <bool V>
+int enqueue_count(igdb_dev *d, const igdb_dev::Pending &p)
+{
+    cudaStream_t st = p.st;
+    const DbView db = d->view();
+    int grid = 0;
+    size_t shm = 0;
+    bool smem = false;
+    if (count_geometry<V>(d, &grid, &shm, &smem)) return -1;
+    if (grow(&d->csegs, &d->cseg_cap, std::max<int64_t>(2 * p.n, 4096), 1, 1)) return -1;
+    if (grow(&d->items, &d->item_cap, std::min<int64_t>(d->db_groups + p.n / 64, item_limit(d, grid)) + 1024, 1, 1))
+        return -1;
+    const unsigned long long seg_cap = (unsigned long long)std::min<int64_t>(d->cseg_cap, 0x7fffffff);
+    const unsigned long long item_cap = (unsigned long long)std::min<int64_t>(d->item_cap, item_limit(d, grid));
+    const int thr = 256;
+    const int nb = (int)((p.n + thr - 1) / thr);
+    const int sb = (d->T + SCAN_B - 1) / SCAN_B;
+    k_cseg_count<V><<<nb, thr, 0, st>>>(db, p.n, p.ctg, p.qs, p.qe, d->cnt2);
+    k_plan1<<<sb, SCAN_T, 0, st>>>(db, d->cnt2, d->plan_tmp, d->plan_bsum);
+    k_scan2<Plan><<<1, SCAN_T, 0, st>>>(d->plan_bsum, sb);
+    k_plan3<<<sb, SCAN_T, 0, st>>>(d->T, d->cnt2, d->plan_tmp, d->plan_bsum, sb, d->cseg_off, d->cseg_mid,
+                                    d->item_off, d->plan_tot);
+    CK(cudaMemcpyAsync((void *)d->h_plan, d->plan_tot, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(d->plan_ev, st));
+    k_cseg_scatter<V><<<nb, thr, 0, st>>>(db, p.n, p.ctg, p.qs, p.qe, d->cnt2, d->cseg_off, d->cseg_mid,
+                                           d->plan_tot, seg_cap, item_cap, d->csegs);
+    k_item_fill<<<d->sm_count * 8, 256, 0, st>>>(db, d->cseg_off, d->cseg_mid, d->item_off, d->plan_tot, seg_cap,
+                                                  item_cap, d->items);
+    CountArgs a{};
+    a.db = db, a.items = d->items, a.segs = d->csegs, a.tot = d->plan_tot;
+    a.seg_cap = seg_cap, a.item_cap = item_cap, a.v = p.v, a.hits = p.hits;
+    CK(cudaEventRecord(d->kev[0], st));
+    if (smem) k_count_items<V, true><<<grid, COUNT_T, shm, st>>>(a);
+    else k_count_items<V, false><<<grid, COUNT_T, 0, st>>>(a);
+    CK(cudaEventRecord(d->kev[1], st));
+    d->kev_valid = true;
+    d->launches += 7;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int enqueue_count(igdb_dev *d, const igdb_dev::Pending &p)
+{
+    if (p.n <= 0) return 0;
+    return p.mode_v ? enqueue_count<true>(d, p) : enqueue_count<false>(d, p);
+}
+
+// wait for the plan of the enqueued batch p; make sure it ran (see above)
+int settle_count(igdb_dev *d, const igdb_dev::Pending &p)
+{
+    if (p.n <= 0) return 0;
+    for (;;) {
+        CK(cudaEventSynchronize(d->plan_ev));
+        const unsigned long long nsegs = d->h_plan[0], nitems = d->h_plan[1];
+        const int64_t lim = item_limit(d, d->count_grid[p.mode_v]);
+        if (nsegs <= (unsigned long long)std::min<int64_t>(d->cseg_cap, 0x7fffffff) &&
+            nitems <= (unsigned long long)std::min<int64_t>(d->item_cap, lim))
+            return 0;
+        // none of this batch's kernels wrote anything, but its segment counters were not counted back down
+        CK(cudaStreamSynchronize(p.st));
+        CK(cudaMemsetAsync(d->cnt2, 0, ((size_t)2 * d->T + 2) * 4, p.st));
+        if (nsegs >= 0x7fffffffull || nitems > (unsigned long long)lim) {
+            if (p.n <= 1) {
+                snprintf(g_err, sizeof g_err, "a single query expands to too many (query, tile) segments");
+                return -1;
+            }
+            igdb_dev::Pending a = p, b = p;
+            a.n = p.n / 2, b.n = p.n - a.n;
+            b.ctg += a.n, b.qs += a.n, b.qe += a.n;
+            if (enqueue_count(d, a) || settle_count(d, a) || enqueue_count(d, b) || settle_count(d, b)) return -1;
+            return 0;
+        }
+        if (grow(&d->csegs, &d->cseg_cap, (int64_t)nsegs) || grow(&d->items, &d->item_cap, (int64_t)nitems)) return -1;
+        if (enqueue_count(d, p)) return -1;
+    }
+}
+
+int finish_pending(igdb_dev *d)
+{
+    if (!d->pending.active) return 0;
+    d->pending.active = false;
+    return settle_count(d, d->pending);
 }
 
 }  // namespace
@@ -633,11 +1042,13 @@ void igdb_dev_destroy(igdb_dev *d)
     cudaSetDevice(d->device);
     void *ptrs[] = {d->tiles, d->d_toff, d->start, d->end, d->idx, d->value, d->tbase, d->d_stage, d->q_ctg,
                     d->q_qs, d->q_qe, d->tile_cnt, d->tile_off, d->nseg, d->qseg_off, d->bsum, d->segs,
-                    d->seg_hits, d->seg_out_off, d->d_hits};
+                    d->seg_hits, d->seg_out_off, d->d_hits, d->cnt2, d->cseg_off, d->cseg_mid, d->item_off,
+                    d->plan_tmp, d->plan_bsum, d->plan_tot, d->csegs, d->items};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (d->pinned) cudaFreeHost(d->pinned);
     if (d->h_scalar) cudaFreeHost(d->h_scalar);
+    if (d->plan_ev) cudaEventDestroy(d->plan_ev);
     for (auto &e : d->ev)
         if (e) cudaEventDestroy(e);
     for (auto &e : d->kev)
@@ -656,6 +1067,8 @@ static int create_impl(igdb_dev *d, const int32_t *ntile, const int32_t *ncnt)
     for (auto &e : d->ev) CK(cudaEventCreate(&e));
     for (auto &e : d->kev) CK(cudaEventCreate(&e));
     CK(cudaMallocHost((void **)&d->h_scalar, 64));
+    d->h_plan = reinterpret_cast<volatile unsigned long long *>(d->h_scalar + 8);
+    CK(cudaEventCreateWithFlags(&d->plan_ev, cudaEventDisableTiming));
 
     std::vector<int32_t> tbase(d->nctg + 1, 0);
     for (int c = 0; c < d->nctg; ++c) tbase[c + 1] = tbase[c] + ntile[c];
@@ -671,6 +1084,7 @@ static int create_impl(igdb_dev *d, const int32_t *ntile, const int32_t *ncnt)
             meta[t].ts = d->nbp * j;            // bin boundary; k_tile_meta turns it into tS
             meta[t].s0 = 0x7fffffff;
             d->toff[t + 1] = d->toff[t] + n;
+            d->db_groups += (n + GROUP - 1) / GROUP;
             p4 += (n + 3) / 4;
         }
     if (p4 >= (int64_t)0xffffffff) {
@@ -683,16 +1097,24 @@ static int create_impl(igdb_dev *d, const int32_t *ntile, const int32_t *ncnt)
         dev_alloc(d, &d->tbase, (size_t)d->nctg + 1) || dev_alloc(d, &d->start, (size_t)d->P + 4) ||
         dev_alloc(d, &d->end, (size_t)d->P + 4) || dev_alloc(d, &d->idx, (size_t)d->P + 4) ||
         dev_alloc(d, &d->value, (size_t)d->P + 4) || dev_alloc(d, &d->tile_cnt, (size_t)d->T + 1) ||
-        dev_alloc(d, &d->tile_off, (size_t)d->T + 1) || dev_alloc(d, &d->d_hits, (size_t)d->nfiles))
+        dev_alloc(d, &d->tile_off, (size_t)d->T + 1) || dev_alloc(d, &d->d_hits, (size_t)d->nfiles) ||
+        dev_alloc(d, &d->cnt2, (size_t)2 * d->T + 2) || dev_alloc(d, &d->cseg_off, (size_t)d->T + 1) ||
+        dev_alloc(d, &d->cseg_mid, (size_t)d->T + 1) || dev_alloc(d, &d->item_off, (size_t)d->T + 1) ||
+        dev_alloc(d, &d->plan_tmp, (size_t)d->T + 1) ||
+        dev_alloc(d, &d->plan_bsum, (size_t)(d->T + SCAN_B - 1) / SCAN_B + 2) || dev_alloc(d, &d->plan_tot, 2))
         return -1;
     CK(cudaMemcpy(d->tiles, meta.data(), meta.size() * sizeof(TileMeta), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d->d_toff, d->toff.data(), d->toff.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d->tbase, tbase.data(), tbase.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-    CK(cudaMemset(d->start, 0x7f, ((size_t)d->P + 4) * 4));
-    CK(cudaMemset(d->end, 0x80, ((size_t)d->P + 4) * 4));
+    // pad records (tiles are padded to a multiple of 4): start = INT_MAX, end = INT_MIN -- overlap no query
+    const unsigned fb = (unsigned)std::min<int64_t>(((int64_t)d->P + 4 + 255) / 256, 148 * 32);
+    k_fill<<<fb, 256>>>(d->start, (int64_t)d->P + 4, IMAX);
+    k_fill<<<fb, 256>>>(d->end, (int64_t)d->P + 4, IMIN);
+    k_fill<<<fb, 256>>>(d->value, (int64_t)d->P + 4, IMIN);
+    CK(cudaGetLastError());
     CK(cudaMemset(d->idx, 0, ((size_t)d->P + 4) * 4));
-    CK(cudaMemset(d->value, 0x80, ((size_t)d->P + 4) * 4));
     CK(cudaMemset(d->tile_cnt, 0, ((size_t)d->T + 1) * 4));
+    CK(cudaMemset(d->cnt2, 0, ((size_t)2 * d->T + 2) * 4));
     return 0;
 }
 
@@ -773,19 +1195,33 @@ int igdb_dev_count_device(igdb_dev *d, int64_t n, const int32_t *d_ctg, const in
                           int mode_v, int32_t v, uint64_t *d_hits, void *stream)
 {
     g_err[0] = 0;
-    if (n <= 0) return 0;
     CK(cudaSetDevice(d->device));
+    if (finish_pending(d)) return -1;
+    if (n <= 0) return 0;
+    if (d->T == 0) return 0;
     cudaStream_t st = stream ? (cudaStream_t)stream : d->stream;
     const int64_t BATCH = 1 << 26;
     for (int64_t a = 0; a < n; a += BATCH) {
-        const int64_t m = std::min(BATCH, n - a);
-        int rc = mode_v ? count_device_impl<true>(d, m, d_ctg + a, d_qs + a, d_qe + a, v,
-                                                 (unsigned long long *)d_hits, st)
-                       : count_device_impl<false>(d, m, d_ctg + a, d_qs + a, d_qe + a, v,
-                                                  (unsigned long long *)d_hits, st);
-        if (rc) return rc;
+        igdb_dev::Pending p;
+        p.mode_v = mode_v != 0, p.n = std::min(BATCH, n - a);
+        p.ctg = d_ctg + a, p.qs = d_qs + a, p.qe = d_qe + a, p.v = v;
+        p.hits = (unsigned long long *)d_hits, p.st = st;
+        if (enqueue_count(d, p)) return -1;
+        if (a + BATCH < n) {                        // the scratch buffers are reused by the next chunk
+            if (settle_count(d, p)) return -1;
+        } else {
+            p.active = true;
+            d->pending = p;
+        }
     }
     return 0;
+}
+
+int igdb_dev_count_finish(igdb_dev *d)
+{
+    g_err[0] = 0;
+    CK(cudaSetDevice(d->device));
+    return finish_pending(d);
 }
 
 int igdb_dev_count_host(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_t *qs, const int32_t *qe, int mode_v,
@@ -793,11 +1229,12 @@ int igdb_dev_count_host(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_
 {
     g_err[0] = 0;
     CK(cudaSetDevice(d->device));
+    if (finish_pending(d)) return -1;
     cudaStream_t st = d->stream;
     CK(cudaMemsetAsync(d->d_hits, 0, (size_t)d->nfiles * 8, st));
     if (t_ms) t_ms[0] = t_ms[1] = t_ms[2] = 0.f;
     const int64_t BATCH = 1 << 26;
-    for (int64_t a = 0; a < n; a += BATCH) {
+    for (int64_t a = 0; a < n && d->T > 0; a += BATCH) {
         const int64_t m = std::min(BATCH, n - a);
         if (ensure_query_cap(d, m)) return -1;
         CK(cudaEventRecord(d->ev[0], st));
@@ -805,21 +1242,40 @@ int igdb_dev_count_host(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_
         CK(cudaMemcpyAsync(d->q_qs, qs + a, (size_t)m * 4, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(d->q_qe, qe + a, (size_t)m * 4, cudaMemcpyHostToDevice, st));
         CK(cudaEventRecord(d->ev[1], st));
-        int rc = mode_v ? count_device_impl<true>(d, m, d->q_ctg, d->q_qs, d->q_qe, v, d->d_hits, st)
-                       : count_device_impl<false>(d, m, d->q_ctg, d->q_qs, d->q_qe, v, d->d_hits, st);
-        if (rc) return rc;
-        CK(cudaEventRecord(d->ev[2], st));
+        igdb_dev::Pending p;
+        p.mode_v = mode_v != 0, p.n = m, p.ctg = d->q_ctg, p.qs = d->q_qs, p.qe = d->q_qe, p.v = v;
+        p.hits = d->d_hits, p.st = st;
+        if (enqueue_count(d, p)) return -1;
+        const bool last = a + BATCH >= n;
+        if (last) {                                 // the result copy rides behind the kernels; no sync yet
+            CK(cudaEventRecord(d->ev[2], st));
+            CK(cudaMemcpyAsync(hits_delta, d->d_hits, (size_t)d->nfiles * 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaEventRecord(d->ev[3], st));
+        }
+        // in the rare case the batch had to be run again, the copy is repeated below
+        const int64_t launches0 = d->launches;
+        if (settle_count(d, p)) return -1;
+        if (last && d->launches != launches0) {
+            CK(cudaEventRecord(d->ev[2], st));
+            CK(cudaMemcpyAsync(hits_delta, d->d_hits, (size_t)d->nfiles * 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaEventRecord(d->ev[3], st));
+        }
+        if (t_ms || !last) CK(cudaStreamSynchronize(st));
         if (t_ms) {
-            CK(cudaEventSynchronize(d->ev[2]));
             float x = 0, y = 0;
             CK(cudaEventElapsedTime(&x, d->ev[0], d->ev[1]));
-            CK(cudaEventElapsedTime(&y, d->ev[1], d->ev[2]));
-            t_ms[0] += x, t_ms[1] += y;
+            t_ms[0] += x;
+            if (last) {
+                CK(cudaEventElapsedTime(&y, d->ev[1], d->ev[2]));
+                t_ms[1] += y;
+            }
         }
     }
-    CK(cudaEventRecord(d->ev[2], st));
-    CK(cudaMemcpyAsync(hits_delta, d->d_hits, (size_t)d->nfiles * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaEventRecord(d->ev[3], st));
+    if (n <= 0 || d->T == 0) {
+        CK(cudaMemcpyAsync(hits_delta, d->d_hits, (size_t)d->nfiles * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return 0;
+    }
     CK(cudaStreamSynchronize(st));
     if (t_ms) CK(cudaEventElapsedTime(&t_ms[2], d->ev[2], d->ev[3]));
     return 0;
@@ -845,7 +1301,7 @@ int64_t igdb_dev_full_host(igdb_dev *d, int64_t n, const int32_t *ctg, const int
     CK(cudaMemcpyAsync(d->q_qs, qs, (size_t)n * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d->q_qe, qe, (size_t)n * 4, cudaMemcpyHostToDevice, st));
     uint32_t nsegs = 0;
-    if (build_segments<false>(d, n, d->q_ctg, d->q_qs, d->q_qe, true, st, &nsegs)) return -1;
+    if (build_segments(d, n, d->q_ctg, d->q_qs, d->q_qe, st, &nsegs)) return -1;
     if (nsegs == 0) return 0;
     {
         int64_t c = d->segx_cap;
@@ -856,7 +1312,7 @@ int64_t igdb_dev_full_host(igdb_dev *d, int64_t n, const int32_t *ctg, const int
     }
     SearchArgs a{};
     a.db = d->view(), a.segs = d->segs, a.nsegs = d->tile_off + d->T, a.seg_hits = d->seg_hits;
-    if (launch_search<false, OUT_COUNT>(d, a, st)) return -1;
+    if (launch_search<OUT_COUNT>(d, a, st)) return -1;
     if (exclusive_scan<uint32_t, unsigned long long>(d, d->seg_hits, d->seg_out_off, nsegs, st)) return -1;
     unsigned long long *h_total = (unsigned long long *)(d->h_scalar + 2);
     CK(cudaMemcpyAsync(h_total, d->seg_out_off + nsegs, 8, cudaMemcpyDeviceToHost, st));
@@ -878,7 +1334,7 @@ int64_t igdb_dev_full_host(igdb_dev *d, int64_t n, const int32_t *ctg, const int
         }
         a.seg_off = d->seg_out_off;
         a.out_s = d_out, a.out_e = d_out + total, a.out_f = d_out + 2 * total;
-        if (launch_search<false, OUT_FILL>(d, a, st)) return -1;
+        if (launch_search<OUT_FILL>(d, a, st)) return -1;
         int32_t *hs = (int32_t *)malloc((size_t)total * 4), *he = (int32_t *)malloc((size_t)total * 4),
                 *hf = (int32_t *)malloc((size_t)total * 4);
         if (!hs || !he || !hf) {

@@ -34,9 +34,13 @@ void *igdb_dev_pinned(igdb_dev *d, size_t bytes);   /* reusable pinned staging b
  * kernels, D2H (may be NULL). */
 int igdb_dev_count_host(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_t *qs, const int32_t *qe,
                         int mode_v, int32_t v, uint64_t *hits_delta, float *t_ms);
-/* device buffers, enqueued on stream; d_hits[nfiles] incremented */
+/* device buffers, enqueued on stream; d_hits[nfiles] incremented.  Pair with igdb_dev_count_finish. */
 int igdb_dev_count_device(igdb_dev *d, int64_t n, const int32_t *d_ctg, const int32_t *d_qs,
                           const int32_t *d_qe, int mode_v, int32_t v, uint64_t *d_hits, void *stream);
+/* waits until the batch enqueued by igdb_dev_count_device has been planned; if its plan did not fit the
+ * scratch buffers (nothing was added to d_hits then) grows them and runs it again.  0 = d_hits is valid
+ * in stream order. */
+int igdb_dev_count_finish(igdb_dev *d);
 
 /* -f: returns total (>= 0) and malloc'ed host arrays; query_off has n+1 entries */
 int64_t igdb_dev_full_host(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_t *qs, const int32_t *qe,

@@ -211,6 +211,12 @@ int igd_b200_count_device(igd_b200_t *h, int64_t n, const int32_t *d_ctg, const 
     return igdb_dev_count_device(h->dev, n, d_ctg, d_qs, d_qe, v > 0, v, d_hits, stream);
 }
 
+int igd_b200_count_device_finish(igd_b200_t *h)
+{
+    g_err[0] = 0;
+    return igdb_dev_count_finish(h->dev);
+}
+
 int64_t get_overlaps_n(igd_b200_t *h, int64_t n, const char *const *chrm, const int32_t *qs,
                        const int32_t *qe, int32_t v, int64_t *hits)
 {

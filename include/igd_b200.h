@@ -62,11 +62,17 @@ int64_t get_overlaps_n(igd_b200_t *h, int64_t n, const char *const *chrm, const 
 int64_t igd_b200_count(igd_b200_t *h, int64_t n, const int32_t *ctg, const int32_t *qs,
                        const int32_t *qe, int32_t v, int64_t *hits);
 /* same, but every buffer is a DEVICE pointer on the handle's device and the work is enqueued on
- * `stream` (a cudaStream_t, may be NULL).  d_hits is uint64[nFiles], incremented.  Returns 0 once the
- * work is enqueued; the caller synchronises.  This is the entry point the multi-GPU driver uses, with an
- * NCCL allreduce of d_hits behind it. */
+ * `stream` (a cudaStream_t, may be NULL) without any host round trip.  d_hits is uint64[nFiles],
+ * incremented.  Returns 0 once the work is enqueued.  This is the entry point the multi-GPU driver uses,
+ * with an NCCL allreduce of d_hits behind it.
+ * igd_b200_count_device_finish must be called before d_hits is consumed (read back, or reduced across
+ * ranks): the search is enqueued speculatively against the handle's scratch buffers, and a batch whose
+ * (query, tile) expansion did not fit them adds NOTHING to d_hits; finish detects that, grows the buffers
+ * and runs the batch again on the same stream (only ever on the first batch of a larger size).  It waits
+ * for the batch's plan, not for the search kernel. */
 int igd_b200_count_device(igd_b200_t *h, int64_t n, const int32_t *d_ctg, const int32_t *d_qs,
                           const int32_t *d_qe, int32_t v, uint64_t *d_hits, void *stream);
+int igd_b200_count_device_finish(igd_b200_t *h);
 
 /* -f: the overlaps themselves, in the reference's order (get_overlaps_f1, src/igd_search.c:537-620:
  * per query, bin n1 from the last start < qe downwards, then later bins ascending).
