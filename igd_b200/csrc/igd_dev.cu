@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(SCAN_T) k_scan3(Tout *__restrict__ out, int64_
 // its work items start (item_off); a tile with s segments and n records has ceil(n/GROUP) * ceil(s/SMAX) items.
 // ------------------------------------------------------------------------------------------------
 constexpr int GROUP = 128;      // records per item: 4 per lane
-constexpr int SMAX = 256;       // segments per item (bounds the cost of one item; hot tiles get many items)
+constexpr int SMAX = 64;        // segments per item: what one pipeline stage holds (hot tiles get many items)
 
 struct __align__(8) CSeg {       // count-mode segment: the query's interval, nothing else
     int32_t qs, qe;
@@ -302,7 +302,8 @@ __device__ __forceinline__ Plan plan_of_tile(const DbView &db, const uint32_t *_
     const unsigned long long s = (unsigned long long)c.x + c.y;
     if (s == 0) return Plan{0, 0};
     const unsigned long long g = ((unsigned long long)(uint32_t)db.tiles[t].n + GROUP - 1) / GROUP;
-    return Plan{s, g * ((s + SMAX - 1) / SMAX)};
+    // a tile's segments start at an even index: 8-byte segments, 16-byte aligned bulk copies
+    return Plan{(s + 1) & ~1ull, g * ((s + SMAX - 1) / SMAX)};
 }
 
 __global__ void __launch_bounds__(SCAN_T) k_plan1(DbView db, const uint32_t *__restrict__ cnt2,
@@ -371,12 +372,13 @@ __global__ void k_cseg_scatter(DbView db, int64_t n, const int32_t *__restrict__
 // Work items of tile t, group-major.  An item is self-contained, so the search kernel goes from the item to
 // its records and segments without touching the tile table:
 //   x = position of the group's first record in the SoA arrays, in units of 4 records
-//   y, z = first segment, one past the last segment
+//   y = first segment (z = one past the last, kept for debugging)
 //   w = records in the group (bits 0-7, 1..128) | first record of the group that starts inside this bin
-//       (bits 8-15, 0..128: the dedupe rule of later bins) | number of first-bin segments (bits 16-31, 0..256;
-//       the later-bin segments follow them)
+//       (bits 8-15, 0..128: the dedupe rule of later bins) | number of first-bin segments (bits 16-22, 0..64;
+//       the later-bin segments follow them) | number of segments (bits 24-30, 1..64)
 __global__ void __launch_bounds__(256) k_item_fill(DbView db, const uint32_t *__restrict__ seg_off,
                                                     const uint32_t *__restrict__ seg_mid,
+                                                    const uint32_t *__restrict__ cnt2,
                                                     const uint32_t *__restrict__ item_off,
                                                     const unsigned long long *__restrict__ tot,
                                                     unsigned long long seg_cap, unsigned long long item_cap,
@@ -384,11 +386,16 @@ __global__ void __launch_bounds__(256) k_item_fill(DbView db, const uint32_t *__
 {
     if (tot[0] > seg_cap || tot[1] > item_cap) return;
     const int lane = threadIdx.x & 31;
+    if (blockIdx.x == 0 && threadIdx.x < 32) {                  // empty items up to a multiple of 32
+        const unsigned long long k = tot[1] + threadIdx.x;
+        if (k < ((tot[1] + 31) & ~31ull)) items[k] = make_int4(0, 0, 0, 0);
+    }
     const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
     for (int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < db.ntiles; t += nw) {
         const uint32_t i0 = __ldg(&item_off[t]), ni = __ldg(&item_off[t + 1]) - i0;
         if (ni == 0) continue;
-        const uint32_t a = __ldg(&seg_off[t]), b = __ldg(&seg_off[t + 1]), mid = __ldg(&seg_mid[t]);
+        const uint32_t a = __ldg(&seg_off[t]), mid = __ldg(&seg_mid[t]);
+        const uint32_t b = mid + __ldg(&cnt2[2 * t + 1]);
         const int4 tm = __ldg(reinterpret_cast<const int4 *>(&db.tiles[t]));
         const uint32_t ch = (b - a + SMAX - 1) / SMAX;
         for (uint32_t k = lane; k < ni; k += 32) {
@@ -399,7 +406,7 @@ __global__ void __launch_bounds__(256) k_item_fill(DbView db, const uint32_t *__
             const uint32_t tsr = (uint32_t)min(max(tm.z - r0, 0), GROUP);
             const uint32_t nfirst = min(max(mid, sa), sb) - sa;
             items[i0 + k] = make_int4((int)((uint32_t)tm.x + g * (GROUP / 4)), (int)sa, (int)sb,
-                                      (int)(nv | (tsr << 8) | (nfirst << 16)));
+                                      (int)(nv | (tsr << 8) | (nfirst << 16) | ((sb - sa) << 24)));
         }
     }
 }
@@ -422,28 +429,35 @@ struct CountArgs {
 
 constexpr int IMAX = 0x7fffffff, IMIN = -0x7fffffff - 1;
 constexpr int COUNT_T = 256;            // threads per CTA of k_count_items
+constexpr int COUNT_K = 4;              // pipeline stages per warp
 
-template <bool V>
-struct ItemRegs {                       // one lane's share of an item, as loaded: 4 records + 1 segment
-    int4 d;                             // the item (see k_item_fill)
-    int4 S, E, I, VV;
-    CSeg q;
-};
-
-// Issue the loads of item r.d.  Slots past the group's records keep (IMAX, IMIN): they can match no query; so
-// do the pad records inside the tile's last block of 4 (written as (IMAX, IMIN) at upload).
-template <bool V>
-__device__ __forceinline__ void load_item(const DbView &db, const CSeg *__restrict__ segs, int lane, ItemRegs<V> &r)
+// ---- asynchronous copies (cp.async -> LDGSTS), shared::cta addresses as 32-bit ------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
 {
-    r.S = make_int4(IMAX, IMAX, IMAX, IMAX), r.E = make_int4(IMIN, IMIN, IMIN, IMIN);
-    r.I = make_int4(0, 0, 0, 0), r.VV = make_int4(0, 0, 0, 0);
-    if (lane * 4 < (r.d.w & 0xff)) {
-        const int64_t p = (int64_t)(uint32_t)r.d.x * 4 + lane * 4;
-        r.S = ldg4(db.start + p), r.E = ldg4(db.end + p), r.I = ldg4(db.idx + p);
-        if (V) r.VV = ldg4(db.value + p);
-    }
-    r.q = CSeg{IMAX, IMIN};
-    if ((uint32_t)r.d.y + lane < (uint32_t)r.d.z) r.q = segs[(uint32_t)r.d.y + lane];
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ int4 lds128(uint32_t addr)
+{
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int2 lds64(uint32_t addr)
+{
+    int2 v;
+    asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
 }
 
 // c += (s < qe && e > qs)
@@ -455,120 +469,168 @@ __device__ __forceinline__ void count_if(int &c, int s, int e, int qs, int qe)
 }
 
 // the segments selected by mask m (lanes of q) against this lane's 4 records
-__device__ __forceinline__ void count_segments(unsigned m, const CSeg &q, const int (&s)[4], const int (&e)[4],
+__device__ __forceinline__ void count_segments(unsigned m, const int2 &q, const int (&s)[4], const int (&e)[4],
                                                int (&c)[4])
 {
     while (m) {
         const int src = __ffs(m) - 1;
         m &= m - 1;
-        const int qs = __shfl_sync(FULL, q.qs, src), qe = __shfl_sync(FULL, q.qe, src);
+        const int qs = __shfl_sync(FULL, q.x, src), qe = __shfl_sync(FULL, q.y, src);
 #pragma unroll
         for (int k = 0; k < 4; ++k) count_if(c[k], s[k], e[k], qs, qe);
     }
 }
 
-template <bool V, bool SMEM>
-__device__ __forceinline__ void count_item(const CountArgs &a, const ItemRegs<V> &r, int lane, uint32_t hist_s)
-{
-    int s[4] = {r.S.x, r.S.y, r.S.z, r.S.w}, e[4] = {r.E.x, r.E.y, r.E.z, r.E.w};
-    const int f[4] = {r.I.x, r.I.y, r.I.z, r.I.w};
-    int c[4] = {0, 0, 0, 0};
-    if (V) {
-        const int vv[4] = {r.VV.x, r.VV.y, r.VV.z, r.VV.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (vv[k] < a.v) s[k] = IMAX;                       // filtered out by -v: matches no query
+// Shared memory of a CTA: [histogram, nfiles x u32, rounded to 128 B] then per warp K stages of
+//   { start[128] | end[128] | idx[128] | (value[128]) | 64 segments x 8 B }   -- the records and segments of one item
+template <bool V>
+struct CountSmem {
+    static constexpr uint32_t ARR = GROUP * 4;                          // one SoA array of a stage
+    static constexpr uint32_t QOFF = (V ? 4 : 3) * ARR;
+    static constexpr uint32_t STAGE = QOFF + SMAX * 8;
+    static constexpr uint32_t WARP = COUNT_K * STAGE;
+    static size_t cta_bytes(int nfiles, bool smem_hist)
+    {
+        return (smem_hist ? ((size_t)nfiles * 4 + 127) / 128 * 128 : 0) + (size_t)(COUNT_T / 32) * WARP;
     }
-    const int smin = min(min(s[0], s[1]), min(s[2], s[3]));
-    const int wsmin = V ? __reduce_min_sync(FULL, smin) : __shfl_sync(FULL, s[0], 0);   // sorted by start
-    const int emax = __reduce_max_sync(FULL, max(max(e[0], e[1]), max(e[2], e[3])));
-    const uint32_t A = (uint32_t)r.d.y, B = (uint32_t)r.d.z;
-    const uint32_t M = A + ((uint32_t)r.d.w >> 16);            // first-bin segments [A, M), later-bin [M, B)
-    // first-bin segments: every record of the tile is a candidate
-    if (M > A) {
-        CSeg q = r.q;
-        for (uint32_t sb = A;;) {
-            const unsigned m = __ballot_sync(FULL, sb + lane < M && q.qe > wsmin && q.qs < emax);
-            count_segments(m, q, s, e, c);
-            sb += 32;
-            if (sb >= M) break;
-            q = CSeg{IMAX, IMIN};
-            if (sb + lane < M) q = a.segs[sb + lane];
-        }
-    }
-    // later-bin segments: only records that start inside this bin (index >= tS, src/igd_search.c:510-511,522)
-    if (B > M) {
-        const int tsr = (r.d.w >> 8) & 0xff;
-        int sl[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) sl[k] = lane * 4 + k >= tsr ? s[k] : IMAX;
-        const int wslmin = __reduce_min_sync(FULL, min(min(sl[0], sl[1]), min(sl[2], sl[3])));
-        if (wslmin != IMAX) {
-            const uint32_t b0 = A + ((M - A) & ~31u);           // 32-aligned (from A) batch holding segment M
-            CSeg q = r.q;
-            for (uint32_t sb = b0;;) {
-                if (sb != A) {
-                    q = CSeg{IMAX, IMIN};
-                    if (sb + lane < B) q = a.segs[sb + lane];
-                }
-                const unsigned m =
-                    __ballot_sync(FULL, sb + lane >= M && sb + lane < B && q.qe > wslmin && q.qs < emax);
-                count_segments(m, q, sl, e, c);
-                sb += 32;
-                if (sb >= B) break;
-            }
-        }
-    }
-    // hits[idx] += count: one atomic per record that overlaps anything
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (SMEM) {
-            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %1, 0;\n\t@p red.shared.add.u32 [%0], %1;\n\t}"
-                         :
-                         : "r"(hist_s + 4u * (uint32_t)f[k]), "r"(c[k])
-                         : "memory");
-        } else if (c[k]) {
-            atomicAdd(&a.hits[f[k]], (unsigned long long)c[k]);
-        }
-    }
-}
+};
 
+// The count-mode search kernel.  Each warp owns blocks of 32 consecutive items (block b of warp w is items
+// [32 (b NW + w), +32); lane j keeps descriptor j of the current and of the next block in registers) and runs a
+// private K-stage asynchronous-copy ring over them: K items ahead of the one being evaluated, every lane
+// cp.async's ITS OWN 4 records of each SoA array (16 B each) and its own one or two segments into its own slots
+// of the stage, so no lane ever reads another lane's bytes and the ring needs no barrier at all -- a lane's
+// cp.async.wait_group covers exactly the bytes it is about to read.  K x 1.5 KB per warp are in flight, which
+// is what keeps HBM busy at 128 records per item.
 template <bool V, bool SMEM>
 __global__ void __launch_bounds__(COUNT_T, 3) k_count_items(const CountArgs a)
 {
-    extern __shared__ uint32_t hist[];
+    using L = CountSmem<V>;
+    extern __shared__ __align__(128) unsigned char smem[];
     const DbView &db = a.db;
+    uint32_t *hist = reinterpret_cast<uint32_t *>(smem);
+    const uint32_t hist_bytes = SMEM ? ((uint32_t)db.nfiles * 4 + 127) / 128 * 128 : 0;
     if (SMEM) {
         for (int f = threadIdx.x; f < db.nfiles; f += blockDim.x) hist[f] = 0;
         __syncthreads();
     }
-    const uint32_t hist_s = (uint32_t)__cvta_generic_to_shared(hist);
-    const int lane = threadIdx.x & 31, W = blockDim.x >> 5;
+    const uint32_t hist_s = smem_u32(smem);
+    const int lane = threadIdx.x & 31, W = blockDim.x >> 5, wib = threadIdx.x >> 5;
+    const uint32_t wbase = hist_s + hist_bytes + (uint32_t)wib * L::WARP;
     const unsigned long long nseg = __ldg(&a.tot[0]), nit = __ldg(&a.tot[1]);
     const uint32_t n_items = (nseg > a.seg_cap || nit > a.item_cap) ? 0u : (uint32_t)nit;
-    const uint32_t stride = gridDim.x * W;
-    uint32_t it = blockIdx.x * W + (threadIdx.x >> 5);
-    // Software pipeline over this warp's items, two register sets (ra, rb) alternating: while an item is
-    // evaluated, the records and first 32 segments of the next one and the descriptor of the one after it are
-    // in flight.
+    const uint32_t nblk = (n_items + 31) >> 5, NW = gridDim.x * W, w = blockIdx.x * W + wib;
+    const uint32_t nb = w < nblk ? (nblk - w + NW - 1) / NW : 0;       // blocks of this warp
+    const uint32_t N = nb * 32;                                         // item slots of this warp
+
     const int4 zero = make_int4(0, 0, 0, 0);
-    ItemRegs<V> ra, rb;
-    ra.d = it < n_items ? __ldg(&a.items[it]) : zero;
-    rb.d = it + stride < n_items ? __ldg(&a.items[it + stride]) : zero;
-    load_item<V>(db, a.segs, lane, ra);
-    while (it < n_items) {
-        load_item<V>(db, a.segs, lane, rb);
-        const int4 da = it + 2 * stride < n_items ? __ldg(&a.items[it + 2 * stride]) : zero;
-        count_item<V, SMEM>(a, ra, lane, hist_s);
-        ra.d = da;
-        it += stride;
-        if (it >= n_items) break;
-        load_item<V>(db, a.segs, lane, ra);
-        const int4 dbn = it + 2 * stride < n_items ? __ldg(&a.items[it + 2 * stride]) : zero;
-        count_item<V, SMEM>(a, rb, lane, hist_s);
-        rb.d = dbn;
-        it += stride;
+    // descriptor j of block 0 / block 1 of this warp (the item array is padded to a multiple of 32)
+    int4 dcur = nb > 0 ? __ldg(&a.items[(size_t)w * 32 + lane]) : zero;
+    int4 dnxt = nb > 1 ? __ldg(&a.items[(size_t)(NW + w) * 32 + lane]) : zero;
+
+    // issue the copies of item slot n (descriptor in lane n % 32 of dd) into stage n % K; one group per slot
+    auto issue = [&](uint32_t n, const int4 &dd) {
+        const int j = n & 31;
+        const uint32_t x = __shfl_sync(FULL, dd.x, j), y = __shfl_sync(FULL, dd.y, j), wd = __shfl_sync(FULL, dd.w, j);
+        const uint32_t sa = wbase + (n % COUNT_K) * L::STAGE;
+        const int nv = wd & 0xff, ns = (wd >> 24) & 0x7f;
+        if (lane * 4 < nv) {
+            const int64_t p = (int64_t)x * 4 + lane * 4;
+            cp_async16(sa + lane * 16, db.start + p);
+            cp_async16(sa + L::ARR + lane * 16, db.end + p);
+            cp_async16(sa + 2 * L::ARR + lane * 16, db.idx + p);
+            if (V) cp_async16(sa + 3 * L::ARR + lane * 16, db.value + p);
+        }
+        if (lane < ns) cp_async8(sa + L::QOFF + lane * 8, a.segs + y + lane);
+        if (lane + 32 < ns) cp_async8(sa + L::QOFF + 256 + lane * 8, a.segs + y + 32 + lane);
+    };
+
+#pragma unroll
+    for (int n = 0; n < COUNT_K - 1; ++n) {                             // prologue: slots 0 .. K-2 (block 0)
+        if ((uint32_t)n < N) issue(n, dcur);
+        cp_async_commit();
     }
+
+    for (uint32_t n = 0; n < N; ++n) {
+        const int j = n & 31;
+        // slot n + K - 1 goes into the stage that slot n - 1 has just released
+        {
+            const uint32_t m = n + COUNT_K - 1;
+            if (m < N) {
+                if ((m >> 5) == (n >> 5)) issue(m, dcur);
+                else issue(m, dnxt);
+            }
+            cp_async_commit();
+        }
+        cp_async_wait<COUNT_K - 1>();                                   // slot n has landed (this lane's bytes)
+        const uint32_t wd = __shfl_sync(FULL, dcur.w, j);
+        const uint32_t sa = wbase + (n % COUNT_K) * L::STAGE;
+        const int nv = wd & 0xff, ns = (wd >> 24) & 0x7f, nf = (wd >> 16) & 0x7f;
+        if (nv) {
+            // this lane's 4 records; a slot past the group's end keeps (IMAX, IMIN) and can match no query, and
+            // so do the pad records inside the tile's last block of 4 (written as (IMAX, IMIN) at upload)
+            int s[4] = {IMAX, IMAX, IMAX, IMAX}, e[4] = {IMIN, IMIN, IMIN, IMIN}, f[4] = {0, 0, 0, 0};
+            int c[4] = {0, 0, 0, 0};
+            if (lane * 4 < nv) {
+                const int4 S = lds128(sa + lane * 16), E = lds128(sa + L::ARR + lane * 16);
+                const int4 I = lds128(sa + 2 * L::ARR + lane * 16);
+                s[0] = S.x, s[1] = S.y, s[2] = S.z, s[3] = S.w;
+                e[0] = E.x, e[1] = E.y, e[2] = E.z, e[3] = E.w;
+                f[0] = I.x, f[1] = I.y, f[2] = I.z, f[3] = I.w;
+                if (V) {
+                    const int4 VV = lds128(sa + 3 * L::ARR + lane * 16);
+                    if (VV.x < a.v) s[0] = IMAX;                        // filtered out by -v: matches no query
+                    if (VV.y < a.v) s[1] = IMAX;
+                    if (VV.z < a.v) s[2] = IMAX;
+                    if (VV.w < a.v) s[3] = IMAX;
+                }
+            }
+            int2 q0 = make_int2(IMAX, IMIN), q1 = make_int2(IMAX, IMIN);    // segments lane and 32 + lane of the item
+            if (lane < ns) q0 = lds64(sa + L::QOFF + lane * 8);
+            if (lane + 32 < ns) q1 = lds64(sa + L::QOFF + 256 + lane * 8);
+            const int smin = min(min(s[0], s[1]), min(s[2], s[3]));
+            const int wsmin = V ? __reduce_min_sync(FULL, smin) : __shfl_sync(FULL, s[0], 0);     // sorted by start
+            const int emax = __reduce_max_sync(FULL, max(max(e[0], e[1]), max(e[2], e[3])));
+            // first-bin segments [0, nf): every record of the tile is a candidate
+            if (nf > 0) {
+                count_segments(__ballot_sync(FULL, lane < nf && q0.y > wsmin && q0.x < emax), q0, s, e, c);
+                if (nf > 32) count_segments(__ballot_sync(FULL, lane + 32 < nf && q1.y > wsmin && q1.x < emax), q1, s, e, c);
+            }
+            // later-bin segments [nf, ns): only records that start inside this bin (index >= tS,
+            // src/igd_search.c:510-511,522)
+            if (ns > nf) {
+                const int tsr = (wd >> 8) & 0xff;
+                int sl[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) sl[k] = lane * 4 + k >= tsr ? s[k] : IMAX;
+                const int wslmin = __reduce_min_sync(FULL, min(min(sl[0], sl[1]), min(sl[2], sl[3])));
+                if (wslmin != IMAX) {
+                    if (nf < 32)
+                        count_segments(__ballot_sync(FULL, lane >= nf && q0.y > wslmin && q0.x < emax), q0, sl, e, c);
+                    if (ns > 32)
+                        count_segments(__ballot_sync(FULL, lane + 32 >= nf && q1.y > wslmin && q1.x < emax), q1, sl, e, c);
+                }
+            }
+            // hits[idx] += count: one atomic per record that overlaps anything
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (SMEM) {
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %1, 0;\n\t@p red.shared.add.u32 [%0], %1;\n\t}"
+                                 :
+                                 : "r"(hist_s + 4u * (uint32_t)f[k]), "r"(c[k])
+                                 : "memory");
+                } else if (c[k]) {
+                    atomicAdd(&a.hits[f[k]], (unsigned long long)c[k]);
+                }
+            }
+        }
+        if (j == 31) {                                                  // next block of descriptors
+            dcur = dnxt;
+            const uint32_t b2 = (n >> 5) + 2;
+            dnxt = b2 < nb ? __ldg(&a.items[(size_t)(b2 * NW + w) * 32 + lane]) : zero;
+        }
+    }
+    cp_async_wait<0>();
     if (SMEM) {
         __syncthreads();
         for (int f = threadIdx.x; f < db.nfiles; f += blockDim.x) {
@@ -918,16 +980,17 @@ int build_segments(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_t *qs
 template <bool V>
 int count_geometry(igdb_dev *d, int *grid, size_t *shm, bool *smem)
 {
-    const size_t hist_bytes = (size_t)d->nfiles * sizeof(uint32_t);
-    *smem = hist_bytes <= 200 * 1024;
-    *shm = *smem ? hist_bytes : 0;
+    // the shared histogram is used while it leaves room for the pipelines of at least one CTA
+    *smem = CountSmem<V>::cta_bytes(d->nfiles, true) <= 200 * 1024;
+    *shm = CountSmem<V>::cta_bytes(d->nfiles, *smem);
     if (d->count_grid[V] == 0) {
         int per_sm = 0;
         if (*smem) {
             CK(cudaFuncSetAttribute(k_count_items<V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*shm));
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_count_items<V, true>, COUNT_T, *shm));
         } else {
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_count_items<V, false>, COUNT_T, 0));
+            CK(cudaFuncSetAttribute(k_count_items<V, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*shm));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_count_items<V, false>, COUNT_T, *shm));
         }
         d->count_grid[V] = d->sm_count * std::max(per_sm, 1);
     }
@@ -935,9 +998,11 @@ int count_geometry(igdb_dev *d, int *grid, size_t *shm, bool *smem)
     return 0;
 }
 
-// a CTA's shared histogram is uint32: an item adds at most GROUP*SMAX = 2^15, a CTA takes at most
-// items/grid + COUNT_T/32 items, so this many items per launch cannot overflow a counter
-int64_t item_limit(const igdb_dev *d, int grid) { return ((int64_t)(1 << 17) - 64) * grid; }
+// a CTA's shared histogram is uint32: an item adds at most GROUP*SMAX = 2^13, a CTA takes at most
+// items/grid + 32*COUNT_T/32 items, so this many items per launch cannot overflow a counter
+int64_t item_limit(const igdb_dev *d, int grid) { return ((int64_t)(1 << 19) - 512) * grid; }
+// the kernels may touch up to 32 descriptors / 1 segment past the plan's totals (padding)
+constexpr int64_t CAP_SLACK = 64;
 
 template <bool V>
 int enqueue_count(igdb_dev *d, const igdb_dev::Pending &p)
@@ -948,11 +1013,12 @@ int enqueue_count(igdb_dev *d, const igdb_dev::Pending &p)
     size_t shm = 0;
     bool smem = false;
     if (count_geometry<V>(d, &grid, &shm, &smem)) return -1;
-    if (grow(&d->csegs, &d->cseg_cap, std::max<int64_t>(2 * p.n, 4096), 1, 1)) return -1;
+    if (grow(&d->csegs, &d->cseg_cap, std::max<int64_t>(2 * p.n + 2 * d->T, 4096), 1, 1)) return -1;
     if (grow(&d->items, &d->item_cap, std::min<int64_t>(d->db_groups + p.n / 64, item_limit(d, grid)) + 1024, 1, 1))
         return -1;
-    const unsigned long long seg_cap = (unsigned long long)std::min<int64_t>(d->cseg_cap, 0x7fffffff);
-    const unsigned long long item_cap = (unsigned long long)std::min<int64_t>(d->item_cap, item_limit(d, grid));
+    const unsigned long long seg_cap = (unsigned long long)std::min<int64_t>(d->cseg_cap - CAP_SLACK, 0x7fffffff);
+    const unsigned long long item_cap =
+        (unsigned long long)std::min<int64_t>(d->item_cap - CAP_SLACK, item_limit(d, grid));
     const int thr = 256;
     const int nb = (int)((p.n + thr - 1) / thr);
     const int sb = (d->T + SCAN_B - 1) / SCAN_B;
@@ -963,16 +1029,17 @@ int enqueue_count(igdb_dev *d, const igdb_dev::Pending &p)
                                     d->item_off, d->plan_tot);
     CK(cudaMemcpyAsync((void *)d->h_plan, d->plan_tot, 16, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(d->plan_ev, st));
+    // (the fill reads the later-bin counters that the scatter counts back down to zero)
+    k_item_fill<<<d->sm_count * 8, 256, 0, st>>>(db, d->cseg_off, d->cseg_mid, d->cnt2, d->item_off, d->plan_tot,
+                                                  seg_cap, item_cap, d->items);
     k_cseg_scatter<V><<<nb, thr, 0, st>>>(db, p.n, p.ctg, p.qs, p.qe, d->cnt2, d->cseg_off, d->cseg_mid,
                                            d->plan_tot, seg_cap, item_cap, d->csegs);
-    k_item_fill<<<d->sm_count * 8, 256, 0, st>>>(db, d->cseg_off, d->cseg_mid, d->item_off, d->plan_tot, seg_cap,
-                                                  item_cap, d->items);
     CountArgs a{};
     a.db = db, a.items = d->items, a.segs = d->csegs, a.tot = d->plan_tot;
     a.seg_cap = seg_cap, a.item_cap = item_cap, a.v = p.v, a.hits = p.hits;
     CK(cudaEventRecord(d->kev[0], st));
     if (smem) k_count_items<V, true><<<grid, COUNT_T, shm, st>>>(a);
-    else k_count_items<V, false><<<grid, COUNT_T, 0, st>>>(a);
+    else k_count_items<V, false><<<grid, COUNT_T, shm, st>>>(a);
     CK(cudaEventRecord(d->kev[1], st));
     d->kev_valid = true;
     d->launches += 7;
@@ -994,8 +1061,8 @@ int settle_count(igdb_dev *d, const igdb_dev::Pending &p)
         CK(cudaEventSynchronize(d->plan_ev));
         const unsigned long long nsegs = d->h_plan[0], nitems = d->h_plan[1];
         const int64_t lim = item_limit(d, d->count_grid[p.mode_v]);
-        if (nsegs <= (unsigned long long)std::min<int64_t>(d->cseg_cap, 0x7fffffff) &&
-            nitems <= (unsigned long long)std::min<int64_t>(d->item_cap, lim))
+        if (nsegs <= (unsigned long long)std::min<int64_t>(d->cseg_cap - CAP_SLACK, 0x7fffffff) &&
+            nitems <= (unsigned long long)std::min<int64_t>(d->item_cap - CAP_SLACK, lim))
             return 0;
         // none of this batch's kernels wrote anything, but its segment counters were not counted back down
         CK(cudaStreamSynchronize(p.st));
@@ -1011,7 +1078,9 @@ int settle_count(igdb_dev *d, const igdb_dev::Pending &p)
             if (enqueue_count(d, a) || settle_count(d, a) || enqueue_count(d, b) || settle_count(d, b)) return -1;
             return 0;
         }
-        if (grow(&d->csegs, &d->cseg_cap, (int64_t)nsegs) || grow(&d->items, &d->item_cap, (int64_t)nitems)) return -1;
+        if (grow(&d->csegs, &d->cseg_cap, (int64_t)nsegs + CAP_SLACK) ||
+            grow(&d->items, &d->item_cap, (int64_t)nitems + CAP_SLACK))
+            return -1;
         if (enqueue_count(d, p)) return -1;
     }
 }
