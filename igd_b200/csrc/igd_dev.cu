@@ -179,7 +179,7 @@ __global__ void k_seg_scatter(DbView db, int64_t n, const int32_t *__restrict__ 
 // ------------------------------------------------------------------------------------------------
 // exclusive scan (three small kernels; n up to ~1e8).  out has n+1 entries, out[n] = total.
 // ------------------------------------------------------------------------------------------------
-constexpr int SCAN_T = 512, SCAN_I = 8, SCAN_B = SCAN_T * SCAN_I;
+constexpr int SCAN_T = 512, SCAN_I = 2, SCAN_B = SCAN_T * SCAN_I;
 
 // two running sums scanned together: segments and work items per tile
 struct Plan {
@@ -279,7 +279,8 @@ __global__ void __launch_bounds__(SCAN_T) k_scan3(Tout *__restrict__ out, int64_
 // yields, per tile, where its segments start (seg_off), where its later-bin segments start (seg_mid) and where
 // its work items start (item_off); a tile with s segments and n records has ceil(n/GROUP) * ceil(s/SMAX) items.
 // ------------------------------------------------------------------------------------------------
-constexpr int GROUP = 128;      // records per item: 4 per lane
+constexpr int SUB = 2;          // 128-record sub-groups per item
+constexpr int GROUP = 128 * SUB; // records per item: a warp evaluates them 128 (4 per lane) at a time
 constexpr int SMAX = 64;        // segments per item: what one pipeline stage holds (hot tiles get many items)
 
 struct __align__(8) CSeg {       // count-mode segment: the query's interval, nothing else
@@ -372,10 +373,11 @@ __global__ void k_cseg_scatter(DbView db, int64_t n, const int32_t *__restrict__
 // Work items of tile t, group-major.  An item is self-contained, so the search kernel goes from the item to
 // its records and segments without touching the tile table:
 //   x = position of the group's first record in the SoA arrays, in units of 4 records
-//   y = first segment (z = one past the last, kept for debugging)
-//   w = records in the group (bits 0-7, 1..128) | first record of the group that starts inside this bin
-//       (bits 8-15, 0..128: the dedupe rule of later bins) | number of first-bin segments (bits 16-22, 0..64;
-//       the later-bin segments follow them) | number of segments (bits 24-30, 1..64)
+//   y = first segment
+//   z = records in the group (bits 0-15, 1..GROUP) | first record of the group that starts inside this bin
+//       (bits 16-31, 0..GROUP: the dedupe rule of later bins)
+//   w = number of first-bin segments (bits 0-7, 0..64; the later-bin segments follow them) | number of
+//       segments (bits 8-15, 1..64)
 __global__ void __launch_bounds__(256) k_item_fill(DbView db, const uint32_t *__restrict__ seg_off,
                                                     const uint32_t *__restrict__ seg_mid,
                                                     const uint32_t *__restrict__ cnt2,
@@ -390,24 +392,39 @@ __global__ void __launch_bounds__(256) k_item_fill(DbView db, const uint32_t *__
         const unsigned long long k = tot[1] + threadIdx.x;
         if (k < ((tot[1] + 31) & ~31ull)) items[k] = make_int4(0, 0, 0, 0);
     }
-    const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < db.ntiles; t += nw) {
-        const uint32_t i0 = __ldg(&item_off[t]), ni = __ldg(&item_off[t + 1]) - i0;
-        if (ni == 0) continue;
-        const uint32_t a = __ldg(&seg_off[t]), mid = __ldg(&seg_mid[t]);
-        const uint32_t b = mid + __ldg(&cnt2[2 * t + 1]);
-        const int4 tm = __ldg(reinterpret_cast<const int4 *>(&db.tiles[t]));
-        const uint32_t ch = (b - a + SMAX - 1) / SMAX;
-        for (uint32_t k = lane; k < ni; k += 32) {
-            const uint32_t g = k / ch, c = k - g * ch;
-            const uint32_t sa = a + c * SMAX, sb = min(sa + (uint32_t)SMAX, b);
-            const int r0 = (int)(g * GROUP);
-            const uint32_t nv = (uint32_t)min(tm.y - r0, GROUP);
-            const uint32_t tsr = (uint32_t)min(max(tm.z - r0, 0), GROUP);
-            const uint32_t nfirst = min(max(mid, sa), sb) - sa;
-            items[i0 + k] = make_int4((int)((uint32_t)tm.x + g * (GROUP / 4)), (int)sa, (int)sb,
-                                      (int)(nv | (tsr << 8) | (nfirst << 16) | ((sb - sa) << 24)));
+    // a thread per tile writes up to 32 items itself; tiles with more are then done by the whole warp
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t i0 = 0, ni = 0, sa0 = 0, mid = 0, sb0 = 0;
+    int4 tm = make_int4(0, 0, 0, 0);
+    if (t < db.ntiles) {
+        i0 = __ldg(&item_off[t]), ni = __ldg(&item_off[t + 1]) - i0;
+        if (ni) {
+            sa0 = __ldg(&seg_off[t]), mid = __ldg(&seg_mid[t]), sb0 = mid + __ldg(&cnt2[2 * t + 1]);
+            tm = __ldg(reinterpret_cast<const int4 *>(&db.tiles[t]));
         }
+    }
+    auto write = [&](uint32_t k, uint32_t i0_, uint32_t a, uint32_t m, uint32_t b, int4 tm_) {
+        const uint32_t ch = (b - a + SMAX - 1) / SMAX;
+        const uint32_t g = k / ch, c = k - g * ch;
+        const uint32_t sa = a + c * SMAX, sb = min(sa + (uint32_t)SMAX, b);
+        const int r0 = (int)(g * GROUP);
+        const uint32_t nv = (uint32_t)min(tm_.y - r0, GROUP);
+        const uint32_t tsr = (uint32_t)min(max(tm_.z - r0, 0), GROUP);
+        const uint32_t nfirst = min(max(m, sa), sb) - sa;
+        items[i0_ + k] = make_int4((int)((uint32_t)tm_.x + g * (GROUP / 4)), (int)sa, (int)(nv | (tsr << 16)),
+                                   (int)(nfirst | ((sb - sa) << 8)));
+    };
+    if (ni <= 32)
+        for (uint32_t k = 0; k < ni; ++k) write(k, i0, sa0, mid, sb0, tm);
+    unsigned heavy = __ballot_sync(FULL, ni > 32);
+    while (heavy) {
+        const int src = __ffs(heavy) - 1;
+        heavy &= heavy - 1;
+        const uint32_t i0_ = __shfl_sync(FULL, i0, src), ni_ = __shfl_sync(FULL, ni, src);
+        const uint32_t a_ = __shfl_sync(FULL, sa0, src), m_ = __shfl_sync(FULL, mid, src), b_ = __shfl_sync(FULL, sb0, src);
+        const int4 tm_ = make_int4(__shfl_sync(FULL, tm.x, src), __shfl_sync(FULL, tm.y, src),
+                                   __shfl_sync(FULL, tm.z, src), 0);
+        for (uint32_t k = lane; k < ni_; k += 32) write(k, i0_, a_, m_, b_, tm_);
     }
 }
 
@@ -428,8 +445,8 @@ struct CountArgs {
 };
 
 constexpr int IMAX = 0x7fffffff, IMIN = -0x7fffffff - 1;
-constexpr int COUNT_T = 256;            // threads per CTA of k_count_items
-constexpr int COUNT_K = 4;              // pipeline stages per warp
+constexpr int COUNT_MAXW = 24;          // most warps per CTA of k_count_items (register budget: 65536 / 768 = 85)
+constexpr int COUNT_K = 3;              // pipeline stages per warp
 
 // ---- asynchronous copies (cp.async -> LDGSTS), shared::cta addresses as 32-bit ------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -482,28 +499,36 @@ __device__ __forceinline__ void count_segments(unsigned m, const int2 &q, const 
 }
 
 // Shared memory of a CTA: [histogram, nfiles x u32, rounded to 128 B] then per warp K stages of
-//   { start[128] | end[128] | idx[128] | (value[128]) | 64 segments x 8 B }   -- the records and segments of one item
+//   { start[GROUP] | end[GROUP] | idx[GROUP] | (value[GROUP]) | 64 segments x 8 B }  -- the records and segments of
+// one item.  Inside an array, sub-group h (records 128 h .. 128 h + 127) is the 512-byte run at 512 h.
 template <bool V>
 struct CountSmem {
     static constexpr uint32_t ARR = GROUP * 4;                          // one SoA array of a stage
     static constexpr uint32_t QOFF = (V ? 4 : 3) * ARR;
     static constexpr uint32_t STAGE = QOFF + SMAX * 8;
     static constexpr uint32_t WARP = COUNT_K * STAGE;
-    static size_t cta_bytes(int nfiles, bool smem_hist)
+    static size_t hist_bytes(int nfiles) { return ((size_t)nfiles * 4 + 127) / 128 * 128; }
+    // warps of the (single) CTA of an SM: as many pipelines as fit beside the histogram
+    static int warps(int nfiles, bool smem_hist)
     {
-        return (smem_hist ? ((size_t)nfiles * 4 + 127) / 128 * 128 : 0) + (size_t)(COUNT_T / 32) * WARP;
+        const size_t room = 226 * 1024 - (smem_hist ? hist_bytes(nfiles) : 0);
+        return (int)std::min<size_t>(room / WARP, COUNT_MAXW);
+    }
+    static size_t cta_bytes(int nfiles, bool smem_hist, int nwarps)
+    {
+        return (smem_hist ? hist_bytes(nfiles) : 0) + (size_t)nwarps * WARP;
     }
 };
 
-// The count-mode search kernel.  Each warp owns blocks of 32 consecutive items (block b of warp w is items
-// [32 (b NW + w), +32); lane j keeps descriptor j of the current and of the next block in registers) and runs a
-// private K-stage asynchronous-copy ring over them: K items ahead of the one being evaluated, every lane
-// cp.async's ITS OWN 4 records of each SoA array (16 B each) and its own one or two segments into its own slots
-// of the stage, so no lane ever reads another lane's bytes and the ring needs no barrier at all -- a lane's
-// cp.async.wait_group covers exactly the bytes it is about to read.  K x 1.5 KB per warp are in flight, which
-// is what keeps HBM busy at 128 records per item.
+// The count-mode search kernel: ONE CTA per SM, as many warps as shared memory has room for pipelines.  Each
+// warp owns blocks of 32 consecutive items (block b of warp w is items [32 (b NW + w), +32); lane j keeps
+// descriptor j of the current and of the next block in registers) and runs a private K-stage asynchronous-copy
+// ring over them: K - 1 items ahead of the one being evaluated, every lane cp.async's ITS OWN records of each
+// SoA array (16 B = 4 records per sub-group) and its own one or two segments into its own slots of the stage,
+// so no lane ever reads another lane's bytes and the ring needs no barrier at all -- a lane's
+// cp.async.wait_group covers exactly the bytes it is about to read.
 template <bool V, bool SMEM>
-__global__ void __launch_bounds__(COUNT_T, 3) k_count_items(const CountArgs a)
+__global__ void __launch_bounds__(COUNT_MAXW * 32, 1) k_count_items(const CountArgs a)
 {
     using L = CountSmem<V>;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -527,22 +552,29 @@ __global__ void __launch_bounds__(COUNT_T, 3) k_count_items(const CountArgs a)
     // descriptor j of block 0 / block 1 of this warp (the item array is padded to a multiple of 32)
     int4 dcur = nb > 0 ? __ldg(&a.items[(size_t)w * 32 + lane]) : zero;
     int4 dnxt = nb > 1 ? __ldg(&a.items[(size_t)(NW + w) * 32 + lane]) : zero;
+    // this lane's column of the SoA arrays and of the segment array
+    const int32_t *const pS = db.start + lane * 4, *const pE = db.end + lane * 4, *const pI = db.idx + lane * 4;
+    const int32_t *const pV = db.value + lane * 4;
+    const CSeg *const pQ = a.segs + lane;
+    const uint32_t lslot = wbase + lane * 16, qslot = wbase + L::QOFF + lane * 8;
 
-    // issue the copies of item slot n (descriptor in lane n % 32 of dd) into stage n % K; one group per slot
+    // issue the copies of item slot n (descriptor in lane n % 32 of dd) into stage n % K
     auto issue = [&](uint32_t n, const int4 &dd) {
         const int j = n & 31;
-        const uint32_t x = __shfl_sync(FULL, dd.x, j), y = __shfl_sync(FULL, dd.y, j), wd = __shfl_sync(FULL, dd.w, j);
-        const uint32_t sa = wbase + (n % COUNT_K) * L::STAGE;
-        const int nv = wd & 0xff, ns = (wd >> 24) & 0x7f;
-        if (lane * 4 < nv) {
-            const int64_t p = (int64_t)x * 4 + lane * 4;
-            cp_async16(sa + lane * 16, db.start + p);
-            cp_async16(sa + L::ARR + lane * 16, db.end + p);
-            cp_async16(sa + 2 * L::ARR + lane * 16, db.idx + p);
-            if (V) cp_async16(sa + 3 * L::ARR + lane * 16, db.value + p);
-        }
-        if (lane < ns) cp_async8(sa + L::QOFF + lane * 8, a.segs + y + lane);
-        if (lane + 32 < ns) cp_async8(sa + L::QOFF + 256 + lane * 8, a.segs + y + 32 + lane);
+        const uint32_t x = __shfl_sync(FULL, dd.x, j), y = __shfl_sync(FULL, dd.y, j);
+        const int nv = __shfl_sync(FULL, dd.z, j) & 0xffff, ns = (__shfl_sync(FULL, dd.w, j) >> 8) & 0xff;
+        const uint32_t so = (n % COUNT_K) * L::STAGE;
+        const size_t p = (size_t)x * 4;
+#pragma unroll
+        for (int h = 0; h < SUB; ++h)
+            if (h * 128 + lane * 4 < nv) {
+                cp_async16(lslot + so + h * 512, pS + p + h * 128);
+                cp_async16(lslot + so + L::ARR + h * 512, pE + p + h * 128);
+                cp_async16(lslot + so + 2 * L::ARR + h * 512, pI + p + h * 128);
+                if (V) cp_async16(lslot + so + 3 * L::ARR + h * 512, pV + p + h * 128);
+            }
+        if (lane < ns) cp_async8(qslot + so, pQ + y);
+        if (lane + 32 < ns) cp_async8(qslot + so + 256, pQ + y + 32);
     };
 
 #pragma unroll
@@ -553,7 +585,7 @@ __global__ void __launch_bounds__(COUNT_T, 3) k_count_items(const CountArgs a)
 
     for (uint32_t n = 0; n < N; ++n) {
         const int j = n & 31;
-        // slot n + K - 1 goes into the stage that slot n - 1 has just released
+        // slot n + K - 1 goes into the stage that slot n - 1 has released
         {
             const uint32_t m = n + COUNT_K - 1;
             if (m < N) {
@@ -563,31 +595,33 @@ __global__ void __launch_bounds__(COUNT_T, 3) k_count_items(const CountArgs a)
             cp_async_commit();
         }
         cp_async_wait<COUNT_K - 1>();                                   // slot n has landed (this lane's bytes)
-        const uint32_t wd = __shfl_sync(FULL, dcur.w, j);
-        const uint32_t sa = wbase + (n % COUNT_K) * L::STAGE;
-        const int nv = wd & 0xff, ns = (wd >> 24) & 0x7f, nf = (wd >> 16) & 0x7f;
-        if (nv) {
-            // this lane's 4 records; a slot past the group's end keeps (IMAX, IMIN) and can match no query, and
-            // so do the pad records inside the tile's last block of 4 (written as (IMAX, IMIN) at upload)
-            int s[4] = {IMAX, IMAX, IMAX, IMAX}, e[4] = {IMIN, IMIN, IMIN, IMIN}, f[4] = {0, 0, 0, 0};
-            int c[4] = {0, 0, 0, 0};
-            if (lane * 4 < nv) {
-                const int4 S = lds128(sa + lane * 16), E = lds128(sa + L::ARR + lane * 16);
-                const int4 I = lds128(sa + 2 * L::ARR + lane * 16);
-                s[0] = S.x, s[1] = S.y, s[2] = S.z, s[3] = S.w;
-                e[0] = E.x, e[1] = E.y, e[2] = E.z, e[3] = E.w;
-                f[0] = I.x, f[1] = I.y, f[2] = I.z, f[3] = I.w;
-                if (V) {
-                    const int4 VV = lds128(sa + 3 * L::ARR + lane * 16);
-                    if (VV.x < a.v) s[0] = IMAX;                        // filtered out by -v: matches no query
-                    if (VV.y < a.v) s[1] = IMAX;
-                    if (VV.z < a.v) s[2] = IMAX;
-                    if (VV.w < a.v) s[3] = IMAX;
-                }
+        const uint32_t dz = __shfl_sync(FULL, dcur.z, j), dw = __shfl_sync(FULL, dcur.w, j);
+        const uint32_t so = (n % COUNT_K) * L::STAGE;
+        const int nv = dz & 0xffff, tsr = dz >> 16, nf = dw & 0xff, ns = (dw >> 8) & 0xff;
+        int2 q0 = make_int2(IMAX, IMIN), q1 = make_int2(IMAX, IMIN);    // segments lane and 32 + lane of the item
+        if (lane < ns) q0 = lds64(qslot + so);
+        if (lane + 32 < ns) q1 = lds64(qslot + so + 256);
+#pragma unroll
+        for (int h = 0; h < SUB; ++h) {
+            if (h * 128 >= nv) break;
+            // this lane's 4 records of the sub-group; a slot past the group's end gets (IMAX, IMIN) and can
+            // match no query, and so do the pad records inside the tile's last block of 4 (written as
+            // (IMAX, IMIN) at upload)
+            const int r0 = h * 128 + lane * 4;
+            const bool have = r0 < nv;
+            int4 S = lds128(lslot + so + h * 512), E = lds128(lslot + so + L::ARR + h * 512);
+            const int4 I = lds128(lslot + so + 2 * L::ARR + h * 512);
+            if (V) {
+                const int4 VV = lds128(lslot + so + 3 * L::ARR + h * 512);
+                if (VV.x < a.v) S.x = IMAX;                             // filtered out by -v: matches no query
+                if (VV.y < a.v) S.y = IMAX;
+                if (VV.z < a.v) S.z = IMAX;
+                if (VV.w < a.v) S.w = IMAX;
             }
-            int2 q0 = make_int2(IMAX, IMIN), q1 = make_int2(IMAX, IMIN);    // segments lane and 32 + lane of the item
-            if (lane < ns) q0 = lds64(sa + L::QOFF + lane * 8);
-            if (lane + 32 < ns) q1 = lds64(sa + L::QOFF + 256 + lane * 8);
+            const int s[4] = {have ? S.x : IMAX, have ? S.y : IMAX, have ? S.z : IMAX, have ? S.w : IMAX};
+            const int e[4] = {have ? E.x : IMIN, have ? E.y : IMIN, have ? E.z : IMIN, have ? E.w : IMIN};
+            const int f[4] = {I.x, I.y, I.z, I.w};
+            int c[4] = {0, 0, 0, 0};
             const int smin = min(min(s[0], s[1]), min(s[2], s[3]));
             const int wsmin = V ? __reduce_min_sync(FULL, smin) : __shfl_sync(FULL, s[0], 0);     // sorted by start
             const int emax = __reduce_max_sync(FULL, max(max(e[0], e[1]), max(e[2], e[3])));
@@ -599,10 +633,9 @@ __global__ void __launch_bounds__(COUNT_T, 3) k_count_items(const CountArgs a)
             // later-bin segments [nf, ns): only records that start inside this bin (index >= tS,
             // src/igd_search.c:510-511,522)
             if (ns > nf) {
-                const int tsr = (wd >> 8) & 0xff;
                 int sl[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) sl[k] = lane * 4 + k >= tsr ? s[k] : IMAX;
+                for (int k = 0; k < 4; ++k) sl[k] = r0 + k >= tsr ? s[k] : IMAX;
                 const int wslmin = __reduce_min_sync(FULL, min(min(sl[0], sl[1]), min(sl[2], sl[3])));
                 if (wslmin != IMAX) {
                     if (nf < 32)
@@ -978,29 +1011,25 @@ int build_segments(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_t *qs
 // the plan's totals when it settles the batch and, in the rare case they did not fit (first batch of a
 // larger size), grows the buffers and runs the batch again -- or splits it when the plan itself is too big.
 template <bool V>
-int count_geometry(igdb_dev *d, int *grid, size_t *shm, bool *smem)
+int count_geometry(igdb_dev *d, int *grid, int *threads, size_t *shm, bool *smem)
 {
-    // the shared histogram is used while it leaves room for the pipelines of at least one CTA
-    *smem = CountSmem<V>::cta_bytes(d->nfiles, true) <= 200 * 1024;
-    *shm = CountSmem<V>::cta_bytes(d->nfiles, *smem);
+    // the shared histogram is used while it leaves room for at least 8 warps' pipelines
+    *smem = CountSmem<V>::warps(d->nfiles, true) >= 8;
+    const int nw = CountSmem<V>::warps(d->nfiles, *smem);
+    *shm = CountSmem<V>::cta_bytes(d->nfiles, *smem, nw);
+    *threads = nw * 32;
     if (d->count_grid[V] == 0) {
-        int per_sm = 0;
-        if (*smem) {
-            CK(cudaFuncSetAttribute(k_count_items<V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*shm));
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_count_items<V, true>, COUNT_T, *shm));
-        } else {
-            CK(cudaFuncSetAttribute(k_count_items<V, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*shm));
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_count_items<V, false>, COUNT_T, *shm));
-        }
-        d->count_grid[V] = d->sm_count * std::max(per_sm, 1);
+        if (*smem) CK(cudaFuncSetAttribute(k_count_items<V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*shm));
+        else CK(cudaFuncSetAttribute(k_count_items<V, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*shm));
+        d->count_grid[V] = d->sm_count;
     }
     *grid = d->count_grid[V];
     return 0;
 }
 
-// a CTA's shared histogram is uint32: an item adds at most GROUP*SMAX = 2^13, a CTA takes at most
-// items/grid + 32*COUNT_T/32 items, so this many items per launch cannot overflow a counter
-int64_t item_limit(const igdb_dev *d, int grid) { return ((int64_t)(1 << 19) - 512) * grid; }
+// a CTA's shared histogram is uint32: an item adds at most GROUP*SMAX <= 2^15, a CTA takes at most
+// items/grid + 32*COUNT_MAXW items, so this many items per launch cannot overflow a counter
+int64_t item_limit(const igdb_dev *d, int grid) { return ((int64_t)(1 << 17) - 1024) * grid; }
 // the kernels may touch up to 32 descriptors / 1 segment past the plan's totals (padding)
 constexpr int64_t CAP_SLACK = 64;
 
@@ -1009,10 +1038,10 @@ int enqueue_count(igdb_dev *d, const igdb_dev::Pending &p)
 {
     cudaStream_t st = p.st;
     const DbView db = d->view();
-    int grid = 0;
+    int grid = 0, threads = 0;
     size_t shm = 0;
     bool smem = false;
-    if (count_geometry<V>(d, &grid, &shm, &smem)) return -1;
+    if (count_geometry<V>(d, &grid, &threads, &shm, &smem)) return -1;
     if (grow(&d->csegs, &d->cseg_cap, std::max<int64_t>(2 * p.n + 2 * d->T, 4096), 1, 1)) return -1;
     if (grow(&d->items, &d->item_cap, std::min<int64_t>(d->db_groups + p.n / 64, item_limit(d, grid)) + 1024, 1, 1))
         return -1;
@@ -1030,7 +1059,7 @@ int enqueue_count(igdb_dev *d, const igdb_dev::Pending &p)
     CK(cudaMemcpyAsync((void *)d->h_plan, d->plan_tot, 16, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(d->plan_ev, st));
     // (the fill reads the later-bin counters that the scatter counts back down to zero)
-    k_item_fill<<<d->sm_count * 8, 256, 0, st>>>(db, d->cseg_off, d->cseg_mid, d->cnt2, d->item_off, d->plan_tot,
+    k_item_fill<<<(d->T + 255) / 256, 256, 0, st>>>(db, d->cseg_off, d->cseg_mid, d->cnt2, d->item_off, d->plan_tot,
                                                   seg_cap, item_cap, d->items);
     k_cseg_scatter<V><<<nb, thr, 0, st>>>(db, p.n, p.ctg, p.qs, p.qe, d->cnt2, d->cseg_off, d->cseg_mid,
                                            d->plan_tot, seg_cap, item_cap, d->csegs);
@@ -1038,8 +1067,8 @@ int enqueue_count(igdb_dev *d, const igdb_dev::Pending &p)
     a.db = db, a.items = d->items, a.segs = d->csegs, a.tot = d->plan_tot;
     a.seg_cap = seg_cap, a.item_cap = item_cap, a.v = p.v, a.hits = p.hits;
     CK(cudaEventRecord(d->kev[0], st));
-    if (smem) k_count_items<V, true><<<grid, COUNT_T, shm, st>>>(a);
-    else k_count_items<V, false><<<grid, COUNT_T, shm, st>>>(a);
+    if (smem) k_count_items<V, true><<<grid, threads, shm, st>>>(a);
+    else k_count_items<V, false><<<grid, threads, shm, st>>>(a);
     CK(cudaEventRecord(d->kev[1], st));
     d->kev_valid = true;
     d->launches += 7;
