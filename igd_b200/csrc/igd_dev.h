@@ -46,6 +46,11 @@ int igdb_dev_count_finish(igdb_dev *d);
 int64_t igdb_dev_full_host(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_t *qs, const int32_t *qe,
                            int64_t **query_off, int32_t **start, int32_t **end, int32_t **file);
 
+/* -s: n queries grouped by query-file chrom (grp[] ascending) and start-sorted inside a group; grp_nq[g] =
+ * queries of group g; acc[nfiles] = sum of matched similarities per file */
+int igdb_dev_seqpare(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_t *qs, const int32_t *qe,
+                     const int32_t *grp, int32_t ngroups, const int32_t *grp_nq, double *acc);
+
 /* -m */
 int64_t igdb_dev_hitsmap_host(igdb_dev *d, int32_t v, uint32_t *hitmap);
 

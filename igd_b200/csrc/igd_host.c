@@ -460,9 +460,65 @@ int64_t getMap_v(uint32_t **hitmap, int32_t v)
     return r < 0 ? 0 : r;
 }
 
+/* ---- -s: seqOverlaps (src/igd_search.c:355-451) ------------------------------------------------------
+ * Host part = the reference's query container: readBED (src/igd_base.c:628-649) keeps the lines parse_bed
+ * accepts, ailist_add (:601-626) drops s > e (as unsigned) and groups by chrom NAME in first-appearance order
+ * of the surviving lines; each group is then sorted by start (qsort + compare_qstart, :373, :23-28; glibc's
+ * qsort is a stable merge sort, reproduced here with the line ordinal as tie-break).  The device does the
+ * rest; the final ratio of :445-448 is applied here. */
+typedef struct { int32_t start, end; int64_t ord; } seq_q;
+static int seq_q_cmp(const void *a, const void *b)
+{
+    const seq_q *x = a, *y = b;
+    if (x->start != y->start) return x->start < y->start ? -1 : 1;
+    return x->ord < y->ord ? -1 : x->ord > y->ord;
+}
+
 int igd_b200_seqpare(igd_b200_t *h, const char *qFile, double *sm)
 {
-    (void)h; (void)qFile; (void)sm;
-    snprintf(g_err, sizeof g_err, "Seqpare (-s) is not implemented on the device yet");
-    return -1;
+    g_err[0] = 0;
+    igd_b200_queries *Q = igd_b200_read_bed(qFile);
+    if (!Q) { set_err("Can't open file %s", qFile); return -1; }
+    int rc = 0;
+    int32_t *gid = malloc(sizeof(int32_t) * (size_t)(Q->n_names + 1));      /* name id -> group */
+    int32_t *gname = malloc(sizeof(int32_t) * (size_t)(Q->n_names + 1));    /* group -> name id */
+    int64_t *gcnt = calloc((size_t)Q->n_names + 1, sizeof(int64_t));
+    int32_t ng = 0;
+    int64_t Nq = 0;
+    for (int k = 0; k < Q->n_names; k++) gid[k] = -1;
+    for (int64_t i = 0; i < Q->n; i++) {
+        if ((uint32_t)Q->qs[i] > (uint32_t)Q->qe[i]) continue;
+        int k = Q->name_id[i];
+        if (gid[k] < 0) { gid[k] = ng; gname[ng++] = k; }
+        gcnt[gid[k]]++;
+        Nq++;
+    }
+    int64_t *goff = malloc(sizeof(int64_t) * (size_t)(ng + 1));
+    goff[0] = 0;
+    for (int g = 0; g < ng; g++) goff[g + 1] = goff[g] + gcnt[g];
+    seq_q *L = malloc(sizeof(seq_q) * (size_t)(Nq + 1));
+    int64_t *fill = calloc((size_t)ng + 1, sizeof(int64_t));
+    for (int64_t i = 0; i < Q->n; i++) {
+        if ((uint32_t)Q->qs[i] > (uint32_t)Q->qe[i]) continue;
+        int g = gid[Q->name_id[i]];
+        seq_q *p = &L[goff[g] + fill[g]];
+        p->start = Q->qs[i], p->end = Q->qe[i], p->ord = fill[g]++;
+    }
+    int32_t *ctg = malloc(sizeof(int32_t) * (size_t)(Nq + 1)), *qs = malloc(sizeof(int32_t) * (size_t)(Nq + 1));
+    int32_t *qe = malloc(sizeof(int32_t) * (size_t)(Nq + 1)), *grp = malloc(sizeof(int32_t) * (size_t)(Nq + 1));
+    int32_t *gnq = malloc(sizeof(int32_t) * (size_t)(ng + 1));
+    for (int g = 0; g < ng; g++) {
+        qsort(L + goff[g], (size_t)gcnt[g], sizeof(seq_q), seq_q_cmp);
+        int32_t c = igd_b200_ctg_id(h, Q->names[gname[g]]);
+        gnq[g] = (int32_t)gcnt[g];
+        for (int64_t i = goff[g]; i < goff[g + 1]; i++) ctg[i] = c, qs[i] = L[i].start, qe[i] = L[i].end, grp[i] = g;
+    }
+    double *acc = calloc((size_t)h->nfiles + 1, sizeof(double));
+    if (igdb_dev_seqpare(h->dev, Nq, ctg, qs, qe, grp, ng, gnq, acc)) rc = -1;
+    else
+        for (int m = 0; m < h->nfiles; m++) sm[m] = acc[m] / ((int)Nq + h->fnr[m] - acc[m]);
+    free(acc); free(gnq); free(grp); free(qe); free(qs); free(ctg); free(fill); free(L); free(goff);
+    free(gcnt); free(gname); free(gid);
+    igd_b200_queries_free(Q);
+    return rc;
 }

@@ -82,7 +82,7 @@ def run_case(name: str, bed_dir: str, qfile: str, extra_regions=(), full_head: i
             text = text.replace(qfile, "q.bed").replace(qf, "qf.bed")
             with gzip.open(os.path.join(out, f"stdout_{key}.txt.gz"), "wt") as f:
                 f.write(text)
-            exp["cli_args"][key] = [{qfile: "q.bed", qf: "qf.bed"}.get(x, x) for x in a]
+            exp["cli_args"][key] = [{qf: "qf.bed", qfile: "q.bed"}.get(x, x) for x in a]
         with open(igd, "rb") as f, gzip.open(os.path.join(out, "db.igd.gz"), "wb", compresslevel=9) as g:
             g.write(f.read())
         shutil.copy(stem + "_index.tsv", os.path.join(out, "db_index.tsv"))

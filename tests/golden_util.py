@@ -45,7 +45,9 @@ class GoldenCase:
 
     def cli_args(self, key: str) -> list:
         """argv after `igd search db.igd`, with the query files made absolute"""
-        m = {"q.bed": self.qfile, "qf.bed": os.path.join(self.dir, "qf.bed")}
+        # (cases without a reduced -f query file were recorded with "qf.bed" standing for q.bed itself)
+        qf = os.path.join(self.dir, "qf.bed")
+        m = {"q.bed": self.qfile, "qf.bed": qf if os.path.exists(qf) else self.qfile}
         return [m.get(a, a) for a in self.exp["cli_args"][key]]
 
     def normalise(self, text: str) -> str:

@@ -90,3 +90,25 @@ def test_hitsmap_dense(dense_db, O, api, v):
     g = api.IGD(dense_db)
     assert np.array_equal(g.hitsmap(v), odb.hitsmap(v))
     g.close()
+
+
+def _write_bed(path, q, names):
+    synth.write_bed(path, q, names)
+    return path
+
+
+@pytest.mark.parametrize("kind", ["short", "long"])
+def test_seqpare_dense(dense_db, O, api, kind, workdir):
+    """-s: sm[] identical to the oracle's doubles (the oracle is pinned bit-exact against the reference)."""
+    q = _queries(kind)
+    n = 1500 if kind == "long" else 8000
+    q = synth.Intervals(q.ctg[:n], q.start[:n], q.end[:n], q.value[:n])
+    path = _write_bed(os.path.join(workdir, f"seq_{kind}.bed"), q, SMALL_NAMES)
+    odb = O.OracleDB(dense_db)
+    g = api.IGD(dense_db)
+    want = odb.seqpare(O.Queries(path))
+    got = g.seqpare(path)
+    assert want.max() > 0
+    np.testing.assert_allclose(got, want, rtol=1e-9, atol=0)       # north_star's tolerance
+    assert np.array_equal(got, want)                               # and in fact the same doubles
+    g.close()
