@@ -5,6 +5,8 @@
 
 One "step" = one pass of the hot path over the whole query batch of the workload (BASELINE.json
 configs[1] by default: 1,905 files x 50k intervals, 1M x 1 kb queries, count mode).  Prints ONE JSON line.
+With N GPUs the database is replicated and the query set is N x 1M queries (weak scaling: 1M per GPU), sorted
+by (contig, start) and cut into contiguous cost-balanced shards; hits[] is combined with one NCCL allreduce.
 
 * value  : query intervals/s, whole job, queries already resident in HBM (CUDA events, max over ranks)
 * e2e    : the same through the C-ABI call with HOST (pinned) buffers: H2D + kernels + D2H inside
@@ -87,7 +89,9 @@ def workload_setup(args, rank, world, barrier):
         build_s = time.time() - t0
     barrier()
     path = os.path.join(workdir, args.workload + ".igd")
-    q = workloads.queries(args.workload, args.queries)
+    # weak scaling: the per-GPU work is fixed -- the query set grows with the number of GPUs
+    per_gpu = args.queries or workloads.CONFIGS[args.workload]["n_queries"]
+    q = workloads.queries(args.workload, per_gpu * world)
     return path, q, (build_s if rank == 0 else 0.0)
 
 
@@ -143,7 +147,8 @@ def run_ours(args):
 
     # multi-GPU: DB replicated, (ctg,start)-sorted queries cut into cost-balanced contiguous shards
     if world > 1:
-        ctg_s, qs_s, qe_s, bounds = workloads.sort_and_shard(igd, ctg_all, qs_all, qe_all, world)
+        hdr = workloads.read_igd_header(path)
+        ctg_s, qs_s, qe_s, bounds = workloads.sort_and_shard(hdr, ctg_all, qs_all, qe_all, world)
         a, b = bounds[rank], bounds[rank + 1]
         ctg_l, qs_l, qe_l = ctg_s[a:b], qs_s[a:b], qe_s[a:b]
     else:
@@ -265,7 +270,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": n_total / (ms_per_step * 1e-3), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
             "data": "synthetic",
             "overlaps_per_s": overlaps / (ms_per_step * 1e-3), "overlaps_per_step": overlaps,
             "config": {"workload": f"{args.workload}: {workloads.CONFIGS[args.workload]['n_files']} files x "
@@ -274,8 +279,9 @@ def run_ours(args):
                        "n_records": int(igd.nrecords), "n_tiles": int(igd.ntiles), "n_queries": n_total,
                        "db_hbm_bytes": int(igd.device_bytes()),
                        "l2": "256 MiB flush write between steps (untimed); DB image > 126 MB L2",
-                       "parallelism": f"db replicated, queries sharded x{world} by scan-byte prefix sum"
-                       if world > 1 else "single GPU", "db_build_s": round(build_s, 1), "db_open_s": round(open_s, 2)},
+                       "parallelism": f"db replicated on {world} GPUs; {n_total} queries ({n_total // world} per GPU) "
+                                      "sorted by (contig, start) and cut into contiguous shards by scan-byte prefix "
+                                      "sum; one NCCL int64 allreduce of hits[]" if world > 1 else "single GPU", "db_build_s": round(build_s, 1), "db_open_s": round(open_s, 2)},
             "e2e": {"value": n_total / (e2e_s / args.steps), "unit": UNIT, "ms_per_step": e2e_s / args.steps * 1e3,
                     "h2d_bytes_per_step": 12 * n_total, "d2h_bytes_per_step": 8 * igd.nfiles * world,
                     "api": "igd_b200_count (C-ABI, host buffers)" if world == 1 else
@@ -303,7 +309,8 @@ def run_reference(args):
         return
     from oracle import oracle as O
     path = workloads.build_db(args.workload, args.workdir)
-    q = workloads.queries(args.workload, args.queries)
+    per_gpu = args.queries or workloads.CONFIGS[args.workload]["n_queries"]
+    q = workloads.queries(args.workload, per_gpu * max(args.gpus, 1))       # same query set as our arm at this N
     n_total = len(q)
     cores = os.cpu_count() or 1
     n = min(n_total, args.ref_sample)
@@ -342,7 +349,7 @@ def run_reference(args):
         if kind == "reference" else f"{n} of {n_total} queries per step, {cores} processes of the oracle port"
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {workloads.CONFIGS[args.workload]['n_files']} files x "
                                    f"{workloads.CONFIGS[args.workload]['per_file']} intervals (hg38, -b 14), "
                                    f"{n_total} queries, count mode", "n_queries": n_total},
@@ -360,7 +367,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(workloads.CONFIGS))
     ap.add_argument("--queries", type=int, default=None, help="override the number of queries")
     ap.add_argument("--workdir", default=os.environ.get("IGD_B200_WORKDIR", "/tmp/igd_b200_bench"))
-    ap.add_argument("--cpu-sample", type=int, default=1_000_000, help="queries in the cpu_baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=8_000_000, help="queries in the cpu_baseline sample")
     ap.add_argument("--ref-sample", type=int, default=1_000_000, help="queries per step of --impl reference")
     args = ap.parse_args()
     if args.impl == "reference":

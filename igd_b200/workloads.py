@@ -64,12 +64,47 @@ def queries(name: str, n: int | None = None) -> synth.Intervals:
                                n or cfg["n_queries"], cfg["q_law"])
 
 
-def sort_and_shard(igd, ctg: np.ndarray, qs: np.ndarray, qe: np.ndarray, n_parts: int):
+def read_igd_header(path: str) -> dict:
+    """nbp, gType, nCtg, nTile[], nCnt[] (flattened contig-major) and contig names of an .igd file
+    (layout: /root/reference/src/igd_base.c:408-422; read like get_igdinfo, :269-323).  Host-only."""
+    with open(path, "rb") as f:
+        nbp, gtype, m = np.fromfile(f, np.int32, 3)
+        ntile = np.fromfile(f, np.int32, m)
+        ncnt = np.fromfile(f, np.int32, int(ntile.sum()))
+        names = [f.read(40).split(b"\0")[0].decode(errors="replace") for _ in range(m)]
+    tbase = np.concatenate([[0], np.cumsum(ntile.astype(np.int64))])
+    return {"nbp": int(nbp), "gtype": int(gtype), "nctg": int(m), "ntile": ntile, "ncnt": ncnt, "tbase": tbase,
+            "names": names}
+
+
+def query_cost(hdr: dict, ctg: np.ndarray, qs: np.ndarray, qe: np.ndarray) -> np.ndarray:
+    """Estimated scan bytes per query: 16 + sum over the bins it touches of (8 + 4 * nCnt) -- the same figure
+    as the library's igd_b200_query_cost, computed from the header alone."""
+    nbp = hdr["nbp"]
+    ctg = np.asarray(ctg, np.int64)
+    ok = (ctg >= 0) & (ctg < hdr["nctg"])
+    c = np.where(ok, ctg, 0)
+    n1 = np.asarray(qs, np.int64) // nbp
+    n1 = np.where(np.asarray(qs) < 0, -(-np.asarray(qs, np.int64) // nbp), n1)      # C truncating division
+    n2 = (np.asarray(qe, np.int64) - 1) // nbp
+    n2 = np.where(np.asarray(qe, np.int64) - 1 < 0, -(-(np.asarray(qe, np.int64) - 1) // nbp), n2)
+    mT = hdr["ntile"][c].astype(np.int64) - 1
+    ok &= (n1 >= 0) & (n1 <= mT)
+    n2 = np.maximum(np.minimum(n2, mT), n1)
+    # prefix sums of (8 + 4 nCnt) over the flattened tile table make any bin range O(1)
+    w = np.concatenate([[0], np.cumsum(8 + 4 * hdr["ncnt"].astype(np.int64))])
+    lo = hdr["tbase"][c] + np.where(ok, n1, 0)
+    hi = hdr["tbase"][c] + np.where(ok, n2, 0) + 1
+    return np.where(ok, 16 + w[hi] - w[lo], 16).astype(np.int64)
+
+
+def sort_and_shard(hdr: dict, ctg: np.ndarray, qs: np.ndarray, qe: np.ndarray, n_parts: int):
     """Sort queries by (contig id, start) and cut them into ``n_parts`` contiguous ranges balanced by the
-    prefix sum of estimated per-query scan bytes (igd_b200_query_cost).  Returns sorted arrays + bounds."""
+    prefix sum of estimated per-query scan bytes.  Host-only; every rank computes the same
+    bounds from the same inputs.  Returns sorted arrays + bounds (len n_parts + 1)."""
     order = np.lexsort((qs, ctg))
     ctg, qs, qe = ctg[order], qs[order], qe[order]
-    cost = igd.query_cost(ctg, qs, qe)
+    cost = query_cost(hdr, ctg, qs, qe)
     cum = np.cumsum(cost)
     total = int(cum[-1]) if len(cum) else 0
     bounds = [0]

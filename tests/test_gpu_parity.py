@@ -112,3 +112,48 @@ def test_seqpare_dense(dense_db, O, api, kind, workdir):
     np.testing.assert_allclose(got, want, rtol=1e-9, atol=0)       # north_star's tolerance
     assert np.array_equal(got, want)                               # and in fact the same doubles
     g.close()
+
+
+def test_query_cost_c_equals_host_planner(dense_db, api):
+    """igd_b200_query_cost (C, from the open handle) == workloads.query_cost (numpy, from the header alone)."""
+    from igd_b200 import workloads
+    q = _queries("long")
+    g = api.IGD(dense_db)
+    hdr = workloads.read_igd_header(dense_db)
+    assert np.array_equal(g.query_cost(q.ctg, q.start, q.end), workloads.query_cost(hdr, q.ctg, q.start, q.end))
+    g.close()
+
+
+def test_count_device_pointers_and_growth(dense_db, O, api):
+    """igd_b200_count_device + _finish on device buffers, batches of growing size (the scratch buffers are
+    sized by the first batch; a larger one must be detected, re-run and still give the reference's hits)."""
+    import torch
+    odb = O.OracleDB(dense_db)
+    g = api.IGD(dense_db)
+    dev = torch.device("cuda", 0)
+    for n, kind in ((50, "short"), (20000, "short"), (3000, "long")):
+        q = _queries(kind)
+        ctg, qs, qe = (torch.from_numpy(np.ascontiguousarray(x[:n])).to(dev) for x in (q.ctg, q.start, q.end))
+        hits = torch.zeros(g.nfiles, dtype=torch.int64, device=dev)
+        torch.cuda.synchronize()
+        g.count_device(n, ctg.data_ptr(), qs.data_ptr(), qe.data_ptr(), 0, hits.data_ptr(), 0)
+        g.count_device_finish()
+        torch.cuda.synchronize()
+        want, _ = odb.count(q.ctg[:n], q.start[:n], q.end[:n], 0)
+        assert np.array_equal(hits.cpu().numpy(), want), (n, kind)
+    g.close()
+
+
+def test_degenerate_and_extreme_queries(dense_db, O, api):
+    """qs == qe, qs > qe, negative starts, INT_MAX ends, unknown contigs, queries beyond the last tile."""
+    I = np.iinfo(np.int32)
+    ctg = np.array([0, 0, 0, 0, 1, 2, -1, 7, 0, 1, 0, 0], np.int32)
+    qs = np.array([5000, 6000, -5, I.min, 0, 199999, 5, 5, 999_999, 16384, 0, 16383], np.int32)
+    qe = np.array([5000, 5500, 300, I.max, I.max, 200001, 50, 50, 2_000_000, 16384, 1, 16385], np.int32)
+    odb = O.OracleDB(dense_db)
+    g = api.IGD(dense_db)
+    for v in (0, 1, 700):
+        want, _ = odb.count(ctg, qs, qe, v)
+        got, _ = g.count(ctg, qs, qe, v)
+        assert np.array_equal(got, want), v
+    g.close()
