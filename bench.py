@@ -222,6 +222,7 @@ def run_ours(args):
     barrier()
     torch.cuda.synchronize()
     launches = igd.launch_count() - launches0
+    plan = igd.last_plan()
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = float(sum(step_ms))
 
@@ -289,7 +290,10 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "k_search (count)", "kernel_ms": kmean,
+                         "traffic": traffic, "kernel": "k_count_items (count-mode search)", "kernel_ms": kmean,
+                         "own_bytes_per_launch": plan["own_bytes"],
+                         "own_frac": plan["own_bytes"] / (kmean * 1e-3) / 1e9 / peak,
+                         "plan_rank0": plan,
                          "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                          "bytes_definition": "SURVEY.md 8(d) reference scan range, oracle-instrumented"
                                              + ("" if orc["sample_n"] == n_total else f" (scaled from a {orc['sample_n']}-query sample)")},

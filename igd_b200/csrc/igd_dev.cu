@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(SCAN_T) k_plan3(int32_t T, const uint32_t *__r
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         const Plan p = bsum[nb];
         seg_off[T] = (uint32_t)p.segs, item_off[T] = (uint32_t)p.items;
-        tot[0] = p.segs, tot[1] = p.items;
+        tot[0] = p.segs, tot[1] = p.items, tot[2] = 0;
     }
 }
 
@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(256) k_item_fill(DbView db, const uint32_t *__
                                                     const uint32_t *__restrict__ seg_mid,
                                                     const uint32_t *__restrict__ cnt2,
                                                     const uint32_t *__restrict__ item_off,
-                                                    const unsigned long long *__restrict__ tot,
+                                                    unsigned long long *__restrict__ tot,
                                                     unsigned long long seg_cap, unsigned long long item_cap,
                                                     int4 *__restrict__ items)
 {
@@ -418,6 +418,11 @@ __global__ void __launch_bounds__(256) k_item_fill(DbView db, const uint32_t *__
     };
     if (ni <= 32)
         for (uint32_t k = 0; k < ni; ++k) write(k, i0, sa0, mid, sb0, tm);
+    // tot[2] = records the items of this batch read (each tile once per 64 of its segments)
+    unsigned long long recs = ni ? (unsigned long long)tm.y * ((sb0 - sa0 + SMAX - 1) / SMAX) : 0ull;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) recs += __shfl_xor_sync(FULL, recs, d);
+    if (lane == 0 && recs) atomicAdd(&tot[2], recs);
     unsigned heavy = __ballot_sync(FULL, ni > 32);
     while (heavy) {
         const int src = __ffs(heavy) - 1;
@@ -1194,11 +1199,11 @@ int enqueue_count(igdb_dev *d, const igdb_dev::Pending &p)
     k_scan2<Plan><<<1, SCAN_T, 0, st>>>(d->plan_bsum, sb);
     k_plan3<<<sb, SCAN_T, 0, st>>>(d->T, d->cnt2, d->plan_tmp, d->plan_bsum, sb, d->cseg_off, d->cseg_mid,
                                     d->item_off, d->plan_tot);
-    CK(cudaMemcpyAsync((void *)d->h_plan, d->plan_tot, 16, cudaMemcpyDeviceToHost, st));
-    CK(cudaEventRecord(d->plan_ev, st));
     // (the fill reads the later-bin counters that the scatter counts back down to zero)
     k_item_fill<<<(d->T + 255) / 256, 256, 0, st>>>(db, d->cseg_off, d->cseg_mid, d->cnt2, d->item_off, d->plan_tot,
                                                   seg_cap, item_cap, d->items);
+    CK(cudaMemcpyAsync((void *)d->h_plan, d->plan_tot, 24, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(d->plan_ev, st));
     k_cseg_scatter<V><<<nb, thr, 0, st>>>(db, p.n, p.ctg, p.qs, p.qe, d->cnt2, d->cseg_off, d->cseg_mid,
                                            d->plan_tot, seg_cap, item_cap, d->csegs);
     CountArgs a{};
@@ -1340,7 +1345,7 @@ static int create_impl(igdb_dev *d, const int32_t *ntile, const int32_t *ncnt)
         dev_alloc(d, &d->cnt2, (size_t)2 * d->T + 2) || dev_alloc(d, &d->cseg_off, (size_t)d->T + 1) ||
         dev_alloc(d, &d->cseg_mid, (size_t)d->T + 1) || dev_alloc(d, &d->item_off, (size_t)d->T + 1) ||
         dev_alloc(d, &d->plan_tmp, (size_t)d->T + 1) ||
-        dev_alloc(d, &d->plan_bsum, (size_t)(d->T + SCAN_B - 1) / SCAN_B + 2) || dev_alloc(d, &d->plan_tot, 2))
+        dev_alloc(d, &d->plan_bsum, (size_t)(d->T + SCAN_B - 1) / SCAN_B + 2) || dev_alloc(d, &d->plan_tot, 4))
         return -1;
     CK(cudaMemcpy(d->tiles, meta.data(), meta.size() * sizeof(TileMeta), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d->d_toff, d->toff.data(), d->toff.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
@@ -1428,6 +1433,10 @@ float igdb_dev_last_search_ms(igdb_dev *d)
 }
 
 int64_t igdb_dev_bytes(const igdb_dev *d) { return d->bytes; }
+void igdb_dev_last_plan(const igdb_dev *d, int64_t out[3])
+{
+    out[0] = (int64_t)d->h_plan[0], out[1] = (int64_t)d->h_plan[1], out[2] = (int64_t)d->h_plan[2];
+}
 int64_t igdb_dev_launches(const igdb_dev *d) { return d->launches; }
 
 int igdb_dev_count_device(igdb_dev *d, int64_t n, const int32_t *d_ctg, const int32_t *d_qs, const int32_t *d_qe,

@@ -25,6 +25,8 @@ int igdb_dev_finalize(igdb_dev *d);
 void igdb_dev_destroy(igdb_dev *d);
 int64_t igdb_dev_bytes(const igdb_dev *d);
 int64_t igdb_dev_launches(const igdb_dev *d);
+/* plan of the last settled count batch: segments, work items, records read by the items */
+void igdb_dev_last_plan(const igdb_dev *d, int64_t out[3]);
 /* device time of the last count-mode search kernel (CUDA events on its stream); < 0 if none */
 float igdb_dev_last_search_ms(igdb_dev *d);
 void *igdb_dev_pinned(igdb_dev *d, size_t bytes);   /* reusable pinned staging buffer (upload) */

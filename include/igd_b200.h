@@ -127,6 +127,10 @@ void igd_b200_last_timing(const igd_b200_t *h, float t[3]);
 /* device time (ms, CUDA events on the launching stream) of the search kernel of the last count call;
  * blocks until that kernel has finished; < 0 if there was none */
 float igd_b200_last_search_kernel_ms(igd_b200_t *h);
+/* plan of the last settled count batch: out[0] (query, tile) segments, out[1] work items, out[2] records the
+ * items read (each touched tile once per 64 of its segments) -- the kernel's own byte count is
+ * 16*items + 12*records (16 with -v) + 8*segments */
+void igd_b200_last_plan(const igd_b200_t *h, int64_t out[3]);
 /* kernel launches issued by this handle since open (for bench.py's gpu_launches) */
 int64_t igd_b200_launch_count(const igd_b200_t *h);
 
