@@ -23,15 +23,24 @@ CONFIGS = {
     # 1e9 intervals (10k files), 10M queries, query-sharded over 1/2/4/8 GPUs
     "cfg3": dict(config=3, n_files=10_000, per_file=100_000, db_law=("lognormal", 6.0, 1.0),
                  n_queries=10_000_000, q_law=("fixed", 1000)),
+    # cfg3's per-tile statistics (5.5k records and ~53 queries per tile, 10k files) on a genome 1/10 the size:
+    # what profiling runs use, since the full cfg3 database takes minutes to generate
+    "cfg3s": dict(config=3, n_files=10_000, per_file=10_000, db_law=("lognormal", 6.0, 1.0),
+                  n_queries=1_000_000, q_law=("fixed", 1000), genome_scale=0.1),
     # a 1/10 cut of cfg2 for smoke runs and CPU-side tests
     "mini": dict(config=2, n_files=200, per_file=50_000, db_law=("lognormal", 6.0, 1.0),
                  n_queries=100_000, q_law=("fixed", 1000)),
 }
 
 
+def genome_sizes(name: str) -> np.ndarray:
+    scale = CONFIGS[name].get("genome_scale", 1.0)
+    return synth.HG38_SIZES if scale == 1.0 else np.maximum((synth.HG38_SIZES * scale).astype(np.int64), 1)
+
+
 def _gen_file(args):
-    config, i, per_file, law = args
-    return synth.gen_intervals(synth.seed_for(config, i), per_file, law)
+    config, i, per_file, law, sizes = args
+    return synth.gen_intervals(synth.seed_for(config, i), per_file, law, sizes)
 
 
 def build_db(name: str, workdir: str, procs: int | None = None) -> str:
@@ -40,10 +49,12 @@ def build_db(name: str, workdir: str, procs: int | None = None) -> str:
     os.makedirs(workdir, exist_ok=True)
     stem = os.path.join(workdir, name)
     marker = stem + ".json"
-    want = json.dumps({k: cfg[k] for k in ("config", "n_files", "per_file", "db_law")}, sort_keys=True)
+    want = json.dumps({k: cfg.get(k) for k in ("config", "n_files", "per_file", "db_law", "genome_scale")},
+                      sort_keys=True)
     if os.path.exists(marker) and os.path.exists(stem + ".igd") and open(marker).read() == want:
         return stem + ".igd"
-    jobs = [(cfg["config"], i, cfg["per_file"], cfg["db_law"]) for i in range(cfg["n_files"])]
+    sizes = genome_sizes(name)
+    jobs = [(cfg["config"], i, cfg["per_file"], cfg["db_law"], sizes) for i in range(cfg["n_files"])]
     procs = procs or min(os.cpu_count() or 1, 16)
     if procs > 1 and len(jobs) >= 64:
         with ProcessPoolExecutor(procs) as ex:
@@ -61,7 +72,7 @@ def build_db(name: str, workdir: str, procs: int | None = None) -> str:
 def queries(name: str, n: int | None = None) -> synth.Intervals:
     cfg = CONFIGS[name]
     return synth.gen_intervals(synth.seed_for(cfg["config"], synth.QUERY_FILE_INDEX),
-                               n or cfg["n_queries"], cfg["q_law"])
+                               n or cfg["n_queries"], cfg["q_law"], genome_sizes(name))
 
 
 def read_igd_header(path: str) -> dict:
