@@ -99,7 +99,7 @@ def load_library():
     L.igd_b200_last_search_kernel_ms.restype = C.c_float
     L.igd_b200_last_search_kernel_ms.argtypes = [vp]
     L.igd_b200_last_timing.argtypes = [vp, C.POINTER(C.c_float * 3)]
-    L.igd_b200_last_plan.argtypes = [vp, C.POINTER(C.c_int64 * 3)]
+    L.igd_b200_last_plan.argtypes = [vp, C.POINTER(C.c_int64 * 4)]
     L.igd_b200_use.argtypes = [vp]
     L.igd_b200_current.restype = vp
     L.get_overlaps.restype = C.c_int32
@@ -212,9 +212,9 @@ class IGD:
 
     def last_plan(self):
         """Plan of the last settled count batch and the bytes its search kernel had to read."""
-        t = (C.c_int64 * 3)()
+        t = (C.c_int64 * 4)()
         self._L.igd_b200_last_plan(self._need(), C.byref(t))
-        return {"segments": t[0], "items": t[1], "records": t[2], "own_bytes": 16 * t[1] + 12 * t[2] + 8 * t[0]}
+        return {"segments": t[0], "items": t[1], "records": t[2], "own_bytes": t[3]}
 
     def last_timing(self):
         t = (C.c_float * 3)()

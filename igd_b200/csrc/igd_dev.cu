@@ -1,9 +1,10 @@
 // igd_b200 CUDA layer: HBM image of an .igd database and the search kernels (sm_100a).
 //
 // Data layout in HBM (built once per igd_b200_open):
-//   tiles[T]          16 B per (contig, bin) tile: {off4, n, ts, s0}
-//                       off4 : first record of the tile in the SoA arrays, in units of 4 records
-//                              (every tile is padded to a multiple of 4 records => 16 B aligned int4 loads)
+//   tiles[T]          16 B per (contig, bin) tile: {off8, n, ts, s0}
+//                       off8 : first record of the tile in the SoA arrays, in units of 8 records
+//                              (every tile is padded to a multiple of 8 records => 16 B aligned vector loads
+//                              of the int32 arrays and of the packed 16-bit arrays below)
 //                       n    : nCnt of the tile                       (iGD_t.nCnt, src/igd_base.h:103)
 //                       ts   : #records with start < bin boundary     (the per-query linear scan of
 //                              src/igd_search.c:510-511 is a per-tile constant; computed once here)
@@ -11,6 +12,13 @@
 //   start/end/idx/value[P]  SoA int32 copies of gdata_t's fields (src/igd_base.h:41-46), tile-major in
 //                       the file's order (each tile sorted by start).  Pad records: start=INT_MAX,
 //                       end=INT_MIN (overlap no query).
+//   ps/pe/pf[P]       uint16 copies for count mode (when nbp <= 16384 and nFiles <= 65536), 6 B per record
+//                       instead of 12: coordinates RELATIVE to the tile's bin boundary bd, clamped to the
+//                       bin -- x' = clamp(x - bd + 1, 0, nbp + 1), exact for every comparison a query that
+//                       visits this tile can make (see k_count_packed) -- and stored pre-biased,
+//                       ps = start' + 1, pe = end' + 0x8000, so that two records are compared with one
+//                       32-bit subtraction per predicate (bit 15 of each half is the answer).
+//                       pf = file index.  Pads: ps = 0x8000 (starts after every query end), pe = 0x8000.
 //   tbase[nctg+1]     global tile index of each contig's tile 0.
 //
 // Query batches are turned into (query, tile) SEGMENTS -- one per non-empty, non-gated tile the reference
@@ -52,7 +60,7 @@ thread_local char g_err[512] = "";
     } while (0)
 
 struct TileMeta {
-    uint32_t off4;
+    uint32_t off8;
     int32_t n, ts, s0;
 };
 static_assert(sizeof(TileMeta) == 16, "TileMeta must be one int4");
@@ -60,6 +68,7 @@ static_assert(sizeof(TileMeta) == 16, "TileMeta must be one int4");
 struct DbView {
     const TileMeta *tiles;
     const int32_t *start, *end, *idx, *value;
+    const uint16_t *ps, *pe, *pf;           // packed tile-relative copies for count mode (may be NULL)
     const int32_t *tbase;
     int32_t nctg, nbp, nfiles, ntiles;
 };
@@ -74,6 +83,21 @@ constexpr unsigned FULL = 0xffffffffu;
 
 __device__ __forceinline__ int4 ldg4(const int32_t *p) { return __ldg(reinterpret_cast<const int4 *>(p)); }
 
+// tile-relative coordinates of the packed count-mode layout: x' = clamp(x - bd + 1, 0, nbp + 1).
+//   a START (record start, always < bd + nbp; or a query start): 0 = before the bin, else 1 .. nbp
+//   an END (record end, always > bd; or a query end > bd): 2 .. nbp + 1, nbp + 1 = at or past the bin's end
+// For a record r of tile j and a query q that the reference lets visit tile j (0 <= qs < qe):
+//   start_r < qe  <=>  start'_r < qe'      and      end_r > qs  <=>  end'_r > qs'
+// (a clamped value only ever stands for "outside the bin on that side", where the comparison is decided).
+__host__ __device__ __forceinline__ int32_t pk_rel(int32_t x, int32_t bd, int32_t nbp)
+{
+    return x < bd ? 0 : min(x - bd, nbp) + 1;       // x - bd cannot overflow: both >= 0 here
+}
+__host__ __device__ __forceinline__ int32_t pk_rel_end(int32_t x, int32_t bd, int32_t nbp)
+{
+    return x <= bd ? 1 : min(x - bd, nbp) + 1;
+}
+
 // ------------------------------------------------------------------------------------------------
 // upload
 // ------------------------------------------------------------------------------------------------
@@ -81,7 +105,8 @@ __device__ __forceinline__ int4 ldg4(const int32_t *p) { return __ldg(reinterpre
 __global__ void k_transpose(const int4 *__restrict__ aos, int64_t rec0, int64_t nrec,
                             const int64_t *__restrict__ toff, int32_t T, const TileMeta *__restrict__ tiles,
                             int32_t *__restrict__ start, int32_t *__restrict__ end, int32_t *__restrict__ idx,
-                            int32_t *__restrict__ value)
+                            int32_t *__restrict__ value, int32_t nbp, uint16_t *__restrict__ ps,
+                            uint16_t *__restrict__ pe, uint16_t *__restrict__ pf)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nrec) return;
@@ -92,8 +117,20 @@ __global__ void k_transpose(const int4 *__restrict__ aos, int64_t rec0, int64_t 
         if (__ldg(&toff[mid]) <= g) lo = mid; else hi = mid;
     }
     int4 r = __ldg(&aos[i]);
-    int64_t dst = (int64_t)tiles[lo].off4 * 4 + (g - __ldg(&toff[lo]));
+    int64_t dst = (int64_t)tiles[lo].off8 * 8 + (g - __ldg(&toff[lo]));
     idx[dst] = r.x, start[dst] = r.y, end[dst] = r.z, value[dst] = r.w;
+    if (ps) {                                   // tiles[].ts still holds the bin boundary here (k_tile_meta)
+        const int32_t bd = tiles[lo].ts;
+        ps[dst] = (uint16_t)(pk_rel(r.y, bd, nbp) + 1);
+        pe[dst] = (uint16_t)(pk_rel_end(r.z, bd, nbp) + 0x8000);
+        pf[dst] = (uint16_t)r.x;
+    }
+}
+
+__global__ void k_fill16(uint16_t *__restrict__ p, int64_t n, uint16_t v)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = v;
 }
 
 __global__ void k_fill(int32_t *__restrict__ p, int64_t n, int32_t v)
@@ -108,7 +145,7 @@ __global__ void k_tile_meta(TileMeta *tiles, int32_t T, const int32_t *__restric
     int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T) return;
     TileMeta m = tiles[t];
-    const int32_t *s = start + (int64_t)m.off4 * 4;
+    const int32_t *s = start + (int64_t)m.off8 * 8;
     int32_t bd = m.ts, lo = 0, hi = m.n;
     while (lo < hi) {
         int32_t mid = (lo + hi) >> 1;
@@ -122,7 +159,7 @@ __global__ void k_tile_meta(TileMeta *tiles, int32_t T, const int32_t *__restric
 // ------------------------------------------------------------------------------------------------
 // query -> segments.  Restates the control flow of get_overlaps (src/igd_search.c:454-534; V=false:
 // nothing at all when bin n1 is empty) and get_overlaps_v (:623-694; V=true: later bins are visited
-// regardless).  f(tile, later, k) is called for each tile the reference would scan.
+// regardless).  f(tile, later, k, bin boundary) is called for each tile the reference would scan.
 // ------------------------------------------------------------------------------------------------
 template <bool V, class F>
 __device__ __forceinline__ int for_each_segment(const DbView &db, int c, int qs, int qe, F f)
@@ -139,7 +176,7 @@ __device__ __forceinline__ int for_each_segment(const DbView &db, int c, int qs,
     for (int j = n1; j <= max(n1, n2); ++j) {
         const int4 m = __ldg(reinterpret_cast<const int4 *>(&db.tiles[tb + j]));
         if (m.y > 0 && qe > m.w) {                           // nCnt > 0 and the qe > start[0] gate
-            f(tb + j, j > n1, k);
+            f(tb + j, j > n1, k, j * nbp);
             ++k;
         }
     }
@@ -154,7 +191,7 @@ __global__ void k_seg_count(DbView db, int64_t n, const int32_t *__restrict__ ct
     int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
     int k = for_each_segment<V>(db, ctg[q], qs[q], qe[q],
-                                [&](int tile, bool, int) { atomicAdd(&tile_cnt[tile], 1u); });
+                                [&](int tile, bool, int, int) { atomicAdd(&tile_cnt[tile], 1u); });
     if (nseg) nseg[q] = k;
 }
 
@@ -169,7 +206,7 @@ __global__ void k_seg_scatter(DbView db, int64_t n, const int32_t *__restrict__ 
     if (q >= n) return;
     const int s = qs[q], e = qe[q];
     const uint32_t sid0 = qseg_off ? qseg_off[q] : 0u;
-    for_each_segment<V>(db, ctg[q], s, e, [&](int tile, bool later, int k) {
+    for_each_segment<V>(db, ctg[q], s, e, [&](int tile, bool later, int k, int) {
         uint32_t pos = tile_off[tile] + atomicSub(&tile_cnt[tile], 1u) - 1u;
         Seg sg;
         sg.qs = s, sg.qe = e, sg.tile = (uint32_t)tile;
@@ -289,14 +326,34 @@ struct __align__(8) CSeg {       // count-mode segment: the query's interval, no
     int32_t qs, qe;
 };
 
-template <bool V>
+// Which queries a count pipeline takes, and in which layout it searches:
+//   M_ALL32  every query, int32 records (k_count_items)           -- databases the packed layout cannot hold
+//   M_PACKED the queries with 0 <= qs < qe, packed 16-bit records (k_count_packed); the others are only counted
+//            (cnt2[2T]) and, if there are any, a second pipeline in mode M_ABN32 takes exactly those
+//   M_ABN32  the queries with qs < 0 or qs >= qe (accepted by parse_bed, src/igd_base.c:69: only en > 0 is
+//            required), int32 records
+enum { M_ALL32 = 0, M_PACKED = 1, M_ABN32 = 2 };
+
+template <int MODE>
+__device__ __forceinline__ bool mode_takes(int qs, int qe)
+{
+    const bool normal = qs >= 0 && qs < qe;
+    return MODE == M_ALL32 ? true : (MODE == M_PACKED ? normal : !normal);
+}
+
+template <bool V, int MODE>
 __global__ void k_cseg_count(DbView db, int64_t n, const int32_t *__restrict__ ctg, const int32_t *__restrict__ qs,
                              const int32_t *__restrict__ qe, uint32_t *__restrict__ cnt2)
 {
     int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
-    for_each_segment<V>(db, ctg[q], qs[q], qe[q],
-                        [&](int tile, bool later, int) { atomicAdd(&cnt2[2 * tile + (later ? 1 : 0)], 1u); });
+    const int s = qs[q], e = qe[q];
+    if (!mode_takes<MODE>(s, e)) {
+        if (MODE == M_PACKED) atomicAdd(&cnt2[2 * db.ntiles], 1u);
+        return;
+    }
+    for_each_segment<V>(db, ctg[q], s, e,
+                        [&](int tile, bool later, int, int) { atomicAdd(&cnt2[2 * tile + (later ? 1 : 0)], 1u); });
 }
 
 __device__ __forceinline__ Plan plan_of_tile(const DbView &db, const uint32_t *__restrict__ cnt2, int32_t t)
@@ -350,31 +407,42 @@ __global__ void __launch_bounds__(SCAN_T) k_plan3(int32_t T, const uint32_t *__r
         const Plan p = bsum[nb];
         seg_off[T] = (uint32_t)p.segs, item_off[T] = (uint32_t)p.items;
         tot[0] = p.segs, tot[1] = p.items, tot[2] = 0;
+        tot[3] = cnt2[2 * T];                              // queries left to the M_ABN32 pipeline (M_PACKED only)
     }
 }
 
 // cnt2 is counted back down to zero here, so it is clean for the next batch.  Nothing is written when the
 // plan does not fit the scratch buffers: the host then grows them and runs the batch again.
-template <bool V>
+// M_PACKED writes 4-byte segments in the tile's packed coordinates, pre-biased like the records:
+//   bits 0-15 = qs' + 1, bits 16-31 = qe' + 0x8000.
+template <bool V, int MODE>
 __global__ void k_cseg_scatter(DbView db, int64_t n, const int32_t *__restrict__ ctg, const int32_t *__restrict__ qs,
                                const int32_t *__restrict__ qe, uint32_t *__restrict__ cnt2,
                                const uint32_t *__restrict__ seg_off, const uint32_t *__restrict__ seg_mid,
                                const unsigned long long *__restrict__ tot, unsigned long long seg_cap,
-                               unsigned long long item_cap, CSeg *__restrict__ segs)
+                               unsigned long long item_cap, void *__restrict__ segs)
 {
     int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n || tot[0] > seg_cap || tot[1] > item_cap) return;
     const int s = qs[q], e = qe[q];
-    for_each_segment<V>(db, ctg[q], s, e, [&](int tile, bool later, int) {
+    if (!mode_takes<MODE>(s, e)) {
+        if (MODE == M_PACKED) atomicSub(&cnt2[2 * db.ntiles], 1u);
+        return;
+    }
+    for_each_segment<V>(db, ctg[q], s, e, [&](int tile, bool later, int, int bd) {
         const uint32_t b = later ? __ldg(&seg_mid[tile]) : __ldg(&seg_off[tile]);
         const uint32_t pos = b + atomicSub(&cnt2[2 * tile + (later ? 1 : 0)], 1u) - 1u;
-        segs[pos] = CSeg{s, e};
+        if (MODE == M_PACKED)
+            static_cast<uint32_t *>(segs)[pos] =
+                (uint32_t)(pk_rel(s, bd, db.nbp) + 1) | (uint32_t)(pk_rel_end(e, bd, db.nbp) + 0x8000) << 16;
+        else
+            static_cast<CSeg *>(segs)[pos] = CSeg{s, e};
     });
 }
 
 // Work items of tile t, group-major.  An item is self-contained, so the search kernel goes from the item to
 // its records and segments without touching the tile table:
-//   x = position of the group's first record in the SoA arrays, in units of 4 records
+//   x = position of the group's first record in the SoA arrays, in units of 8 records
 //   y = first segment
 //   z = records in the group (bits 0-15, 1..GROUP) | first record of the group that starts inside this bin
 //       (bits 16-31, 0..GROUP: the dedupe rule of later bins)
@@ -413,7 +481,7 @@ __global__ void __launch_bounds__(256) k_item_fill(DbView db, const uint32_t *__
         const uint32_t nv = (uint32_t)min(tm_.y - r0, GROUP);
         const uint32_t tsr = (uint32_t)min(max(tm_.z - r0, 0), GROUP);
         const uint32_t nfirst = min(max(m, sa), sb) - sa;
-        items[i0_ + k] = make_int4((int)((uint32_t)tm_.x + g * (GROUP / 4)), (int)sa, (int)(nv | (tsr << 16)),
+        items[i0_ + k] = make_int4((int)((uint32_t)tm_.x + g * (GROUP / 8)), (int)sa, (int)(nv | (tsr << 16)),
                                    (int)(nfirst | ((sb - sa) << 8)));
     };
     if (ni <= 32)
@@ -571,7 +639,7 @@ __global__ void __launch_bounds__(COUNT_MAXW * 32, 1) k_count_items(const CountA
         const uint32_t x = __shfl_sync(FULL, dd.x, j), y = __shfl_sync(FULL, dd.y, j);
         const int nv = __shfl_sync(FULL, dd.z, j) & 0xffff, ns = (__shfl_sync(FULL, dd.w, j) >> 8) & 0xff;
         const uint32_t so = (n % COUNT_K) * L::STAGE;
-        const size_t p = (size_t)x * 4;
+        const size_t p = (size_t)x * 8;
 #pragma unroll
         for (int h = 0; h < SUB; ++h)
             if (h * 128 + lane * 4 < nv) {
@@ -681,6 +749,258 @@ __global__ void __launch_bounds__(COUNT_MAXW * 32, 1) k_count_items(const CountA
 }
 
 // ------------------------------------------------------------------------------------------------
+// count mode on the packed layout (the default path): the same tile-centric, record-stationary scheme as
+// k_count_items, on 16-bit tile-relative coordinates -- half the bytes per record and two records per
+// 32-bit operation.
+//   records  S = start' + 1 (1 .. nbp + 1; 0x8000 = pad / filtered out by -v), E = end' + 0x8000
+//   segments QS = qs' + 1, QE = qe' + 0x8000, each replicated into both halves of a register
+//   A = QE2 - S2 : bit 15 of a half is set  <=>  qe' > start'   (the halves are 0x8000 + qe' - S >= 0: no borrow)
+//   B = E2 - QS2 : bit 15 of a half is set  <=>  end' > qs'     (0x8000 + end' - QS >= 0x8000 - nbp - 1 > 0)
+//   counts (two 16-bit counters per register, <= 64 per item) += (A & B & 0x80008000) >> 15
+// i.e. 2 subtractions, 1 LOP3 and 1 shift-add per PAIR of (record, query) tests; the int32 kernel spends 3
+// ALU-pipe instructions per test.  An item is 256 records (8 per lane: one 16-byte load per array) x <= 64
+// segments.  Later-bin segments see S replaced by 0x8000 for the records that start before the bin (the
+// reference's i >= tS, src/igd_search.c:510-511,522).
+// Scheduling: one CTA per SM; a warp owns every NW-th BLOCK of 8 consecutive items (static, fine-grained
+// interleave: the spread between warps is at most one block), four blocks' descriptors are fetched with one
+// coalesced load.  Per warp a private K-stage cp.async ring as in k_count_items.
+// ------------------------------------------------------------------------------------------------
+constexpr int PK_K = 4;                 // pipeline stages per warp
+constexpr int PK_MAXW = 24;             // most warps per CTA (register budget 65536 / 768 = 85)
+constexpr int PK_IB = 8;                // items per block
+
+template <bool V>
+struct PackedSmem {
+    static constexpr uint32_t ARR = GROUP * 2;                          // one 16-bit array of a stage
+    static constexpr uint32_t VOFF = 3 * ARR;                           // int32 value[GROUP] (-v only)
+    static constexpr uint32_t QOFF = VOFF + (V ? GROUP * 4 : 0);
+    static constexpr uint32_t STAGE = QOFF + SMAX * 4;
+    static constexpr uint32_t LIST = PK_K * STAGE;                      // survivor list: SMAX x {QS2, QE2}
+    static constexpr uint32_t WARP = LIST + SMAX * 8;
+    static size_t hist_bytes(int nfiles) { return ((size_t)nfiles * 4 + 127) / 128 * 128; }
+    static int warps(int nfiles, bool smem_hist)
+    {
+        const size_t room = 226 * 1024 - (smem_hist ? hist_bytes(nfiles) : 0);
+        return (int)std::min<size_t>(room / WARP, PK_MAXW);
+    }
+    static size_t cta_bytes(int nfiles, bool smem_hist, int nwarps)
+    {
+        return (smem_hist ? hist_bytes(nfiles) : 0) + (size_t)nwarps * WARP;
+    }
+};
+
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t x, uint32_t y)
+{
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
+}
+// segments [i0, i1) of the warp's survivor list against this lane's 4 record pairs
+__device__ __forceinline__ void count_pairs(uint32_t list, int i0, int i1, const uint32_t (&S)[4],
+                                            const uint32_t (&E)[4], uint32_t (&c)[4])
+{
+#pragma unroll 2
+    for (int i = i0; i < i1; ++i) {
+        const int2 q = lds64(list + 8u * (uint32_t)i);       // same address in every lane: a broadcast
+        const uint32_t s2 = (uint32_t)q.x, e2 = (uint32_t)q.y;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t t;                                     // (A & B & 0x80008000): one 3-input LOP3
+            asm("lop3.b32 %0, %1, %2, 0x80008000, 0x80;" : "=r"(t) : "r"(e2 - S[k]), "r"(E[k] - s2));
+            c[k] += t >> 15;                                // LEA.HI
+        }
+    }
+}
+
+template <bool V, bool SMEM>
+__global__ void __launch_bounds__(PK_MAXW * 32, 1) k_count_packed(const CountArgs a)
+{
+    using L = PackedSmem<V>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const DbView &db = a.db;
+    uint32_t *hist = reinterpret_cast<uint32_t *>(smem);
+    const uint32_t hist_bytes = SMEM ? ((uint32_t)db.nfiles * 4 + 127) / 128 * 128 : 0;
+    if (SMEM) {
+        for (int f = threadIdx.x; f < db.nfiles; f += blockDim.x) hist[f] = 0;
+        __syncthreads();
+    }
+    const uint32_t hist_s = smem_u32(smem);
+    const int lane = threadIdx.x & 31, W = blockDim.x >> 5, wib = threadIdx.x >> 5;
+    const uint32_t wbase = hist_s + hist_bytes + (uint32_t)wib * L::WARP;
+    const unsigned long long nseg = __ldg(&a.tot[0]), nit = __ldg(&a.tot[1]);
+    const uint32_t n_items = (nseg > a.seg_cap || nit > a.item_cap) ? 0u : (uint32_t)nit;
+    const uint32_t nblk = (n_items + PK_IB - 1) / PK_IB, NW = gridDim.x * W, w = blockIdx.x * W + wib;
+    const uint32_t nb = w < nblk ? (nblk - w + NW - 1) / NW : 0;       // blocks of this warp
+    const uint32_t N = nb * PK_IB;                                      // item slots of this warp
+
+    // descriptor registers: lane j of quad-block g holds item (j % 8) of this warp's block 4 g + j / 8
+    const int4 zero = make_int4(0, 0, 0, 0);
+    auto load_desc = [&](uint32_t g) {
+        const uint32_t b = 4 * g + (lane >> 3);
+        const size_t it = ((size_t)b * NW + w) * PK_IB + (lane & 7);
+        return (b < nb && it < n_items) ? __ldg(&a.items[it]) : zero;
+    };
+    int4 dcur = load_desc(0), dnxt = load_desc(1);
+    const uint16_t *const pS = db.ps + lane * 8, *const pE = db.pe + lane * 8, *const pF = db.pf + lane * 8;
+    const int32_t *const pV = db.value + lane * 8;
+    const uint32_t *const pQ = static_cast<const uint32_t *>(static_cast<const void *>(a.segs)) + lane;
+    const uint32_t lslot = wbase + lane * 16, vslot = wbase + L::VOFF + lane * 32, qslot = wbase + L::QOFF + lane * 4;
+
+    // issue the copies of item slot n (descriptor in lane n % 32 of dd) into stage n % K
+    auto issue = [&](uint32_t n, const int4 &dd) {
+        const int j = n & 31;
+        const uint32_t x = __shfl_sync(FULL, dd.x, j), y = __shfl_sync(FULL, dd.y, j);
+        const int nv = __shfl_sync(FULL, dd.z, j) & 0xffff, ns = (__shfl_sync(FULL, dd.w, j) >> 8) & 0xff;
+        const uint32_t so = (n % PK_K) * L::STAGE;
+        const size_t p = (size_t)x * 8;
+        if (lane * 8 < nv) {
+            cp_async16(lslot + so, pS + p);
+            cp_async16(lslot + so + L::ARR, pE + p);
+            cp_async16(lslot + so + 2 * L::ARR, pF + p);
+            if (V) {
+                cp_async16(vslot + so, pV + p);
+                cp_async16(vslot + so + 16, pV + p + 4);
+            }
+        }
+        if (lane < ns) cp_async4(qslot + so, pQ + y);
+        if (lane + 32 < ns) cp_async4(qslot + so + 128, pQ + y + 32);
+    };
+
+#pragma unroll
+    for (int n = 0; n < PK_K - 1; ++n) {                                // prologue: slots 0 .. K-2 (quad-block 0)
+        if ((uint32_t)n < N) issue(n, dcur);
+        cp_async_commit();
+    }
+
+    for (uint32_t n = 0; n < N; ++n) {
+        const int j = n & 31;
+        {
+            const uint32_t m = n + PK_K - 1;                            // goes into the stage slot n - 1 released
+            if (m < N) {
+                if ((m >> 5) == (n >> 5)) issue(m, dcur);
+                else issue(m, dnxt);
+            }
+            cp_async_commit();
+        }
+        cp_async_wait<PK_K - 1>();                                      // slot n has landed (this lane's bytes)
+        const uint32_t dz = __shfl_sync(FULL, dcur.z, j), dw = __shfl_sync(FULL, dcur.w, j);
+        const uint32_t so = (n % PK_K) * L::STAGE;
+        const int nv = dz & 0xffff, tsr = dz >> 16, nf = dw & 0xff, ns = (dw >> 8) & 0xff;
+        if (nv > 0) {
+            // segments lane and 32 + lane of the item; an absent one has qe' = 0 and survives no prune
+            const uint32_t w0 = lane < ns ? lds32(qslot + so) : 0x80000000u;
+            const uint32_t w1 = lane + 32 < ns ? lds32(qslot + so + 128) : 0x80000000u;
+            const bool have = lane * 8 < nv;
+            uint4 Sv = make_uint4(0x80008000u, 0x80008000u, 0x80008000u, 0x80008000u), Ev = Sv, Fv = make_uint4(0, 0, 0, 0);
+            if (have) {
+                const int4 s_ = lds128(lslot + so), e_ = lds128(lslot + so + L::ARR), f_ = lds128(lslot + so + 2 * L::ARR);
+                Sv = make_uint4(s_.x, s_.y, s_.z, s_.w), Ev = make_uint4(e_.x, e_.y, e_.z, e_.w);
+                Fv = make_uint4(f_.x, f_.y, f_.z, f_.w);
+            }
+            uint32_t S[4] = {Sv.x, Sv.y, Sv.z, Sv.w};
+            const uint32_t E[4] = {Ev.x, Ev.y, Ev.z, Ev.w}, F[4] = {Fv.x, Fv.y, Fv.z, Fv.w};
+            if (V && have) {                                            // value < v: the record matches no query
+                const int4 v0 = lds128(vslot + so), v1 = lds128(vslot + so + 16);
+                const int vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (vv[2 * k] < a.v) S[k] = (S[k] & 0xffff0000u) | 0x8000u;
+                    if (vv[2 * k + 1] < a.v) S[k] = (S[k] & 0x0000ffffu) | 0x80000000u;
+                }
+            }
+            uint32_t c[4] = {0, 0, 0, 0};
+            // prune window of the group: smallest S (records are sorted by start: the first one; with -v the
+            // smallest surviving one) and largest E
+            uint32_t smin;
+            if (V) {
+                const uint32_t m2 = __vminu2(__vminu2(S[0], S[1]), __vminu2(S[2], S[3]));
+                smin = __reduce_min_sync(FULL, min(m2 & 0xffffu, m2 >> 16));
+            } else {
+                smin = __shfl_sync(FULL, S[0], 0) & 0xffffu;
+            }
+            const uint32_t x2 = __vmaxu2(__vmaxu2(E[0], E[1]), __vmaxu2(E[2], E[3]));
+            const uint32_t emax = __reduce_max_sync(FULL, max(x2 & 0xffffu, x2 >> 16));
+            // a segment can touch the group iff qe' > smallest start' and qs' < largest end':
+            //   QE - smin >= 0x8000  and  emax - QS >= 0x8000
+            const uint32_t qe_lo = smin + 0x8000u, qs_hi = emax - 0x8000u;     // QE >= qe_lo, QS <= qs_hi
+            const uint32_t qs2_0 = __byte_perm(w0, 0, 0x1010), qe2_0 = __byte_perm(w0, 0, 0x3232);
+            const uint32_t qs2_1 = __byte_perm(w1, 0, 0x1010), qe2_1 = __byte_perm(w1, 0, 0x3232);
+            const bool ok0 = (w0 >> 16) >= qe_lo && (w0 & 0xffffu) <= qs_hi;
+            const bool ok1 = (w1 >> 16) >= qe_lo && (w1 & 0xffffu) <= qs_hi;
+            // The surviving segments are compacted into the warp's list (first-bin ones, then later-bin ones)
+            // and streamed back with broadcast loads: 1 load + 16 ALU/FMA instructions per segment x 256 records.
+            const uint32_t lt = (1u << lane) - 1u;
+            const uint32_t list = wbase + L::LIST;
+            __syncwarp();                                               // the previous item's list has been read
+            // first-bin segments [0, nf): every record of the tile is a candidate
+            const unsigned f0 = __ballot_sync(FULL, ok0 && lane < nf), f1 = __ballot_sync(FULL, ok1 && lane + 32 < nf);
+            int nF = __popc(f0);
+            if (f0 >> lane & 1) sts64(list + 8u * __popc(f0 & lt), qs2_0, qe2_0);
+            if (f1 >> lane & 1) sts64(list + 8u * (nF + __popc(f1 & lt)), qs2_1, qe2_1);
+            nF += __popc(f1);
+            // later-bin segments [nf, ns): only the records that start inside this bin, i.e. index >= tS
+            int nL = 0;
+            uint32_t SL[4] = {S[0], S[1], S[2], S[3]};
+            if (ns > nf && tsr < nv) {
+                const int nb4 = min(max(tsr - lane * 8, 0), 8);         // this lane's records before the bin
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    SL[k] = nb4 >= 2 * k + 2 ? 0x80008000u : (nb4 == 2 * k + 1 ? ((S[k] & 0xffff0000u) | 0x8000u) : S[k]);
+                // prune with the first (surviving) record that starts inside the bin
+                const uint32_t l2 = __vminu2(__vminu2(SL[0], SL[1]), __vminu2(SL[2], SL[3]));
+                const uint32_t slmin = __reduce_min_sync(FULL, min(l2 & 0xffffu, l2 >> 16));
+                const uint32_t qel = slmin + 0x8000u;
+                const bool okl0 = (w0 >> 16) >= qel && (w0 & 0xffffu) <= qs_hi;
+                const bool okl1 = (w1 >> 16) >= qel && (w1 & 0xffffu) <= qs_hi;
+                const unsigned l0 = __ballot_sync(FULL, okl0 && lane >= nf), l1 = __ballot_sync(FULL, okl1 && lane + 32 >= nf);
+                if (l0 >> lane & 1) sts64(list + 8u * (nF + __popc(l0 & lt)), qs2_0, qe2_0);
+                nL = __popc(l0);
+                if (l1 >> lane & 1) sts64(list + 8u * (nF + nL + __popc(l1 & lt)), qs2_1, qe2_1);
+                nL += __popc(l1);
+            }
+            __syncwarp();
+            count_pairs(list, 0, nF, S, E, c);
+            count_pairs(list, nF, nF + nL, SL, E, c);
+            // hits[file] += count: one atomic per record that overlaps anything
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (c[k]) {
+                    const uint32_t c0 = c[k] & 0xffffu, c1 = c[k] >> 16, f0 = F[k] & 0xffffu, f1 = F[k] >> 16;
+                    if (SMEM) {
+                        if (c0) atomicAdd(&hist[f0], c0);
+                        if (c1) atomicAdd(&hist[f1], c1);
+                    } else {
+                        if (c0) atomicAdd(&a.hits[f0], (unsigned long long)c0);
+                        if (c1) atomicAdd(&a.hits[f1], (unsigned long long)c1);
+                    }
+                }
+            }
+        }
+        if (j == 31) {                                                  // next quad-block of descriptors
+            dcur = dnxt;
+            dnxt = load_desc((n >> 5) + 2);
+        }
+    }
+    cp_async_wait<0>();
+    if (SMEM) {
+        __syncthreads();
+        for (int f = threadIdx.x; f < db.nfiles; f += blockDim.x) {
+            const uint32_t c = hist[f];
+            if (c) atomicAdd(&a.hits[f], (unsigned long long)c);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // -f: one warp per segment, in the reference's visiting order (get_overlaps_f1, src/igd_search.c:537-620).
 //   1. 32-ary ballot search for cnt = #{start < qe} in the tile (tL = cnt-1): every round the 32 lanes
 //      probe 32 evenly spaced records and one ballot narrows the range 32x -- 2 dependent loads for a
@@ -729,7 +1049,7 @@ __global__ void __launch_bounds__(512) k_search(const SearchArgs a)
         const int4 sg = __ldg(reinterpret_cast<const int4 *>(&a.segs[s]));
         const int qs = sg.x, qe = sg.y;
         const int4 tm = __ldg(reinterpret_cast<const int4 *>(&db.tiles[sg.z]));
-        const int64_t off = (int64_t)(uint32_t)tm.x * 4;
+        const int64_t off = (int64_t)(uint32_t)tm.x * 8;
         const int tS = ((uint32_t)sg.w >> 31) ? tm.z : 0;
         const uint32_t sid = (uint32_t)sg.w & 0x7fffffffu;
         const int hi = warp_count_lt(db.start + off, tm.y, qe, lane);        // tL + 1
@@ -798,7 +1118,7 @@ __global__ void __launch_bounds__(256) k_hitsmap(DbView db, const int32_t *__res
         const int t = __ldg(&rec_tile[r]);
         if (t < 0) continue;                                 // pad slot
         const int4 tm = __ldg(reinterpret_cast<const int4 *>(&db.tiles[t]));
-        const int64_t off = (int64_t)(uint32_t)tm.x * 4;
+        const int64_t off = (int64_t)(uint32_t)tm.x * 8;
         const int j = (int)(r - off);
         const int qs = __ldg(&db.start[r]), qe = __ldg(&db.end[r]);
         if (V && !(__ldg(&db.value[r]) > v)) continue;
@@ -836,8 +1156,8 @@ __global__ void k_rec_tile(const TileMeta *__restrict__ tiles, int32_t T, int32_
     const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
     for (int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < T; t += nw) {
         const TileMeta m = tiles[t];
-        const int64_t off = (int64_t)m.off4 * 4;
-        const int np = (m.n + 3) & ~3;
+        const int64_t off = (int64_t)m.off8 * 8;
+        const int np = (m.n + 7) & ~7;
         for (int i = lane; i < np; i += 32) rec_tile[off + i] = i < m.n ? (int32_t)t : -1;
     }
 }
@@ -992,6 +1312,8 @@ struct igdb_dev {
     TileMeta *tiles = nullptr;
     int64_t *d_toff = nullptr;
     int32_t *start = nullptr, *end = nullptr, *idx = nullptr, *value = nullptr, *tbase = nullptr;
+    uint16_t *ps = nullptr, *pe = nullptr, *pf = nullptr;  // packed count-mode copies (NULL: M_ALL32 only)
+    bool packed = false;
     int64_t bytes = 0;
     int64_t launches = 0;
     cudaStream_t stream = nullptr;
@@ -1027,9 +1349,11 @@ struct igdb_dev {
     int4 *items = nullptr;
     int64_t item_cap = 0;
     int64_t db_groups = 0;                                  // sum over tiles of ceil(n / GROUP)
-    int count_grid[2] = {0, 0};                             // CTAs of k_count_items<V> (0 = not yet computed)
+    int count_grid[2][2] = {{0, 0}, {0, 0}};                // CTAs of the search kernel [packed][V] (0 = not set up)
+    int64_t last_plan[4] = {0, 0, 0, 0};                    // segments, items, records, bytes of the last batch
     struct Pending {                                        // count batch enqueued but not yet settled
         bool active = false, mode_v = false;
+        int mode = M_ALL32;
         int64_t n = 0;
         const int32_t *ctg = nullptr, *qs = nullptr, *qe = nullptr;
         int32_t v = 0;
@@ -1040,6 +1364,7 @@ struct igdb_dev {
     {
         DbView v;
         v.tiles = tiles, v.start = start, v.end = end, v.idx = idx, v.value = value, v.tbase = tbase;
+        v.ps = ps, v.pe = pe, v.pf = pf;
         v.nctg = nctg, v.nbp = nbp, v.nfiles = nfiles, v.ntiles = T;
         return v;
     }
@@ -1153,20 +1478,23 @@ int build_segments(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_t *qs
 // plan check on the device that it fits the scratch buffers and do nothing otherwise; the host looks at
 // the plan's totals when it settles the batch and, in the rare case they did not fit (first batch of a
 // larger size), grows the buffers and runs the batch again -- or splits it when the plan itself is too big.
-template <bool V>
+template <bool V, bool PK>
 int count_geometry(igdb_dev *d, int *grid, int *threads, size_t *shm, bool *smem)
 {
+    using LP = PackedSmem<V>;
+    using L32 = CountSmem<V>;
     // the shared histogram is used while it leaves room for at least 8 warps' pipelines
-    *smem = CountSmem<V>::warps(d->nfiles, true) >= 8;
-    const int nw = CountSmem<V>::warps(d->nfiles, *smem);
-    *shm = CountSmem<V>::cta_bytes(d->nfiles, *smem, nw);
+    *smem = (PK ? LP::warps(d->nfiles, true) : L32::warps(d->nfiles, true)) >= 8;
+    const int nw = PK ? LP::warps(d->nfiles, *smem) : L32::warps(d->nfiles, *smem);
+    *shm = PK ? LP::cta_bytes(d->nfiles, *smem, nw) : L32::cta_bytes(d->nfiles, *smem, nw);
     *threads = nw * 32;
-    if (d->count_grid[V] == 0) {
-        if (*smem) CK(cudaFuncSetAttribute(k_count_items<V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*shm));
-        else CK(cudaFuncSetAttribute(k_count_items<V, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*shm));
-        d->count_grid[V] = d->sm_count;
+    if (d->count_grid[PK][V] == 0) {
+        const void *k = PK ? (*smem ? (const void *)k_count_packed<V, true> : (const void *)k_count_packed<V, false>)
+                           : (*smem ? (const void *)k_count_items<V, true> : (const void *)k_count_items<V, false>);
+        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*shm));
+        d->count_grid[PK][V] = d->sm_count;
     }
-    *grid = d->count_grid[V];
+    *grid = d->count_grid[PK][V];
     return 0;
 }
 
@@ -1176,15 +1504,16 @@ int64_t item_limit(const igdb_dev *d, int grid) { return ((int64_t)(1 << 17) - 1
 // the kernels may touch up to 32 descriptors / 1 segment past the plan's totals (padding)
 constexpr int64_t CAP_SLACK = 64;
 
-template <bool V>
+template <bool V, int MODE>
 int enqueue_count(igdb_dev *d, const igdb_dev::Pending &p)
 {
+    constexpr bool PK = MODE == M_PACKED;
     cudaStream_t st = p.st;
     const DbView db = d->view();
     int grid = 0, threads = 0;
     size_t shm = 0;
     bool smem = false;
-    if (count_geometry<V>(d, &grid, &threads, &shm, &smem)) return -1;
+    if (count_geometry<V, PK>(d, &grid, &threads, &shm, &smem)) return -1;
     if (grow(&d->csegs, &d->cseg_cap, std::max<int64_t>(2 * p.n + 2 * d->T, 4096), 1, 1)) return -1;
     if (grow(&d->items, &d->item_cap, std::min<int64_t>(d->db_groups + p.n / 64, item_limit(d, grid)) + 1024, 1, 1))
         return -1;
@@ -1194,7 +1523,7 @@ int enqueue_count(igdb_dev *d, const igdb_dev::Pending &p)
     const int thr = 256;
     const int nb = (int)((p.n + thr - 1) / thr);
     const int sb = (d->T + SCAN_B - 1) / SCAN_B;
-    k_cseg_count<V><<<nb, thr, 0, st>>>(db, p.n, p.ctg, p.qs, p.qe, d->cnt2);
+    k_cseg_count<V, MODE><<<nb, thr, 0, st>>>(db, p.n, p.ctg, p.qs, p.qe, d->cnt2);
     k_plan1<<<sb, SCAN_T, 0, st>>>(db, d->cnt2, d->plan_tmp, d->plan_bsum);
     k_scan2<Plan><<<1, SCAN_T, 0, st>>>(d->plan_bsum, sb);
     k_plan3<<<sb, SCAN_T, 0, st>>>(d->T, d->cnt2, d->plan_tmp, d->plan_bsum, sb, d->cseg_off, d->cseg_mid,
@@ -1202,18 +1531,25 @@ int enqueue_count(igdb_dev *d, const igdb_dev::Pending &p)
     // (the fill reads the later-bin counters that the scatter counts back down to zero)
     k_item_fill<<<(d->T + 255) / 256, 256, 0, st>>>(db, d->cseg_off, d->cseg_mid, d->cnt2, d->item_off, d->plan_tot,
                                                   seg_cap, item_cap, d->items);
-    CK(cudaMemcpyAsync((void *)d->h_plan, d->plan_tot, 24, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync((void *)d->h_plan, d->plan_tot, 32, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(d->plan_ev, st));
-    k_cseg_scatter<V><<<nb, thr, 0, st>>>(db, p.n, p.ctg, p.qs, p.qe, d->cnt2, d->cseg_off, d->cseg_mid,
-                                           d->plan_tot, seg_cap, item_cap, d->csegs);
+    k_cseg_scatter<V, MODE><<<nb, thr, 0, st>>>(db, p.n, p.ctg, p.qs, p.qe, d->cnt2, d->cseg_off, d->cseg_mid,
+                                                 d->plan_tot, seg_cap, item_cap, d->csegs);
     CountArgs a{};
     a.db = db, a.items = d->items, a.segs = d->csegs, a.tot = d->plan_tot;
     a.seg_cap = seg_cap, a.item_cap = item_cap, a.v = p.v, a.hits = p.hits;
-    CK(cudaEventRecord(d->kev[0], st));
-    if (smem) k_count_items<V, true><<<grid, threads, shm, st>>>(a);
-    else k_count_items<V, false><<<grid, threads, shm, st>>>(a);
-    CK(cudaEventRecord(d->kev[1], st));
-    d->kev_valid = true;
+    if (MODE != M_ABN32) CK(cudaEventRecord(d->kev[0], st));
+    if (PK) {
+        if (smem) k_count_packed<V, true><<<grid, threads, shm, st>>>(a);
+        else k_count_packed<V, false><<<grid, threads, shm, st>>>(a);
+    } else {
+        if (smem) k_count_items<V, true><<<grid, threads, shm, st>>>(a);
+        else k_count_items<V, false><<<grid, threads, shm, st>>>(a);
+    }
+    if (MODE != M_ABN32) {
+        CK(cudaEventRecord(d->kev[1], st));
+        d->kev_valid = true;
+    }
     d->launches += 7;
     CK(cudaGetLastError());
     return 0;
@@ -1222,23 +1558,40 @@ int enqueue_count(igdb_dev *d, const igdb_dev::Pending &p)
 int enqueue_count(igdb_dev *d, const igdb_dev::Pending &p)
 {
     if (p.n <= 0) return 0;
-    return p.mode_v ? enqueue_count<true>(d, p) : enqueue_count<false>(d, p);
+    switch (p.mode) {
+    case M_PACKED: return p.mode_v ? enqueue_count<true, M_PACKED>(d, p) : enqueue_count<false, M_PACKED>(d, p);
+    case M_ABN32: return p.mode_v ? enqueue_count<true, M_ABN32>(d, p) : enqueue_count<false, M_ABN32>(d, p);
+    default: return p.mode_v ? enqueue_count<true, M_ALL32>(d, p) : enqueue_count<false, M_ALL32>(d, p);
+    }
 }
 
 // wait for the plan of the enqueued batch p; make sure it ran (see above)
 int settle_count(igdb_dev *d, const igdb_dev::Pending &p)
 {
     if (p.n <= 0) return 0;
+    const bool pk = p.mode == M_PACKED;
     for (;;) {
         CK(cudaEventSynchronize(d->plan_ev));
-        const unsigned long long nsegs = d->h_plan[0], nitems = d->h_plan[1];
+        const unsigned long long nsegs = d->h_plan[0], nitems = d->h_plan[1], nrec = d->h_plan[2], nabn = d->h_plan[3];
         if (getenv("IGD_B200_DEBUG"))
-            fprintf(stderr, "[igd_b200] count batch: n=%lld segments=%llu items=%llu (caps %lld / %lld)\n",
-                    (long long)p.n, nsegs, nitems, (long long)d->cseg_cap, (long long)d->item_cap);
-        const int64_t lim = item_limit(d, d->count_grid[p.mode_v]);
+            fprintf(stderr, "[igd_b200] count batch (mode %d): n=%lld segments=%llu items=%llu left=%llu (caps %lld / %lld)\n",
+                    p.mode, (long long)p.n, nsegs, nitems, nabn, (long long)d->cseg_cap, (long long)d->item_cap);
+        const int64_t lim = item_limit(d, d->count_grid[pk][p.mode_v]);
         if (nsegs <= (unsigned long long)std::min<int64_t>(d->cseg_cap - CAP_SLACK, 0x7fffffff) &&
-            nitems <= (unsigned long long)std::min<int64_t>(d->item_cap - CAP_SLACK, lim))
+            nitems <= (unsigned long long)std::min<int64_t>(d->item_cap - CAP_SLACK, lim)) {
+            if (p.mode != M_ABN32) {
+                // what the search kernel of this batch reads: descriptors, records, segments
+                const int64_t rb = pk ? (p.mode_v ? 10 : 6) : (p.mode_v ? 16 : 12), sgb = pk ? 4 : 8;
+                d->last_plan[0] = (int64_t)nsegs, d->last_plan[1] = (int64_t)nitems, d->last_plan[2] = (int64_t)nrec;
+                d->last_plan[3] = 16 * (int64_t)nitems + rb * (int64_t)nrec + sgb * (int64_t)nsegs;
+            }
+            if (pk && nabn > 0) {           // the queries the packed layout cannot express: second pipeline
+                igdb_dev::Pending q = p;
+                q.mode = M_ABN32;
+                if (enqueue_count(d, q) || settle_count(d, q)) return -1;
+            }
             return 0;
+        }
         // none of this batch's kernels wrote anything, but its segment counters were not counted back down
         CK(cudaStreamSynchronize(p.st));
         CK(cudaMemsetAsync(d->cnt2, 0, ((size_t)2 * d->T + 2) * 4, p.st));
@@ -1287,7 +1640,7 @@ void igdb_dev_destroy(igdb_dev *d)
     void *ptrs[] = {d->tiles, d->d_toff, d->start, d->end, d->idx, d->value, d->tbase, d->d_stage, d->q_ctg,
                     d->q_qs, d->q_qe, d->tile_cnt, d->tile_off, d->nseg, d->qseg_off, d->bsum, d->segs,
                     d->seg_hits, d->seg_out_off, d->d_hits, d->cnt2, d->cseg_off, d->cseg_mid, d->item_off,
-                    d->plan_tmp, d->plan_bsum, d->plan_tot, d->csegs, d->items};
+                    d->plan_tmp, d->plan_bsum, d->plan_tot, d->csegs, d->items, d->ps, d->pe, d->pf};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (d->pinned) cudaFreeHost(d->pinned);
@@ -1319,44 +1672,54 @@ static int create_impl(igdb_dev *d, const int32_t *ntile, const int32_t *ncnt)
     d->T = tbase[d->nctg];
     std::vector<TileMeta> meta((size_t)d->T);
     d->toff.assign((size_t)d->T + 1, 0);
-    int64_t p4 = 0;
+    int64_t p8 = 0;
     for (int c = 0, t = 0; c < d->nctg; ++c)
         for (int j = 0; j < ntile[c]; ++j, ++t) {
             const int32_t n = ncnt[t];
-            meta[t].off4 = (uint32_t)p4;
+            meta[t].off8 = (uint32_t)p8;
             meta[t].n = n;
             meta[t].ts = d->nbp * j;            // bin boundary; k_tile_meta turns it into tS
             meta[t].s0 = 0x7fffffff;
             d->toff[t + 1] = d->toff[t] + n;
             d->db_groups += (n + GROUP - 1) / GROUP;
-            p4 += (n + 3) / 4;
+            p8 += (n + 7) / 8;
         }
-    if (p4 >= (int64_t)0xffffffff) {
+    if (p8 >= (int64_t)0xffffffff) {
         snprintf(g_err, sizeof g_err, "database too large for 32-bit tile offsets");
         return -1;
     }
     d->nrec = d->toff[d->T];
-    d->P = p4 * 4;
+    d->P = p8 * 8;
     if (dev_alloc(d, &d->tiles, (size_t)d->T) || dev_alloc(d, &d->d_toff, (size_t)d->T + 1) ||
-        dev_alloc(d, &d->tbase, (size_t)d->nctg + 1) || dev_alloc(d, &d->start, (size_t)d->P + 4) ||
-        dev_alloc(d, &d->end, (size_t)d->P + 4) || dev_alloc(d, &d->idx, (size_t)d->P + 4) ||
-        dev_alloc(d, &d->value, (size_t)d->P + 4) || dev_alloc(d, &d->tile_cnt, (size_t)d->T + 1) ||
+        dev_alloc(d, &d->tbase, (size_t)d->nctg + 1) || dev_alloc(d, &d->start, (size_t)d->P + 8) ||
+        dev_alloc(d, &d->end, (size_t)d->P + 8) || dev_alloc(d, &d->idx, (size_t)d->P + 8) ||
+        dev_alloc(d, &d->value, (size_t)d->P + 8) || dev_alloc(d, &d->tile_cnt, (size_t)d->T + 1) ||
         dev_alloc(d, &d->tile_off, (size_t)d->T + 1) || dev_alloc(d, &d->d_hits, (size_t)d->nfiles) ||
         dev_alloc(d, &d->cnt2, (size_t)2 * d->T + 2) || dev_alloc(d, &d->cseg_off, (size_t)d->T + 1) ||
         dev_alloc(d, &d->cseg_mid, (size_t)d->T + 1) || dev_alloc(d, &d->item_off, (size_t)d->T + 1) ||
         dev_alloc(d, &d->plan_tmp, (size_t)d->T + 1) ||
-        dev_alloc(d, &d->plan_bsum, (size_t)(d->T + SCAN_B - 1) / SCAN_B + 2) || dev_alloc(d, &d->plan_tot, 4))
+        dev_alloc(d, &d->plan_bsum, (size_t)(d->T + SCAN_B - 1) / SCAN_B + 2) || dev_alloc(d, &d->plan_tot, 8))
+        return -1;
+    // packed count-mode copies: tile-relative coordinates need nbp + 1 < 2^15, file indices 16 bits
+    d->packed = d->nbp <= 16384 && d->nfiles <= 65536 && !getenv("IGD_B200_NO_PACKED");
+    if (d->packed && (dev_alloc(d, &d->ps, (size_t)d->P + 8) || dev_alloc(d, &d->pe, (size_t)d->P + 8) ||
+                      dev_alloc(d, &d->pf, (size_t)d->P + 8)))
         return -1;
     CK(cudaMemcpy(d->tiles, meta.data(), meta.size() * sizeof(TileMeta), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d->d_toff, d->toff.data(), d->toff.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d->tbase, tbase.data(), tbase.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     // pad records (tiles are padded to a multiple of 4): start = INT_MAX, end = INT_MIN -- overlap no query
-    const unsigned fb = (unsigned)std::min<int64_t>(((int64_t)d->P + 4 + 255) / 256, 148 * 32);
-    k_fill<<<fb, 256>>>(d->start, (int64_t)d->P + 4, IMAX);
-    k_fill<<<fb, 256>>>(d->end, (int64_t)d->P + 4, IMIN);
-    k_fill<<<fb, 256>>>(d->value, (int64_t)d->P + 4, IMIN);
+    const unsigned fb = (unsigned)std::min<int64_t>(((int64_t)d->P + 8 + 255) / 256, 148 * 32);
+    k_fill<<<fb, 256>>>(d->start, (int64_t)d->P + 8, IMAX);
+    k_fill<<<fb, 256>>>(d->end, (int64_t)d->P + 8, IMIN);
+    k_fill<<<fb, 256>>>(d->value, (int64_t)d->P + 8, IMIN);
+    if (d->packed) {
+        k_fill16<<<fb, 256>>>(d->ps, (int64_t)d->P + 8, (uint16_t)0x8000);
+        k_fill16<<<fb, 256>>>(d->pe, (int64_t)d->P + 8, (uint16_t)0x8000);
+        CK(cudaMemset(d->pf, 0, ((size_t)d->P + 8) * 2));
+    }
     CK(cudaGetLastError());
-    CK(cudaMemset(d->idx, 0, ((size_t)d->P + 4) * 4));
+    CK(cudaMemset(d->idx, 0, ((size_t)d->P + 8) * 4));
     CK(cudaMemset(d->tile_cnt, 0, ((size_t)d->T + 1) * 4));
     CK(cudaMemset(d->cnt2, 0, ((size_t)2 * d->T + 2) * 4));
     return 0;
@@ -1400,7 +1763,8 @@ int igdb_dev_upload(igdb_dev *d, int64_t rec0, int64_t nrec, const void *aos)
     CK(cudaMemcpyAsync(d->d_stage, aos, bytes, cudaMemcpyHostToDevice, d->stream));
     const int thr = 256;
     k_transpose<<<(unsigned)((nrec + thr - 1) / thr), thr, 0, d->stream>>>(
-        (const int4 *)d->d_stage, rec0, nrec, d->d_toff, d->T, d->tiles, d->start, d->end, d->idx, d->value);
+        (const int4 *)d->d_stage, rec0, nrec, d->d_toff, d->T, d->tiles, d->start, d->end, d->idx, d->value, d->nbp,
+        d->ps, d->pe, d->pf);
     d->launches += 1;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(d->stream));       // the caller reuses its host buffer
@@ -1433,10 +1797,11 @@ float igdb_dev_last_search_ms(igdb_dev *d)
 }
 
 int64_t igdb_dev_bytes(const igdb_dev *d) { return d->bytes; }
-void igdb_dev_last_plan(const igdb_dev *d, int64_t out[3])
+void igdb_dev_last_plan(const igdb_dev *d, int64_t out[4])
 {
-    out[0] = (int64_t)d->h_plan[0], out[1] = (int64_t)d->h_plan[1], out[2] = (int64_t)d->h_plan[2];
+    for (int k = 0; k < 4; ++k) out[k] = d->last_plan[k];
 }
+int igdb_dev_packed(const igdb_dev *d) { return d->packed ? 1 : 0; }
 int64_t igdb_dev_launches(const igdb_dev *d) { return d->launches; }
 
 int igdb_dev_count_device(igdb_dev *d, int64_t n, const int32_t *d_ctg, const int32_t *d_qs, const int32_t *d_qe,
@@ -1454,6 +1819,7 @@ int igdb_dev_count_device(igdb_dev *d, int64_t n, const int32_t *d_ctg, const in
         p.mode_v = mode_v != 0, p.n = std::min(BATCH, n - a);
         p.ctg = d_ctg + a, p.qs = d_qs + a, p.qe = d_qe + a, p.v = v;
         p.hits = (unsigned long long *)d_hits, p.st = st;
+        p.mode = d->packed ? M_PACKED : M_ALL32;
         if (enqueue_count(d, p)) return -1;
         if (a + BATCH < n) {                        // the scratch buffers are reused by the next chunk
             if (settle_count(d, p)) return -1;
@@ -1493,6 +1859,7 @@ int igdb_dev_count_host(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_
         igdb_dev::Pending p;
         p.mode_v = mode_v != 0, p.n = m, p.ctg = d->q_ctg, p.qs = d->q_qs, p.qe = d->q_qe, p.v = v;
         p.hits = d->d_hits, p.st = st;
+        p.mode = d->packed ? M_PACKED : M_ALL32;
         if (enqueue_count(d, p)) return -1;
         const bool last = a + BATCH >= n;
         if (last) {                                 // the result copy rides behind the kernels; no sync yet
@@ -1736,7 +2103,7 @@ int64_t igdb_dev_hitsmap_host(igdb_dev *d, int32_t v, uint32_t *hitmap)
     int32_t *d_rt = nullptr;
     unsigned long long *d_n = nullptr;
     CK(cudaMalloc((void **)&d_map, std::max<size_t>(cells, 1) * 4));
-    CK(cudaMalloc((void **)&d_rt, ((size_t)d->P + 4) * 4));
+    CK(cudaMalloc((void **)&d_rt, ((size_t)d->P + 8) * 4));
     CK(cudaMalloc((void **)&d_n, 8));
     CK(cudaMemcpyAsync(d_map, hitmap, cells * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(d_n, 0, 8, st));

@@ -25,8 +25,11 @@ int igdb_dev_finalize(igdb_dev *d);
 void igdb_dev_destroy(igdb_dev *d);
 int64_t igdb_dev_bytes(const igdb_dev *d);
 int64_t igdb_dev_launches(const igdb_dev *d);
-/* plan of the last settled count batch: segments, work items, records read by the items */
-void igdb_dev_last_plan(const igdb_dev *d, int64_t out[3]);
+/* plan of the last settled count batch: segments, work items, records read by the items, and the bytes
+ * the search kernel had to read for them */
+void igdb_dev_last_plan(const igdb_dev *d, int64_t out[4]);
+/* 1 if count mode runs on the packed 16-bit layout (nbp <= 16384 and nFiles <= 65536) */
+int igdb_dev_packed(const igdb_dev *d);
 /* device time of the last count-mode search kernel (CUDA events on its stream); < 0 if none */
 float igdb_dev_last_search_ms(igdb_dev *d);
 void *igdb_dev_pinned(igdb_dev *d, size_t bytes);   /* reusable pinned staging buffer (upload) */

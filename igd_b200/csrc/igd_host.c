@@ -170,7 +170,7 @@ const char *igd_b200_file_name(const igd_b200_t *h, int32_t i) { return i >= 0 &
 const char *igd_b200_ctg_name(const igd_b200_t *h, int32_t c) { return c >= 0 && c < h->nctg ? h->cname[c] : ""; }
 int64_t igd_b200_device_bytes(const igd_b200_t *h) { return igdb_dev_bytes(h->dev); }
 int64_t igd_b200_launch_count(const igd_b200_t *h) { return igdb_dev_launches(h->dev); }
-void igd_b200_last_plan(const igd_b200_t *h, int64_t out[3]) { igdb_dev_last_plan(h->dev, out); }
+void igd_b200_last_plan(const igd_b200_t *h, int64_t out[4]) { igdb_dev_last_plan(h->dev, out); }
 float igd_b200_last_search_kernel_ms(igd_b200_t *h) { return igdb_dev_last_search_ms(h->dev); }
 void igd_b200_last_timing(const igd_b200_t *h, float t[3]) { t[0] = h->t_ms[0], t[1] = h->t_ms[1], t[2] = h->t_ms[2]; }
 

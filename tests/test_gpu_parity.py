@@ -157,3 +157,72 @@ def test_degenerate_and_extreme_queries(dense_db, O, api):
         got, _ = g.count(ctg, qs, qe, v)
         assert np.array_equal(got, want), v
     g.close()
+
+
+def _abnormal_mix(n=30000, frac=0.15, seed=5):
+    """A query batch in which `frac` of the queries have qs >= qe or qs < 0 (parse_bed accepts them: only
+    en > 0 is required, src/igd_base.c:69) -- the packed layout hands exactly these to the int32 pipeline."""
+    q = make_queries(seed, n, ("lognormal", 6.5, 1.3))
+    rng = np.random.default_rng(seed)
+    qs, qe = q.start.copy(), q.end.copy()
+    pick = rng.random(n) < frac
+    kind = rng.integers(0, 4, n)
+    swap = pick & (kind == 0)
+    qs[swap], qe[swap] = q.end[swap], np.maximum(q.start[swap], 1)          # qs > qe
+    eq = pick & (kind == 1)
+    qe[eq] = np.maximum(qs[eq], 1)                                          # qs == qe (or 0, 1)
+    qs[eq] = qe[eq]
+    neg = pick & (kind == 2)
+    qs[neg] = -rng.integers(1, 40000, int(neg.sum()))                       # negative start
+    far = pick & (kind == 3)
+    qs[far] = qe[far] + rng.integers(0, 3000, int(far.sum()))               # a record must contain [qe, qs]
+    return q.ctg, qs.astype(np.int32), qe.astype(np.int32)
+
+
+@pytest.mark.parametrize("v", [0, 400])
+def test_count_abnormal_mix(dense_db, O, api, v):
+    ctg, qs, qe = _abnormal_mix()
+    odb = O.OracleDB(dense_db)
+    g = api.IGD(dense_db)
+    want, _ = odb.count(ctg, qs, qe, v)
+    got, n = g.count(ctg, qs, qe, v)
+    assert want.sum() > 0 and np.array_equal(got, want) and n == want.sum()
+    # the same batch again: the second (int32) pipeline must leave the scratch state clean
+    got2, _ = g.count(ctg, qs, qe, v)
+    assert np.array_equal(got2, want)
+    g.close()
+
+
+@pytest.mark.parametrize("v", [0, 500])
+def test_count_int32_layout(dense_db, O, api, v, monkeypatch):
+    """The int32 record layout (what databases with nbp > 16384 or more than 65536 files use) gives the same
+    hits[] as the packed 16-bit layout and the oracle."""
+    monkeypatch.setenv("IGD_B200_NO_PACKED", "1")
+    g = api.IGD(dense_db)
+    odb = O.OracleDB(dense_db)
+    for ctg, qs, qe in ((lambda q: (q.ctg, q.start, q.end))(_queries("fixed1k")), _abnormal_mix(8000)):
+        want, _ = odb.count(ctg, qs, qe, v)
+        got, _ = g.count(ctg, qs, qe, v)
+        assert np.array_equal(got, want)
+    assert g.last_plan()["own_bytes"] > 0
+    g.close()
+
+
+@pytest.mark.parametrize("b", [9, 12, 15])
+def test_count_other_bin_sizes(workdir, O, api, b):
+    """igd create -b: nbp = 2^b.  b <= 14 runs on the packed layout, b = 15 on int32."""
+    stem = os.path.join(workdir, f"bins{b}")
+    files = [synth.gen_intervals(4100 + i, 2500, ("lognormal", 6.5, 1.4), SMALL_SIZES) for i in range(11)]
+    synth.write_igd_direct(stem, files, names=SMALL_NAMES, nbp=1 << b)
+    odb = O.OracleDB(stem + ".igd")
+    g = api.IGD(stem + ".igd")
+    assert g.nbp == 1 << b
+    ctg, qs, qe = _abnormal_mix(15000, 0.05, seed=b)
+    for v in (0, 300):
+        want, _ = odb.count(ctg, qs, qe, v)
+        got, _ = g.count(ctg, qs, qe, v)
+        assert want.sum() > 0 and np.array_equal(got, want), (b, v)
+    per, _, s, e, f = odb.full(ctg[:3000], qs[:3000], qe[:3000])
+    qoff, gs, ge, gf = g.full(ctg[:3000], qs[:3000], qe[:3000])
+    assert np.array_equal(np.diff(qoff), per) and np.array_equal(gs, s) and np.array_equal(ge, e) and np.array_equal(gf, f)
+    g.close()
