@@ -366,48 +366,135 @@ __device__ __forceinline__ Plan plan_of_tile(const DbView &db, const uint32_t *_
     return Plan{(s + 1) & ~1ull, g * ((s + SMAX - 1) / SMAX)};
 }
 
-__global__ void __launch_bounds__(SCAN_T) k_plan1(DbView db, const uint32_t *__restrict__ cnt2,
-                                                   Plan *__restrict__ tmp, Plan *__restrict__ bsum)
-{
-    const int32_t T = db.ntiles;
-    const int64_t base = (int64_t)blockIdx.x * SCAN_B + (int64_t)threadIdx.x * SCAN_I;
-    Plan v[SCAN_I], s = Plan{0, 0};
-#pragma unroll
-    for (int k = 0; k < SCAN_I; ++k) {
-        v[k] = base + k < T ? plan_of_tile(db, cnt2, (int32_t)(base + k)) : Plan{0, 0};
-        s += v[k];
-    }
-    Plan tot, ex = block_exclusive<Plan>(s, &tot);
-#pragma unroll
-    for (int k = 0; k < SCAN_I; ++k) {
-        if (base + k < T) tmp[base + k] = ex;
-        ex += v[k];
-    }
-    if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
-}
+// The whole plan in ONE launch: a chained scan over the tiles fused with the item fill.  The grid has at most one
+// CTA per SM (all co-resident), CTA b owns a contiguous range of tiles:
+//   1. block-reduce the plan of its range and publish it (agg[b], then flag[b] = epoch);
+//   2. wait for every CTA's aggregate: the sum of the earlier ones is this CTA's prefix, the sum of all is the
+//      batch total -- if that does not fit the scratch buffers nothing more is written (the host grows them
+//      and runs the batch again);
+//   3. walk the range again in chunks of SCAN_T tiles: block scan + running carry give each tile its first
+//      segment (seg_off), its first later-bin segment (seg_mid) and its first work item, and the tile's items are
+//      written on the spot.
+// Work items of tile t, group-major.  An item is self-contained, so the search kernel goes from the item to
+// its records and segments without touching the tile table:
+//   x = position of the group's first record in the SoA arrays, in units of 8 records
+//   y = first segment
+//   z = records in the group (bits 0-8, 1..GROUP) | first record of the group that starts inside this bin
+//       (bits 9-17, 0..GROUP: the dedupe rule of later bins) | number of first-bin segments (bits 18-24, 0..64;
+//       the later-bin segments follow them) | number of segments (bits 25-31, 1..64)
+//   w = 0
+struct PlanAgg {
+    unsigned long long segs, items, recs;
+};
 
-__global__ void __launch_bounds__(SCAN_T) k_plan3(int32_t T, const uint32_t *__restrict__ cnt2,
-                                                   const Plan *__restrict__ tmp, const Plan *__restrict__ bsum, int nb,
-                                                   uint32_t *__restrict__ seg_off, uint32_t *__restrict__ seg_mid,
-                                                   uint32_t *__restrict__ item_off, unsigned long long *__restrict__ tot)
+__global__ void __launch_bounds__(SCAN_T) k_plan(DbView db, const uint32_t *__restrict__ cnt2, uint32_t epoch,
+                                                  volatile PlanAgg *agg, volatile uint32_t *flag,
+                                                  uint32_t *__restrict__ seg_off, uint32_t *__restrict__ seg_mid,
+                                                  unsigned long long *__restrict__ tot, unsigned long long seg_cap,
+                                                  unsigned long long item_cap, int4 *__restrict__ items)
 {
-    const int64_t base = (int64_t)blockIdx.x * SCAN_B + (int64_t)threadIdx.x * SCAN_I;
-    const Plan add = bsum[blockIdx.x];
-#pragma unroll
-    for (int k = 0; k < SCAN_I; ++k) {
-        const int64_t t = base + k;
-        if (t < T) {
-            const Plan p = tmp[t] + add;
-            seg_off[t] = (uint32_t)p.segs;
-            seg_mid[t] = (uint32_t)p.segs + __ldg(&cnt2[2 * t]);
-            item_off[t] = (uint32_t)p.items;
+    __shared__ unsigned long long red[3][SCAN_T / 32];
+    __shared__ unsigned long long sh_prefix[2], sh_total[3];
+    const int32_t T = db.ntiles;
+    const int G = gridDim.x, b = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int32_t per = (T + G - 1) / G, t0 = min(b * per, T), t1 = min(t0 + per, T);
+
+    // 1. aggregate of this CTA's range
+    unsigned long long segs = 0, its = 0, recs = 0;
+    for (int32_t t = t0 + threadIdx.x; t < t1; t += SCAN_T) {
+        const Plan p = plan_of_tile(db, cnt2, t);
+        segs += p.segs, its += p.items;
+        if (p.items) {
+            const uint2 c = __ldg(reinterpret_cast<const uint2 *>(cnt2) + t);
+            recs += (unsigned long long)(uint32_t)db.tiles[t].n * ((c.x + c.y + SMAX - 1) / SMAX);
         }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        const Plan p = bsum[nb];
-        seg_off[T] = (uint32_t)p.segs, item_off[T] = (uint32_t)p.items;
-        tot[0] = p.segs, tot[1] = p.items, tot[2] = 0;
-        tot[3] = cnt2[2 * T];                              // queries left to the M_ABN32 pipeline (M_PACKED only)
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        segs += __shfl_xor_sync(FULL, segs, d), its += __shfl_xor_sync(FULL, its, d);
+        recs += __shfl_xor_sync(FULL, recs, d);
+    }
+    if (lane == 0) red[0][wid] = segs, red[1][wid] = its, red[2][wid] = recs;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long x = 0, y = 0, z = 0;
+        for (int w = 0; w < SCAN_T / 32; ++w) x += red[0][w], y += red[1][w], z += red[2][w];
+        agg[b].segs = x, agg[b].items = y, agg[b].recs = z;
+        __threadfence();
+        flag[b] = epoch;
+    }
+    // 2. everybody's aggregates
+    if (wid == 0) {
+        unsigned long long ps = 0, pi = 0, ts = 0, ti = 0, tr = 0;
+        for (int i = lane; i < G; i += 32) {
+            while (flag[i] != epoch) __nanosleep(20);
+            __threadfence();
+            const unsigned long long x = agg[i].segs, y = agg[i].items, z = agg[i].recs;
+            ts += x, ti += y, tr += z;
+            if (i < b) ps += x, pi += y;
+        }
+#pragma unroll
+        for (int d = 16; d; d >>= 1) {
+            ps += __shfl_xor_sync(FULL, ps, d), pi += __shfl_xor_sync(FULL, pi, d);
+            ts += __shfl_xor_sync(FULL, ts, d), ti += __shfl_xor_sync(FULL, ti, d), tr += __shfl_xor_sync(FULL, tr, d);
+        }
+        if (lane == 0) {
+            sh_prefix[0] = ps, sh_prefix[1] = pi, sh_total[0] = ts, sh_total[1] = ti, sh_total[2] = tr;
+            if (b == G - 1) {
+                tot[0] = ts, tot[1] = ti, tot[2] = tr;
+                tot[3] = cnt2[2 * T];                      // queries left to the M_ABN32 pipeline (M_PACKED only)
+            }
+        }
+    }
+    __syncthreads();
+    const unsigned long long nseg = sh_total[0], nit = sh_total[1];
+    if (nseg > seg_cap || nit > item_cap) return;
+    if (b == G - 1 && threadIdx.x < 32) {                   // empty items up to a multiple of 32
+        const unsigned long long k = nit + threadIdx.x;
+        if (k < ((nit + 31) & ~31ull)) items[k] = make_int4(0, 0, 0, 0);
+        if (threadIdx.x == 0) seg_off[T] = (uint32_t)nseg;
+    }
+    // 3. per-tile offsets and items
+    Plan carry{sh_prefix[0], sh_prefix[1]};
+    for (int32_t c0 = t0; c0 < t1; c0 += SCAN_T) {
+        const int32_t t = c0 + threadIdx.x;
+        const bool in = t < t1;
+        const Plan mine = in ? plan_of_tile(db, cnt2, t) : Plan{0, 0};
+        Plan ctot;
+        const Plan ex = carry + block_exclusive<Plan>(mine, &ctot);
+        carry += ctot;
+        uint32_t i0 = (uint32_t)ex.items, ni = (uint32_t)mine.items, sa0 = (uint32_t)ex.segs, mid = 0, sb0 = 0;
+        int4 tm = make_int4(0, 0, 0, 0);
+        if (in) {
+            const uint2 c = __ldg(reinterpret_cast<const uint2 *>(cnt2) + t);
+            mid = sa0 + c.x, sb0 = mid + c.y;
+            seg_off[t] = sa0, seg_mid[t] = mid;
+            if (ni) tm = __ldg(reinterpret_cast<const int4 *>(&db.tiles[t]));
+        }
+        auto write = [&](uint32_t k, uint32_t i0_, uint32_t a, uint32_t m, uint32_t e, int4 tm_) {
+            const uint32_t ch = (e - a + SMAX - 1) / SMAX;
+            const uint32_t g = k / ch, c = k - g * ch;
+            const uint32_t sa = a + c * SMAX, sb = min(sa + (uint32_t)SMAX, e);
+            const int r0 = (int)(g * GROUP);
+            const uint32_t nv = (uint32_t)min(tm_.y - r0, GROUP);
+            const uint32_t tsr = (uint32_t)min(max(tm_.z - r0, 0), GROUP);
+            const uint32_t nfirst = min(max(m, sa), sb) - sa;
+            items[i0_ + k] = make_int4((int)((uint32_t)tm_.x + g * (GROUP / 8)), (int)sa,
+                                       (int)(nv | tsr << 9 | nfirst << 18 | (sb - sa) << 25), 0);
+        };
+        // a thread writes up to 32 items of its tile itself; tiles with more are then done by the whole warp
+        if (ni <= 32)
+            for (uint32_t k = 0; k < ni; ++k) write(k, i0, sa0, mid, sb0, tm);
+        unsigned heavy = __ballot_sync(FULL, ni > 32);
+        while (heavy) {
+            const int src = __ffs(heavy) - 1;
+            heavy &= heavy - 1;
+            const uint32_t i0_ = __shfl_sync(FULL, i0, src), ni_ = __shfl_sync(FULL, ni, src);
+            const uint32_t a_ = __shfl_sync(FULL, sa0, src), m_ = __shfl_sync(FULL, mid, src), e_ = __shfl_sync(FULL, sb0, src);
+            const int4 tm_ = make_int4(__shfl_sync(FULL, tm.x, src), __shfl_sync(FULL, tm.y, src),
+                                       __shfl_sync(FULL, tm.z, src), 0);
+            for (uint32_t k = lane; k < ni_; k += 32) write(k, i0_, a_, m_, e_, tm_);
+        }
     }
 }
 
@@ -438,69 +525,6 @@ __global__ void k_cseg_scatter(DbView db, int64_t n, const int32_t *__restrict__
         else
             static_cast<CSeg *>(segs)[pos] = CSeg{s, e};
     });
-}
-
-// Work items of tile t, group-major.  An item is self-contained, so the search kernel goes from the item to
-// its records and segments without touching the tile table:
-//   x = position of the group's first record in the SoA arrays, in units of 8 records
-//   y = first segment
-//   z = records in the group (bits 0-15, 1..GROUP) | first record of the group that starts inside this bin
-//       (bits 16-31, 0..GROUP: the dedupe rule of later bins)
-//   w = number of first-bin segments (bits 0-7, 0..64; the later-bin segments follow them) | number of
-//       segments (bits 8-15, 1..64)
-__global__ void __launch_bounds__(256) k_item_fill(DbView db, const uint32_t *__restrict__ seg_off,
-                                                    const uint32_t *__restrict__ seg_mid,
-                                                    const uint32_t *__restrict__ cnt2,
-                                                    const uint32_t *__restrict__ item_off,
-                                                    unsigned long long *__restrict__ tot,
-                                                    unsigned long long seg_cap, unsigned long long item_cap,
-                                                    int4 *__restrict__ items)
-{
-    if (tot[0] > seg_cap || tot[1] > item_cap) return;
-    const int lane = threadIdx.x & 31;
-    if (blockIdx.x == 0 && threadIdx.x < 32) {                  // empty items up to a multiple of 32
-        const unsigned long long k = tot[1] + threadIdx.x;
-        if (k < ((tot[1] + 31) & ~31ull)) items[k] = make_int4(0, 0, 0, 0);
-    }
-    // a thread per tile writes up to 32 items itself; tiles with more are then done by the whole warp
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t i0 = 0, ni = 0, sa0 = 0, mid = 0, sb0 = 0;
-    int4 tm = make_int4(0, 0, 0, 0);
-    if (t < db.ntiles) {
-        i0 = __ldg(&item_off[t]), ni = __ldg(&item_off[t + 1]) - i0;
-        if (ni) {
-            sa0 = __ldg(&seg_off[t]), mid = __ldg(&seg_mid[t]), sb0 = mid + __ldg(&cnt2[2 * t + 1]);
-            tm = __ldg(reinterpret_cast<const int4 *>(&db.tiles[t]));
-        }
-    }
-    auto write = [&](uint32_t k, uint32_t i0_, uint32_t a, uint32_t m, uint32_t b, int4 tm_) {
-        const uint32_t ch = (b - a + SMAX - 1) / SMAX;
-        const uint32_t g = k / ch, c = k - g * ch;
-        const uint32_t sa = a + c * SMAX, sb = min(sa + (uint32_t)SMAX, b);
-        const int r0 = (int)(g * GROUP);
-        const uint32_t nv = (uint32_t)min(tm_.y - r0, GROUP);
-        const uint32_t tsr = (uint32_t)min(max(tm_.z - r0, 0), GROUP);
-        const uint32_t nfirst = min(max(m, sa), sb) - sa;
-        items[i0_ + k] = make_int4((int)((uint32_t)tm_.x + g * (GROUP / 8)), (int)sa, (int)(nv | (tsr << 16)),
-                                   (int)(nfirst | ((sb - sa) << 8)));
-    };
-    if (ni <= 32)
-        for (uint32_t k = 0; k < ni; ++k) write(k, i0, sa0, mid, sb0, tm);
-    // tot[2] = records the items of this batch read (each tile once per 64 of its segments)
-    unsigned long long recs = ni ? (unsigned long long)tm.y * ((sb0 - sa0 + SMAX - 1) / SMAX) : 0ull;
-#pragma unroll
-    for (int d = 16; d; d >>= 1) recs += __shfl_xor_sync(FULL, recs, d);
-    if (lane == 0 && recs) atomicAdd(&tot[2], recs);
-    unsigned heavy = __ballot_sync(FULL, ni > 32);
-    while (heavy) {
-        const int src = __ffs(heavy) - 1;
-        heavy &= heavy - 1;
-        const uint32_t i0_ = __shfl_sync(FULL, i0, src), ni_ = __shfl_sync(FULL, ni, src);
-        const uint32_t a_ = __shfl_sync(FULL, sa0, src), m_ = __shfl_sync(FULL, mid, src), b_ = __shfl_sync(FULL, sb0, src);
-        const int4 tm_ = make_int4(__shfl_sync(FULL, tm.x, src), __shfl_sync(FULL, tm.y, src),
-                                   __shfl_sync(FULL, tm.z, src), 0);
-        for (uint32_t k = lane; k < ni_; k += 32) write(k, i0_, a_, m_, b_, tm_);
-    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -637,7 +661,8 @@ __global__ void __launch_bounds__(COUNT_MAXW * 32, 1) k_count_items(const CountA
     auto issue = [&](uint32_t n, const int4 &dd) {
         const int j = n & 31;
         const uint32_t x = __shfl_sync(FULL, dd.x, j), y = __shfl_sync(FULL, dd.y, j);
-        const int nv = __shfl_sync(FULL, dd.z, j) & 0xffff, ns = (__shfl_sync(FULL, dd.w, j) >> 8) & 0xff;
+        const uint32_t z = __shfl_sync(FULL, dd.z, j);
+        const int nv = z & 0x1ff, ns = z >> 25;
         const uint32_t so = (n % COUNT_K) * L::STAGE;
         const size_t p = (size_t)x * 8;
 #pragma unroll
@@ -670,9 +695,9 @@ __global__ void __launch_bounds__(COUNT_MAXW * 32, 1) k_count_items(const CountA
             cp_async_commit();
         }
         cp_async_wait<COUNT_K - 1>();                                   // slot n has landed (this lane's bytes)
-        const uint32_t dz = __shfl_sync(FULL, dcur.z, j), dw = __shfl_sync(FULL, dcur.w, j);
+        const uint32_t dz = __shfl_sync(FULL, dcur.z, j);
         const uint32_t so = (n % COUNT_K) * L::STAGE;
-        const int nv = dz & 0xffff, tsr = dz >> 16, nf = dw & 0xff, ns = (dw >> 8) & 0xff;
+        const int nv = dz & 0x1ff, tsr = (dz >> 9) & 0x1ff, nf = (dz >> 18) & 0x7f, ns = dz >> 25;
         int2 q0 = make_int2(IMAX, IMIN), q1 = make_int2(IMAX, IMIN);    // segments lane and 32 + lane of the item
         if (lane < ns) q0 = lds64(qslot + so);
         if (lane + 32 < ns) q1 = lds64(qslot + so + 256);
@@ -808,9 +833,7 @@ __device__ __forceinline__ void sts64(uint32_t addr, uint32_t x, uint32_t y)
 __device__ __forceinline__ void count_pairs(uint32_t list, int i0, int i1, const uint32_t (&S)[4],
                                             const uint32_t (&E)[4], uint32_t (&c)[4])
 {
-#pragma unroll 2
-    for (int i = i0; i < i1; ++i) {
-        const int2 q = lds64(list + 8u * (uint32_t)i);       // same address in every lane: a broadcast
+    auto eval = [&](const int2 q) {
         const uint32_t s2 = (uint32_t)q.x, e2 = (uint32_t)q.y;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -818,7 +841,16 @@ __device__ __forceinline__ void count_pairs(uint32_t list, int i0, int i1, const
             asm("lop3.b32 %0, %1, %2, 0x80008000, 0x80;" : "=r"(t) : "r"(e2 - S[k]), "r"(E[k] - s2));
             c[k] += t >> 15;                                // LEA.HI
         }
+    };
+    uint32_t p = list + 8u * (uint32_t)i0;
+    const uint32_t end = list + 8u * (uint32_t)i1;
+#pragma unroll 1
+    for (; p + 16 <= end; p += 16) {                        // same address in every lane: broadcast loads
+        const int2 q0 = lds64(p), q1 = lds64(p + 8);
+        eval(q0);
+        eval(q1);
     }
+    if (p < end) eval(lds64(p));
 }
 
 template <bool V, bool SMEM>
@@ -855,11 +887,17 @@ __global__ void __launch_bounds__(PK_MAXW * 32, 1) k_count_packed(const CountArg
     const uint32_t *const pQ = static_cast<const uint32_t *>(static_cast<const void *>(a.segs)) + lane;
     const uint32_t lslot = wbase + lane * 16, vslot = wbase + L::VOFF + lane * 32, qslot = wbase + L::QOFF + lane * 4;
 
+    // The stages start out as pads: a lane without records in an item reads what an earlier item (or this fill)
+    // left in its slots -- its counts are discarded, and the prune window only gets wider.
+    for (uint32_t o = lane * 16; o < L::LIST; o += 512)
+        asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(wbase + o), "r"(0x80008000u) : "memory");
+    __syncwarp();
+
     // issue the copies of item slot n (descriptor in lane n % 32 of dd) into stage n % K
     auto issue = [&](uint32_t n, const int4 &dd) {
         const int j = n & 31;
-        const uint32_t x = __shfl_sync(FULL, dd.x, j), y = __shfl_sync(FULL, dd.y, j);
-        const int nv = __shfl_sync(FULL, dd.z, j) & 0xffff, ns = (__shfl_sync(FULL, dd.w, j) >> 8) & 0xff;
+        const uint32_t x = __shfl_sync(FULL, dd.x, j), y = __shfl_sync(FULL, dd.y, j), z = __shfl_sync(FULL, dd.z, j);
+        const int nv = z & 0x1ff, ns = z >> 25;
         const uint32_t so = (n % PK_K) * L::STAGE;
         const size_t p = (size_t)x * 8;
         if (lane * 8 < nv) {
@@ -881,6 +919,8 @@ __global__ void __launch_bounds__(PK_MAXW * 32, 1) k_count_packed(const CountArg
         cp_async_commit();
     }
 
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t list = wbase + L::LIST;
     for (uint32_t n = 0; n < N; ++n) {
         const int j = n & 31;
         {
@@ -892,22 +932,15 @@ __global__ void __launch_bounds__(PK_MAXW * 32, 1) k_count_packed(const CountArg
             cp_async_commit();
         }
         cp_async_wait<PK_K - 1>();                                      // slot n has landed (this lane's bytes)
-        const uint32_t dz = __shfl_sync(FULL, dcur.z, j), dw = __shfl_sync(FULL, dcur.w, j);
+        const uint32_t dz = __shfl_sync(FULL, dcur.z, j);
         const uint32_t so = (n % PK_K) * L::STAGE;
-        const int nv = dz & 0xffff, tsr = dz >> 16, nf = dw & 0xff, ns = (dw >> 8) & 0xff;
+        const int nv = dz & 0x1ff, tsr = (dz >> 9) & 0x1ff, nf = (dz >> 18) & 0x7f, ns = dz >> 25;
         if (nv > 0) {
-            // segments lane and 32 + lane of the item; an absent one has qe' = 0 and survives no prune
-            const uint32_t w0 = lane < ns ? lds32(qslot + so) : 0x80000000u;
-            const uint32_t w1 = lane + 32 < ns ? lds32(qslot + so + 128) : 0x80000000u;
             const bool have = lane * 8 < nv;
-            uint4 Sv = make_uint4(0x80008000u, 0x80008000u, 0x80008000u, 0x80008000u), Ev = Sv, Fv = make_uint4(0, 0, 0, 0);
-            if (have) {
-                const int4 s_ = lds128(lslot + so), e_ = lds128(lslot + so + L::ARR), f_ = lds128(lslot + so + 2 * L::ARR);
-                Sv = make_uint4(s_.x, s_.y, s_.z, s_.w), Ev = make_uint4(e_.x, e_.y, e_.z, e_.w);
-                Fv = make_uint4(f_.x, f_.y, f_.z, f_.w);
-            }
-            uint32_t S[4] = {Sv.x, Sv.y, Sv.z, Sv.w};
-            const uint32_t E[4] = {Ev.x, Ev.y, Ev.z, Ev.w}, F[4] = {Fv.x, Fv.y, Fv.z, Fv.w};
+            const int4 s_ = lds128(lslot + so), e_ = lds128(lslot + so + L::ARR), f_ = lds128(lslot + so + 2 * L::ARR);
+            uint32_t S[4] = {(uint32_t)s_.x, (uint32_t)s_.y, (uint32_t)s_.z, (uint32_t)s_.w};
+            const uint32_t E[4] = {(uint32_t)e_.x, (uint32_t)e_.y, (uint32_t)e_.z, (uint32_t)e_.w};
+            const uint32_t F[4] = {(uint32_t)f_.x, (uint32_t)f_.y, (uint32_t)f_.z, (uint32_t)f_.w};
             if (V && have) {                                            // value < v: the record matches no query
                 const int4 v0 = lds128(vslot + so), v1 = lds128(vslot + so + 16);
                 const int vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
@@ -923,7 +956,7 @@ __global__ void __launch_bounds__(PK_MAXW * 32, 1) k_count_packed(const CountArg
             uint32_t smin;
             if (V) {
                 const uint32_t m2 = __vminu2(__vminu2(S[0], S[1]), __vminu2(S[2], S[3]));
-                smin = __reduce_min_sync(FULL, min(m2 & 0xffffu, m2 >> 16));
+                smin = __reduce_min_sync(FULL, have ? min(m2 & 0xffffu, m2 >> 16) : 0xffffu);
             } else {
                 smin = __shfl_sync(FULL, S[0], 0) & 0xffffu;
             }
@@ -932,53 +965,77 @@ __global__ void __launch_bounds__(PK_MAXW * 32, 1) k_count_packed(const CountArg
             // a segment can touch the group iff qe' > smallest start' and qs' < largest end':
             //   QE - smin >= 0x8000  and  emax - QS >= 0x8000
             const uint32_t qe_lo = smin + 0x8000u, qs_hi = emax - 0x8000u;     // QE >= qe_lo, QS <= qs_hi
+            // segments lane and 32 + lane of the item; an absent one has qe' = 0 and survives no prune
+            const uint32_t w0 = lane < ns ? lds32(qslot + so) : 0x80000000u;
             const uint32_t qs2_0 = __byte_perm(w0, 0, 0x1010), qe2_0 = __byte_perm(w0, 0, 0x3232);
-            const uint32_t qs2_1 = __byte_perm(w1, 0, 0x1010), qe2_1 = __byte_perm(w1, 0, 0x3232);
-            const bool ok0 = (w0 >> 16) >= qe_lo && (w0 & 0xffffu) <= qs_hi;
-            const bool ok1 = (w1 >> 16) >= qe_lo && (w1 & 0xffffu) <= qs_hi;
+            uint32_t w1 = 0x80000000u, qs2_1 = 0, qe2_1 = 0;
+            if (ns > 32) {
+                if (lane + 32 < ns) w1 = lds32(qslot + so + 128);
+                qs2_1 = __byte_perm(w1, 0, 0x1010), qe2_1 = __byte_perm(w1, 0, 0x3232);
+            }
             // The surviving segments are compacted into the warp's list (first-bin ones, then later-bin ones)
             // and streamed back with broadcast loads: 1 load + 16 ALU/FMA instructions per segment x 256 records.
-            const uint32_t lt = (1u << lane) - 1u;
-            const uint32_t list = wbase + L::LIST;
             __syncwarp();                                               // the previous item's list has been read
             // first-bin segments [0, nf): every record of the tile is a candidate
-            const unsigned f0 = __ballot_sync(FULL, ok0 && lane < nf), f1 = __ballot_sync(FULL, ok1 && lane + 32 < nf);
-            int nF = __popc(f0);
-            if (f0 >> lane & 1) sts64(list + 8u * __popc(f0 & lt), qs2_0, qe2_0);
-            if (f1 >> lane & 1) sts64(list + 8u * (nF + __popc(f1 & lt)), qs2_1, qe2_1);
-            nF += __popc(f1);
-            // later-bin segments [nf, ns): only the records that start inside this bin, i.e. index >= tS
+            int nF = 0;
+            if (nf > 0) {
+                const unsigned f0 = __ballot_sync(FULL, (w0 >> 16) >= qe_lo && (w0 & 0xffffu) <= qs_hi && lane < nf);
+                if (f0 >> lane & 1) sts64(list + 8u * __popc(f0 & lt), qs2_0, qe2_0);
+                nF = __popc(f0);
+                if (nf > 32) {
+                    const unsigned f1 = __ballot_sync(FULL, (w1 >> 16) >= qe_lo && (w1 & 0xffffu) <= qs_hi && lane + 32 < nf);
+                    if (f1 >> lane & 1) sts64(list + 8u * (nF + __popc(f1 & lt)), qs2_1, qe2_1);
+                    nF += __popc(f1);
+                }
+            }
+            // later-bin segments [nf, ns): only the records that start inside this bin count (index >= tS,
+            // src/igd_search.c:510-511,522), i.e. start' >= 1.  Such a segment has qs' = 0 (QS = 1), so its
+            // end test is vacuous; it is given X = S + 0x7fff in place of E, which turns that test into
+            // bit 15 of (S + 0x7fff - 1), set  <=>  S >= 2  <=>  start' >= 1.
             int nL = 0;
-            uint32_t SL[4] = {S[0], S[1], S[2], S[3]};
             if (ns > nf && tsr < nv) {
-                const int nb4 = min(max(tsr - lane * 8, 0), 8);         // this lane's records before the bin
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    SL[k] = nb4 >= 2 * k + 2 ? 0x80008000u : (nb4 == 2 * k + 1 ? ((S[k] & 0xffff0000u) | 0x8000u) : S[k]);
-                // prune with the first (surviving) record that starts inside the bin
-                const uint32_t l2 = __vminu2(__vminu2(SL[0], SL[1]), __vminu2(SL[2], SL[3]));
-                const uint32_t slmin = __reduce_min_sync(FULL, min(l2 & 0xffffu, l2 >> 16));
+                // prune with the first record that starts inside the bin (records are sorted by start)
+                uint32_t slmin = smin;
+                if (tsr > 0) {
+                    if (V) {
+                        slmin = max(smin, 2u);
+                    } else {
+                        const int nb4 = min(max(tsr - lane * 8, 0), 8);     // this lane's records before the bin
+                        const uint32_t wd = nb4 < 2 ? S[0] : (nb4 < 4 ? S[1] : (nb4 < 6 ? S[2] : S[3]));
+                        const uint32_t mine = (nb4 >= 8 || !have) ? 0xffffu : ((nb4 & 1) ? wd >> 16 : wd & 0xffffu);
+                        slmin = __reduce_min_sync(FULL, mine);
+                    }
+                }
                 const uint32_t qel = slmin + 0x8000u;
-                const bool okl0 = (w0 >> 16) >= qel && (w0 & 0xffffu) <= qs_hi;
-                const bool okl1 = (w1 >> 16) >= qel && (w1 & 0xffffu) <= qs_hi;
-                const unsigned l0 = __ballot_sync(FULL, okl0 && lane >= nf), l1 = __ballot_sync(FULL, okl1 && lane + 32 >= nf);
-                if (l0 >> lane & 1) sts64(list + 8u * (nF + __popc(l0 & lt)), qs2_0, qe2_0);
-                nL = __popc(l0);
-                if (l1 >> lane & 1) sts64(list + 8u * (nF + nL + __popc(l1 & lt)), qs2_1, qe2_1);
-                nL += __popc(l1);
+                if (nf < 32) {
+                    const unsigned l0 = __ballot_sync(FULL, (w0 >> 16) >= qel && (w0 & 0xffffu) <= qs_hi && lane >= nf);
+                    if (l0 >> lane & 1) sts64(list + 8u * (nF + __popc(l0 & lt)), qs2_0, qe2_0);
+                    nL = __popc(l0);
+                }
+                if (ns > 32) {
+                    const unsigned l1 = __ballot_sync(FULL, (w1 >> 16) >= qel && (w1 & 0xffffu) <= qs_hi && lane + 32 >= nf);
+                    if (l1 >> lane & 1) sts64(list + 8u * (nF + nL + __popc(l1 & lt)), qs2_1, qe2_1);
+                    nL += __popc(l1);
+                }
             }
             __syncwarp();
             count_pairs(list, 0, nF, S, E, c);
-            count_pairs(list, nF, nF + nL, SL, E, c);
-            // hits[file] += count: one atomic per record that overlaps anything
+            if (nL > 0) {
+                const uint32_t X[4] = {S[0] + 0x7fff7fffu, S[1] + 0x7fff7fffu, S[2] + 0x7fff7fffu, S[3] + 0x7fff7fffu};
+                count_pairs(list, nF, nF + nL, S, X, c);
+            }
+            // hits[file] += count.  One test per PAIR of records (neighbours in start order are mostly hit
+            // together or not at all), then one shared-memory atomic per record.
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                if (c[k]) {
-                    const uint32_t c0 = c[k] & 0xffffu, c1 = c[k] >> 16, f0 = F[k] & 0xffffu, f1 = F[k] >> 16;
+                if (have && c[k]) {
+                    const uint32_t c0 = c[k] & 0xffffu, c1 = c[k] >> 16;
                     if (SMEM) {
-                        if (c0) atomicAdd(&hist[f0], c0);
-                        if (c1) atomicAdd(&hist[f1], c1);
+                        const uint32_t a0 = hist_s + ((F[k] << 2) & 0x3fffcu), a1 = hist_s + ((F[k] >> 14) & 0x3fffcu);
+                        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a0), "r"(c0) : "memory");
+                        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a1), "r"(c1) : "memory");
                     } else {
+                        const uint32_t f0 = F[k] & 0xffffu, f1 = F[k] >> 16;
                         if (c0) atomicAdd(&a.hits[f0], (unsigned long long)c0);
                         if (c1) atomicAdd(&a.hits[f1], (unsigned long long)c1);
                     }
@@ -1339,8 +1396,10 @@ struct igdb_dev {
     unsigned long long *d_hits = nullptr;                   // [nfiles]
     uint32_t *h_scalar = nullptr;                           // pinned readback
     // count mode (tile-centric): plan scratch, segments, work items
-    uint32_t *cnt2 = nullptr, *cseg_off = nullptr, *cseg_mid = nullptr, *item_off = nullptr;   // [2T+2],[T+1],[T+1],[T+1]
-    Plan *plan_tmp = nullptr, *plan_bsum = nullptr;         // [T], [scan blocks + 1]
+    uint32_t *cnt2 = nullptr, *cseg_off = nullptr, *cseg_mid = nullptr;   // [2T+2],[T+1],[T+1]
+    PlanAgg *plan_agg = nullptr;                            // [plan_grid] per-CTA aggregates of k_plan
+    uint32_t *plan_flag = nullptr, plan_epoch = 0;          // [plan_grid] = epoch of the batch that published
+    int plan_grid = 1;
     unsigned long long *plan_tot = nullptr;                 // device {segments, items} of the batch in flight
     volatile unsigned long long *h_plan = nullptr;          // pinned copy of plan_tot
     cudaEvent_t plan_ev = nullptr;
@@ -1522,15 +1581,10 @@ int enqueue_count(igdb_dev *d, const igdb_dev::Pending &p)
         (unsigned long long)std::min<int64_t>(d->item_cap - CAP_SLACK, item_limit(d, grid));
     const int thr = 256;
     const int nb = (int)((p.n + thr - 1) / thr);
-    const int sb = (d->T + SCAN_B - 1) / SCAN_B;
     k_cseg_count<V, MODE><<<nb, thr, 0, st>>>(db, p.n, p.ctg, p.qs, p.qe, d->cnt2);
-    k_plan1<<<sb, SCAN_T, 0, st>>>(db, d->cnt2, d->plan_tmp, d->plan_bsum);
-    k_scan2<Plan><<<1, SCAN_T, 0, st>>>(d->plan_bsum, sb);
-    k_plan3<<<sb, SCAN_T, 0, st>>>(d->T, d->cnt2, d->plan_tmp, d->plan_bsum, sb, d->cseg_off, d->cseg_mid,
-                                    d->item_off, d->plan_tot);
-    // (the fill reads the later-bin counters that the scatter counts back down to zero)
-    k_item_fill<<<(d->T + 255) / 256, 256, 0, st>>>(db, d->cseg_off, d->cseg_mid, d->cnt2, d->item_off, d->plan_tot,
-                                                  seg_cap, item_cap, d->items);
+    // (the plan reads the later-bin counters that the scatter counts back down to zero)
+    k_plan<<<d->plan_grid, SCAN_T, 0, st>>>(db, d->cnt2, ++d->plan_epoch, d->plan_agg, d->plan_flag, d->cseg_off,
+                                            d->cseg_mid, d->plan_tot, seg_cap, item_cap, d->items);
     CK(cudaMemcpyAsync((void *)d->h_plan, d->plan_tot, 32, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(d->plan_ev, st));
     k_cseg_scatter<V, MODE><<<nb, thr, 0, st>>>(db, p.n, p.ctg, p.qs, p.qe, d->cnt2, d->cseg_off, d->cseg_mid,
@@ -1550,7 +1604,7 @@ int enqueue_count(igdb_dev *d, const igdb_dev::Pending &p)
         CK(cudaEventRecord(d->kev[1], st));
         d->kev_valid = true;
     }
-    d->launches += 7;
+    d->launches += 4;
     CK(cudaGetLastError());
     return 0;
 }
@@ -1639,8 +1693,8 @@ void igdb_dev_destroy(igdb_dev *d)
     cudaSetDevice(d->device);
     void *ptrs[] = {d->tiles, d->d_toff, d->start, d->end, d->idx, d->value, d->tbase, d->d_stage, d->q_ctg,
                     d->q_qs, d->q_qe, d->tile_cnt, d->tile_off, d->nseg, d->qseg_off, d->bsum, d->segs,
-                    d->seg_hits, d->seg_out_off, d->d_hits, d->cnt2, d->cseg_off, d->cseg_mid, d->item_off,
-                    d->plan_tmp, d->plan_bsum, d->plan_tot, d->csegs, d->items, d->ps, d->pe, d->pf};
+                    d->seg_hits, d->seg_out_off, d->d_hits, d->cnt2, d->cseg_off, d->cseg_mid,
+                    d->plan_agg, d->plan_flag, d->plan_tot, d->csegs, d->items, d->ps, d->pe, d->pf};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (d->pinned) cudaFreeHost(d->pinned);
@@ -1696,9 +1750,9 @@ static int create_impl(igdb_dev *d, const int32_t *ntile, const int32_t *ncnt)
         dev_alloc(d, &d->value, (size_t)d->P + 8) || dev_alloc(d, &d->tile_cnt, (size_t)d->T + 1) ||
         dev_alloc(d, &d->tile_off, (size_t)d->T + 1) || dev_alloc(d, &d->d_hits, (size_t)d->nfiles) ||
         dev_alloc(d, &d->cnt2, (size_t)2 * d->T + 2) || dev_alloc(d, &d->cseg_off, (size_t)d->T + 1) ||
-        dev_alloc(d, &d->cseg_mid, (size_t)d->T + 1) || dev_alloc(d, &d->item_off, (size_t)d->T + 1) ||
-        dev_alloc(d, &d->plan_tmp, (size_t)d->T + 1) ||
-        dev_alloc(d, &d->plan_bsum, (size_t)(d->T + SCAN_B - 1) / SCAN_B + 2) || dev_alloc(d, &d->plan_tot, 8))
+        dev_alloc(d, &d->cseg_mid, (size_t)d->T + 1) ||
+        dev_alloc(d, &d->plan_agg, (size_t)d->sm_count) || dev_alloc(d, &d->plan_flag, (size_t)d->sm_count) ||
+        dev_alloc(d, &d->plan_tot, 8))
         return -1;
     // packed count-mode copies: tile-relative coordinates need nbp + 1 < 2^15, file indices 16 bits
     d->packed = d->nbp <= 16384 && d->nfiles <= 65536 && !getenv("IGD_B200_NO_PACKED");
@@ -1722,6 +1776,9 @@ static int create_impl(igdb_dev *d, const int32_t *ntile, const int32_t *ncnt)
     CK(cudaMemset(d->idx, 0, ((size_t)d->P + 8) * 4));
     CK(cudaMemset(d->tile_cnt, 0, ((size_t)d->T + 1) * 4));
     CK(cudaMemset(d->cnt2, 0, ((size_t)2 * d->T + 2) * 4));
+    CK(cudaMemset(d->plan_flag, 0, (size_t)d->sm_count * 4));
+    // k_plan's CTAs wait for each other: at most one per SM, so that all of them are resident
+    d->plan_grid = std::max(1, std::min(d->sm_count, (d->T + SCAN_T - 1) / SCAN_T));
     return 0;
 }
 
