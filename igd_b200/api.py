@@ -86,6 +86,8 @@ def load_library():
     L.igd_b200_hitlist_free.argtypes = [C.POINTER(_HitList)]
     L.igd_b200_hitsmap.restype = C.c_int64
     L.igd_b200_hitsmap.argtypes = [vp, C.c_int32, _u32p]
+    L.igd_b200_hitsmap_tiles.restype = C.c_int64
+    L.igd_b200_hitsmap_tiles.argtypes = [vp, C.c_int32, C.c_int64, C.c_int64, _u32p]
     L.igd_b200_read_bed.restype = C.POINTER(_Queries)
     L.igd_b200_read_bed.argtypes = [C.c_char_p]
     L.igd_b200_queries_free.argtypes = [C.POINTER(_Queries)]
@@ -307,9 +309,15 @@ class IGD:
             self._L.igd_b200_hitlist_free(C.byref(hl))
 
     # -- -m / -s -----------------------------------------------------------------------------------------
-    def hitsmap(self, v: int = 0) -> np.ndarray:
+    def hitsmap(self, v: int = 0, tiles: tuple[int, int] | None = None) -> np.ndarray:
+        """-m; ``tiles=(lo, hi)`` restricts the self-join to that range of global tile indices (one rank's
+        share of a multi-GPU run: the maps of disjoint ranges add up to the whole map)."""
         hm = np.zeros((self.nfiles, self.nfiles), np.uint32)
-        if self._L.igd_b200_hitsmap(self._need(), int(v), hm.reshape(-1)) < 0:
+        if tiles is None:
+            r = self._L.igd_b200_hitsmap(self._need(), int(v), hm.reshape(-1))
+        else:
+            r = self._L.igd_b200_hitsmap_tiles(self._need(), int(v), int(tiles[0]), int(tiles[1]), hm.reshape(-1))
+        if r < 0:
             raise IGDError(last_error())
         return hm
 

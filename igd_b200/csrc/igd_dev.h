@@ -47,6 +47,15 @@ int igdb_dev_count_device(igdb_dev *d, int64_t n, const int32_t *d_ctg, const in
  * in stream order. */
 int igdb_dev_count_finish(igdb_dev *d);
 
+/* Query ingest on the device.  set_contigs: the database's contig names (nctg x 40 bytes, NUL-terminated) for
+ * get_id on the device.  Between hits_begin and hits_end, count_text takes chunks of BED text made of whole
+ * lines: H2D, parse (parse_bed's rule), count; n_queries = accepted lines on known contigs.  hits_end waits and
+ * returns the counts of all chunks in hits_delta[nfiles]. */
+int igdb_dev_set_contigs(igdb_dev *d, const char *names40);
+int igdb_dev_hits_begin(igdb_dev *d);
+int igdb_dev_count_text(igdb_dev *d, const char *text, size_t len, int mode_v, int32_t v, int64_t *n_queries);
+int igdb_dev_hits_end(igdb_dev *d, uint64_t *hits_delta);
+
 /* -f: returns total (>= 0) and malloc'ed host arrays; query_off has n+1 entries */
 int64_t igdb_dev_full_host(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_t *qs, const int32_t *qe,
                            int64_t **query_off, int32_t **start, int32_t **end, int32_t **file);
@@ -56,8 +65,8 @@ int64_t igdb_dev_full_host(igdb_dev *d, int64_t n, const int32_t *ctg, const int
 int igdb_dev_seqpare(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_t *qs, const int32_t *qe,
                      const int32_t *grp, int32_t ngroups, const int32_t *grp_nq, double *acc);
 
-/* -m */
-int64_t igdb_dev_hitsmap_host(igdb_dev *d, int32_t v, uint32_t *hitmap);
+/* -m restricted to the tiles [t0, t1) (global tile indices, contig-major): hitmap[nfiles*nfiles] is incremented */
+int64_t igdb_dev_hitsmap_host(igdb_dev *d, int32_t v, int64_t t0, int64_t t1, uint32_t *hitmap);
 
 #ifdef __cplusplus
 }

@@ -118,6 +118,7 @@ igd_b200_t *igd_b200_open(const char *igd_path, int device)
     }
     h->dev = igdb_dev_create(device, h->nbp, h->nctg, h->ntile, h->ncnt, h->nfiles);
     if (!h->dev) goto fail;
+    if (igdb_dev_set_contigs(h->dev, (const char *)h->cname)) goto fail;
     {
         const int64_t CH = 4 << 20;                     /* records per chunk: 64 MiB */
         int64_t chunk = h->nrec < CH ? h->nrec : CH;
@@ -254,7 +255,13 @@ void igd_b200_hitlist_free(igd_b200_hitlist *l)
 int64_t igd_b200_hitsmap(igd_b200_t *h, int32_t v, uint32_t *hitmap)
 {
     g_err[0] = 0;
-    return igdb_dev_hitsmap_host(h->dev, v, hitmap);
+    return igdb_dev_hitsmap_host(h->dev, v, 0, h->ntiles, hitmap);
+}
+
+int64_t igd_b200_hitsmap_tiles(igd_b200_t *h, int32_t v, int64_t tile_lo, int64_t tile_hi, uint32_t *hitmap)
+{
+    g_err[0] = 0;
+    return igdb_dev_hitsmap_host(h->dev, v, tile_lo, tile_hi, hitmap);
 }
 
 /* estimated scan bytes per query: 4 * sum of nCnt over the bins the query touches */
@@ -388,19 +395,55 @@ void igd_b200_resolve(const igd_b200_t *h, const igd_b200_queries *q, int32_t *o
     free(map);
 }
 
+/* Whole-file count search -- getOverlaps / getOverlaps_v (src/igd_search.c:696-719, 746-769).  The query file is
+ * streamed through two halves of a pinned buffer in chunks of whole lines; each chunk goes to the GPU as TEXT
+ * and is parsed there (k_parse_bed: parse_bed's acceptance rule and get_id), so the host touches every byte
+ * once (gzread) and the search of chunk k overlaps the reading of chunk k + 1. */
 static int64_t search_mode(igd_b200_t *h, const char *qFile, int mode_v, int32_t v, int64_t *hits)
 {
     g_err[0] = 0;
-    igd_b200_queries *Q = igd_b200_read_bed(qFile);
-    if (!Q) return 0;                               /* unopenable query file -> 0 (src/igd_search.c:701-702) */
-    int64_t r = 0;
-    if (Q->n) {
-        int32_t *ctg = malloc(sizeof(int32_t) * (size_t)Q->n);
-        igd_b200_resolve(h, Q, ctg);
-        r = count_mode(h, Q->n, ctg, Q->qs, Q->qe, mode_v, v, hits);
-        free(ctg);
+    gzFile fp = gzopen(qFile, "r");
+    if (!fp) return 0;                              /* unopenable query file -> 0 (src/igd_search.c:701-702) */
+    gzbuffer(fp, 1 << 20);
+    const size_t CH = (size_t)16 << 20;
+    char *base = igdb_dev_pinned(h->dev, 2 * CH + 16);
+    int64_t r = -1;
+    if (!base) { set_err("%s: cannot allocate the pinned query buffer", qFile); goto out; }
+    if (igdb_dev_hits_begin(h->dev)) goto out;
+    size_t carry = 0;
+    int skipping = 0;                               /* inside a line longer than a chunk: drop up to its '\n' */
+    for (int k = 0;; k++) {
+        char *buf = base + (size_t)(k & 1) * (CH + 8);
+        int got = gzread(fp, buf + carry, (unsigned)(CH - carry));
+        const int eof = got <= 0;
+        if (eof) got = 0;
+        size_t have = carry + (size_t)got, from = 0;
+        if (skipping) {
+            char *nl = memchr(buf, '\n', have);
+            if (!nl) { carry = 0; if (eof) break; continue; }
+            from = (size_t)(nl - buf) + 1, skipping = 0;
+        }
+        size_t use = have;                          /* end of the last whole line */
+        if (!eof) {
+            while (use > from && buf[use - 1] != '\n') use--;
+            if (use == from && have - from == CH) { /* no newline in a full chunk: its head is the line */
+                use = have;
+                skipping = 1;
+            }
+        }
+        if (use > from && igdb_dev_count_text(h->dev, buf + from, use - from, mode_v, v, NULL)) goto out;
+        carry = have - use;
+        if (carry) memcpy(base + (size_t)((k + 1) & 1) * (CH + 8), buf + use, carry);
+        if (eof) break;
     }
-    igd_b200_queries_free(Q);
+    if (igdb_dev_hits_end(h->dev, h->delta)) goto out;
+    r = 0;
+    for (int i = 0; i < h->nfiles; i++) {
+        hits[i] += (int64_t)h->delta[i];
+        r += (int64_t)h->delta[i];
+    }
+out:
+    gzclose(fp);
     return r;
 }
 

@@ -1,0 +1,123 @@
+"""Multi-GPU driver of the search path: one process per GPU, the database replicated, the WORK sharded
+(SURVEY.md §8(e)).  ``torch.distributed`` is the plumbing (NCCL over NVLink on the GPU box, gloo in CPU tests).
+
+* count / -v : queries sorted by (contig, start) and cut into contiguous ranges balanced by the prefix sum of
+               estimated scan bytes; per-rank ``hits[]``; ONE int64 allreduce (nFiles elements).
+* -f         : the same shards; every rank sends its overlaps to ``dst`` (sizes by all_gather, payload by
+               point-to-point send/recv), which restores the ORIGINAL query order -- the result is identical to
+               a single-GPU ``full()`` on the unsorted input.
+* -m         : tiles are independent (getMap, src/igd_search.c:780-782): contiguous tile ranges balanced by the
+               self-join cost estimate sum(nCnt^2); per-rank uint32 maps; one allreduce (two's-complement int32
+               addition wraps exactly like the reference's uint32 counters).
+* -s         : the greedy matching couples all queries of a (chrom, file): replicas only, not sharded.
+
+The class is written against an ENGINE -- any object with ``nfiles``, ``count(ctg, qs, qe, v)``,
+``full(ctg, qs, qe)`` and ``hitsmap(v, tiles=(lo, hi))`` -- which in the product is :class:`igd_b200.api.IGD`
+(the CUDA library; there is no CPU engine in this package).  Host-side planning lives in ``workloads``.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import workloads
+
+
+def tile_bounds(hdr: dict, n_parts: int) -> list[int]:
+    """Cut the global tile range into ``n_parts`` contiguous ranges of equal estimated -m cost: a record of a
+    tile with n records scans O(n) partners, so a tile costs about n^2 (+ n for the pass over its records)."""
+    n = hdr["ncnt"].astype(np.float64)
+    cum = np.cumsum(n * n + n)
+    total = float(cum[-1]) if len(cum) else 0.0
+    b = [0]
+    for p in range(1, n_parts):
+        b.append(int(np.searchsorted(cum, total * p / n_parts, side="left")) if total > 0 else 0)
+    b.append(len(n))
+    return [int(x) for x in np.maximum.accumulate(b)]
+
+
+class ShardedSearch:
+    def __init__(self, engine, hdr: dict, group=None, comm_device="cpu"):
+        import torch.distributed as dist
+        self.e, self.hdr, self.group, self.dev = engine, hdr, group, comm_device
+        self.dist = dist
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+
+    # ---- helpers ---------------------------------------------------------------------------------
+    def _t(self, a):
+        import torch
+        return torch.from_numpy(np.ascontiguousarray(a)).to(self.dev)
+
+    def _plan(self, ctg, qs, qe):
+        ctg, qs, qe = (np.ascontiguousarray(x, np.int32) for x in (ctg, qs, qe))
+        order = np.lexsort((qs, ctg))               # stable: ties keep input order, identically on every rank
+        cs, ss, es = ctg[order], qs[order], qe[order]
+        cost = workloads.query_cost(self.hdr, cs, ss, es)
+        cum = np.cumsum(cost)
+        total = int(cum[-1]) if len(cum) else 0
+        b = [0] + [int(np.searchsorted(cum, total * p / self.world)) for p in range(1, self.world)] + [len(cs)]
+        return order, cs, ss, es, b
+
+    # ---- count / -v ------------------------------------------------------------------------------
+    def count(self, ctg, qs, qe, v: int = 0) -> np.ndarray:
+        """hits[nFiles] of the whole query set, on every rank."""
+        _, cs, ss, es, b = self._plan(ctg, qs, qe)
+        lo, hi = b[self.rank], b[self.rank + 1]
+        hits, _ = self.e.count(cs[lo:hi], ss[lo:hi], es[lo:hi], v)
+        t = self._t(hits.astype(np.int64))
+        self.dist.all_reduce(t, group=self.group)
+        return t.cpu().numpy()
+
+    # ---- -f --------------------------------------------------------------------------------------
+    def full(self, ctg, qs, qe, dst: int = 0):
+        """On ``dst``: (query_off[n+1], start, end, file) in the input's query order, each query's overlaps in
+        the reference's order -- what a single GPU returns.  None elsewhere."""
+        import torch
+        dist = self.dist
+        order, cs, ss, es, b = self._plan(ctg, qs, qe)
+        lo, hi = b[self.rank], b[self.rank + 1]
+        qoff, s, e, f = self.e.full(cs[lo:hi], ss[lo:hi], es[lo:hi])
+        mine = torch.tensor([int(qoff[-1])], dtype=torch.int64, device=self.dev)
+        sizes = [torch.zeros_like(mine) for _ in range(self.world)]
+        dist.all_gather(sizes, mine, group=self.group)
+        sizes = [int(x.item()) for x in sizes]
+        cnt = np.diff(qoff).astype(np.int64)
+        payload = np.stack([s, e, f]).astype(np.int32) if len(s) else np.zeros((3, 0), np.int32)
+        if self.rank != dst:
+            dist.send(self._t(cnt), dst, group=self.group)
+            if sizes[self.rank]:
+                dist.send(self._t(payload), dst, group=self.group)
+            return None
+        cnts, pays = [], []
+        for r in range(self.world):
+            if r == dst:
+                cnts.append(cnt), pays.append(payload)
+                continue
+            c = torch.empty(b[r + 1] - b[r], dtype=torch.int64, device=self.dev)
+            dist.recv(c, r, group=self.group)
+            cnts.append(c.cpu().numpy())
+            p = torch.empty((3, sizes[r]), dtype=torch.int32, device=self.dev)
+            if sizes[r]:
+                dist.recv(p, r, group=self.group)
+            pays.append(p.cpu().numpy())
+        cnt_sorted = np.concatenate(cnts) if cnts else np.zeros(0, np.int64)
+        pay = np.concatenate(pays, axis=1)
+        # sorted position of every original query, then a gather of its run of overlaps
+        n = len(order)
+        pos = np.empty(n, np.int64)
+        pos[order] = np.arange(n)
+        soff = np.concatenate([[0], np.cumsum(cnt_sorted)])
+        cnt_orig = cnt_sorted[pos]
+        qoff_o = np.concatenate([[0], np.cumsum(cnt_orig)]).astype(np.int64)
+        total = int(qoff_o[-1])
+        src = np.repeat(soff[pos], cnt_orig) + (np.arange(total) - np.repeat(qoff_o[:-1], cnt_orig))
+        return qoff_o, pay[0][src], pay[1][src], pay[2][src]
+
+    # ---- -m --------------------------------------------------------------------------------------
+    def hitsmap(self, v: int = 0) -> np.ndarray:
+        """uint32[nFiles, nFiles] of the whole database, on every rank."""
+        b = tile_bounds(self.hdr, self.world)
+        hm = self.e.hitsmap(v, tiles=(b[self.rank], b[self.rank + 1]))
+        t = self._t(hm.view(np.int32))
+        self.dist.all_reduce(t, group=self.group)
+        return t.cpu().numpy().view(np.uint32)

@@ -93,6 +93,11 @@ void igd_b200_hitlist_free(igd_b200_hitlist *l);
  * incremented (wraps mod 2^32 like the reference).  v > 0 selects the strict `value > v` filter.
  * Returns the number of pairs counted or a negative error code. */
 int64_t igd_b200_hitsmap(igd_b200_t *h, int32_t v, uint32_t *hitmap);
+/* the same over the tiles [tile_lo, tile_hi) only (global tile index = tiles of the contigs before + bin;
+ * getMap's outer loops, src/igd_search.c:780-782, cut into a range).  Tiles are independent, so the maps of
+ * disjoint ranges add up to the whole map: this is what one rank of a multi-GPU -m computes before the
+ * uint32 allreduce. */
+int64_t igd_b200_hitsmap_tiles(igd_b200_t *h, int32_t v, int64_t tile_lo, int64_t tile_hi, uint32_t *hitmap);
 
 /* Query ingest: the accepted lines of a BED(.gz) file by parse_bed's rule (src/igd_base.c:53-72: >= 3
  * tab-separated fields, contig starts with "chr", shorter than 40 chars, end > 0), read like

@@ -444,11 +444,19 @@ void orc_seqpare(const orc_db *db, const orc_queries *Q, double *sm)
 /* ---- -m : hitsmap (getMap src/igd_search.c:772-826, getMap_v :829-886) ------------------------------- */
 int64_t orc_hitsmap(const orc_db *db, int32_t v, uint32_t *hitmap)
 {
+    return orc_hitsmap_tiles(db, v, 0, INT64_MAX, hitmap);
+}
+
+/* the same loops restricted to the global tile indices [t_lo, t_hi): getMap's tiles are independent
+ * (src/igd_search.c:780-782 iterates them one by one and no state survives a tile) */
+int64_t orc_hitsmap_tiles(const orc_db *db, int32_t v, int64_t t_lo, int64_t t_hi, uint32_t *hitmap)
+{
     int use_v = v > 0;                      /* dispatch src/igd_search.c:1000-1003 */
     int64_t nols = 0, nf = db->nfiles;
     for (int c = 0; c < db->nctg; c++) {
         for (int32_t n1 = 0; n1 < db->ntile[c]; n1++) {
             int64_t t = db->tbase[c] + n1;
+            if (t < t_lo || t >= t_hi) continue;
             int32_t n = db->ncnt[t], bd = db->nbp * n1;
             if (n == 0) continue;
             const rec_t *r = db->rec + db->toff[t];

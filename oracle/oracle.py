@@ -88,6 +88,8 @@ def lib():
         L.orc_seqpare.argtypes = [C.c_void_p, C.POINTER(_Queries), _f64p]
         L.orc_hitsmap.restype = C.c_int64
         L.orc_hitsmap.argtypes = [C.c_void_p, C.c_int32, _u32p]
+        L.orc_hitsmap_tiles.restype = C.c_int64
+        L.orc_hitsmap_tiles.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, _u32p]
         _lib = L
     return _lib
 
@@ -169,14 +171,23 @@ class OracleDB:
         self.L.orc_full(self.h, n, ctg, qs, qe, total, *[o.ctypes.data for o in out], None)
         return (per, *out)
 
+    def count_file(self, qfile: str, v: int = 0):
+        """getOverlaps / getOverlaps_v on a query file: (hits, the reference's return value)."""
+        q = Queries(qfile)
+        hits, ret = self.count(self.resolve(q), q.qs, q.qe, v)[:2]
+        return hits, ret
+
     def seqpare(self, q: Queries) -> np.ndarray:
         sm = np.zeros(self.nfiles, np.float64)
         self.L.orc_seqpare(self.h, q._p, sm)
         return sm
 
-    def hitsmap(self, v: int = 0) -> np.ndarray:
+    def hitsmap(self, v: int = 0, tiles=None) -> np.ndarray:
         hm = np.zeros((self.nfiles, self.nfiles), np.uint32)
-        self.L.orc_hitsmap(self.h, v, hm.reshape(-1))
+        if tiles is None:
+            self.L.orc_hitsmap(self.h, v, hm.reshape(-1))
+        else:
+            self.L.orc_hitsmap_tiles(self.h, v, int(tiles[0]), int(tiles[1]), hm.reshape(-1))
         return hm
 
 

@@ -1,0 +1,147 @@
+"""igd_b200.multi.ShardedSearch -- the N > 1 logic of count, -f and -m (shard, search, combine, restore order).
+
+CPU (`not gpu`): world_size 2 and 3 over gloo with the CPU oracle standing in as the per-rank engine; what is
+checked is everything that differs from the single-GPU path: the partition, the allreduce, the gather and the
+restoration of the input's query order.
+GPU (`gpu`): the same with the CUDA library as the engine, two ranks (on two GPUs when the box has them,
+otherwise both on cuda:0 with gloo carrying the collectives)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from igd_b200 import multi, workloads
+from tests.conftest import make_dense_db, make_queries
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+class OracleEngine:
+    """Adapter: the oracle with the engine interface of igd_b200.api.IGD (tests only)."""
+
+    def __init__(self, path):
+        from oracle import oracle as O
+        self.db = O.OracleDB(path)
+        self.nfiles = self.db.nfiles
+
+    def count(self, ctg, qs, qe, v=0):
+        hits, _ = self.db.count(ctg, qs, qe, v)
+        return hits, int(hits.sum())
+
+    def full(self, ctg, qs, qe):
+        per, _, s, e, f = self.db.full(ctg, qs, qe)
+        return np.concatenate([[0], np.cumsum(per)]).astype(np.int64), s, e, f
+
+    def hitsmap(self, v=0, tiles=None):
+        return self.db.hitsmap(v, tiles)
+
+
+def _queries():
+    q = make_queries(77, 5000, ("lognormal", 7.5, 1.6))
+    rng = np.random.default_rng(3)
+    p = rng.permutation(len(q))                                     # unsorted, as a query file would be
+    return q.ctg[p], q.start[p], q.end[p]
+
+
+def _rank_main(rank, world, port, igd_path, out_dir, engine_kind):
+    import torch
+    import torch.distributed as dist
+    comm = "cpu"
+    if engine_kind == "cuda":
+        from igd_b200 import api
+        ndev = torch.cuda.device_count()
+        if ndev >= world:
+            torch.cuda.set_device(rank)
+            dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                                    device_id=torch.device("cuda", rank))
+            comm = f"cuda:{rank}"
+            eng = api.IGD(igd_path, device=rank)
+        else:
+            dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+            eng = api.IGD(igd_path, device=0)
+    else:
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+        eng = OracleEngine(igd_path)
+    sh = multi.ShardedSearch(eng, workloads.read_igd_header(igd_path), comm_device=comm)
+    ctg, qs, qe = _queries()
+    out = {}
+    for v in (0, 500):
+        out[f"hits_v{v}"] = sh.count(ctg, qs, qe, v)
+        out[f"map_v{v}"] = sh.hitsmap(v)
+    r = sh.full(ctg, qs, qe, dst=world - 1)
+    assert (r is None) == (rank != world - 1)
+    if r is not None:
+        out["qoff"], out["s"], out["e"], out["f"] = r
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), **out)
+    dist.destroy_process_group()
+
+
+def _check(workdir, world, engine_kind):
+    import torch.multiprocessing as mp
+    stem = os.path.join(workdir, f"multi_db_{engine_kind}{world}")
+    make_dense_db(stem, n_files=13, n_per_file=1500, seed=21)
+    out_dir = os.path.join(workdir, f"multi_out_{engine_kind}{world}")
+    os.makedirs(out_dir, exist_ok=True)
+    mp.spawn(_rank_main, args=(world, _free_port(), stem + ".igd", out_dir, engine_kind), nprocs=world, join=True)
+    ref = OracleEngine(stem + ".igd")
+    ctg, qs, qe = _queries()
+    res = [np.load(os.path.join(out_dir, f"rank{r}.npz")) for r in range(world)]
+    for v in (0, 500):
+        want, _ = ref.count(ctg, qs, qe, v)
+        wmap = ref.hitsmap(v)
+        assert want.sum() > 0 and wmap.sum() > 0
+        for r in res:
+            assert np.array_equal(r[f"hits_v{v}"], want)
+            assert np.array_equal(r[f"map_v{v}"], wmap)
+    qoff, s, e, f = ref.full(ctg, qs, qe)                           # single engine, input order
+    last = res[world - 1]
+    assert np.array_equal(last["qoff"], qoff)
+    assert np.array_equal(last["s"], s) and np.array_equal(last["e"], e) and np.array_equal(last["f"], f)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_search_gloo_cpu(workdir, world):
+    _check(workdir, world, "oracle")
+
+
+@pytest.mark.gpu
+def test_sharded_search_cuda_two_ranks(workdir):
+    _check(workdir, 2, "cuda")
+
+
+def test_tile_bounds_cover_and_balance(workdir):
+    stem = os.path.join(workdir, "tb_db")
+    make_dense_db(stem, n_files=10, n_per_file=800, seed=5)
+    hdr = workloads.read_igd_header(stem + ".igd")
+    for parts in (1, 2, 3, 8):
+        b = multi.tile_bounds(hdr, parts)
+        assert b[0] == 0 and b[-1] == len(hdr["ncnt"]) and all(x <= y for x, y in zip(b, b[1:]))
+        n = hdr["ncnt"].astype(float)
+        cost = np.array([(n[b[i]:b[i + 1]] ** 2).sum() for i in range(parts)])
+        if parts <= 3:
+            assert cost.max() < 1.3 * cost.mean()
+
+
+@pytest.mark.gpu
+def test_hitsmap_tile_ranges_add_up(dense_db):
+    """igd_b200_hitsmap_tiles: maps of disjoint tile ranges add up to the whole map, each equal to the oracle's."""
+    from igd_b200 import api
+    from oracle import oracle as O
+    g, o = api.IGD(dense_db), O.OracleDB(dense_db)
+    T = g.ntiles
+    cuts = [0, 1, T // 3, T // 3, T - 2, T]
+    for v in (0, 300):
+        acc = np.zeros((g.nfiles, g.nfiles), np.uint32)
+        for lo, hi in zip(cuts, cuts[1:]):
+            part = g.hitsmap(v, tiles=(lo, hi))
+            assert np.array_equal(part, o.hitsmap(v, tiles=(lo, hi))), (v, lo, hi)
+            acc += part
+        assert np.array_equal(acc, g.hitsmap(v)) and np.array_equal(acc, o.hitsmap(v))
+    g.close()
