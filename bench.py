@@ -310,7 +310,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "k_count_items (count-mode search)", "kernel_ms": kmean,
+                         "traffic": traffic, "kernel": "k_count_packed (count-mode search, packed 16-bit layout)", "kernel_ms": kmean,
                          "own_bytes_per_launch": plan["own_bytes"],
                          "own_frac": plan["own_bytes"] / (kmean * 1e-3) / 1e9 / peak,
                          "plan_rank0": plan,
