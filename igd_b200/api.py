@@ -294,16 +294,18 @@ class IGD:
         return cost
 
     # -- -f ------------------------------------------------------------------------------------------
-    def full(self, ctg, qs, qe):
-        """-> (query_off[n+1], start, end, file) in the reference's per-query order."""
+    def full(self, ctg, qs, qe, copy: bool = True):
+        """-> (query_off[n+1], start, end, file) in the reference's per-query order.  With ``copy=False`` the
+        arrays are views of the handle's pinned result arena: valid until the next ``full`` on this handle."""
         ctg, qs, qe = self._a(ctg), self._a(qs), self._a(qe)
         hl = _HitList()
         if self._L.igd_b200_full(self._need(), len(ctg), ctg, qs, qe, C.byref(hl)):
             raise IGDError(last_error())
         try:
             n, t = len(ctg), int(hl.total)
-            qoff = np.ctypeslib.as_array(hl.query_off, (n + 1,)).copy()
-            mk = lambda p: np.ctypeslib.as_array(p, (t,)).copy() if t else np.zeros(0, np.int32)
+            fin = (lambda a: a.copy()) if copy else (lambda a: a)
+            qoff = fin(np.ctypeslib.as_array(hl.query_off, (n + 1,)))
+            mk = lambda p: fin(np.ctypeslib.as_array(p, (t,))) if t else np.zeros(0, np.int32)
             return qoff, mk(hl.start), mk(hl.end), mk(hl.file)
         finally:
             self._L.igd_b200_hitlist_free(C.byref(hl))

@@ -1461,6 +1461,8 @@ struct igdb_dev {
     char *ctg_names = nullptr;              // [nctg][40] contig names (device), for the text ingest
     int32_t *ctg_slots = nullptr;           // hash table over them
     uint32_t ctg_mask = 0;
+    void *arena = nullptr;                  // pinned host arena of the -f result lists
+    size_t arena_cap = 0;
     char *d_text = nullptr;                 // query text staging
     size_t d_text_cap = 0;
     bool packed = false;
@@ -1792,6 +1794,7 @@ void igdb_dev_destroy(igdb_dev *d)
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (d->pinned) cudaFreeHost(d->pinned);
+    if (d->arena) cudaFreeHost(d->arena);
     if (d->h_scalar) cudaFreeHost(d->h_scalar);
     if (d->plan_ev) cudaEventDestroy(d->plan_ev);
     for (auto &e : d->ev)
@@ -1890,10 +1893,26 @@ igdb_dev *igdb_dev_create(int device, int32_t nbp, int32_t nctg, const int32_t *
     return d;
 }
 
+void *igdb_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    memset(p, 0, bytes);
+    return p;
+}
+void igdb_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
 void *igdb_dev_pinned(igdb_dev *d, size_t bytes)
 {
     if (bytes > d->pinned_cap) {
         if (d->pinned) cudaFreeHost(d->pinned);
+    if (d->arena) cudaFreeHost(d->arena);
         d->pinned = nullptr, d->pinned_cap = 0;
         if (cudaMallocHost(&d->pinned, bytes) != cudaSuccess) return nullptr;
         d->pinned_cap = bytes;
@@ -2209,11 +2228,16 @@ int upload_queries(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_t *qs
 
 extern "C" {
 
+// The result arrays live in a pinned arena owned by the handle (grown to the high-water mark, reused by every
+// call): the lists come back at PCIe speed instead of being paged into freshly malloc'ed memory.  They stay
+// valid until the next -f call on this handle.
 int64_t igdb_dev_full_host(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_t *qs, const int32_t *qe,
-                           int64_t **query_off, int32_t **out_start, int32_t **out_end, int32_t **out_file)
+                           int64_t **query_off, int32_t **out_start, int32_t **out_end, int32_t **out_file,
+                           float *t_ms)
 {
     g_err[0] = 0;
     *query_off = nullptr, *out_start = *out_end = *out_file = nullptr;
+    if (t_ms) t_ms[0] = t_ms[1] = t_ms[2] = 0.f;
     CK(cudaSetDevice(d->device));
     if (finish_pending(d)) return -1;
     cudaStream_t st = d->stream;
@@ -2221,29 +2245,47 @@ int64_t igdb_dev_full_host(igdb_dev *d, int64_t n, const int32_t *ctg, const int
         snprintf(g_err, sizeof g_err, "igdb_dev_full_host: batch of %lld queries is too large", (long long)n);
         return -1;
     }
-    int64_t *h_qoff = (int64_t *)calloc((size_t)n + 1, sizeof(int64_t));
-    if (!h_qoff) return -1;
-    *query_off = h_qoff;
-    if (n == 0 || d->T == 0) return 0;
+    auto arena = [&](size_t bytes) -> int {
+        if (bytes <= d->arena_cap) return 0;
+        if (d->arena) CK(cudaFreeHost(d->arena));
+        d->arena = nullptr, d->arena_cap = 0;
+        const size_t want = bytes + (bytes >> 3) + 4096;
+        if (cudaHostAlloc(&d->arena, want, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            snprintf(g_err, sizeof g_err, "cannot pin %zu bytes of host memory for the overlap lists", want);
+            return -1;
+        }
+        d->arena_cap = want;
+        return 0;
+    };
+    const size_t qbytes = (((size_t)n + 1) * 8 + 255) & ~(size_t)255;
+    if (n == 0 || d->T == 0) {
+        if (arena(qbytes)) return -1;
+        memset(d->arena, 0, qbytes);
+        *query_off = (int64_t *)d->arena;
+        return 0;
+    }
+    CK(cudaEventRecord(d->ev[0], st));
     if (upload_queries(d, n, ctg, qs, qe, st)) return -1;
+    CK(cudaEventRecord(d->ev[1], st));
     DevBuf qoff, out;
     const int64_t total = full_device(d, n, st, false, qoff, out);
     if (total < 0) return -1;
+    CK(cudaEventRecord(d->ev[2], st));
+    if (arena(qbytes + (size_t)total * 12)) return -1;
+    int64_t *h_qoff = (int64_t *)d->arena;
+    int32_t *hs = (int32_t *)((char *)d->arena + qbytes);
     CK(cudaMemcpyAsync(h_qoff, qoff.p, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, st));
-    if (total > 0) {
-        int32_t *hs = (int32_t *)malloc((size_t)total * 4), *he = (int32_t *)malloc((size_t)total * 4),
-                *hf = (int32_t *)malloc((size_t)total * 4);
-        *out_start = hs, *out_end = he, *out_file = hf;
-        if (!hs || !he || !hf) {
-            snprintf(g_err, sizeof g_err, "out of host memory for %lld overlaps", (long long)total);
-            return -1;
-        }
-        const int32_t *o = out.as<int32_t>();
-        CK(cudaMemcpyAsync(hs, o, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(he, o + total, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(hf, o + 2 * total, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
-    }
+    if (total > 0) CK(cudaMemcpyAsync(hs, out.p, (size_t)total * 12, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(d->ev[3], st));
     CK(cudaStreamSynchronize(st));
+    *query_off = h_qoff;
+    if (total > 0) *out_start = hs, *out_end = hs + total, *out_file = hs + 2 * total;
+    if (t_ms) {
+        CK(cudaEventElapsedTime(&t_ms[0], d->ev[0], d->ev[1]));
+        CK(cudaEventElapsedTime(&t_ms[1], d->ev[1], d->ev[2]));
+        CK(cudaEventElapsedTime(&t_ms[2], d->ev[2], d->ev[3]));
+    }
     return total;
 }
 

@@ -33,6 +33,8 @@ int igdb_dev_packed(const igdb_dev *d);
 /* device time of the last count-mode search kernel (CUDA events on its stream); < 0 if none */
 float igdb_dev_last_search_ms(igdb_dev *d);
 void *igdb_dev_pinned(igdb_dev *d, size_t bytes);   /* reusable pinned staging buffer (upload) */
+void *igdb_host_alloc(size_t bytes);                /* zeroed page-locked host memory (small result buffers) */
+void igdb_host_free(void *p);
 
 /* count (mode_v = 0: get_overlaps control flow) / -v (mode_v = 1: get_overlaps_v control flow and the
  * value >= v predicate).  Host buffers; hits_delta[nfiles] receives the counts of THIS call. t_ms[3] = H2D,
@@ -56,9 +58,10 @@ int igdb_dev_hits_begin(igdb_dev *d);
 int igdb_dev_count_text(igdb_dev *d, const char *text, size_t len, int mode_v, int32_t v, int64_t *n_queries);
 int igdb_dev_hits_end(igdb_dev *d, uint64_t *hits_delta);
 
-/* -f: returns total (>= 0) and malloc'ed host arrays; query_off has n+1 entries */
+/* -f: returns total (>= 0) and host arrays in the handle's pinned arena (valid until the next -f call on the
+ * handle); query_off has n+1 entries.  t_ms[3] = H2D, kernels, D2H (may be NULL). */
 int64_t igdb_dev_full_host(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_t *qs, const int32_t *qe,
-                           int64_t **query_off, int32_t **start, int32_t **end, int32_t **file);
+                           int64_t **query_off, int32_t **start, int32_t **end, int32_t **file, float *t_ms);
 
 /* -s: n queries grouped by query-file chrom (grp[] ascending) and start-sorted inside a group; grp_nq[g] =
  * queries of group g; acc[nfiles] = sum of matched similarities per file */

@@ -110,14 +110,14 @@ igd_b200_t *igd_b200_open(const char *igd_path, int device)
         h->nrec += h->ncnt[t];
     }
     if (read_index_tsv(h, igd_path)) goto fail;
-    h->delta = calloc((size_t)h->nfiles + 1, sizeof(uint64_t));
-
     if (igdb_device_count() <= 0) {
         set_err("%s: no CUDA device available (igd_b200 has no CPU search path)", igd_path);
         goto fail;
     }
     h->dev = igdb_dev_create(device, h->nbp, h->nctg, h->ntile, h->ncnt, h->nfiles);
     if (!h->dev) goto fail;
+    h->delta = igdb_host_alloc(((size_t)h->nfiles + 1) * sizeof(uint64_t));    /* pinned: hits[] D2H target */
+    if (!h->delta) { set_err("%s: cannot allocate pinned host memory", igd_path); goto fail; }
     if (igdb_dev_set_contigs(h->dev, (const char *)h->cname)) goto fail;
     {
         const int64_t CH = 4 << 20;                     /* records per chunk: 64 MiB */
@@ -151,7 +151,7 @@ void igd_b200_close(igd_b200_t *h)
     if (h->dev) igdb_dev_destroy(h->dev);
     if (h->fname) for (int i = 0; i < h->nfiles; i++) free(h->fname[i]);
     free(h->fname); free(h->fnr); free(h->ntile); free(h->tbase); free(h->ncnt); free(h->cname);
-    free(h->delta); free(h);
+    igdb_host_free(h->delta); free(h);
 }
 
 int32_t igd_b200_nfiles(const igd_b200_t *h) { return h->nfiles; }
@@ -240,15 +240,16 @@ int igd_b200_full(igd_b200_t *h, int64_t n, const int32_t *ctg, const int32_t *q
     g_err[0] = 0;
     memset(out, 0, sizeof *out);
     out->n_queries = n;
-    out->total = igdb_dev_full_host(h->dev, n, ctg, qs, qe, &out->query_off, &out->start, &out->end, &out->file);
+    out->total = igdb_dev_full_host(h->dev, n, ctg, qs, qe, &out->query_off, &out->start, &out->end, &out->file,
+                                    h->t_ms);
     if (out->total < 0) { igd_b200_hitlist_free(out); return -1; }
     return 0;
 }
 
+/* the arrays belong to the handle's pinned arena: nothing to release, the struct is just cleared */
 void igd_b200_hitlist_free(igd_b200_hitlist *l)
 {
     if (!l) return;
-    free(l->query_off); free(l->start); free(l->end); free(l->file);
     memset(l, 0, sizeof *l);
 }
 

@@ -76,7 +76,10 @@ int igd_b200_count_device_finish(igd_b200_t *h);
 
 /* -f: the overlaps themselves, in the reference's order (get_overlaps_f1, src/igd_search.c:537-620:
  * per query, bin n1 from the last start < qe downwards, then later bins ascending).
- * The arrays are malloc'ed by the library and released with igd_b200_hitlist_free. */
+ * The arrays live in a pinned host arena owned by the handle (so that the lists come back at PCIe speed): they
+ * stay valid until the next igd_b200_full / -f call on the same handle or igd_b200_close, and must not be
+ * freed by the caller; igd_b200_hitlist_free only clears the struct.  igd_b200_last_timing reports the H2D /
+ * kernel / D2H split of the call. */
 typedef struct {
     int64_t total;          /* number of overlaps */
     int64_t n_queries;
