@@ -239,6 +239,7 @@ def run_ours(args):
         t0 = time.perf_counter()
         hits_e2e = step_e2e()
         e2e_s += time.perf_counter() - t0
+    e2e_split = igd.last_timing() if world == 1 else None
     sampler.stop_flag = True
     sampler.join()
 
@@ -301,6 +302,7 @@ def run_ours(args):
                                       "sum; one NCCL int64 allreduce of hits[]" if world > 1 else "single GPU", "db_build_s": round(build_s, 1), "db_open_s": round(open_s, 2)},
             "e2e": {"value": n_total / (e2e_s / args.steps), "unit": UNIT, "ms_per_step": e2e_s / args.steps * 1e3,
                     "h2d_bytes_per_step": 12 * n_total, "d2h_bytes_per_step": 8 * igd.nfiles * world,
+                    "device_split_ms_last_step": e2e_split,
                     "api": "igd_b200_count (C-ABI, host buffers)" if world == 1 else
                            "pinned H2D + igd_b200_count_device + NCCL allreduce + D2H"},
             "file_ingest": None if file_s is None else {

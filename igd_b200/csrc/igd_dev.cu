@@ -341,19 +341,76 @@ __device__ __forceinline__ bool mode_takes(int qs, int qe)
     return MODE == M_ALL32 ? true : (MODE == M_PACKED ? normal : !normal);
 }
 
-template <bool V, int MODE>
-__global__ void k_cseg_count(DbView db, int64_t n, const int32_t *__restrict__ ctg, const int32_t *__restrict__ qs,
-                             const int32_t *__restrict__ qe, uint32_t *__restrict__ cnt2)
+// Count pass and scatter pass share one walker that keeps CSEG_Q queries per thread in flight: their loads of the
+// query, of the first-bin tile and their atomics are issued back to back (four independent dependency chains per
+// thread instead of one), the later bins -- which few queries have -- follow in a per-query loop.  Restates the
+// control flow of get_overlaps / get_overlaps_v exactly as for_each_segment does (see there).
+constexpr int CSEG_Q = 4, CSEG_T = 256;
+constexpr int CSEG_MAXCTG = 1024;           // contig table kept in shared memory up to this many contigs
+
+template <bool V, int MODE, class F1, class FL>
+__device__ __forceinline__ void cseg_walk(const DbView &db, int64_t n, const int32_t *__restrict__ ctg,
+                                          const int32_t *__restrict__ qs, const int32_t *__restrict__ qe,
+                                          uint32_t *__restrict__ abn, int abn_sign, F1 first, FL later)
 {
-    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n) return;
-    const int s = qs[q], e = qe[q];
-    if (!mode_takes<MODE>(s, e)) {
-        if (MODE == M_PACKED) atomicAdd(&cnt2[2 * db.ntiles], 1u);
-        return;
+    __shared__ int32_t tb_s[CSEG_MAXCTG + 1];
+    const bool in_smem = db.nctg <= CSEG_MAXCTG;
+    if (in_smem) {
+        for (int i = threadIdx.x; i <= db.nctg; i += blockDim.x) tb_s[i] = __ldg(&db.tbase[i]);
+        __syncthreads();
     }
-    for_each_segment<V>(db, ctg[q], s, e,
-                        [&](int tile, bool later, int, int) { atomicAdd(&cnt2[2 * tile + (later ? 1 : 0)], 1u); });
+    const int nbp = db.nbp;
+    const int64_t q0 = (int64_t)blockIdx.x * (CSEG_T * CSEG_Q) + threadIdx.x;
+    int c[CSEG_Q], s[CSEG_Q], e[CSEG_Q], tile[CSEG_Q], nlast[CSEG_Q], bd[CSEG_Q];
+    bool ok[CSEG_Q];
+    int nabn = 0;
+#pragma unroll
+    for (int k = 0; k < CSEG_Q; ++k) {
+        const int64_t q = q0 + (int64_t)k * CSEG_T;
+        ok[k] = q < n;
+        c[k] = ok[k] ? ctg[q] : -1, s[k] = ok[k] ? qs[q] : 0, e[k] = ok[k] ? qe[q] : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < CSEG_Q; ++k) {
+        if (ok[k] && !mode_takes<MODE>(s[k], e[k])) ok[k] = false, nabn += MODE == M_PACKED;
+        ok[k] = ok[k] && c[k] >= 0 && c[k] < db.nctg;                       // unknown chrom (:456-458)
+        tile[k] = nlast[k] = bd[k] = 0;
+        if (ok[k]) {
+            const int n1 = s[k] / nbp, n2 = (e[k] - 1) / nbp;               // C truncating division (:459)
+            const int tb = in_smem ? tb_s[c[k]] : __ldg(&db.tbase[c[k]]);
+            const int mT = (in_smem ? tb_s[c[k] + 1] : __ldg(&db.tbase[c[k] + 1])) - tb - 1;
+            ok[k] = n1 >= 0 && n1 <= mT;                                    // :462
+            tile[k] = tb + n1, nlast[k] = tb + max(n1, min(n2, mT)), bd[k] = n1 * nbp;
+        }
+    }
+    int4 m[CSEG_Q];
+#pragma unroll
+    for (int k = 0; k < CSEG_Q; ++k)
+        m[k] = ok[k] ? __ldg(reinterpret_cast<const int4 *>(&db.tiles[tile[k]])) : make_int4(0, 0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < CSEG_Q; ++k) {
+        if (!V && m[k].y == 0) ok[k] = false;                               // first-bin-empty quirk (:468)
+        if (ok[k] && m[k].y > 0 && e[k] > m[k].w) first(tile[k], s[k], e[k], bd[k]);   // nCnt > 0 and qe > start[0]
+    }
+    if (MODE == M_PACKED && nabn) atomicAdd(abn, (uint32_t)(abn_sign * nabn));   // left to the M_ABN32 pipeline
+#pragma unroll
+    for (int k = 0; k < CSEG_Q; ++k) {
+        if (!ok[k]) continue;
+        for (int t = tile[k] + 1; t <= nlast[k]; ++t) {                     // later bins (:500-531)
+            const int4 mm = __ldg(reinterpret_cast<const int4 *>(&db.tiles[t]));
+            if (mm.y > 0 && e[k] > mm.w) later(t, s[k], e[k], bd[k] + (t - tile[k]) * nbp);
+        }
+    }
+}
+
+template <bool V, int MODE>
+__global__ void __launch_bounds__(CSEG_T) k_cseg_count(DbView db, int64_t n, const int32_t *__restrict__ ctg,
+                                                        const int32_t *__restrict__ qs, const int32_t *__restrict__ qe,
+                                                        uint32_t *__restrict__ cnt2)
+{
+    cseg_walk<V, MODE>(
+        db, n, ctg, qs, qe, &cnt2[2 * db.ntiles], +1, [&](int tile, int, int, int) { atomicAdd(&cnt2[2 * tile], 1u); },
+        [&](int tile, int, int, int) { atomicAdd(&cnt2[2 * tile + 1], 1u); });
 }
 
 __device__ __forceinline__ Plan plan_of_tile(const DbView &db, const uint32_t *__restrict__ cnt2, int32_t t)
@@ -366,8 +423,8 @@ __device__ __forceinline__ Plan plan_of_tile(const DbView &db, const uint32_t *_
     return Plan{(s + 1) & ~1ull, g * ((s + SMAX - 1) / SMAX)};
 }
 
-// The whole plan in ONE launch: a chained scan over the tiles fused with the item fill.  The grid has at most one
-// CTA per SM (all co-resident), CTA b owns a contiguous range of tiles:
+// The whole plan in ONE launch: a chained scan over the tiles fused with the item fill.  The grid has at most four
+// 512-thread CTAs per SM (all co-resident), CTA b owns a contiguous range of tiles:
 //   1. block-reduce the plan of its range and publish it (agg[b], then flag[b] = epoch);
 //   2. wait for every CTA's aggregate: the sum of the earlier ones is this CTA's prefix, the sum of all is the
 //      batch total -- if that does not fit the scratch buffers nothing more is written (the host grows them
@@ -393,7 +450,7 @@ __global__ void __launch_bounds__(SCAN_T) k_plan(DbView db, const uint32_t *__re
                                                   unsigned long long *__restrict__ tot, unsigned long long seg_cap,
                                                   unsigned long long item_cap, int4 *__restrict__ items)
 {
-    __shared__ unsigned long long red[3][SCAN_T / 32];
+    __shared__ unsigned long long red[3][SCAN_T / 32], red5[5][SCAN_T / 32];
     __shared__ unsigned long long sh_prefix[2], sh_total[3];
     const int32_t T = db.ntiles;
     const int G = gridDim.x, b = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -420,28 +477,40 @@ __global__ void __launch_bounds__(SCAN_T) k_plan(DbView db, const uint32_t *__re
         unsigned long long x = 0, y = 0, z = 0;
         for (int w = 0; w < SCAN_T / 32; ++w) x += red[0][w], y += red[1][w], z += red[2][w];
         agg[b].segs = x, agg[b].items = y, agg[b].recs = z;
-        __threadfence();
-        flag[b] = epoch;
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&flag[b]), "r"(epoch) : "memory");
     }
-    // 2. everybody's aggregates
-    if (wid == 0) {
-        unsigned long long ps = 0, pi = 0, ts = 0, ti = 0, tr = 0;
-        for (int i = lane; i < G; i += 32) {
-            while (flag[i] != epoch) __nanosleep(20);
-            __threadfence();
+    // 2. everybody's aggregates (every thread waits for its share of the CTAs)
+    {
+        unsigned long long v5[5] = {0, 0, 0, 0, 0};         // prefix segs / items, total segs / items / records
+        for (int i = threadIdx.x; i < G; i += SCAN_T) {
+            for (;;) {                                      // acquire: the aggregate is visible once the flag is
+                uint32_t f;
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(&flag[i]) : "memory");
+                if (f == epoch) break;
+                __nanosleep(20);
+            }
             const unsigned long long x = agg[i].segs, y = agg[i].items, z = agg[i].recs;
-            ts += x, ti += y, tr += z;
-            if (i < b) ps += x, pi += y;
+            v5[2] += x, v5[3] += y, v5[4] += z;
+            if (i < b) v5[0] += x, v5[1] += y;
         }
 #pragma unroll
-        for (int d = 16; d; d >>= 1) {
-            ps += __shfl_xor_sync(FULL, ps, d), pi += __shfl_xor_sync(FULL, pi, d);
-            ts += __shfl_xor_sync(FULL, ts, d), ti += __shfl_xor_sync(FULL, ti, d), tr += __shfl_xor_sync(FULL, tr, d);
+        for (int k = 0; k < 5; ++k) {
+#pragma unroll
+            for (int d = 16; d; d >>= 1) v5[k] += __shfl_xor_sync(FULL, v5[k], d);
         }
+        __syncthreads();                                    // red[] was read by thread 0 above
         if (lane == 0) {
-            sh_prefix[0] = ps, sh_prefix[1] = pi, sh_total[0] = ts, sh_total[1] = ti, sh_total[2] = tr;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) red5[k][wid] = v5[k];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long t5[5] = {0, 0, 0, 0, 0};
+            for (int w = 0; w < SCAN_T / 32; ++w)
+                for (int k = 0; k < 5; ++k) t5[k] += red5[k][w];
+            sh_prefix[0] = t5[0], sh_prefix[1] = t5[1], sh_total[0] = t5[2], sh_total[1] = t5[3], sh_total[2] = t5[4];
             if (b == G - 1) {
-                tot[0] = ts, tot[1] = ti, tot[2] = tr;
+                tot[0] = t5[2], tot[1] = t5[3], tot[2] = t5[4];
                 tot[3] = cnt2[2 * T];                      // queries left to the M_ABN32 pipeline (M_PACKED only)
             }
         }
@@ -503,28 +572,32 @@ __global__ void __launch_bounds__(SCAN_T) k_plan(DbView db, const uint32_t *__re
 // M_PACKED writes 4-byte segments in the tile's packed coordinates, pre-biased like the records:
 //   bits 0-15 = qs' + 1, bits 16-31 = qe' + 0x8000.
 template <bool V, int MODE>
-__global__ void k_cseg_scatter(DbView db, int64_t n, const int32_t *__restrict__ ctg, const int32_t *__restrict__ qs,
-                               const int32_t *__restrict__ qe, uint32_t *__restrict__ cnt2,
-                               const uint32_t *__restrict__ seg_off, const uint32_t *__restrict__ seg_mid,
-                               const unsigned long long *__restrict__ tot, unsigned long long seg_cap,
-                               unsigned long long item_cap, void *__restrict__ segs)
+__global__ void __launch_bounds__(CSEG_T) k_cseg_scatter(DbView db, int64_t n, const int32_t *__restrict__ ctg,
+                                                          const int32_t *__restrict__ qs, const int32_t *__restrict__ qe,
+                                                          uint32_t *__restrict__ cnt2, const uint32_t *__restrict__ seg_off,
+                                                          const uint32_t *__restrict__ seg_mid,
+                                                          const unsigned long long *__restrict__ tot,
+                                                          unsigned long long seg_cap, unsigned long long item_cap,
+                                                          void *__restrict__ segs)
 {
-    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n || tot[0] > seg_cap || tot[1] > item_cap) return;
-    const int s = qs[q], e = qe[q];
-    if (!mode_takes<MODE>(s, e)) {
-        if (MODE == M_PACKED) atomicSub(&cnt2[2 * db.ntiles], 1u);
-        return;
-    }
-    for_each_segment<V>(db, ctg[q], s, e, [&](int tile, bool later, int, int bd) {
-        const uint32_t b = later ? __ldg(&seg_mid[tile]) : __ldg(&seg_off[tile]);
-        const uint32_t pos = b + atomicSub(&cnt2[2 * tile + (later ? 1 : 0)], 1u) - 1u;
+    if (tot[0] > seg_cap || tot[1] > item_cap) return;
+    const int nbp = db.nbp;
+    auto put = [&](uint32_t pos, int s, int e, int bd) {
         if (MODE == M_PACKED)
             static_cast<uint32_t *>(segs)[pos] =
-                (uint32_t)(pk_rel(s, bd, db.nbp) + 1) | (uint32_t)(pk_rel_end(e, bd, db.nbp) + 0x8000) << 16;
+                (uint32_t)(pk_rel(s, bd, nbp) + 1) | (uint32_t)(pk_rel_end(e, bd, nbp) + 0x8000) << 16;
         else
             static_cast<CSeg *>(segs)[pos] = CSeg{s, e};
-    });
+    };
+    // (the queries left to the M_ABN32 pipeline are counted back down too)
+    cseg_walk<V, MODE>(
+        db, n, ctg, qs, qe, &cnt2[2 * db.ntiles], -1,
+        [&](int tile, int s, int e, int bd) {
+            put(__ldg(&seg_off[tile]) + atomicSub(&cnt2[2 * tile], 1u) - 1u, s, e, bd);
+        },
+        [&](int tile, int s, int e, int bd) {
+            put(__ldg(&seg_mid[tile]) + atomicSub(&cnt2[2 * tile + 1], 1u) - 1u, s, e, bd);
+        });
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1497,7 +1570,8 @@ struct igdb_dev {
     int plan_grid = 1;
     unsigned long long *plan_tot = nullptr;                 // device {segments, items} of the batch in flight
     volatile unsigned long long *h_plan = nullptr;          // pinned copy of plan_tot
-    cudaEvent_t plan_ev = nullptr;
+    cudaEvent_t plan_ev = nullptr, plan_done = nullptr;
+    cudaStream_t side = nullptr;                            // carries the plan readback
     CSeg *csegs = nullptr;
     int64_t cseg_cap = 0;
     int4 *items = nullptr;
@@ -1674,14 +1748,17 @@ int enqueue_count(igdb_dev *d, const igdb_dev::Pending &p)
     const unsigned long long seg_cap = (unsigned long long)std::min<int64_t>(d->cseg_cap - CAP_SLACK, 0x7fffffff);
     const unsigned long long item_cap =
         (unsigned long long)std::min<int64_t>(d->item_cap - CAP_SLACK, item_limit(d, grid));
-    const int thr = 256;
-    const int nb = (int)((p.n + thr - 1) / thr);
+    const int thr = CSEG_T;
+    const int nb = (int)((p.n + CSEG_T * CSEG_Q - 1) / (CSEG_T * CSEG_Q));
     k_cseg_count<V, MODE><<<nb, thr, 0, st>>>(db, p.n, p.ctg, p.qs, p.qe, d->cnt2);
     // (the plan reads the later-bin counters that the scatter counts back down to zero)
     k_plan<<<d->plan_grid, SCAN_T, 0, st>>>(db, d->cnt2, ++d->plan_epoch, d->plan_agg, d->plan_flag, d->cseg_off,
                                             d->cseg_mid, d->plan_tot, seg_cap, item_cap, d->items);
-    CK(cudaMemcpyAsync((void *)d->h_plan, d->plan_tot, 32, cudaMemcpyDeviceToHost, st));
-    CK(cudaEventRecord(d->plan_ev, st));
+    // the plan's totals go back to the host on a side stream, so that the copy does not sit between the kernels
+    CK(cudaEventRecord(d->plan_done, st));
+    CK(cudaStreamWaitEvent(d->side, d->plan_done, 0));
+    CK(cudaMemcpyAsync((void *)d->h_plan, d->plan_tot, 32, cudaMemcpyDeviceToHost, d->side));
+    CK(cudaEventRecord(d->plan_ev, d->side));
     k_cseg_scatter<V, MODE><<<nb, thr, 0, st>>>(db, p.n, p.ctg, p.qs, p.qe, d->cnt2, d->cseg_off, d->cseg_mid,
                                                  d->plan_tot, seg_cap, item_cap, d->csegs);
     CountArgs a{};
@@ -1797,6 +1874,8 @@ void igdb_dev_destroy(igdb_dev *d)
     if (d->arena) cudaFreeHost(d->arena);
     if (d->h_scalar) cudaFreeHost(d->h_scalar);
     if (d->plan_ev) cudaEventDestroy(d->plan_ev);
+    if (d->plan_done) cudaEventDestroy(d->plan_done);
+    if (d->side) cudaStreamDestroy(d->side);
     for (auto &e : d->ev)
         if (e) cudaEventDestroy(e);
     for (auto &e : d->kev)
@@ -1817,6 +1896,8 @@ static int create_impl(igdb_dev *d, const int32_t *ntile, const int32_t *ncnt)
     CK(cudaMallocHost((void **)&d->h_scalar, 64));
     d->h_plan = reinterpret_cast<volatile unsigned long long *>(d->h_scalar + 8);
     CK(cudaEventCreateWithFlags(&d->plan_ev, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&d->plan_done, cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&d->side, cudaStreamNonBlocking));
 
     std::vector<int32_t> tbase(d->nctg + 1, 0);
     for (int c = 0; c < d->nctg; ++c) tbase[c + 1] = tbase[c] + ntile[c];
@@ -1849,7 +1930,7 @@ static int create_impl(igdb_dev *d, const int32_t *ntile, const int32_t *ncnt)
         dev_alloc(d, &d->tile_off, (size_t)d->T + 1) || dev_alloc(d, &d->d_hits, (size_t)d->nfiles) ||
         dev_alloc(d, &d->cnt2, (size_t)2 * d->T + 2) || dev_alloc(d, &d->cseg_off, (size_t)d->T + 1) ||
         dev_alloc(d, &d->cseg_mid, (size_t)d->T + 1) ||
-        dev_alloc(d, &d->plan_agg, (size_t)d->sm_count) || dev_alloc(d, &d->plan_flag, (size_t)d->sm_count) ||
+        dev_alloc(d, &d->plan_agg, (size_t)4 * d->sm_count) || dev_alloc(d, &d->plan_flag, (size_t)4 * d->sm_count) ||
         dev_alloc(d, &d->plan_tot, 8))
         return -1;
     // packed count-mode copies: tile-relative coordinates need nbp + 1 < 2^15, file indices 16 bits
@@ -1874,9 +1955,13 @@ static int create_impl(igdb_dev *d, const int32_t *ntile, const int32_t *ncnt)
     CK(cudaMemset(d->idx, 0, ((size_t)d->P + 8) * 4));
     CK(cudaMemset(d->tile_cnt, 0, ((size_t)d->T + 1) * 4));
     CK(cudaMemset(d->cnt2, 0, ((size_t)2 * d->T + 2) * 4));
-    CK(cudaMemset(d->plan_flag, 0, (size_t)d->sm_count * 4));
-    // k_plan's CTAs wait for each other: at most one per SM, so that all of them are resident
-    d->plan_grid = std::max(1, std::min(d->sm_count, (d->T + SCAN_T - 1) / SCAN_T));
+    CK(cudaMemset(d->plan_flag, 0, (size_t)4 * d->sm_count * 4));
+    // k_plan's CTAs wait for each other, so all of them must be resident at once: never more than the
+    // occupancy calculator allows (and at most 4 per SM, the size of the flag arrays)
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_plan, SCAN_T, 0));
+    per_sm = std::max(1, std::min(per_sm, 4));
+    d->plan_grid = std::max(1, std::min(per_sm * d->sm_count, (d->T + SCAN_T - 1) / SCAN_T));
     return 0;
 }
 

@@ -226,3 +226,20 @@ def test_count_other_bin_sizes(workdir, O, api, b):
     qoff, gs, ge, gf = g.full(ctg[:3000], qs[:3000], qe[:3000])
     assert np.array_equal(np.diff(qoff), per) and np.array_equal(gs, s) and np.array_equal(ge, e) and np.array_equal(gf, f)
     g.close()
+
+
+def test_count_many_tiles(workdir, O, api):
+    """-b 12 on hg38: 754k tiles, more than one plan CTA per 512 tiles can be resident at once -- the chained
+    scan of k_plan must cap its grid (a grid larger than the resident capacity would wait for itself)."""
+    stem = os.path.join(workdir, "manytiles")
+    law = ("lognormal", 7.0, 1.5)
+    files = [synth.gen_intervals(synth.seed_for(1, 50 + i), 20000, law) for i in range(10)]
+    synth.write_igd_direct(stem, files, nbp=4096)
+    q = synth.gen_intervals(synth.seed_for(1, 999), 200000, ("lognormal", 8.0, 1.5))
+    odb, g = O.OracleDB(stem + ".igd"), api.IGD(stem + ".igd")
+    assert g.ntiles > 700000
+    for v in (0, 500):
+        want, _ = odb.count(q.ctg, q.start, q.end, v)
+        got, _ = g.count(q.ctg, q.start, q.end, v)
+        assert want.sum() > 0 and np.array_equal(got, want)
+    g.close()
