@@ -223,6 +223,13 @@ def run_ours(args):
     torch.cuda.synchronize()
     launches = igd.launch_count() - launches0
     plan = igd.last_plan()
+    # one more (untimed) step with CUDA events around each of the four launches
+    igd.stage_timing(True)
+    flush.fill_(3)
+    step_device()
+    torch.cuda.synchronize()
+    stages = igd.last_stage_ms()
+    igd.stage_timing(False)
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = float(sum(step_ms))
 
@@ -313,6 +320,7 @@ def run_ours(args):
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "k_count_packed (count-mode search, packed 16-bit layout)", "kernel_ms": kmean,
+                         "stages_ms_rank0": stages,
                          "own_bytes_per_launch": plan["own_bytes"],
                          "own_frac": plan["own_bytes"] / (kmean * 1e-3) / 1e9 / peak,
                          "plan_rank0": plan,

@@ -102,6 +102,9 @@ def load_library():
     L.igd_b200_last_search_kernel_ms.argtypes = [vp]
     L.igd_b200_last_timing.argtypes = [vp, C.POINTER(C.c_float * 3)]
     L.igd_b200_last_plan.argtypes = [vp, C.POINTER(C.c_int64 * 4)]
+    L.igd_b200_stage_timing.argtypes = [vp, C.c_int]
+    L.igd_b200_last_stage_ms.restype = C.c_int
+    L.igd_b200_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float * 4)]
     L.igd_b200_use.argtypes = [vp]
     L.igd_b200_current.restype = vp
     L.get_overlaps.restype = C.c_int32
@@ -217,6 +220,15 @@ class IGD:
         t = (C.c_int64 * 4)()
         self._L.igd_b200_last_plan(self._need(), C.byref(t))
         return {"segments": t[0], "items": t[1], "records": t[2], "own_bytes": t[3]}
+
+    def stage_timing(self, on: bool = True) -> None:
+        self._L.igd_b200_stage_timing(self._need(), int(on))
+
+    def last_stage_ms(self):
+        t = (C.c_float * 4)()
+        if self._L.igd_b200_last_stage_ms(self._need(), C.byref(t)) < 0:
+            return None
+        return {"seg_count": t[0], "plan": t[1], "seg_scatter": t[2], "search": t[3]}
 
     def last_timing(self):
         t = (C.c_float * 3)()

@@ -81,6 +81,13 @@ struct __align__(16) Seg {
 
 constexpr unsigned FULL = 0xffffffffu;
 
+// Programmatic dependent launch (sm_90+): the four kernels of a count batch are launched with the
+// programmatic-stream-serialization attribute, so that the launch of kernel k + 1 overlaps the execution of
+// kernel k.  pdl_wait() must come before the first access to anything the previous kernel wrote;
+// pdl_launch_dependents() lets the next kernel's CTAs be scheduled as soon as every CTA of this one has started.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+
 __device__ __forceinline__ int4 ldg4(const int32_t *p) { return __ldg(reinterpret_cast<const int4 *>(p)); }
 
 // tile-relative coordinates of the packed count-mode layout: x' = clamp(x - bd + 1, 0, nbp + 1).
@@ -355,12 +362,14 @@ __device__ __forceinline__ void cseg_walk(const DbView &db, int64_t n, const int
 {
     __shared__ int32_t tb_s[CSEG_MAXCTG + 1];
     const bool in_smem = db.nctg <= CSEG_MAXCTG;
+    pdl_launch_dependents();
     if (in_smem) {
         for (int i = threadIdx.x; i <= db.nctg; i += blockDim.x) tb_s[i] = __ldg(&db.tbase[i]);
         __syncthreads();
     }
     const int nbp = db.nbp;
     const int64_t q0 = (int64_t)blockIdx.x * (CSEG_T * CSEG_Q) + threadIdx.x;
+    pdl_wait();                                             // the queries / counters of the previous launch
     int c[CSEG_Q], s[CSEG_Q], e[CSEG_Q], tile[CSEG_Q], nlast[CSEG_Q], bd[CSEG_Q];
     bool ok[CSEG_Q];
     int nabn = 0;
@@ -455,6 +464,8 @@ __global__ void __launch_bounds__(SCAN_T) k_plan(DbView db, const uint32_t *__re
     const int32_t T = db.ntiles;
     const int G = gridDim.x, b = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int32_t per = (T + G - 1) / G, t0 = min(b * per, T), t1 = min(t0 + per, T);
+    pdl_launch_dependents();
+    pdl_wait();                                             // the segment counters
 
     // 1. aggregate of this CTA's range
     unsigned long long segs = 0, its = 0, recs = 0;
@@ -580,6 +591,7 @@ __global__ void __launch_bounds__(CSEG_T) k_cseg_scatter(DbView db, int64_t n, c
                                                           unsigned long long seg_cap, unsigned long long item_cap,
                                                           void *__restrict__ segs)
 {
+    pdl_wait();                                             // the plan
     if (tot[0] > seg_cap || tot[1] > item_cap) return;
     const int nbp = db.nbp;
     auto put = [&](uint32_t pos, int s, int e, int bd) {
@@ -683,8 +695,9 @@ struct CountSmem {
     // warps of the (single) CTA of an SM: as many pipelines as fit beside the histogram
     static int warps(int nfiles, bool smem_hist)
     {
-        const size_t room = 226 * 1024 - (smem_hist ? hist_bytes(nfiles) : 0);
-        return (int)std::min<size_t>(room / WARP, COUNT_MAXW);
+        const size_t total = 226 * 1024, hist = smem_hist ? hist_bytes(nfiles) : 0;
+        if (hist >= total) return 0;                        // the histogram alone does not fit
+        return (int)std::min<size_t>((total - hist) / WARP, COUNT_MAXW);
     }
     static size_t cta_bytes(int nfiles, bool smem_hist, int nwarps)
     {
@@ -878,8 +891,9 @@ struct PackedSmem {
     static size_t hist_bytes(int nfiles) { return ((size_t)nfiles * 4 + 127) / 128 * 128; }
     static int warps(int nfiles, bool smem_hist)
     {
-        const size_t room = 226 * 1024 - (smem_hist ? hist_bytes(nfiles) : 0);
-        return (int)std::min<size_t>(room / WARP, PK_MAXW);
+        const size_t total = 226 * 1024, hist = smem_hist ? hist_bytes(nfiles) : 0;
+        if (hist >= total) return 0;                        // the histogram alone does not fit
+        return (int)std::min<size_t>((total - hist) / WARP, PK_MAXW);
     }
     static size_t cta_bytes(int nfiles, bool smem_hist, int nwarps)
     {
@@ -941,7 +955,8 @@ __global__ void __launch_bounds__(PK_MAXW * 32, 1) k_count_packed(const CountArg
     const uint32_t hist_s = smem_u32(smem);
     const int lane = threadIdx.x & 31, W = blockDim.x >> 5, wib = threadIdx.x >> 5;
     const uint32_t wbase = hist_s + hist_bytes + (uint32_t)wib * L::WARP;
-    const unsigned long long nseg = __ldg(&a.tot[0]), nit = __ldg(&a.tot[1]);
+    pdl_wait();                                             // the plan, the items, the segments
+    const unsigned long long nseg = a.tot[0], nit = a.tot[1];
     const uint32_t n_items = (nseg > a.seg_cap || nit > a.item_cap) ? 0u : (uint32_t)nit;
     const uint32_t nblk = (n_items + PK_IB - 1) / PK_IB, NW = gridDim.x * W, w = blockIdx.x * W + wib;
     const uint32_t nb = w < nblk ? (nblk - w + NW - 1) / NW : 0;       // blocks of this warp
@@ -1571,6 +1586,8 @@ struct igdb_dev {
     unsigned long long *plan_tot = nullptr;                 // device {segments, items} of the batch in flight
     volatile unsigned long long *h_plan = nullptr;          // pinned copy of plan_tot
     cudaEvent_t plan_ev = nullptr, plan_done = nullptr;
+    cudaEvent_t stage_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // around the 4 launches (diagnostics)
+    bool stage_timing = false, stage_valid = false;
     cudaStream_t side = nullptr;                            // carries the plan readback
     CSeg *csegs = nullptr;
     int64_t cseg_cap = 0;
@@ -1706,6 +1723,19 @@ int build_segments(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_t *qs
 // plan check on the device that it fits the scratch buffers and do nothing otherwise; the host looks at
 // the plan's totals when it settles the batch and, in the rare case they did not fit (first batch of a
 // larger size), grows the buffers and runs the batch again -- or splits it when the plan itself is too big.
+// launch with programmatic stream serialization (see pdl_wait): only for kernels that call pdl_wait()
+template <class... KArgs, class... Args>
+cudaError_t launch_pdl(void (*k)(KArgs...), unsigned grid, unsigned block, size_t shm, cudaStream_t st, Args &&...args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(block), cfg.dynamicSmemBytes = shm, cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at, cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k, KArgs(std::forward<Args>(args))...);
+}
+
 template <bool V, bool PK>
 int count_geometry(igdb_dev *d, int *grid, int *threads, size_t *shm, bool *smem)
 {
@@ -1750,24 +1780,29 @@ int enqueue_count(igdb_dev *d, const igdb_dev::Pending &p)
         (unsigned long long)std::min<int64_t>(d->item_cap - CAP_SLACK, item_limit(d, grid));
     const int thr = CSEG_T;
     const int nb = (int)((p.n + CSEG_T * CSEG_Q - 1) / (CSEG_T * CSEG_Q));
-    k_cseg_count<V, MODE><<<nb, thr, 0, st>>>(db, p.n, p.ctg, p.qs, p.qe, d->cnt2);
+    const bool stages = d->stage_timing && MODE != M_ABN32;
+    if (stages) CK(cudaEventRecord(d->stage_ev[0], st));
+    CK(launch_pdl(k_cseg_count<V, MODE>, nb, thr, 0, st, db, p.n, p.ctg, p.qs, p.qe, d->cnt2));
+    if (stages) CK(cudaEventRecord(d->stage_ev[1], st));
     // (the plan reads the later-bin counters that the scatter counts back down to zero)
-    k_plan<<<d->plan_grid, SCAN_T, 0, st>>>(db, d->cnt2, ++d->plan_epoch, d->plan_agg, d->plan_flag, d->cseg_off,
-                                            d->cseg_mid, d->plan_tot, seg_cap, item_cap, d->items);
+    CK(launch_pdl(k_plan, d->plan_grid, SCAN_T, 0, st, db, d->cnt2, ++d->plan_epoch, d->plan_agg, d->plan_flag,
+                  d->cseg_off, d->cseg_mid, d->plan_tot, seg_cap, item_cap, d->items));
+    if (stages) CK(cudaEventRecord(d->stage_ev[2], st));
+    CK(launch_pdl(k_cseg_scatter<V, MODE>, nb, thr, 0, st, db, p.n, p.ctg, p.qs, p.qe, d->cnt2, d->cseg_off,
+                  d->cseg_mid, d->plan_tot, seg_cap, item_cap, (void *)d->csegs));
     // the plan's totals go back to the host on a side stream, so that the copy does not sit between the kernels
     CK(cudaEventRecord(d->plan_done, st));
     CK(cudaStreamWaitEvent(d->side, d->plan_done, 0));
     CK(cudaMemcpyAsync((void *)d->h_plan, d->plan_tot, 32, cudaMemcpyDeviceToHost, d->side));
     CK(cudaEventRecord(d->plan_ev, d->side));
-    k_cseg_scatter<V, MODE><<<nb, thr, 0, st>>>(db, p.n, p.ctg, p.qs, p.qe, d->cnt2, d->cseg_off, d->cseg_mid,
-                                                 d->plan_tot, seg_cap, item_cap, d->csegs);
     CountArgs a{};
     a.db = db, a.items = d->items, a.segs = d->csegs, a.tot = d->plan_tot;
     a.seg_cap = seg_cap, a.item_cap = item_cap, a.v = p.v, a.hits = p.hits;
+    if (stages) CK(cudaEventRecord(d->stage_ev[3], st));
     if (MODE != M_ABN32) CK(cudaEventRecord(d->kev[0], st));
     if (PK) {
-        if (smem) k_count_packed<V, true><<<grid, threads, shm, st>>>(a);
-        else k_count_packed<V, false><<<grid, threads, shm, st>>>(a);
+        if (smem) CK(launch_pdl(k_count_packed<V, true>, grid, threads, shm, st, a));
+        else CK(launch_pdl(k_count_packed<V, false>, grid, threads, shm, st, a));
     } else {
         if (smem) k_count_items<V, true><<<grid, threads, shm, st>>>(a);
         else k_count_items<V, false><<<grid, threads, shm, st>>>(a);
@@ -1775,6 +1810,10 @@ int enqueue_count(igdb_dev *d, const igdb_dev::Pending &p)
     if (MODE != M_ABN32) {
         CK(cudaEventRecord(d->kev[1], st));
         d->kev_valid = true;
+    }
+    if (stages) {
+        CK(cudaEventRecord(d->stage_ev[4], st));
+        d->stage_valid = true;
     }
     d->launches += 4;
     CK(cudaGetLastError());
@@ -1880,6 +1919,8 @@ void igdb_dev_destroy(igdb_dev *d)
         if (e) cudaEventDestroy(e);
     for (auto &e : d->kev)
         if (e) cudaEventDestroy(e);
+    for (auto &e : d->stage_ev)
+        if (e) cudaEventDestroy(e);
     if (d->stream) cudaStreamDestroy(d->stream);
     delete d;
 }
@@ -1893,6 +1934,7 @@ static int create_impl(igdb_dev *d, const int32_t *ntile, const int32_t *ncnt)
     CK(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
     for (auto &e : d->ev) CK(cudaEventCreate(&e));
     for (auto &e : d->kev) CK(cudaEventCreate(&e));
+    for (auto &e : d->stage_ev) CK(cudaEventCreate(&e));
     CK(cudaMallocHost((void **)&d->h_scalar, 64));
     d->h_plan = reinterpret_cast<volatile unsigned long long *>(d->h_scalar + 8);
     CK(cudaEventCreateWithFlags(&d->plan_ev, cudaEventDisableTiming));
@@ -2050,6 +2092,15 @@ float igdb_dev_last_search_ms(igdb_dev *d)
     if (cudaEventSynchronize(d->kev[1]) != cudaSuccess) return ms;
     if (cudaEventElapsedTime(&ms, d->kev[0], d->kev[1]) != cudaSuccess) return -1.f;
     return ms;
+}
+
+void igdb_dev_stage_timing(igdb_dev *d, int on) { d->stage_timing = on != 0, d->stage_valid = false; }
+int igdb_dev_last_stages(igdb_dev *d, float out[4])
+{
+    if (!d->stage_valid || cudaEventSynchronize(d->stage_ev[4]) != cudaSuccess) return -1;
+    for (int k = 0; k < 4; ++k)
+        if (cudaEventElapsedTime(&out[k], d->stage_ev[k], d->stage_ev[k + 1]) != cudaSuccess) return -1;
+    return 0;
 }
 
 int64_t igdb_dev_bytes(const igdb_dev *d) { return d->bytes; }

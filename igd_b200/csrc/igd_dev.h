@@ -32,6 +32,9 @@ void igdb_dev_last_plan(const igdb_dev *d, int64_t out[4]);
 int igdb_dev_packed(const igdb_dev *d);
 /* device time of the last count-mode search kernel (CUDA events on its stream); < 0 if none */
 float igdb_dev_last_search_ms(igdb_dev *d);
+/* diagnostics: CUDA events around the four launches of a count batch (segment count, plan, scatter, search) */
+void igdb_dev_stage_timing(igdb_dev *d, int on);
+int igdb_dev_last_stages(igdb_dev *d, float out[4]);
 void *igdb_dev_pinned(igdb_dev *d, size_t bytes);   /* reusable pinned staging buffer (upload) */
 void *igdb_host_alloc(size_t bytes);                /* zeroed page-locked host memory (small result buffers) */
 void igdb_host_free(void *p);

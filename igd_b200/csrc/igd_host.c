@@ -173,6 +173,8 @@ int64_t igd_b200_device_bytes(const igd_b200_t *h) { return igdb_dev_bytes(h->de
 int64_t igd_b200_launch_count(const igd_b200_t *h) { return igdb_dev_launches(h->dev); }
 void igd_b200_last_plan(const igd_b200_t *h, int64_t out[4]) { igdb_dev_last_plan(h->dev, out); }
 float igd_b200_last_search_kernel_ms(igd_b200_t *h) { return igdb_dev_last_search_ms(h->dev); }
+void igd_b200_stage_timing(igd_b200_t *h, int on) { igdb_dev_stage_timing(h->dev, on); }
+int igd_b200_last_stage_ms(igd_b200_t *h, float t[4]) { return igdb_dev_last_stages(h->dev, t); }
 void igd_b200_last_timing(const igd_b200_t *h, float t[3]) { t[0] = h->t_ms[0], t[1] = h->t_ms[1], t[2] = h->t_ms[2]; }
 
 /* get_id (src/igd_base.c:325-331): exact string match on the contig name */

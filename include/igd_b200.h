@@ -135,6 +135,10 @@ void igd_b200_last_timing(const igd_b200_t *h, float t[3]);
 /* device time (ms, CUDA events on the launching stream) of the search kernel of the last count call;
  * blocks until that kernel has finished; < 0 if there was none */
 float igd_b200_last_search_kernel_ms(igd_b200_t *h);
+/* diagnostics: with stage timing on, every count batch records CUDA events around its four launches;
+ * t[0..3] = segment count, plan, segment scatter, search kernel of the last batch, ms (< 0 return: none) */
+void igd_b200_stage_timing(igd_b200_t *h, int on);
+int igd_b200_last_stage_ms(igd_b200_t *h, float t[4]);
 /* plan of the last settled count batch: out[0] (query, tile) segments, out[1] work items, out[2] records the
  * items read (each touched tile once per 64 of its segments), out[3] the bytes the search kernel had to read
  * for them: 16*items + 6*records (10 with -v) + 4*segments on the packed 16-bit layout,

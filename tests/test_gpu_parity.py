@@ -243,3 +243,27 @@ def test_count_many_tiles(workdir, O, api):
         got, _ = g.count(q.ctg, q.start, q.end, v)
         assert want.sum() > 0 and np.array_equal(got, want)
     g.close()
+
+
+@pytest.mark.parametrize("n_files", [50_000, 70_000])
+def test_count_many_files(workdir, O, api, n_files):
+    """More files than a per-CTA shared-memory histogram holds: 50 000 runs the packed kernel with global
+    atomics, 70 000 (> 65 536: file indices no longer fit 16 bits) the int32 kernel with global atomics."""
+    stem = os.path.join(workdir, f"manyfiles{n_files}")
+    rng = np.random.default_rng(n_files)
+    files = []
+    for i in range(n_files):
+        n = 12
+        ctg = rng.integers(0, 3, n).astype(np.int32)
+        start = (rng.random(n) * (SMALL_SIZES[ctg] - 5000)).astype(np.int32)
+        files.append(synth.Intervals(ctg, start, (start + rng.integers(1, 4000, n)).astype(np.int32),
+                                     rng.integers(0, 1000, n).astype(np.int32)))
+    synth.write_igd_direct(stem, files, names=SMALL_NAMES)
+    q = make_queries(9, 3000, ("lognormal", 7.0, 1.2))
+    odb, g = O.OracleDB(stem + ".igd"), api.IGD(stem + ".igd")
+    assert g.nfiles == n_files
+    for v in (0, 600):
+        want, _ = odb.count(q.ctg, q.start, q.end, v)
+        got, _ = g.count(q.ctg, q.start, q.end, v)
+        assert want.sum() > 0 and np.array_equal(got, want)
+    g.close()
