@@ -1,4 +1,4 @@
-/* Thin C-ABI between the host C code (igd_host.c) and the CUDA layer (igd_dev.cu).
+/* Thin C-ABI between the host C code (igd_host.c) and the CUDA layer (igd_dev_*.cu; shared definitions in igd_dev_impl.cuh).
  * Internal to libigd_b200.so; the public boundary is include/igd_b200.h. */
 #ifndef IGD_DEV_H
 #define IGD_DEV_H

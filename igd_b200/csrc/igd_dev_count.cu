@@ -1,0 +1,1107 @@
+// igd_b200 CUDA layer -- count mode (-q, -v): segments, plan, the search kernels, the host pipeline.  The hot path.
+#include "igd_dev_impl.cuh"
+
+namespace {
+
+template <int MODE>
+__device__ __forceinline__ bool mode_takes(int qs, int qe)
+{
+    const bool normal = qs >= 0 && qs < qe;
+    return MODE == M_ALL32 ? true : (MODE == M_PACKED ? normal : !normal);
+}
+
+// Count pass and scatter pass share one walker that keeps CSEG_Q queries per thread in flight: their loads of the
+// query, of the first-bin tile and their atomics are issued back to back (four independent dependency chains per
+// thread instead of one), the later bins -- which few queries have -- follow in a per-query loop.  Restates the
+// control flow of get_overlaps / get_overlaps_v exactly as for_each_segment does (see there).
+constexpr int CSEG_Q = 4, CSEG_T = 256;
+constexpr int CSEG_MAXCTG = 1024;           // contig table kept in shared memory up to this many contigs
+
+template <bool V, int MODE, class F1, class FL>
+__device__ __forceinline__ void cseg_walk(const DbView &db, int64_t n, const int32_t *__restrict__ ctg,
+                                          const int32_t *__restrict__ qs, const int32_t *__restrict__ qe,
+                                          uint32_t *__restrict__ abn, int abn_sign, F1 first, FL later)
+{
+    __shared__ int32_t tb_s[CSEG_MAXCTG + 1];
+    const bool in_smem = db.nctg <= CSEG_MAXCTG;
+    pdl_launch_dependents();
+    if (in_smem) {
+        for (int i = threadIdx.x; i <= db.nctg; i += blockDim.x) tb_s[i] = __ldg(&db.tbase[i]);
+        __syncthreads();
+    }
+    const int nbp = db.nbp;
+    const int64_t q0 = (int64_t)blockIdx.x * (CSEG_T * CSEG_Q) + threadIdx.x;
+    pdl_wait();                                             // the queries / counters of the previous launch
+    int c[CSEG_Q], s[CSEG_Q], e[CSEG_Q], tile[CSEG_Q], nlast[CSEG_Q], bd[CSEG_Q];
+    bool ok[CSEG_Q];
+    int nabn = 0;
+#pragma unroll
+    for (int k = 0; k < CSEG_Q; ++k) {
+        const int64_t q = q0 + (int64_t)k * CSEG_T;
+        ok[k] = q < n;
+        c[k] = ok[k] ? ctg[q] : -1, s[k] = ok[k] ? qs[q] : 0, e[k] = ok[k] ? qe[q] : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < CSEG_Q; ++k) {
+        if (ok[k] && !mode_takes<MODE>(s[k], e[k])) ok[k] = false, nabn += MODE == M_PACKED;
+        ok[k] = ok[k] && c[k] >= 0 && c[k] < db.nctg;                       // unknown chrom (:456-458)
+        tile[k] = nlast[k] = bd[k] = 0;
+        if (ok[k]) {
+            const int n1 = s[k] / nbp, n2 = (e[k] - 1) / nbp;               // C truncating division (:459)
+            const int tb = in_smem ? tb_s[c[k]] : __ldg(&db.tbase[c[k]]);
+            const int mT = (in_smem ? tb_s[c[k] + 1] : __ldg(&db.tbase[c[k] + 1])) - tb - 1;
+            ok[k] = n1 >= 0 && n1 <= mT;                                    // :462
+            tile[k] = tb + n1, nlast[k] = tb + max(n1, min(n2, mT)), bd[k] = n1 * nbp;
+        }
+    }
+    int4 m[CSEG_Q];
+#pragma unroll
+    for (int k = 0; k < CSEG_Q; ++k)
+        m[k] = ok[k] ? __ldg(reinterpret_cast<const int4 *>(&db.tiles[tile[k]])) : make_int4(0, 0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < CSEG_Q; ++k) {
+        if (!V && m[k].y == 0) ok[k] = false;                               // first-bin-empty quirk (:468)
+        if (ok[k] && m[k].y > 0 && e[k] > m[k].w) first(tile[k], s[k], e[k], bd[k]);   // nCnt > 0 and qe > start[0]
+    }
+    if (MODE == M_PACKED && nabn) atomicAdd(abn, (uint32_t)(abn_sign * nabn));   // left to the M_ABN32 pipeline
+#pragma unroll
+    for (int k = 0; k < CSEG_Q; ++k) {
+        if (!ok[k]) continue;
+        for (int t = tile[k] + 1; t <= nlast[k]; ++t) {                     // later bins (:500-531)
+            const int4 mm = __ldg(reinterpret_cast<const int4 *>(&db.tiles[t]));
+            if (mm.y > 0 && e[k] > mm.w) later(t, s[k], e[k], bd[k] + (t - tile[k]) * nbp);
+        }
+    }
+}
+
+template <bool V, int MODE>
+__global__ void __launch_bounds__(CSEG_T) k_cseg_count(DbView db, int64_t n, const int32_t *__restrict__ ctg,
+                                                        const int32_t *__restrict__ qs, const int32_t *__restrict__ qe,
+                                                        uint32_t *__restrict__ cnt2)
+{
+    cseg_walk<V, MODE>(
+        db, n, ctg, qs, qe, &cnt2[2 * db.ntiles], +1, [&](int tile, int, int, int) { atomicAdd(&cnt2[2 * tile], 1u); },
+        [&](int tile, int, int, int) { atomicAdd(&cnt2[2 * tile + 1], 1u); });
+}
+
+__device__ __forceinline__ Plan plan_of_tile(const DbView &db, const uint32_t *__restrict__ cnt2, int32_t t)
+{
+    const uint2 c = __ldg(reinterpret_cast<const uint2 *>(cnt2) + t);
+    const unsigned long long s = (unsigned long long)c.x + c.y;
+    if (s == 0) return Plan{0, 0};
+    const unsigned long long g = ((unsigned long long)(uint32_t)db.tiles[t].n + GROUP - 1) / GROUP;
+    // a tile's segments start at an even index: 8-byte segments, 16-byte aligned bulk copies
+    return Plan{(s + 1) & ~1ull, g * ((s + SMAX - 1) / SMAX)};
+}
+
+// The whole plan in ONE launch: a chained scan over the tiles fused with the item fill.  The grid has at most four
+// 512-thread CTAs per SM (all co-resident), CTA b owns a contiguous range of tiles:
+//   1. block-reduce the plan of its range and publish it (agg[b], then flag[b] = epoch);
+//   2. wait for every CTA's aggregate: the sum of the earlier ones is this CTA's prefix, the sum of all is the
+//      batch total -- if that does not fit the scratch buffers nothing more is written (the host grows them
+//      and runs the batch again);
+//   3. walk the range again in chunks of SCAN_T tiles: block scan + running carry give each tile its first
+//      segment (seg_off), its first later-bin segment (seg_mid) and its first work item, and the tile's items are
+//      written on the spot.
+// Work items of tile t, group-major.  An item is self-contained, so the search kernel goes from the item to
+// its records and segments without touching the tile table:
+//   x = position of the group's first record in the SoA arrays, in units of 8 records
+//   y = first segment
+//   z = records in the group (bits 0-8, 1..GROUP) | first record of the group that starts inside this bin
+//       (bits 9-17, 0..GROUP: the dedupe rule of later bins) | number of first-bin segments (bits 18-24, 0..64;
+//       the later-bin segments follow them) | number of segments (bits 25-31, 1..64)
+//   w = 0
+
+__global__ void __launch_bounds__(SCAN_T) k_plan(DbView db, const uint32_t *__restrict__ cnt2, uint32_t epoch,
+                                                  volatile PlanAgg *agg, volatile uint32_t *flag,
+                                                  uint32_t *__restrict__ seg_off, uint32_t *__restrict__ seg_mid,
+                                                  unsigned long long *__restrict__ tot, unsigned long long seg_cap,
+                                                  unsigned long long item_cap, int4 *__restrict__ items)
+{
+    __shared__ unsigned long long red[3][SCAN_T / 32], red5[5][SCAN_T / 32];
+    __shared__ unsigned long long sh_prefix[2], sh_total[3];
+    const int32_t T = db.ntiles;
+    const int G = gridDim.x, b = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int32_t per = (T + G - 1) / G, t0 = min(b * per, T), t1 = min(t0 + per, T);
+    pdl_launch_dependents();
+    pdl_wait();                                             // the segment counters
+
+    // 1. aggregate of this CTA's range
+    unsigned long long segs = 0, its = 0, recs = 0;
+    for (int32_t t = t0 + threadIdx.x; t < t1; t += SCAN_T) {
+        const Plan p = plan_of_tile(db, cnt2, t);
+        segs += p.segs, its += p.items;
+        if (p.items) {
+            const uint2 c = __ldg(reinterpret_cast<const uint2 *>(cnt2) + t);
+            recs += (unsigned long long)(uint32_t)db.tiles[t].n * ((c.x + c.y + SMAX - 1) / SMAX);
+        }
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        segs += __shfl_xor_sync(FULL, segs, d), its += __shfl_xor_sync(FULL, its, d);
+        recs += __shfl_xor_sync(FULL, recs, d);
+    }
+    if (lane == 0) red[0][wid] = segs, red[1][wid] = its, red[2][wid] = recs;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long x = 0, y = 0, z = 0;
+        for (int w = 0; w < SCAN_T / 32; ++w) x += red[0][w], y += red[1][w], z += red[2][w];
+        agg[b].segs = x, agg[b].items = y, agg[b].recs = z;
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&flag[b]), "r"(epoch) : "memory");
+    }
+    // 2. everybody's aggregates (every thread waits for its share of the CTAs)
+    {
+        unsigned long long v5[5] = {0, 0, 0, 0, 0};         // prefix segs / items, total segs / items / records
+        for (int i = threadIdx.x; i < G; i += SCAN_T) {
+            for (;;) {                                      // acquire: the aggregate is visible once the flag is
+                uint32_t f;
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(&flag[i]) : "memory");
+                if (f == epoch) break;
+                __nanosleep(20);
+            }
+            const unsigned long long x = agg[i].segs, y = agg[i].items, z = agg[i].recs;
+            v5[2] += x, v5[3] += y, v5[4] += z;
+            if (i < b) v5[0] += x, v5[1] += y;
+        }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+#pragma unroll
+            for (int d = 16; d; d >>= 1) v5[k] += __shfl_xor_sync(FULL, v5[k], d);
+        }
+        __syncthreads();                                    // red[] was read by thread 0 above
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 5; ++k) red5[k][wid] = v5[k];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long t5[5] = {0, 0, 0, 0, 0};
+            for (int w = 0; w < SCAN_T / 32; ++w)
+                for (int k = 0; k < 5; ++k) t5[k] += red5[k][w];
+            sh_prefix[0] = t5[0], sh_prefix[1] = t5[1], sh_total[0] = t5[2], sh_total[1] = t5[3], sh_total[2] = t5[4];
+            if (b == G - 1) {
+                tot[0] = t5[2], tot[1] = t5[3], tot[2] = t5[4];
+                tot[3] = cnt2[2 * T];                      // queries left to the M_ABN32 pipeline (M_PACKED only)
+            }
+        }
+    }
+    __syncthreads();
+    const unsigned long long nseg = sh_total[0], nit = sh_total[1];
+    if (nseg > seg_cap || nit > item_cap) return;
+    if (b == G - 1 && threadIdx.x < 32) {                   // empty items up to a multiple of 32
+        const unsigned long long k = nit + threadIdx.x;
+        if (k < ((nit + 31) & ~31ull)) items[k] = make_int4(0, 0, 0, 0);
+        if (threadIdx.x == 0) seg_off[T] = (uint32_t)nseg;
+    }
+    // 3. per-tile offsets and items
+    Plan carry{sh_prefix[0], sh_prefix[1]};
+    for (int32_t c0 = t0; c0 < t1; c0 += SCAN_T) {
+        const int32_t t = c0 + threadIdx.x;
+        const bool in = t < t1;
+        const Plan mine = in ? plan_of_tile(db, cnt2, t) : Plan{0, 0};
+        Plan ctot;
+        const Plan ex = carry + block_exclusive<Plan>(mine, &ctot);
+        carry += ctot;
+        uint32_t i0 = (uint32_t)ex.items, ni = (uint32_t)mine.items, sa0 = (uint32_t)ex.segs, mid = 0, sb0 = 0;
+        int4 tm = make_int4(0, 0, 0, 0);
+        if (in) {
+            const uint2 c = __ldg(reinterpret_cast<const uint2 *>(cnt2) + t);
+            mid = sa0 + c.x, sb0 = mid + c.y;
+            seg_off[t] = sa0, seg_mid[t] = mid;
+            if (ni) tm = __ldg(reinterpret_cast<const int4 *>(&db.tiles[t]));
+        }
+        auto write = [&](uint32_t k, uint32_t i0_, uint32_t a, uint32_t m, uint32_t e, int4 tm_) {
+            const uint32_t ch = (e - a + SMAX - 1) / SMAX;
+            const uint32_t g = k / ch, c = k - g * ch;
+            const uint32_t sa = a + c * SMAX, sb = min(sa + (uint32_t)SMAX, e);
+            const int r0 = (int)(g * GROUP);
+            const uint32_t nv = (uint32_t)min(tm_.y - r0, GROUP);
+            const uint32_t tsr = (uint32_t)min(max(tm_.z - r0, 0), GROUP);
+            const uint32_t nfirst = min(max(m, sa), sb) - sa;
+            items[i0_ + k] = make_int4((int)((uint32_t)tm_.x + g * (GROUP / 8)), (int)sa,
+                                       (int)(nv | tsr << 9 | nfirst << 18 | (sb - sa) << 25), 0);
+        };
+        // a thread writes up to 32 items of its tile itself; tiles with more are then done by the whole warp
+        if (ni <= 32)
+            for (uint32_t k = 0; k < ni; ++k) write(k, i0, sa0, mid, sb0, tm);
+        unsigned heavy = __ballot_sync(FULL, ni > 32);
+        while (heavy) {
+            const int src = __ffs(heavy) - 1;
+            heavy &= heavy - 1;
+            const uint32_t i0_ = __shfl_sync(FULL, i0, src), ni_ = __shfl_sync(FULL, ni, src);
+            const uint32_t a_ = __shfl_sync(FULL, sa0, src), m_ = __shfl_sync(FULL, mid, src), e_ = __shfl_sync(FULL, sb0, src);
+            const int4 tm_ = make_int4(__shfl_sync(FULL, tm.x, src), __shfl_sync(FULL, tm.y, src),
+                                       __shfl_sync(FULL, tm.z, src), 0);
+            for (uint32_t k = lane; k < ni_; k += 32) write(k, i0_, a_, m_, e_, tm_);
+        }
+    }
+}
+
+// cnt2 is counted back down to zero here, so it is clean for the next batch.  Nothing is written when the
+// plan does not fit the scratch buffers: the host then grows them and runs the batch again.
+// M_PACKED writes 4-byte segments in the tile's packed coordinates, pre-biased like the records:
+//   bits 0-15 = qs' + 1, bits 16-31 = qe' + 0x8000.
+template <bool V, int MODE>
+__global__ void __launch_bounds__(CSEG_T) k_cseg_scatter(DbView db, int64_t n, const int32_t *__restrict__ ctg,
+                                                          const int32_t *__restrict__ qs, const int32_t *__restrict__ qe,
+                                                          uint32_t *__restrict__ cnt2, const uint32_t *__restrict__ seg_off,
+                                                          const uint32_t *__restrict__ seg_mid,
+                                                          const unsigned long long *__restrict__ tot,
+                                                          unsigned long long seg_cap, unsigned long long item_cap,
+                                                          void *__restrict__ segs)
+{
+    pdl_wait();                                             // the plan
+    if (tot[0] > seg_cap || tot[1] > item_cap) return;
+    const int nbp = db.nbp;
+    auto put = [&](uint32_t pos, int s, int e, int bd) {
+        if (MODE == M_PACKED)
+            static_cast<uint32_t *>(segs)[pos] =
+                (uint32_t)(pk_rel(s, bd, nbp) + 1) | (uint32_t)(pk_rel_end(e, bd, nbp) + 0x8000) << 16;
+        else
+            static_cast<CSeg *>(segs)[pos] = CSeg{s, e};
+    };
+    // (the queries left to the M_ABN32 pipeline are counted back down too)
+    cseg_walk<V, MODE>(
+        db, n, ctg, qs, qe, &cnt2[2 * db.ntiles], -1,
+        [&](int tile, int s, int e, int bd) {
+            put(__ldg(&seg_off[tile]) + atomicSub(&cnt2[2 * tile], 1u) - 1u, s, e, bd);
+        },
+        [&](int tile, int s, int e, int bd) {
+            put(__ldg(&seg_mid[tile]) + atomicSub(&cnt2[2 * tile + 1], 1u) - 1u, s, e, bd);
+        });
+}
+
+// ------------------------------------------------------------------------------------------------
+// count mode, the search kernel (see the file header).  Restates the per-record predicate of get_overlaps
+// (src/igd_search.c:489-493, 522-526: start < qe from the binary search, end > qs from the scan, and in later
+// bins i >= tS, i.e. start >= bin boundary) and get_overlaps_v (:650-653, 680-683: ... && value >= v); which
+// tiles a query reaches at all was decided when its segments were made (for_each_segment).
+// ------------------------------------------------------------------------------------------------
+struct CountArgs {
+    DbView db;
+    const int4 *items;
+    const CSeg *segs;
+    const unsigned long long *tot;      // device: {segments, items} of this batch
+    unsigned long long seg_cap, item_cap;
+    int32_t v;
+    unsigned long long *hits;
+};
+
+constexpr int COUNT_MAXW = 24;          // most warps per CTA of k_count_items (register budget: 65536 / 768 = 85)
+constexpr int COUNT_K = 3;              // pipeline stages per warp
+
+// ---- asynchronous copies (cp.async -> LDGSTS), shared::cta addresses as 32-bit ------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ int4 lds128(uint32_t addr)
+{
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int2 lds64(uint32_t addr)
+{
+    int2 v;
+    asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+
+// c += (s < qe && e > qs)
+__device__ __forceinline__ void count_if(int &c, int s, int e, int qs, int qe)
+{
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %1, %4;\n\tsetp.gt.and.s32 p, %2, %3, p;\n\t@p add.s32 %0, %0, 1;\n\t}"
+        : "+r"(c)
+        : "r"(s), "r"(e), "r"(qs), "r"(qe));
+}
+
+// the segments selected by mask m (lanes of q) against this lane's 4 records
+__device__ __forceinline__ void count_segments(unsigned m, const int2 &q, const int (&s)[4], const int (&e)[4],
+                                               int (&c)[4])
+{
+    while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const int qs = __shfl_sync(FULL, q.x, src), qe = __shfl_sync(FULL, q.y, src);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) count_if(c[k], s[k], e[k], qs, qe);
+    }
+}
+
+// Shared memory of a CTA: [histogram, nfiles x u32, rounded to 128 B] then per warp K stages of
+//   { start[GROUP] | end[GROUP] | idx[GROUP] | (value[GROUP]) | 64 segments x 8 B }  -- the records and segments of
+// one item.  Inside an array, sub-group h (records 128 h .. 128 h + 127) is the 512-byte run at 512 h.
+template <bool V>
+struct CountSmem {
+    static constexpr uint32_t ARR = GROUP * 4;                          // one SoA array of a stage
+    static constexpr uint32_t QOFF = (V ? 4 : 3) * ARR;
+    static constexpr uint32_t STAGE = QOFF + SMAX * 8;
+    static constexpr uint32_t WARP = COUNT_K * STAGE;
+    static size_t hist_bytes(int nfiles) { return ((size_t)nfiles * 4 + 127) / 128 * 128; }
+    // warps of the (single) CTA of an SM: as many pipelines as fit beside the histogram
+    static int warps(int nfiles, bool smem_hist)
+    {
+        const size_t total = 226 * 1024, hist = smem_hist ? hist_bytes(nfiles) : 0;
+        if (hist >= total) return 0;                        // the histogram alone does not fit
+        return (int)std::min<size_t>((total - hist) / WARP, COUNT_MAXW);
+    }
+    static size_t cta_bytes(int nfiles, bool smem_hist, int nwarps)
+    {
+        return (smem_hist ? hist_bytes(nfiles) : 0) + (size_t)nwarps * WARP;
+    }
+};
+
+// The count-mode search kernel: ONE CTA per SM, as many warps as shared memory has room for pipelines.  Each
+// warp owns blocks of 32 consecutive items (block b of warp w is items [32 (b NW + w), +32); lane j keeps
+// descriptor j of the current and of the next block in registers) and runs a private K-stage asynchronous-copy
+// ring over them: K - 1 items ahead of the one being evaluated, every lane cp.async's ITS OWN records of each
+// SoA array (16 B = 4 records per sub-group) and its own one or two segments into its own slots of the stage,
+// so no lane ever reads another lane's bytes and the ring needs no barrier at all -- a lane's
+// cp.async.wait_group covers exactly the bytes it is about to read.
+template <bool V, bool SMEM>
+__global__ void __launch_bounds__(COUNT_MAXW * 32, 1) k_count_items(const CountArgs a)
+{
+    using L = CountSmem<V>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const DbView &db = a.db;
+    uint32_t *hist = reinterpret_cast<uint32_t *>(smem);
+    const uint32_t hist_bytes = SMEM ? ((uint32_t)db.nfiles * 4 + 127) / 128 * 128 : 0;
+    if (SMEM) {
+        for (int f = threadIdx.x; f < db.nfiles; f += blockDim.x) hist[f] = 0;
+        __syncthreads();
+    }
+    const uint32_t hist_s = smem_u32(smem);
+    const int lane = threadIdx.x & 31, W = blockDim.x >> 5, wib = threadIdx.x >> 5;
+    const uint32_t wbase = hist_s + hist_bytes + (uint32_t)wib * L::WARP;
+    const unsigned long long nseg = __ldg(&a.tot[0]), nit = __ldg(&a.tot[1]);
+    const uint32_t n_items = (nseg > a.seg_cap || nit > a.item_cap) ? 0u : (uint32_t)nit;
+    const uint32_t nblk = (n_items + 31) >> 5, NW = gridDim.x * W, w = blockIdx.x * W + wib;
+    const uint32_t nb = w < nblk ? (nblk - w + NW - 1) / NW : 0;       // blocks of this warp
+    const uint32_t N = nb * 32;                                         // item slots of this warp
+
+    const int4 zero = make_int4(0, 0, 0, 0);
+    // descriptor j of block 0 / block 1 of this warp (the item array is padded to a multiple of 32)
+    int4 dcur = nb > 0 ? __ldg(&a.items[(size_t)w * 32 + lane]) : zero;
+    int4 dnxt = nb > 1 ? __ldg(&a.items[(size_t)(NW + w) * 32 + lane]) : zero;
+    // this lane's column of the SoA arrays and of the segment array
+    const int32_t *const pS = db.start + lane * 4, *const pE = db.end + lane * 4, *const pI = db.idx + lane * 4;
+    const int32_t *const pV = db.value + lane * 4;
+    const CSeg *const pQ = a.segs + lane;
+    const uint32_t lslot = wbase + lane * 16, qslot = wbase + L::QOFF + lane * 8;
+
+    // issue the copies of item slot n (descriptor in lane n % 32 of dd) into stage n % K
+    auto issue = [&](uint32_t n, const int4 &dd) {
+        const int j = n & 31;
+        const uint32_t x = __shfl_sync(FULL, dd.x, j), y = __shfl_sync(FULL, dd.y, j);
+        const uint32_t z = __shfl_sync(FULL, dd.z, j);
+        const int nv = z & 0x1ff, ns = z >> 25;
+        const uint32_t so = (n % COUNT_K) * L::STAGE;
+        const size_t p = (size_t)x * 8;
+#pragma unroll
+        for (int h = 0; h < SUB; ++h)
+            if (h * 128 + lane * 4 < nv) {
+                cp_async16(lslot + so + h * 512, pS + p + h * 128);
+                cp_async16(lslot + so + L::ARR + h * 512, pE + p + h * 128);
+                cp_async16(lslot + so + 2 * L::ARR + h * 512, pI + p + h * 128);
+                if (V) cp_async16(lslot + so + 3 * L::ARR + h * 512, pV + p + h * 128);
+            }
+        if (lane < ns) cp_async8(qslot + so, pQ + y);
+        if (lane + 32 < ns) cp_async8(qslot + so + 256, pQ + y + 32);
+    };
+
+#pragma unroll
+    for (int n = 0; n < COUNT_K - 1; ++n) {                             // prologue: slots 0 .. K-2 (block 0)
+        if ((uint32_t)n < N) issue(n, dcur);
+        cp_async_commit();
+    }
+
+    for (uint32_t n = 0; n < N; ++n) {
+        const int j = n & 31;
+        // slot n + K - 1 goes into the stage that slot n - 1 has released
+        {
+            const uint32_t m = n + COUNT_K - 1;
+            if (m < N) {
+                if ((m >> 5) == (n >> 5)) issue(m, dcur);
+                else issue(m, dnxt);
+            }
+            cp_async_commit();
+        }
+        cp_async_wait<COUNT_K - 1>();                                   // slot n has landed (this lane's bytes)
+        const uint32_t dz = __shfl_sync(FULL, dcur.z, j);
+        const uint32_t so = (n % COUNT_K) * L::STAGE;
+        const int nv = dz & 0x1ff, tsr = (dz >> 9) & 0x1ff, nf = (dz >> 18) & 0x7f, ns = dz >> 25;
+        int2 q0 = make_int2(IMAX, IMIN), q1 = make_int2(IMAX, IMIN);    // segments lane and 32 + lane of the item
+        if (lane < ns) q0 = lds64(qslot + so);
+        if (lane + 32 < ns) q1 = lds64(qslot + so + 256);
+#pragma unroll
+        for (int h = 0; h < SUB; ++h) {
+            if (h * 128 >= nv) break;
+            // this lane's 4 records of the sub-group; a slot past the group's end gets (IMAX, IMIN) and can
+            // match no query, and so do the pad records inside the tile's last block of 4 (written as
+            // (IMAX, IMIN) at upload)
+            const int r0 = h * 128 + lane * 4;
+            const bool have = r0 < nv;
+            int4 S = lds128(lslot + so + h * 512), E = lds128(lslot + so + L::ARR + h * 512);
+            const int4 I = lds128(lslot + so + 2 * L::ARR + h * 512);
+            if (V) {
+                const int4 VV = lds128(lslot + so + 3 * L::ARR + h * 512);
+                if (VV.x < a.v) S.x = IMAX;                             // filtered out by -v: matches no query
+                if (VV.y < a.v) S.y = IMAX;
+                if (VV.z < a.v) S.z = IMAX;
+                if (VV.w < a.v) S.w = IMAX;
+            }
+            const int s[4] = {have ? S.x : IMAX, have ? S.y : IMAX, have ? S.z : IMAX, have ? S.w : IMAX};
+            const int e[4] = {have ? E.x : IMIN, have ? E.y : IMIN, have ? E.z : IMIN, have ? E.w : IMIN};
+            const int f[4] = {I.x, I.y, I.z, I.w};
+            int c[4] = {0, 0, 0, 0};
+            const int smin = min(min(s[0], s[1]), min(s[2], s[3]));
+            const int wsmin = V ? __reduce_min_sync(FULL, smin) : __shfl_sync(FULL, s[0], 0);     // sorted by start
+            const int emax = __reduce_max_sync(FULL, max(max(e[0], e[1]), max(e[2], e[3])));
+            // first-bin segments [0, nf): every record of the tile is a candidate
+            if (nf > 0) {
+                count_segments(__ballot_sync(FULL, lane < nf && q0.y > wsmin && q0.x < emax), q0, s, e, c);
+                if (nf > 32) count_segments(__ballot_sync(FULL, lane + 32 < nf && q1.y > wsmin && q1.x < emax), q1, s, e, c);
+            }
+            // later-bin segments [nf, ns): only records that start inside this bin (index >= tS,
+            // src/igd_search.c:510-511,522)
+            if (ns > nf) {
+                int sl[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) sl[k] = r0 + k >= tsr ? s[k] : IMAX;
+                const int wslmin = __reduce_min_sync(FULL, min(min(sl[0], sl[1]), min(sl[2], sl[3])));
+                if (wslmin != IMAX) {
+                    if (nf < 32)
+                        count_segments(__ballot_sync(FULL, lane >= nf && q0.y > wslmin && q0.x < emax), q0, sl, e, c);
+                    if (ns > 32)
+                        count_segments(__ballot_sync(FULL, lane + 32 >= nf && q1.y > wslmin && q1.x < emax), q1, sl, e, c);
+                }
+            }
+            // hits[idx] += count: one atomic per record that overlaps anything
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (SMEM) {
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %1, 0;\n\t@p red.shared.add.u32 [%0], %1;\n\t}"
+                                 :
+                                 : "r"(hist_s + 4u * (uint32_t)f[k]), "r"(c[k])
+                                 : "memory");
+                } else if (c[k]) {
+                    atomicAdd(&a.hits[f[k]], (unsigned long long)c[k]);
+                }
+            }
+        }
+        if (j == 31) {                                                  // next block of descriptors
+            dcur = dnxt;
+            const uint32_t b2 = (n >> 5) + 2;
+            dnxt = b2 < nb ? __ldg(&a.items[(size_t)(b2 * NW + w) * 32 + lane]) : zero;
+        }
+    }
+    cp_async_wait<0>();
+    if (SMEM) {
+        __syncthreads();
+        for (int f = threadIdx.x; f < db.nfiles; f += blockDim.x) {
+            const uint32_t c = hist[f];
+            if (c) atomicAdd(&a.hits[f], (unsigned long long)c);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// count mode on the packed layout (the default path): the same tile-centric, record-stationary scheme as
+// k_count_items, on 16-bit tile-relative coordinates -- half the bytes per record and two records per
+// 32-bit operation.
+//   records  S = start' + 1 (1 .. nbp + 1; 0x8000 = pad / filtered out by -v), E = end' + 0x8000
+//   segments QS = qs' + 1, QE = qe' + 0x8000, each replicated into both halves of a register
+//   A = QE2 - S2 : bit 15 of a half is set  <=>  qe' > start'   (the halves are 0x8000 + qe' - S >= 0: no borrow)
+//   B = E2 - QS2 : bit 15 of a half is set  <=>  end' > qs'     (0x8000 + end' - QS >= 0x8000 - nbp - 1 > 0)
+//   counts (two 16-bit counters per register, <= 64 per item) += (A & B & 0x80008000) >> 15
+// i.e. 2 subtractions, 1 LOP3 and 1 shift-add per PAIR of (record, query) tests; the int32 kernel spends 3
+// ALU-pipe instructions per test.  An item is 256 records (8 per lane: one 16-byte load per array) x <= 64
+// segments.  Later-bin segments see S replaced by 0x8000 for the records that start before the bin (the
+// reference's i >= tS, src/igd_search.c:510-511,522).
+// Scheduling: one CTA per SM; a warp owns every NW-th BLOCK of 8 consecutive items (static, fine-grained
+// interleave: the spread between warps is at most one block), four blocks' descriptors are fetched with one
+// coalesced load.  Per warp a private K-stage cp.async ring as in k_count_items.
+// ------------------------------------------------------------------------------------------------
+constexpr int PK_K = 4;                 // pipeline stages per warp
+constexpr int PK_MAXW = 24;             // most warps per CTA (register budget 65536 / 768 = 85)
+constexpr int PK_IB = 8;                // items per block
+
+template <bool V>
+struct PackedSmem {
+    static constexpr uint32_t ARR = GROUP * 2;                          // one 16-bit array of a stage
+    static constexpr uint32_t VOFF = 3 * ARR;                           // int32 value[GROUP] (-v only)
+    static constexpr uint32_t QOFF = VOFF + (V ? GROUP * 4 : 0);
+    static constexpr uint32_t STAGE = QOFF + SMAX * 4;
+    static constexpr uint32_t LIST = PK_K * STAGE;                      // survivor list: SMAX x {QS2, QE2}
+    static constexpr uint32_t WARP = LIST + SMAX * 8;
+    static size_t hist_bytes(int nfiles) { return ((size_t)nfiles * 4 + 127) / 128 * 128; }
+    static int warps(int nfiles, bool smem_hist)
+    {
+        const size_t total = 226 * 1024, hist = smem_hist ? hist_bytes(nfiles) : 0;
+        if (hist >= total) return 0;                        // the histogram alone does not fit
+        return (int)std::min<size_t>((total - hist) / WARP, PK_MAXW);
+    }
+    static size_t cta_bytes(int nfiles, bool smem_hist, int nwarps)
+    {
+        return (smem_hist ? hist_bytes(nfiles) : 0) + (size_t)nwarps * WARP;
+    }
+};
+
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t x, uint32_t y)
+{
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
+}
+// segments [i0, i1) of the warp's survivor list against this lane's 4 record pairs
+__device__ __forceinline__ void count_pairs(uint32_t list, int i0, int i1, const uint32_t (&S)[4],
+                                            const uint32_t (&E)[4], uint32_t (&c)[4])
+{
+    auto eval = [&](const int2 q) {
+        const uint32_t s2 = (uint32_t)q.x, e2 = (uint32_t)q.y;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t t;                                     // (A & B & 0x80008000): one 3-input LOP3
+            asm("lop3.b32 %0, %1, %2, 0x80008000, 0x80;" : "=r"(t) : "r"(e2 - S[k]), "r"(E[k] - s2));
+            c[k] += t >> 15;                                // LEA.HI
+        }
+    };
+    uint32_t p = list + 8u * (uint32_t)i0;
+    const uint32_t end = list + 8u * (uint32_t)i1;
+#pragma unroll 1
+    for (; p + 16 <= end; p += 16) {                        // same address in every lane: broadcast loads
+        const int2 q0 = lds64(p), q1 = lds64(p + 8);
+        eval(q0);
+        eval(q1);
+    }
+    if (p < end) eval(lds64(p));
+}
+
+template <bool V, bool SMEM>
+__global__ void __launch_bounds__(PK_MAXW * 32, 1) k_count_packed(const CountArgs a)
+{
+    using L = PackedSmem<V>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const DbView &db = a.db;
+    uint32_t *hist = reinterpret_cast<uint32_t *>(smem);
+    const uint32_t hist_bytes = SMEM ? ((uint32_t)db.nfiles * 4 + 127) / 128 * 128 : 0;
+    if (SMEM) {
+        for (int f = threadIdx.x; f < db.nfiles; f += blockDim.x) hist[f] = 0;
+        __syncthreads();
+    }
+    const uint32_t hist_s = smem_u32(smem);
+    const int lane = threadIdx.x & 31, W = blockDim.x >> 5, wib = threadIdx.x >> 5;
+    const uint32_t wbase = hist_s + hist_bytes + (uint32_t)wib * L::WARP;
+    pdl_wait();                                             // the plan, the items, the segments
+    const unsigned long long nseg = a.tot[0], nit = a.tot[1];
+    const uint32_t n_items = (nseg > a.seg_cap || nit > a.item_cap) ? 0u : (uint32_t)nit;
+    const uint32_t nblk = (n_items + PK_IB - 1) / PK_IB, NW = gridDim.x * W, w = blockIdx.x * W + wib;
+    const uint32_t nb = w < nblk ? (nblk - w + NW - 1) / NW : 0;       // blocks of this warp
+    const uint32_t N = nb * PK_IB;                                      // item slots of this warp
+
+    // descriptor registers: lane j of quad-block g holds item (j % 8) of this warp's block 4 g + j / 8
+    const int4 zero = make_int4(0, 0, 0, 0);
+    auto load_desc = [&](uint32_t g) {
+        const uint32_t b = 4 * g + (lane >> 3);
+        const size_t it = ((size_t)b * NW + w) * PK_IB + (lane & 7);
+        return (b < nb && it < n_items) ? __ldg(&a.items[it]) : zero;
+    };
+    int4 dcur = load_desc(0), dnxt = load_desc(1);
+    const uint16_t *const pS = db.ps + lane * 8, *const pE = db.pe + lane * 8, *const pF = db.pf + lane * 8;
+    const int32_t *const pV = db.value + lane * 8;
+    const uint32_t *const pQ = static_cast<const uint32_t *>(static_cast<const void *>(a.segs)) + lane;
+    const uint32_t lslot = wbase + lane * 16, vslot = wbase + L::VOFF + lane * 32, qslot = wbase + L::QOFF + lane * 4;
+
+    // The stages start out as pads: a lane without records in an item reads what an earlier item (or this fill)
+    // left in its slots -- its counts are discarded, and the prune window only gets wider.
+    for (uint32_t o = lane * 16; o < L::LIST; o += 512)
+        asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(wbase + o), "r"(0x80008000u) : "memory");
+    __syncwarp();
+
+    // issue the copies of item slot n (descriptor in lane n % 32 of dd) into stage n % K
+    auto issue = [&](uint32_t n, const int4 &dd) {
+        const int j = n & 31;
+        const uint32_t x = __shfl_sync(FULL, dd.x, j), y = __shfl_sync(FULL, dd.y, j), z = __shfl_sync(FULL, dd.z, j);
+        const int nv = z & 0x1ff, ns = z >> 25;
+        const uint32_t so = (n % PK_K) * L::STAGE;
+        const size_t p = (size_t)x * 8;
+        if (lane * 8 < nv) {
+            cp_async16(lslot + so, pS + p);
+            cp_async16(lslot + so + L::ARR, pE + p);
+            cp_async16(lslot + so + 2 * L::ARR, pF + p);
+            if (V) {
+                cp_async16(vslot + so, pV + p);
+                cp_async16(vslot + so + 16, pV + p + 4);
+            }
+        }
+        if (lane < ns) cp_async4(qslot + so, pQ + y);
+        if (lane + 32 < ns) cp_async4(qslot + so + 128, pQ + y + 32);
+    };
+
+#pragma unroll
+    for (int n = 0; n < PK_K - 1; ++n) {                                // prologue: slots 0 .. K-2 (quad-block 0)
+        if ((uint32_t)n < N) issue(n, dcur);
+        cp_async_commit();
+    }
+
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t list = wbase + L::LIST;
+    for (uint32_t n = 0; n < N; ++n) {
+        const int j = n & 31;
+        {
+            const uint32_t m = n + PK_K - 1;                            // goes into the stage slot n - 1 released
+            if (m < N) {
+                if ((m >> 5) == (n >> 5)) issue(m, dcur);
+                else issue(m, dnxt);
+            }
+            cp_async_commit();
+        }
+        cp_async_wait<PK_K - 1>();                                      // slot n has landed (this lane's bytes)
+        const uint32_t dz = __shfl_sync(FULL, dcur.z, j);
+        const uint32_t so = (n % PK_K) * L::STAGE;
+        const int nv = dz & 0x1ff, tsr = (dz >> 9) & 0x1ff, nf = (dz >> 18) & 0x7f, ns = dz >> 25;
+        if (nv > 0) {
+            const bool have = lane * 8 < nv;
+            const int4 s_ = lds128(lslot + so), e_ = lds128(lslot + so + L::ARR), f_ = lds128(lslot + so + 2 * L::ARR);
+            uint32_t S[4] = {(uint32_t)s_.x, (uint32_t)s_.y, (uint32_t)s_.z, (uint32_t)s_.w};
+            const uint32_t E[4] = {(uint32_t)e_.x, (uint32_t)e_.y, (uint32_t)e_.z, (uint32_t)e_.w};
+            const uint32_t F[4] = {(uint32_t)f_.x, (uint32_t)f_.y, (uint32_t)f_.z, (uint32_t)f_.w};
+            if (V && have) {                                            // value < v: the record matches no query
+                const int4 v0 = lds128(vslot + so), v1 = lds128(vslot + so + 16);
+                const int vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (vv[2 * k] < a.v) S[k] = (S[k] & 0xffff0000u) | 0x8000u;
+                    if (vv[2 * k + 1] < a.v) S[k] = (S[k] & 0x0000ffffu) | 0x80000000u;
+                }
+            }
+            uint32_t c[4] = {0, 0, 0, 0};
+            // prune window of the group: smallest S (records are sorted by start: the first one; with -v the
+            // smallest surviving one) and largest E
+            uint32_t smin;
+            if (V) {
+                const uint32_t m2 = __vminu2(__vminu2(S[0], S[1]), __vminu2(S[2], S[3]));
+                smin = __reduce_min_sync(FULL, have ? min(m2 & 0xffffu, m2 >> 16) : 0xffffu);
+            } else {
+                smin = __shfl_sync(FULL, S[0], 0) & 0xffffu;
+            }
+            const uint32_t x2 = __vmaxu2(__vmaxu2(E[0], E[1]), __vmaxu2(E[2], E[3]));
+            const uint32_t emax = __reduce_max_sync(FULL, max(x2 & 0xffffu, x2 >> 16));
+            // a segment can touch the group iff qe' > smallest start' and qs' < largest end':
+            //   QE - smin >= 0x8000  and  emax - QS >= 0x8000
+            const uint32_t qe_lo = smin + 0x8000u, qs_hi = emax - 0x8000u;     // QE >= qe_lo, QS <= qs_hi
+            // segments lane and 32 + lane of the item; an absent one has qe' = 0 and survives no prune
+            const uint32_t w0 = lane < ns ? lds32(qslot + so) : 0x80000000u;
+            const uint32_t qs2_0 = __byte_perm(w0, 0, 0x1010), qe2_0 = __byte_perm(w0, 0, 0x3232);
+            uint32_t w1 = 0x80000000u, qs2_1 = 0, qe2_1 = 0;
+            if (ns > 32) {
+                if (lane + 32 < ns) w1 = lds32(qslot + so + 128);
+                qs2_1 = __byte_perm(w1, 0, 0x1010), qe2_1 = __byte_perm(w1, 0, 0x3232);
+            }
+            // The surviving segments are compacted into the warp's list (first-bin ones, then later-bin ones)
+            // and streamed back with broadcast loads: 1 load + 16 ALU/FMA instructions per segment x 256 records.
+            __syncwarp();                                               // the previous item's list has been read
+            // first-bin segments [0, nf): every record of the tile is a candidate
+            int nF = 0;
+            if (nf > 0) {
+                const unsigned f0 = __ballot_sync(FULL, (w0 >> 16) >= qe_lo && (w0 & 0xffffu) <= qs_hi && lane < nf);
+                if (f0 >> lane & 1) sts64(list + 8u * __popc(f0 & lt), qs2_0, qe2_0);
+                nF = __popc(f0);
+                if (nf > 32) {
+                    const unsigned f1 = __ballot_sync(FULL, (w1 >> 16) >= qe_lo && (w1 & 0xffffu) <= qs_hi && lane + 32 < nf);
+                    if (f1 >> lane & 1) sts64(list + 8u * (nF + __popc(f1 & lt)), qs2_1, qe2_1);
+                    nF += __popc(f1);
+                }
+            }
+            // later-bin segments [nf, ns): only the records that start inside this bin count (index >= tS,
+            // src/igd_search.c:510-511,522), i.e. start' >= 1.  Such a segment has qs' = 0 (QS = 1), so its
+            // end test is vacuous; it is given X = S + 0x7fff in place of E, which turns that test into
+            // bit 15 of (S + 0x7fff - 1), set  <=>  S >= 2  <=>  start' >= 1.
+            int nL = 0;
+            if (ns > nf && tsr < nv) {
+                // prune with the first record that starts inside the bin (records are sorted by start)
+                uint32_t slmin = smin;
+                if (tsr > 0) {
+                    if (V) {
+                        slmin = max(smin, 2u);
+                    } else {
+                        const int nb4 = min(max(tsr - lane * 8, 0), 8);     // this lane's records before the bin
+                        const uint32_t wd = nb4 < 2 ? S[0] : (nb4 < 4 ? S[1] : (nb4 < 6 ? S[2] : S[3]));
+                        const uint32_t mine = (nb4 >= 8 || !have) ? 0xffffu : ((nb4 & 1) ? wd >> 16 : wd & 0xffffu);
+                        slmin = __reduce_min_sync(FULL, mine);
+                    }
+                }
+                const uint32_t qel = slmin + 0x8000u;
+                if (nf < 32) {
+                    const unsigned l0 = __ballot_sync(FULL, (w0 >> 16) >= qel && (w0 & 0xffffu) <= qs_hi && lane >= nf);
+                    if (l0 >> lane & 1) sts64(list + 8u * (nF + __popc(l0 & lt)), qs2_0, qe2_0);
+                    nL = __popc(l0);
+                }
+                if (ns > 32) {
+                    const unsigned l1 = __ballot_sync(FULL, (w1 >> 16) >= qel && (w1 & 0xffffu) <= qs_hi && lane + 32 >= nf);
+                    if (l1 >> lane & 1) sts64(list + 8u * (nF + nL + __popc(l1 & lt)), qs2_1, qe2_1);
+                    nL += __popc(l1);
+                }
+            }
+            __syncwarp();
+            count_pairs(list, 0, nF, S, E, c);
+            if (nL > 0) {
+                const uint32_t X[4] = {S[0] + 0x7fff7fffu, S[1] + 0x7fff7fffu, S[2] + 0x7fff7fffu, S[3] + 0x7fff7fffu};
+                count_pairs(list, nF, nF + nL, S, X, c);
+            }
+            // hits[file] += count.  One test per PAIR of records (neighbours in start order are mostly hit
+            // together or not at all), then one shared-memory atomic per record.
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (have && c[k]) {
+                    const uint32_t c0 = c[k] & 0xffffu, c1 = c[k] >> 16;
+                    if (SMEM) {
+                        const uint32_t a0 = hist_s + ((F[k] << 2) & 0x3fffcu), a1 = hist_s + ((F[k] >> 14) & 0x3fffcu);
+                        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a0), "r"(c0) : "memory");
+                        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a1), "r"(c1) : "memory");
+                    } else {
+                        const uint32_t f0 = F[k] & 0xffffu, f1 = F[k] >> 16;
+                        if (c0) atomicAdd(&a.hits[f0], (unsigned long long)c0);
+                        if (c1) atomicAdd(&a.hits[f1], (unsigned long long)c1);
+                    }
+                }
+            }
+        }
+        if (j == 31) {                                                  // next quad-block of descriptors
+            dcur = dnxt;
+            dnxt = load_desc((n >> 5) + 2);
+        }
+    }
+    cp_async_wait<0>();
+    if (SMEM) {
+        __syncthreads();
+        for (int f = threadIdx.x; f < db.nfiles; f += blockDim.x) {
+            const uint32_t c = hist[f];
+            if (c) atomicAdd(&a.hits[f], (unsigned long long)c);
+        }
+    }
+}
+
+
+// ---- count mode ----------------------------------------------------------------------------------
+// One batch = 7 launches on one stream with no host round trip in between: the kernels that consume the
+// plan check on the device that it fits the scratch buffers and do nothing otherwise; the host looks at
+// the plan's totals when it settles the batch and, in the rare case they did not fit (first batch of a
+// larger size), grows the buffers and runs the batch again -- or splits it when the plan itself is too big.
+// launch with programmatic stream serialization (see pdl_wait): only for kernels that call pdl_wait()
+template <class... KArgs, class... Args>
+cudaError_t launch_pdl(void (*k)(KArgs...), unsigned grid, unsigned block, size_t shm, cudaStream_t st, Args &&...args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(block), cfg.dynamicSmemBytes = shm, cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at, cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k, KArgs(std::forward<Args>(args))...);
+}
+
+template <bool V, bool PK>
+int count_geometry(igdb_dev *d, int *grid, int *threads, size_t *shm, bool *smem)
+{
+    using LP = PackedSmem<V>;
+    using L32 = CountSmem<V>;
+    // the shared histogram is used while it leaves room for at least 8 warps' pipelines
+    *smem = (PK ? LP::warps(d->nfiles, true) : L32::warps(d->nfiles, true)) >= 8;
+    const int nw = PK ? LP::warps(d->nfiles, *smem) : L32::warps(d->nfiles, *smem);
+    *shm = PK ? LP::cta_bytes(d->nfiles, *smem, nw) : L32::cta_bytes(d->nfiles, *smem, nw);
+    *threads = nw * 32;
+    if (d->count_grid[PK][V] == 0) {
+        const void *k = PK ? (*smem ? (const void *)k_count_packed<V, true> : (const void *)k_count_packed<V, false>)
+                           : (*smem ? (const void *)k_count_items<V, true> : (const void *)k_count_items<V, false>);
+        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*shm));
+        d->count_grid[PK][V] = d->sm_count;
+    }
+    *grid = d->count_grid[PK][V];
+    return 0;
+}
+
+// a CTA's shared histogram is uint32: an item adds at most GROUP*SMAX <= 2^15, a CTA takes at most
+// items/grid + 32*COUNT_MAXW items, so this many items per launch cannot overflow a counter
+int64_t item_limit(const igdb_dev *d, int grid) { return ((int64_t)(1 << 17) - 1024) * grid; }
+// the kernels may touch up to 32 descriptors / 1 segment past the plan's totals (padding)
+constexpr int64_t CAP_SLACK = 64;
+
+template <bool V, int MODE>
+int enqueue_count_t(igdb_dev *d, const igdb_dev::Pending &p)
+{
+    constexpr bool PK = MODE == M_PACKED;
+    cudaStream_t st = p.st;
+    const DbView db = d->view();
+    int grid = 0, threads = 0;
+    size_t shm = 0;
+    bool smem = false;
+    if (count_geometry<V, PK>(d, &grid, &threads, &shm, &smem)) return -1;
+    if (grow(&d->csegs, &d->cseg_cap, std::max<int64_t>(2 * p.n + 2 * d->T, 4096), 1, 1)) return -1;
+    if (grow(&d->items, &d->item_cap, std::min<int64_t>(d->db_groups + p.n / 64, item_limit(d, grid)) + 1024, 1, 1))
+        return -1;
+    const unsigned long long seg_cap = (unsigned long long)std::min<int64_t>(d->cseg_cap - CAP_SLACK, 0x7fffffff);
+    const unsigned long long item_cap =
+        (unsigned long long)std::min<int64_t>(d->item_cap - CAP_SLACK, item_limit(d, grid));
+    const int thr = CSEG_T;
+    const int nb = (int)((p.n + CSEG_T * CSEG_Q - 1) / (CSEG_T * CSEG_Q));
+    if (d->plan_grid == 0) {
+        // k_plan's CTAs wait for each other, so all of them must be resident at once: never more than the
+        // occupancy calculator allows (and at most 4 per SM, the size of the flag arrays)
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_plan, SCAN_T, 0));
+        per_sm = std::max(1, std::min(per_sm, 4));
+        d->plan_grid = std::max(1, std::min(per_sm * d->sm_count, (d->T + SCAN_T - 1) / SCAN_T));
+    }
+    const bool stages = d->stage_timing && MODE != M_ABN32;
+    if (stages) CK(cudaEventRecord(d->stage_ev[0], st));
+    CK(launch_pdl(k_cseg_count<V, MODE>, nb, thr, 0, st, db, p.n, p.ctg, p.qs, p.qe, d->cnt2));
+    if (stages) CK(cudaEventRecord(d->stage_ev[1], st));
+    // (the plan reads the later-bin counters that the scatter counts back down to zero)
+    CK(launch_pdl(k_plan, d->plan_grid, SCAN_T, 0, st, db, d->cnt2, ++d->plan_epoch, d->plan_agg, d->plan_flag,
+                  d->cseg_off, d->cseg_mid, d->plan_tot, seg_cap, item_cap, d->items));
+    if (stages) CK(cudaEventRecord(d->stage_ev[2], st));
+    CK(launch_pdl(k_cseg_scatter<V, MODE>, nb, thr, 0, st, db, p.n, p.ctg, p.qs, p.qe, d->cnt2, d->cseg_off,
+                  d->cseg_mid, d->plan_tot, seg_cap, item_cap, (void *)d->csegs));
+    // the plan's totals go back to the host on a side stream, so that the copy does not sit between the kernels
+    CK(cudaEventRecord(d->plan_done, st));
+    CK(cudaStreamWaitEvent(d->side, d->plan_done, 0));
+    CK(cudaMemcpyAsync((void *)d->h_plan, d->plan_tot, 32, cudaMemcpyDeviceToHost, d->side));
+    CK(cudaEventRecord(d->plan_ev, d->side));
+    CountArgs a{};
+    a.db = db, a.items = d->items, a.segs = d->csegs, a.tot = d->plan_tot;
+    a.seg_cap = seg_cap, a.item_cap = item_cap, a.v = p.v, a.hits = p.hits;
+    if (stages) CK(cudaEventRecord(d->stage_ev[3], st));
+    if (MODE != M_ABN32) CK(cudaEventRecord(d->kev[0], st));
+    if (PK) {
+        if (smem) CK(launch_pdl(k_count_packed<V, true>, grid, threads, shm, st, a));
+        else CK(launch_pdl(k_count_packed<V, false>, grid, threads, shm, st, a));
+    } else {
+        if (smem) k_count_items<V, true><<<grid, threads, shm, st>>>(a);
+        else k_count_items<V, false><<<grid, threads, shm, st>>>(a);
+    }
+    if (MODE != M_ABN32) {
+        CK(cudaEventRecord(d->kev[1], st));
+        d->kev_valid = true;
+    }
+    if (stages) {
+        CK(cudaEventRecord(d->stage_ev[4], st));
+        d->stage_valid = true;
+    }
+    d->launches += 4;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+int igdb::enqueue_count(igdb_dev *d, const igdb_dev::Pending &p)
+{
+    if (p.n <= 0) return 0;
+    switch (p.mode) {
+    case M_PACKED: return p.mode_v ? enqueue_count_t<true, M_PACKED>(d, p) : enqueue_count_t<false, M_PACKED>(d, p);
+    case M_ABN32: return p.mode_v ? enqueue_count_t<true, M_ABN32>(d, p) : enqueue_count_t<false, M_ABN32>(d, p);
+    default: return p.mode_v ? enqueue_count_t<true, M_ALL32>(d, p) : enqueue_count_t<false, M_ALL32>(d, p);
+    }
+}
+
+namespace {
+
+// wait for the plan of the enqueued batch p; make sure it ran (see above)
+int settle_count(igdb_dev *d, const igdb_dev::Pending &p)
+{
+    if (p.n <= 0) return 0;
+    const bool pk = p.mode == M_PACKED;
+    for (;;) {
+        CK(cudaEventSynchronize(d->plan_ev));
+        const unsigned long long nsegs = d->h_plan[0], nitems = d->h_plan[1], nrec = d->h_plan[2], nabn = d->h_plan[3];
+        if (getenv("IGD_B200_DEBUG"))
+            fprintf(stderr, "[igd_b200] count batch (mode %d): n=%lld segments=%llu items=%llu left=%llu (caps %lld / %lld)\n",
+                    p.mode, (long long)p.n, nsegs, nitems, nabn, (long long)d->cseg_cap, (long long)d->item_cap);
+        const int64_t lim = item_limit(d, d->count_grid[pk][p.mode_v]);
+        if (nsegs <= (unsigned long long)std::min<int64_t>(d->cseg_cap - CAP_SLACK, 0x7fffffff) &&
+            nitems <= (unsigned long long)std::min<int64_t>(d->item_cap - CAP_SLACK, lim)) {
+            if (p.mode != M_ABN32) {
+                // what the search kernel of this batch reads: descriptors, records, segments
+                const int64_t rb = pk ? (p.mode_v ? 10 : 6) : (p.mode_v ? 16 : 12), sgb = pk ? 4 : 8;
+                d->last_plan[0] = (int64_t)nsegs, d->last_plan[1] = (int64_t)nitems, d->last_plan[2] = (int64_t)nrec;
+                d->last_plan[3] = 16 * (int64_t)nitems + rb * (int64_t)nrec + sgb * (int64_t)nsegs;
+            }
+            if (pk && nabn > 0) {           // the queries the packed layout cannot express: second pipeline
+                igdb_dev::Pending q = p;
+                q.mode = M_ABN32;
+                if (enqueue_count(d, q) || settle_count(d, q)) return -1;
+            }
+            return 0;
+        }
+        // none of this batch's kernels wrote anything, but its segment counters were not counted back down
+        CK(cudaStreamSynchronize(p.st));
+        CK(cudaMemsetAsync(d->cnt2, 0, ((size_t)2 * d->T + 2) * 4, p.st));
+        if (nsegs >= 0x7fffffffull || nitems > (unsigned long long)lim) {
+            if (p.n <= 1) {
+                snprintf(g_err, sizeof g_err, "a single query expands to too many (query, tile) segments");
+                return -1;
+            }
+            igdb_dev::Pending a = p, b = p;
+            a.n = p.n / 2, b.n = p.n - a.n;
+            b.ctg += a.n, b.qs += a.n, b.qe += a.n;
+            if (enqueue_count(d, a) || settle_count(d, a) || enqueue_count(d, b) || settle_count(d, b)) return -1;
+            return 0;
+        }
+        if (grow(&d->csegs, &d->cseg_cap, (int64_t)nsegs + CAP_SLACK) ||
+            grow(&d->items, &d->item_cap, (int64_t)nitems + CAP_SLACK))
+            return -1;
+        if (enqueue_count(d, p)) return -1;
+    }
+}
+
+}  // namespace
+
+int igdb::finish_pending(igdb_dev *d)
+{
+    if (!d->pending.active) return 0;
+    d->pending.active = false;
+    return settle_count(d, d->pending);
+}
+
+
+extern "C" {
+
+float igdb_dev_last_search_ms(igdb_dev *d)
+{
+    float ms = -1.f;
+    if (!d->kev_valid) return ms;
+    if (cudaEventSynchronize(d->kev[1]) != cudaSuccess) return ms;
+    if (cudaEventElapsedTime(&ms, d->kev[0], d->kev[1]) != cudaSuccess) return -1.f;
+    return ms;
+}
+
+void igdb_dev_stage_timing(igdb_dev *d, int on) { d->stage_timing = on != 0, d->stage_valid = false; }
+int igdb_dev_last_stages(igdb_dev *d, float out[4])
+{
+    if (!d->stage_valid || cudaEventSynchronize(d->stage_ev[4]) != cudaSuccess) return -1;
+    for (int k = 0; k < 4; ++k)
+        if (cudaEventElapsedTime(&out[k], d->stage_ev[k], d->stage_ev[k + 1]) != cudaSuccess) return -1;
+    return 0;
+}
+
+
+void igdb_dev_last_plan(const igdb_dev *d, int64_t out[4])
+{
+    for (int k = 0; k < 4; ++k) out[k] = d->last_plan[k];
+}
+
+int igdb_dev_count_device(igdb_dev *d, int64_t n, const int32_t *d_ctg, const int32_t *d_qs, const int32_t *d_qe,
+                          int mode_v, int32_t v, uint64_t *d_hits, void *stream)
+{
+    g_err[0] = 0;
+    CK(cudaSetDevice(d->device));
+    if (finish_pending(d)) return -1;
+    if (n <= 0) return 0;
+    if (d->T == 0) return 0;
+    cudaStream_t st = stream ? (cudaStream_t)stream : d->stream;
+    const int64_t BATCH = 1 << 26;
+    for (int64_t a = 0; a < n; a += BATCH) {
+        igdb_dev::Pending p;
+        p.mode_v = mode_v != 0, p.n = std::min(BATCH, n - a);
+        p.ctg = d_ctg + a, p.qs = d_qs + a, p.qe = d_qe + a, p.v = v;
+        p.hits = (unsigned long long *)d_hits, p.st = st;
+        p.mode = d->packed ? M_PACKED : M_ALL32;
+        if (enqueue_count(d, p)) return -1;
+        if (a + BATCH < n) {                        // the scratch buffers are reused by the next chunk
+            if (settle_count(d, p)) return -1;
+        } else {
+            p.active = true;
+            d->pending = p;
+        }
+    }
+    return 0;
+}
+
+int igdb_dev_count_finish(igdb_dev *d)
+{
+    g_err[0] = 0;
+    CK(cudaSetDevice(d->device));
+    return finish_pending(d);
+}
+
+int igdb_dev_count_host(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_t *qs, const int32_t *qe, int mode_v,
+                        int32_t v, uint64_t *hits_delta, float *t_ms)
+{
+    g_err[0] = 0;
+    CK(cudaSetDevice(d->device));
+    if (finish_pending(d)) return -1;
+    cudaStream_t st = d->stream;
+    CK(cudaMemsetAsync(d->d_hits, 0, (size_t)d->nfiles * 8, st));
+    if (t_ms) t_ms[0] = t_ms[1] = t_ms[2] = 0.f;
+    const int64_t BATCH = 1 << 26;
+    for (int64_t a = 0; a < n && d->T > 0; a += BATCH) {
+        const int64_t m = std::min(BATCH, n - a);
+        if (ensure_query_cap(d, m)) return -1;
+        CK(cudaEventRecord(d->ev[0], st));
+        CK(cudaMemcpyAsync(d->q_ctg, ctg + a, (size_t)m * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d->q_qs, qs + a, (size_t)m * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d->q_qe, qe + a, (size_t)m * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaEventRecord(d->ev[1], st));
+        igdb_dev::Pending p;
+        p.mode_v = mode_v != 0, p.n = m, p.ctg = d->q_ctg, p.qs = d->q_qs, p.qe = d->q_qe, p.v = v;
+        p.hits = d->d_hits, p.st = st;
+        p.mode = d->packed ? M_PACKED : M_ALL32;
+        if (enqueue_count(d, p)) return -1;
+        const bool last = a + BATCH >= n;
+        if (last) {                                 // the result copy rides behind the kernels; no sync yet
+            CK(cudaEventRecord(d->ev[2], st));
+            CK(cudaMemcpyAsync(hits_delta, d->d_hits, (size_t)d->nfiles * 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaEventRecord(d->ev[3], st));
+        }
+        // in the rare case the batch had to be run again, the copy is repeated below
+        const int64_t launches0 = d->launches;
+        if (settle_count(d, p)) return -1;
+        if (last && d->launches != launches0) {
+            CK(cudaEventRecord(d->ev[2], st));
+            CK(cudaMemcpyAsync(hits_delta, d->d_hits, (size_t)d->nfiles * 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaEventRecord(d->ev[3], st));
+        }
+        if (t_ms || !last) CK(cudaStreamSynchronize(st));
+        if (t_ms) {
+            float x = 0, y = 0;
+            CK(cudaEventElapsedTime(&x, d->ev[0], d->ev[1]));
+            t_ms[0] += x;
+            if (last) {
+                CK(cudaEventElapsedTime(&y, d->ev[1], d->ev[2]));
+                t_ms[1] += y;
+            }
+        }
+    }
+    if (n <= 0 || d->T == 0) {
+        CK(cudaMemcpyAsync(hits_delta, d->d_hits, (size_t)d->nfiles * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return 0;
+    }
+    CK(cudaStreamSynchronize(st));
+    if (t_ms) CK(cudaEventElapsedTime(&t_ms[2], d->ev[2], d->ev[3]));
+    return 0;
+}
+
+}  // extern "C"

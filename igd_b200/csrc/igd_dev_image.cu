@@ -1,0 +1,297 @@
+// igd_b200 CUDA layer -- the HBM image of a database: create, upload (AoS -> SoA + packed copy), finalize, destroy.
+#include "igd_dev_impl.cuh"
+
+namespace igdb {
+thread_local char g_err[512] = "";
+}
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// upload
+// ------------------------------------------------------------------------------------------------
+// AoS gdata_t {idx,start,end,value} -> padded SoA.  toff[T+1] = unpadded record prefix (file order).
+__global__ void k_transpose(const int4 *__restrict__ aos, int64_t rec0, int64_t nrec,
+                            const int64_t *__restrict__ toff, int32_t T, const TileMeta *__restrict__ tiles,
+                            int32_t *__restrict__ start, int32_t *__restrict__ end, int32_t *__restrict__ idx,
+                            int32_t *__restrict__ value, int32_t nbp, uint16_t *__restrict__ ps,
+                            uint16_t *__restrict__ pe, uint16_t *__restrict__ pf)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrec) return;
+    int64_t g = rec0 + i;
+    int32_t lo = 0, hi = T;                 // last t with toff[t] <= g
+    while (hi - lo > 1) {
+        int32_t mid = (lo + hi) >> 1;
+        if (__ldg(&toff[mid]) <= g) lo = mid; else hi = mid;
+    }
+    int4 r = __ldg(&aos[i]);
+    int64_t dst = (int64_t)tiles[lo].off8 * 8 + (g - __ldg(&toff[lo]));
+    idx[dst] = r.x, start[dst] = r.y, end[dst] = r.z, value[dst] = r.w;
+    if (ps) {                                   // tiles[].ts still holds the bin boundary here (k_tile_meta)
+        const int32_t bd = tiles[lo].ts;
+        ps[dst] = (uint16_t)(pk_rel(r.y, bd, nbp) + 1);
+        pe[dst] = (uint16_t)(pk_rel_end(r.z, bd, nbp) + 0x8000);
+        pf[dst] = (uint16_t)r.x;
+    }
+}
+
+__global__ void k_fill16(uint16_t *__restrict__ p, int64_t n, uint16_t v)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = v;
+}
+
+__global__ void k_fill(int32_t *__restrict__ p, int64_t n, int32_t v)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = v;
+}
+
+// per tile: ts = #records with start < bd (bd arrives in .ts), s0 = first start
+__global__ void k_tile_meta(TileMeta *tiles, int32_t T, const int32_t *__restrict__ start)
+{
+    int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    TileMeta m = tiles[t];
+    const int32_t *s = start + (int64_t)m.off8 * 8;
+    int32_t bd = m.ts, lo = 0, hi = m.n;
+    while (lo < hi) {
+        int32_t mid = (lo + hi) >> 1;
+        if (s[mid] < bd) lo = mid + 1; else hi = mid;
+    }
+    m.ts = lo;
+    m.s0 = m.n > 0 ? s[0] : 0x7fffffff;
+    tiles[t] = m;
+}
+
+
+}  // namespace
+
+namespace igdb {
+
+int ensure_query_cap(igdb_dev *d, int64_t n)
+{
+    if (n <= d->q_cap) return 0;
+    int64_t c = 0;
+    int64_t cap0 = d->q_cap;
+    c = cap0; if (grow(&d->q_ctg, &c, n)) return -1;
+    c = cap0; if (grow(&d->q_qs, &c, n)) return -1;
+    c = cap0; if (grow(&d->q_qe, &c, n)) return -1;
+    c = cap0; if (grow(&d->nseg, &c, n)) return -1;
+    c = cap0; if (grow(&d->qseg_off, &c, n + 1)) return -1;
+    d->q_cap = n * 5 / 4 + 1024 - 1;        // the smallest of the capacities above
+    return 0;
+}
+
+int upload_queries(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_t *qs, const int32_t *qe, cudaStream_t st)
+{
+    if (ensure_query_cap(d, std::max<int64_t>(n, 1))) return -1;
+    CK(cudaMemcpyAsync(d->q_ctg, ctg, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d->q_qs, qs, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d->q_qe, qe, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    return 0;
+}
+
+}  // namespace igdb
+
+extern "C" {
+
+const char *igdb_dev_error(void) { return g_err; }
+
+int igdb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+
+void igdb_dev_destroy(igdb_dev *d)
+{
+    if (!d) return;
+    cudaSetDevice(d->device);
+    void *ptrs[] = {d->tiles, d->d_toff, d->start, d->end, d->idx, d->value, d->tbase, d->d_stage, d->q_ctg,
+                    d->q_qs, d->q_qe, d->tile_cnt, d->tile_off, d->nseg, d->qseg_off, d->bsum, d->segs,
+                    d->seg_hits, d->seg_out_off, d->d_hits, d->cnt2, d->cseg_off, d->cseg_mid,
+                    d->plan_agg, d->plan_flag, d->plan_tot, d->csegs, d->items, d->ps, d->pe, d->pf,
+                    d->ctg_names, d->ctg_slots, d->d_text};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (d->pinned) cudaFreeHost(d->pinned);
+    if (d->arena) cudaFreeHost(d->arena);
+    if (d->h_scalar) cudaFreeHost(d->h_scalar);
+    if (d->plan_ev) cudaEventDestroy(d->plan_ev);
+    if (d->plan_done) cudaEventDestroy(d->plan_done);
+    if (d->side) cudaStreamDestroy(d->side);
+    for (auto &e : d->ev)
+        if (e) cudaEventDestroy(e);
+    for (auto &e : d->kev)
+        if (e) cudaEventDestroy(e);
+    for (auto &e : d->stage_ev)
+        if (e) cudaEventDestroy(e);
+    if (d->stream) cudaStreamDestroy(d->stream);
+    delete d;
+}
+
+static int create_impl(igdb_dev *d, const int32_t *ntile, const int32_t *ncnt)
+{
+    CK(cudaSetDevice(d->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, d->device));
+    d->sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+    for (auto &e : d->ev) CK(cudaEventCreate(&e));
+    for (auto &e : d->kev) CK(cudaEventCreate(&e));
+    for (auto &e : d->stage_ev) CK(cudaEventCreate(&e));
+    CK(cudaMallocHost((void **)&d->h_scalar, 64));
+    d->h_plan = reinterpret_cast<volatile unsigned long long *>(d->h_scalar + 8);
+    CK(cudaEventCreateWithFlags(&d->plan_ev, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&d->plan_done, cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&d->side, cudaStreamNonBlocking));
+
+    std::vector<int32_t> tbase(d->nctg + 1, 0);
+    for (int c = 0; c < d->nctg; ++c) tbase[c + 1] = tbase[c] + ntile[c];
+    d->T = tbase[d->nctg];
+    std::vector<TileMeta> meta((size_t)d->T);
+    d->toff.assign((size_t)d->T + 1, 0);
+    int64_t p8 = 0;
+    for (int c = 0, t = 0; c < d->nctg; ++c)
+        for (int j = 0; j < ntile[c]; ++j, ++t) {
+            const int32_t n = ncnt[t];
+            meta[t].off8 = (uint32_t)p8;
+            d->off8.push_back((uint32_t)p8);
+            meta[t].n = n;
+            meta[t].ts = d->nbp * j;            // bin boundary; k_tile_meta turns it into tS
+            meta[t].s0 = 0x7fffffff;
+            d->toff[t + 1] = d->toff[t] + n;
+            d->db_groups += (n + GROUP - 1) / GROUP;
+            p8 += (n + 7) / 8;
+        }
+    if (p8 >= (int64_t)0xffffffff) {
+        snprintf(g_err, sizeof g_err, "database too large for 32-bit tile offsets");
+        return -1;
+    }
+    d->nrec = d->toff[d->T];
+    d->P = p8 * 8;
+    if (dev_alloc(d, &d->tiles, (size_t)d->T) || dev_alloc(d, &d->d_toff, (size_t)d->T + 1) ||
+        dev_alloc(d, &d->tbase, (size_t)d->nctg + 1) || dev_alloc(d, &d->start, (size_t)d->P + 8) ||
+        dev_alloc(d, &d->end, (size_t)d->P + 8) || dev_alloc(d, &d->idx, (size_t)d->P + 8) ||
+        dev_alloc(d, &d->value, (size_t)d->P + 8) || dev_alloc(d, &d->tile_cnt, (size_t)d->T + 1) ||
+        dev_alloc(d, &d->tile_off, (size_t)d->T + 1) || dev_alloc(d, &d->d_hits, (size_t)d->nfiles) ||
+        dev_alloc(d, &d->cnt2, (size_t)2 * d->T + 2) || dev_alloc(d, &d->cseg_off, (size_t)d->T + 1) ||
+        dev_alloc(d, &d->cseg_mid, (size_t)d->T + 1) ||
+        dev_alloc(d, &d->plan_agg, (size_t)4 * d->sm_count) || dev_alloc(d, &d->plan_flag, (size_t)4 * d->sm_count) ||
+        dev_alloc(d, &d->plan_tot, 8))
+        return -1;
+    // packed count-mode copies: tile-relative coordinates need nbp + 1 < 2^15, file indices 16 bits
+    d->packed = d->nbp <= 16384 && d->nfiles <= 65536 && !getenv("IGD_B200_NO_PACKED");
+    if (d->packed && (dev_alloc(d, &d->ps, (size_t)d->P + 8) || dev_alloc(d, &d->pe, (size_t)d->P + 8) ||
+                      dev_alloc(d, &d->pf, (size_t)d->P + 8)))
+        return -1;
+    CK(cudaMemcpy(d->tiles, meta.data(), meta.size() * sizeof(TileMeta), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d->d_toff, d->toff.data(), d->toff.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d->tbase, tbase.data(), tbase.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    // pad records (tiles are padded to a multiple of 4): start = INT_MAX, end = INT_MIN -- overlap no query
+    const unsigned fb = (unsigned)std::min<int64_t>(((int64_t)d->P + 8 + 255) / 256, 148 * 32);
+    k_fill<<<fb, 256>>>(d->start, (int64_t)d->P + 8, IMAX);
+    k_fill<<<fb, 256>>>(d->end, (int64_t)d->P + 8, IMIN);
+    k_fill<<<fb, 256>>>(d->value, (int64_t)d->P + 8, IMIN);
+    if (d->packed) {
+        k_fill16<<<fb, 256>>>(d->ps, (int64_t)d->P + 8, (uint16_t)0x8000);
+        k_fill16<<<fb, 256>>>(d->pe, (int64_t)d->P + 8, (uint16_t)0x8000);
+        CK(cudaMemset(d->pf, 0, ((size_t)d->P + 8) * 2));
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemset(d->idx, 0, ((size_t)d->P + 8) * 4));
+    CK(cudaMemset(d->tile_cnt, 0, ((size_t)d->T + 1) * 4));
+    CK(cudaMemset(d->cnt2, 0, ((size_t)2 * d->T + 2) * 4));
+    CK(cudaMemset(d->plan_flag, 0, (size_t)4 * d->sm_count * 4));
+    d->plan_grid = 0;                           // chosen at the first count batch (igd_dev_count.cu)
+    return 0;
+}
+
+igdb_dev *igdb_dev_create(int device, int32_t nbp, int32_t nctg, const int32_t *ntile, const int32_t *ncnt,
+                          int32_t nfiles)
+{
+    g_err[0] = 0;
+    igdb_dev *d = new igdb_dev();
+    d->device = device, d->nbp = nbp, d->nctg = nctg, d->nfiles = nfiles;
+    if (create_impl(d, ntile, ncnt)) {
+        igdb_dev_destroy(d);
+        return nullptr;
+    }
+    return d;
+}
+
+void *igdb_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    memset(p, 0, bytes);
+    return p;
+}
+void igdb_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+void *igdb_dev_pinned(igdb_dev *d, size_t bytes)
+{
+    if (bytes > d->pinned_cap) {
+        if (d->pinned) cudaFreeHost(d->pinned);
+    if (d->arena) cudaFreeHost(d->arena);
+        d->pinned = nullptr, d->pinned_cap = 0;
+        if (cudaMallocHost(&d->pinned, bytes) != cudaSuccess) return nullptr;
+        d->pinned_cap = bytes;
+    }
+    return d->pinned;
+}
+
+int igdb_dev_upload(igdb_dev *d, int64_t rec0, int64_t nrec, const void *aos)
+{
+    if (nrec <= 0) return 0;
+    CK(cudaSetDevice(d->device));
+    const size_t bytes = (size_t)nrec * 16;
+    if (bytes > d->d_stage_cap) {
+        if (d->d_stage) CK(cudaFree(d->d_stage));
+        d->d_stage = nullptr;
+        CK(cudaMalloc(&d->d_stage, bytes));
+        d->d_stage_cap = bytes;
+    }
+    CK(cudaMemcpyAsync(d->d_stage, aos, bytes, cudaMemcpyHostToDevice, d->stream));
+    const int thr = 256;
+    k_transpose<<<(unsigned)((nrec + thr - 1) / thr), thr, 0, d->stream>>>(
+        (const int4 *)d->d_stage, rec0, nrec, d->d_toff, d->T, d->tiles, d->start, d->end, d->idx, d->value, d->nbp,
+        d->ps, d->pe, d->pf);
+    d->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(d->stream));       // the caller reuses its host buffer
+    return 0;
+}
+
+int igdb_dev_finalize(igdb_dev *d)
+{
+    CK(cudaSetDevice(d->device));
+    if (d->T > 0) {
+        k_tile_meta<<<(d->T + 255) / 256, 256, 0, d->stream>>>(d->tiles, d->T, d->start);
+        d->launches += 1;
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(d->stream));
+    if (d->d_stage) {
+        CK(cudaFree(d->d_stage));
+        d->d_stage = nullptr, d->d_stage_cap = 0;
+    }
+    return 0;
+}
+
+int64_t igdb_dev_bytes(const igdb_dev *d) { return d->bytes; }
+int igdb_dev_packed(const igdb_dev *d) { return d->packed ? 1 : 0; }
+int64_t igdb_dev_launches(const igdb_dev *d) { return d->launches; }
+
+
+}  // extern "C"

@@ -1,0 +1,234 @@
+// igd_b200 CUDA layer -- -s: Seqpare similarity.
+#include "igd_dev_impl.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// -s Seqpare (seq_overlaps + seqOverlaps, src/igd_search.c:253-451).
+//   K4  k_seq_candidates: one thread per overlap of the -f hit list (same hit set and order as seq_overlaps:
+//       :275-350).  Pair similarity in IEEE fp32 exactly as the reference computes it (:255, :291-299:
+//       st / ((qlen + rlen) - st), round-to-nearest adds/subs/div, no FMA).  The candidate's sort key is
+//       (problem = query-chrom group * nFiles + file) << 32 | ~bits(sm): ascending key = per (chrom, file)
+//       problem, similarity descending.  The input order is (query rank, scan order), so a STABLE sort by that
+//       key alone gives the reference's tie-break: smallest query rank, then earliest in scan order.
+//   K5  k_seq_sweep: one thread per (chrom, file) problem walks its candidates in that order and accepts one
+//       iff neither its row (query) nor its column is taken -- equivalent to the reference's repeated arg-max
+//       with row retirement and column zeroing (:397-438).  A column is identified the way
+//       the reference does it, quirk included: (n1 OF THE QUERY, index inside whichever tile the record was
+//       found in) (:298, :342).  Taken rows/columns live in a per-problem open-addressing table.
+//       The accepted similarities are written out in pick order; k_seq_sum adds them per file in the
+//       reference's order (chrom groups ascending, picks in order) so the fp64 sums are bit-identical.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_seq_candidates(DbView db, int64_t n, const int64_t *__restrict__ qoff,
+                                 const int32_t *__restrict__ qs, const int32_t *__restrict__ qe,
+                                 const int32_t *__restrict__ grp, int64_t total, const int32_t *__restrict__ os,
+                                 const int32_t *__restrict__ oe, const int32_t *__restrict__ of,
+                                 const int32_t *__restrict__ og, unsigned long long *__restrict__ key,
+                                 uint32_t *__restrict__ val, uint32_t *__restrict__ row,
+                                 unsigned long long *__restrict__ col)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= total) return;
+    int64_t lo = 0, hi = n;                                 // last q with qoff[q] <= p
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(&qoff[mid]) <= p) lo = mid; else hi = mid;
+    }
+    const int32_t s = __ldg(&qs[lo]), e = __ldg(&qe[lo]);
+    const int32_t rs = os[p], re = oe[p];
+    const float qlen = __int2float_rn(e - s), rlen = __int2float_rn(re - rs);
+    const float st = __int2float_rn(min(e, re) - max(s, rs));
+    const float sm = __fdiv_rn(st, __fsub_rn(__fadd_rn(qlen, rlen), st));
+    const unsigned long long prob = (unsigned long long)__ldg(&grp[lo]) * (unsigned)db.nfiles + (unsigned)of[p];
+    key[p] = prob << 32 | (uint32_t)~__float_as_uint(sm);
+    val[p] = (uint32_t)p;
+    row[p] = (uint32_t)lo;
+    col[p] = 1ull << 62 | (unsigned long long)(uint32_t)(s / db.nbp) << 32 | (uint32_t)og[p];
+}
+
+__device__ __forceinline__ int64_t lower_bound_key(const unsigned long long *__restrict__ k, int64_t n,
+                                                   unsigned long long x)
+{
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(&k[mid]) < x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// per problem: where its candidates start in the sorted array, and the size of its table
+__global__ void k_seq_ranges(const unsigned long long *__restrict__ key, int64_t total, int64_t nprob, int32_t nfiles,
+                             const int32_t *__restrict__ grp_nq, int64_t *__restrict__ pstart,
+                             uint32_t *__restrict__ tsize)
+{
+    const int64_t pid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pid > nprob) return;
+    const int64_t a = lower_bound_key(key, total, (unsigned long long)pid << 32);
+    pstart[pid] = a;
+    if (pid == nprob) return;
+    const int64_t b = lower_bound_key(key, total, (unsigned long long)(pid + 1) << 32);
+    // at most one row and one column are inserted per accepted candidate, and every accepted candidate retires
+    // a distinct query of the group
+    const int64_t picks = min(b - a, (int64_t)grp_nq[pid / nfiles]);
+    uint32_t sz = 0;
+    if (picks > 0) {
+        sz = 16;
+        while ((int64_t)sz < 4 * picks) sz <<= 1;
+    }
+    tsize[pid] = sz;
+}
+
+__device__ __forceinline__ uint32_t seq_hash(unsigned long long x)
+{
+    x ^= x >> 33, x *= 0xff51afd7ed558ccdULL, x ^= x >> 33, x *= 0xc4ceb9fe1a85ec53ULL, x ^= x >> 33;
+    return (uint32_t)x;
+}
+// true if x was already in the table; inserts it otherwise when `insert`
+__device__ __forceinline__ bool seq_probe(unsigned long long *t, uint32_t mask, unsigned long long x, bool insert)
+{
+    for (uint32_t h = seq_hash(x) & mask;; h = (h + 1) & mask) {
+        const unsigned long long y = t[h];
+        if (y == x) return true;
+        if (y == 0) {
+            if (insert) t[h] = x;
+            return false;
+        }
+    }
+}
+
+__global__ void k_seq_sweep(const unsigned long long *__restrict__ key, const uint32_t *__restrict__ val,
+                            const uint32_t *__restrict__ row, const unsigned long long *__restrict__ col,
+                            int64_t nprob, const int64_t *__restrict__ pstart, const uint32_t *__restrict__ tsize,
+                            const unsigned long long *__restrict__ toff, unsigned long long *__restrict__ tables,
+                            float *__restrict__ pick, uint32_t *__restrict__ npick)
+{
+    const int64_t pid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pid >= nprob) return;
+    const int64_t a = pstart[pid], b = pstart[pid + 1];
+    uint32_t np = 0;
+    if (b > a) {
+        unsigned long long *t = tables + toff[pid];
+        const uint32_t mask = tsize[pid] - 1;
+        for (int64_t i = a; i < b; ++i) {
+            const uint32_t bits = ~(uint32_t)key[i];
+            if ((int32_t)bits <= 0) break;                  // similarity 0: the reference stops at maxf == 0
+            const uint32_t c = val[i];
+            const unsigned long long r = 1ull << 63 | row[c], cc = col[c];
+            if (seq_probe(t, mask, r, false) || seq_probe(t, mask, cc, false)) continue;
+            seq_probe(t, mask, r, true);
+            seq_probe(t, mask, cc, true);
+            pick[a + np++] = __uint_as_float(bits);
+        }
+    }
+    npick[pid] = np;
+}
+
+// sm[m] += maxf in the reference's order (src/igd_search.c:367,397,419): chrom groups ascending, picks in order
+__global__ void k_seq_sum(int32_t nfiles, int32_t ngroups, const int64_t *__restrict__ pstart,
+                          const float *__restrict__ pick, const uint32_t *__restrict__ npick, double *__restrict__ acc)
+{
+    const int32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nfiles) return;
+    double s = 0.0;
+    for (int32_t g = 0; g < ngroups; ++g) {
+        const int64_t pid = (int64_t)g * nfiles + f, a = pstart[pid];
+        const uint32_t np = npick[pid];
+        for (uint32_t k = 0; k < np; ++k) s += (double)pick[a + k];
+    }
+    acc[f] = s;
+}
+
+
+}  // namespace
+
+extern "C" {
+
+// -s: queries grouped by query-file chrom (grp[q] ascending, 0..ngroups-1) and sorted by start inside a group
+// (the host did readBED + qsort, src/igd_base.c:628-649, src/igd_search.c:373).  acc[m] receives the sum of the
+// matched similarities of file m, i.e. sm[m] before the final ratio of src/igd_search.c:445-448.
+int igdb_dev_seqpare(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_t *qs, const int32_t *qe,
+                     const int32_t *grp, int32_t ngroups, const int32_t *grp_nq, double *acc)
+{
+    g_err[0] = 0;
+    CK(cudaSetDevice(d->device));
+    if (finish_pending(d)) return -1;
+    cudaStream_t st = d->stream;
+    for (int32_t m = 0; m < d->nfiles; ++m) acc[m] = 0.0;
+    if (n == 0 || d->T == 0 || d->nfiles == 0) return 0;
+    const int64_t nprob = (int64_t)ngroups * d->nfiles;
+    if (n >= (1 << 26) || nprob >= (1ll << 31)) {
+        snprintf(g_err, sizeof g_err, "Seqpare: query set too large (%lld queries, %lld chrom x file problems)",
+                 (long long)n, (long long)nprob);
+        return -1;
+    }
+    if (upload_queries(d, n, ctg, qs, qe, st)) return -1;
+    DevBuf qoff, out;
+    const int64_t total = full_device(d, n, st, true, qoff, out);
+    if (total < 0) return -1;
+    if (total == 0) return 0;
+    if (total >= (1ll << 31)) {
+        snprintf(g_err, sizeof g_err, "Seqpare: %lld candidate pairs exceed one pass (2^31)", (long long)total);
+        return -1;
+    }
+    DevBuf b_grp, b_gnq, b_key, b_key2, b_val, b_val2, b_row, b_col, b_tmp;
+    if (b_grp.alloc((size_t)n * 4) || b_gnq.alloc((size_t)ngroups * 4) || b_key.alloc((size_t)total * 8) ||
+        b_key2.alloc((size_t)total * 8) || b_val.alloc((size_t)total * 4) || b_val2.alloc((size_t)total * 4) ||
+        b_row.alloc((size_t)total * 4) || b_col.alloc((size_t)total * 8))
+        return -1;
+    CK(cudaMemcpyAsync(b_grp.p, grp, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(b_gnq.p, grp_nq, (size_t)ngroups * 4, cudaMemcpyHostToDevice, st));
+    const int32_t *o = out.as<int32_t>();
+    k_seq_candidates<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        d->view(), n, qoff.as<int64_t>(), d->q_qs, d->q_qe, b_grp.as<int32_t>(), total, o, o + total, o + 2 * total,
+        o + 3 * total, b_key.as<unsigned long long>(), b_val.as<uint32_t>(), b_row.as<uint32_t>(),
+        b_col.as<unsigned long long>());
+    CK(cudaGetLastError());
+    // stable LSD radix sort (CUB, a library primitive) on the used key bits only
+    int end_bit = 32;
+    while (end_bit < 64 && (nprob >> (end_bit - 32)) != 0) ++end_bit;
+    size_t tmp_bytes = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, b_key.as<unsigned long long>(),
+                                       b_key2.as<unsigned long long>(), b_val.as<uint32_t>(), b_val2.as<uint32_t>(),
+                                       (int)total, 0, end_bit, st));
+    if (b_tmp.alloc(tmp_bytes)) return -1;
+    CK(cub::DeviceRadixSort::SortPairs(b_tmp.p, tmp_bytes, b_key.as<unsigned long long>(),
+                                       b_key2.as<unsigned long long>(), b_val.as<uint32_t>(), b_val2.as<uint32_t>(),
+                                       (int)total, 0, end_bit, st));
+    DevBuf b_pstart, b_tsize, b_toff, b_tab, b_pick, b_npick, b_acc;
+    if (b_pstart.alloc((size_t)(nprob + 1) * 8) || b_tsize.alloc((size_t)(nprob + 1) * 4) ||
+        b_toff.alloc((size_t)(nprob + 1) * 8) || b_pick.alloc((size_t)total * 4) ||
+        b_npick.alloc((size_t)nprob * 4) || b_acc.alloc((size_t)d->nfiles * 8))
+        return -1;
+    k_seq_ranges<<<(unsigned)((nprob + 1 + 255) / 256), 256, 0, st>>>(
+        b_key2.as<unsigned long long>(), total, nprob, d->nfiles, b_gnq.as<int32_t>(), b_pstart.as<int64_t>(),
+        b_tsize.as<uint32_t>());
+    CK(cudaGetLastError());
+    if (exclusive_scan<uint32_t, unsigned long long>(d, b_tsize.as<uint32_t>(), b_toff.as<unsigned long long>(), nprob,
+                                                     st))
+        return -1;
+    unsigned long long *h_total = (unsigned long long *)(d->h_scalar + 2);
+    CK(cudaMemcpyAsync(h_total, b_toff.as<unsigned long long>() + nprob, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const size_t slots = (size_t)*h_total;
+    if (b_tab.alloc(slots * 8)) {
+        snprintf(g_err, sizeof g_err, "Seqpare: matching tables (%zu slots) do not fit in device memory", slots);
+        return -1;
+    }
+    CK(cudaMemsetAsync(b_tab.p, 0, std::max<size_t>(slots * 8, 16), st));
+    k_seq_sweep<<<(unsigned)((nprob + 127) / 128), 128, 0, st>>>(
+        b_key2.as<unsigned long long>(), b_val2.as<uint32_t>(), b_row.as<uint32_t>(), b_col.as<unsigned long long>(),
+        nprob, b_pstart.as<int64_t>(), b_tsize.as<uint32_t>(), b_toff.as<unsigned long long>(),
+        b_tab.as<unsigned long long>(), b_pick.as<float>(), b_npick.as<uint32_t>());
+    k_seq_sum<<<(d->nfiles + 127) / 128, 128, 0, st>>>(d->nfiles, ngroups, b_pstart.as<int64_t>(), b_pick.as<float>(),
+                                                       b_npick.as<uint32_t>(), b_acc.as<double>());
+    d->launches += 5;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(acc, b_acc.p, (size_t)d->nfiles * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+}  // extern "C"

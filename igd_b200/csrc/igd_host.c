@@ -1,6 +1,6 @@
 /* igd_b200 host side (C): .igd / _index.tsv parsing, BED query ingest, the handle-based C-ABI of
  * include/igd_b200.h and the reference-named global-state entry points.  All searching is done by the
- * CUDA layer (igd_dev.cu) through igd_dev.h; there is no CPU search path in this library. */
+ * CUDA layer (igd_dev_*.cu) through igd_dev.h; there is no CPU search path in this library. */
 #define _GNU_SOURCE
 #include "igd_b200.h"
 #include "igd_dev.h"

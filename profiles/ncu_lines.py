@@ -26,7 +26,8 @@ for l in dis:
     m = re.match(r'\s*/\*([0-9a-f]{4,})\*/\s+(\S.*?);', l)
     if m and cur is not None:
         line_of[int(m.group(1), 16)] = cur
-src_lines = open(os.path.join(os.path.dirname(os.path.abspath(lib)), '..', 'csrc', 'igd_dev.cu')).read().splitlines()
+csrc = os.path.join(os.path.dirname(os.path.abspath(lib)), '..', 'csrc')
+src_files = {f: open(os.path.join(csrc, f)).read().splitlines() for f in os.listdir(csrc) if f.endswith(('.cu', '.cuh'))}
 raw = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr = rows[1]
@@ -50,5 +51,5 @@ for key in sorted(agg):
     ex, smp = agg[key]
     f, ln = key
     if ex >= tot * thr:
-        text = src_lines[ln - 1].strip()[:100] if f == 'igd_dev.cu' and 0 < ln <= len(src_lines) else f
+        text = src_files[f][ln - 1].strip()[:100] if f in src_files and 0 < ln <= len(src_files[f]) else f
         print(f'{ex/1e6:8.2f}M {100*ex/tot:5.1f}% smp={smp:6d}  L{ln}: {text}')

@@ -1,4 +1,4 @@
-"""The arithmetic identity behind the packed count-mode layout (igd_dev.cu: pk_rel, pk_rel_end,
+"""The arithmetic identity behind the packed count-mode layout (igd_dev_impl.cuh: pk_rel, pk_rel_end; igd_dev_count.cu:
 k_count_packed), restated in numpy and checked against the reference's int32 predicate on random tiles:
 
   start_r < qe  and  end_r > qs   <=>   bit 15 of (QE - S)  and  bit 15 of (E - QS)
