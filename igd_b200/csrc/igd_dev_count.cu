@@ -94,12 +94,12 @@ __device__ __forceinline__ Plan plan_of_tile(const DbView &db, const uint32_t *_
     return Plan{(s + 1) & ~1ull, g * ((s + SMAX - 1) / SMAX)};
 }
 
-// The whole plan in ONE launch: a chained scan over the tiles fused with the item fill.  The grid has at most four
-// 512-thread CTAs per SM (all co-resident), CTA b owns a contiguous range of tiles:
-//   1. block-reduce the plan of its range and publish it (agg[b], then flag[b] = epoch);
-//   2. wait for every CTA's aggregate: the sum of the earlier ones is this CTA's prefix, the sum of all is the
-//      batch total -- if that does not fit the scratch buffers nothing more is written (the host grows them
-//      and runs the batch again);
+// The whole plan in ONE launch: a scan over the tiles fused with the item fill.  The grid is small enough that all
+// of its 512-thread CTAs are resident at once; CTA b owns a contiguous range of tiles:
+//   1. block-reduce the plan of its range, publish it (agg[b]) and take a ticket;
+//   2. the CTA that draws the last ticket turns the aggregates into exclusive prefixes, writes the batch totals
+//      and raises ONE flag (= epoch of this launch) that every CTA waits on with one thread -- if the totals do
+//      not fit the scratch buffers nothing more is written (the host grows them and runs the batch again);
 //   3. walk the range again in chunks of SCAN_T tiles: block scan + running carry give each tile its first
 //      segment (seg_off), its first later-bin segment (seg_mid) and its first work item, and the tile's items are
 //      written on the spot.
@@ -114,12 +114,13 @@ __device__ __forceinline__ Plan plan_of_tile(const DbView &db, const uint32_t *_
 
 __global__ void __launch_bounds__(SCAN_T) k_plan(DbView db, const uint32_t *__restrict__ cnt2, uint32_t epoch,
                                                   volatile PlanAgg *agg, volatile uint32_t *flag,
-                                                  uint32_t *__restrict__ seg_off, uint32_t *__restrict__ seg_mid,
+                                                  uint32_t *ticket, uint32_t *__restrict__ seg_off, uint32_t *__restrict__ seg_mid,
                                                   unsigned long long *__restrict__ tot, unsigned long long seg_cap,
                                                   unsigned long long item_cap, int4 *__restrict__ items)
 {
-    __shared__ unsigned long long red[3][SCAN_T / 32], red5[5][SCAN_T / 32];
+    __shared__ unsigned long long red[3][SCAN_T / 32];
     __shared__ unsigned long long sh_prefix[2], sh_total[3];
+    __shared__ bool sh_last;
     const int32_t T = db.ntiles;
     const int G = gridDim.x, b = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int32_t per = (T + G - 1) / G, t0 = min(b * per, T), t1 = min(t0 + per, T);
@@ -147,43 +148,43 @@ __global__ void __launch_bounds__(SCAN_T) k_plan(DbView db, const uint32_t *__re
         unsigned long long x = 0, y = 0, z = 0;
         for (int w = 0; w < SCAN_T / 32; ++w) x += red[0][w], y += red[1][w], z += red[2][w];
         agg[b].segs = x, agg[b].items = y, agg[b].recs = z;
-        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&flag[b]), "r"(epoch) : "memory");
+        __threadfence();
+        sh_last = atomicAdd(ticket, 1u) == (uint32_t)G - 1;         // the last CTA to get here scans for everybody
     }
-    // 2. everybody's aggregates (every thread waits for its share of the CTAs)
-    {
-        unsigned long long v5[5] = {0, 0, 0, 0, 0};         // prefix segs / items, total segs / items / records
-        for (int i = threadIdx.x; i < G; i += SCAN_T) {
-            for (;;) {                                      // acquire: the aggregate is visible once the flag is
-                uint32_t f;
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(&flag[i]) : "memory");
-                if (f == epoch) break;
-                __nanosleep(20);
-            }
-            const unsigned long long x = agg[i].segs, y = agg[i].items, z = agg[i].recs;
-            v5[2] += x, v5[3] += y, v5[4] += z;
-            if (i < b) v5[0] += x, v5[1] += y;
-        }
+    __syncthreads();
+    // 2. the last CTA turns the aggregates into exclusive prefixes (G <= SCAN_T: one per thread), writes the batch
+    //    totals and raises the flag; every CTA waits on that ONE flag with ONE thread
+    if (sh_last) {
+        __threadfence();
+        const bool in = (int)threadIdx.x < G;
+        const Plan mine = in ? Plan{agg[threadIdx.x].segs, agg[threadIdx.x].items} : Plan{0, 0};
+        unsigned long long r = in ? agg[threadIdx.x].recs : 0ull;
+        Plan all;
+        const Plan ex = block_exclusive<Plan>(mine, &all);
+        if (in) agg[threadIdx.x].segs = ex.segs, agg[threadIdx.x].items = ex.items;     // now: prefixes
 #pragma unroll
-        for (int k = 0; k < 5; ++k) {
-#pragma unroll
-            for (int d = 16; d; d >>= 1) v5[k] += __shfl_xor_sync(FULL, v5[k], d);
-        }
-        __syncthreads();                                    // red[] was read by thread 0 above
-        if (lane == 0) {
-#pragma unroll
-            for (int k = 0; k < 5; ++k) red5[k][wid] = v5[k];
-        }
+        for (int d = 16; d; d >>= 1) r += __shfl_xor_sync(FULL, r, d);
+        if (lane == 0) red[2][wid] = r;
         __syncthreads();
         if (threadIdx.x == 0) {
-            unsigned long long t5[5] = {0, 0, 0, 0, 0};
-            for (int w = 0; w < SCAN_T / 32; ++w)
-                for (int k = 0; k < 5; ++k) t5[k] += red5[k][w];
-            sh_prefix[0] = t5[0], sh_prefix[1] = t5[1], sh_total[0] = t5[2], sh_total[1] = t5[3], sh_total[2] = t5[4];
-            if (b == G - 1) {
-                tot[0] = t5[2], tot[1] = t5[3], tot[2] = t5[4];
-                tot[3] = cnt2[2 * T];                      // queries left to the M_ABN32 pipeline (M_PACKED only)
-            }
+            unsigned long long z = 0;
+            for (int w = 0; w < SCAN_T / 32; ++w) z += red[2][w];
+            tot[0] = all.segs, tot[1] = all.items, tot[2] = z;
+            tot[3] = cnt2[2 * T];                          // queries left to the M_ABN32 pipeline (M_PACKED only)
+            *ticket = 0;                                    // ready for the next launch
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
         }
+    }
+    if (threadIdx.x == 0) {
+        for (;;) {                                          // acquire: prefixes and totals are visible with the flag
+            uint32_t f;
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(flag) : "memory");
+            if (f == epoch) break;
+            __nanosleep(40);
+        }
+        sh_prefix[0] = agg[b].segs, sh_prefix[1] = agg[b].items;
+        const volatile unsigned long long *vt = tot;
+        sh_total[0] = vt[0], sh_total[1] = vt[1], sh_total[2] = vt[2];
     }
     __syncthreads();
     const unsigned long long nseg = sh_total[0], nit = sh_total[1];
@@ -868,11 +869,11 @@ int enqueue_count_t(igdb_dev *d, const igdb_dev::Pending &p)
     const int nb = (int)((p.n + CSEG_T * CSEG_Q - 1) / (CSEG_T * CSEG_Q));
     if (d->plan_grid == 0) {
         // k_plan's CTAs wait for each other, so all of them must be resident at once: never more than the
-        // occupancy calculator allows (and at most 4 per SM, the size of the flag arrays)
+        // occupancy calculator allows, and at most SCAN_T (the last CTA scans one aggregate per thread)
         int per_sm = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_plan, SCAN_T, 0));
         per_sm = std::max(1, std::min(per_sm, 4));
-        d->plan_grid = std::max(1, std::min(per_sm * d->sm_count, (d->T + SCAN_T - 1) / SCAN_T));
+        d->plan_grid = std::max(1, std::min({per_sm * d->sm_count, SCAN_T, (d->T + SCAN_T - 1) / SCAN_T}));
     }
     const bool stages = d->stage_timing && MODE != M_ABN32;
     if (stages) CK(cudaEventRecord(d->stage_ev[0], st));
@@ -880,7 +881,7 @@ int enqueue_count_t(igdb_dev *d, const igdb_dev::Pending &p)
     if (stages) CK(cudaEventRecord(d->stage_ev[1], st));
     // (the plan reads the later-bin counters that the scatter counts back down to zero)
     CK(launch_pdl(k_plan, d->plan_grid, SCAN_T, 0, st, db, d->cnt2, ++d->plan_epoch, d->plan_agg, d->plan_flag,
-                  d->cseg_off, d->cseg_mid, d->plan_tot, seg_cap, item_cap, d->items));
+                  d->plan_flag + 1, d->cseg_off, d->cseg_mid, d->plan_tot, seg_cap, item_cap, d->items));
     if (stages) CK(cudaEventRecord(d->stage_ev[2], st));
     CK(launch_pdl(k_cseg_scatter<V, MODE>, nb, thr, 0, st, db, p.n, p.ctg, p.qs, p.qe, d->cnt2, d->cseg_off,
                   d->cseg_mid, d->plan_tot, seg_cap, item_cap, (void *)d->csegs));
