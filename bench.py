@@ -315,7 +315,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": n_total / (ms_per_step * 1e-3), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16",
             "data": "synthetic",
             "overlaps_per_s": overlaps / (ms_per_step * 1e-3), "overlaps_per_step": overlaps,
             "config": {"workload": f"{args.workload}: {workloads.CONFIGS[args.workload]['n_files']} files x "
