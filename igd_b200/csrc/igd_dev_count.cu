@@ -542,8 +542,8 @@ constexpr int PK_IB = 8;                // items per block
 template <bool V>
 struct PackedSmem {
     static constexpr uint32_t ARR = GROUP * 2;                          // one 16-bit array of a stage
-    static constexpr uint32_t VOFF = 3 * ARR;                           // int32 value[GROUP] (-v only)
-    static constexpr uint32_t QOFF = VOFF + (V ? GROUP * 4 : 0);
+    static constexpr uint32_t VOFF = 3 * ARR;                           // 16-bit value[GROUP] (-v only)
+    static constexpr uint32_t QOFF = VOFF + (V ? ARR : 0);
     static constexpr uint32_t STAGE = QOFF + SMAX * 4;
     static constexpr uint32_t LIST = PK_K * STAGE;                      // survivor list: SMAX x {QS2, QE2}
     static constexpr uint32_t WARP = LIST + SMAX * 8;
@@ -630,9 +630,9 @@ __global__ void __launch_bounds__(PK_MAXW * 32, 1) k_count_packed(const CountArg
     };
     int4 dcur = load_desc(0), dnxt = load_desc(1);
     const uint16_t *const pS = db.ps + lane * 8, *const pE = db.pe + lane * 8, *const pF = db.pf + lane * 8;
-    const int32_t *const pV = db.value + lane * 8;
+    const uint16_t *const pV = db.pv + lane * 8;
     const uint32_t *const pQ = static_cast<const uint32_t *>(static_cast<const void *>(a.segs)) + lane;
-    const uint32_t lslot = wbase + lane * 16, vslot = wbase + L::VOFF + lane * 32, qslot = wbase + L::QOFF + lane * 4;
+    const uint32_t lslot = wbase + lane * 16, vslot = wbase + L::VOFF + lane * 16, qslot = wbase + L::QOFF + lane * 4;
 
     // The stages start out as pads: a lane without records in an item reads what an earlier item (or this fill)
     // left in its slots -- its counts are discarded, and the prune window only gets wider.
@@ -653,7 +653,6 @@ __global__ void __launch_bounds__(PK_MAXW * 32, 1) k_count_packed(const CountArg
             cp_async16(lslot + so + 2 * L::ARR, pF + p);
             if (V) {
                 cp_async16(vslot + so, pV + p);
-                cp_async16(vslot + so + 16, pV + p + 4);
             }
         }
         if (lane < ns) cp_async4(qslot + so, pQ + y);
@@ -689,12 +688,15 @@ __global__ void __launch_bounds__(PK_MAXW * 32, 1) k_count_packed(const CountArg
             const uint32_t E[4] = {(uint32_t)e_.x, (uint32_t)e_.y, (uint32_t)e_.z, (uint32_t)e_.w};
             const uint32_t F[4] = {(uint32_t)f_.x, (uint32_t)f_.y, (uint32_t)f_.z, (uint32_t)f_.w};
             if (V && have) {                                            // value < v: the record matches no query
-                const int4 v0 = lds128(vslot + so), v1 = lds128(vslot + so + 16);
-                const int vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                // pv = value' + 0x8000 with value' = clamp(value, 0, 32767), and 1 <= v <= 32767 on this path:
+                // bit 15 of a half of (pv2 - v2) is set  <=>  value' >= v  <=>  value >= v  (no half borrows)
+                const int4 pv_ = lds128(vslot + so);
+                const uint32_t pv2[4] = {(uint32_t)pv_.x, (uint32_t)pv_.y, (uint32_t)pv_.z, (uint32_t)pv_.w};
+                const uint32_t v2 = (uint32_t)a.v * 0x10001u;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    if (vv[2 * k] < a.v) S[k] = (S[k] & 0xffff0000u) | 0x8000u;
-                    if (vv[2 * k + 1] < a.v) S[k] = (S[k] & 0x0000ffffu) | 0x80000000u;
+                    const uint32_t keep = (((pv2[k] - v2) & 0x80008000u) >> 15) * 0xffffu;   // 0xffff per kept half
+                    S[k] = (S[k] & keep) | (0x80008000u & ~keep);
                 }
             }
             uint32_t c[4] = {0, 0, 0, 0};
@@ -945,7 +947,7 @@ int settle_count(igdb_dev *d, const igdb_dev::Pending &p)
             nitems <= (unsigned long long)std::min<int64_t>(d->item_cap - CAP_SLACK, lim)) {
             if (p.mode != M_ABN32) {
                 // what the search kernel of this batch reads: descriptors, records, segments
-                const int64_t rb = pk ? (p.mode_v ? 10 : 6) : (p.mode_v ? 16 : 12), sgb = pk ? 4 : 8;
+                const int64_t rb = pk ? (p.mode_v ? 8 : 6) : (p.mode_v ? 16 : 12), sgb = pk ? 4 : 8;
                 d->last_plan[0] = (int64_t)nsegs, d->last_plan[1] = (int64_t)nitems, d->last_plan[2] = (int64_t)nrec;
                 d->last_plan[3] = 16 * (int64_t)nitems + rb * (int64_t)nrec + sgb * (int64_t)nsegs;
             }
@@ -978,6 +980,12 @@ int settle_count(igdb_dev *d, const igdb_dev::Pending &p)
 }
 
 }  // namespace
+
+int igdb::count_mode_for(const igdb_dev *d, bool mode_v, int32_t v)
+{
+    // the packed layout holds value clamped to [0, 32767]: exact for the thresholds 1 .. 32767 only
+    return d->packed && (!mode_v || (v >= 1 && v <= 32767)) ? M_PACKED : M_ALL32;
+}
 
 int igdb::finish_pending(igdb_dev *d)
 {
@@ -1028,7 +1036,7 @@ int igdb_dev_count_device(igdb_dev *d, int64_t n, const int32_t *d_ctg, const in
         p.mode_v = mode_v != 0, p.n = std::min(BATCH, n - a);
         p.ctg = d_ctg + a, p.qs = d_qs + a, p.qe = d_qe + a, p.v = v;
         p.hits = (unsigned long long *)d_hits, p.st = st;
-        p.mode = d->packed ? M_PACKED : M_ALL32;
+        p.mode = count_mode_for(d, p.mode_v, p.v);
         if (enqueue_count(d, p)) return -1;
         if (a + BATCH < n) {                        // the scratch buffers are reused by the next chunk
             if (settle_count(d, p)) return -1;
@@ -1068,7 +1076,7 @@ int igdb_dev_count_host(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_
         igdb_dev::Pending p;
         p.mode_v = mode_v != 0, p.n = m, p.ctg = d->q_ctg, p.qs = d->q_qs, p.qe = d->q_qe, p.v = v;
         p.hits = d->d_hits, p.st = st;
-        p.mode = d->packed ? M_PACKED : M_ALL32;
+        p.mode = count_mode_for(d, p.mode_v, p.v);
         if (enqueue_count(d, p)) return -1;
         const bool last = a + BATCH >= n;
         if (last) {                                 // the result copy rides behind the kernels; no sync yet

@@ -15,7 +15,7 @@ __global__ void k_transpose(const int4 *__restrict__ aos, int64_t rec0, int64_t 
                             const int64_t *__restrict__ toff, int32_t T, const TileMeta *__restrict__ tiles,
                             int32_t *__restrict__ start, int32_t *__restrict__ end, int32_t *__restrict__ idx,
                             int32_t *__restrict__ value, int32_t nbp, uint16_t *__restrict__ ps,
-                            uint16_t *__restrict__ pe, uint16_t *__restrict__ pf)
+                            uint16_t *__restrict__ pe, uint16_t *__restrict__ pf, uint16_t *__restrict__ pv)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nrec) return;
@@ -33,6 +33,7 @@ __global__ void k_transpose(const int4 *__restrict__ aos, int64_t rec0, int64_t 
         ps[dst] = (uint16_t)(pk_rel(r.y, bd, nbp) + 1);
         pe[dst] = (uint16_t)(pk_rel_end(r.z, bd, nbp) + 0x8000);
         pf[dst] = (uint16_t)r.x;
+        pv[dst] = (uint16_t)(min(max(r.w, 0), 32767) + 0x8000);
     }
 }
 
@@ -114,7 +115,7 @@ void igdb_dev_destroy(igdb_dev *d)
     void *ptrs[] = {d->tiles, d->d_toff, d->start, d->end, d->idx, d->value, d->tbase, d->d_stage, d->q_ctg,
                     d->q_qs, d->q_qe, d->tile_cnt, d->tile_off, d->nseg, d->qseg_off, d->bsum, d->segs,
                     d->seg_hits, d->seg_out_off, d->d_hits, d->cnt2, d->cseg_off, d->cseg_mid,
-                    d->plan_agg, d->plan_flag, d->plan_tot, d->csegs, d->items, d->ps, d->pe, d->pf,
+                    d->plan_agg, d->plan_flag, d->plan_tot, d->csegs, d->items, d->ps, d->pe, d->pf, d->pv,
                     d->ctg_names, d->ctg_slots, d->d_text};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -187,7 +188,7 @@ static int create_impl(igdb_dev *d, const int32_t *ntile, const int32_t *ncnt)
     // packed count-mode copies: tile-relative coordinates need nbp + 1 < 2^15, file indices 16 bits
     d->packed = d->nbp <= 16384 && d->nfiles <= 65536 && !getenv("IGD_B200_NO_PACKED");
     if (d->packed && (dev_alloc(d, &d->ps, (size_t)d->P + 8) || dev_alloc(d, &d->pe, (size_t)d->P + 8) ||
-                      dev_alloc(d, &d->pf, (size_t)d->P + 8)))
+                      dev_alloc(d, &d->pf, (size_t)d->P + 8) || dev_alloc(d, &d->pv, (size_t)d->P + 8)))
         return -1;
     CK(cudaMemcpy(d->tiles, meta.data(), meta.size() * sizeof(TileMeta), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d->d_toff, d->toff.data(), d->toff.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
@@ -201,6 +202,7 @@ static int create_impl(igdb_dev *d, const int32_t *ntile, const int32_t *ncnt)
         k_fill16<<<fb, 256>>>(d->ps, (int64_t)d->P + 8, (uint16_t)0x8000);
         k_fill16<<<fb, 256>>>(d->pe, (int64_t)d->P + 8, (uint16_t)0x8000);
         CK(cudaMemset(d->pf, 0, ((size_t)d->P + 8) * 2));
+        k_fill16<<<fb, 256>>>(d->pv, (int64_t)d->P + 8, (uint16_t)0x8000);
     }
     CK(cudaGetLastError());
     CK(cudaMemset(d->idx, 0, ((size_t)d->P + 8) * 4));
@@ -266,7 +268,7 @@ int igdb_dev_upload(igdb_dev *d, int64_t rec0, int64_t nrec, const void *aos)
     const int thr = 256;
     k_transpose<<<(unsigned)((nrec + thr - 1) / thr), thr, 0, d->stream>>>(
         (const int4 *)d->d_stage, rec0, nrec, d->d_toff, d->T, d->tiles, d->start, d->end, d->idx, d->value, d->nbp,
-        d->ps, d->pe, d->pf);
+        d->ps, d->pe, d->pf, d->pv);
     d->launches += 1;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(d->stream));       // the caller reuses its host buffer

@@ -18,7 +18,9 @@
 //                       visits this tile can make (see k_count_packed) -- and stored pre-biased,
 //                       ps = start' + 1, pe = end' + 0x8000, so that two records are compared with one
 //                       32-bit subtraction per predicate (bit 15 of each half is the answer).
-//                       pf = file index.  Pads: ps = 0x8000 (starts after every query end), pe = 0x8000.
+//                       pf = file index, pv = clamp(value, 0, 32767) + 0x8000 (exact for the -v thresholds
+//                       1 .. 32767; any other threshold runs on the int32 arrays).
+//                       Pads: ps = 0x8000 (starts after every query end), pe = 0x8000.
 //   tbase[nctg+1]     global tile index of each contig's tile 0.
 //
 // Query batches are turned into (query, tile) SEGMENTS -- one per non-empty, non-gated tile the reference
@@ -72,7 +74,7 @@ static_assert(sizeof(TileMeta) == 16, "TileMeta must be one int4");
 struct DbView {
     const TileMeta *tiles;
     const int32_t *start, *end, *idx, *value;
-    const uint16_t *ps, *pe, *pf;           // packed tile-relative copies for count mode (may be NULL)
+    const uint16_t *ps, *pe, *pf, *pv;      // packed tile-relative copies for count mode (may be NULL)
     const int32_t *tbase;
     int32_t nctg, nbp, nfiles, ntiles;
 };
@@ -272,7 +274,7 @@ struct igdb_dev {
     TileMeta *tiles = nullptr;
     int64_t *d_toff = nullptr;
     int32_t *start = nullptr, *end = nullptr, *idx = nullptr, *value = nullptr, *tbase = nullptr;
-    uint16_t *ps = nullptr, *pe = nullptr, *pf = nullptr;  // packed count-mode copies (NULL: M_ALL32 only)
+    uint16_t *ps = nullptr, *pe = nullptr, *pf = nullptr, *pv = nullptr;   // packed count-mode copies (NULL: M_ALL32 only)
     char *ctg_names = nullptr;              // [nctg][40] contig names (device), for the text ingest
     int32_t *ctg_slots = nullptr;           // hash table over them
     uint32_t ctg_mask = 0;
@@ -336,7 +338,7 @@ struct igdb_dev {
     {
         DbView v;
         v.tiles = tiles, v.start = start, v.end = end, v.idx = idx, v.value = value, v.tbase = tbase;
-        v.ps = ps, v.pe = pe, v.pf = pf;
+        v.ps = ps, v.pe = pe, v.pf = pf, v.pv = pv;
         v.nctg = nctg, v.nbp = nbp, v.nfiles = nfiles, v.ntiles = T;
         return v;
     }
@@ -407,6 +409,7 @@ int upload_queries(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_t *qs
                    cudaStream_t st);                                               // igd_dev_image.cu
 int enqueue_count(igdb_dev *d, const igdb_dev::Pending &p);                        // igd_dev_count.cu
 int finish_pending(igdb_dev *d);                                                   // igd_dev_count.cu
+int count_mode_for(const igdb_dev *d, bool mode_v, int32_t v);                     // igd_dev_count.cu
 int64_t full_device(igdb_dev *d, int64_t n, cudaStream_t st, bool with_g, DevBuf &qoff, DevBuf &out);   // igd_dev_full.cu
 
 }  // namespace igdb

@@ -175,7 +175,7 @@ int igdb_dev_count_text(igdb_dev *d, const char *text, size_t len, int mode_v, i
     igdb_dev::Pending p;
     p.mode_v = mode_v != 0, p.n = n, p.ctg = d->q_ctg, p.qs = d->q_qs, p.qe = d->q_qe, p.v = v;
     p.hits = d->d_hits, p.st = st;
-    p.mode = d->packed ? M_PACKED : M_ALL32;
+    p.mode = count_mode_for(d, p.mode_v, p.v);
     if (enqueue_count(d, p)) return -1;
     p.active = true;
     d->pending = p;

@@ -141,7 +141,7 @@ void igd_b200_stage_timing(igd_b200_t *h, int on);
 int igd_b200_last_stage_ms(igd_b200_t *h, float t[4]);
 /* plan of the last settled count batch: out[0] (query, tile) segments, out[1] work items, out[2] records the
  * items read (each touched tile once per 64 of its segments), out[3] the bytes the search kernel had to read
- * for them: 16*items + 6*records (10 with -v) + 4*segments on the packed 16-bit layout,
+ * for them: 16*items + 6*records (8 with -v) + 4*segments on the packed 16-bit layout,
  * 16*items + 12*records (16 with -v) + 8*segments on the int32 layout */
 void igd_b200_last_plan(const igd_b200_t *h, int64_t out[4]);
 /* kernel launches issued by this handle since open (for bench.py's gpu_launches) */

@@ -267,3 +267,27 @@ def test_count_many_files(workdir, O, api, n_files):
         got, _ = g.count(q.ctg, q.start, q.end, v)
         assert want.sum() > 0 and np.array_equal(got, want)
     g.close()
+
+
+def test_count_v_thresholds_and_negative_values(workdir, O, api):
+    """-v on the packed path keeps value clamped to [0, 32767] in 16 bits: thresholds inside 1 .. 32767 take it,
+    thresholds outside (and get_overlaps_v's v <= 0 through the reference-named entry point) take the int32
+    arrays; values below 0 and above 32767 are in the database."""
+    stem = os.path.join(workdir, "vals")
+    rng = np.random.default_rng(77)
+    files = []
+    for i in range(12):
+        iv = synth.gen_intervals(6000 + i, 3000, ("lognormal", 6.5, 1.2), SMALL_SIZES)
+        val = rng.choice(np.array([-500, -1, 0, 1, 499, 500, 501, 32766, 32767, 32768, 40000, 2_000_000_000], np.int32),
+                         len(iv))
+        files.append(synth.Intervals(iv.ctg, iv.start, iv.end, val.astype(np.int32)))
+    synth.write_igd_direct(stem, files, names=SMALL_NAMES)
+    q = make_queries(8, 8000, ("lognormal", 7.0, 1.3))
+    odb, g = O.OracleDB(stem + ".igd"), api.IGD(stem + ".igd")
+    for v in (1, 2, 500, 501, 32766, 32767, 32768, 40001, 2_000_000_000):
+        want, _ = odb.count(q.ctg, q.start, q.end, v)
+        got, n = g.count(q.ctg, q.start, q.end, v)
+        assert np.array_equal(got, want), v
+        assert n == want.sum()
+    assert odb.count(q.ctg, q.start, q.end, 32767)[0].sum() > 0
+    g.close()
