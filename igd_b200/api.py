@@ -115,6 +115,10 @@ def load_library():
     L.getOverlaps.argtypes = [C.c_char_p, _i64p]
     L.getOverlaps_v.restype = C.c_int64
     L.getOverlaps_v.argtypes = [C.c_char_p, _i64p, C.c_int32]
+    L.get_overlaps0.restype = C.c_int32
+    L.get_overlaps0.argtypes = [C.c_char_p, C.c_int32, C.c_int32, _i64p]
+    L.getOverlaps0.restype = C.c_int64
+    L.getOverlaps0.argtypes = [C.c_char_p, _i64p]
     L.getMap.restype = C.c_int64
     L.getMap_v.restype = C.c_int64
     L.seqOverlaps.argtypes = [C.c_char_p, _f64p]
@@ -166,6 +170,7 @@ class IGD:
         self.nfiles = L.igd_b200_nfiles(h)
         self.nctg = L.igd_b200_nctg(h)
         self.nbp = L.igd_b200_nbp(h)
+        self.gtype = L.igd_b200_gtype(h)
         self.ntiles = L.igd_b200_ntiles(h)
         self.nrecords = L.igd_b200_nrecords(h)
         self.ctg_names = [L.igd_b200_ctg_name(h, c).decode(errors="replace") for c in range(self.nctg)]

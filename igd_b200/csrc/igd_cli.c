@@ -88,6 +88,10 @@ int64_t getOverlaps_f1(char *qFile)
     return total;
 }
 
+/* gType-0 twins (src/igd_search.c:103-208, 232-250): identical output over gdata0_t records */
+int32_t get_overlaps_f0(char *chrm, int32_t qs, int32_t qe) { return get_overlaps_f1(chrm, qs, qe); }
+int64_t getOverlaps_f0(char *qFile) { return getOverlaps_f1(qFile); }
+
 void seqOverlaps(char *qFile, double *sm)
 {
     igd_b200_t *h = igd_b200_current();

@@ -18,8 +18,9 @@ const char *igdb_dev_error(void);       /* thread-local message of the last CUDA
  * (reference layout: src/igd_base.c:408-419). */
 igdb_dev *igdb_dev_create(int device, int32_t nbp, int32_t nctg, const int32_t *ntile,
                           const int32_t *ncnt, int32_t nfiles);
-/* stream a run of on-disk gdata_t records [rec0, rec0+nrec) (AoS, 16 B each) into the SoA image */
-int igdb_dev_upload(igdb_dev *d, int64_t rec0, int64_t nrec, const void *aos);
+/* stream a run of on-disk records [rec0, rec0+nrec) (AoS) into the SoA image: rec_words = 4 for gdata_t
+ * (16 B, gType 1), 3 for gdata0_t (12 B, gType 0; the image's value column reads 0) */
+int igdb_dev_upload(igdb_dev *d, int64_t rec0, int64_t nrec, const void *aos, int rec_words);
 /* after the last upload: per-tile dedupe start (tS) and first start */
 int igdb_dev_finalize(igdb_dev *d);
 void igdb_dev_destroy(igdb_dev *d);

@@ -10,8 +10,10 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 // upload
 // ------------------------------------------------------------------------------------------------
-// AoS gdata_t {idx,start,end,value} -> padded SoA.  toff[T+1] = unpadded record prefix (file order).
-__global__ void k_transpose(const int4 *__restrict__ aos, int64_t rec0, int64_t nrec,
+// AoS gdata_t {idx,start,end,value} (W = 4, src/igd_base.h:41-46) or gdata0_t {idx,start,end} (W = 3, :48-52:
+// gType-0 databases, value reads as 0) -> padded SoA.  toff[T+1] = unpadded record prefix (file order).
+template <int W>
+__global__ void k_transpose(const int32_t *__restrict__ aos, int64_t rec0, int64_t nrec,
                             const int64_t *__restrict__ toff, int32_t T, const TileMeta *__restrict__ tiles,
                             int32_t *__restrict__ start, int32_t *__restrict__ end, int32_t *__restrict__ idx,
                             int32_t *__restrict__ value, int32_t nbp, uint16_t *__restrict__ ps,
@@ -25,7 +27,9 @@ __global__ void k_transpose(const int4 *__restrict__ aos, int64_t rec0, int64_t 
         int32_t mid = (lo + hi) >> 1;
         if (__ldg(&toff[mid]) <= g) lo = mid; else hi = mid;
     }
-    int4 r = __ldg(&aos[i]);
+    int4 r;
+    if (W == 4) r = __ldg(reinterpret_cast<const int4 *>(aos) + i);
+    else r = make_int4(__ldg(&aos[3 * i]), __ldg(&aos[3 * i + 1]), __ldg(&aos[3 * i + 2]), 0);
     int64_t dst = (int64_t)tiles[lo].off8 * 8 + (g - __ldg(&toff[lo]));
     idx[dst] = r.x, start[dst] = r.y, end[dst] = r.z, value[dst] = r.w;
     if (ps) {                                   // tiles[].ts still holds the bin boundary here (k_tile_meta)
@@ -253,11 +257,15 @@ void *igdb_dev_pinned(igdb_dev *d, size_t bytes)
     return d->pinned;
 }
 
-int igdb_dev_upload(igdb_dev *d, int64_t rec0, int64_t nrec, const void *aos)
+int igdb_dev_upload(igdb_dev *d, int64_t rec0, int64_t nrec, const void *aos, int rec_words)
 {
     if (nrec <= 0) return 0;
+    if (rec_words != 3 && rec_words != 4) {
+        snprintf(g_err, sizeof g_err, "upload: records of %d words (gdata_t = 4, gdata0_t = 3)", rec_words);
+        return -1;
+    }
     CK(cudaSetDevice(d->device));
-    const size_t bytes = (size_t)nrec * 16;
+    const size_t bytes = (size_t)nrec * 4 * (size_t)rec_words;
     if (bytes > d->d_stage_cap) {
         if (d->d_stage) CK(cudaFree(d->d_stage));
         d->d_stage = nullptr;
@@ -266,9 +274,10 @@ int igdb_dev_upload(igdb_dev *d, int64_t rec0, int64_t nrec, const void *aos)
     }
     CK(cudaMemcpyAsync(d->d_stage, aos, bytes, cudaMemcpyHostToDevice, d->stream));
     const int thr = 256;
-    k_transpose<<<(unsigned)((nrec + thr - 1) / thr), thr, 0, d->stream>>>(
-        (const int4 *)d->d_stage, rec0, nrec, d->d_toff, d->T, d->tiles, d->start, d->end, d->idx, d->value, d->nbp,
-        d->ps, d->pe, d->pf, d->pv);
+    auto kern = rec_words == 4 ? k_transpose<4> : k_transpose<3>;
+    kern<<<(unsigned)((nrec + thr - 1) / thr), thr, 0, d->stream>>>(
+        (const int32_t *)d->d_stage, rec0, nrec, d->d_toff, d->T, d->tiles, d->start, d->end, d->idx, d->value,
+        d->nbp, d->ps, d->pe, d->pf, d->pv);
     d->launches += 1;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(d->stream));       // the caller reuses its host buffer

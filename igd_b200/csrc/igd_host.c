@@ -84,7 +84,9 @@ igd_b200_t *igd_b200_open(const char *igd_path, int device)
     int32_t hd[3];
     if (fread(hd, 4, 3, f) != 3) { set_err("%s: truncated header", igd_path); goto fail; }
     h->nbp = hd[0], h->gtype = hd[1], h->nctg = hd[2];
-    if (h->gtype != 1) { set_err("%s: only gType 1 (gdata_t) databases are supported", igd_path); goto fail; }
+    /* gType 1 = gdata_t records (16 B), gType 0 = gdata0_t (12 B, no value; `igd create -s 0`,
+     * src/igd_create.c:245-332, record size chosen as in get_igdinfo src/igd_base.c:279-283) */
+    if (h->gtype != 0 && h->gtype != 1) { set_err("%s: unknown gType (0 and 1 are supported)", igd_path); goto fail; }
     if (h->nbp <= 0 || h->nctg < 0) { set_err("%s: corrupt header", igd_path); goto fail; }
     int32_t m = h->nctg;
     h->ntile = malloc(sizeof(int32_t) * (size_t)(m + 1));
@@ -121,18 +123,19 @@ igd_b200_t *igd_b200_open(const char *igd_path, int device)
     if (igdb_dev_set_contigs(h->dev, (const char *)h->cname)) goto fail;
     {
         const int64_t CH = 4 << 20;                     /* records per chunk: 64 MiB */
+        const int W = h->gtype == 0 ? 3 : 4;            /* 32-bit words per record */
         int64_t chunk = h->nrec < CH ? h->nrec : CH;
         char *buf = chunk ? igdb_dev_pinned(h->dev, (size_t)chunk * 16) : NULL;
         if (chunk && !buf) { set_err("%s: cannot allocate the pinned upload buffer", igd_path); goto fail; }
         for (int64_t r = 0; r < h->nrec; r += chunk) {
             int64_t k = h->nrec - r < chunk ? h->nrec - r : chunk;
-            if (fread(buf, 16, (size_t)k, f) != (size_t)k) { set_err("%s: truncated tile data", igd_path); goto fail; }
+            if (fread(buf, 4 * (size_t)W, (size_t)k, f) != (size_t)k) { set_err("%s: truncated tile data", igd_path); goto fail; }
             /* file indices index hits[]: reject records the reference would write out of bounds with */
             for (int64_t i = 0; i < k; i++) {
-                int32_t idx = ((int32_t *)buf)[4 * i];
+                int32_t idx = ((int32_t *)buf)[W * i];
                 if (idx < 0 || idx >= h->nfiles) { set_err("%s: record with file index outside _index.tsv", igd_path); goto fail; }
             }
-            if (igdb_dev_upload(h->dev, r, k, buf)) goto fail;
+            if (igdb_dev_upload(h->dev, r, k, buf, W)) goto fail;
         }
         if (igdb_dev_finalize(h->dev)) goto fail;
     }
@@ -201,18 +204,21 @@ static int64_t count_mode(igd_b200_t *h, int64_t n, const int32_t *ctg, const in
 }
 
 /* the CLI's dispatch: the signal filter (and get_overlaps_v's control flow) only when v > 0
- * (src/igd_search.c:1027,1045) */
+ * (src/igd_search.c:1027,1045), and never on a gType-0 database, whose records have no value: the reference
+ * calls getOverlaps0 / get_overlaps0 there whatever -v says (:1024-1025, :1042-1043) */
+static int filter_on(const igd_b200_t *h, int32_t v) { return v > 0 && h->gtype != 0; }
+
 int64_t igd_b200_count(igd_b200_t *h, int64_t n, const int32_t *ctg, const int32_t *qs, const int32_t *qe,
                        int32_t v, int64_t *hits)
 {
-    return count_mode(h, n, ctg, qs, qe, v > 0, v, hits);
+    return count_mode(h, n, ctg, qs, qe, filter_on(h, v), v, hits);
 }
 
 int igd_b200_count_device(igd_b200_t *h, int64_t n, const int32_t *d_ctg, const int32_t *d_qs,
                           const int32_t *d_qe, int32_t v, uint64_t *d_hits, void *stream)
 {
     g_err[0] = 0;
-    return igdb_dev_count_device(h->dev, n, d_ctg, d_qs, d_qe, v > 0, v, d_hits, stream);
+    return igdb_dev_count_device(h->dev, n, d_ctg, d_qs, d_qe, filter_on(h, v), v, d_hits, stream);
 }
 
 int igd_b200_count_device_finish(igd_b200_t *h)
@@ -452,7 +458,7 @@ out:
 
 int64_t search(igd_b200_t *h, const char *qFile, int32_t v, int64_t *hits)
 {
-    return search_mode(h, qFile, v > 0, v, hits);
+    return search_mode(h, qFile, filter_on(h, v), v, hits);
 }
 
 /* ---- (2) reference-named entry points over the current handle ---------------------------------------- */
@@ -491,6 +497,11 @@ int64_t getOverlaps_v(char *qFile, int64_t *hits, int32_t v)
     int64_t r = search_mode(g_current, qFile, 1, v, hits);
     return r < 0 ? 0 : r;
 }
+
+/* gType-0 twins (src/igd_search.c:30-101, 210-230): the same control flow over gdata0_t records.  The handle
+ * knows its record type, so they are the same searches; like the reference's they return 0. */
+int32_t get_overlaps0(char *chrm, int32_t qs, int32_t qe, int64_t *hits) { return get_overlaps(chrm, qs, qe, hits); }
+int64_t getOverlaps0(char *qFile, int64_t *hits) { return getOverlaps(qFile, hits); }
 
 int64_t getMap(uint32_t **hitmap) { return getMap_v(hitmap, 0); }
 

@@ -182,8 +182,9 @@ def _expand_sort(crank, start, end, nbp, m, use_cuda=None):
 def write_igd_direct(stem: str, files: list[Intervals] | None = None, *, nbp: int = 16384,
                      names=HG38_NAMES, file_names: list[str] | None = None,
                      gen=None, n_files: int | None = None, ctg_order: list[int] | None = None,
-                     use_cuda: bool | None = None) -> dict:
-    """Write ``stem + '.igd'`` and ``stem + '_index.tsv'``.
+                     use_cuda: bool | None = None, gtype: int = 1) -> dict:
+    """Write ``stem + '.igd'`` and ``stem + '_index.tsv'``.  ``gtype`` 1 writes gdata_t records (16 B), 0 the
+    value-less gdata0_t records of ``igd create -s 0`` (12 B, /root/reference/src/igd_base.h:48-52).
 
     ``files`` is a list of per-file interval bags, or pass ``gen(i) -> Intervals`` with ``n_files``.
     Layout follows /root/reference/src/igd_base.c:408-458 (header, nTile[], nCnt[][], 40-byte names,
@@ -221,14 +222,17 @@ def write_igd_direct(stem: str, files: list[Intervals] | None = None, *, nbp: in
 
     rep, ncnt, ntile, total_tiles = _expand_sort(rank[ctg], start, end, nbp, m, use_cuda)
 
-    rec = np.empty((rep.shape[0], 4), dtype=np.int32)   # gdata_t {idx,start,end,value} igd_base.h:41-46
+    assert gtype in (0, 1)
+    W = 4 if gtype == 1 else 3
+    rec = np.empty((rep.shape[0], W), dtype=np.int32)   # gdata_t {idx,start,end,value} igd_base.h:41-46
     rec[:, 0] = fidx[rep]
     rec[:, 1] = start[rep]
     rec[:, 2] = end[rep]
-    rec[:, 3] = value[rep]
+    if gtype == 1:
+        rec[:, 3] = value[rep]
 
     with open(stem + ".igd", "wb") as f:
-        np.array([nbp, 1, m], dtype=np.int32).tofile(f)
+        np.array([nbp, gtype, m], dtype=np.int32).tofile(f)
         ntile.tofile(f)
         ncnt.tofile(f)
         for c in ctg_order:
@@ -239,4 +243,4 @@ def write_igd_direct(stem: str, files: list[Intervals] | None = None, *, nbp: in
         for i in range(n_files):
             f.write("%i\t%s\t%i\t%f\n" % (i, file_names[i], nr[i], avg[i]))
     return {"n_files": n_files, "n_intervals": int(nr.sum()), "n_records": int(rec.shape[0]),
-            "n_tiles": total_tiles, "n_ctg": m, "bytes": 12 + 44 * m + 4 * total_tiles + 16 * int(rec.shape[0])}
+            "n_tiles": total_tiles, "n_ctg": m, "bytes": 12 + 44 * m + 4 * total_tiles + 4 * W * int(rec.shape[0])}

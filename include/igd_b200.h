@@ -25,7 +25,9 @@ typedef struct igd_b200 igd_b200_t;          /* replaces iGD_t*, IGDr/src/igd_ba
 
 /* open_iGD (IGDr/src/igd_base.h:97) + get_igdinfo/get_fileinfo (src/igd_base.c:269-323, 235-267):
  * parses <db>.igd and <db>_index.tsv and uploads every tile into the HBM of CUDA device `device`
- * (CSR of tile offsets + SoA start/end/idx/value).  NULL on failure. */
+ * (CSR of tile offsets + SoA start/end/idx/value).  Both record types are read: gType 1 (gdata_t, 16 B) and
+ * gType 0 (gdata0_t, 12 B: no value -- -v is ignored in count mode exactly as igd_search does,
+ * src/igd_search.c:1024,1042, and the value column reads 0 everywhere else).  NULL on failure. */
 igd_b200_t *igd_b200_open(const char *igd_path, int device);
 /* close_iGD (IGDr/src/igd_base.h:124) */
 void igd_b200_close(igd_b200_t *h);
@@ -164,6 +166,11 @@ int64_t getMap_v(uint32_t **hitmap, int32_t v);                                 
 int32_t get_overlaps_f1(char *chrm, int32_t qs, int32_t qe);                          /* igd_search.h:36 */
 int64_t getOverlaps_f1(char *qFile);                                                  /* igd_search.h:38 */
 void seqOverlaps(char *qFile, double *sm);                                            /* igd_search.h:20 */
+/* the gType-0 (gdata0_t, `igd create -s 0`) twins: same searches, the handle knows its record type */
+int32_t get_overlaps0(char *chrm, int32_t qs, int32_t qe, int64_t *hits);             /* igd_search.h:15 */
+int64_t getOverlaps0(char *qFile, int64_t *hits);                                     /* igd_search.h:16 */
+int32_t get_overlaps_f0(char *chrm, int32_t qs, int32_t qe);                          /* igd_search.h:35 */
+int64_t getOverlaps_f0(char *qFile);                                                  /* igd_search.h:37 */
 int igd_search(int argc, char **argv);                                                /* igd_search.h:41 */
 
 #ifdef __cplusplus

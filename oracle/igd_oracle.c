@@ -32,7 +32,9 @@ orc_db *orc_open(const char *path)
     int32_t h[3];
     if (fread(h, 4, 3, f) != 3) goto fail;
     db->nbp = h[0], db->gtype = h[1], db->nctg = h[2];
-    if (db->gtype != 1 || db->nctg <= 0 || db->nbp <= 0) goto fail;      /* gdata_t databases only */
+    /* gType 1 = gdata_t (16 B), gType 0 = gdata0_t (12 B, src/igd_base.h:48-52); record size as in
+     * get_igdinfo, src/igd_base.c:279-283 */
+    if ((db->gtype != 0 && db->gtype != 1) || db->nctg <= 0 || db->nbp <= 0) goto fail;
     int32_t m = db->nctg;
     db->ntile = malloc(4 * (size_t)m);
     if (fread(db->ntile, 4, m, f) != (size_t)m) goto fail;
@@ -49,7 +51,15 @@ orc_db *orc_open(const char *path)
     for (int64_t t = 0; t < T; t++) db->toff[t + 1] = db->toff[t] + db->ncnt[t];
     db->nrec = db->toff[T];
     db->rec = malloc(sizeof(rec_t) * (size_t)db->nrec + 16);
-    if (db->nrec && fread(db->rec, sizeof(rec_t), db->nrec, f) != (size_t)db->nrec) goto fail;
+    if (db->gtype == 1) {
+        if (db->nrec && fread(db->rec, sizeof(rec_t), db->nrec, f) != (size_t)db->nrec) goto fail;
+    } else {                                /* gdata0_t {idx,start,end}: kept as rec_t with value 0 */
+        for (int64_t i = 0; i < db->nrec; i++) {
+            int32_t r3[3];
+            if (fread(r3, 4, 3, f) != 3) goto fail;
+            db->rec[i].idx = r3[0], db->rec[i].start = r3[1], db->rec[i].end = r3[2], db->rec[i].value = 0;
+        }
+    }
     fclose(f);
     f = NULL;
 
@@ -297,7 +307,9 @@ static void hit_count(void *ctx, int64_t q, int32_t n1, int32_t i, const rec_t *
 int64_t orc_count(const orc_db *db, int64_t n, const int32_t *ctg, const int32_t *qs, const int32_t *qe,
                   int32_t v, int64_t *hits, orc_stats *st)
 {
-    int mode_v = v > 0;                     /* igd_search dispatches on v>0, src/igd_search.c:1027,1045 */
+    /* igd_search dispatches on v>0 (src/igd_search.c:1027,1045) -- and on a gType-0 database on nothing:
+     * getOverlaps0 / get_overlaps0 (:30-101, same control flow as get_overlaps) whatever -v says (:1024,:1042) */
+    int mode_v = v > 0 && db->gtype != 0;
     uint8_t *seen = st ? calloc(db->tbase[db->nctg] + 1, 1) : NULL;
     int64_t ret = 0;
     for (int64_t q = 0; q < n; q++) {

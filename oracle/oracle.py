@@ -124,6 +124,7 @@ class OracleDB:
         self.nctg = self.L.orc_nctg(self.h)
         self.nbp = self.L.orc_nbp(self.h)
         self.nrecords = self.L.orc_nrecords(self.h)
+        self.gtype = self.L.orc_gtype(self.h)
         self.ctg_names = [self.L.orc_ctg_name(self.h, c).decode(errors="replace") for c in range(self.nctg)]
         self.ntile = [self.L.orc_ntile(self.h, c) for c in range(self.nctg)]
         self.file_names = [self.L.orc_file_name(self.h, i).decode() for i in range(self.nfiles)]
@@ -217,12 +218,19 @@ class RefLib:
         self.L.seqOverlaps.argtypes = [C.c_char_p, _f64p]
         self.L.ref_getmap_dense.restype = C.c_int64
         self.L.ref_getmap_dense.argtypes = [_u32p, C.c_int32]
+        self.L.getOverlaps0.restype = C.c_int64
+        self.L.getOverlaps0.argtypes = [C.c_char_p, _i64p]
+        self.L.get_overlaps0.restype = C.c_int32
+        self.L.get_overlaps0.argtypes = [C.c_char_p, C.c_int32, C.c_int32, _i64p]
+        self.gtype = self.L.ref_gtype()
 
     def close(self):
         self.L.ref_close()
 
     def count_file(self, qfile: str, v: int = 0):
         hits = np.zeros(self.nfiles, np.int64)
+        if self.gtype == 0:         # igd_search's dispatch, src/igd_search.c:1024-1025: -v is not looked at
+            return hits, self.L.getOverlaps0(qfile.encode(), hits)
         ret = self.L.getOverlaps_v(qfile.encode(), hits, v) if v > 0 else self.L.getOverlaps(qfile.encode(), hits)
         return hits, ret
 
@@ -230,6 +238,8 @@ class RefLib:
         if hits is None:
             hits = np.zeros(self.nfiles, np.int64)
         b = C.create_string_buffer(chrm.encode())
+        if self.gtype == 0:         # src/igd_search.c:1042-1043
+            return hits, self.L.get_overlaps0(b, qs, qe, hits)
         ret = (self.L.get_overlaps_v(b, qs, qe, v, hits) if v > 0 else self.L.get_overlaps(b, qs, qe, hits))
         return hits, ret
 
@@ -262,13 +272,15 @@ def ref_cli(args: list[str], cwd: str | None = None) -> str:
     return r.stdout.decode(errors="replace")
 
 
-def ref_create(bed_dir: str, out_dir: str, name: str, b: int = 14) -> str:
+def ref_create(bed_dir: str, out_dir: str, name: str, b: int = 14, gtype: int = 1) -> str:
+    """the reference's own `igd create` (gtype 0: `-s 0`, gdata0_t records)"""
     os.makedirs(out_dir, exist_ok=True)
     if not bed_dir.endswith("/"):
         bed_dir += "/"
     if not out_dir.endswith("/"):
         out_dir += "/"
-    subprocess.run([REF_BIN, "create", bed_dir, out_dir, name, "-b", str(b)], check=True, capture_output=True)
+    subprocess.run([REF_BIN, "create", bed_dir, out_dir, name, "-b", str(b)] + (["-s", "0"] if gtype == 0 else []),
+                   check=True, capture_output=True)
     return os.path.join(out_dir, name + ".igd")
 
 

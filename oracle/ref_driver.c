@@ -41,6 +41,8 @@ void ref_close(void)
     fP = NULL;
     if (gData) free(gData);
     gData = NULL;
+    if (gData0) free(gData0);
+    gData0 = NULL;
     /* the reference leaks IGD's members on purpose-built paths; a test process does not care */
 }
 
