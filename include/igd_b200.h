@@ -173,6 +173,17 @@ int32_t get_overlaps_f0(char *chrm, int32_t qs, int32_t qe);                    
 int64_t getOverlaps_f0(char *qFile);                                                  /* igd_search.h:37 */
 int igd_search(int argc, char **argv);                                                /* igd_search.h:41 */
 
+/* ------------------------------------------------------------------------------------------------
+ * (3) index build -- src/igd_create.h:11-17.  Host-side C (no GPU needed): reads the same inputs and writes the
+ *     same <out>/<name>.igd and <name>_index.tsv as the reference, records in the same order.
+ * ---------------------------------------------------------------------------------------------- */
+extern int32_t tile_size;                                           /* src/igd.c:18; bin width of the next build */
+void create_igd(char *iPath, char *oPath, char *igdName);           /* igd_create.h:11: glob of BED(.gz) files */
+void create_igd0(char *iPath, char *oPath, char *igdName);          /* igd_create.h:12: -s 0, gdata0_t records */
+void create_igd_f(char *iPath, char *oPath, char *igdName);         /* igd_create.h:13: -f, list of files */
+void create_igd_bed4(char *iPath, char *oPath, char *igdName);      /* igd_create.h:14: -s 2, one file, column 4 = dataset */
+int igd_create(int argc, char **argv);                              /* igd_create.h:17 */
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,215 @@
+"""`igd create` of this repo (host C, igd_b200/csrc/igd_create.c) against the UNMODIFIED reference's `igd create`
+(oracle/_ref/igd, compiled in place from /root/reference): same .igd bytes -- header, tile tables and every
+record in the same order, ties of the reference's unstable radix sort included; the 40-byte contig names are
+compared as strings because the reference writes heap bytes behind the terminator (src/igd_base.c:422) -- same
+_index.tsv, same stdout.  The committed fixture tests/golden/create holds the reference's outputs for a box
+without /root/reference."""
+import gzip
+import hashlib
+import json
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from igd_b200 import api, synth
+from oracle import oracle as O
+from tests.conftest import SMALL_SIZES
+
+NAMES = ["chr1", "chr2", "chr3"]
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "create")
+
+
+def canonical_igd(path: str) -> bytes:
+    """the .igd file with the bytes behind each contig name's terminator zeroed"""
+    raw = bytearray(open(path, "rb").read())
+    nbp, gtype, m = np.frombuffer(raw, np.int32, 3)
+    ntile = np.frombuffer(raw, np.int32, m, 12)
+    off = 12 + 4 * m + 4 * int(ntile.sum())
+    for i in range(m):
+        nm = raw[off + 40 * i: off + 40 * (i + 1)]
+        k = nm.find(b"\0")
+        if k >= 0:
+            raw[off + 40 * i + k: off + 40 * (i + 1)] = b"\0" * (40 - k)
+    return bytes(raw)
+
+
+def run_create(binary, src, out, name, *opts):
+    r = subprocess.run([binary, "create", src, out, name, *opts], capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    return r.stdout.decode(errors="replace")
+
+
+def write_inputs(bed, seed=0, n_files=12, n=3000, gz_every=4):
+    """BED files with many equal starts (ties), long records spanning tiles, a dense tile of several hundred
+    records (the radix path, > 64 per tile), 3- to 6-column lines and some awkward ones."""
+    os.makedirs(bed)
+    rng = np.random.default_rng(77 + seed)
+    for i in range(n_files):
+        iv = synth.gen_intervals(9100 + 31 * seed + i, n, ("lognormal", 6.5, 1.4), SMALL_SIZES)
+        lines = []
+        for c, s, e, v in zip(iv.ctg, iv.start, iv.end, iv.value):
+            s = int(s) // 64 * 64                      # many ties on start
+            e = max(int(e), s + 1)
+            lines.append(f"{NAMES[c]}\t{s}\t{e}\t.\t{v}\n")
+        for k in range(400):                            # one hot tile: ties inside a > 64-record run
+            s = 70000 + int(rng.integers(0, 40)) * 16
+            lines.append(f"chr2\t{s}\t{s + int(rng.integers(1, 60000))}\tx\t{int(rng.integers(0, 1000))}\t+\n")
+        lines.insert(5, "chr1\t500\t400\t.\t3\n")      # start >= end: counted in the tsv, not stored
+        lines.insert(9, "chr1\t100\t200\n")            # three columns: no value
+        lines.insert(10, "chr3\t10\t20\t.\t7\textra\tcols\there\n")
+        lines.append("chrNew%d\t5\t50000\t.\t1\n" % (i % 3))       # contigs appearing late
+        p = os.path.join(bed, f"f{i:05d}.bed")
+        if gz_every and i % gz_every == 1:
+            with gzip.open(p + ".gz", "wt") as f:
+                f.writelines(lines)
+        else:
+            with open(p, "w") as f:
+                f.writelines(lines)
+
+
+CASES = {
+    "default": [],
+    "b12": ["-b", "12"],
+    "gtype0": ["-s", "0"],
+    "b17": ["-b", "17"],
+}
+
+
+def outputs(binary, work, bed, tag, opts):
+    out = os.path.join(work, tag) + "/"
+    stdout = run_create(binary, bed, out, "db", *opts)
+    return {"igd": canonical_igd(out + "db.igd"), "tsv": open(out + "db_index.tsv").read(),
+            "stdout": stdout.replace(out, "<OUT>/").replace(work, "<W>"), "listing": sorted(os.listdir(out))}
+
+
+@pytest.fixture(scope="module")
+def inputs(workdir):
+    bed = os.path.join(workdir, "create_bed")
+    if not os.path.isdir(bed):
+        write_inputs(bed)
+    return bed
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_create_matches_committed_reference_output(case, inputs, workdir):
+    """works without /root/reference: digests of the reference's outputs are committed (make_fixture below)"""
+    exp = json.load(open(os.path.join(GOLD, "expected.json")))[case]
+    got = outputs(api.CLI_PATH, workdir, inputs, "mine_gold_" + case, CASES[case])
+    assert hashlib.sha256(got["igd"]).hexdigest() == exp["igd_sha256"]
+    assert got["tsv"] == exp["tsv"]
+    assert got["stdout"] == exp["stdout"]
+    assert got["listing"] == exp["listing"]
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("case", list(CASES))
+def test_create_matches_reference_live(case, inputs, workdir):
+    ref = outputs(O.REF_BIN, workdir, inputs, "ref_" + case, CASES[case])
+    got = outputs(api.CLI_PATH, workdir, inputs, "mine_" + case, CASES[case])
+    assert got["igd"] == ref["igd"]
+    assert got["tsv"] == ref["tsv"]
+    assert got["stdout"] == ref["stdout"]
+    assert got["listing"] == ref["listing"]
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built")
+def test_create_list_mode_and_bed4(inputs, workdir):
+    """-f (a file listing the sources; parse_bed's rule per line) and -s 2 (one file, 4th column = dataset)"""
+    lst = os.path.join(workdir, "sources.txt")
+    files = sorted(os.path.join(inputs, f) for f in os.listdir(inputs))
+    with open(lst, "w") as f:
+        f.write("\n".join(files[:11] + ["/nonexistent/file.bed"]) + "\n")
+    outs = []
+    for binary, tag in ((O.REF_BIN, "ref_list"), (api.CLI_PATH, "mine_list")):
+        out = os.path.join(workdir, tag) + "/"
+        so = run_create(binary, lst, out, "db", "-f")
+        outs.append((canonical_igd(out + "db.igd"), open(out + "db_index.tsv").read(),
+                     so.replace(out, "<OUT>/").replace(workdir, "<W>")))
+    a, b = outs
+    # -f passes an UNINITIALISED value to igd_add in the reference (src/igd_create.c:139,189): compare all but it
+    ra, rb = (np.frombuffer(x[0][-(len(x[0]) - hdr_len(x[0])):], np.int32).reshape(-1, 4) for x in (a, b))
+    assert a[0][:hdr_len(a[0])] == b[0][:hdr_len(b[0])]
+    assert np.array_equal(ra[:, :3], rb[:, :3]) and not rb[:, 3].any()
+    assert a[1] == b[1] and a[2] == b[2]
+
+    bed4 = os.path.join(workdir, "jaspar.bed")
+    rng = np.random.default_rng(5)
+    with open(bed4, "w") as f:
+        for k in range(20000):
+            s = int(rng.integers(0, 900000))
+            f.write(f"chr{1 + k % 3}\t{s}\t{s + int(rng.integers(1, 3000))}\tTF{int(rng.integers(0, 37))}\t{k % 1000}\n")
+    outs = []
+    for binary, tag in ((O.REF_BIN, "ref_bed4"), (api.CLI_PATH, "mine_bed4")):
+        out = os.path.join(workdir, tag) + "/"
+        so = run_create(binary, bed4, out, "db", "-s", "2")
+        outs.append((canonical_igd(out + "db.igd"), open(out + "db_index.tsv").read(),
+                     so.replace(out, "<OUT>/").replace(workdir, "<W>")))
+    assert outs[0] == outs[1]
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built")
+def test_create_dense_tiles_radix_levels(workdir):
+    """thousands of records per tile with heavy ties: the in-place byte-radix levels of the reference's sort, whose
+    order of equal starts is an artefact of its displacement cycles, reproduced record for record"""
+    bed = os.path.join(workdir, "create_bed_dense")
+    write_inputs(bed, seed=1, n_files=10, n=40000, gz_every=0)
+    ref = outputs(O.REF_BIN, workdir, bed, "ref_dense", [])
+    got = outputs(api.CLI_PATH, workdir, bed, "mine_dense", [])
+    assert got == ref
+    nrec = (len(got["igd"]) - hdr_len(got["igd"])) // 16
+    m = int(np.frombuffer(got["igd"], np.int32, 1, 8)[0])
+    ntiles = int(np.frombuffer(got["igd"], np.int32, m, 12).sum())
+    assert nrec / ntiles > 1000
+
+
+def hdr_len(b: bytes) -> int:
+    m = int(np.frombuffer(b, np.int32, 1, 8)[0])
+    return 12 + 44 * m + 4 * int(np.frombuffer(b, np.int32, m, 12).sum())
+
+
+def test_create_refuses_existing_and_prints_help(inputs, workdir):
+    out = os.path.join(workdir, "mine_twice") + "/"
+    run_create(api.CLI_PATH, inputs, out, "db")
+    again = run_create(api.CLI_PATH, inputs, out, "db")
+    assert again == f"The igd database file {out}db.igd exists!\n"
+    r = subprocess.run([api.CLI_PATH, "create", inputs], capture_output=True, text=True)
+    assert r.returncode == 0 and "usage:   igd create <input dir>" in r.stderr
+
+
+def test_created_database_searches_like_the_reference_one(inputs, workdir):
+    """end to end on the CPU side: the oracle gives the same hits[] on our database as the committed count"""
+    out = os.path.join(workdir, "mine_search") + "/"
+    run_create(api.CLI_PATH, inputs, out, "db")
+    db = O.OracleDB(out + "db.igd")
+    q = synth.gen_intervals(4242, 3000, ("lognormal", 7.0, 1.5), SMALL_SIZES)
+    hits, _ = db.count(q.ctg, q.start, q.end)
+    exp = json.load(open(os.path.join(GOLD, "expected.json")))
+    assert hits.tolist() == exp["search_hits"]
+
+
+def make_fixture():
+    """python -m tests.test_create  (needs oracle/_ref): writes tests/golden/create/expected.json"""
+    import tempfile
+    assert O.have_ref()
+    with tempfile.TemporaryDirectory(prefix="c") as work:
+        bed = os.path.join(work, "create_bed")
+        write_inputs(bed)
+        exp = {}
+        for case, opts in CASES.items():
+            o = outputs(O.REF_BIN, work, bed, "ref_" + case, opts)
+            exp[case] = {"igd_sha256": hashlib.sha256(o["igd"]).hexdigest(), "tsv": o["tsv"], "stdout": o["stdout"],
+                         "listing": o["listing"]}
+        db = O.OracleDB(os.path.join(work, "ref_default", "db.igd"))
+        q = synth.gen_intervals(4242, 3000, ("lognormal", 7.0, 1.5), SMALL_SIZES)
+        exp["search_hits"] = db.count(q.ctg, q.start, q.end)[0].tolist()
+        os.makedirs(GOLD, exist_ok=True)
+        with open(os.path.join(GOLD, "expected.json"), "w") as f:
+            json.dump(exp, f, indent=1)
+    print("wrote", os.path.join(GOLD, "expected.json"))
+
+
+if __name__ == "__main__":
+    make_fixture()
