@@ -32,6 +32,13 @@ class _Queries(C.Structure):
                 ("qe", C.POINTER(C.c_int32)), ("n_names", C.c_int32), ("names", C.POINTER(C.c_char_p))]
 
 
+class _Overlaps(C.Structure):          # igd_b200_overlaps = overlaps_t, src/igd_base.h:116-119
+    _fields_ = [("nn", C.c_int32), ("mm", C.c_int32), ("olist", C.c_void_p)]
+
+
+# igd_b200_overlap = overlap_t, src/igd_base.h:109-114
+OVERLAP_DTYPE = np.dtype([("idx_t", np.int32), ("idx_g", np.int32), ("idx_f", np.int32), ("sm", np.float32)])
+
 _i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
 _i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
 _u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
@@ -75,6 +82,12 @@ def load_library():
     L.igd_b200_ctg_id.argtypes = [vp, C.c_char_p]
     L.get_overlaps_n.restype = C.c_int64
     L.get_overlaps_n.argtypes = [vp, C.c_int64, C.POINTER(C.c_char_p), _i32p, _i32p, C.c_int32, _i64p]
+    L.get_overlaps_n32.restype = C.c_int64
+    L.get_overlaps_n32.argtypes = [vp, C.c_int64, C.POINTER(C.c_char_p), _i32p, _i32p, _i32p]
+    L.igd_b200_bin_data.restype = C.c_int32
+    L.igd_b200_bin_data.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, vp]
+    L.create_iGD.restype = C.c_int
+    L.create_iGD.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
     L.igd_b200_count.restype = C.c_int64
     L.igd_b200_count.argtypes = [vp, C.c_int64, vp, vp, vp, C.c_int32, _i64p]
     L.igd_b200_count_device.restype = C.c_int
@@ -96,6 +109,11 @@ def load_library():
     L.search.argtypes = [vp, C.c_char_p, C.c_int32, _i64p]
     L.igd_b200_seqpare.restype = C.c_int
     L.igd_b200_seqpare.argtypes = [vp, C.c_char_p, _f64p]
+    L.igd_b200_seq_overlaps.restype = C.c_int64
+    L.igd_b200_seq_overlaps.argtypes = [vp, C.c_int64, _i32p, _i32p, _i32p, C.POINTER(C.POINTER(C.c_int64)),
+                                        C.POINTER(vp)]
+    L.seq_overlaps.restype = None
+    L.seq_overlaps.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.POINTER(_Overlaps)]
     L.igd_b200_query_cost.restype = C.c_int
     L.igd_b200_query_cost.argtypes = [vp, C.c_int64, _i32p, _i32p, _i32p, _i64p]
     L.igd_b200_last_search_kernel_ms.restype = C.c_float
@@ -128,6 +146,12 @@ def load_library():
 
 def last_error() -> str:
     return load_library().igd_b200_last_error().decode(errors="replace")
+
+
+def create(iPath: str, oPath: str, igdName: str, bin_size: int = 16384) -> bool:
+    """igd_py.create(iPath, oPath, igdName, bin_size) (src_py/igd_py.pyx:33-34): build <oPath>/<igdName>.igd from
+    the BED(.gz) files under iPath -- host C, no GPU needed.  False if the database exists already."""
+    return load_library().create_iGD(os.fsencode(iPath), os.fsencode(oPath), igdName.encode(), int(bin_size)) == 0
 
 
 class QuerySet:
@@ -281,6 +305,26 @@ class IGD:
             raise IGDError(last_error())
         return hits, int(r)
 
+    def search_nr(self, chrm: list[str], qs, qe) -> np.ndarray:
+        """R's search_nr(igdr, n, chrm, qs, qe) (IGDr/R/IGDr.R:54-57): a fresh 32-bit hits vector."""
+        qs, qe = self._a(qs), self._a(qe)
+        hits = np.zeros(self.nfiles, np.int32)
+        arr = (C.c_char_p * len(chrm))(*[c.encode() for c in chrm])
+        if self._L.get_overlaps_n32(self._need(), len(chrm), arr, qs, qe, hits) < 0:
+            raise IGDError(last_error())
+        return hits
+
+    def bin_data(self, ctg: int, bin: int):
+        """R's get_binData(igdr, ichr, bin) (IGDr/src/igd_search.c:357-393), 0-based here: (idx, start, end, value)
+        of one tile, read back from the HBM image."""
+        n = self._L.igd_b200_bin_data(self._need(), ctg, bin, 0, None, None, None, None)
+        if n < 0:
+            raise IGDError(last_error())
+        cols = [np.zeros(n, np.int32) for _ in range(4)]
+        if n and self._L.igd_b200_bin_data(self._need(), ctg, bin, n, *[c.ctypes.data for c in cols]) < 0:
+            raise IGDError(last_error())
+        return tuple(cols)
+
     def search_1(self, chrm: str, qs: int, qe: int, hits: np.ndarray | None = None, v: int = 0):
         """igd_py.search_1 (src_py/igd_py.pyx:39-41)."""
         return self.get_overlaps_n([chrm], [qs], [qe], v, hits)
@@ -339,6 +383,17 @@ class IGD:
         if r < 0:
             raise IGDError(last_error())
         return hm
+
+    def seq_overlaps(self, ctg, qs, qe):
+        """seq_overlaps for a batch: (query_off[n+1], structured array of overlap_t records in scan order)"""
+        ctg, qs, qe = self._a(ctg), self._a(qs), self._a(qe)
+        qoff, lst = C.POINTER(C.c_int64)(), C.c_void_p()
+        t = self._L.igd_b200_seq_overlaps(self._need(), len(ctg), ctg, qs, qe, C.byref(qoff), C.byref(lst))
+        if t < 0:
+            raise IGDError(last_error())
+        off = np.ctypeslib.as_array(qoff, (len(ctg) + 1,)).copy()
+        rec = np.frombuffer(C.string_at(lst, 16 * t), OVERLAP_DTYPE).copy() if t else np.zeros(0, OVERLAP_DTYPE)
+        return off, rec
 
     def seqpare(self, qfile: str) -> np.ndarray:
         sm = np.zeros(self.nfiles, np.float64)

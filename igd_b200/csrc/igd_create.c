@@ -575,6 +575,32 @@ void create_igd_bed4(char *iPath, char *oPath, char *igdName)
     free(nr), free(avg);
 }
 
+/* create_iGD (src_py/igd_create.c:19-49): what igd_py.create calls -- the default flavour, bin width in bp */
+int create_iGD(const char *iPath, const char *oPath, const char *igdName, int tile_size_bp)
+{
+    char ipath[1024], opath[1024], ftmp[2200], name[512];
+    snprintf(ipath, sizeof ipath - 2, "%s", iPath);
+    snprintf(opath, sizeof opath - 1, "%s", oPath);
+    snprintf(name, sizeof name, "%s", igdName);
+    size_t lo = strlen(opath), li = strlen(ipath);
+    if (lo == 0 || opath[lo - 1] != '/') strcat(opath, "/");
+    if (li > 0 && ipath[li - 1] == '/') strcat(ipath, "*");
+    else if (li > 0 && ipath[li - 1] != '*') strcat(ipath, "/*");
+    struct stat st;
+    snprintf(ftmp, sizeof ftmp, "%s%s.igd", opath, name);
+    if (stat(ftmp, &st) == 0) {
+        printf("The igd database file %s exists!\n", ftmp);
+        return 1;
+    }
+    if (stat(opath, &st) == -1) mkdir(opath, 0777);
+    snprintf(ftmp, sizeof ftmp, "%sdata0", opath);
+    if (stat(ftmp, &st) == -1) mkdir(ftmp, 0777);
+    tile_size = tile_size_bp > 0 ? tile_size_bp : 16384;
+    create_igd(ipath, opath, name);
+    fflush(stdout);
+    return 0;
+}
+
 static int create_usage(void)
 {
     fprintf(stderr,

@@ -23,6 +23,9 @@ igdb_dev *igdb_dev_create(int device, int32_t nbp, int32_t nctg, const int32_t *
 int igdb_dev_upload(igdb_dev *d, int64_t rec0, int64_t nrec, const void *aos, int rec_words);
 /* after the last upload: per-tile dedupe start (tS) and first start */
 int igdb_dev_finalize(igdb_dev *d);
+/* copies up to cap records of one tile (global tile index) out of the image; returns how many (< 0: error) */
+int igdb_dev_tile_read(igdb_dev *d, int64_t tile, int32_t cap, int32_t *idx, int32_t *start, int32_t *end,
+                       int32_t *value);
 void igdb_dev_destroy(igdb_dev *d);
 int64_t igdb_dev_bytes(const igdb_dev *d);
 int64_t igdb_dev_launches(const igdb_dev *d);
@@ -71,6 +74,11 @@ int64_t igdb_dev_full_host(igdb_dev *d, int64_t n, const int32_t *ctg, const int
  * queries of group g; acc[nfiles] = sum of matched similarities per file */
 int igdb_dev_seqpare(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_t *qs, const int32_t *qe,
                      const int32_t *grp, int32_t ngroups, const int32_t *grp_nq, double *acc);
+
+/* seq_overlaps (src/igd_search.c:253-353) for n queries: overlap_t records {idx_t, idx_g, idx_f, float sm} (16 B) in
+ * the reference's scan order, query q owning [query_off[q], query_off[q+1]); arrays in the handle's pinned arena */
+int64_t igdb_dev_seq_pairs_host(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_t *qs, const int32_t *qe,
+                                int64_t **query_off, void **pairs);
 
 /* -m restricted to the tiles [t0, t1) (global tile indices, contig-major): hitmap[nfiles*nfiles] is incremented */
 int64_t igdb_dev_hitsmap_host(igdb_dev *d, int32_t v, int64_t t0, int64_t t1, uint32_t *hitmap);

@@ -300,6 +300,24 @@ int igdb_dev_finalize(igdb_dev *d)
     return 0;
 }
 
+// the records of one tile back on the host (get_binData, IGDr/src/igd_search.c:357-393): up to cap of each column
+int igdb_dev_tile_read(igdb_dev *d, int64_t tile, int32_t cap, int32_t *idx, int32_t *start, int32_t *end,
+                       int32_t *value)
+{
+    g_err[0] = 0;
+    if (tile < 0 || tile >= d->T) return 0;
+    CK(cudaSetDevice(d->device));
+    const int64_t n = std::min<int64_t>(d->toff[tile + 1] - d->toff[tile], cap);
+    if (n <= 0) return 0;
+    const size_t o = (size_t)d->off8[tile] * 8, b = (size_t)n * 4;
+    CK(cudaStreamSynchronize(d->stream));
+    if (idx) CK(cudaMemcpy(idx, d->idx + o, b, cudaMemcpyDeviceToHost));
+    if (start) CK(cudaMemcpy(start, d->start + o, b, cudaMemcpyDeviceToHost));
+    if (end) CK(cudaMemcpy(end, d->end + o, b, cudaMemcpyDeviceToHost));
+    if (value) CK(cudaMemcpy(value, d->value + o, b, cudaMemcpyDeviceToHost));
+    return (int)n;
+}
+
 int64_t igdb_dev_bytes(const igdb_dev *d) { return d->bytes; }
 int igdb_dev_packed(const igdb_dev *d) { return d->packed ? 1 : 0; }
 int64_t igdb_dev_launches(const igdb_dev *d) { return d->launches; }

@@ -48,6 +48,28 @@ __global__ void k_seq_candidates(DbView db, int64_t n, const int64_t *__restrict
     col[p] = 1ull << 62 | (unsigned long long)(uint32_t)(s / db.nbp) << 32 | (uint32_t)og[p];
 }
 
+// seq_overlaps as a list (src/igd_search.c:253-353): the same pairs, as the reference's overlap_t records
+// {idx_t = n1 of the QUERY, idx_g = index in the tile the record was found in, idx_f, sm} in its scan order
+__global__ void k_seq_pairs(int32_t nbp, int64_t n, const int64_t *__restrict__ qoff, const int32_t *__restrict__ qs,
+                            const int32_t *__restrict__ qe, int64_t total, const int32_t *__restrict__ os,
+                            const int32_t *__restrict__ oe, const int32_t *__restrict__ of,
+                            const int32_t *__restrict__ og, int4 *__restrict__ out)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= total) return;
+    int64_t lo = 0, hi = n;
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(&qoff[mid]) <= p) lo = mid; else hi = mid;
+    }
+    const int32_t s = __ldg(&qs[lo]), e = __ldg(&qe[lo]);
+    const int32_t rs = os[p], re = oe[p];
+    const float qlen = __int2float_rn(e - s), rlen = __int2float_rn(re - rs);
+    const float st = __int2float_rn(min(e, re) - max(s, rs));
+    const float sm = __fdiv_rn(st, __fsub_rn(__fadd_rn(qlen, rlen), st));
+    out[p] = make_int4(s / nbp, og[p], of[p], __float_as_int(sm));
+}
+
 __device__ __forceinline__ int64_t lower_bound_key(const unsigned long long *__restrict__ k, int64_t n,
                                                    unsigned long long x)
 {
@@ -145,6 +167,62 @@ __global__ void k_seq_sum(int32_t nfiles, int32_t ngroups, const int64_t *__rest
 }  // namespace
 
 extern "C" {
+
+// seq_overlaps for a batch of queries: query_off[n+1] and the overlap_t records (16 B each) in the handle's pinned
+// arena (valid until the next list-returning call on the handle).  Returns the number of records.
+int64_t igdb_dev_seq_pairs_host(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_t *qs, const int32_t *qe,
+                                int64_t **query_off, void **pairs)
+{
+    g_err[0] = 0;
+    *query_off = nullptr, *pairs = nullptr;
+    CK(cudaSetDevice(d->device));
+    if (finish_pending(d)) return -1;
+    cudaStream_t st = d->stream;
+    if (n >= (1 << 26)) {
+        snprintf(g_err, sizeof g_err, "seq_overlaps: batch of %lld queries is too large", (long long)n);
+        return -1;
+    }
+    const size_t qbytes = (((size_t)std::max<int64_t>(n, 0) + 1) * 8 + 255) & ~(size_t)255;
+    auto arena = [&](size_t bytes) -> int {
+        if (bytes <= d->arena_cap) return 0;
+        if (d->arena) CK(cudaFreeHost(d->arena));
+        d->arena = nullptr, d->arena_cap = 0;
+        const size_t want = bytes + (bytes >> 3) + 4096;
+        if (cudaHostAlloc(&d->arena, want, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            snprintf(g_err, sizeof g_err, "cannot pin %zu bytes of host memory for the overlap lists", want);
+            return -1;
+        }
+        d->arena_cap = want;
+        return 0;
+    };
+    if (n <= 0 || d->T == 0) {
+        if (arena(qbytes)) return -1;
+        memset(d->arena, 0, qbytes);
+        *query_off = (int64_t *)d->arena;
+        return 0;
+    }
+    if (upload_queries(d, n, ctg, qs, qe, st)) return -1;
+    DevBuf qoff, out, rec;
+    const int64_t total = full_device(d, n, st, true, qoff, out);
+    if (total < 0) return -1;
+    if (arena(qbytes + (size_t)total * 16)) return -1;
+    CK(cudaMemcpyAsync(d->arena, qoff.p, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, st));
+    if (total > 0) {
+        if (rec.alloc((size_t)total * 16)) return -1;
+        const int32_t *o = out.as<int32_t>();
+        k_seq_pairs<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d->nbp, n, qoff.as<int64_t>(), d->q_qs, d->q_qe,
+                                                                    total, o, o + total, o + 2 * total, o + 3 * total,
+                                                                    rec.as<int4>());
+        d->launches += 1;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync((char *)d->arena + qbytes, rec.p, (size_t)total * 16, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    *query_off = (int64_t *)d->arena;
+    if (total > 0) *pairs = (char *)d->arena + qbytes;
+    return total;
+}
 
 // -s: queries grouped by query-file chrom (grp[q] ascending, 0..ngroups-1) and sorted by start inside a group
 // (the host did readBED + qsort, src/igd_base.c:628-649, src/igd_search.c:373).  acc[m] receives the sum of the

@@ -242,6 +242,27 @@ int64_t get_overlaps_n(igd_b200_t *h, int64_t n, const char *const *chrm, const 
     return r;
 }
 
+int64_t get_overlaps_n32(igd_b200_t *h, int64_t n, const char *const *chrm, const int32_t *qs,
+                         const int32_t *qe, int32_t *hits)
+{
+    int64_t *wide = calloc((size_t)h->nfiles + 1, sizeof(int64_t));
+    int64_t r = get_overlaps_n(h, n, chrm, qs, qe, 0, wide);
+    if (r >= 0)
+        for (int i = 0; i < h->nfiles; i++) hits[i] = (int32_t)((uint32_t)hits[i] + (uint32_t)wide[i]);
+    free(wide);
+    return r;
+}
+
+int32_t igd_b200_bin_data(igd_b200_t *h, int32_t ctg, int32_t bin, int32_t cap, int32_t *idx, int32_t *start,
+                          int32_t *end, int32_t *value)
+{
+    g_err[0] = 0;
+    if (ctg < 0 || ctg >= h->nctg || bin < 0 || bin >= h->ntile[ctg]) return 0;
+    int64_t t = h->tbase[ctg] + bin;
+    if (cap > 0 && igdb_dev_tile_read(h->dev, t, cap, idx, start, end, value) < 0) return -1;
+    return h->ncnt[t];
+}
+
 int igd_b200_full(igd_b200_t *h, int64_t n, const int32_t *ctg, const int32_t *qs, const int32_t *qe,
                   igd_b200_hitlist *out)
 {
@@ -516,6 +537,36 @@ int64_t getMap_v(uint32_t **hitmap, int32_t v)
         for (int i = 0; i < n; i++) memcpy(hitmap[i], dense + (size_t)i * n, sizeof(uint32_t) * (size_t)n);
     free(dense);
     return r < 0 ? 0 : r;
+}
+
+/* ---- seq_overlaps (src/igd_search.c:253-353) ------------------------------------------------------------ */
+int64_t igd_b200_seq_overlaps(igd_b200_t *h, int64_t n, const int32_t *ctg, const int32_t *qs, const int32_t *qe,
+                              int64_t **query_off, igd_b200_overlap **list)
+{
+    g_err[0] = 0;
+    void *p = NULL;
+    int64_t total = igdb_dev_seq_pairs_host(h->dev, n, ctg, qs, qe, query_off, &p);
+    *list = p;
+    return total;
+}
+
+/* one query, appended to the caller's growable list (EXPAND doubles the capacity, 2 if empty) */
+void seq_overlaps(char *chrm, int32_t qs, int32_t qe, igd_b200_overlaps *olp)
+{
+    if (!g_current || !olp) return;
+    int32_t c = igd_b200_ctg_id(g_current, chrm);
+    int64_t *qoff;
+    igd_b200_overlap *list;
+    int64_t total = igd_b200_seq_overlaps(g_current, 1, &c, &qs, &qe, &qoff, &list);
+    if (total <= 0) return;
+    if ((int64_t)olp->nn + total > olp->mm) {
+        int32_t mm = olp->mm;
+        while ((int64_t)olp->nn + total > mm) mm = mm ? mm << 1 : 2;
+        olp->olist = realloc(olp->olist, sizeof(igd_b200_overlap) * (size_t)mm);
+        olp->mm = mm;
+    }
+    memcpy(olp->olist + olp->nn, list, sizeof(igd_b200_overlap) * (size_t)total);
+    olp->nn += (int32_t)total;
 }
 
 /* ---- -s: seqOverlaps (src/igd_search.c:355-451) ------------------------------------------------------

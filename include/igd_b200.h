@@ -50,6 +50,11 @@ const char *igd_b200_file_name(const igd_b200_t *h, int32_t i);     /* info_t.fi
 const char *igd_b200_ctg_name(const igd_b200_t *h, int32_t ctg);    /* iGD_t.cName[ctg] */
 /* get_id (src/igd_base.c:325-331): contig index, -1 if absent */
 int32_t igd_b200_ctg_id(const igd_b200_t *h, const char *chrm);
+/* get_binData (IGDr/src/igd_search.c:357-393): the records of tile `bin` of contig `ctg`, in file order, read back
+ * from the HBM image.  Copies up to cap entries into each non-NULL array; returns nCnt of the tile (0 if the
+ * tile does not exist), negative on a CUDA error. */
+int32_t igd_b200_bin_data(igd_b200_t *h, int32_t ctg, int32_t bin, int32_t cap, int32_t *idx, int32_t *start,
+                          int32_t *end, int32_t *value);
 /* bytes of HBM held by the database image */
 int64_t igd_b200_device_bytes(const igd_b200_t *h);
 
@@ -60,6 +65,10 @@ int64_t igd_b200_device_bytes(const igd_b200_t *h);
  * (The reference's own return value -- 0 for plain, the count for -v -- is what group (2) returns.) */
 int64_t get_overlaps_n(igd_b200_t *h, int64_t n, const char *const *chrm, const int32_t *qs,
                        const int32_t *qe, int32_t v, int64_t *hits);
+/* search_nr as the R package calls it (IGDr/src/igd_search.c:340-355): n x get_overlaps32 (:105-186), 32-bit
+ * counters, incremented (they wrap like the reference's int).  Returns the overlaps found or a negative error code. */
+int64_t get_overlaps_n32(igd_b200_t *h, int64_t n, const char *const *chrm, const int32_t *qs,
+                         const int32_t *qe, int32_t *hits);
 /* same, contig ids already resolved with igd_b200_ctg_id (-1 = unknown chrom: contributes nothing) */
 int64_t igd_b200_count(igd_b200_t *h, int64_t n, const int32_t *ctg, const int32_t *qs,
                        const int32_t *qe, int32_t v, int64_t *hits);
@@ -126,6 +135,16 @@ int64_t search(igd_b200_t *h, const char *qFile, int32_t v, int64_t *hits);
 /* -s: seqOverlaps (src/igd_search.c:355-451); sm[nFiles] is overwritten.  0 on success. */
 int igd_b200_seqpare(igd_b200_t *h, const char *qFile, double *sm);
 
+/* seq_overlaps (src/igd_search.c:253-353), batched: for every query the records it overlaps as the reference's
+ * overlap_t (src/igd_base.h:109-114) -- idx_t = the QUERY's first bin, idx_g = index inside the tile the record
+ * was found in, idx_f = file, sm = fp32 pair similarity st / (qlen + rlen - st) -- in the reference's scan order.
+ * query_off[n+1] and list[] live in the handle's pinned arena (valid until the next list-returning call on the
+ * handle).  Returns the number of records or a negative error code. */
+typedef struct { int32_t idx_t, idx_g, idx_f; float sm; } igd_b200_overlap;             /* overlap_t */
+typedef struct { int32_t nn, mm; igd_b200_overlap *olist; } igd_b200_overlaps;          /* overlaps_t, igd_base.h:116-119 */
+int64_t igd_b200_seq_overlaps(igd_b200_t *h, int64_t n, const int32_t *ctg, const int32_t *qs, const int32_t *qe,
+                              int64_t **query_off, igd_b200_overlap **list);
+
 /* Multi-GPU planning: cost[i] = estimated scan bytes of query i (sum over its bins of
  * 4*nCnt); used to cut a (ctg,start)-sorted query set into contiguous, cost-balanced shards. */
 int igd_b200_query_cost(const igd_b200_t *h, int64_t n, const int32_t *ctg, const int32_t *qs,
@@ -166,6 +185,8 @@ int64_t getMap_v(uint32_t **hitmap, int32_t v);                                 
 int32_t get_overlaps_f1(char *chrm, int32_t qs, int32_t qe);                          /* igd_search.h:36 */
 int64_t getOverlaps_f1(char *qFile);                                                  /* igd_search.h:38 */
 void seqOverlaps(char *qFile, double *sm);                                            /* igd_search.h:20 */
+/* appends to olp->olist (malloc'ed by the caller or NULL with mm == 0; grown by doubling like EXPAND) */
+void seq_overlaps(char *chrm, int32_t qs, int32_t qe, igd_b200_overlaps *olp);        /* igd_search.h:19 */
 /* the gType-0 (gdata0_t, `igd create -s 0`) twins: same searches, the handle knows its record type */
 int32_t get_overlaps0(char *chrm, int32_t qs, int32_t qe, int64_t *hits);             /* igd_search.h:15 */
 int64_t getOverlaps0(char *qFile, int64_t *hits);                                     /* igd_search.h:16 */
@@ -183,6 +204,9 @@ void create_igd0(char *iPath, char *oPath, char *igdName);          /* igd_creat
 void create_igd_f(char *iPath, char *oPath, char *igdName);         /* igd_create.h:13: -f, list of files */
 void create_igd_bed4(char *iPath, char *oPath, char *igdName);      /* igd_create.h:14: -s 2, one file, column 4 = dataset */
 int igd_create(int argc, char **argv);                              /* igd_create.h:17 */
+/* create_iGD (src_py/igd_create.c:19-49, igd_py.create of src_py/igd_py.pyx:33-34): the default build with the
+ * bin width given in bp; 0 on success, 1 if <oPath>/<igdName>.igd exists already (nothing is written then) */
+int create_iGD(const char *iPath, const char *oPath, const char *igdName, int tile_size_bp);
 
 #ifdef __cplusplus
 }

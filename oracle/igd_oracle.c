@@ -365,6 +365,19 @@ static void hit_seq(void *ctx_, int64_t q, int32_t n1, int32_t i, const rec_t *r
     c->n++;
 }
 
+/* seq_overlaps for one query as a list: up to cap records {idx_t, idx_g, idx_f, sm} (16 B each) in scan order;
+ * returns how many there are */
+int64_t orc_seq_overlaps(const orc_db *db, int32_t ctg, int32_t qs, int32_t qe, int64_t cap, void *out16)
+{
+    cand_ctx cc = { NULL, 0, 0, qs, qe };
+    walk(db, 0, ctg, qs, qe, 0, 0, hit_seq, &cc, NULL, NULL);
+    struct { int32_t t, g, f; float sm; } *o = out16;
+    for (int64_t i = 0; i < cc.n && i < cap; i++)
+        o[i].t = cc.a[i].idx_t, o[i].g = cc.a[i].idx_g, o[i].f = cc.a[i].idx_f, o[i].sm = cc.a[i].sm;
+    free(cc.a);
+    return cc.n;
+}
+
 typedef struct { int32_t start, end; int64_t ord; } qrec_t;
 static int cmp_qstart(const void *a, const void *b)                /* compare_qstart igd_base.c:23-28, stable */
 {

@@ -49,6 +49,14 @@ _i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
 _u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
 _f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
 
+# overlap_t, src/igd_base.h:109-114
+OVERLAP_DTYPE = np.dtype([("idx_t", np.int32), ("idx_g", np.int32), ("idx_f", np.int32), ("sm", np.float32)])
+
+
+class _Overlaps(C.Structure):          # overlaps_t, src/igd_base.h:116-119
+    _fields_ = [("nn", C.c_int32), ("mm", C.c_int32), ("olist", C.c_void_p)]
+
+
 _lib = None
 
 
@@ -86,6 +94,8 @@ def lib():
         L.orc_full.argtypes = [C.c_void_p, C.c_int64, _i32p, _i32p, _i32p, C.c_int64,
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_seqpare.argtypes = [C.c_void_p, C.POINTER(_Queries), _f64p]
+        L.orc_seq_overlaps.restype = C.c_int64
+        L.orc_seq_overlaps.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p]
         L.orc_hitsmap.restype = C.c_int64
         L.orc_hitsmap.argtypes = [C.c_void_p, C.c_int32, _u32p]
         L.orc_hitsmap_tiles.restype = C.c_int64
@@ -183,6 +193,14 @@ class OracleDB:
         self.L.orc_seqpare(self.h, q._p, sm)
         return sm
 
+    def seq_overlaps(self, ctg: int, qs: int, qe: int) -> np.ndarray:
+        """seq_overlaps of one query: structured array (idx_t, idx_g, idx_f, sm) in scan order"""
+        n = self.L.orc_seq_overlaps(self.h, ctg, qs, qe, 0, None)
+        out = np.zeros(n, OVERLAP_DTYPE)
+        if n:
+            self.L.orc_seq_overlaps(self.h, ctg, qs, qe, n, out.ctypes.data)
+        return out
+
     def hitsmap(self, v: int = 0, tiles=None) -> np.ndarray:
         hm = np.zeros((self.nfiles, self.nfiles), np.uint32)
         if tiles is None:
@@ -247,6 +265,19 @@ class RefLib:
         sm = np.zeros(self.nfiles, np.float64)
         self.L.seqOverlaps(qfile.encode(), sm)
         return sm
+
+    def seq_overlaps(self, chrm: str, qs: int, qe: int) -> np.ndarray:
+        """the reference's own seq_overlaps(chrm, qs, qe, olp) on an empty list (the list is malloc'ed by libc)"""
+        libc = C.CDLL(None)
+        libc.malloc.restype = C.c_void_p
+        libc.free.argtypes = [C.c_void_p]
+        o = _Overlaps(0, 16, libc.malloc(16 * 16))
+        self.L.seq_overlaps.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.POINTER(_Overlaps)]
+        self.L.seq_overlaps.restype = None
+        self.L.seq_overlaps(C.create_string_buffer(chrm.encode()), qs, qe, C.byref(o))
+        out = np.frombuffer(C.string_at(o.olist, 16 * o.nn), OVERLAP_DTYPE).copy() if o.nn else np.zeros(0, OVERLAP_DTYPE)
+        libc.free(o.olist)
+        return out
 
     def hitsmap(self, v: int = 0) -> np.ndarray:
         hm = np.zeros((self.nfiles, self.nfiles), np.uint32)
