@@ -5,9 +5,11 @@
  * create_igd0 (-s 0, :245-332) and create_igd_bed4 (-s 2, :334-433) -- but not its mechanism.  The reference
  * grows one malloc'd list per tile, spills every 2^28 records into one temp file per tile under <out>/data0/
  * (igd_saveT, src/igd_base.c:333-364) and re-reads, sorts and appends them tile by tile (igd_save, :396-461).
- * Here the accepted intervals are kept as one flat array; a counting pass sizes every tile, a second pass drops
- * each interval into the tiles it touches in arrival order (what the appends to the temp files amount to), the
- * tiles are sorted in parallel on all host cores and the file is written once.
+ * Here the input files are parsed in parallel (one file per thread at a time) into flat per-file arrays of
+ * accepted intervals; one sequential pass over them, in file order, numbers the contigs by first appearance and
+ * replays the reference's batch accounting; a counting pass sizes every tile, a second pass drops each interval
+ * into the tiles it touches in arrival order (what the appends to the temp files amount to) -- both passes and
+ * the tile sort run on all host cores, each thread owning a range of tiles -- and the file is written once.
  *
  * The output is meant to be byte-identical to the reference's:
  *   - header, nTile[], nCnt[][] and the record payload are; that includes the ORDER OF EQUAL STARTS inside a
@@ -32,6 +34,7 @@
 #include <string.h>
 #include <sys/stat.h>
 #include <sys/types.h>
+#include <time.h>
 #include <unistd.h>
 #include <zlib.h>
 
@@ -43,6 +46,22 @@ int32_t tile_size = 16384;              /* the reference's global of the same na
 
 typedef struct { int32_t idx, start, end, value; } rec_t;               /* gdata_t, src/igd_base.h:41-46 */
 typedef struct { int32_t ctg, idx, start, end, value; } raw_t;          /* one accepted input interval */
+
+/* IGD_B200_CREATE_TIMING=1: phase times on stderr (stdout stays the reference's) */
+static double now_s(void)
+{
+    struct timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec;
+}
+static double g_t0;
+static void phase(const char *what)
+{
+    if (!getenv("IGD_B200_CREATE_TIMING")) return;
+    double t = now_s();
+    if (what) fprintf(stderr, "igd create: %-28s %8.3f s\n", what, t - g_t0);
+    g_t0 = t;
+}
 
 /* ---- string -> small integer, first-appearance numbering (contigs; dataset names of -s 2) --------------- */
 typedef struct {
@@ -96,54 +115,72 @@ static int32_t names_get(names_t *t, const char *s, int add)
 }
 
 /* ---- the build in progress ---------------------------------------------------------------------------- */
+/* what one input file contributes: its accepted intervals in line order, contigs numbered locally */
+typedef struct {
+    raw_t *raw;                         /* .ctg = index into `ctg` below until merge_parts() makes it global */
+    int64_t nraw, cap;
+    names_t ctg;
+    int32_t nr;                         /* lines counted for the tsv */
+    double avg;                         /* sum of end - start over those lines */
+    int state_first, state_last;        /* the splitter's field limit after the first / last line (-1: no line) */
+    int opened;
+} part_t;
+
 typedef struct {
     int32_t nbp, gtype;
     names_t ctg;
     int32_t *mtiles;                    /* per contig: ctg_t.mTiles = 1 + the largest (end-1)/nbp seen */
     int32_t mt_cap;
-    raw_t *raw;
-    int64_t nraw, raw_cap;
+    part_t *part;
+    int32_t nparts;
     int64_t batch;                      /* igd_t.total: replicated records since the last "spill" */
     int64_t nrec;                       /* replicated records in all */
 } build_t;
 
-static void build_init(build_t *b, int gtype)
+static void part_init(part_t *p)
 {
+    memset(p, 0, sizeof *p);
+    names_init(&p->ctg);
+    p->state_first = p->state_last = -1;
+}
+
+static void part_free(part_t *p)
+{
+    names_free(&p->ctg);
+    free(p->raw);
+}
+
+static void build_init(build_t *b, int gtype, int32_t nparts)
+{
+    phase(NULL);
     memset(b, 0, sizeof *b);
     b->nbp = tile_size, b->gtype = gtype;
     names_init(&b->ctg);
     b->mt_cap = 64;
     b->mtiles = calloc((size_t)b->mt_cap, sizeof(int32_t));
-    b->raw_cap = 1 << 20;
-    b->raw = malloc(sizeof(raw_t) * (size_t)b->raw_cap);
+    b->nparts = nparts;
+    b->part = malloc(sizeof(part_t) * (size_t)(nparts + 1));
+    for (int32_t i = 0; i < nparts; i++) part_init(&b->part[i]);
 }
 
 static void build_free(build_t *b)
 {
+    for (int32_t i = 0; i < b->nparts; i++) part_free(&b->part[i]);
     names_free(&b->ctg);
-    free(b->mtiles), free(b->raw);
+    free(b->mtiles), free(b->part);
 }
 
 /* first tile of an interval; a start below -nbp would index tile -1 in the reference (out of bounds there) */
 static int32_t first_tile(int32_t s, int32_t nbp) { return s < 0 ? 0 : s / nbp; }
 
-/* igd_add / igd0_add (src/igd_base.c:118-174, 176-233): empty intervals vanish BEFORE the contig is looked
- * up; the interval is replicated into the tiles s/nbp .. (e-1)/nbp. */
-static void build_add(build_t *b, const char *chrm, int32_t s, int32_t e, int32_t v, int32_t idx)
+/* igd_add / igd0_add (src/igd_base.c:118-174, 176-233), the part that depends on the line alone: empty
+ * intervals vanish BEFORE the contig is looked up */
+static void part_add(part_t *p, const char *chrm, int32_t s, int32_t e, int32_t v, int32_t idx)
 {
     if (s >= e) return;
-    int32_t c = names_get(&b->ctg, chrm, 1);
-    if (c >= b->mt_cap) {
-        b->mtiles = realloc(b->mtiles, sizeof(int32_t) * (size_t)b->mt_cap * 2);
-        memset(b->mtiles + b->mt_cap, 0, sizeof(int32_t) * (size_t)b->mt_cap);
-        b->mt_cap *= 2;
-    }
-    int32_t n1 = first_tile(s, b->nbp), n2 = (e - 1) / b->nbp;
-    if (n2 + 1 > b->mtiles[c]) b->mtiles[c] = n2 + 1;
-    if (b->nraw == b->raw_cap) b->raw = realloc(b->raw, sizeof(raw_t) * (size_t)(b->raw_cap *= 2));
-    raw_t *r = &b->raw[b->nraw++];
-    r->ctg = c, r->idx = idx, r->start = s, r->end = e, r->value = v;
-    if (n2 >= n1) b->batch += n2 - n1 + 1, b->nrec += n2 - n1 + 1;
+    if (p->nraw == p->cap) p->raw = realloc(p->raw, sizeof(raw_t) * (size_t)(p->cap = p->cap ? p->cap * 2 : 4096));
+    raw_t *r = &p->raw[p->nraw++];
+    r->ctg = names_get(&p->ctg, chrm, 1), r->idx = idx, r->start = s, r->end = e, r->value = v;
 }
 
 /* igd_saveT's progress line (src/igd_base.c:362); nothing is spilled here */
@@ -153,6 +190,39 @@ static void batch_line(build_t *b)
     for (int32_t i = 0; i < b->ctg.n; i++) nt += b->mtiles[i];
     printf("nCtgs, nRegions, nTiles: %i\t %lld\t %lld\n", b->ctg.n, (long long)b->batch, (long long)nt);
     b->batch = 0;
+}
+
+/* The rest of igd_add for one interval whose contig is already numbered: it is replicated into the tiles
+ * s/nbp .. (e-1)/nbp, and a contig has as many tiles as its largest end needs */
+static void account(build_t *b, const raw_t *r)
+{
+    if (r->ctg >= b->mt_cap) {
+        int32_t cap = b->mt_cap;
+        while (r->ctg >= cap) cap *= 2;
+        b->mtiles = realloc(b->mtiles, sizeof(int32_t) * (size_t)cap);
+        memset(b->mtiles + b->mt_cap, 0, sizeof(int32_t) * (size_t)(cap - b->mt_cap));
+        b->mt_cap = cap;
+    }
+    int32_t n1 = first_tile(r->start, b->nbp), n2 = (r->end - 1) / b->nbp;
+    if (n2 + 1 > b->mtiles[r->ctg]) b->mtiles[r->ctg] = n2 + 1;
+    if (n2 >= n1) b->batch += n2 - n1 + 1, b->nrec += n2 - n1 + 1;
+}
+
+/* One part in arrival order: contigs are numbered by first appearance over all parts.  The reference checks
+ * after every line whether its batch exceeds 2^28 records and then closes the file, spills and reopens
+ * (src/igd_create.c:72-91); `spill` reproduces what that prints. */
+static void merge_part(build_t *b, part_t *p, void (*spill)(build_t *, int32_t), int32_t ig)
+{
+    int32_t *global = malloc(sizeof(int32_t) * (size_t)(p->ctg.n + 1));
+    for (int32_t k = 0; k < p->ctg.n; k++) global[k] = -1;
+    for (int64_t i = 0; i < p->nraw; i++) {
+        raw_t *r = &p->raw[i];
+        if (global[r->ctg] < 0) global[r->ctg] = names_get(&b->ctg, p->ctg.name[r->ctg], 1);
+        r->ctg = global[r->ctg];
+        account(b, r);
+        if (b->batch > BATCH_RECORDS) spill(b, ig);
+    }
+    free(global);
 }
 
 /* ---- tile sort ------------------------------------------------------------------------------------------
@@ -212,25 +282,62 @@ static void sort_tile(rec_t *a, int64_t n)
     else sort_level(a, a + n, 24);
 }
 
+/* ---- filling and sorting the tiles: every thread owns a contiguous range of global tile indices ------------ */
 typedef struct {
+    const build_t *b;
+    const int64_t *tbase;               /* [nctg + 1] first global tile of each contig */
+    int64_t *toff;                      /* [T + 1]; pass 1 leaves counts in toff[t + 1] */
     rec_t *rec;
-    const int64_t *toff;
-    int64_t ntiles;
-    int64_t next;                       /* shared cursor, claimed in blocks */
-    pthread_mutex_t mu;
-} sort_job;
+    int64_t *cur;                       /* [T] fill cursors (pass 2) */
+    int64_t t0, t1;                     /* this thread's tiles */
+    int pass;
+} fill_job;
 
-static void *sort_worker(void *arg)
+static void *fill_worker(void *arg)
 {
-    sort_job *J = arg;
-    for (;;) {
-        pthread_mutex_lock(&J->mu);
-        int64_t t0 = J->next, t1 = t0 + 256 < J->ntiles ? t0 + 256 : J->ntiles;
-        J->next = t1;
-        pthread_mutex_unlock(&J->mu);
-        if (t0 >= t1) return NULL;
-        for (int64_t t = t0; t < t1; t++) sort_tile(J->rec + J->toff[t], J->toff[t + 1] - J->toff[t]);
+    fill_job *J = arg;
+    const build_t *b = J->b;
+    if (J->pass == 3) {
+        for (int64_t t = J->t0; t < J->t1; t++) sort_tile(J->rec + J->toff[t], J->toff[t + 1] - J->toff[t]);
+        return NULL;
     }
+    for (int32_t f = 0; f < b->nparts; f++) {
+        const part_t *p = &b->part[f];
+        for (int64_t i = 0; i < p->nraw; i++) {
+            const raw_t *r = &p->raw[i];
+            const int64_t g = J->tbase[r->ctg];
+            int64_t lo = g + first_tile(r->start, b->nbp), hi = g + (r->end - 1) / b->nbp;
+            if (lo < J->t0) lo = J->t0;
+            if (hi >= J->t1) hi = J->t1 - 1;
+            if (lo > hi) continue;
+            if (J->pass == 1) {
+                for (int64_t t = lo; t <= hi; t++) J->toff[t + 1]++;
+            } else {
+                const rec_t x = { r->idx, r->start, r->end, r->value };
+                for (int64_t t = lo; t <= hi; t++) J->rec[J->cur[t]++] = x;
+            }
+        }
+    }
+    return NULL;
+}
+
+static void run_fill(fill_job *jobs, int nth, int pass)
+{
+    pthread_t th[64];
+    int started = 0;
+    for (int i = 0; i < nth; i++) jobs[i].pass = pass;
+    for (int i = 1; i < nth; i++)
+        if (pthread_create(&th[started], NULL, fill_worker, &jobs[i]) == 0) started++;
+        else fill_worker(&jobs[i]);
+    fill_worker(&jobs[0]);
+    for (int i = 0; i < started; i++) pthread_join(th[i], NULL);
+}
+
+static int host_threads(void)
+{
+    const char *e = getenv("IGD_B200_CREATE_THREADS");
+    long nc = e ? atol(e) : sysconf(_SC_NPROCESSORS_ONLN);
+    return (int)(nc < 1 ? 1 : nc > 64 ? 64 : nc);
 }
 
 /* ---- igd_save / igd0_save (src/igd_base.c:396-461, 463-517) --------------------------------------------- */
@@ -246,40 +353,27 @@ static int build_write(build_t *b, const char *opath, const char *name)
     for (int32_t i = 0; i < m; i++) tbase[i + 1] = tbase[i] + b->mtiles[i];
     const int64_t T = tbase[m];
     int64_t *toff = calloc((size_t)T + 2, sizeof(int64_t));
-    /* pass 1: records per tile */
-    for (int64_t i = 0; i < b->nraw; i++) {
-        const raw_t *r = &b->raw[i];
-        int64_t g = tbase[r->ctg];
-        for (int32_t j = first_tile(r->start, b->nbp), n2 = (r->end - 1) / b->nbp; j <= n2; j++) toff[g + j + 1]++;
-    }
     int32_t *ncnt = malloc(sizeof(int32_t) * (size_t)(T + 1));
-    for (int64_t t = 0; t < T; t++) ncnt[t] = (int32_t)toff[t + 1], toff[t + 1] += toff[t];
-    /* pass 2: arrival order inside every tile */
     rec_t *rec = malloc(sizeof(rec_t) * (size_t)(b->nrec + 1));
     int64_t *cur = malloc(sizeof(int64_t) * (size_t)(T + 1));
-    if (!rec || !cur) { printf("Can't alloc mem %lld\n", (long long)(b->nrec * (int64_t)sizeof(rec_t))); return -1; }
-    memcpy(cur, toff, sizeof(int64_t) * (size_t)(T + 1));
-    for (int64_t i = 0; i < b->nraw; i++) {
-        const raw_t *r = &b->raw[i];
-        int64_t g = tbase[r->ctg];
-        rec_t x = { r->idx, r->start, r->end, r->value };
-        for (int32_t j = first_tile(r->start, b->nbp), n2 = (r->end - 1) / b->nbp; j <= n2; j++) rec[cur[g + j]++] = x;
+    if (!rec || !cur || !toff || !ncnt) {
+        printf("Can't alloc mem %lld\n", (long long)(b->nrec * (int64_t)sizeof(rec_t)));
+        return -1;
     }
-    free(cur);
-    free(b->raw), b->raw = NULL;
-    /* sort every tile by start, all cores */
-    {
-        long nc = sysconf(_SC_NPROCESSORS_ONLN);
-        int nth = (int)(nc < 1 ? 1 : nc > 64 ? 64 : nc);
-        if (T < 512) nth = 1;
-        sort_job J = { rec, toff, T, 0, PTHREAD_MUTEX_INITIALIZER };
-        pthread_t th[64];
-        int started = 0;
-        for (int i = 1; i < nth; i++)
-            if (pthread_create(&th[started], NULL, sort_worker, &J) == 0) started++;
-        sort_worker(&J);
-        for (int i = 0; i < started; i++) pthread_join(th[i], NULL);
+    int nth = host_threads();
+    if (T < 4096 || b->nrec < (1 << 18)) nth = 1;
+    fill_job jobs[64];
+    for (int i = 0; i < nth; i++) {
+        fill_job J = { b, tbase, toff, rec, cur, T * i / nth, T * (i + 1) / nth, 0 };
+        jobs[i] = J;
     }
+    run_fill(jobs, nth, 1);                                 /* pass 1: records per tile */
+    for (int64_t t = 0; t < T; t++) ncnt[t] = (int32_t)toff[t + 1], toff[t + 1] += toff[t];
+    memcpy(cur, toff, sizeof(int64_t) * (size_t)T);
+    run_fill(jobs, nth, 2);                                 /* pass 2: arrival order inside every tile */
+    phase("count + scatter into tiles");
+    run_fill(jobs, nth, 3);                                 /* sort every tile by start */
+    phase("sort tiles");
     /* header: nbp, gType, nCtg, nTile[nCtg], nCnt[][], 40-byte names */
     setvbuf(fp, NULL, _IOFBF, 1 << 22);
     fwrite(&b->nbp, 4, 1, fp);
@@ -299,7 +393,8 @@ static int build_write(build_t *b, const char *opath, const char *name)
         for (int64_t i = 0; i < b->nrec; i++) fwrite(&rec[i], 12, 1, fp);      /* gdata0_t = {idx, start, end} */
     int bad = ferror(fp);
     bad |= fclose(fp);
-    free(rec), free(ncnt), free(toff), free(tbase);
+    phase("write");
+    free(rec), free(ncnt), free(toff), free(tbase), free(cur);
     return bad ? -1 : 0;
 }
 
@@ -376,52 +471,106 @@ static char *accept_bed(char *s, int32_t *st_out, int32_t *en_out)
 }
 
 /* ---- the file loop shared by create_igd, create_igd_f and create_igd0 ---------------------------------------
- * The reference reads until igd->total exceeds 2^28, spills, and resumes in the same file at the next line
- * (src/igd_create.c:51-91).  Reading straight through adds the same records in the same order; what is left of
- * the batches is their trace on stdout, reproduced by batch_line() and the dots. */
+ * Files are parsed independently, several at a time.  The one thing a file inherits from its predecessor in the
+ * reference is the splitter's field limit; a file is parsed as if it inherited the initial limit and parsed again,
+ * during the ordered merge, in the rare case where the limit it really inherits would have cut its first line
+ * shorter (parse_file() records the limit after the first line for that check). */
 enum { MODE_DIR, MODE_LIST, MODE_G0 };
+
+static void parse_file(part_t *p, const char *path, int mode, int state_in, int32_t ig)
+{
+    const int linecap = mode == MODE_G0 ? 256 : 1024;       /* gzgets buffer sizes, :46 and :268 */
+    char buffer[1024];
+    splitter S;
+    memset(&S, 0, sizeof S);                                /* no field pointers survive from another file */
+    S.nmax = state_in;
+    gzFile fp = gzopen(path, "r");
+    p->opened = fp != NULL;
+    if (!fp) return;
+    gzbuffer(fp, 1 << 18);
+    while (gzgets(fp, buffer, linecap) != NULL) {
+        if (mode == MODE_LIST) {
+            int32_t st, en;
+            char *ctg = accept_bed(buffer, &st, &en);
+            if (ctg && st >= 0 && en < 321000000) {         /* :188 */
+                part_add(p, ctg, st, en, 0, ig);
+                p->nr++;
+                p->avg += en - st;
+            }
+            continue;
+        }
+        split_line(&S, buffer);
+        if (p->state_first < 0) p->state_first = S.nmax;
+        p->state_last = S.nmax;
+        int32_t st = field_int(&S, 1), en = field_int(&S, 2), va = 0;
+        if (mode == MODE_DIR && S.nmax > 4) va = field_int(&S, 4);
+        part_add(p, S.field[0], st, en, va, ig);
+        p->nr++;
+        p->avg += en - st;
+    }
+    gzclose(fp);
+}
+
+typedef struct {
+    build_t *b;
+    char **file_ids;
+    int mode;
+    int32_t next;
+    pthread_mutex_t mu;
+} parse_job;
+
+static void *parse_worker(void *arg)
+{
+    parse_job *J = arg;
+    for (;;) {
+        pthread_mutex_lock(&J->mu);
+        int32_t ig = J->next++;
+        pthread_mutex_unlock(&J->mu);
+        if (ig >= J->b->nparts) return NULL;
+        parse_file(&J->b->part[ig], J->file_ids[ig], J->mode, 16, ig);
+    }
+}
+
+static int32_t g_nf10;
+static void spill_trace(build_t *b, int32_t ig)             /* the file is closed, the batch spilled (:77-85) */
+{
+    if (g_nf10 && ig % g_nf10 == 0) printf(".");
+    batch_line(b);
+}
+static void spill_quiet(build_t *b, int32_t ig) { (void)ig; b->batch = 0; }    /* igd0_saveT prints nothing */
 
 static void read_files(build_t *b, int mode, int32_t n_files, char **file_ids, int32_t *nr, double *avg)
 {
-    const int linecap = mode == MODE_G0 ? 256 : 1024;       /* gzgets buffer sizes, :46 and :268 */
-    const int32_t nf10 = n_files / 10;
-    char buffer[1024];
-    splitter S;
-    memset(&S, 0, sizeof S);
-    S.nmax = 16;
+    parse_job J = { b, file_ids, mode, 0, PTHREAD_MUTEX_INITIALIZER };
+    int nth = host_threads();
+    if (nth > n_files) nth = n_files;
+    pthread_t th[64];
+    int started = 0;
+    for (int i = 1; i < nth; i++)
+        if (pthread_create(&th[started], NULL, parse_worker, &J) == 0) started++;
+    parse_worker(&J);
+    for (int i = 0; i < started; i++) pthread_join(th[i], NULL);
+    phase("read + parse");
+    g_nf10 = n_files / 10;
+    int state = 16;                                         /* nCols, :45 */
     for (int32_t ig = 0; ig < n_files; ig++) {
-        gzFile fp = gzopen(file_ids[ig], "r");
-        if (!fp) {
+        part_t *p = &b->part[ig];
+        if (!p->opened) {
             if (mode == MODE_LIST) continue;
-            return;                                         /* :57-58 */
+            break;                                          /* :57-58: the reference gives up here */
         }
-        gzbuffer(fp, 1 << 18);
-        while (gzgets(fp, buffer, linecap) != NULL) {
-            if (mode == MODE_LIST) {
-                int32_t st, en;
-                char *ctg = accept_bed(buffer, &st, &en);
-                if (ctg && st >= 0 && en < 321000000) {     /* :188 */
-                    build_add(b, ctg, st, en, 0, ig);
-                    nr[ig]++;
-                    avg[ig] += en - st;
-                }
-            } else {
-                split_line(&S, buffer);
-                int32_t st = field_int(&S, 1), en = field_int(&S, 2), va = 0;
-                if (mode == MODE_DIR && S.nmax > 4) va = field_int(&S, 4);
-                build_add(b, S.field[0], st, en, va, ig);
-                nr[ig]++;
-                avg[ig] += en - st;
-            }
-            if (b->batch > BATCH_RECORDS && mode != MODE_G0) {      /* the reference closes the file, spills, reopens */
-                if (nf10 && ig % nf10 == 0) printf(".");
-                batch_line(b);
-            } else if (b->batch > BATCH_RECORDS) b->batch = 0;      /* igd0_saveT prints nothing */
+        if (mode != MODE_LIST && p->state_first > state + 1) {      /* would have been cut at state + 1 fields */
+            part_free(p);
+            part_init(p);
+            parse_file(p, file_ids[ig], mode, state, ig);
         }
-        gzclose(fp);
-        if (mode != MODE_G0 && nf10 && (ig + 1) % nf10 == 0) printf(".");
+        if (p->state_last >= 0) state = p->state_last;
+        nr[ig] = p->nr, avg[ig] = p->avg;
+        merge_part(b, p, mode == MODE_G0 ? spill_quiet : spill_trace, ig);
+        if (mode != MODE_G0 && g_nf10 && (ig + 1) % g_nf10 == 0) printf(".");
     }
     if (mode != MODE_G0) batch_line(b);
+    phase("merge (contig numbering)");
 }
 
 static void closing_lines(int64_t nT, double l_avg)
@@ -440,7 +589,7 @@ void create_igd(char *iPath, char *oPath, char *igdName)
     int32_t *nr = calloc((size_t)n_files + 1, sizeof(int32_t));
     double *avg = calloc((size_t)n_files + 1, sizeof(double));
     build_t b;
-    build_init(&b, 1);
+    build_init(&b, 1, n_files);
     read_files(&b, MODE_DIR, n_files, g.gl_pathv, nr, avg);
     printf("\n");
     int64_t nT;
@@ -481,7 +630,7 @@ void create_igd_f(char *iPath, char *oPath, char *igdName)
     int32_t *nr = calloc((size_t)n_files + 1, sizeof(int32_t));
     double *avg = calloc((size_t)n_files + 1, sizeof(double));
     build_t b;
-    build_init(&b, 1);
+    build_init(&b, 1, n_files);
     read_files(&b, MODE_LIST, n_files, file_ids, nr, avg);
     printf("\n");
     int64_t nT;
@@ -506,7 +655,7 @@ void create_igd0(char *iPath, char *oPath, char *igdName)
     double *avg = calloc((size_t)n_files + 1, sizeof(double));
     printf("igd_create 1: %i\n", n_files);
     build_t b;
-    build_init(&b, 0);
+    build_init(&b, 0, n_files);
     read_files(&b, MODE_G0, n_files, g.gl_pathv, nr, avg);
     int64_t nT;
     double l_avg;
@@ -526,7 +675,8 @@ void create_igd_bed4(char *iPath, char *oPath, char *igdName)
 {
     printf("igd_create 1\n");
     build_t b;
-    build_init(&b, 1);
+    build_init(&b, 1, 1);
+    part_t *P = &b.part[0];             /* one input file: its contig numbering is the global one */
     names_t sets;
     names_init(&sets);
     int32_t cap = 1024;
@@ -536,7 +686,7 @@ void create_igd_bed4(char *iPath, char *oPath, char *igdName)
     splitter S;
     memset(&S, 0, sizeof S);
     S.nmax = 32;
-    int64_t nL = 0;
+    int64_t nL = 0, seen = 0;
     int spills = 0;
     gzFile fp = gzopen(iPath, "r");
     while (fp && gzgets(fp, buffer, sizeof buffer) != NULL) {
@@ -550,10 +700,15 @@ void create_igd_bed4(char *iPath, char *oPath, char *igdName)
             cap *= 2;
         }
         int32_t st = field_int(&S, 1), en = field_int(&S, 2);
-        build_add(&b, S.field[0], st, en, field_int(&S, 4), idx);
+        part_add(P, S.field[0], st, en, field_int(&S, 4), idx);
         nr[idx]++;
         avg[idx] += en - st;
         nL++;
+        if (P->nraw > seen) {           /* the line added an interval: account for it in step with the reading */
+            const raw_t *r = &P->raw[seen++];
+            if (r->ctg == b.ctg.n) names_get(&b.ctg, P->ctg.name[r->ctg], 1);
+            account(&b, r);
+        }
         if (b.batch >= BATCH_RECORDS) {
             printf("--igd_saveT1--%i, %lld\n", ++spills, (long long)b.batch);
             batch_line(&b);

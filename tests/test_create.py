@@ -61,6 +61,11 @@ def write_inputs(bed, seed=0, n_files=12, n=3000, gz_every=4):
         lines.insert(9, "chr1\t100\t200\n")            # three columns: no value
         lines.insert(10, "chr3\t10\t20\t.\t7\textra\tcols\there\n")
         lines.append("chrNew%d\t5\t50000\t.\t1\n" % (i % 3))       # contigs appearing late
+        if i % 5 == 2:      # the splitter's field limit crosses files: this one ends on 3-column lines ...
+            lines += ["chr1\t%d\t%d\n" % (900 + k, 1900 + k) for k in range(3)]
+        if i % 5 == 3:      # ... so the next one's first 6-column line is cut at 4 fields and loses its value
+            lines.insert(0, "chr2\t4000\t4800\tname\t777\t-\n")
+            lines.insert(1, "chr2\t4100\t4900\tname\t778\t-\n")
         p = os.path.join(bed, f"f{i:05d}.bed")
         if gz_every and i % gz_every == 1:
             with gzip.open(p + ".gz", "wt") as f:
@@ -163,6 +168,22 @@ def test_create_dense_tiles_radix_levels(workdir):
     m = int(np.frombuffer(got["igd"], np.int32, 1, 8)[0])
     ntiles = int(np.frombuffer(got["igd"], np.int32, m, 12).sum())
     assert nrec / ntiles > 1000
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built")
+def test_create_hg38_threads(workdir):
+    """hg38-sized tile table (188 k tiles): the multi-threaded fill and sort, against the reference and against a
+    single-threaded run of itself"""
+    bed = os.path.join(workdir, "create_bed_hg38")
+    synth.write_bed_files(bed, 2, 20, 20000, ("lognormal", 6.0, 1.0))
+    ref = outputs(O.REF_BIN, workdir, bed, "ref_hg38", [])
+    got = outputs(api.CLI_PATH, workdir, bed, "mine_hg38", [])
+    assert got == ref
+    out1 = os.path.join(workdir, "mine_hg38_1t") + "/"
+    r = subprocess.run([api.CLI_PATH, "create", bed, out1, "db"], capture_output=True,
+                       env=dict(os.environ, IGD_B200_CREATE_THREADS="1"))
+    assert r.returncode == 0
+    assert canonical_igd(out1 + "db.igd") == got["igd"]
 
 
 def hdr_len(b: bytes) -> int:
