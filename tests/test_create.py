@@ -186,6 +186,43 @@ def test_create_hg38_threads(workdir):
     assert canonical_igd(out1 + "db.igd") == got["igd"]
 
 
+def test_create_under_asan_ubsan(inputs, workdir):
+    """the host C of `igd create` built with -fsanitize=address,undefined (sanitizer builds of the
+    host C) over every flavour: no report, and the same bytes as the product binary"""
+    import shutil
+    src = os.path.join(os.path.dirname(api.LIB_PATH), "..", "csrc", "igd_create.c")
+    inc = os.path.dirname(api.HEADER_PATH)
+    main_c = os.path.join(workdir, "asan_main.c")
+    with open(main_c, "w") as f:
+        f.write("int igd_create(int argc, char **argv);\nint main(int c, char **v) { return igd_create(c, v); }\n")
+    exe = os.path.join(workdir, "igd_create_asan")
+    cc = shutil.which("gcc") or "gcc"
+    r = subprocess.run([cc, "-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-I", inc, "-o", exe,
+                        main_c, src, "-lz", "-lpthread", "-lm"], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("no sanitizer runtime here: " + r.stderr[-200:])
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=1:halt_on_error=1", UBSAN_OPTIONS="halt_on_error=1:print_stacktrace=1")
+    for case, opts in CASES.items():
+        out = os.path.join(workdir, "asan_" + case) + "/"
+        r = subprocess.run([exe, "create", inputs, out, "db", *opts], capture_output=True, env=env)
+        assert r.returncode == 0 and b"ERROR" not in r.stderr and b"runtime error" not in r.stderr, r.stderr.decode()[-2000:]
+        ref = os.path.join(workdir, "mine_gold_" + case, "db.igd")
+        if os.path.exists(ref):
+            assert canonical_igd(out + "db.igd") == canonical_igd(ref)
+    lst = os.path.join(workdir, "asan_sources.txt")
+    with open(lst, "w") as f:
+        f.write("\n".join(sorted(os.path.join(inputs, x) for x in os.listdir(inputs))) + "\n/nonexistent\n")
+    r = subprocess.run([exe, "create", lst, os.path.join(workdir, "asan_list"), "db", "-f"], capture_output=True, env=env)
+    assert r.returncode == 0 and b"ERROR" not in r.stderr and b"runtime error" not in r.stderr, r.stderr.decode()[-2000:]
+    bed4 = os.path.join(workdir, "asan_bed4.bed")
+    with open(bed4, "w") as f:
+        for k in range(5000):
+            f.write(f"chr{1 + k % 3}\t{k * 37}\t{k * 37 + 500 + k % 900}\tTF{k % 23}\t{k % 1000}\n")
+        f.write("chr1\t5\n\nchr2\n")
+    r = subprocess.run([exe, "create", bed4, os.path.join(workdir, "asan_b4"), "db", "-s", "2"], capture_output=True, env=env)
+    assert r.returncode == 0 and b"ERROR" not in r.stderr and b"runtime error" not in r.stderr, r.stderr.decode()[-2000:]
+
+
 def hdr_len(b: bytes) -> int:
     m = int(np.frombuffer(b, np.int32, 1, 8)[0])
     return 12 + 44 * m + 4 * int(np.frombuffer(b, np.int32, m, 12).sum())
