@@ -1,0 +1,77 @@
+"""Work-item boundaries of the count kernels (an item = up to 256 records of one tile x up to 64 segments): tiles
+of every size around 8 / 256 / 512 / 768 records, and tiles whose first 300 records all start before the bin (the
+later-bin dedupe rule decided in a tile's second item), with and without -v, against the oracle.
+
+(A variant of the packed kernel that let a tile's last item carry up to 64 records past 256 -- 26 % fewer items at
+BASELINE config 2 -- was built on these tests and measured SLOWER, 0.167 vs 0.159 ms: the small remainder items are
+cheap, their windows prune almost every segment.  It was dropped; profiles/r1l_tail_variant.json keeps the numbers.)"""
+import os
+
+import numpy as np
+import pytest
+
+from igd_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+NBP = 16384
+
+
+def boundary_db(stem):
+    """one contig; tile k holds a chosen number of records around 256 / 320 / 512 / 576 ..., plus 300 long records
+    that start in tile 0 and span tiles 0..3 (so tiles 1..3 begin with 300 records that start before the bin)"""
+    sizes = [1, 7, 8, 9, 255, 256, 257, 300, 319, 320, 321, 322, 383, 384, 500, 511, 512, 513, 525, 575, 576, 577,
+             578, 640, 767, 768, 769, 832, 833, 1100]
+    rng = np.random.default_rng(2024)
+    files = []
+    nfiles = 12
+    per_file = [[] for _ in range(nfiles)]
+    for k, n in enumerate(sizes):
+        t = 4 + k                                   # tiles 4.. hold the sized sets (short records inside the bin)
+        s = rng.integers(t * NBP, (t + 1) * NBP - 700, n)
+        ln = rng.integers(1, 600, n)
+        for a, b in zip(s, ln):
+            per_file[int(rng.integers(0, nfiles))].append((0, int(a), int(a + b), int(rng.integers(0, 1000))))
+    for j in range(300):                            # long records over tiles 0..3
+        a = int(rng.integers(100, 9000))
+        per_file[j % nfiles].append((0, a, a + 3 * NBP + int(rng.integers(0, 6000)), int(rng.integers(0, 1000))))
+    for t in (1, 2, 3):                             # a few in-bin records in those tiles: 300 + r records each
+        for j in range((5, 20, 63)[t - 1]):
+            a = int(rng.integers(t * NBP + 10, (t + 1) * NBP - 500))
+            per_file[j % nfiles].append((0, a, a + int(rng.integers(1, 400)), int(rng.integers(0, 1000))))
+    for rows in per_file:
+        r = np.array(rows, np.int64)
+        files.append(synth.Intervals(r[:, 0].astype(np.int32), r[:, 1].astype(np.int32), r[:, 2].astype(np.int32),
+                                     r[:, 3].astype(np.int32)))
+    synth.write_igd_direct(stem, files, names=["chrT"])
+    return (4 + len(sizes)) * NBP
+
+
+def queries(span, seed, n):
+    rng = np.random.default_rng(seed)
+    s = rng.integers(0, span, n)
+    ln = np.where(rng.random(n) < 0.8, rng.integers(1, 2000, n), rng.integers(2000, 5 * NBP, n))
+    return np.zeros(n, np.int32), s.astype(np.int32), (s + ln).astype(np.int32)
+
+
+@pytest.fixture(scope="module")
+def db(workdir):
+    stem = os.path.join(workdir, "tail_db")
+    span = boundary_db(stem)
+    return stem + ".igd", span
+
+
+@pytest.mark.parametrize("v", [0, 1, 500])
+def test_item_boundaries(db, v):
+    from igd_b200 import api
+    from oracle import oracle as O
+    path, span = db
+    odb = O.OracleDB(path)
+    with api.IGD(path) as g:
+        for seed, n in ((1, 30000), (2, 17), (3, 1000)):
+            ctg, qs, qe = queries(span, seed, n)
+            want, _ = odb.count(ctg, qs, qe, v)
+            got, _ = g.count(ctg, qs, qe, v)
+            assert np.array_equal(got, want), (v, seed)
+        items = g.last_plan()["items"]
+    assert want.sum() > 0 and items > 0
