@@ -97,6 +97,8 @@ def load_library():
     L.igd_b200_full.restype = C.c_int
     L.igd_b200_full.argtypes = [vp, C.c_int64, _i32p, _i32p, _i32p, C.POINTER(_HitList)]
     L.igd_b200_hitlist_free.argtypes = [C.POINTER(_HitList)]
+    L.igd_b200_full_device.restype = C.c_int64
+    L.igd_b200_full_device.argtypes = [vp, C.c_int64, vp, vp, vp, vp, C.POINTER(vp), C.POINTER(vp)]
     L.igd_b200_hitsmap.restype = C.c_int64
     L.igd_b200_hitsmap.argtypes = [vp, C.c_int32, _u32p]
     L.igd_b200_hitsmap_tiles.restype = C.c_int64
@@ -152,6 +154,15 @@ def create(iPath: str, oPath: str, igdName: str, bin_size: int = 16384) -> bool:
     """igd_py.create(iPath, oPath, igdName, bin_size) (src_py/igd_py.pyx:33-34): build <oPath>/<igdName>.igd from
     the BED(.gz) files under iPath -- host C, no GPU needed.  False if the database exists already."""
     return load_library().create_iGD(os.fsencode(iPath), os.fsencode(oPath), igdName.encode(), int(bin_size)) == 0
+
+
+class device_view:
+    """A typed window on device memory owned by the library (``__cuda_array_interface__``): ``torch.as_tensor(
+    device_view(ptr, n, "<i4"), device="cuda")`` is a tensor over the same bytes, no copy."""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"data": (int(ptr), False), "shape": (int(n),), "typestr": typestr,
+                                         "version": 2, "strides": None}
 
 
 class QuerySet:
@@ -370,6 +381,16 @@ class IGD:
             return qoff, mk(hl.start), mk(hl.end), mk(hl.file)
         finally:
             self._L.igd_b200_hitlist_free(C.byref(hl))
+
+    def full_device(self, n: int, d_ctg: int, d_qs: int, d_qe: int, stream: int = 0):
+        """-f, device to device: raw device pointers in, ``(total, d_query_off, d_lists)`` out -- ``d_query_off``
+        is int64[n + 1], ``d_lists`` int32 ``start[total] | end[total] | file[total]``; both are owned by the
+        handle until the next ``full_device``.  :func:`device_view` wraps them for torch without a copy."""
+        qoff, lst = C.c_void_p(), C.c_void_p()
+        t = self._L.igd_b200_full_device(self._need(), n, d_ctg, d_qs, d_qe, stream, C.byref(qoff), C.byref(lst))
+        if t < 0:
+            raise IGDError(last_error())
+        return int(t), qoff.value or 0, lst.value or 0
 
     # -- -m / -s -----------------------------------------------------------------------------------------
     def hitsmap(self, v: int = 0, tiles: tuple[int, int] | None = None) -> np.ndarray:

@@ -70,6 +70,11 @@ int igdb_dev_hits_end(igdb_dev *d, uint64_t *hits_delta);
 int64_t igdb_dev_full_host(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_t *qs, const int32_t *qe,
                            int64_t **query_off, int32_t **start, int32_t **end, int32_t **file, float *t_ms);
 
+/* -f, device to device: queries in device buffers, results left in HBM -- *d_query_off = int64[n+1],
+ * *d_lists = int32 start[total] | end[total] | file[total]; both owned by the handle until the next call. */
+int64_t igdb_dev_full_device(igdb_dev *d, int64_t n, const int32_t *d_ctg, const int32_t *d_qs, const int32_t *d_qe,
+                             void *stream, int64_t **d_query_off, int32_t **d_lists);
+
 /* -s: n queries grouped by query-file chrom (grp[] ascending) and start-sorted inside a group; grp_nq[g] =
  * queries of group g; acc[nfiles] = sum of matched similarities per file */
 int igdb_dev_seqpare(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_t *qs, const int32_t *qe,

@@ -302,4 +302,43 @@ int64_t igdb_dev_full_host(igdb_dev *d, int64_t n, const int32_t *ctg, const int
     return total;
 }
 
+// -f with everything left on the device: queries come from device buffers, query_off[n+1] (int64) and the lists
+// start[total] | end[total] | file[total] (int32, one allocation) stay in HBM, owned by the handle until the next
+// call of this function (or destroy).  What a multi-GPU driver hands to its gather without crossing the host.
+int64_t igdb_dev_full_device(igdb_dev *d, int64_t n, const int32_t *d_ctg, const int32_t *d_qs, const int32_t *d_qe,
+                             void *stream, int64_t **d_query_off, int32_t **d_lists)
+{
+    g_err[0] = 0;
+    *d_query_off = nullptr, *d_lists = nullptr;
+    CK(cudaSetDevice(d->device));
+    if (finish_pending(d)) return -1;
+    if (n < 0 || n >= (1 << 26)) {
+        snprintf(g_err, sizeof g_err, "igdb_dev_full_device: batch of %lld queries is too large", (long long)n);
+        return -1;
+    }
+    cudaStream_t st = stream ? (cudaStream_t)stream : d->stream;
+    if (d->dres_qoff) cudaFree(d->dres_qoff);
+    if (d->dres_out) cudaFree(d->dres_out);
+    d->dres_qoff = d->dres_out = nullptr;
+    DevBuf qoff, out;
+    int64_t total = 0;
+    if (n == 0 || d->T == 0) {
+        if (qoff.alloc(((size_t)n + 1) * 8)) return -1;
+        CK(cudaMemsetAsync(qoff.p, 0, ((size_t)n + 1) * 8, st));
+    } else {
+        if (ensure_query_cap(d, n)) return -1;
+        CK(cudaMemcpyAsync(d->q_ctg, d_ctg, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(d->q_qs, d_qs, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(d->q_qe, d_qe, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+        total = full_device(d, n, st, false, qoff, out);
+        if (total < 0) return -1;
+    }
+    CK(cudaStreamSynchronize(st));
+    d->dres_qoff = qoff.p, d->dres_out = out.p;
+    qoff.p = out.p = nullptr;                                   // ownership moves to the handle
+    *d_query_off = (int64_t *)d->dres_qoff;
+    *d_lists = (int32_t *)d->dres_out;
+    return total;
+}
+
 }  // extern "C"

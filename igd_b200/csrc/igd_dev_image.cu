@@ -123,6 +123,8 @@ void igdb_dev_destroy(igdb_dev *d)
                     d->ctg_names, d->ctg_slots, d->d_text};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    if (d->dres_qoff) cudaFree(d->dres_qoff);
+    if (d->dres_out) cudaFree(d->dres_out);
     if (d->pinned) cudaFreeHost(d->pinned);
     if (d->arena) cudaFreeHost(d->arena);
     if (d->h_scalar) cudaFreeHost(d->h_scalar);

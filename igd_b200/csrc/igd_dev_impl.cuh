@@ -280,6 +280,7 @@ struct igdb_dev {
     uint32_t ctg_mask = 0;
     void *arena = nullptr;                  // pinned host arena of the -f result lists
     size_t arena_cap = 0;
+    void *dres_qoff = nullptr, *dres_out = nullptr;     // device-resident -f result of the last igdb_dev_full_device
     char *d_text = nullptr;                 // query text staging
     size_t d_text_cap = 0;
     bool packed = false;

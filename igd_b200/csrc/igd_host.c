@@ -275,6 +275,13 @@ int igd_b200_full(igd_b200_t *h, int64_t n, const int32_t *ctg, const int32_t *q
     return 0;
 }
 
+int64_t igd_b200_full_device(igd_b200_t *h, int64_t n, const int32_t *d_ctg, const int32_t *d_qs, const int32_t *d_qe,
+                             void *stream, int64_t **d_query_off, int32_t **d_lists)
+{
+    g_err[0] = 0;
+    return igdb_dev_full_device(h->dev, n, d_ctg, d_qs, d_qe, stream, d_query_off, d_lists);
+}
+
 /* the arrays belong to the handle's pinned arena: nothing to release, the struct is just cleared */
 void igd_b200_hitlist_free(igd_b200_hitlist *l)
 {

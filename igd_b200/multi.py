@@ -5,7 +5,9 @@
                estimated scan bytes; per-rank ``hits[]``; ONE int64 allreduce (nFiles elements).
 * -f         : the same shards; every rank sends its overlaps to ``dst`` (sizes by all_gather, payload by
                point-to-point send/recv), which restores the ORIGINAL query order -- the result is identical to
-               a single-GPU ``full()`` on the unsorted input.
+               a single-GPU ``full()`` on the unsorted input.  With the CUDA engine and a CUDA communicator the
+               lists never touch the host on the way: ``igd_b200_full_device`` leaves them in HBM, NCCL sends
+               them from there, and the order is restored on ``dst``'s GPU.
 * -m         : tiles are independent (getMap, src/igd_search.c:780-782): contiguous tile ranges balanced by the
                self-join cost estimate sum(nCnt^2); per-rank uint32 maps; one allreduce (two's-complement int32
                addition wraps exactly like the reference's uint32 counters).
@@ -76,6 +78,8 @@ class ShardedSearch:
         dist = self.dist
         order, cs, ss, es, b = self._plan(ctg, qs, qe)
         lo, hi = b[self.rank], b[self.rank + 1]
+        if str(self.dev) != "cpu" and hasattr(self.e, "full_device"):
+            return self._full_on_device(order, cs[lo:hi], ss[lo:hi], es[lo:hi], b, dst)
         qoff, s, e, f = self.e.full(cs[lo:hi], ss[lo:hi], es[lo:hi])
         mine = torch.tensor([int(qoff[-1])], dtype=torch.int64, device=self.dev)
         sizes = [torch.zeros_like(mine) for _ in range(self.world)]
@@ -112,6 +116,53 @@ class ShardedSearch:
         total = int(qoff_o[-1])
         src = np.repeat(soff[pos], cnt_orig) + (np.arange(total) - np.repeat(qoff_o[:-1], cnt_orig))
         return qoff_o, pay[0][src], pay[1][src], pay[2][src]
+
+    def _full_on_device(self, order, cs, ss, es, b, dst):
+        """-f with the lists resident in HBM from the search to the restored order (one D2H at the very end)."""
+        import torch
+
+        from .api import device_view
+        dist, dev = self.dist, self.dev
+        n = len(cs)
+        d_c, d_s, d_e = self._t(cs), self._t(ss), self._t(es)
+        stream = torch.cuda.current_stream().cuda_stream
+        total, p_qoff, p_lists = self.e.full_device(n, d_c.data_ptr(), d_s.data_ptr(), d_e.data_ptr(), stream)
+        qoff = torch.as_tensor(device_view(p_qoff, n + 1, "<i8"), device=dev)
+        cnt = (qoff[1:] - qoff[:-1]).contiguous()
+        pay = (torch.as_tensor(device_view(p_lists, 3 * total, "<i4"), device=dev).view(3, total) if total
+               else torch.zeros((3, 0), dtype=torch.int32, device=dev))
+        mine = torch.tensor([total], dtype=torch.int64, device=dev)
+        sizes = [torch.zeros_like(mine) for _ in range(self.world)]
+        dist.all_gather(sizes, mine, group=self.group)
+        sizes = [int(x.item()) for x in sizes]
+        if self.rank != dst:
+            dist.send(cnt, dst, group=self.group)
+            if total:
+                dist.send(pay.contiguous(), dst, group=self.group)
+            return None
+        cnts, pays = [], []
+        for r in range(self.world):
+            if r == dst:
+                cnts.append(cnt), pays.append(pay)
+                continue
+            c = torch.empty(b[r + 1] - b[r], dtype=torch.int64, device=dev)
+            dist.recv(c, r, group=self.group)
+            p = torch.empty((3, sizes[r]), dtype=torch.int32, device=dev)
+            if sizes[r]:
+                dist.recv(p, r, group=self.group)
+            cnts.append(c), pays.append(p)
+        cnt_sorted, pay = torch.cat(cnts), torch.cat(pays, dim=1)
+        nq = len(order)
+        pos = torch.empty(nq, dtype=torch.int64, device=dev)
+        pos[torch.from_numpy(order).to(dev)] = torch.arange(nq, device=dev)
+        soff = torch.cumsum(cnt_sorted, 0) - cnt_sorted
+        cnt_orig = cnt_sorted[pos]
+        qoff_o = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(cnt_orig, 0)])
+        tot = int(qoff_o[-1].item())
+        src = (torch.repeat_interleave(soff[pos] - qoff_o[:-1], cnt_orig, output_size=tot)
+               + torch.arange(tot, device=dev))
+        out = pay[:, src]
+        return (qoff_o.cpu().numpy(), out[0].cpu().numpy(), out[1].cpu().numpy(), out[2].cpu().numpy())
 
     # ---- -m --------------------------------------------------------------------------------------
     def hitsmap(self, v: int = 0) -> np.ndarray:

@@ -102,6 +102,13 @@ typedef struct {
 int igd_b200_full(igd_b200_t *h, int64_t n, const int32_t *ctg, const int32_t *qs, const int32_t *qe,
                   igd_b200_hitlist *out);
 void igd_b200_hitlist_free(igd_b200_hitlist *l);
+/* the same with every buffer on the handle's device: the queries are read from device memory and the result stays
+ * there -- *d_query_off = int64[n + 1], *d_lists = int32 start[total] | end[total] | file[total] (one allocation),
+ * both owned by the handle until the next igd_b200_full_device call or igd_b200_close.  The work is enqueued on
+ * `stream` (a cudaStream_t; NULL = the handle's own) and has completed when the call returns.  Returns total or a
+ * negative error code.  This is what a multi-GPU -f hands to its gather (NCCL reads the lists where they are). */
+int64_t igd_b200_full_device(igd_b200_t *h, int64_t n, const int32_t *d_ctg, const int32_t *d_qs, const int32_t *d_qe,
+                             void *stream, int64_t **d_query_off, int32_t **d_lists);
 
 /* -m: getMap / getMap_v (src/igd_search.c:772-886) as one dense row-major uint32[nFiles*nFiles],
  * incremented (wraps mod 2^32 like the reference).  v > 0 selects the strict `value > v` filter.

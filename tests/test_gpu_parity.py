@@ -291,3 +291,29 @@ def test_count_v_thresholds_and_negative_values(workdir, O, api):
         assert n == want.sum()
     assert odb.count(q.ctg, q.start, q.end, 32767)[0].sum() > 0
     g.close()
+
+
+def test_full_device_matches_full(dense_db, api):
+    """igd_b200_full_device (queries read from HBM, lists left in HBM) = igd_b200_full, viewed through torch
+    without a copy; the handle keeps the buffers until the next call"""
+    import torch
+    q = make_queries(31, 6000, ("lognormal", 7.5, 1.5))
+    with api.IGD(dense_db) as g:
+        qoff, s, e, f = g.full(q.ctg, q.start, q.end)
+        dev = torch.device("cuda", 0)
+        d = [torch.from_numpy(np.ascontiguousarray(x, np.int32)).to(dev) for x in (q.ctg, q.start, q.end)]
+        n = len(q.ctg)
+        total, p_off, p_lists = g.full_device(n, d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr())
+        assert total == len(s) > 0
+        t_off = torch.as_tensor(api.device_view(p_off, n + 1, "<i8"), device=dev)
+        t_l = torch.as_tensor(api.device_view(p_lists, 3 * total, "<i4"), device=dev).view(3, total)
+        assert np.array_equal(t_off.cpu().numpy(), qoff)
+        got = t_l.cpu().numpy()
+        assert np.array_equal(got[0], s) and np.array_equal(got[1], e) and np.array_equal(got[2], f)
+        # an empty batch, and a batch without overlaps
+        total, p_off, p_lists = g.full_device(0, 0, 0, 0)
+        assert total == 0
+        far = torch.full((4,), -1, dtype=torch.int32, device=dev)          # unknown contigs
+        total, p_off, _ = g.full_device(4, far.data_ptr(), d[1].data_ptr(), d[2].data_ptr())
+        assert total == 0
+        assert torch.as_tensor(api.device_view(p_off, 5, "<i8"), device=dev).cpu().tolist() == [0] * 5
