@@ -148,6 +148,59 @@ __global__ void k_seq_sweep(const unsigned long long *__restrict__ key, const ui
     npick[pid] = np;
 }
 
+// The same sweep, one WARP per problem.  A candidate whose row or column is taken stays rejected for good (the
+// tables only grow), so the lanes test 32 candidates at a time against the tables -- their key / value / row /
+// column gathers in flight together instead of one dependent chain per candidate -- and only the few that pass
+// are replayed in order by lane 0, which tests them again (an earlier one of the same batch may have taken their
+// row or column) and inserts.  Picks and their order are exactly those of k_seq_sweep.
+__global__ void k_seq_sweep_warp(const unsigned long long *__restrict__ key, const uint32_t *__restrict__ val,
+                                 const uint32_t *__restrict__ row, const unsigned long long *__restrict__ col,
+                                 int64_t nprob, const int64_t *__restrict__ pstart, const uint32_t *__restrict__ tsize,
+                                 const unsigned long long *__restrict__ toff, unsigned long long *__restrict__ tables,
+                                 float *__restrict__ pick, uint32_t *__restrict__ npick)
+{
+    const int64_t pid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (pid >= nprob) return;
+    const int64_t a = pstart[pid], b = pstart[pid + 1];
+    uint32_t np = 0;
+    if (b > a) {
+        unsigned long long *t = tables + toff[pid];
+        const uint32_t mask = tsize[pid] - 1;
+        for (int64_t base = a; base < b; base += 32) {
+            const int64_t i = base + lane;
+            const bool valid = i < b;
+            const uint32_t bits = valid ? ~(uint32_t)key[i] : 0u;
+            const bool alive = valid && (int32_t)bits > 0;              // similarity 0: the reference stops (maxf == 0)
+            unsigned long long r = 0, cc = 0;
+            bool open = false;
+            if (alive) {
+                const uint32_t c = val[i];
+                r = 1ull << 63 | row[c], cc = col[c];
+                open = !seq_probe(t, mask, r, false) && !seq_probe(t, mask, cc, false);
+            }
+            unsigned m = __ballot_sync(FULL, open);
+            while (m) {
+                const int j = __ffs(m) - 1;
+                m &= m - 1;
+                const unsigned long long rj = __shfl_sync(FULL, r, j), cj = __shfl_sync(FULL, cc, j);
+                const uint32_t bj = __shfl_sync(FULL, bits, j);
+                int took = 0;
+                if (lane == 0 && !seq_probe(t, mask, rj, false) && !seq_probe(t, mask, cj, false)) {
+                    seq_probe(t, mask, rj, true);
+                    seq_probe(t, mask, cj, true);
+                    pick[a + np] = __uint_as_float(bj);
+                    took = 1;
+                }
+                __syncwarp();                                           // lane 0's inserts, for everybody's next probes
+                np += __shfl_sync(FULL, took, 0);
+            }
+            if (__any_sync(FULL, valid && !alive)) break;
+        }
+    }
+    if (lane == 0) npick[pid] = np;
+}
+
 // sm[m] += maxf in the reference's order (src/igd_search.c:367,397,419): chrom groups ascending, picks in order
 __global__ void k_seq_sum(int32_t nfiles, int32_t ngroups, const int64_t *__restrict__ pstart,
                           const float *__restrict__ pick, const uint32_t *__restrict__ npick, double *__restrict__ acc)
@@ -242,11 +295,21 @@ int igdb_dev_seqpare(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_t *
                  (long long)n, (long long)nprob);
         return -1;
     }
+    // IGD_B200_DEBUG: stage times on stderr (events on the stream)
+    const bool dbg = getenv("IGD_B200_DEBUG") != nullptr;
+    cudaEvent_t tev[6] = {};
+    auto mark = [&](int k) {
+        if (!dbg) return;
+        if (!tev[k]) cudaEventCreate(&tev[k]);
+        cudaEventRecord(tev[k], st);
+    };
+    mark(0);
     if (upload_queries(d, n, ctg, qs, qe, st)) return -1;
     DevBuf qoff, out;
     const int64_t total = full_device(d, n, st, true, qoff, out);
     if (total < 0) return -1;
     if (total == 0) return 0;
+    mark(1);
     if (total >= (1ll << 31)) {
         snprintf(g_err, sizeof g_err, "Seqpare: %lld candidate pairs exceed one pass (2^31)", (long long)total);
         return -1;
@@ -264,6 +327,7 @@ int igdb_dev_seqpare(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_t *
         o + 3 * total, b_key.as<unsigned long long>(), b_val.as<uint32_t>(), b_row.as<uint32_t>(),
         b_col.as<unsigned long long>());
     CK(cudaGetLastError());
+    mark(2);
     // stable LSD radix sort (CUB, a library primitive) on the used key bits only
     int end_bit = 32;
     while (end_bit < 64 && (nprob >> (end_bit - 32)) != 0) ++end_bit;
@@ -275,6 +339,7 @@ int igdb_dev_seqpare(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_t *
     CK(cub::DeviceRadixSort::SortPairs(b_tmp.p, tmp_bytes, b_key.as<unsigned long long>(),
                                        b_key2.as<unsigned long long>(), b_val.as<uint32_t>(), b_val2.as<uint32_t>(),
                                        (int)total, 0, end_bit, st));
+    mark(3);
     DevBuf b_pstart, b_tsize, b_toff, b_tab, b_pick, b_npick, b_acc;
     if (b_pstart.alloc((size_t)(nprob + 1) * 8) || b_tsize.alloc((size_t)(nprob + 1) * 4) ||
         b_toff.alloc((size_t)(nprob + 1) * 8) || b_pick.alloc((size_t)total * 4) ||
@@ -296,16 +361,33 @@ int igdb_dev_seqpare(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_t *
         return -1;
     }
     CK(cudaMemsetAsync(b_tab.p, 0, std::max<size_t>(slots * 8, 16), st));
-    k_seq_sweep<<<(unsigned)((nprob + 127) / 128), 128, 0, st>>>(
-        b_key2.as<unsigned long long>(), b_val2.as<uint32_t>(), b_row.as<uint32_t>(), b_col.as<unsigned long long>(),
-        nprob, b_pstart.as<int64_t>(), b_tsize.as<uint32_t>(), b_toff.as<unsigned long long>(),
-        b_tab.as<unsigned long long>(), b_pick.as<float>(), b_npick.as<uint32_t>());
+    static const bool thread_sweep = getenv("IGD_B200_SEQ_THREAD_SWEEP") != nullptr;    // the one-thread-per-problem form
+    if (thread_sweep)
+        k_seq_sweep<<<(unsigned)((nprob + 127) / 128), 128, 0, st>>>(
+            b_key2.as<unsigned long long>(), b_val2.as<uint32_t>(), b_row.as<uint32_t>(), b_col.as<unsigned long long>(),
+            nprob, b_pstart.as<int64_t>(), b_tsize.as<uint32_t>(), b_toff.as<unsigned long long>(),
+            b_tab.as<unsigned long long>(), b_pick.as<float>(), b_npick.as<uint32_t>());
+    else
+        k_seq_sweep_warp<<<(unsigned)((nprob * 32 + 255) / 256), 256, 0, st>>>(
+            b_key2.as<unsigned long long>(), b_val2.as<uint32_t>(), b_row.as<uint32_t>(), b_col.as<unsigned long long>(),
+            nprob, b_pstart.as<int64_t>(), b_tsize.as<uint32_t>(), b_toff.as<unsigned long long>(),
+            b_tab.as<unsigned long long>(), b_pick.as<float>(), b_npick.as<uint32_t>());
+    mark(4);
     k_seq_sum<<<(d->nfiles + 127) / 128, 128, 0, st>>>(d->nfiles, ngroups, b_pstart.as<int64_t>(), b_pick.as<float>(),
                                                        b_npick.as<uint32_t>(), b_acc.as<double>());
+    mark(5);
     d->launches += 5;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(acc, b_acc.p, (size_t)d->nfiles * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    if (dbg) {
+        float ms[5] = {};
+        for (int k = 0; k < 5; ++k) cudaEventElapsedTime(&ms[k], tev[k], tev[k + 1]);
+        fprintf(stderr, "[igd_b200] seqpare: %lld pairs, %lld problems; -f lists %.2f ms, candidates %.2f, sort %.2f, "
+                        "ranges+tables+sweep %.2f, sum %.2f\n", (long long)total, (long long)nprob, ms[0], ms[1], ms[2],
+                ms[3], ms[4]);
+        for (auto &e : tev) if (e) cudaEventDestroy(e);
+    }
     return 0;
 }
 
