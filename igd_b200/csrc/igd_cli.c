@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #define IGD_PROGRAM "igd"
 #define IGD_VERSION "0.1.1"
@@ -27,6 +28,32 @@ static int search_usage(void)
             "             -m hitsmap of igd datasets\n",
             IGD_PROGRAM, IGD_VERSION, IGD_PROGRAM);
     return 0;
+}
+
+static double wall_s(void)
+{
+    struct timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec;
+}
+
+/* --metrics <file> (extension; stdout stays the reference's): one JSON object about the search just done */
+static void write_metrics(const char *path, igd_b200_t *h, const char *mode, double open_s, double search_s,
+                          long long overlaps)
+{
+    FILE *f = fopen(path, "w");
+    if (!f) { fprintf(stderr, "igd: cannot write %s\n", path); return; }
+    int64_t plan[4] = {0, 0, 0, 0};
+    igd_b200_last_plan(h, plan);
+    fprintf(f, "{\"mode\": \"%s\", \"files\": %d, \"records\": %lld, \"tiles\": %lld, \"device_bytes\": %lld, "
+               "\"open_s\": %.6f, \"search_s\": %.6f, \"overlaps\": %lld, \"overlaps_per_s\": %.1f, "
+               "\"kernel_launches\": %lld, \"count_plan\": {\"segments\": %lld, \"items\": %lld, \"records\": %lld, "
+               "\"bytes\": %lld}}\n",
+            mode, igd_b200_nfiles(h), (long long)igd_b200_nrecords(h), (long long)igd_b200_ntiles(h),
+            (long long)igd_b200_device_bytes(h), open_s, search_s, overlaps,
+            search_s > 0 ? (double)overlaps / search_s : 0.0, (long long)igd_b200_launch_count(h),
+            (long long)plan[0], (long long)plan[1], (long long)plan[2], (long long)plan[3]);
+    fclose(f);
 }
 
 /* The banner is printed once the contig is known and the first bin exists (src/igd_search.c:540-548). */
@@ -121,7 +148,7 @@ int igd_search(int argc, char **argv)
     int32_t v = 0, qs = 1, qe = 2;
     int mode = -1, full = 0, device = 0;
     char out[1024] = "";
-    char *chrm = NULL, *qfName = "";
+    char *chrm = NULL, *qfName = "", *metrics = NULL;
     for (int i = 3; i < argc; i++) {
         if (strcmp(argv[i], "-q") == 0) {
             if (i + 1 < argc) { qfName = argv[i + 1]; mode = 1; }
@@ -140,15 +167,22 @@ int igd_search(int argc, char **argv)
             full = 1;
         } else if (strcmp(argv[i], "--device") == 0) {      /* extension: CUDA device ordinal */
             if (i + 1 < argc) device = atoi(argv[i + 1]);
+        } else if (strcmp(argv[i], "--metrics") == 0) {     /* extension: JSON about the run, beside stdout */
+            if (i + 1 < argc) metrics = argv[i + 1];
         }
     }
 
+    double t_open = wall_s();
     igd_b200_t *h = igd_b200_open(igdName, device);
     if (!h) {
         fprintf(stderr, "igd: %s\n", igd_b200_last_error());
         return 1;
     }
+    t_open = wall_s() - t_open;
     igd_b200_use(h);
+    double t_search = wall_s();
+    long long found = 0;
+    const char *mname = "none";
     int32_t nfiles = igd_b200_nfiles(h);
     int64_t *hits = calloc((size_t)nfiles + 1, sizeof(int64_t));
 
@@ -156,15 +190,19 @@ int igd_search(int argc, char **argv)
         if (mode == 1) {
             int64_t total = getOverlaps_f1(qfName);
             printf("Total overlaps: %lld\n", (long long)total);
+            found = total, mname = "-q -f";
         } else if (mode == 2) {
             int64_t total = get_overlaps_f1(chrm, qs, qe);
             printf("Total overlaps: %lld\n", (long long)total);
+            found = total, mname = "-r -f";
         } else {
             printf("Not supported -f option\n");
         }
     } else if (mode == 0) {
         uint32_t *map = calloc((size_t)nfiles * (size_t)nfiles + 1, sizeof(uint32_t));
-        if (igd_b200_hitsmap(h, v, map) < 0) fprintf(stderr, "igd: %s\n", igd_b200_last_error());
+        int64_t pairs = igd_b200_hitsmap(h, v, map);
+        if (pairs < 0) fprintf(stderr, "igd: %s\n", igd_b200_last_error());
+        found = pairs, mname = "-m";
         /* the reference prints a running tile counter every 1000 tiles while it works (:783-784) */
         for (int64_t m = 1000, T = igd_b200_ntiles(h); m <= T; m += 1000) printf("%i\n", (int)m);
         if (strlen(out) < 2) strcpy(out, "Hitsmap");
@@ -189,15 +227,20 @@ int igd_search(int argc, char **argv)
             total += hits[i];
         }
         printf("Total: %lld\n", (long long)total);
+        found = total, mname = "-q";
     } else if (mode == 2) {
         int32_t c = igd_b200_ctg_id(h, chrm);
         if (igd_b200_count(h, 1, &c, &qs, &qe, v, hits) < 0) fprintf(stderr, "igd: %s\n", igd_b200_last_error());
         printf("index\t number of regions\t number of hits\t File_name\n");
-        for (int i = 0; i < nfiles; i++)
+        for (int i = 0; i < nfiles; i++) {
             printf("%i\t%i\t%lld\t%s\n", i, igd_b200_file_nr(h, i), (long long)hits[i], igd_b200_file_name(h, i));
+            found += hits[i];
+        }
+        mname = "-r";
     } else if (mode == 3) {
         double *sm = calloc((size_t)nfiles + 1, sizeof(double));
         seqOverlaps(qfName, sm);
+        mname = "-q -s";
         printf("index\t number of regions\t similarity\t dataset name\n");
         for (int i = 0; i < nfiles; i++)
             printf("%i\t%i\t%10.6f\t%s\n", i, igd_b200_file_nr(h, i), sm[i], igd_b200_file_name(h, i));
@@ -207,6 +250,7 @@ int igd_search(int argc, char **argv)
         igd_b200_close(h);
         return search_usage();
     }
+    if (metrics) write_metrics(metrics, h, mname, t_open, wall_s() - t_search, found);
     free(hits);
     igd_b200_close(h);
     return 0;
