@@ -21,6 +21,10 @@ igdb_dev *igdb_dev_create(int device, int32_t nbp, int32_t nctg, const int32_t *
 /* stream a run of on-disk records [rec0, rec0+nrec) (AoS) into the SoA image: rec_words = 4 for gdata_t
  * (16 B, gType 1), 3 for gdata0_t (12 B, gType 0; the image's value column reads 0) */
 int igdb_dev_upload(igdb_dev *d, int64_t rec0, int64_t nrec, const void *aos, int rec_words);
+/* the same without waiting: slot 0 or 1 names the staging buffer; the host buffer may be reused after
+ * igdb_dev_upload_wait(slot).  Records whose file index is outside [0, nfiles) make igdb_dev_finalize fail. */
+int igdb_dev_upload_slot(igdb_dev *d, int slot, int64_t rec0, int64_t nrec, const void *aos, int rec_words);
+int igdb_dev_upload_wait(igdb_dev *d, int slot);
 /* after the last upload: per-tile dedupe start (tS) and first start */
 int igdb_dev_finalize(igdb_dev *d);
 /* copies up to cap records of one tile (global tile index) out of the image; returns how many (< 0: error) */

@@ -17,7 +17,8 @@ __global__ void k_transpose(const int32_t *__restrict__ aos, int64_t rec0, int64
                             const int64_t *__restrict__ toff, int32_t T, const TileMeta *__restrict__ tiles,
                             int32_t *__restrict__ start, int32_t *__restrict__ end, int32_t *__restrict__ idx,
                             int32_t *__restrict__ value, int32_t nbp, uint16_t *__restrict__ ps,
-                            uint16_t *__restrict__ pe, uint16_t *__restrict__ pf, uint16_t *__restrict__ pv)
+                            uint16_t *__restrict__ pe, uint16_t *__restrict__ pf, uint16_t *__restrict__ pv,
+                            uint32_t nfiles, uint32_t *__restrict__ bad)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nrec) return;
@@ -30,6 +31,10 @@ __global__ void k_transpose(const int32_t *__restrict__ aos, int64_t rec0, int64
     int4 r;
     if (W == 4) r = __ldg(reinterpret_cast<const int4 *>(aos) + i);
     else r = make_int4(__ldg(&aos[3 * i]), __ldg(&aos[3 * i + 1]), __ldg(&aos[3 * i + 2]), 0);
+    if ((uint32_t)r.x >= nfiles) {              // would index hits[] out of bounds: the open fails (igdb_dev_finalize)
+        atomicOr(bad, 1u);
+        r.x = 0;
+    }
     int64_t dst = (int64_t)tiles[lo].off8 * 8 + (g - __ldg(&toff[lo]));
     idx[dst] = r.x, start[dst] = r.y, end[dst] = r.z, value[dst] = r.w;
     if (ps) {                                   // tiles[].ts still holds the bin boundary here (k_tile_meta)
@@ -123,6 +128,11 @@ void igdb_dev_destroy(igdb_dev *d)
                     d->ctg_names, d->ctg_slots, d->d_text};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    for (int k = 0; k < 2; ++k) {
+        if (d->up_stage[k]) cudaFree(d->up_stage[k]);
+        if (d->up_ev[k]) cudaEventDestroy(d->up_ev[k]);
+    }
+    if (d->bad_idx) cudaFree(d->bad_idx);
     if (d->dres_qoff) cudaFree(d->dres_qoff);
     if (d->dres_out) cudaFree(d->dres_out);
     if (d->pinned) cudaFreeHost(d->pinned);
@@ -251,7 +261,6 @@ void *igdb_dev_pinned(igdb_dev *d, size_t bytes)
 {
     if (bytes > d->pinned_cap) {
         if (d->pinned) cudaFreeHost(d->pinned);
-    if (d->arena) cudaFreeHost(d->arena);
         d->pinned = nullptr, d->pinned_cap = 0;
         if (cudaMallocHost(&d->pinned, bytes) != cudaSuccess) return nullptr;
         d->pinned_cap = bytes;
@@ -259,31 +268,55 @@ void *igdb_dev_pinned(igdb_dev *d, size_t bytes)
     return d->pinned;
 }
 
-int igdb_dev_upload(igdb_dev *d, int64_t rec0, int64_t nrec, const void *aos, int rec_words)
+// One chunk of the file's record payload: H2D into staging slot `slot` and the transpose, both asynchronous.  The
+// host buffer and the slot are free again after igdb_dev_upload_wait(slot); the caller alternates two slots so that
+// reading chunk k + 1 from the file overlaps the copy and transpose of chunk k.
+int igdb_dev_upload_slot(igdb_dev *d, int slot, int64_t rec0, int64_t nrec, const void *aos, int rec_words)
 {
     if (nrec <= 0) return 0;
-    if (rec_words != 3 && rec_words != 4) {
-        snprintf(g_err, sizeof g_err, "upload: records of %d words (gdata_t = 4, gdata0_t = 3)", rec_words);
+    if ((rec_words != 3 && rec_words != 4) || slot < 0 || slot > 1) {
+        snprintf(g_err, sizeof g_err, "upload: records of %d words (gdata_t = 4, gdata0_t = 3), slot %d", rec_words, slot);
         return -1;
     }
     CK(cudaSetDevice(d->device));
     const size_t bytes = (size_t)nrec * 4 * (size_t)rec_words;
-    if (bytes > d->d_stage_cap) {
-        if (d->d_stage) CK(cudaFree(d->d_stage));
-        d->d_stage = nullptr;
-        CK(cudaMalloc(&d->d_stage, bytes));
-        d->d_stage_cap = bytes;
+    if (!d->up_ev[slot]) CK(cudaEventCreateWithFlags(&d->up_ev[slot], cudaEventDisableTiming));
+    if (!d->bad_idx) {
+        CK(cudaMalloc(&d->bad_idx, 4));
+        CK(cudaMemsetAsync(d->bad_idx, 0, 4, d->stream));
     }
-    CK(cudaMemcpyAsync(d->d_stage, aos, bytes, cudaMemcpyHostToDevice, d->stream));
+    if (bytes > d->up_cap[slot]) {
+        if (d->up_busy[slot]) CK(cudaEventSynchronize(d->up_ev[slot]));
+        if (d->up_stage[slot]) CK(cudaFree(d->up_stage[slot]));
+        d->up_stage[slot] = nullptr, d->up_cap[slot] = 0;
+        CK(cudaMalloc(&d->up_stage[slot], bytes));
+        d->up_cap[slot] = bytes;
+    }
+    CK(cudaMemcpyAsync(d->up_stage[slot], aos, bytes, cudaMemcpyHostToDevice, d->stream));
     const int thr = 256;
     auto kern = rec_words == 4 ? k_transpose<4> : k_transpose<3>;
     kern<<<(unsigned)((nrec + thr - 1) / thr), thr, 0, d->stream>>>(
-        (const int32_t *)d->d_stage, rec0, nrec, d->d_toff, d->T, d->tiles, d->start, d->end, d->idx, d->value,
-        d->nbp, d->ps, d->pe, d->pf, d->pv);
+        (const int32_t *)d->up_stage[slot], rec0, nrec, d->d_toff, d->T, d->tiles, d->start, d->end, d->idx, d->value,
+        d->nbp, d->ps, d->pe, d->pf, d->pv, (uint32_t)d->nfiles, d->bad_idx);
     d->launches += 1;
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(d->stream));       // the caller reuses its host buffer
+    CK(cudaEventRecord(d->up_ev[slot], d->stream));
+    d->up_busy[slot] = true;
     return 0;
+}
+
+int igdb_dev_upload_wait(igdb_dev *d, int slot)
+{
+    if (slot < 0 || slot > 1 || !d->up_busy[slot]) return 0;
+    CK(cudaEventSynchronize(d->up_ev[slot]));
+    d->up_busy[slot] = false;
+    return 0;
+}
+
+int igdb_dev_upload(igdb_dev *d, int64_t rec0, int64_t nrec, const void *aos, int rec_words)
+{
+    if (igdb_dev_upload_slot(d, 0, rec0, nrec, aos, rec_words)) return -1;
+    return igdb_dev_upload_wait(d, 0);          // the caller reuses its host buffer
 }
 
 int igdb_dev_finalize(igdb_dev *d)
@@ -295,9 +328,19 @@ int igdb_dev_finalize(igdb_dev *d)
         CK(cudaGetLastError());
     }
     CK(cudaStreamSynchronize(d->stream));
-    if (d->d_stage) {
-        CK(cudaFree(d->d_stage));
-        d->d_stage = nullptr, d->d_stage_cap = 0;
+    for (int k = 0; k < 2; ++k) {
+        if (d->up_stage[k]) CK(cudaFree(d->up_stage[k]));
+        d->up_stage[k] = nullptr, d->up_cap[k] = 0, d->up_busy[k] = false;
+    }
+    if (d->bad_idx) {
+        uint32_t bad = 0;
+        CK(cudaMemcpy(&bad, d->bad_idx, 4, cudaMemcpyDeviceToHost));
+        CK(cudaFree(d->bad_idx));
+        d->bad_idx = nullptr;
+        if (bad) {
+            snprintf(g_err, sizeof g_err, "record with file index outside _index.tsv");
+            return -1;
+        }
     }
     return 0;
 }

@@ -295,6 +295,11 @@ struct igdb_dev {
     size_t pinned_cap = 0;
     void *d_stage = nullptr;
     size_t d_stage_cap = 0;
+    void *up_stage[2] = {nullptr, nullptr};                 // upload: two device staging slots, filled alternately
+    size_t up_cap[2] = {0, 0};
+    cudaEvent_t up_ev[2] = {nullptr, nullptr};              // slot k's transpose has read its host and staging buffer
+    bool up_busy[2] = {false, false};
+    uint32_t *bad_idx = nullptr;                            // device flag: a record's file index was outside [0, nFiles)
     int32_t *q_ctg = nullptr, *q_qs = nullptr, *q_qe = nullptr;
     int64_t q_cap = 0;
     uint32_t *tile_cnt = nullptr, *tile_off = nullptr;     // [T], [T+1]

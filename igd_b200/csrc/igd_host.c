@@ -5,9 +5,11 @@
 #include "igd_b200.h"
 #include "igd_dev.h"
 
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 #include <zlib.h>
 
 struct igd_b200 {
@@ -72,6 +74,44 @@ static int read_index_tsv(igd_b200_t *h, const char *igd_path)
     return 0;
 }
 
+/* the payload is read by several threads at once (pread of disjoint slices): one thread copies out of the page
+ * cache at 3-4 GB/s, which is what bounded the open of a 17 GB database */
+typedef struct { int fd; char *dst; size_t len; off_t off; int ok; } slice_t;
+static void *read_slice(void *arg)
+{
+    slice_t *s = arg;
+    size_t done = 0;
+    while (done < s->len) {
+        ssize_t r = pread(s->fd, s->dst + done, s->len - done, s->off + (off_t)done);
+        if (r <= 0) { s->ok = 0; return NULL; }
+        done += (size_t)r;
+    }
+    s->ok = 1;
+    return NULL;
+}
+static int read_parallel(int fd, char *dst, size_t len, off_t off)
+{
+    long nc = sysconf(_SC_NPROCESSORS_ONLN);
+    int nt = (int)(nc < 1 ? 1 : nc > 8 ? 8 : nc);
+    if (len < ((size_t)4 << 20)) nt = 1;
+    slice_t sl[8];
+    pthread_t th[8];
+    int started = 0;
+    for (int i = 0; i < nt; i++) {
+        size_t a = len * (size_t)i / (size_t)nt, b = len * (size_t)(i + 1) / (size_t)nt;
+        sl[i].fd = fd, sl[i].dst = dst + a, sl[i].len = b - a, sl[i].off = off + (off_t)a, sl[i].ok = 0;
+    }
+    for (int i = 1; i < nt; i++) {
+        if (pthread_create(&th[started], NULL, read_slice, &sl[i]) == 0) started++;
+        else read_slice(&sl[i]);
+    }
+    read_slice(&sl[0]);
+    for (int i = 0; i < started; i++) pthread_join(th[i], NULL);
+    for (int i = 0; i < nt; i++)
+        if (!sl[i].ok) return -1;
+    return 0;
+}
+
 /* ---- .igd: header tables as in get_igdinfo (src/igd_base.c:269-323); payload streamed to the device.
  * Layout (src/igd_base.c:408-458): nbp, gType, nCtg, nTile[nCtg], nCnt[sum nTile], 40-byte names, then
  * every tile's gdata_t records, contig-major. ---------------------------------------------------------- */
@@ -125,19 +165,28 @@ igd_b200_t *igd_b200_open(const char *igd_path, int device)
         const int64_t CH = 4 << 20;                     /* records per chunk: 64 MiB */
         const int W = h->gtype == 0 ? 3 : 4;            /* 32-bit words per record */
         int64_t chunk = h->nrec < CH ? h->nrec : CH;
-        char *buf = chunk ? igdb_dev_pinned(h->dev, (size_t)chunk * 16) : NULL;
+        /* two halves of one pinned buffer: chunk k + 1 is read from the file while chunk k is copied and
+         * transposed on the device.  File indices index hits[]: the transpose flags any outside
+         * [0, nFiles) -- records the reference would write out of bounds with -- and finalize fails. */
+        char *buf = chunk ? igdb_dev_pinned(h->dev, (size_t)chunk * 16 * 2) : NULL;
         if (chunk && !buf) { set_err("%s: cannot allocate the pinned upload buffer", igd_path); goto fail; }
-        for (int64_t r = 0; r < h->nrec; r += chunk) {
-            int64_t k = h->nrec - r < chunk ? h->nrec - r : chunk;
-            if (fread(buf, 4 * (size_t)W, (size_t)k, f) != (size_t)k) { set_err("%s: truncated tile data", igd_path); goto fail; }
-            /* file indices index hits[]: reject records the reference would write out of bounds with */
-            for (int64_t i = 0; i < k; i++) {
-                int32_t idx = ((int32_t *)buf)[W * i];
-                if (idx < 0 || idx >= h->nfiles) { set_err("%s: record with file index outside _index.tsv", igd_path); goto fail; }
+        const off_t payload = ftello(f);
+        const int fd = fileno(f);
+        int k = 0;
+        for (int64_t r = 0; r < h->nrec; r += chunk, k++) {
+            int64_t m = h->nrec - r < chunk ? h->nrec - r : chunk;
+            char *half = buf + (size_t)(k & 1) * (size_t)chunk * 16;
+            if (igdb_dev_upload_wait(h->dev, k & 1)) goto fail;
+            if (read_parallel(fd, half, (size_t)m * 4 * (size_t)W, payload + (off_t)r * 4 * W)) {
+                set_err("%s: truncated tile data", igd_path);
+                goto fail;
             }
-            if (igdb_dev_upload(h->dev, r, k, buf, W)) goto fail;
+            if (igdb_dev_upload_slot(h->dev, k & 1, r, m, half, W)) goto fail;
         }
-        if (igdb_dev_finalize(h->dev)) goto fail;
+        if (igdb_dev_finalize(h->dev)) {
+            if (strstr(igdb_dev_error(), "file index")) set_err("%s: record with file index outside _index.tsv", igd_path);
+            goto fail;
+        }
     }
     fclose(f);
     return h;

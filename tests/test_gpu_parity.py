@@ -317,3 +317,47 @@ def test_full_device_matches_full(dense_db, api):
         total, p_off, _ = g.full_device(4, far.data_ptr(), d[1].data_ptr(), d[2].data_ptr())
         assert total == 0
         assert torch.as_tensor(api.device_view(p_off, 5, "<i8"), device=dev).cpu().tolist() == [0] * 5
+
+
+def test_list_results_survive_a_file_search_on_a_small_database(workdir, O, api):
+    """-f, then search() of a query FILE (which grows the handle's pinned staging buffer on a database smaller than
+    a file chunk), then -f again: the pinned result arena of -f is a different buffer and must stay intact (a stray
+    cudaFreeHost of the arena in the staging-buffer growth path was found and removed in round 1)"""
+    stem = os.path.join(workdir, "tiny_arena")
+    files = [synth.gen_intervals(88000 + i, 300, ("lognormal", 6.0, 1.2), SMALL_SIZES) for i in range(10)]
+    synth.write_igd_direct(stem, files, names=SMALL_NAMES)
+    q = make_queries(12, 4000, ("lognormal", 7.0, 1.5))
+    qbed = os.path.join(workdir, "tiny_arena_q.bed")
+    synth.write_bed(qbed, q, SMALL_NAMES)
+    odb = O.OracleDB(stem + ".igd")
+    per, _, s, e, f = odb.full(q.ctg, q.start, q.end)
+    want, _ = odb.count(q.ctg, q.start, q.end)
+    with api.IGD(stem + ".igd") as g:
+        for _ in range(3):
+            qoff, gs, ge, gf = g.full(q.ctg, q.start, q.end, copy=False)      # views of the arena
+            hits, _ = g.search_n(qbed)
+            assert np.array_equal(hits, want)
+            assert np.array_equal(np.diff(qoff), per) and np.array_equal(gs, s) and np.array_equal(ge, e) and np.array_equal(gf, f)
+            off, rec = g.seq_overlaps(q.ctg[:50], q.start[:50], q.end[:50])
+            assert off[-1] == len(rec)
+
+
+def test_open_rejects_file_index_outside_tsv(workdir, api):
+    """a record whose idx is outside [0, nFiles) would make the reference write outside hits[]; the open fails
+    (the check runs on the device while the payload streams in)"""
+    stem = os.path.join(workdir, "bad_idx")
+    files = [synth.gen_intervals(91000 + i, 200, ("lognormal", 6.0, 1.2), SMALL_SIZES) for i in range(10)]
+    synth.write_igd_direct(stem, files, names=SMALL_NAMES)
+    raw = np.fromfile(stem + ".igd", np.int32)
+    m = raw[2]
+    hdr = 3 + m + int(raw[3:3 + m].sum()) + 10 * m
+    for bad in (10, -1):
+        r = raw.copy()
+        r[hdr + 4 * 77] = bad
+        p = os.path.join(workdir, f"bad_idx_{bad & 0xff}.igd")
+        r.tofile(p)
+        import shutil
+        shutil.copy(stem + "_index.tsv", p[:-4] + "_index.tsv")
+        with pytest.raises(api.IGDError, match="file index outside"):
+            api.IGD(p)
+    api.IGD(stem + ".igd").close()
