@@ -42,6 +42,28 @@ def env_int(k, d):
     return int(os.environ.get(k, d))
 
 
+# stdout carries exactly ONE line, the JSON: whatever libraries print there meanwhile (NCCL announces its
+# version on stdout when NCCL_DEBUG is set) goes to stderr instead
+_JSON_FD = None
+
+
+def claim_stdout():
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -351,7 +373,7 @@ def run_ours(args):
                              "sample": f"{orc['sample_n']} of {n_total} queries of the same workload, oracle/igd_oracle.c, {orc['seconds']:.1f} s"},
             "parity_vs_oracle": parity,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     igd.close()
     if world > 1:
         dist.destroy_process_group()
@@ -423,7 +445,7 @@ def run_reference(args):
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
                              "value_sorted_queries": sorted_val},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -438,6 +460,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=8_000_000, help="queries in the cpu_baseline sample")
     ap.add_argument("--ref-sample", type=int, default=1_000_000, help="queries per step of --impl reference")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
