@@ -125,7 +125,7 @@ void igdb_dev_destroy(igdb_dev *d)
                     d->q_qs, d->q_qe, d->tile_cnt, d->tile_off, d->nseg, d->qseg_off, d->bsum, d->segs,
                     d->seg_hits, d->seg_out_off, d->d_hits, d->cnt2, d->cseg_off, d->cseg_mid,
                     d->plan_agg, d->plan_flag, d->plan_tot, d->csegs, d->items, d->ps, d->pe, d->pf, d->pv,
-                    d->ctg_names, d->ctg_slots, d->d_text};
+                    d->ctg_names, d->ctg_slots, d->d_text, d->d_starts};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (int k = 0; k < 2; ++k) {

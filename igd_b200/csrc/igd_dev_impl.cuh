@@ -283,6 +283,7 @@ struct igdb_dev {
     void *dres_qoff = nullptr, *dres_out = nullptr;     // device-resident -f result of the last igdb_dev_full_device
     char *d_text = nullptr;                 // query text staging
     size_t d_text_cap = 0;
+    uint32_t *d_starts = nullptr;                           // ingest: offsets of the candidate lines of a chunk
     bool packed = false;
     int64_t bytes = 0;
     int64_t launches = 0;
