@@ -680,7 +680,7 @@ __global__ void __launch_bounds__(PK_MAXW * 32, 1) k_count_packed(const CountArg
         cp_async_wait<PK_K - 1>();                                      // slot n has landed (this lane's bytes)
         const uint32_t dz = __shfl_sync(FULL, dcur.z, j);
         const uint32_t so = (n % PK_K) * L::STAGE;
-        const int nv = dz & 0x1ff, tsr = (dz >> 9) & 0x1ff, nf = (dz >> 18) & 0x7f, ns = dz >> 25;
+        const int nv = dz & 0x1ff, nf = (dz >> 18) & 0x7f, ns = dz >> 25;
         if (nv > 0) {
             const bool have = lane * 8 < nv;
             const int4 s_ = lds128(lslot + so), e_ = lds128(lslot + so + L::ARR), f_ = lds128(lslot + so + 2 * L::ARR);
@@ -702,12 +702,12 @@ __global__ void __launch_bounds__(PK_MAXW * 32, 1) k_count_packed(const CountArg
             uint32_t c[4] = {0, 0, 0, 0};
             // prune window of the group: smallest S (records are sorted by start: the first one; with -v the
             // smallest surviving one) and largest E
+            // (a dense tile's packed copy is not in start order -- its long records are kept apart, k_pack_tiles --
+            // so the smallest start is found, not assumed to be the first record's)
             uint32_t smin;
-            if (V) {
+            {
                 const uint32_t m2 = __vminu2(__vminu2(S[0], S[1]), __vminu2(S[2], S[3]));
                 smin = __reduce_min_sync(FULL, have ? min(m2 & 0xffffu, m2 >> 16) : 0xffffu);
-            } else {
-                smin = __shfl_sync(FULL, S[0], 0) & 0xffffu;
             }
             const uint32_t x2 = __vmaxu2(__vmaxu2(E[0], E[1]), __vmaxu2(E[2], E[3]));
             const uint32_t emax = __reduce_max_sync(FULL, max(x2 & 0xffffu, x2 >> 16));
@@ -742,18 +742,15 @@ __global__ void __launch_bounds__(PK_MAXW * 32, 1) k_count_packed(const CountArg
             // end test is vacuous; it is given X = S + 0x7fff in place of E, which turns that test into
             // bit 15 of (S + 0x7fff - 1), set  <=>  S >= 2  <=>  start' >= 1.
             int nL = 0;
-            if (ns > nf && tsr < nv) {
-                // prune with the first record that starts inside the bin (records are sorted by start)
-                uint32_t slmin = smin;
-                if (tsr > 0) {
-                    if (V) {
-                        slmin = max(smin, 2u);
-                    } else {
-                        const int nb4 = min(max(tsr - lane * 8, 0), 8);     // this lane's records before the bin
-                        const uint32_t wd = nb4 < 2 ? S[0] : (nb4 < 4 ? S[1] : (nb4 < 6 ? S[2] : S[3]));
-                        const uint32_t mine = (nb4 >= 8 || !have) ? 0xffffu : ((nb4 & 1) ? wd >> 16 : wd & 0xffffu);
-                        slmin = __reduce_min_sync(FULL, mine);
-                    }
+            if (ns > nf) {
+                // prune with the smallest start among the records that start inside the bin (S >= 2): per half,
+                // S - 2 wraps to >= 0xfffe for the others, which no minimum picks while a real one exists
+                uint32_t slmin;
+                {
+                    const uint32_t two = 0x00020002u;
+                    const uint32_t m2 = __vminu2(__vminu2(__vsub2(S[0], two), __vsub2(S[1], two)),
+                                                 __vminu2(__vsub2(S[2], two), __vsub2(S[3], two)));
+                    slmin = __reduce_min_sync(FULL, have ? min(m2 & 0xffffu, m2 >> 16) : 0xffffu) + 2u;
                 }
                 const uint32_t qel = slmin + 0x8000u;
                 if (nf < 32) {

@@ -16,9 +16,7 @@ template <int W>
 __global__ void k_transpose(const int32_t *__restrict__ aos, int64_t rec0, int64_t nrec,
                             const int64_t *__restrict__ toff, int32_t T, const TileMeta *__restrict__ tiles,
                             int32_t *__restrict__ start, int32_t *__restrict__ end, int32_t *__restrict__ idx,
-                            int32_t *__restrict__ value, int32_t nbp, uint16_t *__restrict__ ps,
-                            uint16_t *__restrict__ pe, uint16_t *__restrict__ pf, uint16_t *__restrict__ pv,
-                            uint32_t nfiles, uint32_t *__restrict__ bad)
+                            int32_t *__restrict__ value, int32_t nbp, uint32_t nfiles, uint32_t *__restrict__ bad)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nrec) return;
@@ -37,12 +35,77 @@ __global__ void k_transpose(const int32_t *__restrict__ aos, int64_t rec0, int64
     }
     int64_t dst = (int64_t)tiles[lo].off8 * 8 + (g - __ldg(&toff[lo]));
     idx[dst] = r.x, start[dst] = r.y, end[dst] = r.z, value[dst] = r.w;
-    if (ps) {                                   // tiles[].ts still holds the bin boundary here (k_tile_meta)
-        const int32_t bd = tiles[lo].ts;
-        ps[dst] = (uint16_t)(pk_rel(r.y, bd, nbp) + 1);
-        pe[dst] = (uint16_t)(pk_rel_end(r.z, bd, nbp) + 0x8000);
-        pf[dst] = (uint16_t)r.x;
-        pv[dst] = (uint16_t)(min(max(r.w, 0), 32767) + 0x8000);
+}
+
+// The count-mode copy of every tile (ps / pe / pf / pv: 16-bit, relative to the tile's bin, pre-biased -- see
+// pk_rel), written from the SoA arrays once they are complete.  One warp per tile.  A sparse tile keeps the file's
+// start order.  A DENSE tile (>= PK_SPLIT_N records) is written as two runs, each in start order: the records no
+// longer than a threshold first, the longer ones after them.  The search kernel prunes a tile's queries against
+// the window [smallest start, largest end] of each group of 256 records, and with a long-tailed length
+// distribution the largest end of 256 consecutive records is set by one or two outliers; kept apart, the short
+// records' groups get tight windows (cfg3: 38 % of a tile's segments survive a group's window in start order,
+// 25 % like this) and the few long ones share a couple of wide groups.  The threshold is the tile's own: the
+// smallest power of two that at least 90 % of its records do not exceed (2048 bp for lognormal(6, 1) lengths).
+// The kernel does not depend on the order of the records inside a tile.  tiles[].ts still holds the bin boundary
+// here (k_tile_meta runs afterwards).
+constexpr int PK_SPLIT_N = 2048;
+
+__global__ void __launch_bounds__(256) k_pack_tiles(const TileMeta *__restrict__ tiles, int32_t T,
+                                                     const int32_t *__restrict__ start, const int32_t *__restrict__ end,
+                                                     const int32_t *__restrict__ idx, const int32_t *__restrict__ value,
+                                                     int32_t nbp, int32_t split_n, uint16_t *__restrict__ ps,
+                                                     uint16_t *__restrict__ pe, uint16_t *__restrict__ pf,
+                                                     uint16_t *__restrict__ pv)
+{
+    const int32_t t = (int32_t)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (t >= T) return;
+    const TileMeta m = tiles[t];
+    const int64_t base = (int64_t)m.off8 * 8;
+    const int32_t n = m.n, bd = m.ts;
+    const bool split = n >= split_n;
+    __shared__ uint32_t hist_s[8][32];
+    uint32_t thr = 0xffffffffu;
+    auto len_of = [&](int32_t i) { return (uint32_t)end[base + i] - (uint32_t)start[base + i]; };
+    int32_t nshort = n;
+    if (split) {
+        // lengths by power of two: bucket b counts the records with 2^(b-1) < len <= 2^b
+        uint32_t *h = hist_s[threadIdx.x >> 5];
+        h[lane] = 0;
+        __syncwarp();
+        for (int32_t i = lane; i < n; i += 32) {
+            const uint32_t len = len_of(i);
+            atomicAdd(&h[len <= 1 ? 0 : min(31, 32 - __clz(len - 1))], 1u);
+        }
+        __syncwarp();
+        uint32_t inc = h[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(FULL, inc, d);
+            if (lane >= d) inc += o;
+        }
+        const unsigned enough = __ballot_sync(FULL, (unsigned long long)inc * 10 >= (unsigned long long)n * 9);
+        const int b = __ffs(enough) - 1;                        // lane 31 holds all of them: never empty
+        thr = b >= 31 ? 0xffffffffu : 1u << b;
+        nshort = (int32_t)__shfl_sync(FULL, inc, b);
+    }
+    auto is_short = [&](int32_t i) { return len_of(i) <= thr; };
+    const uint32_t lt = (1u << lane) - 1u;
+    int32_t cs = 0, cl = nshort;
+    for (int32_t i0 = 0; i0 < n; i0 += 32) {
+        const int32_t i = i0 + lane;
+        const bool valid = i < n;
+        const bool sh = valid && (!split || is_short(i));
+        const unsigned bs = __ballot_sync(FULL, sh), bl = __ballot_sync(FULL, valid && !sh);
+        if (valid) {
+            const int64_t dst = base + (sh ? cs + __popc(bs & lt) : cl + __popc(bl & lt));
+            const int32_t s = start[base + i], e = end[base + i];
+            ps[dst] = (uint16_t)(pk_rel(s, bd, nbp) + 1);
+            pe[dst] = (uint16_t)(pk_rel_end(e, bd, nbp) + 0x8000);
+            pf[dst] = (uint16_t)idx[base + i];
+            pv[dst] = (uint16_t)(min(max(value[base + i], 0), 32767) + 0x8000);
+        }
+        cs += __popc(bs), cl += __popc(bl);
     }
 }
 
@@ -297,7 +360,7 @@ int igdb_dev_upload_slot(igdb_dev *d, int slot, int64_t rec0, int64_t nrec, cons
     auto kern = rec_words == 4 ? k_transpose<4> : k_transpose<3>;
     kern<<<(unsigned)((nrec + thr - 1) / thr), thr, 0, d->stream>>>(
         (const int32_t *)d->up_stage[slot], rec0, nrec, d->d_toff, d->T, d->tiles, d->start, d->end, d->idx, d->value,
-        d->nbp, d->ps, d->pe, d->pf, d->pv, (uint32_t)d->nfiles, d->bad_idx);
+        d->nbp, (uint32_t)d->nfiles, d->bad_idx);
     d->launches += 1;
     CK(cudaGetLastError());
     CK(cudaEventRecord(d->up_ev[slot], d->stream));
@@ -323,6 +386,13 @@ int igdb_dev_finalize(igdb_dev *d)
 {
     CK(cudaSetDevice(d->device));
     if (d->T > 0) {
+        if (d->packed) {
+            const char *e = getenv("IGD_B200_PK_SPLIT");        // 0 keeps every tile in start order
+            const int32_t split_n = e && atoi(e) == 0 ? 0x7fffffff : PK_SPLIT_N;
+            k_pack_tiles<<<(unsigned)(((int64_t)d->T * 32 + 255) / 256), 256, 0, d->stream>>>(
+                d->tiles, d->T, d->start, d->end, d->idx, d->value, d->nbp, split_n, d->ps, d->pe, d->pf, d->pv);
+            d->launches += 1;
+        }
         k_tile_meta<<<(d->T + 255) / 256, 256, 0, d->stream>>>(d->tiles, d->T, d->start);
         d->launches += 1;
         CK(cudaGetLastError());

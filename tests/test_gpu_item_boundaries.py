@@ -75,3 +75,38 @@ def test_item_boundaries(db, v):
             assert np.array_equal(got, want), (v, seed)
         items = g.last_plan()["items"]
     assert want.sum() > 0 and items > 0
+
+
+@pytest.mark.parametrize("v", [0, 500])
+def test_dense_tiles_long_records_kept_apart(workdir, v):
+    """thousands of records per tile with a long-tailed length distribution: the packed copy of such a tile holds
+    the records longer than 2 kb after the others (k_pack_tiles), so groups are no longer in start order; hits[]
+    must not notice -- also for queries spanning many bins (the later-bin rule) and with the split switched off"""
+    import subprocess
+    import sys
+    from igd_b200 import api
+    from oracle import oracle as O
+    from tests.conftest import SMALL_NAMES, SMALL_SIZES
+    stem = os.path.join(workdir, "dense_split")
+    if not os.path.exists(stem + ".igd"):
+        files = [synth.gen_intervals(70000 + i, 20000, ("lognormal", 6.3, 1.5), SMALL_SIZES) for i in range(15)]
+        synth.write_igd_direct(stem, files, names=SMALL_NAMES)
+    odb = O.OracleDB(stem + ".igd")
+    assert odb.nrecords / sum(odb.ntile) > 2500
+    qa = synth.gen_intervals(71, 30000, ("lognormal", 6.5, 1.2), SMALL_SIZES)
+    qb = synth.gen_intervals(72, 2000, ("fixed", 90000), SMALL_SIZES)
+    ctg = np.concatenate([qa.ctg, qb.ctg])
+    qs, qe = np.concatenate([qa.start, qb.start]), np.concatenate([qa.end, qb.end])
+    want, _ = odb.count(ctg, qs, qe, v)
+    with api.IGD(stem + ".igd") as g:
+        got, _ = g.count(ctg, qs, qe, v)
+    assert np.array_equal(got, want)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    np.savez(os.path.join(workdir, "dense_split_q.npz"), ctg=ctg, qs=qs, qe=qe)
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); from igd_b200 import api; q = np.load(sys.argv[2]); "
+            "g = api.IGD(sys.argv[1]); print(' '.join(map(str, g.count(q['ctg'], q['qs'], q['qe'], int(sys.argv[3]))[0].tolist())))"
+            % root)
+    r = subprocess.run([sys.executable, "-c", code, stem + ".igd", os.path.join(workdir, "dense_split_q.npz"), str(v)],
+                       capture_output=True, text=True, env=dict(os.environ, IGD_B200_PK_SPLIT="0"))
+    assert r.returncode == 0, r.stderr[-1500:]
+    assert r.stdout.split() == [str(x) for x in want.tolist()]
