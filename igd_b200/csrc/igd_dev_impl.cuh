@@ -294,8 +294,6 @@ struct igdb_dev {
     // staging / scratch (grown on demand)
     void *pinned = nullptr;
     size_t pinned_cap = 0;
-    void *d_stage = nullptr;
-    size_t d_stage_cap = 0;
     void *up_stage[2] = {nullptr, nullptr};                 // upload: two device staging slots, filled alternately
     size_t up_cap[2] = {0, 0};
     cudaEvent_t up_ev[2] = {nullptr, nullptr};              // slot k's transpose has read its host and staging buffer
