@@ -351,7 +351,12 @@ def run_ours(args):
                                       "sum; one NCCL int64 allreduce of hits[]" if world > 1 else "single GPU", "db_build_s": round(build_s, 1), "db_open_s": round(open_s, 2)},
             "e2e": {"value": n_total / (e2e_s / args.steps), "unit": UNIT, "ms_per_step": e2e_s / args.steps * 1e3,
                     "h2d_bytes_per_step": 12 * n_total, "d2h_bytes_per_step": 8 * igd.nfiles * world,
-                    "device_split_ms_last_step": e2e_split, "cpu_binding": numa,
+                    "device_split_ms_last_step": e2e_split,
+                    # the H2D leg runs at whatever the box's PCIe path gives at that moment: 16 to 54 GB/s were
+                    # seen on this pool's boxes for the same pinned buffers (profiles/microbench/h2d_*.py)
+                    "h2d_gbs_last_step": (12 * n_total / (e2e_split["h2d_ms"] * 1e-3) / 1e9
+                                          if e2e_split and e2e_split["h2d_ms"] > 0 else None),
+                    "cpu_binding": numa,
                     "api": "igd_b200_count (C-ABI, host buffers)" if world == 1 else
                            "pinned H2D + igd_b200_count_device + NCCL allreduce + D2H"},
             "file_ingest": None if file_s is None else {
