@@ -6,7 +6,7 @@
 One "step" = one pass of the hot path over the whole query batch of the workload (BASELINE.json
 configs[1] by default: 1,905 files x 50k intervals, 1M x 1 kb queries, count mode).  Prints ONE JSON line.
 With N GPUs the database is replicated and the query set is N x 1M queries (weak scaling: 1M per GPU), sorted
-by (contig, start) and cut into contiguous cost-balanced shards; hits[] is combined with one NCCL allreduce.
+by (contig, start) and cut into contiguous cost-balanced shards; hits[] is combined by one exchange kernel over NVLink peer memory (NCCL allreduce as the fallback).
 
 * value  : query intervals/s, whole job, queries already resident in HBM (CUDA events, max over ranks)
 * e2e    : the same through the C-ABI call with HOST (pinned) buffers: H2D + kernels + D2H inside
@@ -208,12 +208,35 @@ def run_ours(args):
     torch.cuda.set_stream(side)
     stream = side.cuda_stream
 
+    # the one exchange of the path: hits[] summed over the ranks by the library's own kernel over NVLink peer
+    # memory (igd_b200_reducer_*); NCCL's all-reduce if that cannot be set up on every rank (or on request)
+    reducer = None
+    if world > 1:
+        ok = 0
+        if not os.environ.get("IGD_B200_NCCL_REDUCE"):
+            try:
+                reducer = api.HitsReducer(local, igd.nfiles)
+                ok = 1
+            except Exception as e:  # pragma: no cover
+                print(f"[bench] rank {rank}: peer-memory reducer unavailable ({e}); NCCL all-reduce", file=sys.stderr)
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0 and reducer is not None:
+            reducer.close()
+            reducer = None
+
+    def combine():
+        if reducer is not None:
+            reducer.allreduce(d_hits.data_ptr(), stream)
+        else:
+            dist.all_reduce(d_hits)
+
     def step_device():
         d_hits.zero_()
         igd.count_device(n_local, d_ctg.data_ptr(), d_qs.data_ptr(), d_qe.data_ptr(), 0, d_hits.data_ptr(), stream)
         igd.count_device_finish()
         if world > 1:
-            dist.all_reduce(d_hits)
+            combine()
 
     # pinned host copies for the end-to-end path
     h_ctg = torch.from_numpy(np.ascontiguousarray(ctg_l)).pin_memory()
@@ -234,7 +257,7 @@ def run_ours(args):
         d_hits.zero_()
         igd.count_device(n_local, e_ctg.data_ptr(), e_qs.data_ptr(), e_qe.data_ptr(), 0, d_hits.data_ptr(), stream)
         igd.count_device_finish()
-        dist.all_reduce(d_hits)
+        combine()
         h_hits.copy_(d_hits, non_blocking=True)
         torch.cuda.synchronize()
         return h_hits.numpy()
@@ -348,7 +371,9 @@ def run_ours(args):
                        "l2": "256 MiB flush write between steps (untimed); DB image > 126 MB L2",
                        "parallelism": f"db replicated on {world} GPUs; {n_total} queries ({n_total // world} per GPU) "
                                       "sorted by (contig, start) and cut into contiguous shards by scan-byte prefix "
-                                      "sum; one NCCL int64 allreduce of hits[]" if world > 1 else "single GPU", "db_build_s": round(build_s, 1), "db_open_s": round(open_s, 2)},
+                                      "sum; hits[] combined by " + ("one exchange kernel per rank over NVLink peer memory "
+                                      "(igd_b200_reducer)" if reducer is not None else "one NCCL int64 allreduce")
+                                      if world > 1 else "single GPU", "db_build_s": round(build_s, 1), "db_open_s": round(open_s, 2)},
             "e2e": {"value": n_total / (e2e_s / args.steps), "unit": UNIT, "ms_per_step": e2e_s / args.steps * 1e3,
                     "h2d_bytes_per_step": 12 * n_total, "d2h_bytes_per_step": 8 * igd.nfiles * world,
                     "device_split_ms_last_step": e2e_split,
@@ -358,7 +383,7 @@ def run_ours(args):
                                           if e2e_split and e2e_split["h2d_ms"] > 0 else None),
                     "cpu_binding": numa,
                     "api": "igd_b200_count (C-ABI, host buffers)" if world == 1 else
-                           "pinned H2D + igd_b200_count_device + NCCL allreduce + D2H"},
+                           "pinned H2D + igd_b200_count_device + hits[] exchange + D2H"},
             "file_ingest": None if file_s is None else {
                 "value": n_total / file_s, "unit": UNIT, "ms": file_s * 1e3, "file_bytes": file_bytes,
                 "api": "search(igd, qFile) -- BED text (warm page cache) -> pinned chunks -> H2D -> parsed on the "
@@ -379,6 +404,9 @@ def run_ours(args):
             "parity_vs_oracle": parity,
         }
         emit(line)
+    if reducer is not None:
+        dist.barrier()
+        reducer.close()
     igd.close()
     if world > 1:
         dist.destroy_process_group()

@@ -125,6 +125,12 @@ def load_library():
     L.igd_b200_stage_timing.argtypes = [vp, C.c_int]
     L.igd_b200_last_stage_ms.restype = C.c_int
     L.igd_b200_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float * 4)]
+    L.igd_b200_reducer_create.restype = vp
+    L.igd_b200_reducer_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int32]
+    L.igd_b200_reducer_handle.argtypes = [vp, vp]
+    L.igd_b200_reducer_connect.argtypes = [vp, vp]
+    L.igd_b200_reducer_allreduce.argtypes = [vp, vp, vp]
+    L.igd_b200_reducer_destroy.argtypes = [vp]
     L.igd_b200_use.argtypes = [vp]
     L.igd_b200_current.restype = vp
     L.get_overlaps.restype = C.c_int32
@@ -163,6 +169,41 @@ class device_view:
     def __init__(self, ptr: int, n: int, typestr: str):
         self.__cuda_array_interface__ = {"data": (int(ptr), False), "shape": (int(n),), "typestr": typestr,
                                          "version": 2, "strides": None}
+
+
+class HitsReducer:
+    """The exchange step of the multi-GPU count path over NVLink peer memory (igd_b200_reducer_*, igd_dev_p2p.cu):
+    ``allreduce`` turns each rank's device ``hits[]`` into the sum over the ranks with one small kernel per rank.
+    The 64-byte IPC handles are exchanged with ``torch.distributed`` (whatever backend the group has)."""
+
+    def __init__(self, device: int, nfiles: int, group=None):
+        import torch
+        import torch.distributed as dist
+        self._L = load_library()
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self._r = self._L.igd_b200_reducer_create(device, self.rank, self.world, nfiles)
+        if not self._r:
+            raise IGDError(last_error())
+        mine = (C.c_uint8 * 64)()
+        if self._L.igd_b200_reducer_handle(self._r, mine):
+            raise IGDError(last_error())
+        on = torch.device("cuda", device) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        t = torch.tensor(list(mine), dtype=torch.uint8, device=on)
+        allh = [torch.zeros_like(t) for _ in range(self.world)]
+        dist.all_gather(allh, t, group=group)
+        blob = bytes(torch.cat(allh).cpu().tolist())
+        if self._L.igd_b200_reducer_connect(self._r, C.c_char_p(blob)):
+            raise IGDError(last_error())
+        dist.barrier(group)             # every mailbox is mapped everywhere before the first push
+
+    def allreduce(self, d_hits_ptr: int, stream: int = 0) -> None:
+        if self._L.igd_b200_reducer_allreduce(self._r, d_hits_ptr, stream):
+            raise IGDError(last_error())
+
+    def close(self) -> None:
+        if getattr(self, "_r", None):
+            self._L.igd_b200_reducer_destroy(self._r)
+            self._r = None
 
 
 class QuerySet:

@@ -92,6 +92,16 @@ int64_t igdb_dev_seq_pairs_host(igdb_dev *d, int64_t n, const int32_t *ctg, cons
 /* -m restricted to the tiles [t0, t1) (global tile indices, contig-major): hitmap[nfiles*nfiles] is incremented */
 int64_t igdb_dev_hitsmap_host(igdb_dev *d, int32_t v, int64_t t0, int64_t t1, uint32_t *hitmap);
 
+/* The exchange step of the multi-GPU count path (igd_dev_p2p.cu): hits[] summed over the ranks by one kernel per
+ * rank over peer memory.  create -> handle (64-byte CUDA IPC handle of this rank's mailbox) -> connect (all ranks'
+ * handles, rank-major) -> allreduce any number of times, the same number on every rank. */
+typedef struct igdb_reducer igdb_reducer;
+igdb_reducer *igdb_reducer_create(int device, int rank, int world, int32_t nfiles);
+int igdb_reducer_handle(igdb_reducer *r, void *out64);
+int igdb_reducer_connect(igdb_reducer *r, const void *handles);
+int igdb_reducer_allreduce(igdb_reducer *r, unsigned long long *d_hits, void *stream);
+void igdb_reducer_destroy(igdb_reducer *r);
+
 #ifdef __cplusplus
 }
 #endif

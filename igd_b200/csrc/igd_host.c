@@ -593,6 +593,21 @@ int64_t search(igd_b200_t *h, const char *qFile, int32_t v, int64_t *hits)
     return search_mode(h, qFile, filter_on(h, v), v, hits);
 }
 
+/* ---- the multi-GPU exchange step (igd_dev_p2p.cu) ---------------------------------------------------------- */
+igd_b200_reducer *igd_b200_reducer_create(int device, int rank, int world, int32_t nfiles)
+{
+    g_err[0] = 0;
+    return igdb_reducer_create(device, rank, world, nfiles);
+}
+int igd_b200_reducer_handle(igd_b200_reducer *r, void *out64) { g_err[0] = 0; return igdb_reducer_handle(r, out64); }
+int igd_b200_reducer_connect(igd_b200_reducer *r, const void *handles) { g_err[0] = 0; return igdb_reducer_connect(r, handles); }
+int igd_b200_reducer_allreduce(igd_b200_reducer *r, uint64_t *d_hits, void *stream)
+{
+    g_err[0] = 0;
+    return igdb_reducer_allreduce(r, (unsigned long long *)d_hits, stream);
+}
+void igd_b200_reducer_destroy(igd_b200_reducer *r) { igdb_reducer_destroy(r); }
+
 /* ---- (2) reference-named entry points over the current handle ---------------------------------------- */
 void igd_b200_use(igd_b200_t *h) { g_current = h; }
 igd_b200_t *igd_b200_current(void) { return g_current; }

@@ -2,7 +2,9 @@
 (SURVEY.md §8(e)).  ``torch.distributed`` is the plumbing (NCCL over NVLink on the GPU box, gloo in CPU tests).
 
 * count / -v : queries sorted by (contig, start) and cut into contiguous ranges balanced by the prefix sum of
-               estimated scan bytes; per-rank ``hits[]``; ONE int64 allreduce (nFiles elements).
+               estimated scan bytes; per-rank ``hits[]``; ONE exchange of nFiles int64 -- with the CUDA engine and
+               a CUDA communicator the library's own kernel over NVLink peer memory (``api.HitsReducer``,
+               igd_dev_p2p.cu) queued right behind the search, otherwise an all-reduce of the group's backend.
 * -f         : the same shards; every rank sends its overlaps to ``dst`` (sizes by all_gather, payload by
                point-to-point send/recv), which restores the ORIGINAL query order -- the result is identical to
                a single-GPU ``full()`` on the unsorted input.  With the CUDA engine and a CUDA communicator the
@@ -65,10 +67,34 @@ class ShardedSearch:
         """hits[nFiles] of the whole query set, on every rank."""
         _, cs, ss, es, b = self._plan(ctg, qs, qe)
         lo, hi = b[self.rank], b[self.rank + 1]
+        if str(self.dev) != "cpu" and hasattr(self.e, "count_device"):
+            return self._count_on_device(cs[lo:hi], ss[lo:hi], es[lo:hi], v)
         hits, _ = self.e.count(cs[lo:hi], ss[lo:hi], es[lo:hi], v)
         t = self._t(hits.astype(np.int64))
         self.dist.all_reduce(t, group=self.group)
         return t.cpu().numpy()
+
+    def _count_on_device(self, cs, ss, es, v):
+        """shard -> HBM, search, exchange by the peer-memory kernel on the same stream, one D2H of hits[]"""
+        import torch
+
+        from .api import HitsReducer
+        if getattr(self, "_reducer", None) is None:
+            self._reducer = HitsReducer(torch.device(self.dev).index or 0, self.e.nfiles, self.group)
+            self._stream = torch.cuda.Stream(device=self.dev)
+        # one real stream carries the copies, the search and the exchange (a NULL stream would mean the library's
+        # own for the search and the legacy default for the exchange: no order between them)
+        with torch.cuda.stream(self._stream):
+            d_c, d_s, d_e = self._t(cs), self._t(ss), self._t(es)
+            d_hits = torch.zeros(self.e.nfiles, dtype=torch.int64, device=self.dev)
+            stream = self._stream.cuda_stream
+            if len(cs):
+                self.e.count_device(len(cs), d_c.data_ptr(), d_s.data_ptr(), d_e.data_ptr(), v, d_hits.data_ptr(), stream)
+                self.e.count_device_finish()
+            self._reducer.allreduce(d_hits.data_ptr(), stream)
+            out = d_hits.cpu()
+        self._stream.synchronize()
+        return out.numpy()
 
     # ---- -f --------------------------------------------------------------------------------------
     def full(self, ctg, qs, qe, dst: int = 0):

@@ -157,6 +157,24 @@ int64_t igd_b200_seq_overlaps(igd_b200_t *h, int64_t n, const int32_t *ctg, cons
 int igd_b200_query_cost(const igd_b200_t *h, int64_t n, const int32_t *ctg, const int32_t *qs,
                         const int32_t *qe, int64_t *cost);
 
+/* The one exchange of the multi-GPU count path -- hits[] summed over the ranks ("one allreduce of
+ * hits[nFiles]") -- as ONE small kernel per rank over NVLink peer memory instead of a library collective: every
+ * rank stores its counts into a mailbox in every peer's HBM, raises a flag there, waits for the flags in its own
+ * mailbox and adds the slots up in rank order (igd_dev_p2p.cu).  One process per GPU:
+ *   r = igd_b200_reducer_create(device, rank, world, nFiles);
+ *   igd_b200_reducer_handle(r, h64);            -- 64-byte CUDA IPC handle of this rank's mailbox
+ *   ... exchange the handles between the processes (any transport) ...
+ *   igd_b200_reducer_connect(r, all_handles);   -- world x 64 bytes, rank-major
+ *   igd_b200_count_device(..., d_hits, stream); igd_b200_count_device_finish(h);
+ *   igd_b200_reducer_allreduce(r, d_hits, stream);    -- d_hits (uint64[nFiles], device) becomes the sum; enqueued
+ * Every rank must call allreduce the same number of times.  0 on success, negative on error. */
+typedef struct igdb_reducer igd_b200_reducer;
+igd_b200_reducer *igd_b200_reducer_create(int device, int rank, int world, int32_t nfiles);
+int igd_b200_reducer_handle(igd_b200_reducer *r, void *out64);
+int igd_b200_reducer_connect(igd_b200_reducer *r, const void *handles);
+int igd_b200_reducer_allreduce(igd_b200_reducer *r, uint64_t *d_hits, void *stream);
+void igd_b200_reducer_destroy(igd_b200_reducer *r);
+
 /* timing of the last igd_b200_count / get_overlaps_n call on this handle, milliseconds (CUDA events):
  * t[0] H2D, t[1] kernels, t[2] D2H */
 void igd_b200_last_timing(const igd_b200_t *h, float t[3]);

@@ -36,3 +36,8 @@ int64_t igdb_dev_full_device(igdb_dev *d, int64_t n, const int32_t *a, const int
 int64_t igdb_dev_seq_pairs_host(igdb_dev *d, int64_t n, const int32_t *a, const int32_t *b, const int32_t *c, int64_t **q, void **p) { (void)d; (void)n; (void)a; (void)b; (void)c; (void)q; (void)p; return -1; }
 int igdb_dev_seqpare(igdb_dev *d, int64_t n, const int32_t *a, const int32_t *b, const int32_t *c, const int32_t *g, int32_t ng, const int32_t *gn, double *acc) { (void)d; (void)n; (void)a; (void)b; (void)c; (void)g; (void)ng; (void)gn; (void)acc; return -1; }
 int64_t igdb_dev_hitsmap_host(igdb_dev *d, int32_t v, int64_t t0, int64_t t1, uint32_t *h) { (void)d; (void)v; (void)t0; (void)t1; (void)h; return -1; }
+igdb_reducer *igdb_reducer_create(int d, int r, int w, int32_t n) { (void)d; (void)r; (void)w; (void)n; return NULL; }
+int igdb_reducer_handle(igdb_reducer *r, void *o) { (void)r; (void)o; return -1; }
+int igdb_reducer_connect(igdb_reducer *r, const void *h) { (void)r; (void)h; return -1; }
+int igdb_reducer_allreduce(igdb_reducer *r, unsigned long long *h, void *s) { (void)r; (void)h; (void)s; return -1; }
+void igdb_reducer_destroy(igdb_reducer *r) { (void)r; }

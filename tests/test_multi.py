@@ -145,3 +145,50 @@ def test_hitsmap_tile_ranges_add_up(dense_db):
             acc += part
         assert np.array_equal(acc, g.hitsmap(v)) and np.array_equal(acc, o.hitsmap(v))
     g.close()
+
+
+def _reducer_rank(rank, world, port, out_dir):
+    import signal
+    import torch
+    import torch.distributed as dist
+    from igd_b200 import api
+    signal.alarm(150)                                   # a lost flag would spin forever: die instead
+    ndev = torch.cuda.device_count()
+    dev = rank if ndev >= world else 0                  # one GPU: the ranks share it (IPC works within a device too)
+    torch.cuda.set_device(dev)
+    if ndev >= world:
+        dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                                device_id=torch.device("cuda", dev))
+    else:
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    nfiles = 1905
+    red = api.HitsReducer(dev, nfiles)
+    stream = torch.cuda.Stream(device=dev)
+    ok = True
+    with torch.cuda.stream(stream):
+        for epoch in range(7):
+            g = torch.Generator().manual_seed(1000 * epoch + rank)
+            mine = torch.randint(0, 2**40, (nfiles,), generator=g, dtype=torch.int64).to(f"cuda:{dev}")
+            want = sum(torch.randint(0, 2**40, (nfiles,), generator=torch.Generator().manual_seed(1000 * epoch + q),
+                                     dtype=torch.int64) for q in range(world))
+            red.allreduce(mine.data_ptr(), stream.cuda_stream)
+            stream.synchronize()
+            ok = ok and bool(torch.equal(mine.cpu(), want))
+    red.close()
+    open(os.path.join(out_dir, f"reducer{rank}.txt"), "w").write("ok" if ok else "MISMATCH")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3])
+def test_peer_memory_hits_reducer(workdir, world):
+    """igd_b200_reducer_*: hits[] summed over the ranks by one kernel per rank over peer memory, seven epochs in a
+    row (both mailbox slots reused), against the sums computed on the host.  On a one-GPU box the ranks share the
+    device (their kernels wait for each other across time slices)."""
+    import torch.multiprocessing as mp
+    out_dir = os.path.join(workdir, f"reducer_out{world}")
+    os.makedirs(out_dir, exist_ok=True)
+    mp.spawn(_reducer_rank, args=(world, _free_port(), out_dir), nprocs=world, join=True)
+    for r in range(world):
+        assert open(os.path.join(out_dir, f"reducer{r}.txt")).read() == "ok"
