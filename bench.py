@@ -267,6 +267,17 @@ def run_ours(args):
         flush.fill_(1)
         step_device()
     torch.cuda.synchronize()
+    if world > 1:
+        # did every exchange meet all its peers?  if not (anywhere), everybody goes back to NCCL and warms up again
+        bad = torch.tensor([reducer.status() if reducer is not None else 1], dtype=torch.int32, device=dev)
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+        if reducer is not None and int(bad.item()) != 0:
+            print(f"[bench] rank {rank}: peer-memory exchange failed its check; NCCL all-reduce", file=sys.stderr)
+            reducer.close()
+            reducer = None
+            for _ in range(3):
+                step_device()
+            torch.cuda.synchronize()
     hits_dev = d_hits.cpu().numpy().copy()
 
     # ---- timed: device-resident inputs -----------------------------------------------------------

@@ -130,6 +130,8 @@ def load_library():
     L.igd_b200_reducer_handle.argtypes = [vp, vp]
     L.igd_b200_reducer_connect.argtypes = [vp, vp]
     L.igd_b200_reducer_allreduce.argtypes = [vp, vp, vp]
+    L.igd_b200_reducer_status.restype = C.c_int
+    L.igd_b200_reducer_status.argtypes = [vp]
     L.igd_b200_reducer_destroy.argtypes = [vp]
     L.igd_b200_use.argtypes = [vp]
     L.igd_b200_current.restype = vp
@@ -199,6 +201,10 @@ class HitsReducer:
     def allreduce(self, d_hits_ptr: int, stream: int = 0) -> None:
         if self._L.igd_b200_reducer_allreduce(self._r, d_hits_ptr, stream):
             raise IGDError(last_error())
+
+    def status(self) -> int:
+        """0 = every exchange so far met all its peers (waits for the device)."""
+        return int(self._L.igd_b200_reducer_status(self._r))
 
     def close(self) -> None:
         if getattr(self, "_r", None):

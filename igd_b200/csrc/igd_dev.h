@@ -100,6 +100,7 @@ igdb_reducer *igdb_reducer_create(int device, int rank, int world, int32_t nfile
 int igdb_reducer_handle(igdb_reducer *r, void *out64);
 int igdb_reducer_connect(igdb_reducer *r, const void *handles);
 int igdb_reducer_allreduce(igdb_reducer *r, unsigned long long *d_hits, void *stream);
+int igdb_reducer_status(igdb_reducer *r);       /* 0 ok; k > 0: a wait for rank k - 1 timed out; < 0: CUDA error */
 void igdb_reducer_destroy(igdb_reducer *r);
 
 #ifdef __cplusplus

@@ -21,7 +21,7 @@
 struct igdb_reducer {
     int device = 0, rank = 0, world = 1;
     int32_t nfiles = 0;
-    unsigned long long *mailbox = nullptr;          // own: recv[2][world][nfiles] then flag[2][world]
+    unsigned long long *mailbox = nullptr;          // own: recv[2][world][nfiles], flag[2][world], one status word
     unsigned long long *peer[64] = {};              // every rank's mailbox as mapped here (peer[rank] == mailbox)
     unsigned long long **d_peer = nullptr;          // device copy of peer[]
     unsigned long long epoch = 0;
@@ -41,6 +41,8 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     return v;
 }
 
+constexpr unsigned long long EXCHANGE_TIMEOUT_NS = 20ull * 1000 * 1000 * 1000;
+
 __global__ void __launch_bounds__(1024) k_hits_exchange(unsigned long long *__restrict__ hits, int32_t nfiles, int rank,
                                                          int world, unsigned long long epoch,
                                                          unsigned long long *const *__restrict__ peer)
@@ -55,10 +57,20 @@ __global__ void __launch_bounds__(1024) k_hits_exchange(unsigned long long *__re
     __threadfence_system();
     __syncthreads();
     if ((int)threadIdx.x < world) st_release_sys(peer[threadIdx.x] + flags + rank, epoch);
-    // 2. wait for everybody's push into MY mailbox
+    // 2. wait for everybody's push into MY mailbox (a peer that never arrives must not hang the GPU: after
+    //    EXCHANGE_TIMEOUT_NS the wait gives up and leaves a mark that igdb_reducer_status reports)
     if ((int)threadIdx.x < world) {
         const unsigned long long *fl = peer[rank] + flags + threadIdx.x;
-        while (ld_acquire_sys(fl) != epoch) __nanosleep(100);
+        unsigned long long t0 = 0, now = 0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (ld_acquire_sys(fl) != epoch) {
+            __nanosleep(100);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (now - t0 > EXCHANGE_TIMEOUT_NS) {
+                peer[rank][(size_t)2 * world * nfiles + (size_t)2 * world] = 1ull + threadIdx.x;    // status word
+                break;
+            }
+        }
     }
     __syncthreads();
     // 3. sum in rank order
@@ -70,7 +82,8 @@ __global__ void __launch_bounds__(1024) k_hits_exchange(unsigned long long *__re
     }
 }
 
-size_t mailbox_words(int world, int32_t nfiles) { return (size_t)2 * world * nfiles + (size_t)2 * world; }
+// recv[2][world][nfiles], flag[2][world], one status word
+size_t mailbox_words(int world, int32_t nfiles) { return (size_t)2 * world * nfiles + (size_t)2 * world + 1; }
 
 }  // namespace
 
@@ -142,6 +155,19 @@ int igdb_reducer_allreduce(igdb_reducer *r, unsigned long long *d_hits, void *st
     k_hits_exchange<<<1, threads, 0, (cudaStream_t)stream>>>(d_hits, r->nfiles, r->rank, r->world, r->epoch, r->d_peer);
     CK(cudaGetLastError());
     return 0;
+}
+
+// 0 = every exchange so far met all its peers; k > 0 = a wait for rank k - 1 timed out (results are then invalid).
+// Synchronises the device.
+int igdb_reducer_status(igdb_reducer *r)
+{
+    g_err[0] = 0;
+    if (r->world == 1) return 0;
+    CK(cudaSetDevice(r->device));
+    unsigned long long st = 0;
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(&st, r->mailbox + mailbox_words(r->world, r->nfiles) - 1, 8, cudaMemcpyDeviceToHost));
+    return (int)st;
 }
 
 void igdb_reducer_destroy(igdb_reducer *r)

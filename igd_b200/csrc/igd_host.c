@@ -606,6 +606,7 @@ int igd_b200_reducer_allreduce(igd_b200_reducer *r, uint64_t *d_hits, void *stre
     g_err[0] = 0;
     return igdb_reducer_allreduce(r, (unsigned long long *)d_hits, stream);
 }
+int igd_b200_reducer_status(igd_b200_reducer *r) { g_err[0] = 0; return igdb_reducer_status(r); }
 void igd_b200_reducer_destroy(igd_b200_reducer *r) { igdb_reducer_destroy(r); }
 
 /* ---- (2) reference-named entry points over the current handle ---------------------------------------- */

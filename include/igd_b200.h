@@ -173,6 +173,9 @@ igd_b200_reducer *igd_b200_reducer_create(int device, int rank, int world, int32
 int igd_b200_reducer_handle(igd_b200_reducer *r, void *out64);
 int igd_b200_reducer_connect(igd_b200_reducer *r, const void *handles);
 int igd_b200_reducer_allreduce(igd_b200_reducer *r, uint64_t *d_hits, void *stream);
+/* waits for the device; 0 = every exchange so far met all its peers, k > 0 = the wait for rank k - 1 gave up after
+ * 20 s (a rank died or skipped a call: the sums are then invalid), negative = CUDA error */
+int igd_b200_reducer_status(igd_b200_reducer *r);
 void igd_b200_reducer_destroy(igd_b200_reducer *r);
 
 /* timing of the last igd_b200_count / get_overlaps_n call on this handle, milliseconds (CUDA events):

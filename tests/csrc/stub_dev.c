@@ -41,3 +41,4 @@ int igdb_reducer_handle(igdb_reducer *r, void *o) { (void)r; (void)o; return -1;
 int igdb_reducer_connect(igdb_reducer *r, const void *h) { (void)r; (void)h; return -1; }
 int igdb_reducer_allreduce(igdb_reducer *r, unsigned long long *h, void *s) { (void)r; (void)h; (void)s; return -1; }
 void igdb_reducer_destroy(igdb_reducer *r) { (void)r; }
+int igdb_reducer_status(igdb_reducer *r) { (void)r; return -1; }

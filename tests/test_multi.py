@@ -174,6 +174,7 @@ def _reducer_rank(rank, world, port, out_dir):
             red.allreduce(mine.data_ptr(), stream.cuda_stream)
             stream.synchronize()
             ok = ok and bool(torch.equal(mine.cpu(), want))
+    ok = ok and red.status() == 0
     red.close()
     open(os.path.join(out_dir, f"reducer{rank}.txt"), "w").write("ok" if ok else "MISMATCH")
     dist.barrier()
