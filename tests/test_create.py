@@ -223,6 +223,67 @@ def test_create_under_asan_ubsan(inputs, workdir):
     assert r.returncode == 0 and b"ERROR" not in r.stderr and b"runtime error" not in r.stderr, r.stderr.decode()[-2000:]
 
 
+def _awkward_files(bed, with_overflow=False):
+    os.makedirs(bed)
+    rng = np.random.default_rng(3)
+
+    def base(n=300):
+        L = []
+        for k in range(n):
+            a = int(rng.integers(0, 900000))
+            L.append(f"chr{1 + k % 3}\t{a}\t{a + int(rng.integers(1, 5000))}\tn{k}\t{int(rng.integers(0, 1000))}\n")
+        return L
+
+    cases = {
+        1: lambda L: L[:5] + ["chr1\t100\t200\t" + "x" * 3000 + "\t5\n"] + L[5:],      # longer than the 1024-byte line buffer
+        2: lambda L: L[:7] + ["chr2\t500\t400\t.\t9\n", "chr2\t500\t500\t.\t9\n"] + L[7:],   # start >= end
+        3: lambda L: [x.replace("\n", "\r\n") for x in L],                              # CRLF
+        4: lambda L: L[:3] + ["chr1\t-50\t300\t.\t4\n"] + L[3:],                        # negative start
+        5: lambda L: L[:4] + ["chr1 10 20 . 5\n"] + L[4:],                                # blanks instead of tabs
+        6: lambda L: L[:2] + ["chr3\t1000\t2000\n"] * 3 + L[2:],                          # three columns in the middle
+        7: lambda L: L[:9] + ["chr1\t 77\t 99 \t.\t 12\n"] + L[9:],                      # blanks around the numbers
+        9: lambda L: L + ["chr2\t10\t20\t.\t3"],                                        # no newline at the end
+        10: lambda L: L[:8] + ["chrVeryLongContigName_0123456789_0123456789_0123456789\t5\t50\t.\t1\n"] + L[8:],
+        11: lambda L: L[:1] + ["chr1\t100\t200\t.\t1e3\n", "chr1\t0x10\t0x20\t.\t7\n", "chr1\t+5\t+50\t.\t-3\n"] + L[1:],
+    }
+    if with_overflow:       # beyond int32: the reference indexes a negative tile and dies
+        cases[8] = lambda L: L[:6] + ["chr1\t3000000000\t3000000100\t.\t1\n"] + L[6:]
+    for i in range(12):
+        L = base()
+        if i in cases:
+            L = cases[i](L)
+        with open(os.path.join(bed, f"f{i:05d}.bed"), "w", newline="") as f:
+            f.writelines(L)
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built")
+def test_create_awkward_lines_like_the_reference(workdir):
+    """over-long lines (split by the 1024-byte gzgets buffer), CRLF, start >= end, a negative start, blanks for
+    tabs, 3-column lines in the middle of 5-column ones, a 54-character contig name, odd numerals, a last line
+    without newline: same bytes, tsv and stdout as the unmodified reference"""
+    bed = os.path.join(workdir, "create_bed_awkward")
+    _awkward_files(bed)
+    ref = outputs(O.REF_BIN, workdir, bed, "ref_awkward", [])
+    got = outputs(api.CLI_PATH, workdir, bed, "mine_awkward", [])
+    assert got == ref
+    # (the reference's -s 0 flavour segfaults on these files; this one must at least get through them)
+    got0 = outputs(api.CLI_PATH, workdir, bed, "mine_awkward0", ["-s", "0"])
+    assert len(got0["igd"]) > 12
+
+
+def test_create_survives_coordinates_beyond_int32(workdir):
+    """`chr1 3000000000 3000000100` narrows to a negative interval: the reference indexes tile -79040 and
+    segfaults; here the line is counted in the tsv and stored nowhere"""
+    bed = os.path.join(workdir, "create_bed_overflow")
+    _awkward_files(bed, with_overflow=True)
+    got = outputs(api.CLI_PATH, workdir, bed, "mine_overflow", [])
+    clean = os.path.join(workdir, "create_bed_awkward")
+    if os.path.isdir(clean):
+        base = outputs(api.CLI_PATH, workdir, clean, "mine_awkward_again", [])
+        assert got["igd"] == base["igd"]                 # the extra line added no record
+    assert "\t301\t" in got["tsv"].split("\n")[9]       # file 8 has one line more
+
+
 def hdr_len(b: bytes) -> int:
     m = int(np.frombuffer(b, np.int32, 1, 8)[0])
     return 12 + 44 * m + 4 * int(np.frombuffer(b, np.int32, m, 12).sum())
