@@ -20,7 +20,7 @@ NBP = 16384
 def boundary_db(stem):
     """one contig; tile k holds a chosen number of records around 256 / 320 / 512 / 576 ..., plus 300 long records
     that start in tile 0 and span tiles 0..3 (so tiles 1..3 begin with 300 records that start before the bin)"""
-    sizes = [1, 7, 8, 9, 255, 256, 257, 300, 319, 320, 321, 322, 383, 384, 500, 511, 512, 513, 525, 575, 576, 577,
+    sizes = [1, 2, 7, 8, 9, 15, 16, 17, 31, 32, 33, 63, 64, 65, 255, 256, 257, 300, 319, 320, 321, 322, 383, 384, 500, 511, 512, 513, 525, 575, 576, 577,
              578, 640, 767, 768, 769, 832, 833, 1100]
     rng = np.random.default_rng(2024)
     files = []
@@ -29,6 +29,8 @@ def boundary_db(stem):
     for k, n in enumerate(sizes):
         t = 4 + k                                   # tiles 4.. hold the sized sets (short records inside the bin)
         s = rng.integers(t * NBP, (t + 1) * NBP - 700, n)
+        if n > 4:
+            s[: n // 3] = s[0]                      # duplicate starts (SURVEY §8c's list of known-answer cases)
         ln = rng.integers(1, 600, n)
         for a, b in zip(s, ln):
             per_file[int(rng.integers(0, nfiles))].append((0, int(a), int(a + b), int(rng.integers(0, 1000))))
@@ -110,3 +112,22 @@ def test_dense_tiles_long_records_kept_apart(workdir, v):
                        capture_output=True, text=True, env=dict(os.environ, IGD_B200_PK_SPLIT="0"))
     assert r.returncode == 0, r.stderr[-1500:]
     assert r.stdout.split() == [str(x) for x in want.tolist()]
+
+
+def test_item_boundary_tiles_full_hitsmap_seqpare(db, workdir):
+    """the same tiles (1, 2, 15, 16, 17, 31, 32, 33 ... records, duplicate starts) through the query-centric
+    kernels: -f (the 32-ary ballot search and the descending scan), -m, -m -v, and Seqpare's candidate lists"""
+    from igd_b200 import api
+    from oracle import oracle as O
+    path, span = db
+    odb = O.OracleDB(path)
+    ctg, qs, qe = queries(span, 9, 6000)
+    with api.IGD(path) as g:
+        per, _, s, e, f = odb.full(ctg, qs, qe)
+        qoff, gs, ge, gf = g.full(ctg, qs, qe)
+        assert np.array_equal(np.diff(qoff), per) and np.array_equal(gs, s) and np.array_equal(ge, e) and np.array_equal(gf, f)
+        for v in (0, 500):
+            assert np.array_equal(g.hitsmap(v), odb.hitsmap(v)), v
+        off, rec = g.seq_overlaps(ctg[:400], qs[:400], qe[:400])
+        for i in range(0, 400, 7):
+            assert rec[off[i]:off[i + 1]].tobytes() == odb.seq_overlaps(int(ctg[i]), int(qs[i]), int(qe[i])).tobytes(), i
