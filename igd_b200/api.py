@@ -183,20 +183,32 @@ class HitsReducer:
         import torch.distributed as dist
         self._L = load_library()
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        self._r = self._L.igd_b200_reducer_create(device, self.rank, self.world, nfiles)
-        if not self._r:
-            raise IGDError(last_error())
-        mine = (C.c_uint8 * 64)()
-        if self._L.igd_b200_reducer_handle(self._r, mine):
-            raise IGDError(last_error())
         on = torch.device("cuda", device) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+
+        def everybody(ok: bool) -> bool:
+            f = torch.tensor([1 if ok else 0], dtype=torch.int32, device=on)
+            dist.all_reduce(f, op=dist.ReduceOp.MIN, group=group)
+            return bool(f.item())
+
+        # Every rank walks through the SAME collectives whether or not its own step worked, and all of them raise
+        # together: a rank that failed alone would otherwise leave the others waiting in the next collective.
+        err = ""
+        mine = (C.c_uint8 * 64)()
+        self._r = self._L.igd_b200_reducer_create(device, self.rank, self.world, nfiles)
+        if not self._r or self._L.igd_b200_reducer_handle(self._r, mine):
+            err = last_error() or "igd_b200_reducer_create failed"
         t = torch.tensor(list(mine), dtype=torch.uint8, device=on)
         allh = [torch.zeros_like(t) for _ in range(self.world)]
         dist.all_gather(allh, t, group=group)
-        blob = bytes(torch.cat(allh).cpu().tolist())
-        if self._L.igd_b200_reducer_connect(self._r, C.c_char_p(blob)):
-            raise IGDError(last_error())
-        dist.barrier(group)             # every mailbox is mapped everywhere before the first push
+        good = everybody(not err)
+        if good:
+            blob = bytes(torch.cat(allh).cpu().tolist())
+            if self._L.igd_b200_reducer_connect(self._r, C.c_char_p(blob)):
+                err = last_error() or "igd_b200_reducer_connect failed"
+            good = everybody(not err)           # also: every mailbox is mapped everywhere before the first push
+        if not good:
+            self.close()
+            raise IGDError(err or "the peer-memory exchange could not be set up on another rank")
 
     def allreduce(self, d_hits_ptr: int, stream: int = 0) -> None:
         if self._L.igd_b200_reducer_allreduce(self._r, d_hits_ptr, stream):
