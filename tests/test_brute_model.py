@@ -86,3 +86,32 @@ def test_brute_model_agrees_with_oracle_on_seeded_inputs(dense_db):
         for v in (0, 300):
             want, _ = odb.count(q.ctg, q.start, q.end, v)
             assert np.array_equal(brute_count(dense_db, names, q.start, q.end, v, odb.nfiles), want), (seed, v)
+
+
+def brute_hitsmap(igd_path, v, nfiles):
+    """-m in closed form: the tile-by-tile self-join with its dedupe rule (a record that starts before the bin
+    only meets partners that start inside it, src/igd_search.c:802-804) counts every ORDERED pair of overlapping
+    intervals of a contig exactly once -- in the tile where the later of the two starts -- self-pairs included;
+    getMap_v keeps the pairs whose two values both exceed v (:856,872)."""
+    names, nbp, ctg, fidx, s, e, val = intervals_of(igd_path)
+    hm = np.zeros((nfiles, nfiles), np.int64)
+    for c in range(len(names)):
+        sel = ctg == c
+        S, E, F, V = s[sel], e[sel], fidx[sel], val[sel]
+        if v > 0:
+            k = V > v
+            S, E, F = S[k], E[k], F[k]
+        for i0 in range(0, len(S), 1024):
+            M = (S[None, :] < E[i0:i0 + 1024, None]) & (E[None, :] > S[i0:i0 + 1024, None])
+            rows = np.repeat(F[i0:i0 + 1024], M.sum(1))
+            cols = np.broadcast_to(F[None, :], M.shape)[M]
+            np.add.at(hm, (rows, cols), 1)
+    return (hm & 0xffffffff).astype(np.uint32)
+
+
+@pytest.mark.parametrize("name", ["quirk", "dense", "cfg1"])
+def test_brute_hitsmap_reproduces_the_reference(name, workdir):
+    case = GoldenCase(name, workdir)
+    n = len(case.exp["hits"])
+    assert np.array_equal(brute_hitsmap(case.igd, 0, n), case.hitsmap(0))
+    assert np.array_equal(brute_hitsmap(case.igd, 500, n), case.hitsmap(500))
