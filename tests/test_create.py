@@ -271,6 +271,49 @@ def test_create_awkward_lines_like_the_reference(workdir):
     assert len(got0["igd"]) > 12
 
 
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built")
+def test_create_odd_input_directories_like_the_reference(workdir):
+    """an empty file (its tsv line reads `-nan`), a sub-directory among the inputs, a multi-member gzip file and
+    a header line: same bytes, tsv and stdout as the unmodified reference."""
+    bed = os.path.join(workdir, "create_bed_odd")
+    _awkward_files(bed)
+    for i in (1, 2, 3, 4, 5, 6, 7, 9, 10, 11):          # plain files again, the oddities are about the directory
+        rng = np.random.default_rng(40 + i)
+        with open(os.path.join(bed, f"f{i:05d}.bed"), "w") as f:
+            for k in range(200):
+                a = int(rng.integers(0, 900000))
+                f.write(f"chr{1 + k % 3}\t{a}\t{a + int(rng.integers(1, 5000))}\tn{k}\t{int(rng.integers(0, 1000))}\n")
+    open(os.path.join(bed, "f00003.bed"), "w").close()                       # empty
+    os.makedirs(os.path.join(bed, "f00005.dir"))                              # a directory in the glob
+    lines = open(os.path.join(bed, "f00006.bed")).readlines()
+    os.remove(os.path.join(bed, "f00006.bed"))
+    with open(os.path.join(bed, "f00006.bed.gz"), "wb") as f:                 # two gzip members in one file
+        f.write(gzip.compress("".join(lines[:100]).encode()))
+        f.write(gzip.compress("".join(lines[100:]).encode()))
+    first = open(os.path.join(bed, "f00000.bed")).readlines()
+    with open(os.path.join(bed, "f00000.bed"), "w") as f:
+        f.writelines(["chrom\tstart\tend\tname\tscore\n"] + first)           # header line: atol("start") = 0 = atol("end")
+    ref = outputs(O.REF_BIN, workdir, bed, "ref_odd", [])
+    got = outputs(api.CLI_PATH, workdir, bed, "mine_odd", [])
+    assert got == ref
+    assert "nan" in got["tsv"]
+
+
+def test_create_gets_through_blank_and_comment_lines(workdir):
+    """two lines in a row with fewer fields than the code reads make the reference dereference the NULL that
+    str_splits just planted and die; this build reads an absent field as 0 and carries on.  (ONE such line does
+    not crash the reference -- it parses whatever the previous line left behind those stale pointers -- and there
+    the two agree, blanks-for-tabs case of the awkward-lines test.)"""
+    bed = os.path.join(workdir, "create_bed_blank")
+    _awkward_files(bed)
+    with open(os.path.join(bed, "f00000.bed"), "a") as f:
+        f.write("\n\n# a comment\ntrack name=x\n")
+    got = outputs(api.CLI_PATH, workdir, bed, "mine_blank", [])
+    assert "Save igd database to" in got["stdout"]
+    db = O.OracleDB(os.path.join(workdir, "mine_blank", "db.igd"))
+    assert db.nfiles == 12 and db.file_nr[0] == 304          # the four lines are counted in the tsv like any other
+
+
 def test_create_survives_coordinates_beyond_int32(workdir):
     """`chr1 3000000000 3000000100` narrows to a negative interval: the reference indexes tile -79040 and
     segfaults; here the line is counted in the tsv and stored nowhere"""
