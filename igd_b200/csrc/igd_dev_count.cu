@@ -84,14 +84,22 @@ __global__ void __launch_bounds__(CSEG_T) k_cseg_count(DbView db, int64_t n, con
         [&](int tile, int, int, int) { atomicAdd(&cnt2[2 * tile + 1], 1u); });
 }
 
-__device__ __forceinline__ Plan plan_of_tile(const DbView &db, const uint32_t *__restrict__ cnt2, int32_t t)
+// rank != 0 (M_PACKED, k_count_rank): a tile's records are searched as START entries against all of its segments
+// and as END entries against its first-bin segments, so it has ceil(n/GROUP) * (ceil(s/SMAX) + ceil(first/SMAX)) items
+constexpr uint32_t RK_END = 0x1ff;      // an END item of k_count_rank carries this in the tsr field of its descriptor
+
+__device__ __forceinline__ Plan plan_of_tile(const DbView &db, const uint32_t *__restrict__ cnt2, int32_t t, int rank,
+                                             unsigned long long *chunks = nullptr)
 {
     const uint2 c = __ldg(reinterpret_cast<const uint2 *>(cnt2) + t);
     const unsigned long long s = (unsigned long long)c.x + c.y;
+    if (chunks) *chunks = 0;
     if (s == 0) return Plan{0, 0};
     const unsigned long long g = ((unsigned long long)(uint32_t)db.tiles[t].n + GROUP - 1) / GROUP;
+    const unsigned long long ch = (s + SMAX - 1) / SMAX + (rank ? ((unsigned long long)c.x + SMAX - 1) / SMAX : 0);
+    if (chunks) *chunks = ch;
     // a tile's segments start at an even index: 8-byte segments, 16-byte aligned bulk copies
-    return Plan{(s + 1) & ~1ull, g * ((s + SMAX - 1) / SMAX)};
+    return Plan{(s + 1) & ~1ull, g * ch};
 }
 
 // The whole plan in ONE launch: a scan over the tiles fused with the item fill.  The grid is small enough that all
@@ -110,13 +118,15 @@ __device__ __forceinline__ Plan plan_of_tile(const DbView &db, const uint32_t *_
 //   z = records in the group (bits 0-8, 1..GROUP) | first record of the group that starts inside this bin
 //       (bits 9-17, 0..GROUP: the dedupe rule of later bins) | number of first-bin segments (bits 18-24, 0..64;
 //       the later-bin segments follow them) | number of segments (bits 25-31, 1..64)
-//   w = 0
+//   w = 0 (rank != 0: the group's number, see gk[])
+// An END item of k_count_rank (rank != 0) has x inside the END half of the count-mode copy, RK_END in the second
+// field of z, and only the first-bin segments of its chunk.
 
 __global__ void __launch_bounds__(SCAN_T) k_plan(DbView db, const uint32_t *__restrict__ cnt2, uint32_t epoch,
                                                   volatile PlanAgg *agg, volatile uint32_t *flag,
                                                   uint32_t *ticket, uint32_t *__restrict__ seg_off, uint32_t *__restrict__ seg_mid,
                                                   unsigned long long *__restrict__ tot, unsigned long long seg_cap,
-                                                  unsigned long long item_cap, int4 *__restrict__ items)
+                                                  unsigned long long item_cap, int4 *__restrict__ items, int rank)
 {
     __shared__ unsigned long long red[3][SCAN_T / 32];
     __shared__ unsigned long long sh_prefix[2], sh_total[3];
@@ -130,12 +140,10 @@ __global__ void __launch_bounds__(SCAN_T) k_plan(DbView db, const uint32_t *__re
     // 1. aggregate of this CTA's range
     unsigned long long segs = 0, its = 0, recs = 0;
     for (int32_t t = t0 + threadIdx.x; t < t1; t += SCAN_T) {
-        const Plan p = plan_of_tile(db, cnt2, t);
+        unsigned long long ch;
+        const Plan p = plan_of_tile(db, cnt2, t, rank, &ch);
         segs += p.segs, its += p.items;
-        if (p.items) {
-            const uint2 c = __ldg(reinterpret_cast<const uint2 *>(cnt2) + t);
-            recs += (unsigned long long)(uint32_t)db.tiles[t].n * ((c.x + c.y + SMAX - 1) / SMAX);
-        }
+        if (p.items) recs += (unsigned long long)(uint32_t)db.tiles[t].n * ch;
     }
 #pragma unroll
     for (int d = 16; d; d >>= 1) {
@@ -199,7 +207,7 @@ __global__ void __launch_bounds__(SCAN_T) k_plan(DbView db, const uint32_t *__re
     for (int32_t c0 = t0; c0 < t1; c0 += SCAN_T) {
         const int32_t t = c0 + threadIdx.x;
         const bool in = t < t1;
-        const Plan mine = in ? plan_of_tile(db, cnt2, t) : Plan{0, 0};
+        const Plan mine = in ? plan_of_tile(db, cnt2, t, rank) : Plan{0, 0};
         Plan ctot;
         const Plan ex = carry + block_exclusive<Plan>(mine, &ctot);
         carry += ctot;
@@ -209,18 +217,25 @@ __global__ void __launch_bounds__(SCAN_T) k_plan(DbView db, const uint32_t *__re
             const uint2 c = __ldg(reinterpret_cast<const uint2 *>(cnt2) + t);
             mid = sa0 + c.x, sb0 = mid + c.y;
             seg_off[t] = sa0, seg_mid[t] = mid;
-            if (ni) tm = __ldg(reinterpret_cast<const int4 *>(&db.tiles[t]));
+            if (ni) {
+                tm = __ldg(reinterpret_cast<const int4 *>(&db.tiles[t]));
+                tm.w = rank ? (int)__ldg(&db.gbase[t]) : 0;     // (s0 is not needed here)
+            }
         }
-        auto write = [&](uint32_t k, uint32_t i0_, uint32_t a, uint32_t m, uint32_t e, int4 tm_) {
+        auto write = [&](uint32_t k, uint32_t i0_, uint32_t a, uint32_t m, uint32_t e, int4 tm_) {   // tm_.w = first group
             const uint32_t ch = (e - a + SMAX - 1) / SMAX;
-            const uint32_t g = k / ch, c = k - g * ch;
-            const uint32_t sa = a + c * SMAX, sb = min(sa + (uint32_t)SMAX, e);
+            const uint32_t ng = ((uint32_t)tm_.y + GROUP - 1) / GROUP;
+            const bool endk = k >= ng * ch;                 // the END items follow the START items (rank only)
+            const uint32_t kk = endk ? k - ng * ch : k, chx = endk ? (m - a + SMAX - 1) / SMAX : ch;
+            const uint32_t g = kk / chx, c = kk - g * chx;
+            const uint32_t sa = a + c * SMAX, sb = min(sa + (uint32_t)SMAX, endk ? m : e);
             const int r0 = (int)(g * GROUP);
             const uint32_t nv = (uint32_t)min(tm_.y - r0, GROUP);
-            const uint32_t tsr = (uint32_t)min(max(tm_.z - r0, 0), GROUP);
+            const uint32_t tsr = endk ? RK_END : (uint32_t)min(max(tm_.z - r0, 0), GROUP);
             const uint32_t nfirst = min(max(m, sa), sb) - sa;
-            items[i0_ + k] = make_int4((int)((uint32_t)tm_.x + g * (GROUP / 8)), (int)sa,
-                                       (int)(nv | tsr << 9 | nfirst << 18 | (sb - sa) << 25), 0);
+            items[i0_ + k] = make_int4((int)((uint32_t)tm_.x + g * (GROUP / 8) + (endk ? db.eoff8 : 0u)), (int)sa,
+                                       (int)(nv | tsr << 9 | nfirst << 18 | (sb - sa) << 25),
+                                       (int)((uint32_t)tm_.w + g + (endk ? db.ngroups : 0u)));
         };
         // a thread writes up to 32 items of its tile itself; tiles with more are then done by the whole warp
         if (ni <= 32)
@@ -232,7 +247,7 @@ __global__ void __launch_bounds__(SCAN_T) k_plan(DbView db, const uint32_t *__re
             const uint32_t i0_ = __shfl_sync(FULL, i0, src), ni_ = __shfl_sync(FULL, ni, src);
             const uint32_t a_ = __shfl_sync(FULL, sa0, src), m_ = __shfl_sync(FULL, mid, src), e_ = __shfl_sync(FULL, sb0, src);
             const int4 tm_ = make_int4(__shfl_sync(FULL, tm.x, src), __shfl_sync(FULL, tm.y, src),
-                                       __shfl_sync(FULL, tm.z, src), 0);
+                                       __shfl_sync(FULL, tm.z, src), __shfl_sync(FULL, tm.w, src));
             for (uint32_t k = lane; k < ni_; k += 32) write(k, i0_, a_, m_, e_, tm_);
         }
     }
@@ -240,8 +255,8 @@ __global__ void __launch_bounds__(SCAN_T) k_plan(DbView db, const uint32_t *__re
 
 // cnt2 is counted back down to zero here, so it is clean for the next batch.  Nothing is written when the
 // plan does not fit the scratch buffers: the host then grows them and runs the batch again.
-// M_PACKED writes 4-byte segments in the tile's packed coordinates, pre-biased like the records:
-//   bits 0-15 = qs' + 1, bits 16-31 = qe' + 0x8000.
+// M_PACKED writes 4-byte segments in the tile's clamped coordinates, biased for k_count_rank's subtractions:
+//   bits 0-15 = qs' + 0x8000, bits 16-31 = qe' + 0x8000.
 template <bool V, int MODE>
 __global__ void __launch_bounds__(CSEG_T) k_cseg_scatter(DbView db, int64_t n, const int32_t *__restrict__ ctg,
                                                           const int32_t *__restrict__ qs, const int32_t *__restrict__ qe,
@@ -257,7 +272,7 @@ __global__ void __launch_bounds__(CSEG_T) k_cseg_scatter(DbView db, int64_t n, c
     auto put = [&](uint32_t pos, int s, int e, int bd) {
         if (MODE == M_PACKED)
             static_cast<uint32_t *>(segs)[pos] =
-                (uint32_t)(pk_rel(s, bd, nbp) + 1) | (uint32_t)(pk_rel_end(e, bd, nbp) + 0x8000) << 16;
+                (uint32_t)(pk_rel(s, bd, nbp) + 0x8000) | (uint32_t)(pk_rel_end(e, bd, nbp) + 0x8000) << 16;
         else
             static_cast<CSeg *>(segs)[pos] = CSeg{s, e};
     };
@@ -281,6 +296,7 @@ __global__ void __launch_bounds__(CSEG_T) k_cseg_scatter(DbView db, int64_t n, c
 struct CountArgs {
     DbView db;
     const int4 *items;
+    const int4 *desc;                   // k_count_rank: 2 x int4 per item (k_item_windows)
     const CSeg *segs;
     const unsigned long long *tot;      // device: {segments, items} of this batch
     unsigned long long seg_cap, item_cap;
@@ -519,40 +535,115 @@ __global__ void __launch_bounds__(COUNT_MAXW * 32, 1) k_count_items(const CountA
 }
 
 // ------------------------------------------------------------------------------------------------
-// count mode on the packed layout (the default path): the same tile-centric, record-stationary scheme as
-// k_count_items, on 16-bit tile-relative coordinates -- half the bytes per record and two records per
-// 32-bit operation.
-//   records  S = start' + 1 (1 .. nbp + 1; 0x8000 = pad / filtered out by -v), E = end' + 0x8000
-//   segments QS = qs' + 1, QE = qe' + 0x8000, each replicated into both halves of a register
-//   A = QE2 - S2 : bit 15 of a half is set  <=>  qe' > start'   (the halves are 0x8000 + qe' - S >= 0: no borrow)
-//   B = E2 - QS2 : bit 15 of a half is set  <=>  end' > qs'     (0x8000 + end' - QS >= 0x8000 - nbp - 1 > 0)
-//   counts (two 16-bit counters per register, <= 64 per item) += (A & B & 0x80008000) >> 15
-// i.e. 2 subtractions, 1 LOP3 and 1 shift-add per PAIR of (record, query) tests; the int32 kernel spends 3
-// ALU-pipe instructions per test.  An item is 256 records (8 per lane: one 16-byte load per array) x <= 64
-// segments.  Later-bin segments see S replaced by 0x8000 for the records that start before the bin (the
-// reference's i >= tS, src/igd_search.c:510-511,522).
-// Scheduling: one CTA per SM; a warp owns every NW-th BLOCK of 8 consecutive items (static, fine-grained
-// interleave: the spread between warps is at most one block), four blocks' descriptors are fetched with one
-// coalesced load.  Per warp a private K-stage cp.async ring as in k_count_items.
+// count mode on the 16-bit START / END entries (the default path).
+//
+// For a record r of a tile and the tile's first-bin segments F (queries whose first bin this is) and later-bin
+// segments L (queries that began in an earlier bin; src/igd_search.c:500-531 lets them count only the records that
+// start inside this bin, index >= tS), in the tile's clamped coordinates (pk_rel):
+//
+//   hits(r) = #{F : start'_r < qe' and end'_r > qs'} + [start'_r >= 1] #{L : start'_r < qe'}
+//           = #{F : qe' > start'_r} - #{F : qs' >= end'_r} + [start'_r >= 1] #{L : qe' > start'_r}
+//
+// (end'_r <= qs' implies start'_r < end'_r <= qs' < qe', so the second set lies inside the first).  The first and
+// third term depend on the record's START only, the second on its END only: a record is searched as two
+// independent entries, hits[file] += H(start') and hits[file] -= K(end'), with
+//   H(s) = #{F u L : qe' > s} for s >= 1,  H(0) = |F|;      K(e) = #{F : qs' >= e}
+// -- per-CTA sums are taken modulo 2^32 and flushed sign-extended.  Both halves of the count-mode copy are sorted
+// by their key inside a tile (igd_dev_impl.cuh), so an item's 256 keys lie in [klo, khi] = [first, last] and a
+// segment is on the far side of ALL of them (it goes into a base count), of NONE, or INSIDE THE WINDOW -- only
+// those are compared entry by entry: with ~56 segments per 5 500-record tile (BASELINE config 3) 2-3 of them per
+// item, where a pair test of records against segments meets 14-20.
+//
+//   entries  START: S = start' + 1 (1 .. nbp + 1; pads 0x8000)        END: E = end' (2 .. nbp + 1; pads 0x7fff)
+//   segments 4 B: xe = qs' + 0x8000 | (xs = qe' + 0x8000) << 16;      x = xs (START items), xe (END items)
+//   x - key >= 0x8000  <=>  qe' > start'  resp.  qs' >= end';   no 16-bit half ever borrows (tests/test_packed_math.py)
+//   counts (two 16-bit counters per register, <= 64 per item) += ((x2 - key2) & 0x80008000) >> 15
+// i.e. 1 subtraction, 1 LOP3 and 1 shift-add per PAIR of entries and segment inside the window.
+//
+// Which segments are in an item's window is the same for all 32 lanes, so it is not decided in the search kernel,
+// where a warp-uniform instruction costs 32 lanes: k_item_windows (one THREAD per item) reads the item's first and
+// last key and its <= 64 segments and leaves the base count and a 64-bit mask of the segments inside the window in
+// the item's descriptor.
 // ------------------------------------------------------------------------------------------------
-constexpr int PK_K = 4;                 // pipeline stages per warp
-constexpr int PK_MAXW = 24;             // most warps per CTA (register budget 65536 / 768 = 85)
-constexpr int PK_IB = 8;                // items per block
+constexpr int RK_MAXW = 32;             // most warps per CTA
+constexpr int RK_IB = 8;                // items per block
+constexpr uint32_t RK_INL = 4;          // segments inside an item's window that travel in its descriptor
+
+// descriptor of k_count_rank, 2 x int4:
+//   A.x = first entry of the item in the count-mode copy, in units of 8 entries     A.y = first segment
+//   A.z = entries (bits 0-8) | segments (9-15) | base count (16-22) | later-bin segments (23-29) | END item (30)
+//         | fix (31: a START item with entries before the bin AND later-bin segments -- see k_count_rank)
+//   A.w = window mask of segments 0-31                                                B.x = of segments 32-63
+//   B.w = number of segments inside the window; when there are <= RK_INL of them their x values themselves are in
+//         B.y (first | second << 16) and B.z, and the search kernel touches neither the masks nor the segments
+__global__ void __launch_bounds__(256) k_item_windows(DbView db, const int4 *__restrict__ items,
+                                                       const uint32_t *__restrict__ segs,
+                                                       const unsigned long long *__restrict__ tot,
+                                                       unsigned long long seg_cap, unsigned long long item_cap,
+                                                       int4 *__restrict__ out)
+{
+    pdl_launch_dependents();
+    pdl_wait();                                             // the plan, the items, the segments
+    const unsigned long long nseg = tot[0], nit = tot[1];
+    if (nseg > seg_cap || nit > item_cap) return;
+    const unsigned long long nk = (nit + 31) & ~31ull;      // (the item array is padded to a multiple of 32)
+    for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < nk;
+         k += (unsigned long long)gridDim.x * blockDim.x) {
+        const int4 it = __ldg(&items[k]);
+        const uint32_t z = (uint32_t)it.z;
+        const uint32_t nv = z & 0x1ffu, tsf = (z >> 9) & 0x1ffu, nf = (z >> 18) & 0x7fu, ns = z >> 25;
+        if (nv == 0) {
+            out[2 * k] = make_int4(0, 0, 0, 0), out[2 * k + 1] = make_int4(0, 0, 0, 0);
+            continue;
+        }
+        const bool endk = tsf == RK_END;
+        const uint32_t kr = __ldg(&db.gk[(uint32_t)it.w]);          // the group's smallest and largest key
+        const uint32_t lo_t = (kr & 0xffffu) + 0x8000u, hi_t = (kr >> 16) + 0x8000u;
+        const uint32_t *sg = segs + (uint32_t)it.y;
+        uint32_t base = 0, m[2] = {0, 0}, nin = 0, v01 = 0, v23 = 0;
+#pragma unroll 4
+        for (uint32_t i = 0; i < ns; ++i) {
+            const uint32_t w = __ldg(&sg[i]), x = endk ? w & 0xffffu : w >> 16;
+            base += x >= hi_t;                              // past every key of the item
+            if (x >= lo_t && x < hi_t) {                    // past some: compared entry by entry
+                m[i >> 5] |= 1u << (i & 31);
+                if (nin < 2) v01 |= x << (16 * nin);
+                else if (nin < 4) v23 |= x << (16 * (nin - 2));
+                ++nin;
+            }
+        }
+        const uint32_t fix = !endk && tsf > 0 && ns > nf;
+        out[2 * k] = make_int4(it.x, it.y,
+                               (int)(nv | ns << 9 | base << 16 | (ns - nf) << 23 | (uint32_t)endk << 30 | fix << 31), (int)m[0]);
+        out[2 * k + 1] = make_int4((int)m[1], (int)v01, (int)v23, (int)nin);
+    }
+}
+
+__device__ __forceinline__ uint32_t lds32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const int4 v)
+{
+    asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+constexpr int RK_K = 3;                 // stages of a warp's entry ring
 
 template <bool V>
-struct PackedSmem {
+struct RankSmem {
+    static constexpr uint32_t DESC = 2 * 32 * 32;                       // a warp's ring of 64 descriptors
     static constexpr uint32_t ARR = GROUP * 2;                          // one 16-bit array of a stage
-    static constexpr uint32_t VOFF = 3 * ARR;                           // 16-bit value[GROUP] (-v only)
-    static constexpr uint32_t QOFF = VOFF + (V ? ARR : 0);
-    static constexpr uint32_t STAGE = QOFF + SMAX * 4;
-    static constexpr uint32_t LIST = PK_K * STAGE;                      // survivor list: SMAX x {QS2, QE2}
-    static constexpr uint32_t WARP = LIST + SMAX * 8;
-    static size_t hist_bytes(int nfiles) { return ((size_t)nfiles * 4 + 127) / 128 * 128; }
+    static constexpr uint32_t STAGE = (V ? 3 : 2) * ARR;                // keys | files | (values)
+    static constexpr uint32_t WARP = DESC + RK_K * STAGE;
+    static size_t hist_bytes(int nfiles) { return ((size_t)(nfiles + 1) * 4 + 127) / 128 * 128; }   // + the pads' slot
     static int warps(int nfiles, bool smem_hist)
     {
         const size_t total = 226 * 1024, hist = smem_hist ? hist_bytes(nfiles) : 0;
         if (hist >= total) return 0;                        // the histogram alone does not fit
-        return (int)std::min<size_t>((total - hist) / WARP, PK_MAXW);
+        return (int)std::min<size_t>((total - hist) / WARP, RK_MAXW);
     }
     static size_t cta_bytes(int nfiles, bool smem_hist, int nwarps)
     {
@@ -560,245 +651,181 @@ struct PackedSmem {
     }
 };
 
-__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ uint32_t lds32(uint32_t addr)
-{
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-
-__device__ __forceinline__ void sts64(uint32_t addr, uint32_t x, uint32_t y)
-{
-    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
-}
-// segments [i0, i1) of the warp's survivor list against this lane's 4 record pairs
-__device__ __forceinline__ void count_pairs(uint32_t list, int i0, int i1, const uint32_t (&S)[4],
-                                            const uint32_t (&E)[4], uint32_t (&c)[4])
-{
-    auto eval = [&](const int2 q) {
-        const uint32_t s2 = (uint32_t)q.x, e2 = (uint32_t)q.y;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            uint32_t t;                                     // (A & B & 0x80008000): one 3-input LOP3
-            asm("lop3.b32 %0, %1, %2, 0x80008000, 0x80;" : "=r"(t) : "r"(e2 - S[k]), "r"(E[k] - s2));
-            c[k] += t >> 15;                                // LEA.HI
-        }
-    };
-    uint32_t p = list + 8u * (uint32_t)i0;
-    const uint32_t end = list + 8u * (uint32_t)i1;
-#pragma unroll 1
-    for (; p + 16 <= end; p += 16) {                        // same address in every lane: broadcast loads
-        const int2 q0 = lds64(p), q1 = lds64(p + 8);
-        eval(q0);
-        eval(q1);
-    }
-    if (p < end) eval(lds64(p));
-}
-
+// The count-mode search kernel: ONE CTA per SM, up to 32 warps.  A warp owns every NW-th BLOCK of 8 consecutive
+// items (static, fine-grained interleave); the descriptors of 32 items at a time go through a warp-private ring in
+// shared memory (read back with broadcast loads); the entries go through a private K-stage cp.async ring: K - 1
+// items ahead of the one being evaluated every lane copies ITS OWN 16 bytes of keys and of file indices into its
+// own slots, so no lane reads another lane's bytes and the ring needs no barrier -- a lane's cp.async.wait_group
+// covers exactly the bytes it is about to read.  (Loading straight into registers two items ahead was tried: the
+// hardware's six scoreboards per warp are shared between the slots, and a use of the oldest slot then waits for
+// the loads issued just before it.)
 template <bool V, bool SMEM>
-__global__ void __launch_bounds__(PK_MAXW * 32, 1) k_count_packed(const CountArgs a)
+__global__ void __launch_bounds__(RK_MAXW * 32, 1) k_count_rank(const CountArgs a)
 {
-    using L = PackedSmem<V>;
+    using L = RankSmem<V>;
     extern __shared__ __align__(128) unsigned char smem[];
     const DbView &db = a.db;
     uint32_t *hist = reinterpret_cast<uint32_t *>(smem);
-    const uint32_t hist_bytes = SMEM ? ((uint32_t)db.nfiles * 4 + 127) / 128 * 128 : 0;
+    const uint32_t hist_bytes = SMEM ? ((uint32_t)(db.nfiles + 1) * 4 + 127) / 128 * 128 : 0;
     if (SMEM) {
-        for (int f = threadIdx.x; f < db.nfiles; f += blockDim.x) hist[f] = 0;
+        for (int f = threadIdx.x; f <= db.nfiles; f += blockDim.x) hist[f] = 0;
         __syncthreads();
     }
     const uint32_t hist_s = smem_u32(smem);
     const int lane = threadIdx.x & 31, W = blockDim.x >> 5, wib = threadIdx.x >> 5;
-    const uint32_t wbase = hist_s + hist_bytes + (uint32_t)wib * L::WARP;
-    pdl_wait();                                             // the plan, the items, the segments
+    const uint32_t ring = hist_s + hist_bytes + (uint32_t)wib * L::WARP;       // descriptors
+    const uint32_t lslot = ring + L::DESC + lane * 16;                          // this lane's column of the stages
+    pdl_wait();                                             // the plan, the descriptors, the segments
     const unsigned long long nseg = a.tot[0], nit = a.tot[1];
     const uint32_t n_items = (nseg > a.seg_cap || nit > a.item_cap) ? 0u : (uint32_t)nit;
-    const uint32_t nblk = (n_items + PK_IB - 1) / PK_IB, NW = gridDim.x * W, w = blockIdx.x * W + wib;
+    const uint32_t nblk = (n_items + RK_IB - 1) / RK_IB, NW = gridDim.x * W, w = blockIdx.x * W + wib;
     const uint32_t nb = w < nblk ? (nblk - w + NW - 1) / NW : 0;       // blocks of this warp
-    const uint32_t N = nb * PK_IB;                                      // item slots of this warp
+    const uint32_t N = nb * RK_IB;                                      // item slots of this warp
 
-    // descriptor registers: lane j of quad-block g holds item (j % 8) of this warp's block 4 g + j / 8
+    // descriptors: lane j of quad-block g holds item (j % 8) of this warp's block 4 g + j / 8; quad-block g lives in
+    // half g % 2 of the ring, 32 bytes per item
     const int4 zero = make_int4(0, 0, 0, 0);
-    auto load_desc = [&](uint32_t g) {
+    auto load_desc = [&](uint32_t g, int4 &A, int4 &B) {
         const uint32_t b = 4 * g + (lane >> 3);
-        const size_t it = ((size_t)b * NW + w) * PK_IB + (lane & 7);
-        return (b < nb && it < n_items) ? __ldg(&a.items[it]) : zero;
+        const size_t it = ((size_t)b * NW + w) * RK_IB + (lane & 7);
+        const bool in = b < nb && it < n_items;
+        A = in ? __ldg(&a.desc[2 * it]) : zero;
+        B = in ? __ldg(&a.desc[2 * it + 1]) : zero;
     };
-    int4 dcur = load_desc(0), dnxt = load_desc(1);
-    const uint16_t *const pS = db.ps + lane * 8, *const pE = db.pe + lane * 8, *const pF = db.pf + lane * 8;
-    const uint16_t *const pV = db.pv + lane * 8;
-    const uint32_t *const pQ = static_cast<const uint32_t *>(static_cast<const void *>(a.segs)) + lane;
-    const uint32_t lslot = wbase + lane * 16, vslot = wbase + L::VOFF + lane * 16, qslot = wbase + L::QOFF + lane * 4;
-
-    // The stages start out as pads: a lane without records in an item reads what an earlier item (or this fill)
-    // left in its slots -- its counts are discarded, and the prune window only gets wider.
-    for (uint32_t o = lane * 16; o < L::LIST; o += 512)
-        asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(wbase + o), "r"(0x80008000u) : "memory");
+    auto store_desc = [&](uint32_t g, const int4 &A, const int4 &B) {
+        const uint32_t p = ring + (g & 1) * 1024 + lane * 32;
+        sts128(p, A), sts128(p + 16, B);
+    };
+    int4 nA, nB;
+    load_desc(0, nA, nB);
+    store_desc(0, nA, nB);
+    load_desc(1, nA, nB);
+    store_desc(1, nA, nB);
     __syncwarp();
+    load_desc(2, nA, nB);
 
-    // issue the copies of item slot n (descriptor in lane n % 32 of dd) into stage n % K
-    auto issue = [&](uint32_t n, const int4 &dd) {
-        const int j = n & 31;
-        const uint32_t x = __shfl_sync(FULL, dd.x, j), y = __shfl_sync(FULL, dd.y, j), z = __shfl_sync(FULL, dd.z, j);
-        const int nv = z & 0x1ff, ns = z >> 25;
-        const uint32_t so = (n % PK_K) * L::STAGE;
-        const size_t p = (size_t)x * 8;
-        if (lane * 8 < nv) {
-            cp_async16(lslot + so, pS + p);
-            cp_async16(lslot + so + L::ARR, pE + p);
-            cp_async16(lslot + so + 2 * L::ARR, pF + p);
-            if (V) {
-                cp_async16(vslot + so, pV + p);
+    const uint16_t *const pB = db.rb + lane * 8;
+    const uint16_t *const pV = db.rv + lane * 8;
+
+    // issue the copies of item slot n into stage n % K
+    auto issue = [&](uint32_t n) {
+        if (n < N) {
+            const int2 xz = lds64(ring + (n & 63) * 32);                // A.x, A.y
+            const uint32_t z = lds32(ring + (n & 63) * 32 + 8), nv = z & 0x1ffu;
+            if ((uint32_t)lane * 8 < nv) {
+                const uint32_t so = lslot + (n % RK_K) * L::STAGE, nvp = (nv + 7) & ~7u;
+                const uint16_t *p = pB + (size_t)(uint32_t)xz.x * 16;
+                cp_async16(so, p);
+                cp_async16(so + L::ARR, p + nvp);
+                if (V) cp_async16(so + 2 * L::ARR, pV + (size_t)(uint32_t)xz.x * 8);
             }
         }
-        if (lane < ns) cp_async4(qslot + so, pQ + y);
-        if (lane + 32 < ns) cp_async4(qslot + so + 128, pQ + y + 32);
+        cp_async_commit();
     };
 
-#pragma unroll
-    for (int n = 0; n < PK_K - 1; ++n) {                                // prologue: slots 0 .. K-2 (quad-block 0)
-        if ((uint32_t)n < N) issue(n, dcur);
-        cp_async_commit();
-    }
-
-    const uint32_t lt = (1u << lane) - 1u;
-    const uint32_t list = wbase + L::LIST;
-    for (uint32_t n = 0; n < N; ++n) {
-        const int j = n & 31;
-        {
-            const uint32_t m = n + PK_K - 1;                            // goes into the stage slot n - 1 released
-            if (m < N) {
-                if ((m >> 5) == (n >> 5)) issue(m, dcur);
-                else issue(m, dnxt);
-            }
-            cp_async_commit();
-        }
-        cp_async_wait<PK_K - 1>();                                      // slot n has landed (this lane's bytes)
-        const uint32_t dz = __shfl_sync(FULL, dcur.z, j);
-        const uint32_t so = (n % PK_K) * L::STAGE;
-        const int nv = dz & 0x1ff, nf = (dz >> 18) & 0x7f, ns = dz >> 25;
-        if (nv > 0) {
-            const bool have = lane * 8 < nv;
-            const int4 s_ = lds128(lslot + so), e_ = lds128(lslot + so + L::ARR), f_ = lds128(lslot + so + 2 * L::ARR);
-            uint32_t S[4] = {(uint32_t)s_.x, (uint32_t)s_.y, (uint32_t)s_.z, (uint32_t)s_.w};
-            const uint32_t E[4] = {(uint32_t)e_.x, (uint32_t)e_.y, (uint32_t)e_.z, (uint32_t)e_.w};
-            const uint32_t F[4] = {(uint32_t)f_.x, (uint32_t)f_.y, (uint32_t)f_.z, (uint32_t)f_.w};
-            if (V && have) {                                            // value < v: the record matches no query
-                // pv = value' + 0x8000 with value' = clamp(value, 0, 32767), and 1 <= v <= 32767 on this path:
-                // bit 15 of a half of (pv2 - v2) is set  <=>  value' >= v  <=>  value >= v  (no half borrows)
-                const int4 pv_ = lds128(vslot + so);
-                const uint32_t pv2[4] = {(uint32_t)pv_.x, (uint32_t)pv_.y, (uint32_t)pv_.z, (uint32_t)pv_.w};
-                const uint32_t v2 = (uint32_t)a.v * 0x10001u;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint32_t keep = (((pv2[k] - v2) & 0x80008000u) >> 15) * 0xffffu;   // 0xffff per kept half
-                    S[k] = (S[k] & keep) | (0x80008000u & ~keep);
-                }
-            }
-            uint32_t c[4] = {0, 0, 0, 0};
-            // prune window of the group: smallest S (records are sorted by start: the first one; with -v the
-            // smallest surviving one) and largest E
-            // (a dense tile's packed copy is not in start order -- its long records are kept apart, k_pack_tiles --
-            // so the smallest start is found, not assumed to be the first record's)
-            uint32_t smin;
-            {
-                const uint32_t m2 = __vminu2(__vminu2(S[0], S[1]), __vminu2(S[2], S[3]));
-                smin = __reduce_min_sync(FULL, have ? min(m2 & 0xffffu, m2 >> 16) : 0xffffu);
-            }
-            const uint32_t x2 = __vmaxu2(__vmaxu2(E[0], E[1]), __vmaxu2(E[2], E[3]));
-            const uint32_t emax = __reduce_max_sync(FULL, max(x2 & 0xffffu, x2 >> 16));
-            // a segment can touch the group iff qe' > smallest start' and qs' < largest end':
-            //   QE - smin >= 0x8000  and  emax - QS >= 0x8000
-            const uint32_t qe_lo = smin + 0x8000u, qs_hi = emax - 0x8000u;     // QE >= qe_lo, QS <= qs_hi
-            // segments lane and 32 + lane of the item; an absent one has qe' = 0 and survives no prune
-            const uint32_t w0 = lane < ns ? lds32(qslot + so) : 0x80000000u;
-            const uint32_t qs2_0 = __byte_perm(w0, 0, 0x1010), qe2_0 = __byte_perm(w0, 0, 0x3232);
-            uint32_t w1 = 0x80000000u, qs2_1 = 0, qe2_1 = 0;
-            if (ns > 32) {
-                if (lane + 32 < ns) w1 = lds32(qslot + so + 128);
-                qs2_1 = __byte_perm(w1, 0, 0x1010), qe2_1 = __byte_perm(w1, 0, 0x3232);
-            }
-            // The surviving segments are compacted into the warp's list (first-bin ones, then later-bin ones)
-            // and streamed back with broadcast loads: 1 load + 16 ALU/FMA instructions per segment x 256 records.
-            __syncwarp();                                               // the previous item's list has been read
-            // first-bin segments [0, nf): every record of the tile is a candidate
-            int nF = 0;
-            if (nf > 0) {
-                const unsigned f0 = __ballot_sync(FULL, (w0 >> 16) >= qe_lo && (w0 & 0xffffu) <= qs_hi && lane < nf);
-                if (f0 >> lane & 1) sts64(list + 8u * __popc(f0 & lt), qs2_0, qe2_0);
-                nF = __popc(f0);
-                if (nf > 32) {
-                    const unsigned f1 = __ballot_sync(FULL, (w1 >> 16) >= qe_lo && (w1 & 0xffffu) <= qs_hi && lane + 32 < nf);
-                    if (f1 >> lane & 1) sts64(list + 8u * (nF + __popc(f1 & lt)), qs2_1, qe2_1);
-                    nF += __popc(f1);
-                }
-            }
-            // later-bin segments [nf, ns): only the records that start inside this bin count (index >= tS,
-            // src/igd_search.c:510-511,522), i.e. start' >= 1.  Such a segment has qs' = 0 (QS = 1), so its
-            // end test is vacuous; it is given X = S + 0x7fff in place of E, which turns that test into
-            // bit 15 of (S + 0x7fff - 1), set  <=>  S >= 2  <=>  start' >= 1.
-            int nL = 0;
-            if (ns > nf) {
-                // prune with the smallest start among the records that start inside the bin (S >= 2): per half,
-                // S - 2 wraps to >= 0xfffe for the others, which no minimum picks while a real one exists
-                uint32_t slmin;
-                {
-                    const uint32_t two = 0x00020002u;
-                    const uint32_t m2 = __vminu2(__vminu2(__vsub2(S[0], two), __vsub2(S[1], two)),
-                                                 __vminu2(__vsub2(S[2], two), __vsub2(S[3], two)));
-                    slmin = __reduce_min_sync(FULL, have ? min(m2 & 0xffffu, m2 >> 16) : 0xffffu) + 2u;
-                }
-                const uint32_t qel = slmin + 0x8000u;
-                if (nf < 32) {
-                    const unsigned l0 = __ballot_sync(FULL, (w0 >> 16) >= qel && (w0 & 0xffffu) <= qs_hi && lane >= nf);
-                    if (l0 >> lane & 1) sts64(list + 8u * (nF + __popc(l0 & lt)), qs2_0, qe2_0);
-                    nL = __popc(l0);
-                }
-                if (ns > 32) {
-                    const unsigned l1 = __ballot_sync(FULL, (w1 >> 16) >= qel && (w1 & 0xffffu) <= qs_hi && lane + 32 >= nf);
-                    if (l1 >> lane & 1) sts64(list + 8u * (nF + nL + __popc(l1 & lt)), qs2_1, qe2_1);
-                    nL += __popc(l1);
-                }
-            }
-            __syncwarp();
-            count_pairs(list, 0, nF, S, E, c);
-            if (nL > 0) {
-                const uint32_t X[4] = {S[0] + 0x7fff7fffu, S[1] + 0x7fff7fffu, S[2] + 0x7fff7fffu, S[3] + 0x7fff7fffu};
-                count_pairs(list, nF, nF + nL, S, X, c);
-            }
-            // hits[file] += count.  One test per PAIR of records (neighbours in start order are mostly hit
-            // together or not at all), then one shared-memory atomic per record.
+    // evaluate item slot n
+    auto eval = [&](uint32_t n) {
+        const int4 A = lds128(ring + (n & 63) * 32);
+        const uint32_t z = (uint32_t)A.z, nv = z & 0x1ffu;
+        if (nv == 0) return;
+        const int4 B = lds128(ring + (n & 63) * 32 + 16);
+        const bool endk = z >> 30 & 1;
+        const uint32_t so = lslot + (n % RK_K) * L::STAGE;
+        const int4 k_ = lds128(so), f_ = lds128(so + L::ARR);
+        const uint32_t K[4] = {(uint32_t)k_.x, (uint32_t)k_.y, (uint32_t)k_.z, (uint32_t)k_.w};
+        const uint32_t F[4] = {(uint32_t)f_.x, (uint32_t)f_.y, (uint32_t)f_.z, (uint32_t)f_.w};
+        const uint32_t base2 = ((z >> 16) & 0x7fu) * 0x10001u;
+        uint32_t c[4] = {base2, base2, base2, base2};
+        auto step = [&](const uint32_t x2) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                if (have && c[k]) {
-                    const uint32_t c0 = c[k] & 0xffffu, c1 = c[k] >> 16;
-                    if (SMEM) {
-                        const uint32_t a0 = hist_s + ((F[k] << 2) & 0x3fffcu), a1 = hist_s + ((F[k] >> 14) & 0x3fffcu);
-                        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a0), "r"(c0) : "memory");
-                        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a1), "r"(c1) : "memory");
-                    } else {
-                        const uint32_t f0 = F[k] & 0xffffu, f1 = F[k] >> 16;
-                        if (c0) atomicAdd(&a.hits[f0], (unsigned long long)c0);
-                        if (c1) atomicAdd(&a.hits[f1], (unsigned long long)c1);
-                    }
+                uint32_t t;                                             // (x2 - K) & 0x80008000
+                asm("lop3.b32 %0, %1, 0x80008000, 0, 0xc0;" : "=r"(t) : "r"(x2 - K[k]));
+                c[k] += t >> 15;                                        // LEA.HI
+            }
+        };
+        const uint32_t nin = (uint32_t)B.w;                             // the segments inside the window
+        if (nin <= RK_INL) {
+            if (nin > 0) step(__byte_perm((uint32_t)B.y, 0, 0x1010));
+            if (nin > 1) step(__byte_perm((uint32_t)B.y, 0, 0x3232));
+            if (nin > 2) step(__byte_perm((uint32_t)B.z, 0, 0x1010));
+            if (nin > 3) step(__byte_perm((uint32_t)B.z, 0, 0x3232));
+        } else {
+            // more than the descriptor holds (few items): lane i fetches segment i / 32 + i if it is in the window
+            const uint32_t sel = endk ? 0x1010u : 0x3232u;              // x = xe (END items) or xs, in both halves
+            const uint32_t *pQ = static_cast<const uint32_t *>(static_cast<const void *>(a.segs)) + (uint32_t)A.y + lane;
+            uint32_t m0 = (uint32_t)A.w, m1 = (uint32_t)B.x;
+            const uint32_t w0 = m0 >> lane & 1 ? __ldg(pQ) : 0u, w1 = m1 >> lane & 1 ? __ldg(pQ + 32) : 0u;
+            while (m0) {
+                const int i = __ffs(m0) - 1;
+                m0 &= m0 - 1;
+                step(__byte_perm(__shfl_sync(FULL, w0, i), 0, sel));
+            }
+            while (m1) {
+                const int i = __ffs(m1) - 1;
+                m1 &= m1 - 1;
+                step(__byte_perm(__shfl_sync(FULL, w1, i), 0, sel));
+            }
+        }
+        if (z >> 31) {
+            // a START item with entries that start before the bin (S == 1) and later-bin segments, which count only
+            // for the entries inside the bin (src/igd_search.c:510-511,522): every xs is past S == 1, so those
+            // entries have counted all of them -- taken back here
+            const uint32_t nl = (z >> 23) & 0x7fu;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) c[k] -= (((0x80018001u - K[k]) & 0x80008000u) >> 15) * nl;
+        }
+        if (V) {                                                        // value < v: the record counts for no query
+            // rv = value' + 0x8000 with value' = clamp(value, 0, 32767), and 1 <= v <= 32767 on this path:
+            // bit 15 of a half of (rv2 - v2) is set  <=>  value' >= v  <=>  value >= v  (no half borrows)
+            const int4 v_ = lds128(so + 2 * L::ARR);
+            const uint32_t pv2[4] = {(uint32_t)v_.x, (uint32_t)v_.y, (uint32_t)v_.z, (uint32_t)v_.w};
+            const uint32_t v2 = (uint32_t)a.v * 0x10001u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) c[k] &= (((pv2[k] - v2) & 0x80008000u) >> 15) * 0xffffu;
+        }
+        // hits[file] += count (START) or -= count (END): one shared-memory atomic per entry; the pads of a tile's
+        // last group carry file = nfiles, the histogram's trash slot
+        if ((uint32_t)lane * 8 < nv) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint32_t c0 = c[k] & 0xffffu, c1 = c[k] >> 16;
+                if (endk) c0 = 0u - c0, c1 = 0u - c1;
+                if (SMEM) {
+                    const uint32_t a0 = hist_s + ((F[k] << 2) & 0x3fffcu), a1 = hist_s + ((F[k] >> 14) & 0x3fffcu);
+                    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a0), "r"(c0) : "memory");
+                    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a1), "r"(c1) : "memory");
+                } else {
+                    const uint32_t f0 = F[k] & 0xffffu, f1 = F[k] >> 16;
+                    if (c0 && f0 < (uint32_t)db.nfiles) atomicAdd(&a.hits[f0], (unsigned long long)(long long)(int32_t)c0);
+                    if (c1 && f1 < (uint32_t)db.nfiles) atomicAdd(&a.hits[f1], (unsigned long long)(long long)(int32_t)c1);
                 }
             }
         }
-        if (j == 31) {                                                  // next quad-block of descriptors
-            dcur = dnxt;
-            dnxt = load_desc((n >> 5) + 2);
+    };
+
+#pragma unroll
+    for (int n = 0; n < RK_K - 1; ++n) issue(n);                        // prologue: slots 0 .. K-2
+    for (uint32_t n = 0; n < N; ++n) {
+        issue(n + RK_K - 1);                                            // goes into the stage slot n - 1 released
+        cp_async_wait<RK_K - 1>();                                      // slot n has landed (this lane's bytes)
+        eval(n);
+        // every 32 items the descriptors of the quad-block after next move into the half of the ring that the one
+        // just finished has left (items n + 1 .. n + K - 1 -- already issued -- are in the other half)
+        if ((n & 31) == 31) {
+            const uint32_t g = (n >> 5) + 2;
+            __syncwarp();
+            store_desc(g, nA, nB);
+            __syncwarp();
+            load_desc(g + 1, nA, nB);
         }
     }
     cp_async_wait<0>();
     if (SMEM) {
         __syncthreads();
         for (int f = threadIdx.x; f < db.nfiles; f += blockDim.x) {
-            const uint32_t c = hist[f];
-            if (c) atomicAdd(&a.hits[f], (unsigned long long)c);
+            const uint32_t c = hist[f];                                 // a sum modulo 2^32 of +H and -K: signed
+            if (c) atomicAdd(&a.hits[f], (unsigned long long)(long long)(int32_t)c);
         }
     }
 }
@@ -825,7 +852,7 @@ cudaError_t launch_pdl(void (*k)(KArgs...), unsigned grid, unsigned block, size_
 template <bool V, bool PK>
 int count_geometry(igdb_dev *d, int *grid, int *threads, size_t *shm, bool *smem)
 {
-    using LP = PackedSmem<V>;
+    using LP = RankSmem<V>;
     using L32 = CountSmem<V>;
     // the shared histogram is used while it leaves room for at least 8 warps' pipelines
     *smem = (PK ? LP::warps(d->nfiles, true) : L32::warps(d->nfiles, true)) >= 8;
@@ -833,7 +860,7 @@ int count_geometry(igdb_dev *d, int *grid, int *threads, size_t *shm, bool *smem
     *shm = PK ? LP::cta_bytes(d->nfiles, *smem, nw) : L32::cta_bytes(d->nfiles, *smem, nw);
     *threads = nw * 32;
     if (d->count_grid[PK][V] == 0) {
-        const void *k = PK ? (*smem ? (const void *)k_count_packed<V, true> : (const void *)k_count_packed<V, false>)
+        const void *k = PK ? (*smem ? (const void *)k_count_rank<V, true> : (const void *)k_count_rank<V, false>)
                            : (*smem ? (const void *)k_count_items<V, true> : (const void *)k_count_items<V, false>);
         CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*shm));
         d->count_grid[PK][V] = d->sm_count;
@@ -842,8 +869,9 @@ int count_geometry(igdb_dev *d, int *grid, int *threads, size_t *shm, bool *smem
     return 0;
 }
 
-// a CTA's shared histogram is uint32: an item adds at most GROUP*SMAX <= 2^15, a CTA takes at most
-// items/grid + 32*COUNT_MAXW items, so this many items per launch cannot overflow a counter
+// a CTA's shared histogram is 32 bits wide (k_count_rank: a SIGNED sum of +H and -K): an item moves a counter by at
+// most GROUP*SMAX = 2^14, a CTA takes at most items/grid + 32*COUNT_MAXW items, so with this many items per launch
+// no counter leaves (-2^31, 2^31)
 int64_t item_limit(const igdb_dev *d, int grid) { return ((int64_t)(1 << 17) - 1024) * grid; }
 // the kernels may touch up to 32 descriptors / 1 segment past the plan's totals (padding)
 constexpr int64_t CAP_SLACK = 64;
@@ -859,8 +887,9 @@ int enqueue_count_t(igdb_dev *d, const igdb_dev::Pending &p)
     bool smem = false;
     if (count_geometry<V, PK>(d, &grid, &threads, &shm, &smem)) return -1;
     if (grow(&d->csegs, &d->cseg_cap, std::max<int64_t>(2 * p.n + 2 * d->T, 4096), 1, 1)) return -1;
-    if (grow(&d->items, &d->item_cap, std::min<int64_t>(d->db_groups + p.n / 64, item_limit(d, grid)) + 1024, 1, 1))
+    if (grow(&d->items, &d->item_cap, std::min<int64_t>((PK ? 2 : 1) * (d->db_groups + p.n / 64), item_limit(d, grid)) + 1024, 1, 1))
         return -1;
+    if (PK && grow(&d->items2, &d->item2_cap, 2 * d->item_cap, 1, 1)) return -1;
     const unsigned long long seg_cap = (unsigned long long)std::min<int64_t>(d->cseg_cap - CAP_SLACK, 0x7fffffff);
     const unsigned long long item_cap =
         (unsigned long long)std::min<int64_t>(d->item_cap - CAP_SLACK, item_limit(d, grid));
@@ -880,7 +909,7 @@ int enqueue_count_t(igdb_dev *d, const igdb_dev::Pending &p)
     if (stages) CK(cudaEventRecord(d->stage_ev[1], st));
     // (the plan reads the later-bin counters that the scatter counts back down to zero)
     CK(launch_pdl(k_plan, d->plan_grid, SCAN_T, 0, st, db, d->cnt2, ++d->plan_epoch, d->plan_agg, d->plan_flag,
-                  d->plan_flag + 1, d->cseg_off, d->cseg_mid, d->plan_tot, seg_cap, item_cap, d->items));
+                  d->plan_flag + 1, d->cseg_off, d->cseg_mid, d->plan_tot, seg_cap, item_cap, d->items, PK ? 1 : 0));
     if (stages) CK(cudaEventRecord(d->stage_ev[2], st));
     CK(launch_pdl(k_cseg_scatter<V, MODE>, nb, thr, 0, st, db, p.n, p.ctg, p.qs, p.qe, d->cnt2, d->cseg_off,
                   d->cseg_mid, d->plan_tot, seg_cap, item_cap, (void *)d->csegs));
@@ -890,13 +919,20 @@ int enqueue_count_t(igdb_dev *d, const igdb_dev::Pending &p)
     CK(cudaMemcpyAsync((void *)d->h_plan, d->plan_tot, 32, cudaMemcpyDeviceToHost, d->side));
     CK(cudaEventRecord(d->plan_ev, d->side));
     CountArgs a{};
-    a.db = db, a.items = d->items, a.segs = d->csegs, a.tot = d->plan_tot;
+    a.db = db, a.items = d->items, a.desc = d->items2, a.segs = d->csegs, a.tot = d->plan_tot;
     a.seg_cap = seg_cap, a.item_cap = item_cap, a.v = p.v, a.hits = p.hits;
+    if (PK) {
+        // the windows of the items (descriptors of k_count_rank): one thread per item
+        CK(launch_pdl(k_item_windows, (unsigned)(d->sm_count * 8), 256, 0, st, db, (const int4 *)d->items,
+                      (const uint32_t *)(const void *)d->csegs, (const unsigned long long *)d->plan_tot, seg_cap, item_cap,
+                      d->items2));
+        d->launches += 1;
+    }
     if (stages) CK(cudaEventRecord(d->stage_ev[3], st));
     if (MODE != M_ABN32) CK(cudaEventRecord(d->kev[0], st));
     if (PK) {
-        if (smem) CK(launch_pdl(k_count_packed<V, true>, grid, threads, shm, st, a));
-        else CK(launch_pdl(k_count_packed<V, false>, grid, threads, shm, st, a));
+        if (smem) CK(launch_pdl(k_count_rank<V, true>, grid, threads, shm, st, a));
+        else CK(launch_pdl(k_count_rank<V, false>, grid, threads, shm, st, a));
     } else {
         if (smem) k_count_items<V, true><<<grid, threads, shm, st>>>(a);
         else k_count_items<V, false><<<grid, threads, shm, st>>>(a);
@@ -944,7 +980,7 @@ int settle_count(igdb_dev *d, const igdb_dev::Pending &p)
             nitems <= (unsigned long long)std::min<int64_t>(d->item_cap - CAP_SLACK, lim)) {
             if (p.mode != M_ABN32) {
                 // what the search kernel of this batch reads: descriptors, records, segments
-                const int64_t rb = pk ? (p.mode_v ? 8 : 6) : (p.mode_v ? 16 : 12), sgb = pk ? 4 : 8;
+                const int64_t rb = pk ? (p.mode_v ? 6 : 4) : (p.mode_v ? 16 : 12), sgb = pk ? 4 : 8;
                 d->last_plan[0] = (int64_t)nsegs, d->last_plan[1] = (int64_t)nitems, d->last_plan[2] = (int64_t)nrec;
                 d->last_plan[3] = 16 * (int64_t)nitems + rb * (int64_t)nrec + sgb * (int64_t)nsegs;
             }

@@ -37,75 +37,137 @@ __global__ void k_transpose(const int32_t *__restrict__ aos, int64_t rec0, int64
     idx[dst] = r.x, start[dst] = r.y, end[dst] = r.z, value[dst] = r.w;
 }
 
-// The count-mode copy of every tile (ps / pe / pf / pv: 16-bit, relative to the tile's bin, pre-biased -- see
-// pk_rel), written from the SoA arrays once they are complete.  One warp per tile.  A sparse tile keeps the file's
-// start order.  A DENSE tile (>= PK_SPLIT_N records) is written as two runs, each in start order: the records no
-// longer than a threshold first, the longer ones after them.  The search kernel prunes a tile's queries against
-// the window [smallest start, largest end] of each group of 256 records, and with a long-tailed length
-// distribution the largest end of 256 consecutive records is set by one or two outliers; kept apart, the short
-// records' groups get tight windows (cfg3: 38 % of a tile's segments survive a group's window in start order,
-// 25 % like this) and the few long ones share a couple of wide groups.  The threshold is the tile's own: the
-// smallest power of two that at least 90 % of its records do not exceed (2048 bp for lognormal(6, 1) lengths).
-// The kernel does not depend on the order of the records inside a tile.  tiles[].ts still holds the bin boundary
-// here (k_tile_meta runs afterwards).
-constexpr int PK_SPLIT_N = 2048;
+// The count-mode copy of every tile (rb / rv: 16-bit, relative to the tile's bin -- see pk_rel), written from the
+// SoA arrays once they are complete.  Every record becomes a START entry and an END entry (igd_dev_impl.cuh).
+// Entry e of a tile lies in group e / 256; a group of nvp entries (256, or what is left of the tile rounded up to 8)
+// is one block of 4 nvp bytes: nvp keys, then nvp file indices.
+__device__ __forceinline__ int64_t rb_key_index(int64_t base16, int32_t n, int32_t e, int32_t *nvp)
+{
+    const int32_t g = e >> 8, n8 = (n + 7) & ~7;
+    *nvp = min(n8 - (g << 8), GROUP);
+    return base16 + (int64_t)g * (2 * GROUP) + (e & (GROUP - 1));
+}
 
-__global__ void __launch_bounds__(256) k_pack_tiles(const TileMeta *__restrict__ tiles, int32_t T,
-                                                     const int32_t *__restrict__ start, const int32_t *__restrict__ end,
-                                                     const int32_t *__restrict__ idx, const int32_t *__restrict__ value,
-                                                     int32_t nbp, int32_t split_n, uint16_t *__restrict__ ps,
-                                                     uint16_t *__restrict__ pe, uint16_t *__restrict__ pf,
-                                                     uint16_t *__restrict__ pv)
+// START half: the tile in the file's order, which is start order (src/igd_base.c:426-458 sorts every tile by start
+// before it is written; a clamped start is monotone in the start).  One warp per tile; pads included (key 0x8000,
+// file = nfiles: the trash slot of the histogram).  tiles[].ts still holds the bin boundary here (k_tile_meta runs
+// afterwards).
+__global__ void __launch_bounds__(256) k_pack_start(const TileMeta *__restrict__ tiles, int32_t T,
+                                                     const int32_t *__restrict__ start, const int32_t *__restrict__ idx,
+                                                     const int32_t *__restrict__ value, int32_t nbp, int32_t nfiles,
+                                                     uint16_t *__restrict__ rb, uint16_t *__restrict__ rv)
 {
     const int32_t t = (int32_t)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     if (t >= T) return;
     const TileMeta m = tiles[t];
     const int64_t base = (int64_t)m.off8 * 8;
-    const int32_t n = m.n, bd = m.ts;
-    const bool split = n >= split_n;
-    __shared__ uint32_t hist_s[8][32];
-    uint32_t thr = 0xffffffffu;
-    auto len_of = [&](int32_t i) { return (uint32_t)end[base + i] - (uint32_t)start[base + i]; };
-    int32_t nshort = n;
-    if (split) {
-        // lengths by power of two: bucket b counts the records with 2^(b-1) < len <= 2^b
-        uint32_t *h = hist_s[threadIdx.x >> 5];
-        h[lane] = 0;
-        __syncwarp();
-        for (int32_t i = lane; i < n; i += 32) {
-            const uint32_t len = len_of(i);
-            atomicAdd(&h[len <= 1 ? 0 : min(31, 32 - __clz(len - 1))], 1u);
-        }
-        __syncwarp();
-        uint32_t inc = h[lane];
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t o = __shfl_up_sync(FULL, inc, d);
-            if (lane >= d) inc += o;
-        }
-        const unsigned enough = __ballot_sync(FULL, (unsigned long long)inc * 10 >= (unsigned long long)n * 9);
-        const int b = __ffs(enough) - 1;                        // lane 31 holds all of them: never empty
-        thr = b >= 31 ? 0xffffffffu : 1u << b;
-        nshort = (int32_t)__shfl_sync(FULL, inc, b);
+    const int32_t n = m.n, bd = m.ts, n8 = (n + 7) & ~7;
+    for (int32_t i = lane; i < n8; i += 32) {
+        int32_t nvp;
+        const int64_t k = rb_key_index(base * 2, n, i, &nvp);
+        const bool real = i < n;
+        rb[k] = real ? (uint16_t)(pk_rel(start[base + i], bd, nbp) + 1) : (uint16_t)0x8000;
+        rb[k + nvp] = real ? (uint16_t)idx[base + i] : (uint16_t)nfiles;
+        rv[base + i] = real ? (uint16_t)(min(max(value[base + i], 0), 32767) + 0x8000) : (uint16_t)0x8000;
     }
-    auto is_short = [&](int32_t i) { return len_of(i) <= thr; };
-    const uint32_t lt = (1u << lane) - 1u;
-    int32_t cs = 0, cl = nshort;
-    for (int32_t i0 = 0; i0 < n; i0 += 32) {
-        const int32_t i = i0 + lane;
-        const bool valid = i < n;
-        const bool sh = valid && (!split || is_short(i));
-        const unsigned bs = __ballot_sync(FULL, sh), bl = __ballot_sync(FULL, valid && !sh);
-        if (valid) {
-            const int64_t dst = base + (sh ? cs + __popc(bs & lt) : cl + __popc(bl & lt));
-            const int32_t s = start[base + i], e = end[base + i];
-            ps[dst] = (uint16_t)(pk_rel(s, bd, nbp) + 1);
-            pe[dst] = (uint16_t)(pk_rel_end(e, bd, nbp) + 0x8000);
-            pf[dst] = (uint16_t)idx[base + i];
-            pv[dst] = (uint16_t)(min(max(value[base + i], 0), 32767) + 0x8000);
+}
+
+// END half: the tile's records ordered by their clamped end -- a counting sort over the nbp + 2 possible keys in
+// shared memory, one CTA per tile at a time (any tile size; the order among equal ends is irrelevant, count mode
+// adds them up).  eo = first entry of the END half.  Pads: key 0x7fff, file = nfiles.
+__global__ void __launch_bounds__(SCAN_T) k_pack_end(const TileMeta *__restrict__ tiles, int32_t T,
+                                                      const int32_t *__restrict__ end, const int32_t *__restrict__ idx,
+                                                      const int32_t *__restrict__ value, int32_t nbp, int32_t nfiles,
+                                                      int64_t eo, uint16_t *__restrict__ rb, uint16_t *__restrict__ rv)
+{
+    extern __shared__ uint32_t bucket[];                        // [nbp + 2]
+    const int32_t nb = nbp + 2, per = (nb + SCAN_T - 1) / SCAN_T;
+    for (int32_t t = blockIdx.x; t < T; t += gridDim.x) {
+        const TileMeta m = tiles[t];
+        const int32_t n = m.n, bd = m.ts, n8 = (n + 7) & ~7;
+        if (n <= 0) continue;
+        const int64_t base = (int64_t)m.off8 * 8;
+        for (int32_t k = threadIdx.x; k < nb; k += SCAN_T) bucket[k] = 0;
+        __syncthreads();
+        for (int32_t i = threadIdx.x; i < n; i += SCAN_T) atomicAdd(&bucket[pk_rel_end(end[base + i], bd, nbp)], 1u);
+        __syncthreads();
+        // exclusive scan of the buckets: every thread owns `per` consecutive ones
+        const int32_t k0 = min((int32_t)threadIdx.x * per, nb), k1 = min(k0 + per, nb);
+        uint32_t sum = 0;
+        for (int32_t k = k0; k < k1; ++k) sum += bucket[k];
+        uint32_t tot, ex = block_exclusive<uint32_t>(sum, &tot);
+        for (int32_t k = k0; k < k1; ++k) {
+            const uint32_t c = bucket[k];
+            bucket[k] = ex;
+            ex += c;
         }
-        cs += __popc(bs), cl += __popc(bl);
+        __syncthreads();
+        for (int32_t i = threadIdx.x; i < n8; i += SCAN_T) {
+            const bool real = i < n;
+            const int32_t e = real ? pk_rel_end(end[base + i], bd, nbp) : 0x7fff;
+            const int32_t pos = real ? (int32_t)atomicAdd(&bucket[e], 1u) : i;
+            int32_t nvp;
+            const int64_t k = rb_key_index((eo + base) * 2, n, pos, &nvp);
+            rb[k] = (uint16_t)e;
+            rb[k + nvp] = real ? (uint16_t)idx[base + i] : (uint16_t)nfiles;
+            rv[eo + base + pos] = real ? (uint16_t)(min(max(value[base + i], 0), 32767) + 0x8000) : (uint16_t)0x8000;
+        }
+        __syncthreads();
+    }
+}
+
+// Inside every group of 256 entries (both halves), order the real entries by (file mod 32) -- the bank of hist[file]
+// in shared memory -- and record the group's key range.  k_count_rank gives lane l entries 8 l .. 8 l + 7 and issues
+// one shared-memory atomic per k for the 32 entries {8 l + k}: 32 positions 8 apart in bank order, i.e. about one
+// per bank (measured on B200: 3.6 -> ~2 wavefronts per ATOMS).  One warp per tile.
+__global__ void __launch_bounds__(256) k_group_banksort(const TileMeta *__restrict__ tiles, int32_t T, int64_t eo,
+                                                         const uint32_t *__restrict__ gbase, uint32_t ngroups,
+                                                         uint16_t *__restrict__ rb, uint16_t *__restrict__ rv,
+                                                         uint32_t *__restrict__ gk)
+{
+    __shared__ uint16_t sk[8][GROUP], sf[8][GROUP], sv[8][GROUP];
+    __shared__ uint32_t cnt[8][32];
+    const int32_t t = (int32_t)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (t >= T) return;
+    const TileMeta m = tiles[t];
+    const int32_t n = m.n, n8 = (n + 7) & ~7;
+    if (n <= 0) return;
+    for (int half = 0; half < 2; ++half) {
+        const int64_t base = (int64_t)m.off8 * 8 + (half ? eo : 0);
+        for (int32_t g = 0; g * GROUP < n; ++g) {
+            const int32_t nvp = min(n8 - g * GROUP, GROUP), nv = min(n - g * GROUP, GROUP);
+            uint16_t *kb = rb + base * 2 + (int64_t)g * (2 * GROUP), *fb = kb + nvp, *vb = rv + base + (int64_t)g * GROUP;
+            cnt[w][lane] = 0;
+            __syncwarp();
+            uint32_t kmin = 0xffffu, kmax = 0;
+            for (int32_t i = lane; i < nv; i += 32) {
+                const uint32_t k = kb[i];
+                kmin = min(kmin, k), kmax = max(kmax, k);
+                atomicAdd(&cnt[w][fb[i] & 31], 1u);
+            }
+            kmin = __reduce_min_sync(FULL, kmin), kmax = __reduce_max_sync(FULL, kmax);
+            __syncwarp();
+            uint32_t c = cnt[w][lane], inc = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(FULL, inc, d);
+                if (lane >= d) inc += o;
+            }
+            __syncwarp();
+            cnt[w][lane] = inc - c;                             // first position of bank `lane`
+            __syncwarp();
+            for (int32_t i = lane; i < nv; i += 32) {
+                const uint16_t f = fb[i];
+                const uint32_t pos = atomicAdd(&cnt[w][f & 31], 1u);
+                sk[w][pos] = kb[i], sf[w][pos] = f, sv[w][pos] = vb[i];
+            }
+            __syncwarp();
+            for (int32_t i = lane; i < nv; i += 32) kb[i] = sk[w][i], fb[i] = sf[w][i], vb[i] = sv[w][i];
+            if (lane == 0) gk[gbase[t] + (uint32_t)g + (half ? ngroups : 0u)] = kmin | kmax << 16;
+            __syncwarp();
+        }
     }
 }
 
@@ -187,7 +249,7 @@ void igdb_dev_destroy(igdb_dev *d)
     void *ptrs[] = {d->tiles, d->d_toff, d->start, d->end, d->idx, d->value, d->tbase, d->q_ctg,
                     d->q_qs, d->q_qe, d->tile_cnt, d->tile_off, d->nseg, d->qseg_off, d->bsum, d->segs,
                     d->seg_hits, d->seg_out_off, d->d_hits, d->cnt2, d->cseg_off, d->cseg_mid,
-                    d->plan_agg, d->plan_flag, d->plan_tot, d->csegs, d->items, d->ps, d->pe, d->pf, d->pv,
+                    d->plan_agg, d->plan_flag, d->plan_tot, d->csegs, d->items, d->items2, d->rb, d->rv, d->gbase, d->gk,
                     d->ctg_names, d->ctg_slots, d->d_text, d->d_starts};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -234,6 +296,7 @@ static int create_impl(igdb_dev *d, const int32_t *ntile, const int32_t *ncnt)
     for (int c = 0; c < d->nctg; ++c) tbase[c + 1] = tbase[c] + ntile[c];
     d->T = tbase[d->nctg];
     std::vector<TileMeta> meta((size_t)d->T);
+    std::vector<uint32_t> gbase((size_t)d->T + 1, 0);
     d->toff.assign((size_t)d->T + 1, 0);
     int64_t p8 = 0;
     for (int c = 0, t = 0; c < d->nctg; ++c)
@@ -245,10 +308,11 @@ static int create_impl(igdb_dev *d, const int32_t *ntile, const int32_t *ncnt)
             meta[t].ts = d->nbp * j;            // bin boundary; k_tile_meta turns it into tS
             meta[t].s0 = 0x7fffffff;
             d->toff[t + 1] = d->toff[t] + n;
+            gbase[t] = (uint32_t)d->db_groups;
             d->db_groups += (n + GROUP - 1) / GROUP;
             p8 += (n + 7) / 8;
         }
-    if (p8 >= (int64_t)0xffffffff) {
+    if (p8 >= (int64_t)0x7ffffff0) {             // the END half of the count-mode copy starts at p8 + 1
         snprintf(g_err, sizeof g_err, "database too large for 32-bit tile offsets");
         return -1;
     }
@@ -265,10 +329,16 @@ static int create_impl(igdb_dev *d, const int32_t *ntile, const int32_t *ncnt)
         dev_alloc(d, &d->plan_tot, 8))
         return -1;
     // packed count-mode copies: tile-relative coordinates need nbp + 1 < 2^15, file indices 16 bits
-    d->packed = d->nbp <= 16384 && d->nfiles <= 65536 && !getenv("IGD_B200_NO_PACKED");
-    if (d->packed && (dev_alloc(d, &d->ps, (size_t)d->P + 8) || dev_alloc(d, &d->pe, (size_t)d->P + 8) ||
-                      dev_alloc(d, &d->pf, (size_t)d->P + 8) || dev_alloc(d, &d->pv, (size_t)d->P + 8)))
+    d->packed = d->nbp <= 16384 && d->nfiles <= 65535 && !getenv("IGD_B200_NO_PACKED");
+    const size_t half = (size_t)d->P + 8;       // START half, END half (igd_dev_impl.cuh)
+    if (d->db_groups >= (int64_t)0x7fffffff) {
+        snprintf(g_err, sizeof g_err, "database too large for 32-bit group numbers");
         return -1;
+    }
+    if (d->packed && (dev_alloc(d, &d->rb, 4 * half) || dev_alloc(d, &d->rv, 2 * half) ||
+                      dev_alloc(d, &d->gbase, (size_t)d->T + 1) || dev_alloc(d, &d->gk, (size_t)2 * d->db_groups + 1)))
+        return -1;
+    if (d->packed) CK(cudaMemcpy(d->gbase, gbase.data(), gbase.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d->tiles, meta.data(), meta.size() * sizeof(TileMeta), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d->d_toff, d->toff.data(), d->toff.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d->tbase, tbase.data(), tbase.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
@@ -278,10 +348,9 @@ static int create_impl(igdb_dev *d, const int32_t *ntile, const int32_t *ncnt)
     k_fill<<<fb, 256>>>(d->end, (int64_t)d->P + 8, IMIN);
     k_fill<<<fb, 256>>>(d->value, (int64_t)d->P + 8, IMIN);
     if (d->packed) {
-        k_fill16<<<fb, 256>>>(d->ps, (int64_t)d->P + 8, (uint16_t)0x8000);
-        k_fill16<<<fb, 256>>>(d->pe, (int64_t)d->P + 8, (uint16_t)0x8000);
-        CK(cudaMemset(d->pf, 0, ((size_t)d->P + 8) * 2));
-        k_fill16<<<fb, 256>>>(d->pv, (int64_t)d->P + 8, (uint16_t)0x8000);
+        // (every entry of a tile, pads included, is written by k_pack_start / k_pack_end; this covers the slack)
+        k_fill16<<<fb, 256>>>(d->rb, (int64_t)(4 * half), (uint16_t)0x8000);
+        k_fill16<<<fb, 256>>>(d->rv, (int64_t)(2 * half), (uint16_t)0x8000);
     }
     CK(cudaGetLastError());
     CK(cudaMemset(d->idx, 0, ((size_t)d->P + 8) * 4));
@@ -387,11 +456,15 @@ int igdb_dev_finalize(igdb_dev *d)
     CK(cudaSetDevice(d->device));
     if (d->T > 0) {
         if (d->packed) {
-            const char *e = getenv("IGD_B200_PK_SPLIT");        // 0 keeps every tile in start order
-            const int32_t split_n = e && atoi(e) == 0 ? 0x7fffffff : PK_SPLIT_N;
-            k_pack_tiles<<<(unsigned)(((int64_t)d->T * 32 + 255) / 256), 256, 0, d->stream>>>(
-                d->tiles, d->T, d->start, d->end, d->idx, d->value, d->nbp, split_n, d->ps, d->pe, d->pf, d->pv);
-            d->launches += 1;
+            k_pack_start<<<(unsigned)(((int64_t)d->T * 32 + 255) / 256), 256, 0, d->stream>>>(
+                d->tiles, d->T, d->start, d->idx, d->value, d->nbp, d->nfiles, d->rb, d->rv);
+            const size_t shm = ((size_t)d->nbp + 2) * 4;
+            CK(cudaFuncSetAttribute(k_pack_end, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+            k_pack_end<<<(unsigned)std::min<int64_t>(d->T, (int64_t)d->sm_count * 16), SCAN_T, shm, d->stream>>>(
+                d->tiles, d->T, d->end, d->idx, d->value, d->nbp, d->nfiles, (int64_t)d->P + 8, d->rb, d->rv);
+            k_group_banksort<<<(unsigned)(((int64_t)d->T * 32 + 255) / 256), 256, 0, d->stream>>>(
+                d->tiles, d->T, (int64_t)d->P + 8, d->gbase, (uint32_t)d->db_groups, d->rb, d->rv, d->gk);
+            d->launches += 3;
         }
         k_tile_meta<<<(d->T + 255) / 256, 256, 0, d->stream>>>(d->tiles, d->T, d->start);
         d->launches += 1;

@@ -12,29 +12,36 @@
 //   start/end/idx/value[P]  SoA int32 copies of gdata_t's fields (src/igd_base.h:41-46), tile-major in
 //                       the file's order (each tile sorted by start).  Pad records: start=INT_MAX,
 //                       end=INT_MIN (overlap no query).
-//   ps/pe/pf[P]       uint16 copies for count mode (when nbp <= 16384 and nFiles <= 65536), 6 B per record
-//                       instead of 12: coordinates RELATIVE to the tile's bin boundary bd, clamped to the
-//                       bin -- x' = clamp(x - bd + 1, 0, nbp + 1), exact for every comparison a query that
-//                       visits this tile can make (see k_count_packed) -- and stored pre-biased,
-//                       ps = start' + 1, pe = end' + 0x8000, so that two records are compared with one
-//                       32-bit subtraction per predicate (bit 15 of each half is the answer).
-//                       pf = file index, pv = clamp(value, 0, 32767) + 0x8000 (exact for the -v thresholds
-//                       1 .. 32767; any other threshold runs on the int32 arrays).
-//                       Pads: ps = 0x8000 (starts after every query end), pe = 0x8000.
+//   rb[4(P+8)], rv[2(P+8)]  the count-mode copy, uint16 (when nbp <= 16384 and nFiles <= 65535): every record
+//                       appears TWICE, as a START entry and as an END entry, each {key, file} (+ value in rv):
+//                         START half: key = start' + 1, the tile in START order (the file's)
+//                         END half (from entry P+8 on): key = end', the tile sorted by END
+//                       with coordinates RELATIVE to the tile's bin boundary bd and clamped to the bin,
+//                       x' = clamp(x - bd + 1, 0, nbp + 1) -- exact for every comparison a query that visits the
+//                       tile can make.  The overlap count of a record against a tile's segments separates into a
+//                       function of its start alone minus a function of its end alone (see k_count_rank), so the
+//                       two halves are searched independently, each a merge of two sorted sequences.
+//                       A tile's entries are stored in GROUPS of 256 (the last one: what is left, rounded up to 8),
+//                       each one block of keys followed by its file indices -- one contiguous read per work item.
+//                       A group is a contiguous slice of the tile's sorted sequence, but INSIDE a group the entries
+//                       are ordered by (file mod 32), the shared-memory bank of their histogram counter: the k-th
+//                       entries of the 32 lanes then fall on (nearly) distinct banks (k_group_banksort; the
+//                       group's smallest and largest key are kept in gk[]).
+//                       rv = clamp(value, 0, 32767) + 0x8000 per entry (exact for the -v thresholds 1 .. 32767;
+//                       any other threshold runs on the int32 arrays).
+//                       Pads: START key 0x8000, END key 0x7fff (past every real key), file = nFiles (a trash slot).
 //   tbase[nctg+1]     global tile index of each contig's tile 0.
 //
 // Query batches are turned into (query, tile) SEGMENTS -- one per non-empty, non-gated tile the reference
 // would visit for that query, first-bin-empty quirk included -- counting-sorted by tile on the device, so
 // that the work is organised by tile whatever the order of the input.
 //
-// Count mode (-q, -v) is TILE-CENTRIC and RECORD-STATIONARY: a warp task ("item") is 128 consecutive
-// records of one tile against up to 256 of the tile's segments.  Every lane keeps 4 records in registers
-// (one 128-bit load each of start/end/idx[/value] -- the tile is read from HBM once however many queries
-// hit it), the segments are streamed through the warp 32 at a time, pruned against the warp's
-// [min start, max end] window with one ballot, and broadcast with shuffles; a lane adds the number of
-// segments overlapping each of its records and issues ONE shared-memory atomic per record with a non-zero
-// count (hits[idx] += count), not one per overlap.  -f keeps the query-centric warp-per-segment kernel
-// because it needs the reference's per-query output order.
+// Count mode (-q, -v) is TILE-CENTRIC and RECORD-STATIONARY: a warp task ("item") is up to 256 consecutive
+// entries of one tile against up to 64 of the tile's segments.  Every lane keeps 8 entries in registers (one
+// 128-bit load per array -- the tile is read from HBM once however many queries hit it) and adds, per entry, the
+// number of segments on the far side of its key; ONE shared-memory atomic per entry (hits[file] += count), not
+// one per overlap.  -f keeps the query-centric warp-per-segment kernel because it needs the reference's
+// per-query output order.
 #ifndef IGD_DEV_IMPL_CUH
 #define IGD_DEV_IMPL_CUH
 #include "igd_dev.h"
@@ -74,7 +81,10 @@ static_assert(sizeof(TileMeta) == 16, "TileMeta must be one int4");
 struct DbView {
     const TileMeta *tiles;
     const int32_t *start, *end, *idx, *value;
-    const uint16_t *ps, *pe, *pf, *pv;      // packed tile-relative copies for count mode (may be NULL)
+    const uint16_t *rb, *rv;                // count-mode copy: {keys, files} blocks and values; START half then END half (may be NULL)
+    uint32_t eoff8;                         // first entry of the END half, in units of 8 entries
+    const uint32_t *gbase, *gk;             // first group of each tile; per group smallest | largest << 16 real key (END half: + ngroups)
+    uint32_t ngroups;
     const int32_t *tbase;
     int32_t nctg, nbp, nfiles, ntiles;
 };
@@ -227,7 +237,7 @@ struct __align__(8) CSeg {       // count-mode segment: the query's interval, no
 
 // Which queries a count pipeline takes, and in which layout it searches:
 //   M_ALL32  every query, int32 records (k_count_items)           -- databases the packed layout cannot hold
-//   M_PACKED the queries with 0 <= qs < qe, packed 16-bit records (k_count_packed); the others are only counted
+//   M_PACKED the queries with 0 <= qs < qe, 16-bit START / END entries (k_count_rank); the others are only counted
 //            (cnt2[2T]) and, if there are any, a second pipeline in mode M_ABN32 takes exactly those
 //   M_ABN32  the queries with qs < 0 or qs >= qe (accepted by parse_bed, src/igd_base.c:69: only en > 0 is
 //            required), int32 records
@@ -274,7 +284,8 @@ struct igdb_dev {
     TileMeta *tiles = nullptr;
     int64_t *d_toff = nullptr;
     int32_t *start = nullptr, *end = nullptr, *idx = nullptr, *value = nullptr, *tbase = nullptr;
-    uint16_t *ps = nullptr, *pe = nullptr, *pf = nullptr, *pv = nullptr;   // packed count-mode copies (NULL: M_ALL32 only)
+    uint16_t *rb = nullptr, *rv = nullptr;  // count-mode copy, START half + END half (NULL: M_ALL32 only)
+    uint32_t *gbase = nullptr, *gk = nullptr;   // [T] first group of a tile, [2 db_groups] key range of each group
     char *ctg_names = nullptr;              // [nctg][40] contig names (device), for the text ingest
     int32_t *ctg_slots = nullptr;           // hash table over them
     uint32_t ctg_mask = 0;
@@ -327,6 +338,8 @@ struct igdb_dev {
     int64_t cseg_cap = 0;
     int4 *items = nullptr;
     int64_t item_cap = 0;
+    int4 *items2 = nullptr;                                 // k_count_rank's descriptors (2 x int4 per item), k_item_windows
+    int64_t item2_cap = 0;
     int64_t db_groups = 0;                                  // sum over tiles of ceil(n / GROUP)
     int count_grid[2][2] = {{0, 0}, {0, 0}};                // CTAs of the search kernel [packed][V] (0 = not set up)
     int64_t last_plan[4] = {0, 0, 0, 0};                    // segments, items, records, bytes of the last batch
@@ -343,7 +356,7 @@ struct igdb_dev {
     {
         DbView v;
         v.tiles = tiles, v.start = start, v.end = end, v.idx = idx, v.value = value, v.tbase = tbase;
-        v.ps = ps, v.pe = pe, v.pf = pf, v.pv = pv;
+        v.rb = rb, v.rv = rv, v.eoff8 = (uint32_t)((P + 8) / 8), v.gbase = gbase, v.gk = gk, v.ngroups = (uint32_t)db_groups;
         v.nctg = nctg, v.nbp = nbp, v.nfiles = nfiles, v.ntiles = T;
         return v;
     }

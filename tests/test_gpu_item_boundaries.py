@@ -1,4 +1,4 @@
-"""Work-item boundaries of the count kernels (an item = up to 256 records of one tile x up to 64 segments): tiles
+"""Work-item boundaries of the count kernels (an item = up to 256 entries of one tile x up to 64 segments): tiles
 of every size around 8 / 256 / 512 / 768 records, and tiles whose first 300 records all start before the bin (the
 later-bin dedupe rule decided in a tile's second item), with and without -v, against the oracle.
 
@@ -80,12 +80,9 @@ def test_item_boundaries(db, v):
 
 
 @pytest.mark.parametrize("v", [0, 500])
-def test_dense_tiles_long_records_kept_apart(workdir, v):
-    """thousands of records per tile with a long-tailed length distribution: the packed copy of such a tile holds
-    the records longer than 2 kb after the others (k_pack_tiles), so groups are no longer in start order; hits[]
-    must not notice -- also for queries spanning many bins (the later-bin rule) and with the split switched off"""
-    import subprocess
-    import sys
+def test_dense_tiles_long_tailed_lengths(workdir, v):
+    """thousands of records per tile with a long-tailed length distribution (the END half of the count-mode copy
+    is a tile sorted by end: k_pack_end), also for queries spanning many bins (the later-bin rule)"""
     from igd_b200 import api
     from oracle import oracle as O
     from tests.conftest import SMALL_NAMES, SMALL_SIZES
@@ -103,15 +100,6 @@ def test_dense_tiles_long_records_kept_apart(workdir, v):
     with api.IGD(stem + ".igd") as g:
         got, _ = g.count(ctg, qs, qe, v)
     assert np.array_equal(got, want)
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    np.savez(os.path.join(workdir, "dense_split_q.npz"), ctg=ctg, qs=qs, qe=qe)
-    code = ("import sys, numpy as np; sys.path.insert(0, %r); from igd_b200 import api; q = np.load(sys.argv[2]); "
-            "g = api.IGD(sys.argv[1]); print(' '.join(map(str, g.count(q['ctg'], q['qs'], q['qe'], int(sys.argv[3]))[0].tolist())))"
-            % root)
-    r = subprocess.run([sys.executable, "-c", code, stem + ".igd", os.path.join(workdir, "dense_split_q.npz"), str(v)],
-                       capture_output=True, text=True, env=dict(os.environ, IGD_B200_PK_SPLIT="0"))
-    assert r.returncode == 0, r.stderr[-1500:]
-    assert r.stdout.split() == [str(x) for x in want.tolist()]
 
 
 def test_item_boundary_tiles_full_hitsmap_seqpare(db, workdir):
