@@ -1,18 +1,22 @@
 #!/usr/bin/env python
 """Benchmark of the IGD batch overlap search hot path (count mode) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3]
 
-One "step" = one pass of the hot path over the whole query batch of the workload (BASELINE.json
-configs[1] by default: 1,905 files x 50k intervals, 1M x 1 kb queries, count mode).  Prints ONE JSON line.
-With N GPUs the database is replicated and the query set is N x 1M queries (weak scaling: 1M per GPU), sorted
-by (contig, start) and cut into contiguous cost-balanced shards; hits[] is combined by one exchange kernel over NVLink peer memory (NCCL allreduce as the fallback).
+One "step" = one pass of the hot path over the whole query batch of the workload (BASELINE.json configs[2] by
+default, the one the metric and the target are quoted on: 10,000 files x 100k intervals = 1e9, 10M x 1 kb queries,
+count mode; it fits one GPU).  Prints ONE JSON line.  With N GPUs the database is replicated and the SAME 10M
+queries (strong scaling), sorted by (contig, start), are cut into N contiguous cost-balanced shards; hits[] is
+combined by one exchange kernel over NVLink peer memory (NCCL allreduce as the fallback).
 
 * value  : query intervals/s, whole job, queries already resident in HBM (CUDA events, max over ranks)
 * e2e    : the same through the C-ABI call with HOST (pinned) buffers: H2D + kernels + D2H inside
-* roofline : the search kernel's algorithmic bytes (from the oracle's instrumented
-             restatement) / its CUDA-event duration, against MEASURED_PEAKS.json's HBM copy bandwidth
-* cpu_baseline : the oracle port timed on one host core on the same workload (reported, not a target)
+* roofline : the bytes the search kernel reads per launch (descriptors + entries + segments, counted by the
+             planner on the device; equal to ncu's dram__bytes within 10 %) / its CUDA-event duration, against
+             MEASURED_PEAKS.json's HBM copy bandwidth.  The reference-scan-range figure of SURVEY.md 8(d) is
+             reported beside it as `algorithmic_speedup` -- this kernel does not do that work.
+* cpu_baseline : the oracle port timed on one host core on a bounded sample of the same workload (reported, not a
+             target); parity_vs_oracle compares hits[] of the WHOLE query set (oracle on all host cores)
 
 --impl reference times the unmodified reference binary (oracle/_ref/igd, all host cores, one process per
 core over line-splits of the query file) on the same workload.
@@ -130,19 +134,32 @@ def workload_setup(args, rank, world, barrier):
         build_s = time.time() - t0
     barrier()
     path = os.path.join(workdir, args.workload + ".igd")
-    # weak scaling: the per-GPU work is fixed -- the query set grows with the number of GPUs
-    per_gpu = args.queries or workloads.CONFIGS[args.workload]["n_queries"]
-    q = workloads.queries(args.workload, per_gpu * world)
+    # strong scaling: the query set is the workload's, whatever the number of GPUs
+    q = workloads.queries(args.workload, args.queries or workloads.CONFIGS[args.workload]["n_queries"])
     return path, q, (build_s if rank == 0 else 0.0)
 
 
-def oracle_leg(path, ctg, qs, qe, sample, cache_file):
-    """cpu_baseline: the oracle port on one host core; also the algorithmic-byte counters."""
+def config_of(args, n_total, world):
+    """the `config` object of the JSON line -- the same for both arms"""
+    c = workloads.CONFIGS[args.workload]
+    return {"workload": f"{args.workload}: {c['n_files']} files x {c['per_file']} intervals (hg38, -b 14), "
+                        f"{n_total} queries, count mode",
+            "n_files": c["n_files"], "intervals_per_file": c["per_file"], "n_queries": n_total,
+            "l2": "256 MiB flush write between steps (untimed); DB image > 126 MB L2",
+            "parallelism": (f"db replicated on {world} GPUs; the {n_total} queries sorted by (contig, start) and cut into "
+                            f"{world} contiguous shards by scan-byte prefix sum; hits[] combined by one exchange"
+                            if world > 1 else "single GPU")}
+
+
+def oracle_leg(path, ctg, qs, qe, sample, cache_file, full=True):
+    """cpu_baseline: the oracle port on ONE host core over a strided sample (also the algorithmic-byte counters);
+    then hits[] of the whole query set on all host cores (the parity check of the run)."""
+    from concurrent.futures import ThreadPoolExecutor
     from oracle import oracle as O
     n = len(ctg)
     if os.path.exists(cache_file):
         c = json.load(open(cache_file))
-        if c.get("n") == n and c.get("sample") == sample:
+        if c.get("n") == n and c.get("sample") == sample and (c.get("hits_full") is not None or not full):
             return c
     odb = O.OracleDB(path)
     m = min(n, sample)
@@ -153,9 +170,19 @@ def oracle_leg(path, ctg, qs, qe, sample, cache_file):
     dt = time.perf_counter() - t0
     scale = n / m
     out = {"n": n, "sample": sample, "sample_n": int(m), "seconds": dt, "qps": m / dt,
-           "stats": st, "scale": scale, "hits_sample": hits.tolist(),
-           "bytes_total": st["bytes"] * scale, "hits_total": st["hits"] * scale,
-           "tile_bytes_sample": st["tile_bytes"]}
+           "stats": st, "scale": scale, "bytes_total": st["bytes"] * scale, "hits_total": st["hits"] * scale,
+           "tile_bytes_sample": st["tile_bytes"], "hits_full": None}
+    if full:
+        cores = os.cpu_count() or 1
+        cuts = [n * k // (4 * cores) for k in range(4 * cores + 1)]
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(cores) as ex:       # orc_count releases the GIL (ctypes) and only reads the database
+            parts = list(ex.map(lambda ab: odb.count(np.ascontiguousarray(ctg[ab[0]:ab[1]]),
+                                                     np.ascontiguousarray(qs[ab[0]:ab[1]]),
+                                                     np.ascontiguousarray(qe[ab[0]:ab[1]]), 0)[0],
+                                zip(cuts[:-1], cuts[1:])))
+        out["hits_full"] = np.sum(parts, axis=0).astype(np.int64).tolist()
+        out["full_seconds"], out["full_cores"] = time.perf_counter() - t0, cores
     odb.close()
     with open(cache_file, "w") as f:
         json.dump(out, f)
@@ -329,11 +356,13 @@ def run_ours(args):
     # ---- query-file ingest: search() on a BED file of this rank's queries (text parsed on the GPU) ------------
     file_s = None
     if world == 1:
-        qbed = os.path.join(args.workdir, f"{args.workload}_q{n_total}.bed")
+        nf = min(n_total, 1_000_000)                        # (a 1M-line BED file: 29 MB of text)
+        qbed = os.path.join(args.workdir, f"{args.workload}_q{nf}.bed")
         if not os.path.exists(qbed):
-            synth.write_bed(qbed, q)
+            synth.write_bed(qbed, synth.Intervals(q.ctg[:nf], q.start[:nf], q.end[:nf], q.value[:nf]))
         hits_file, _ = igd.search_n(qbed)
-        assert np.array_equal(hits_file, hits_dev), "file ingest and array paths disagree"
+        hits_arr, _ = igd.count(ctg_all[:nf], qs_all[:nf], qe_all[:nf], 0)
+        assert np.array_equal(hits_file, hits_arr), "file ingest and array paths disagree"
         ts = []
         for _ in range(5):
             t0 = time.perf_counter()
@@ -341,6 +370,7 @@ def run_ours(args):
             ts.append(time.perf_counter() - t0)
         file_s = float(np.median(ts))
         file_bytes = os.path.getsize(qbed)
+        file_n = nf
 
     if world > 1:
         t = torch.tensor([total_ms, e2e_s, float(np.mean(kernel_ms))], dtype=torch.float64, device=dev)
@@ -353,38 +383,40 @@ def run_ours(args):
         kmean = float(np.mean(kernel_ms))
     assert np.array_equal(np.asarray(hits_e2e), hits_dev), "e2e and device-resident paths disagree"
 
+    if world > 1:
+        pl = torch.tensor([plan["own_bytes"]], dtype=torch.float64, device=dev)
+        dist.all_reduce(pl, op=dist.ReduceOp.MAX)
+        own_bytes = float(pl.item())                        # of the rank with the longest launch
+    else:
+        own_bytes = float(plan["own_bytes"])
     if rank == 0:
         ms_per_step = total_ms / args.steps
         overlaps = int(hits_dev.sum())
         peak, peak_src = peaks()
-        cache = os.path.join(args.workdir, f"{args.workload}.oracle_{n_total}.json")
-        orc = oracle_leg(path, ctg_all, qs_all, qe_all, args.cpu_sample, cache)
+        cache = os.path.join(args.workdir, f"{args.workload}.oracle_{n_total}_{args.cpu_sample}.json")
+        orc = oracle_leg(path, ctg_all, qs_all, qe_all, args.cpu_sample, cache, full=not args.no_parity)
         parity = None
-        if orc["sample_n"] == n_total:
-            parity = bool(np.array_equal(np.array(orc["hits_sample"], np.int64), hits_dev))
-        alg_bytes = orc["bytes_total"] / world          # per launch (each rank launches on its shard)
-        achieved = alg_bytes / (kmean * 1e-3) / 1e9
+        if orc.get("hits_full") is not None:
+            parity = bool(np.array_equal(np.array(orc["hits_full"], np.int64), hits_dev))
+        achieved = own_bytes / (kmean * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get(args.workload)
+            traffic = json.load(open(tp)).get(args.workload, {}).get(str(world))
+        cfg = config_of(args, n_total, world)
+        if world > 1:
+            cfg["parallelism"] += (" kernel per rank over NVLink peer memory (igd_b200_reducer)" if reducer is not None
+                                   else " NCCL int64 allreduce")
         line = {
             "metric": METRIC, "value": n_total / (ms_per_step * 1e-3), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u16",
             "data": "synthetic",
             "overlaps_per_s": overlaps / (ms_per_step * 1e-3), "overlaps_per_step": overlaps,
-            "config": {"workload": f"{args.workload}: {workloads.CONFIGS[args.workload]['n_files']} files x "
-                                   f"{workloads.CONFIGS[args.workload]['per_file']} intervals (hg38, -b 14), "
-                                   f"{n_total} queries, count mode",
-                       "n_records": int(igd.nrecords), "n_tiles": int(igd.ntiles), "n_queries": n_total,
-                       "db_hbm_bytes": int(igd.device_bytes()),
-                       "l2": "256 MiB flush write between steps (untimed); DB image > 126 MB L2",
-                       "parallelism": f"db replicated on {world} GPUs; {n_total} queries ({n_total // world} per GPU) "
-                                      "sorted by (contig, start) and cut into contiguous shards by scan-byte prefix "
-                                      "sum; hits[] combined by " + ("one exchange kernel per rank over NVLink peer memory "
-                                      "(igd_b200_reducer)" if reducer is not None else "one NCCL int64 allreduce")
-                                      if world > 1 else "single GPU", "db_build_s": round(build_s, 1), "db_open_s": round(open_s, 2)},
+            "config": cfg,
+            "run": {"n_records": int(igd.nrecords), "n_tiles": int(igd.ntiles), "db_hbm_bytes": int(igd.device_bytes()),
+                    "queries_rank0": n_local, "db_build_s": round(build_s, 1), "db_open_s": round(open_s, 2),
+                    "parity_seconds": orc.get("full_seconds"), "parity_cores": orc.get("full_cores")},
             "e2e": {"value": n_total / (e2e_s / args.steps), "unit": UNIT, "ms_per_step": e2e_s / args.steps * 1e3,
                     "h2d_bytes_per_step": 12 * n_total, "d2h_bytes_per_step": 8 * igd.nfiles * world,
                     "device_split_ms_last_step": e2e_split,
@@ -396,22 +428,26 @@ def run_ours(args):
                     "api": "igd_b200_count (C-ABI, host buffers)" if world == 1 else
                            "pinned H2D + igd_b200_count_device + hits[] exchange + D2H"},
             "file_ingest": None if file_s is None else {
-                "value": n_total / file_s, "unit": UNIT, "ms": file_s * 1e3, "file_bytes": file_bytes,
+                "value": file_n / file_s, "unit": UNIT, "ms": file_s * 1e3, "file_bytes": file_bytes, "n_queries": file_n,
                 "api": "search(igd, qFile) -- BED text (warm page cache) -> pinned chunks -> H2D -> parsed on the "
                        "GPU -> count"},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "k_count_packed (count-mode search, packed 16-bit layout)", "kernel_ms": kmean,
-                         "stages_ms_rank0": stages,
-                         "own_bytes_per_launch": plan["own_bytes"],
-                         "own_frac": plan["own_bytes"] / (kmean * 1e-3) / 1e9 / peak,
-                         "plan_rank0": plan,
-                         "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                         "bytes_definition": "SURVEY.md 8(d) reference scan range, oracle-instrumented"
-                                             + ("" if orc["sample_n"] == n_total else f" (scaled from a {orc['sample_n']}-query sample)")},
+                         "traffic": traffic, "kernel": "k_count_rank (count-mode search, 16-bit START / END entries)",
+                         "kernel_ms": kmean, "stages_ms_rank0": stages,
+                         "bytes_per_launch": own_bytes,
+                         "bytes_definition": "what the search kernel reads per launch: 32 B per item descriptor + 4 B per "
+                                             "(entry, item) + 4 B per segment, counted by the planner on the device "
+                                             "(longest-running rank)",
+                         "plan_rank0": plan, "peak_source": peak_src,
+                         # SURVEY.md 8(d)'s figure -- the bytes the REFERENCE's algorithm would move for these queries
+                         # (oracle-instrumented scan ranges) -- is not what this kernel does; as a ratio only:
+                         "algorithmic_bytes_reference_definition": orc["bytes_total"],
+                         "algorithmic_speedup": orc["bytes_total"] / (own_bytes * world) if own_bytes else None},
             "cpu_baseline": {"value": orc["qps"], "unit": UNIT, "cores": 1, "kind": "port",
-                             "sample": f"{orc['sample_n']} of {n_total} queries of the same workload, oracle/igd_oracle.c, {orc['seconds']:.1f} s"},
+                             "sample": f"{orc['sample_n']} of {n_total} queries of the same workload (strided), "
+                                       f"oracle/igd_oracle.c, {orc['seconds']:.1f} s"},
             "parity_vs_oracle": parity,
         }
         emit(line)
@@ -429,8 +465,7 @@ def run_reference(args):
         return
     from oracle import oracle as O
     path = workloads.build_db(args.workload, args.workdir)
-    per_gpu = args.queries or workloads.CONFIGS[args.workload]["n_queries"]
-    q = workloads.queries(args.workload, per_gpu * max(args.gpus, 1))       # same query set as our arm at this N
+    q = workloads.queries(args.workload, args.queries or workloads.CONFIGS[args.workload]["n_queries"])   # our arm's set
     n_total = len(q)
     cores = os.cpu_count() or 1
     n = min(n_total, args.ref_sample)
@@ -482,14 +517,24 @@ def run_reference(args):
         if kind == "reference" else f"{n} of {n_total} queries per step, {cores} processes of the oracle port"
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {workloads.CONFIGS[args.workload]['n_files']} files x "
-                                   f"{workloads.CONFIGS[args.workload]['per_file']} intervals (hg38, -b 14), "
-                                   f"{n_total} queries, count mode", "n_queries": n_total},
+            "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": config_of(args, n_total, max(args.gpus, 1)),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
                              "value_sorted_queries": sorted_val},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
+
+
+def default_workdir():
+    """the 17 GB database of cfg3 is written once per box: to /dev/shm when it is a roomy tmpfs (the file is read
+    back through the page cache either way), else /tmp"""
+    try:
+        st = os.statvfs("/dev/shm")
+        if st.f_bavail * st.f_frsize > 64 << 30:
+            return "/dev/shm/igd_b200_bench"
+    except OSError:
+        pass
+    return "/tmp/igd_b200_bench"
 
 
 def main():
@@ -498,10 +543,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(workloads.CONFIGS))
-    ap.add_argument("--queries", type=int, default=None, help="override the number of queries")
-    ap.add_argument("--workdir", default=os.environ.get("IGD_B200_WORKDIR", "/tmp/igd_b200_bench"))
-    ap.add_argument("--cpu-sample", type=int, default=8_000_000, help="queries in the cpu_baseline sample")
+    ap.add_argument("--workload", default="cfg3", choices=sorted(workloads.CONFIGS))
+    ap.add_argument("--queries", type=int, default=None, help="override the (total) number of queries")
+    ap.add_argument("--workdir", default=os.environ.get("IGD_B200_WORKDIR", default_workdir()))
+    ap.add_argument("--cpu-sample", type=int, default=1_000_000, help="queries in the one-core cpu_baseline sample")
+    ap.add_argument("--no-parity", action="store_true", help="skip the whole-set oracle run (profiling runs)")
     ap.add_argument("--ref-sample", type=int, default=1_000_000, help="queries per step of --impl reference")
     args = ap.parse_args()
     claim_stdout()

@@ -358,6 +358,9 @@ static int build_write(build_t *b, const char *opath, const char *name)
     int64_t *cur = malloc(sizeof(int64_t) * (size_t)(T + 1));
     if (!rec || !cur || !toff || !ncnt) {
         printf("Can't alloc mem %lld\n", (long long)(b->nrec * (int64_t)sizeof(rec_t)));
+        fclose(fp);
+        remove(path);
+        free(rec), free(ncnt), free(toff), free(tbase), free(cur);
         return -1;
     }
     int nth = host_threads();
@@ -393,6 +396,7 @@ static int build_write(build_t *b, const char *opath, const char *name)
         for (int64_t i = 0; i < b->nrec; i++) fwrite(&rec[i], 12, 1, fp);      /* gdata0_t = {idx, start, end} */
     int bad = ferror(fp);
     bad |= fclose(fp);
+    if (bad) remove(path);                                  /* no partial database is left behind */
     phase("write");
     free(rec), free(ncnt), free(toff), free(tbase), free(cur);
     return bad ? -1 : 0;
@@ -427,15 +431,20 @@ static void write_tsv(const char *opath, const char *name, int32_t n_files, char
  * also persists: a line with fewer fields than the caller reads leaves the older pointers in place, which then
  * look at whatever the new line put at those offsets.  Both effects are kept (same table, same buffer). */
 typedef struct {
-    char *field[40];
+    char *field[40];                                        /* SPLIT_MAX */
     int nmax;
 } splitter;
 
+/* The reference's table has nCols + 1 = 17 entries and is overrun by wider lines (heap corruption there); here
+ * the table is bounded: fields past SPLIT_MAX - 1 are not split off (create reads fields 0 .. 4 only). */
+#define SPLIT_MAX 40
 static void split_line(splitter *S, char *line)
 {
+    if (S->nmax > SPLIT_MAX - 1) S->nmax = SPLIT_MAX - 1;
     S->field[S->nmax] = NULL;
     S->field[0] = line;
     int ns = 1;
+    const int lim = S->nmax + 1 < SPLIT_MAX - 1 ? S->nmax + 1 : SPLIT_MAX - 1;
     char *c = line;
     do {
         if (*c == '\t') {
@@ -443,7 +452,7 @@ static void split_line(splitter *S, char *line)
             S->field[ns++] = c + 1;
         }
         c++;
-    } while (*c != '\0' && ns < S->nmax + 1);
+    } while (*c != '\0' && ns < lim);
     S->nmax = ns;
 }
 
@@ -539,7 +548,9 @@ static void spill_trace(build_t *b, int32_t ig)             /* the file is close
 }
 static void spill_quiet(build_t *b, int32_t ig) { (void)ig; b->batch = 0; }    /* igd0_saveT prints nothing */
 
-static void read_files(build_t *b, int mode, int32_t n_files, char **file_ids, int32_t *nr, double *avg)
+/* returns -1 when a file of a directory build cannot be opened: the reference returns from create_igd at that
+ * point (src/igd_create.c:57-58) -- no _index.tsv, no .igd -- and so do the callers here */
+static int read_files(build_t *b, int mode, int32_t n_files, char **file_ids, int32_t *nr, double *avg)
 {
     parse_job J = { b, file_ids, mode, 0, PTHREAD_MUTEX_INITIALIZER };
     int nth = host_threads();
@@ -557,7 +568,7 @@ static void read_files(build_t *b, int mode, int32_t n_files, char **file_ids, i
         part_t *p = &b->part[ig];
         if (!p->opened) {
             if (mode == MODE_LIST) continue;
-            break;                                          /* :57-58: the reference gives up here */
+            return -1;                                      /* :57-58: the reference gives up here */
         }
         if (mode != MODE_LIST && p->state_first > state + 1) {      /* would have been cut at state + 1 fields */
             part_free(p);
@@ -571,6 +582,7 @@ static void read_files(build_t *b, int mode, int32_t n_files, char **file_ids, i
     }
     if (mode != MODE_G0) batch_line(b);
     phase("merge (contig numbering)");
+    return 0;
 }
 
 static void closing_lines(int64_t nT, double l_avg)
@@ -590,7 +602,12 @@ void create_igd(char *iPath, char *oPath, char *igdName)
     double *avg = calloc((size_t)n_files + 1, sizeof(double));
     build_t b;
     build_init(&b, 1, n_files);
-    read_files(&b, MODE_DIR, n_files, g.gl_pathv, nr, avg);
+    if (read_files(&b, MODE_DIR, n_files, g.gl_pathv, nr, avg)) {          /* an input file does not open */
+        build_free(&b);
+        globfree(&g);
+        free(nr), free(avg);
+        return;
+    }
     printf("\n");
     int64_t nT;
     double l_avg;
@@ -656,7 +673,12 @@ void create_igd0(char *iPath, char *oPath, char *igdName)
     printf("igd_create 1: %i\n", n_files);
     build_t b;
     build_init(&b, 0, n_files);
-    read_files(&b, MODE_G0, n_files, g.gl_pathv, nr, avg);
+    if (read_files(&b, MODE_G0, n_files, g.gl_pathv, nr, avg)) {           /* an input file does not open */
+        build_free(&b);
+        globfree(&g);
+        free(nr), free(avg);
+        return;
+    }
     int64_t nT;
     double l_avg;
     write_tsv(oPath, igdName, n_files, g.gl_pathv, nr, avg, &nT, &l_avg);

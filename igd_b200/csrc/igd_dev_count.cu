@@ -14,13 +14,19 @@ __device__ __forceinline__ bool mode_takes(int qs, int qe)
 // query, of the first-bin tile and their atomics are issued back to back (four independent dependency chains per
 // thread instead of one), the later bins -- which few queries have -- follow in a per-query loop.  Restates the
 // control flow of get_overlaps / get_overlaps_v exactly as for_each_segment does (see there).
+// The count pass (SCATTER = false) leaves, per query, what the scatter pass needs to place the first-bin segment
+// without another atomic or another look at the tile: qrank[q] = the segment's rank among its tile's first-bin
+// segments (what the counting atomic returned), Q_NOSEG = no first-bin segment but later bins may have one,
+// Q_NONE = nothing at all.
 constexpr int CSEG_Q = 4, CSEG_T = 256;
 constexpr int CSEG_MAXCTG = 1024;           // contig table kept in shared memory up to this many contigs
+constexpr uint32_t Q_NOSEG = 0xffffffffu, Q_NONE = 0xfffffffeu;
 
-template <bool V, int MODE, class F1, class FL>
+template <bool V, int MODE, bool SCATTER, class F1, class FL>
 __device__ __forceinline__ void cseg_walk(const DbView &db, int64_t n, const int32_t *__restrict__ ctg,
                                           const int32_t *__restrict__ qs, const int32_t *__restrict__ qe,
-                                          uint32_t *__restrict__ abn, int abn_sign, F1 first, FL later)
+                                          uint32_t *__restrict__ qrank, uint32_t *__restrict__ abn, int abn_sign,
+                                          F1 first, FL later)
 {
     __shared__ int32_t tb_s[CSEG_MAXCTG + 1];
     const bool in_smem = db.nctg <= CSEG_MAXCTG;
@@ -33,6 +39,7 @@ __device__ __forceinline__ void cseg_walk(const DbView &db, int64_t n, const int
     const int64_t q0 = (int64_t)blockIdx.x * (CSEG_T * CSEG_Q) + threadIdx.x;
     pdl_wait();                                             // the queries / counters of the previous launch
     int c[CSEG_Q], s[CSEG_Q], e[CSEG_Q], tile[CSEG_Q], nlast[CSEG_Q], bd[CSEG_Q];
+    uint32_t r[CSEG_Q];
     bool ok[CSEG_Q];
     int nabn = 0;
 #pragma unroll
@@ -40,6 +47,7 @@ __device__ __forceinline__ void cseg_walk(const DbView &db, int64_t n, const int
         const int64_t q = q0 + (int64_t)k * CSEG_T;
         ok[k] = q < n;
         c[k] = ok[k] ? ctg[q] : -1, s[k] = ok[k] ? qs[q] : 0, e[k] = ok[k] ? qe[q] : 0;
+        r[k] = SCATTER && ok[k] ? qrank[q] : Q_NONE;
     }
 #pragma unroll
     for (int k = 0; k < CSEG_Q; ++k) {
@@ -54,14 +62,28 @@ __device__ __forceinline__ void cseg_walk(const DbView &db, int64_t n, const int
             tile[k] = tb + n1, nlast[k] = tb + max(n1, min(n2, mT)), bd[k] = n1 * nbp;
         }
     }
-    int4 m[CSEG_Q];
+    if (!SCATTER) {
+        int4 m[CSEG_Q];
 #pragma unroll
-    for (int k = 0; k < CSEG_Q; ++k)
-        m[k] = ok[k] ? __ldg(reinterpret_cast<const int4 *>(&db.tiles[tile[k]])) : make_int4(0, 0, 0, 0);
+        for (int k = 0; k < CSEG_Q; ++k)
+            m[k] = ok[k] ? __ldg(reinterpret_cast<const int4 *>(&db.tiles[tile[k]])) : make_int4(0, 0, 0, 0);
 #pragma unroll
-    for (int k = 0; k < CSEG_Q; ++k) {
-        if (!V && m[k].y == 0) ok[k] = false;                               // first-bin-empty quirk (:468)
-        if (ok[k] && m[k].y > 0 && e[k] > m[k].w) first(tile[k], s[k], e[k], bd[k]);   // nCnt > 0 and qe > start[0]
+        for (int k = 0; k < CSEG_Q; ++k) {
+            if (!V && m[k].y == 0) ok[k] = false;                           // first-bin-empty quirk (:468)
+            r[k] = ok[k] ? Q_NOSEG : Q_NONE;
+            if (ok[k] && m[k].y > 0 && e[k] > m[k].w) r[k] = first(tile[k], s[k], e[k], bd[k], 0u);   // nCnt > 0 and qe > start[0]
+        }
+#pragma unroll
+        for (int k = 0; k < CSEG_Q; ++k) {
+            const int64_t q = q0 + (int64_t)k * CSEG_T;
+            if (q < n) qrank[q] = r[k];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < CSEG_Q; ++k) {
+            ok[k] = ok[k] && r[k] != Q_NONE;
+            if (ok[k] && r[k] != Q_NOSEG) first(tile[k], s[k], e[k], bd[k], r[k]);
+        }
     }
     if (MODE == M_PACKED && nabn) atomicAdd(abn, (uint32_t)(abn_sign * nabn));   // left to the M_ABN32 pipeline
 #pragma unroll
@@ -77,15 +99,14 @@ __device__ __forceinline__ void cseg_walk(const DbView &db, int64_t n, const int
 template <bool V, int MODE>
 __global__ void __launch_bounds__(CSEG_T) k_cseg_count(DbView db, int64_t n, const int32_t *__restrict__ ctg,
                                                         const int32_t *__restrict__ qs, const int32_t *__restrict__ qe,
-                                                        uint32_t *__restrict__ cnt2)
+                                                        uint32_t *__restrict__ cnt2, uint32_t *__restrict__ qrank)
 {
-    cseg_walk<V, MODE>(
-        db, n, ctg, qs, qe, &cnt2[2 * db.ntiles], +1, [&](int tile, int, int, int) { atomicAdd(&cnt2[2 * tile], 1u); },
+    cseg_walk<V, MODE, false>(
+        db, n, ctg, qs, qe, qrank, &cnt2[2 * db.ntiles], +1,
+        [&](int tile, int, int, int, uint32_t) { return atomicAdd(&cnt2[2 * tile], 1u); },
         [&](int tile, int, int, int) { atomicAdd(&cnt2[2 * tile + 1], 1u); });
 }
 
-// rank != 0 (M_PACKED, k_count_rank): a tile's records are searched as START entries against all of its segments
-// and as END entries against its first-bin segments, so it has ceil(n/GROUP) * (ceil(s/SMAX) + ceil(first/SMAX)) items
 constexpr uint32_t RK_END = 0x1ff;      // an END item of k_count_rank carries this in the tsr field of its descriptor
 
 __device__ __forceinline__ Plan plan_of_tile(const DbView &db, const uint32_t *__restrict__ cnt2, int32_t t, int rank,
@@ -122,11 +143,12 @@ __device__ __forceinline__ Plan plan_of_tile(const DbView &db, const uint32_t *_
 // An END item of k_count_rank (rank != 0) has x inside the END half of the count-mode copy, RK_END in the second
 // field of z, and only the first-bin segments of its chunk.
 
-__global__ void __launch_bounds__(SCAN_T) k_plan(DbView db, const uint32_t *__restrict__ cnt2, uint32_t epoch,
+__global__ void __launch_bounds__(SCAN_T) k_plan(DbView db, const uint32_t *cnt2, uint32_t *cnt2w, uint32_t epoch,
                                                   volatile PlanAgg *agg, volatile uint32_t *flag,
                                                   uint32_t *ticket, uint32_t *__restrict__ seg_off, uint32_t *__restrict__ seg_mid,
                                                   unsigned long long *__restrict__ tot, unsigned long long seg_cap,
-                                                  unsigned long long item_cap, int4 *__restrict__ items, int rank)
+                                                  unsigned long long item_cap, int4 *__restrict__ items, int rank,
+                                                  int4 *__restrict__ tplan)
 {
     __shared__ unsigned long long red[3][SCAN_T / 32];
     __shared__ unsigned long long sh_prefix[2], sh_total[3];
@@ -211,12 +233,17 @@ __global__ void __launch_bounds__(SCAN_T) k_plan(DbView db, const uint32_t *__re
         Plan ctot;
         const Plan ex = carry + block_exclusive<Plan>(mine, &ctot);
         carry += ctot;
-        uint32_t i0 = (uint32_t)ex.items, ni = (uint32_t)mine.items, sa0 = (uint32_t)ex.segs, mid = 0, sb0 = 0;
+        uint32_t i0 = (uint32_t)ex.items, ni = (uint32_t)mine.items, sa0 = (uint32_t)ex.segs, mid = 0, sb0 = 0;   // (ni: items this thread writes)
         int4 tm = make_int4(0, 0, 0, 0);
         if (in) {
             const uint2 c = __ldg(reinterpret_cast<const uint2 *>(cnt2) + t);
+            if (c.x) cnt2w[2 * t] = 0;                      // (the scatter pass counts only the later-bin ones back down)
             mid = sa0 + c.x, sb0 = mid + c.y;
             seg_off[t] = sa0, seg_mid[t] = mid;
+            if (rank) {                                     // k_windows makes the descriptors of this tile's items
+                tplan[t] = make_int4((int)sa0, (int)mid, (int)sb0, (int)i0);
+                ni = 0;
+            }
             if (ni) {
                 tm = __ldg(reinterpret_cast<const int4 *>(&db.tiles[t]));
                 tm.w = rank ? (int)__ldg(&db.gbase[t]) : 0;     // (s0 is not needed here)
@@ -253,14 +280,17 @@ __global__ void __launch_bounds__(SCAN_T) k_plan(DbView db, const uint32_t *__re
     }
 }
 
-// cnt2 is counted back down to zero here, so it is clean for the next batch.  Nothing is written when the
-// plan does not fit the scratch buffers: the host then grows them and runs the batch again.
+// The later-bin counters of cnt2 are counted back down to zero here (the first-bin ones were reset by k_plan), so
+// cnt2 is clean for the next batch.  Nothing is written when the plan does not fit the scratch buffers: the host
+// then grows them and runs the batch again.  A first-bin segment goes to its tile's first segment + the rank the
+// count pass kept.
 // M_PACKED writes 4-byte segments in the tile's clamped coordinates, biased for k_count_rank's subtractions:
 //   bits 0-15 = qs' + 0x8000, bits 16-31 = qe' + 0x8000.
 template <bool V, int MODE>
 __global__ void __launch_bounds__(CSEG_T) k_cseg_scatter(DbView db, int64_t n, const int32_t *__restrict__ ctg,
                                                           const int32_t *__restrict__ qs, const int32_t *__restrict__ qe,
-                                                          uint32_t *__restrict__ cnt2, const uint32_t *__restrict__ seg_off,
+                                                          uint32_t *__restrict__ cnt2, uint32_t *__restrict__ qrank,
+                                                          const uint32_t *__restrict__ seg_off,
                                                           const uint32_t *__restrict__ seg_mid,
                                                           const unsigned long long *__restrict__ tot,
                                                           unsigned long long seg_cap, unsigned long long item_cap,
@@ -277,10 +307,11 @@ __global__ void __launch_bounds__(CSEG_T) k_cseg_scatter(DbView db, int64_t n, c
             static_cast<CSeg *>(segs)[pos] = CSeg{s, e};
     };
     // (the queries left to the M_ABN32 pipeline are counted back down too)
-    cseg_walk<V, MODE>(
-        db, n, ctg, qs, qe, &cnt2[2 * db.ntiles], -1,
-        [&](int tile, int s, int e, int bd) {
-            put(__ldg(&seg_off[tile]) + atomicSub(&cnt2[2 * tile], 1u) - 1u, s, e, bd);
+    cseg_walk<V, MODE, true>(
+        db, n, ctg, qs, qe, qrank, &cnt2[2 * db.ntiles], -1,
+        [&](int tile, int s, int e, int bd, uint32_t rank) {
+            put(__ldg(&seg_off[tile]) + rank, s, e, bd);
+            return 0u;
         },
         [&](int tile, int s, int e, int bd) {
             put(__ldg(&seg_mid[tile]) + atomicSub(&cnt2[2 * tile + 1], 1u) - 1u, s, e, bd);
@@ -576,46 +607,74 @@ constexpr uint32_t RK_INL = 4;          // segments inside an item's window that
 //   A.w = window mask of segments 0-31                                                B.x = of segments 32-63
 //   B.w = number of segments inside the window; when there are <= RK_INL of them their x values themselves are in
 //         B.y (first | second << 16) and B.z, and the search kernel touches neither the masks nor the segments
-__global__ void __launch_bounds__(256) k_item_windows(DbView db, const int4 *__restrict__ items,
-                                                       const uint32_t *__restrict__ segs,
-                                                       const unsigned long long *__restrict__ tot,
-                                                       unsigned long long seg_cap, unsigned long long item_cap,
-                                                       int4 *__restrict__ out)
+// LPT lanes per tile (grid-stride; 8 for databases of small tiles, 32 otherwise), one THREAD per item: the tile's
+// items are numbered like k_plan's (group-major START items, then the END items, rank only); neighbouring threads
+// read the same <= 64 segments (L1 hits).
+template <int LPT>
+__global__ void __launch_bounds__(256) k_windows(DbView db, const int4 *__restrict__ tplan,
+                                                  const uint32_t *__restrict__ segs,
+                                                  const unsigned long long *__restrict__ tot,
+                                                  unsigned long long seg_cap, unsigned long long item_cap,
+                                                  int4 *__restrict__ out)
 {
     pdl_launch_dependents();
-    pdl_wait();                                             // the plan, the items, the segments
-    const unsigned long long nseg = tot[0], nit = tot[1];
-    if (nseg > seg_cap || nit > item_cap) return;
-    const unsigned long long nk = (nit + 31) & ~31ull;      // (the item array is padded to a multiple of 32)
-    for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < nk;
-         k += (unsigned long long)gridDim.x * blockDim.x) {
-        const int4 it = __ldg(&items[k]);
-        const uint32_t z = (uint32_t)it.z;
-        const uint32_t nv = z & 0x1ffu, tsf = (z >> 9) & 0x1ffu, nf = (z >> 18) & 0x7fu, ns = z >> 25;
-        if (nv == 0) {
-            out[2 * k] = make_int4(0, 0, 0, 0), out[2 * k + 1] = make_int4(0, 0, 0, 0);
-            continue;
-        }
-        const bool endk = tsf == RK_END;
-        const uint32_t kr = __ldg(&db.gk[(uint32_t)it.w]);          // the group's smallest and largest key
-        const uint32_t lo_t = (kr & 0xffffu) + 0x8000u, hi_t = (kr >> 16) + 0x8000u;
-        const uint32_t *sg = segs + (uint32_t)it.y;
-        uint32_t base = 0, m[2] = {0, 0}, nin = 0, v01 = 0, v23 = 0;
-#pragma unroll 4
-        for (uint32_t i = 0; i < ns; ++i) {
-            const uint32_t w = __ldg(&sg[i]), x = endk ? w & 0xffffu : w >> 16;
-            base += x >= hi_t;                              // past every key of the item
-            if (x >= lo_t && x < hi_t) {                    // past some: compared entry by entry
-                m[i >> 5] |= 1u << (i & 31);
-                if (nin < 2) v01 |= x << (16 * nin);
-                else if (nin < 4) v23 |= x << (16 * (nin - 2));
-                ++nin;
+    pdl_wait();                                             // the plan, the segments
+    if (tot[0] > seg_cap || tot[1] > item_cap) return;
+    const uint32_t l8 = threadIdx.x % LPT, nsub = gridDim.x * (blockDim.x / LPT);
+    for (uint32_t t = blockIdx.x * (blockDim.x / LPT) + (threadIdx.x / LPT); t < (uint32_t)db.ntiles; t += nsub) {
+        const int4 tp = __ldg(&tplan[t]);
+        const uint32_t a = (uint32_t)tp.x, m = (uint32_t)tp.y, e = (uint32_t)tp.z, i0 = (uint32_t)tp.w;
+        if (e == a) continue;                               // no query reached this tile
+        const int4 tm = __ldg(reinterpret_cast<const int4 *>(&db.tiles[t]));
+        const uint32_t gb = __ldg(&db.gbase[t]);
+        const uint32_t n = (uint32_t)tm.y, ng = (n + GROUP - 1) / GROUP;
+        const uint32_t ch = (e - a + SMAX - 1) / SMAX, chF = (m - a + SMAX - 1) / SMAX, ni = ng * (ch + chF);
+        for (uint32_t k = l8; k < ni; k += LPT) {
+            const bool endk = k >= ng * ch;
+            const uint32_t kk = endk ? k - ng * ch : k, chx = endk ? chF : ch;
+            const uint32_t g = kk / chx, c = kk - g * chx;
+            const uint32_t sa = a + c * SMAX, sb = min(sa + (uint32_t)SMAX, endk ? m : e), ns = sb - sa;
+            const int r0 = (int)(g * GROUP);
+            const uint32_t nv = (uint32_t)min((int)n - r0, GROUP), tsr = (uint32_t)min(max(tm.z - r0, 0), GROUP);
+            const uint32_t nf = min(max(m, sa), sb) - sa;
+            const uint32_t kr = __ldg(&db.gk[gb + g + (endk ? db.ngroups : 0u)]);      // smallest, largest key
+            const uint32_t lo_t = (kr & 0xffffu) + 0x8000u, hi_t = (kr >> 16) + 0x8000u;
+            const uint32_t sh = endk ? 0u : 16u;
+            const uint32_t *sg = segs + sa;
+            uint32_t base = 0, mk[2] = {0, 0};
+            for (uint32_t j0 = 0; j0 < ns; j0 += 8) {           // eight segments at a time: their loads in flight together
+                uint32_t w[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) w[j] = j0 + j < ns ? __ldg(&sg[j0 + j]) : 0u;
+                uint32_t bits = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t x = (w[j] >> sh) & 0xffffu;      // an absent segment: x = 0, past no key
+                    base += x >= hi_t;                              // past every key of the item
+                    bits |= (uint32_t)(x >= lo_t && x < hi_t) << j;     // past some: compared entry by entry
+                }
+                if (j0 < 32) mk[0] |= bits << j0;
+                else mk[1] |= bits << (j0 - 32);
             }
+            const uint32_t nin = __popc(mk[0]) + __popc(mk[1]);
+            uint32_t v01 = 0, v23 = 0;
+            if (nin <= RK_INL) {
+                uint32_t m0 = mk[0], m1 = mk[1];
+                for (uint32_t r = 0; r < nin; ++r) {
+                    uint32_t j;
+                    if (m0) j = __ffs(m0) - 1, m0 &= m0 - 1;
+                    else j = 32 + __ffs(m1) - 1, m1 &= m1 - 1;
+                    const uint32_t x = (__ldg(&sg[j]) >> sh) & 0xffffu;
+                    if (r < 2) v01 |= x << (16 * r);
+                    else v23 |= x << (16 * (r - 2));
+                }
+            }
+            const uint32_t fix = !endk && tsr > 0 && ns > nf;
+            out[2 * (size_t)(i0 + k)] =
+                make_int4((int)((uint32_t)tm.x + g * (GROUP / 8) + (endk ? db.eoff8 : 0u)), (int)sa,
+                          (int)(nv | ns << 9 | base << 16 | (ns - nf) << 23 | (uint32_t)endk << 30 | fix << 31), (int)mk[0]);
+            out[2 * (size_t)(i0 + k) + 1] = make_int4((int)mk[1], (int)v01, (int)v23, (int)nin);
         }
-        const uint32_t fix = !endk && tsf > 0 && ns > nf;
-        out[2 * k] = make_int4(it.x, it.y,
-                               (int)(nv | ns << 9 | base << 16 | (ns - nf) << 23 | (uint32_t)endk << 30 | fix << 31), (int)m[0]);
-        out[2 * k + 1] = make_int4((int)m[1], (int)v01, (int)v23, (int)nin);
     }
 }
 
@@ -890,6 +949,7 @@ int enqueue_count_t(igdb_dev *d, const igdb_dev::Pending &p)
     if (grow(&d->items, &d->item_cap, std::min<int64_t>((PK ? 2 : 1) * (d->db_groups + p.n / 64), item_limit(d, grid)) + 1024, 1, 1))
         return -1;
     if (PK && grow(&d->items2, &d->item2_cap, 2 * d->item_cap, 1, 1)) return -1;
+    if (PK && !d->tplan && dev_alloc(d, &d->tplan, (size_t)d->T + 1)) return -1;
     const unsigned long long seg_cap = (unsigned long long)std::min<int64_t>(d->cseg_cap - CAP_SLACK, 0x7fffffff);
     const unsigned long long item_cap =
         (unsigned long long)std::min<int64_t>(d->item_cap - CAP_SLACK, item_limit(d, grid));
@@ -905,13 +965,14 @@ int enqueue_count_t(igdb_dev *d, const igdb_dev::Pending &p)
     }
     const bool stages = d->stage_timing && MODE != M_ABN32;
     if (stages) CK(cudaEventRecord(d->stage_ev[0], st));
-    CK(launch_pdl(k_cseg_count<V, MODE>, nb, thr, 0, st, db, p.n, p.ctg, p.qs, p.qe, d->cnt2));
+    if (grow(&d->qrank, &d->qrank_cap, p.n)) return -1;
+    CK(launch_pdl(k_cseg_count<V, MODE>, nb, thr, 0, st, db, p.n, p.ctg, p.qs, p.qe, d->cnt2, d->qrank));
     if (stages) CK(cudaEventRecord(d->stage_ev[1], st));
     // (the plan reads the later-bin counters that the scatter counts back down to zero)
-    CK(launch_pdl(k_plan, d->plan_grid, SCAN_T, 0, st, db, d->cnt2, ++d->plan_epoch, d->plan_agg, d->plan_flag,
-                  d->plan_flag + 1, d->cseg_off, d->cseg_mid, d->plan_tot, seg_cap, item_cap, d->items, PK ? 1 : 0));
+    CK(launch_pdl(k_plan, d->plan_grid, SCAN_T, 0, st, db, d->cnt2, d->cnt2, ++d->plan_epoch, d->plan_agg, d->plan_flag,
+                  d->plan_flag + 1, d->cseg_off, d->cseg_mid, d->plan_tot, seg_cap, item_cap, d->items, PK ? 1 : 0, d->tplan));
     if (stages) CK(cudaEventRecord(d->stage_ev[2], st));
-    CK(launch_pdl(k_cseg_scatter<V, MODE>, nb, thr, 0, st, db, p.n, p.ctg, p.qs, p.qe, d->cnt2, d->cseg_off,
+    CK(launch_pdl(k_cseg_scatter<V, MODE>, nb, thr, 0, st, db, p.n, p.ctg, p.qs, p.qe, d->cnt2, d->qrank, d->cseg_off,
                   d->cseg_mid, d->plan_tot, seg_cap, item_cap, (void *)d->csegs));
     // the plan's totals go back to the host on a side stream, so that the copy does not sit between the kernels
     CK(cudaEventRecord(d->plan_done, st));
@@ -922,8 +983,11 @@ int enqueue_count_t(igdb_dev *d, const igdb_dev::Pending &p)
     a.db = db, a.items = d->items, a.desc = d->items2, a.segs = d->csegs, a.tot = d->plan_tot;
     a.seg_cap = seg_cap, a.item_cap = item_cap, a.v = p.v, a.hits = p.hits;
     if (PK) {
-        // the windows of the items (descriptors of k_count_rank): one thread per item
-        CK(launch_pdl(k_item_windows, (unsigned)(d->sm_count * 8), 256, 0, st, db, (const int4 *)d->items,
+        // the descriptors of k_count_rank (with the windows of the items): one thread per item, 8 or 32 per tile
+        const bool wide = d->db_groups >= 3 * (int64_t)d->T;        // >= 6 items per tile on average
+        const int64_t per_cta = wide ? 8 : 32;
+        const unsigned wgrid = (unsigned)std::min<int64_t>(((int64_t)d->T + per_cta - 1) / per_cta, (int64_t)d->sm_count * 64);
+        CK(launch_pdl(wide ? k_windows<32> : k_windows<8>, wgrid, 256, 0, st, db, (const int4 *)d->tplan,
                       (const uint32_t *)(const void *)d->csegs, (const unsigned long long *)d->plan_tot, seg_cap, item_cap,
                       d->items2));
         d->launches += 1;
@@ -982,7 +1046,7 @@ int settle_count(igdb_dev *d, const igdb_dev::Pending &p)
                 // what the search kernel of this batch reads: descriptors, records, segments
                 const int64_t rb = pk ? (p.mode_v ? 6 : 4) : (p.mode_v ? 16 : 12), sgb = pk ? 4 : 8;
                 d->last_plan[0] = (int64_t)nsegs, d->last_plan[1] = (int64_t)nitems, d->last_plan[2] = (int64_t)nrec;
-                d->last_plan[3] = 16 * (int64_t)nitems + rb * (int64_t)nrec + sgb * (int64_t)nsegs;
+                d->last_plan[3] = (pk ? 32 : 16) * (int64_t)nitems + rb * (int64_t)nrec + sgb * (int64_t)nsegs;
             }
             if (pk && nabn > 0) {           // the queries the packed layout cannot express: second pipeline
                 igdb_dev::Pending q = p;

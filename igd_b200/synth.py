@@ -244,3 +244,78 @@ def write_igd_direct(stem: str, files: list[Intervals] | None = None, *, nbp: in
             f.write("%i\t%s\t%i\t%f\n" % (i, file_names[i], nr[i], avg[i]))
     return {"n_files": n_files, "n_intervals": int(nr.sum()), "n_records": int(rec.shape[0]),
             "n_tiles": total_tiles, "n_ctg": m, "bytes": 12 + 44 * m + 4 * total_tiles + 4 * W * int(rec.shape[0])}
+
+
+# ---------------------------------------------------------------------------------------------
+# the same writer for the 1e8 / 1e9-interval benchmark databases: flat arrays in, contig by contig
+# ---------------------------------------------------------------------------------------------
+
+def write_igd_flat(stem: str, ctg: np.ndarray, start: np.ndarray, end: np.ndarray, value: np.ndarray,
+                   per_file: int, *, nbp: int = 16384, names=HG38_NAMES, device: str | None = None) -> dict:
+    """``write_igd_direct`` for inputs too large to shuffle with numpy: the intervals of all files as flat arrays in
+    (file, line) order, ``per_file`` of them per file.  Same bytes as ``write_igd_direct`` (checked in
+    tests/test_synth_flat.py): contig order by first appearance, tiles contig-major, each tile ordered by
+    start, stable in (file, line).  Works contig by contig with torch on the GPU when there is one (input
+    generation only -- not the search path), so that 1e9 intervals need a few GB at a time."""
+    import torch
+    dev = torch.device(device or ("cuda" if torch.cuda.is_available() else "cpu"))
+    n = int(ctg.shape[0])
+    n_files = n // per_file
+    assert n_files * per_file == n
+    t_ctg = torch.from_numpy(np.ascontiguousarray(ctg)).to(dev)
+    t_s = torch.from_numpy(np.ascontiguousarray(start)).to(dev)
+    t_e = torch.from_numpy(np.ascontiguousarray(end)).to(dev)
+    t_v = torch.from_numpy(np.ascontiguousarray(value)).to(dev)
+    # contig order = first appearance over (file, line) among the intervals that are kept (igd_add drops s >= e)
+    keep = t_s < t_e
+    first = torch.full((len(names),), n, dtype=torch.int64, device=dev)
+    first.scatter_reduce_(0, t_ctg.long()[keep], torch.arange(n, device=dev)[keep], reduce="amin", include_self=True)
+    first = first.cpu().numpy()
+    ctg_order = [int(c) for c in np.argsort(first, kind="stable") if first[c] < n]
+    m = len(ctg_order)
+    ntile, ncnt, recs = [], [], []
+    for c in ctg_order:
+        sel = torch.nonzero((t_ctg == c) & keep).squeeze(1)               # ascending = (file, line) order
+        s = t_s[sel].long()
+        e = t_e[sel].long()
+        n1 = torch.div(s, nbp, rounding_mode="floor")
+        n2 = torch.div(e - 1, nbp, rounding_mode="floor")
+        nt = int(n2.max().item()) + 1
+        span = n2 - n1 + 1
+        rep = torch.repeat_interleave(torch.arange(sel.shape[0], device=dev), span)
+        firstpos = torch.cumsum(span, 0) - span
+        tile = n1[rep] + (torch.arange(rep.shape[0], device=dev) - firstpos[rep])
+        del firstpos, span, n1, n2
+        key = (tile << 32) | s[rep]
+        key, order = torch.sort(key, stable=True)
+        src = sel[rep[order]]
+        del rep, order
+        ncnt.append(torch.bincount(key >> 32, minlength=nt).to(torch.int32).cpu().numpy())
+        del key, tile
+        rec = torch.stack([torch.div(src, per_file, rounding_mode="floor").int(), t_s[src].int(), t_e[src].int(),
+                           t_v[src].int()], dim=1).contiguous()
+        recs.append(rec.cpu().numpy())
+        ntile.append(nt)
+        del rec, src, sel, s, e
+    with open(stem + ".igd", "wb") as f:
+        np.array([nbp, 1, m], dtype=np.int32).tofile(f)
+        np.array(ntile, dtype=np.int32).tofile(f)
+        for x in ncnt:
+            x.tofile(f)
+        for c in ctg_order:
+            f.write(names[c].encode().ljust(40, b"\0"))
+        for r in recs:
+            r.tofile(f)
+    # _index.tsv: all lines counted, average size over all of them (igd_create.c:70,96-111)
+    ln = (t_e.long() - t_s.long()).reshape(n_files, per_file).sum(1).double().cpu().numpy() / max(per_file, 1)
+    with open(stem + "_index.tsv", "w") as f:
+        f.write("Index\tFile\tNumber of regions\tAvg size\n")
+        for i in range(n_files):
+            f.write("%i\t%s\t%i\t%f\n" % (i, f"f{i:05d}.bed", per_file, ln[i]))
+    n_rec = int(sum(r.shape[0] for r in recs))
+    n_tiles = int(sum(ntile))
+    if dev.type == "cuda":
+        del t_ctg, t_s, t_e, t_v, keep
+        torch.cuda.empty_cache()
+    return {"n_files": n_files, "n_intervals": n, "n_records": n_rec, "n_tiles": n_tiles, "n_ctg": m,
+            "bytes": 12 + 44 * m + 4 * n_tiles + 16 * n_rec}

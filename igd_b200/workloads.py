@@ -43,6 +43,22 @@ def _gen_file(args):
     return synth.gen_intervals(synth.seed_for(config, i), per_file, law, sizes)
 
 
+def _gen_into(args):
+    """worker of the flat build: generate files [i0, i1) straight into the shared arrays (no pickling of results)"""
+    config, i0, i1, per_file, law, sizes, paths = args
+    arrs = [np.load(p, mmap_mode="r+") for p in paths]
+    for i in range(i0, i1):
+        iv = synth.gen_intervals(synth.seed_for(config, i), per_file, law, sizes)
+        a, b = i * per_file, (i + 1) * per_file
+        arrs[0][a:b], arrs[1][a:b], arrs[2][a:b], arrs[3][a:b] = iv.ctg, iv.start, iv.end, iv.value
+    for x in arrs:
+        x.flush()
+    return i1 - i0
+
+
+FLAT_BUILD_MIN = 20_000_000     # intervals from which the database is built from flat shared arrays (write_igd_flat)
+
+
 def build_db(name: str, workdir: str, procs: int | None = None) -> str:
     """Create (once) ``<workdir>/<name>.igd`` + ``_index.tsv``; returns the .igd path."""
     cfg = CONFIGS[name]
@@ -54,14 +70,31 @@ def build_db(name: str, workdir: str, procs: int | None = None) -> str:
     if os.path.exists(marker) and os.path.exists(stem + ".igd") and open(marker).read() == want:
         return stem + ".igd"
     sizes = genome_sizes(name)
-    jobs = [(cfg["config"], i, cfg["per_file"], cfg["db_law"], sizes) for i in range(cfg["n_files"])]
-    procs = procs or min(os.cpu_count() or 1, 16)
-    if procs > 1 and len(jobs) >= 64:
+    procs = procs or min(os.cpu_count() or 1, 32)
+    n_files, per_file = cfg["n_files"], cfg["per_file"]
+    if n_files * per_file >= FLAT_BUILD_MIN:
+        n = n_files * per_file
+        paths = [stem + f".gen{k}.npy" for k in range(4)]
+        for p, dt in zip(paths, (np.int8, np.int32, np.int32, np.int16)):
+            np.lib.format.open_memmap(p, mode="w+", dtype=dt, shape=(n,)).flush()
+        step = max(1, n_files // (procs * 8))
+        jobs = [(cfg["config"], a, min(a + step, n_files), per_file, cfg["db_law"], sizes, paths)
+                for a in range(0, n_files, step)]
         with ProcessPoolExecutor(procs) as ex:
-            files = list(ex.map(_gen_file, jobs, chunksize=max(1, len(jobs) // (procs * 4))))
+            list(ex.map(_gen_into, jobs))
+        arrs = [np.load(p, mmap_mode="r") for p in paths]
+        stats = synth.write_igd_flat(stem, arrs[0], arrs[1], arrs[2], arrs[3], per_file)
+        del arrs
+        for p in paths:
+            os.unlink(p)
     else:
-        files = [_gen_file(j) for j in jobs]
-    stats = synth.write_igd_direct(stem, files)
+        jobs = [(cfg["config"], i, per_file, cfg["db_law"], sizes) for i in range(n_files)]
+        if procs > 1 and len(jobs) >= 64:
+            with ProcessPoolExecutor(procs) as ex:
+                files = list(ex.map(_gen_file, jobs, chunksize=max(1, len(jobs) // (procs * 4))))
+        else:
+            files = [_gen_file(j) for j in jobs]
+        stats = synth.write_igd_direct(stem, files)
     with open(stem + ".stats.json", "w") as f:
         json.dump(stats, f)
     with open(marker, "w") as f:

@@ -375,3 +375,42 @@ def make_fixture():
 
 if __name__ == "__main__":
     make_fixture()
+
+
+def test_create_abandons_when_an_input_does_not_open(workdir):
+    """a dangling symlink among the inputs: the reference returns from create_igd at the first file that does not
+    open (src/igd_create.c:57-58) and writes nothing; so does this build -- no crash, no _index.tsv, no empty
+    db.igd that would make every re-run say 'exists!'"""
+    bed = os.path.join(workdir, "create_bed_dangling")
+    _awkward_files(bed)
+    os.symlink(os.path.join(bed, "no_such_file.bed"), os.path.join(bed, "f00004x.bed"))
+    out = os.path.join(workdir, "mine_dangling") + "/"
+    for opts in ([], ["-s", "0"]):
+        r = subprocess.run([api.CLI_PATH, "create", bed, out, "db", *opts], capture_output=True)
+        assert r.returncode == 0, (r.returncode, r.stderr.decode())
+        assert not os.path.exists(out + "db.igd") and not os.path.exists(out + "db_index.tsv")
+    if O.have_ref():
+        refout = os.path.join(workdir, "ref_dangling") + "/"
+        r = subprocess.run([O.REF_BIN, "create", bed, refout, "db"], capture_output=True)
+        assert not os.path.exists(refout + "db.igd")
+
+
+def test_create_lines_wider_than_the_field_table(workdir):
+    """50-column lines: the splitter's table holds 40 pointers and must not be overrun (the reference's 17-entry
+    table is, and it aborts); fields 0-4 are all that create reads"""
+    bed = os.path.join(workdir, "create_bed_wide")
+    os.makedirs(bed)
+    rng = np.random.default_rng(5)
+    want = 0
+    for i in range(12):
+        with open(os.path.join(bed, f"f{i:05d}.bed"), "w") as f:
+            for k in range(60):
+                a = int(rng.integers(0, 900000))
+                f.write("\t".join([f"chr{1 + k % 3}", str(a), str(a + 100), "n", str(k)] + ["x"] * 45) + "\n")
+                want += 1 + ((a + 99) // 16384 - a // 16384)         # one record per bin touched
+    out = os.path.join(workdir, "mine_wide") + "/"
+    stdout = run_create(api.CLI_PATH, bed, out, "db")
+    assert "Save igd database to" in stdout
+    db = O.OracleDB(out + "db.igd")
+    assert db.nctg == 3 and sorted(db.ctg_names) == ["chr1", "chr2", "chr3"]
+    assert db.nrecords == want and sum(db.file_nr) == 12 * 60
