@@ -402,7 +402,8 @@ def run_ours(args):
         traffic = None
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get(args.workload, {}).get(str(world))
+            tr = json.load(open(tp)).get(args.workload)
+            traffic = tr.get(str(world)) if isinstance(tr, dict) else None
         cfg = config_of(args, n_total, world)
         if world > 1:
             cfg["parallelism"] += (" kernel per rank over NVLink peer memory (igd_b200_reducer)" if reducer is not None

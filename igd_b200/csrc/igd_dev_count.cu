@@ -241,7 +241,11 @@ __global__ void __launch_bounds__(SCAN_T) k_plan(DbView db, const uint32_t *cnt2
             mid = sa0 + c.x, sb0 = mid + c.y;
             seg_off[t] = sa0, seg_mid[t] = mid;
             if (rank) {                                     // k_windows makes the descriptors of this tile's items
-                tplan[t] = make_int4((int)sa0, (int)mid, (int)sb0, (int)i0);
+                tplan[2 * t] = make_int4((int)sa0, (int)mid, (int)sb0, (int)i0);
+                if (sb0 != sa0) {                           // everything else it needs about the tile, in one place
+                    const int4 tq = __ldg(reinterpret_cast<const int4 *>(&db.tiles[t]));
+                    tplan[2 * t + 1] = make_int4(tq.x, tq.y, tq.z, (int)__ldg(&db.gbase[t]));
+                }
                 ni = 0;
             }
             if (ni) {
@@ -607,73 +611,187 @@ constexpr uint32_t RK_INL = 4;          // segments inside an item's window that
 //   A.w = window mask of segments 0-31                                                B.x = of segments 32-63
 //   B.w = number of segments inside the window; when there are <= RK_INL of them their x values themselves are in
 //         B.y (first | second << 16) and B.z, and the search kernel touches neither the masks nor the segments
-// LPT lanes per tile (grid-stride; 8 for databases of small tiles, 32 otherwise), one THREAD per item: the tile's
-// items are numbered like k_plan's (group-major START items, then the END items, rank only); neighbouring threads
-// read the same <= 64 segments (L1 hits).
+// tiles that k_windows_small takes (see there)
+constexpr uint32_t WS_S = 16, WS_G = 8;
+__device__ __forceinline__ bool windows_small_tile(uint32_t nseg, uint32_t ng) { return nseg <= WS_S && ng <= WS_G; }
+
+// LPT lanes per tile (grid-stride).  Per (chunk of <= 64 segments,
+// START / END): the groups' key ranges ascend, so a segment x is past ALL keys of the groups before its HOME group
+// (the first one whose largest key it is not past), possibly inside the window of the home group, and past NO key
+// of the groups after it.  The lanes take the segments (a binary search each over the tile's gk[]), leave one
+// count per home group and one window bit in shared memory, and then take the groups: an item's base count is the
+// number of segments whose home lies behind its group (a suffix sum), its window the bits left at its group.
+// O(segments * log(groups) + groups) per chunk, where testing every segment against every item is their product.
 template <int LPT>
-__global__ void __launch_bounds__(256) k_windows(DbView db, const int4 *__restrict__ tplan,
+__global__ void __launch_bounds__(256, 4) k_windows(DbView db, const int4 *__restrict__ tplan,
                                                   const uint32_t *__restrict__ segs,
                                                   const unsigned long long *__restrict__ tot,
                                                   unsigned long long seg_cap, unsigned long long item_cap,
-                                                  int4 *__restrict__ out)
+                                                  int4 *__restrict__ out, int small_done)
+{
+    constexpr int NSUB = 256 / LPT, NGT = 4 * LPT;          // NGT: groups of a tile whose key ranges are staged in shared memory
+    __shared__ uint32_t s_cnt[NSUB][LPT + 1], s_m0[NSUB][LPT], s_m1[NSUB][LPT], s_x[NSUB][SMAX], s_gk[NSUB][2][NGT];
+    pdl_launch_dependents();
+    pdl_wait();                                             // the plan, the segments
+    if (tot[0] > seg_cap || tot[1] > item_cap) return;
+    static_assert(LPT == 32, "a warp per tile: the tiles are taken 32 at a time, one per lane, to see which need work");
+    const uint32_t l = threadIdx.x % LPT, sub = threadIdx.x / LPT;
+    const unsigned lmask = FULL;
+    uint32_t *cnt = s_cnt[sub], *m0 = s_m0[sub], *m1 = s_m1[sub], *sx = s_x[sub];
+    const uint32_t T = (uint32_t)db.ntiles;
+    // per warp `tpw` tiles at a time (32 when k_windows_small has taken most of them, else 1): lane i looks at tile
+    // tb + i (coalesced), then the warp works through the ones that have items to describe
+    const uint32_t tpw = small_done ? 32u : 1u;
+    for (uint32_t tb = (blockIdx.x * NSUB + sub) * tpw; tb < T; tb += gridDim.x * NSUB * tpw) {
+      int4 tp_l = make_int4(0, 0, 0, 0), tm_l = make_int4(0, 0, 0, 0);
+      if (l < tpw && tb + l < T) {
+          tp_l = __ldg(&tplan[2 * (tb + l)]);
+          if (tp_l.z != tp_l.x) tm_l = __ldg(&tplan[2 * (tb + l) + 1]);
+      }
+      bool need = tp_l.z != tp_l.x;
+      if (need && small_done && windows_small_tile((uint32_t)(tp_l.z - tp_l.x), ((uint32_t)tm_l.y + GROUP - 1) / GROUP))
+          need = false;                                     // k_windows_small has done this tile
+      unsigned todo = __ballot_sync(FULL, need);
+      while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int4 tp = make_int4(__shfl_sync(FULL, tp_l.x, src), __shfl_sync(FULL, tp_l.y, src),
+                                  __shfl_sync(FULL, tp_l.z, src), __shfl_sync(FULL, tp_l.w, src));
+        const int4 tm = make_int4(__shfl_sync(FULL, tm_l.x, src), __shfl_sync(FULL, tm_l.y, src),
+                                  __shfl_sync(FULL, tm_l.z, src), __shfl_sync(FULL, tm_l.w, src));   // off8, n, ts, first group
+        const uint32_t a = (uint32_t)tp.x, m = (uint32_t)tp.y, e = (uint32_t)tp.z, i0 = (uint32_t)tp.w;
+        const uint32_t gb = (uint32_t)tm.w;
+        const uint32_t n = (uint32_t)tm.y, ng = (n + GROUP - 1) / GROUP;
+        const uint32_t ch = (e - a + SMAX - 1) / SMAX, chF = (m - a + SMAX - 1) / SMAX;
+        const bool staged = ng <= (uint32_t)NGT;            // the key ranges of the tile's groups, START and END
+        if (staged) {
+            for (uint32_t i = l; i < ng; i += LPT)
+                s_gk[sub][0][i] = __ldg(&db.gk[gb + i]), s_gk[sub][1][i] = __ldg(&db.gk[gb + db.ngroups + i]);
+            __syncwarp(lmask);
+        }
+        for (uint32_t c = 0; c < ch; ++c) {
+            const uint32_t sa = a + c * SMAX, ns_all = min(sa + (uint32_t)SMAX, e) - sa;
+            const uint32_t nf = min(max(m, sa), sa + ns_all) - sa;         // first-bin segments of the chunk
+            for (uint32_t kind = 0; kind < (c < chF ? 2u : 1u); ++kind) {
+                const uint32_t ns = kind ? nf : ns_all, sh = kind ? 0u : 16u;
+                const uint32_t *gk = staged ? s_gk[sub][kind] : db.gk + gb + (kind ? db.ngroups : 0u);
+                for (uint32_t g0 = 0; g0 < ng; g0 += LPT) {
+                    cnt[l] = 0, m0[l] = 0, m1[l] = 0;
+                    if (l == 0) cnt[LPT] = 0;
+                    __syncwarp(lmask);
+                    for (uint32_t j = l; j < ns; j += LPT) {
+                        const uint32_t x = (__ldg(&segs[sa + j]) >> sh) & 0xffffu;
+                        if (g0 == 0) sx[j] = x;
+                        uint32_t lo = 0, hi = ng;           // home = #groups whose largest key x is past
+                        while (lo < hi) {
+                            const uint32_t mid = (lo + hi) >> 1;
+                            if (x >= (gk[mid] >> 16) + 0x8000u) lo = mid + 1;
+                            else hi = mid;
+                        }
+                        if (lo >= g0 + LPT) atomicAdd(&cnt[LPT], 1u);
+                        else if (lo >= g0) {
+                            atomicAdd(&cnt[lo - g0], 1u);
+                            if (lo < ng && x >= (gk[lo] & 0xffffu) + 0x8000u)      // past the home group's smallest key
+                                atomicOr(j < 32 ? &m0[lo - g0] : &m1[lo - g0], 1u << (j & 31));
+                        }
+                    }
+                    __syncwarp(lmask);
+                    // lane l <-> group g0 + l: base = segments whose home lies behind it
+                    uint32_t suf = cnt[l + 1];
+#pragma unroll
+                    for (int d = 1; d < LPT; d <<= 1) {
+                        const uint32_t o = __shfl_down_sync(lmask, suf, d, LPT);
+                        if (l + d < LPT) suf += o;
+                    }
+                    const uint32_t g = g0 + l;
+                    if (g < ng) {
+                        const uint32_t mm0 = m0[l], mm1 = m1[l], nin = __popc(mm0) + __popc(mm1);
+                        uint32_t v01 = 0, v23 = 0;
+                        if (nin <= RK_INL) {
+                            uint32_t q0 = mm0, q1 = mm1;
+                            for (uint32_t r = 0; r < nin; ++r) {
+                                uint32_t j;
+                                if (q0) j = __ffs(q0) - 1, q0 &= q0 - 1;
+                                else j = 32 + __ffs(q1) - 1, q1 &= q1 - 1;
+                                if (r < 2) v01 |= sx[j] << (16 * r);
+                                else v23 |= sx[j] << (16 * (r - 2));
+                            }
+                        }
+                        const int r0 = (int)(g * GROUP);
+                        const uint32_t nv = (uint32_t)min((int)n - r0, GROUP), tsr = (uint32_t)min(max(tm.z - r0, 0), GROUP);
+                        const uint32_t nl = kind ? 0u : ns_all - nf, fix = !kind && tsr > 0 && nl > 0;
+                        const size_t k = (size_t)i0 + (kind ? ng * ch + g * chF + c : g * ch + c);
+                        out[2 * k] = make_int4((int)((uint32_t)tm.x + g * (GROUP / 8) + (kind ? db.eoff8 : 0u)), (int)sa,
+                                               (int)(nv | ns << 9 | suf << 16 | nl << 23 | kind << 30 | fix << 31), (int)mm0);
+                        out[2 * k + 1] = make_int4((int)mm1, (int)v01, (int)v23, (int)nin);
+                    }
+                    __syncwarp(lmask);
+                }
+            }
+        }
+        __syncwarp(lmask);
+      }
+    }
+}
+
+// The same for SMALL tiles -- at most WS_S segments in all and at most WS_G groups, what a sparse database
+// (BASELINE config 2: ~6 segments and 3 groups per tile) consists of: one THREAD per tile, segments and key ranges
+// in registers, every (group, segment) pair tested.  k_windows<LPT> skips these tiles when `small_done` is set.
+
+__global__ void __launch_bounds__(128) k_windows_small(DbView db, const int4 *__restrict__ tplan,
+                                                        const uint32_t *__restrict__ segs,
+                                                        const unsigned long long *__restrict__ tot,
+                                                        unsigned long long seg_cap, unsigned long long item_cap,
+                                                        int4 *__restrict__ out)
 {
     pdl_launch_dependents();
     pdl_wait();                                             // the plan, the segments
     if (tot[0] > seg_cap || tot[1] > item_cap) return;
-    const uint32_t l8 = threadIdx.x % LPT, nsub = gridDim.x * (blockDim.x / LPT);
-    for (uint32_t t = blockIdx.x * (blockDim.x / LPT) + (threadIdx.x / LPT); t < (uint32_t)db.ntiles; t += nsub) {
-        const int4 tp = __ldg(&tplan[t]);
-        const uint32_t a = (uint32_t)tp.x, m = (uint32_t)tp.y, e = (uint32_t)tp.z, i0 = (uint32_t)tp.w;
-        if (e == a) continue;                               // no query reached this tile
-        const int4 tm = __ldg(reinterpret_cast<const int4 *>(&db.tiles[t]));
-        const uint32_t gb = __ldg(&db.gbase[t]);
-        const uint32_t n = (uint32_t)tm.y, ng = (n + GROUP - 1) / GROUP;
-        const uint32_t ch = (e - a + SMAX - 1) / SMAX, chF = (m - a + SMAX - 1) / SMAX, ni = ng * (ch + chF);
-        for (uint32_t k = l8; k < ni; k += LPT) {
-            const bool endk = k >= ng * ch;
-            const uint32_t kk = endk ? k - ng * ch : k, chx = endk ? chF : ch;
-            const uint32_t g = kk / chx, c = kk - g * chx;
-            const uint32_t sa = a + c * SMAX, sb = min(sa + (uint32_t)SMAX, endk ? m : e), ns = sb - sa;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint32_t)db.ntiles) return;
+    const int4 tp = __ldg(&tplan[2 * t]);
+    const uint32_t a = (uint32_t)tp.x, m = (uint32_t)tp.y, e = (uint32_t)tp.z, i0 = (uint32_t)tp.w;
+    if (e == a) return;                                     // no query reached this tile
+    const int4 tm = __ldg(&tplan[2 * t + 1]);               // the tile's off8, n, ts, first group
+    const uint32_t n = (uint32_t)tm.y, ng = (n + GROUP - 1) / GROUP, ns_all = e - a, nf = m - a;
+    if (!windows_small_tile(ns_all, ng)) return;
+    uint32_t w[WS_S], ks[WS_G], ke[WS_G];
+#pragma unroll
+    for (uint32_t j = 0; j < WS_S; ++j) w[j] = j < ns_all ? __ldg(&segs[a + j]) : 0u;
+#pragma unroll
+    for (uint32_t g = 0; g < WS_G; ++g) {
+        ks[g] = g < ng ? __ldg(&db.gk[(uint32_t)tm.w + g]) : 0u;
+        ke[g] = g < ng && nf > 0 ? __ldg(&db.gk[(uint32_t)tm.w + db.ngroups + g]) : 0u;
+    }
+#pragma unroll
+    for (uint32_t kind = 0; kind < 2; ++kind) {
+        if (kind && nf == 0) break;
+        const uint32_t ns = kind ? nf : ns_all, sh = kind ? 0u : 16u;
+#pragma unroll
+        for (uint32_t g = 0; g < WS_G; ++g) {
+            if (g >= ng) break;
+            const uint32_t kr = kind ? ke[g] : ks[g];
+            const uint32_t lo_t = (kr & 0xffffu) + 0x8000u, hi_t = (kr >> 16) + 0x8000u;
+            uint32_t base = 0, mk = 0, nin = 0, v01 = 0, v23 = 0;
+#pragma unroll
+            for (uint32_t j = 0; j < WS_S; ++j) {
+                const uint32_t x = (w[j] >> sh) & 0xffffu;
+                const bool on = j < ns;
+                base += on && x >= hi_t;                    // past every key of the item
+                if (on && x >= lo_t && x < hi_t) {          // past some: compared entry by entry
+                    mk |= 1u << j;
+                    if (nin < 2) v01 |= x << (16 * nin);
+                    else if (nin < 4) v23 |= x << (16 * (nin - 2));
+                    ++nin;
+                }
+            }
             const int r0 = (int)(g * GROUP);
             const uint32_t nv = (uint32_t)min((int)n - r0, GROUP), tsr = (uint32_t)min(max(tm.z - r0, 0), GROUP);
-            const uint32_t nf = min(max(m, sa), sb) - sa;
-            const uint32_t kr = __ldg(&db.gk[gb + g + (endk ? db.ngroups : 0u)]);      // smallest, largest key
-            const uint32_t lo_t = (kr & 0xffffu) + 0x8000u, hi_t = (kr >> 16) + 0x8000u;
-            const uint32_t sh = endk ? 0u : 16u;
-            const uint32_t *sg = segs + sa;
-            uint32_t base = 0, mk[2] = {0, 0};
-            for (uint32_t j0 = 0; j0 < ns; j0 += 8) {           // eight segments at a time: their loads in flight together
-                uint32_t w[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) w[j] = j0 + j < ns ? __ldg(&sg[j0 + j]) : 0u;
-                uint32_t bits = 0;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const uint32_t x = (w[j] >> sh) & 0xffffu;      // an absent segment: x = 0, past no key
-                    base += x >= hi_t;                              // past every key of the item
-                    bits |= (uint32_t)(x >= lo_t && x < hi_t) << j;     // past some: compared entry by entry
-                }
-                if (j0 < 32) mk[0] |= bits << j0;
-                else mk[1] |= bits << (j0 - 32);
-            }
-            const uint32_t nin = __popc(mk[0]) + __popc(mk[1]);
-            uint32_t v01 = 0, v23 = 0;
-            if (nin <= RK_INL) {
-                uint32_t m0 = mk[0], m1 = mk[1];
-                for (uint32_t r = 0; r < nin; ++r) {
-                    uint32_t j;
-                    if (m0) j = __ffs(m0) - 1, m0 &= m0 - 1;
-                    else j = 32 + __ffs(m1) - 1, m1 &= m1 - 1;
-                    const uint32_t x = (__ldg(&sg[j]) >> sh) & 0xffffu;
-                    if (r < 2) v01 |= x << (16 * r);
-                    else v23 |= x << (16 * (r - 2));
-                }
-            }
-            const uint32_t fix = !endk && tsr > 0 && ns > nf;
-            out[2 * (size_t)(i0 + k)] =
-                make_int4((int)((uint32_t)tm.x + g * (GROUP / 8) + (endk ? db.eoff8 : 0u)), (int)sa,
-                          (int)(nv | ns << 9 | base << 16 | (ns - nf) << 23 | (uint32_t)endk << 30 | fix << 31), (int)mk[0]);
-            out[2 * (size_t)(i0 + k) + 1] = make_int4((int)mk[1], (int)v01, (int)v23, (int)nin);
+            const uint32_t nl = kind ? 0u : ns_all - nf, fix = !kind && tsr > 0 && nl > 0;
+            const size_t k = (size_t)i0 + (kind ? ng + g : g);      // one chunk: ch = chF = 1
+            out[2 * k] = make_int4((int)((uint32_t)tm.x + g * (GROUP / 8) + (kind ? db.eoff8 : 0u)), (int)a,
+                                   (int)(nv | ns << 9 | base << 16 | nl << 23 | kind << 30 | fix << 31), (int)mk);
+            out[2 * k + 1] = make_int4(0, (int)v01, (int)v23, (int)nin);
         }
     }
 }
@@ -949,7 +1067,7 @@ int enqueue_count_t(igdb_dev *d, const igdb_dev::Pending &p)
     if (grow(&d->items, &d->item_cap, std::min<int64_t>((PK ? 2 : 1) * (d->db_groups + p.n / 64), item_limit(d, grid)) + 1024, 1, 1))
         return -1;
     if (PK && grow(&d->items2, &d->item2_cap, 2 * d->item_cap, 1, 1)) return -1;
-    if (PK && !d->tplan && dev_alloc(d, &d->tplan, (size_t)d->T + 1)) return -1;
+    if (PK && !d->tplan && dev_alloc(d, &d->tplan, 2 * (size_t)d->T + 2)) return -1;
     const unsigned long long seg_cap = (unsigned long long)std::min<int64_t>(d->cseg_cap - CAP_SLACK, 0x7fffffff);
     const unsigned long long item_cap =
         (unsigned long long)std::min<int64_t>(d->item_cap - CAP_SLACK, item_limit(d, grid));
@@ -984,12 +1102,19 @@ int enqueue_count_t(igdb_dev *d, const igdb_dev::Pending &p)
     a.seg_cap = seg_cap, a.item_cap = item_cap, a.v = p.v, a.hits = p.hits;
     if (PK) {
         // the descriptors of k_count_rank (with the windows of the items): one thread per item, 8 or 32 per tile
-        const bool wide = d->db_groups >= 3 * (int64_t)d->T;        // >= 6 items per tile on average
-        const int64_t per_cta = wide ? 8 : 32;
-        const unsigned wgrid = (unsigned)std::min<int64_t>(((int64_t)d->T + per_cta - 1) / per_cta, (int64_t)d->sm_count * 64);
-        CK(launch_pdl(wide ? k_windows<32> : k_windows<8>, wgrid, 256, 0, st, db, (const int4 *)d->tplan,
+        // a database of small tiles: most of them by k_windows_small, the others (many segments) by the general kernel
+        const bool sparse = d->db_groups < 6 * (int64_t)d->T;       // groups per tile on average
+        if (sparse) {
+            CK(launch_pdl(k_windows_small, (unsigned)((d->T + 127) / 128), 128, 0, st, db, (const int4 *)d->tplan,
+                          (const uint32_t *)(const void *)d->csegs, (const unsigned long long *)d->plan_tot, seg_cap,
+                          item_cap, d->items2));
+            d->launches += 1;
+        }
+        const int64_t tpc = sparse ? 256 : 8;                       // tiles per CTA and turn
+        const unsigned wgrid = (unsigned)std::min<int64_t>(((int64_t)d->T + tpc - 1) / tpc, (int64_t)d->sm_count * 64);
+        CK(launch_pdl(k_windows<32>, wgrid, 256, 0, st, db, (const int4 *)d->tplan,
                       (const uint32_t *)(const void *)d->csegs, (const unsigned long long *)d->plan_tot, seg_cap, item_cap,
-                      d->items2));
+                      d->items2, sparse ? 1 : 0));
         d->launches += 1;
     }
     if (stages) CK(cudaEventRecord(d->stage_ev[3], st));

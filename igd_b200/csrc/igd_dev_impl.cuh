@@ -341,7 +341,7 @@ struct igdb_dev {
     int4 *items2 = nullptr;                                 // k_count_rank's descriptors (2 x int4 per item), k_windows
     uint32_t *qrank = nullptr;                              // [n] per query: rank of its first-bin segment (k_cseg_count)
     int64_t qrank_cap = 0;
-    int4 *tplan = nullptr;                                  // [T] per tile {first segment, first later-bin one, end, first item}
+    int4 *tplan = nullptr;                                  // [2T] per tile {first segment, first later-bin one, end, first item}, {off8, n, ts, first group}
     int64_t item2_cap = 0;
     int64_t db_groups = 0;                                  // sum over tiles of ceil(n / GROUP)
     int count_grid[2][2] = {{0, 0}, {0, 0}};                // CTAs of the search kernel [packed][V] (0 = not set up)
