@@ -146,8 +146,8 @@ def config_of(args, n_total, world):
                         f"{n_total} queries, count mode",
             "n_files": c["n_files"], "intervals_per_file": c["per_file"], "n_queries": n_total,
             "l2": "256 MiB flush write between steps (untimed); DB image > 126 MB L2",
-            "parallelism": (f"db replicated on {world} GPUs; the {n_total} queries sorted by (contig, start) and cut into "
-                            f"{world} contiguous shards by scan-byte prefix sum; hits[] combined by one exchange"
+            "parallelism": (f"db replicated on {world} GPUs; the {n_total} queries cut into {world} contiguous tile ranges of "
+                            f"the (contig, start) order by scan-byte prefix sum, on the devices; hits[] combined by one exchange"
                             if world > 1 else "single GPU")}
 
 
@@ -214,26 +214,35 @@ def run_ours(args):
     qs_all, qe_all = q.start, q.end
     n_total = len(ctg_all)
 
-    # multi-GPU: DB replicated, (ctg,start)-sorted queries cut into cost-balanced contiguous shards
-    if world > 1:
-        hdr = workloads.read_igd_header(path)
-        ctg_s, qs_s, qe_s, bounds = workloads.sort_and_shard(hdr, ctg_all, qs_all, qe_all, world)
-        a, b = bounds[rank], bounds[rank + 1]
-        ctg_l, qs_l, qe_l = ctg_s[a:b], qs_s[a:b], qe_s[a:b]
-    else:
-        ctg_l, qs_l, qe_l = ctg_all, qs_all, qe_all
-    n_local = len(ctg_l)
-
-    d_ctg = torch.from_numpy(np.ascontiguousarray(ctg_l)).to(dev)
-    d_qs = torch.from_numpy(np.ascontiguousarray(qs_l)).to(dev)
-    d_qe = torch.from_numpy(np.ascontiguousarray(qe_l)).to(dev)
-    d_hits = torch.zeros(igd.nfiles, dtype=torch.int64, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
     # a real (non-default) stream: the library enqueues its kernels on the stream it is handed, and the
-    # CUDA events / NCCL collective below are recorded on the same one
+    # CUDA events / NCCL collectives below are recorded on the same one
     side = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(side)
     stream = side.cuda_stream
+
+    # multi-GPU: DB replicated; every rank starts from ITS 1/N slice of the query set as generated (any order) and
+    # the shards -- contiguous tile ranges of the (contig, start) order, balanced by the prefix sum of estimated scan
+    # bytes -- are made on the devices (igd_b200_shard_*: per-tile cost, all-reduce, cuts, partition, all-to-all)
+    tile_lo, tile_hi = 0, int(igd.ntiles)
+    if world > 1:
+        from igd_b200.multi import DeviceSharder
+        a, b = n_total * rank // world, n_total * (rank + 1) // world
+        ctg_l, qs_l, qe_l = ctg_all[a:b], qs_all[a:b], qe_all[a:b]
+        sharder = DeviceSharder(igd, dev)
+        u_ctg, u_qs, u_qe = (torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (ctg_l, qs_l, qe_l))
+        d_ctg, d_qs, d_qe, tile_lo, tile_hi = sharder.shard(u_ctg, u_qs, u_qe)
+        d_ctg, d_qs, d_qe = d_ctg.clone(), d_qs.clone(), d_qe.clone()
+        torch.cuda.synchronize()
+    else:
+        ctg_l, qs_l, qe_l = ctg_all, qs_all, qe_all
+        d_ctg = torch.from_numpy(np.ascontiguousarray(ctg_l)).to(dev)
+        d_qs = torch.from_numpy(np.ascontiguousarray(qs_l)).to(dev)
+        d_qe = torch.from_numpy(np.ascontiguousarray(qe_l)).to(dev)
+    n_local = int(d_ctg.shape[0])                   # queries of this rank's shard
+    n_slice = len(ctg_l)                            # queries this rank uploads in the end-to-end leg
+
+    d_hits = torch.zeros(igd.nfiles, dtype=torch.int64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
 
     # the one exchange of the path: hits[] summed over the ranks by the library's own kernel over NVLink peer
     # memory (igd_b200_reducer_*); NCCL's all-reduce if that cannot be set up on every rank (or on request)
@@ -260,8 +269,10 @@ def run_ours(args):
 
     def step_device():
         d_hits.zero_()
-        igd.count_device(n_local, d_ctg.data_ptr(), d_qs.data_ptr(), d_qe.data_ptr(), 0, d_hits.data_ptr(), stream)
-        igd.count_device_finish()
+        if n_local:
+            igd.count_device_tiles(n_local, d_ctg.data_ptr(), d_qs.data_ptr(), d_qe.data_ptr(), 0, d_hits.data_ptr(),
+                                   stream, tile_lo, tile_hi)
+            igd.count_device_finish()
         if world > 1:
             combine()
 
@@ -270,7 +281,7 @@ def run_ours(args):
     h_qs = torch.from_numpy(np.ascontiguousarray(qs_l)).pin_memory()
     h_qe = torch.from_numpy(np.ascontiguousarray(qe_l)).pin_memory()
     h_hits = torch.zeros(igd.nfiles, dtype=torch.int64).pin_memory()
-    e_ctg, e_qs, e_qe = (torch.empty_like(d_ctg) for _ in range(3))
+    e_ctg, e_qs, e_qe = (torch.empty(n_slice, dtype=torch.int32, device=dev) for _ in range(3))
 
     def step_e2e():
         if world == 1:
@@ -278,12 +289,16 @@ def run_ours(args):
             hits = np.zeros(igd.nfiles, np.int64)
             igd.count_ptr(n_local, h_ctg.data_ptr(), h_qs.data_ptr(), h_qe.data_ptr(), 0, hits)
             return hits
+        # this rank's slice of the unsorted query set: H2D, shard plan + exchange on the devices, search, combine
         e_ctg.copy_(h_ctg, non_blocking=True)
         e_qs.copy_(h_qs, non_blocking=True)
         e_qe.copy_(h_qe, non_blocking=True)
+        s_ctg, s_qs, s_qe, lo, hi = sharder.shard(e_ctg, e_qs, e_qe)
         d_hits.zero_()
-        igd.count_device(n_local, e_ctg.data_ptr(), e_qs.data_ptr(), e_qe.data_ptr(), 0, d_hits.data_ptr(), stream)
-        igd.count_device_finish()
+        if s_ctg.shape[0]:
+            igd.count_device_tiles(int(s_ctg.shape[0]), s_ctg.data_ptr(), s_qs.data_ptr(), s_qe.data_ptr(), 0,
+                                   d_hits.data_ptr(), stream, lo, hi)
+            igd.count_device_finish()
         combine()
         h_hits.copy_(d_hits, non_blocking=True)
         torch.cuda.synchronize()
@@ -427,7 +442,8 @@ def run_ours(args):
                                           if e2e_split and e2e_split["h2d_ms"] > 0 else None),
                     "cpu_binding": numa,
                     "api": "igd_b200_count (C-ABI, host buffers)" if world == 1 else
-                           "pinned H2D + igd_b200_count_device + hits[] exchange + D2H"},
+                           "pinned H2D of this rank's 1/N of the queries + igd_b200_shard_* (cost, all-reduce, cuts, partition, "
+                           "all-to-all) + igd_b200_count_device_tiles + hits[] exchange + D2H"},
             "file_ingest": None if file_s is None else {
                 "value": file_n / file_s, "unit": UNIT, "ms": file_s * 1e3, "file_bytes": file_bytes, "n_queries": file_n,
                 "api": "search(igd, qFile) -- BED text (warm page cache) -> pinned chunks -> H2D -> parsed on the "

@@ -94,6 +94,14 @@ def load_library():
     L.igd_b200_count_device.argtypes = [vp, C.c_int64, vp, vp, vp, C.c_int32, vp, vp]
     L.igd_b200_count_device_finish.restype = C.c_int
     L.igd_b200_count_device_finish.argtypes = [vp]
+    L.igd_b200_count_device_tiles.restype = C.c_int
+    L.igd_b200_count_device_tiles.argtypes = [vp, C.c_int64, vp, vp, vp, C.c_int32, vp, vp, C.c_int32, C.c_int32]
+    L.igd_b200_shard_cost.restype = C.c_int
+    L.igd_b200_shard_cost.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp]
+    L.igd_b200_shard_cuts.restype = C.c_int
+    L.igd_b200_shard_cuts.argtypes = [vp, vp, C.c_int32, vp, vp]
+    L.igd_b200_shard_partition.restype = C.c_int
+    L.igd_b200_shard_partition.argtypes = [vp, C.c_int64, vp, vp, vp, vp, C.c_int32, vp, vp, vp, vp, vp, vp]
     L.igd_b200_full.restype = C.c_int
     L.igd_b200_full.argtypes = [vp, C.c_int64, _i32p, _i32p, _i32p, C.POINTER(_HitList)]
     L.igd_b200_hitlist_free.argtypes = [C.POINTER(_HitList)]
@@ -412,6 +420,28 @@ class IGD:
         """Device-pointer form: enqueue on a CUDA stream; d_hits is uint64[nfiles], incremented.
         Call :meth:`count_device_finish` before consuming d_hits."""
         if self._L.igd_b200_count_device(self._need(), n, d_ctg, d_qs, d_qe, int(v), d_hits, stream):
+            raise IGDError(last_error())
+
+    def count_device_tiles(self, n: int, d_ctg: int, d_qs: int, d_qe: int, v: int, d_hits: int, stream: int,
+                           tile_lo: int, tile_hi: int) -> None:
+        """count_device for a shard: no query touches a tile outside [tile_lo, tile_hi)."""
+        if self._L.igd_b200_count_device_tiles(self._need(), n, d_ctg, d_qs, d_qe, int(v), d_hits, stream,
+                                               int(tile_lo), int(tile_hi)):
+            raise IGDError(last_error())
+
+    # -- the shard plan of a multi-GPU search, on the device (device pointers; enqueued on `stream`) --------
+    def shard_cost(self, n: int, d_ctg: int, d_qs: int, d_qe: int, d_tile_cost: int, stream: int = 0) -> None:
+        if self._L.igd_b200_shard_cost(self._need(), n, d_ctg, d_qs, d_qe, d_tile_cost, stream):
+            raise IGDError(last_error())
+
+    def shard_cuts(self, d_tile_cost: int, n_parts: int, d_cuts: int, stream: int = 0) -> None:
+        if self._L.igd_b200_shard_cuts(self._need(), d_tile_cost, int(n_parts), d_cuts, stream):
+            raise IGDError(last_error())
+
+    def shard_partition(self, n: int, d_ctg: int, d_qs: int, d_qe: int, d_cuts: int, n_parts: int, o_ctg: int, o_qs: int,
+                        o_qe: int, d_part_off: int, d_reach: int = 0, stream: int = 0) -> None:
+        if self._L.igd_b200_shard_partition(self._need(), n, d_ctg, d_qs, d_qe, d_cuts, int(n_parts), o_ctg, o_qs, o_qe,
+                                            d_part_off, d_reach, stream):
             raise IGDError(last_error())
 
     def count_device_finish(self) -> None:

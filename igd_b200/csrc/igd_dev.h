@@ -55,6 +55,10 @@ int igdb_dev_count_host(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_
 /* device buffers, enqueued on stream; d_hits[nfiles] incremented.  Pair with igdb_dev_count_finish. */
 int igdb_dev_count_device(igdb_dev *d, int64_t n, const int32_t *d_ctg, const int32_t *d_qs,
                           const int32_t *d_qe, int mode_v, int32_t v, uint64_t *d_hits, void *stream);
+/* the same when no query touches a tile outside [tile_lo, tile_hi) (global tile indices): plan and descriptors
+ * cover that range only */
+int igdb_dev_count_device_tiles(igdb_dev *d, int64_t n, const int32_t *d_ctg, const int32_t *d_qs, const int32_t *d_qe,
+                                int mode_v, int32_t v, uint64_t *d_hits, void *stream, int32_t tile_lo, int32_t tile_hi);
 /* waits until the batch enqueued by igdb_dev_count_device has been planned; if its plan did not fit the
  * scratch buffers (nothing was added to d_hits then) grows them and runs it again.  0 = d_hits is valid
  * in stream order. */
@@ -91,6 +95,17 @@ int64_t igdb_dev_seq_pairs_host(igdb_dev *d, int64_t n, const int32_t *ctg, cons
 
 /* -m restricted to the tiles [t0, t1) (global tile indices, contig-major): hitmap[nfiles*nfiles] is incremented */
 int64_t igdb_dev_hitsmap_host(igdb_dev *d, int32_t v, int64_t t0, int64_t t1, uint32_t *hitmap);
+
+/* Sharding a query set over n_parts ranks on the device (igd_dev_shard.cu): cost adds every query's estimated scan
+ * bytes to its first tile's slot of d_tile_cost[nTiles + 1]; cuts turns the (all-reduced) slots into n_parts + 1
+ * tile boundaries; partition reorders the queries by destination rank (d_part_off[n_parts + 1], device) and
+ * reports in d_reach[n_parts] (may be NULL) one past the last tile each destination's queries touch. */
+int igdb_dev_shard_cost(igdb_dev *d, int64_t n, const int32_t *d_ctg, const int32_t *d_qs, const int32_t *d_qe,
+                        uint64_t *d_tile_cost, void *stream);
+int igdb_dev_shard_cuts(igdb_dev *d, const uint64_t *d_tile_cost, int32_t n_parts, int32_t *d_cuts, void *stream);
+int igdb_dev_shard_partition(igdb_dev *d, int64_t n, const int32_t *d_ctg, const int32_t *d_qs, const int32_t *d_qe,
+                             const int32_t *d_cuts, int32_t n_parts, int32_t *o_ctg, int32_t *o_qs, int32_t *o_qe,
+                             int64_t *d_part_off, int32_t *d_reach, void *stream);
 
 /* The exchange step of the multi-GPU count path (igd_dev_p2p.cu): hits[] summed over the ranks by one kernel per
  * rank over peer memory.  create -> handle (64-byte CUDA IPC handle of this rank's mailbox) -> connect (all ranks'

@@ -148,14 +148,15 @@ __global__ void __launch_bounds__(SCAN_T) k_plan(DbView db, const uint32_t *cnt2
                                                   uint32_t *ticket, uint32_t *__restrict__ seg_off, uint32_t *__restrict__ seg_mid,
                                                   unsigned long long *__restrict__ tot, unsigned long long seg_cap,
                                                   unsigned long long item_cap, int4 *__restrict__ items, int rank,
-                                                  int4 *__restrict__ tplan)
+                                                  int4 *__restrict__ tplan, int32_t tlo, int32_t thi)
 {
     __shared__ unsigned long long red[3][SCAN_T / 32];
     __shared__ unsigned long long sh_prefix[2], sh_total[3];
     __shared__ bool sh_last;
     const int32_t T = db.ntiles;
     const int G = gridDim.x, b = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int32_t per = (T + G - 1) / G, t0 = min(b * per, T), t1 = min(t0 + per, T);
+    // only the tiles [tlo, thi) can have segments (a shard of a multi-GPU search: igd_dev_shard.cu; else all of them)
+    const int32_t per = (thi - tlo + G - 1) / G, t0 = min(tlo + b * per, thi), t1 = min(t0 + per, thi);
     pdl_launch_dependents();
     pdl_wait();                                             // the segment counters
 
@@ -627,7 +628,7 @@ __global__ void __launch_bounds__(256, 4) k_windows(DbView db, const int4 *__res
                                                   const uint32_t *__restrict__ segs,
                                                   const unsigned long long *__restrict__ tot,
                                                   unsigned long long seg_cap, unsigned long long item_cap,
-                                                  int4 *__restrict__ out, int small_done)
+                                                  int4 *__restrict__ out, int small_done, uint32_t tlo, uint32_t thi)
 {
     constexpr int NSUB = 256 / LPT, NGT = 4 * LPT;          // NGT: groups of a tile whose key ranges are staged in shared memory
     __shared__ uint32_t s_cnt[NSUB][LPT + 1], s_m0[NSUB][LPT], s_m1[NSUB][LPT], s_x[NSUB][SMAX], s_gk[NSUB][2][NGT];
@@ -638,11 +639,11 @@ __global__ void __launch_bounds__(256, 4) k_windows(DbView db, const int4 *__res
     const uint32_t l = threadIdx.x % LPT, sub = threadIdx.x / LPT;
     const unsigned lmask = FULL;
     uint32_t *cnt = s_cnt[sub], *m0 = s_m0[sub], *m1 = s_m1[sub], *sx = s_x[sub];
-    const uint32_t T = (uint32_t)db.ntiles;
+    const uint32_t T = thi;
     // per warp `tpw` tiles at a time (32 when k_windows_small has taken most of them, else 1): lane i looks at tile
     // tb + i (coalesced), then the warp works through the ones that have items to describe
     const uint32_t tpw = small_done ? 32u : 1u;
-    for (uint32_t tb = (blockIdx.x * NSUB + sub) * tpw; tb < T; tb += gridDim.x * NSUB * tpw) {
+    for (uint32_t tb = tlo + (blockIdx.x * NSUB + sub) * tpw; tb < T; tb += gridDim.x * NSUB * tpw) {
       int4 tp_l = make_int4(0, 0, 0, 0), tm_l = make_int4(0, 0, 0, 0);
       if (l < tpw && tb + l < T) {
           tp_l = __ldg(&tplan[2 * (tb + l)]);
@@ -742,13 +743,13 @@ __global__ void __launch_bounds__(128) k_windows_small(DbView db, const int4 *__
                                                         const uint32_t *__restrict__ segs,
                                                         const unsigned long long *__restrict__ tot,
                                                         unsigned long long seg_cap, unsigned long long item_cap,
-                                                        int4 *__restrict__ out)
+                                                        int4 *__restrict__ out, uint32_t tlo, uint32_t thi)
 {
     pdl_launch_dependents();
     pdl_wait();                                             // the plan, the segments
     if (tot[0] > seg_cap || tot[1] > item_cap) return;
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (uint32_t)db.ntiles) return;
+    const uint32_t t = tlo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= thi) return;
     const int4 tp = __ldg(&tplan[2 * t]);
     const uint32_t a = (uint32_t)tp.x, m = (uint32_t)tp.y, e = (uint32_t)tp.z, i0 = (uint32_t)tp.w;
     if (e == a) return;                                     // no query reached this tile
@@ -1073,14 +1074,16 @@ int enqueue_count_t(igdb_dev *d, const igdb_dev::Pending &p)
         (unsigned long long)std::min<int64_t>(d->item_cap - CAP_SLACK, item_limit(d, grid));
     const int thr = CSEG_T;
     const int nb = (int)((p.n + CSEG_T * CSEG_Q - 1) / (CSEG_T * CSEG_Q));
-    if (d->plan_grid == 0) {
+    const int32_t tlo = std::max(0, std::min(p.tile_lo, d->T)), thi = std::max(tlo, std::min(p.tile_hi, d->T));
+    if (d->plan_grid_max == 0) {
         // k_plan's CTAs wait for each other, so all of them must be resident at once: never more than the
         // occupancy calculator allows, and at most SCAN_T (the last CTA scans one aggregate per thread)
         int per_sm = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_plan, SCAN_T, 0));
         per_sm = std::max(1, std::min(per_sm, 4));
-        d->plan_grid = std::max(1, std::min({per_sm * d->sm_count, SCAN_T, (d->T + SCAN_T - 1) / SCAN_T}));
+        d->plan_grid_max = std::max(1, std::min(per_sm * d->sm_count, SCAN_T));
     }
+    d->plan_grid = std::max(1, std::min(d->plan_grid_max, (thi - tlo + SCAN_T - 1) / SCAN_T));
     const bool stages = d->stage_timing && MODE != M_ABN32;
     if (stages) CK(cudaEventRecord(d->stage_ev[0], st));
     if (grow(&d->qrank, &d->qrank_cap, p.n)) return -1;
@@ -1088,7 +1091,8 @@ int enqueue_count_t(igdb_dev *d, const igdb_dev::Pending &p)
     if (stages) CK(cudaEventRecord(d->stage_ev[1], st));
     // (the plan reads the later-bin counters that the scatter counts back down to zero)
     CK(launch_pdl(k_plan, d->plan_grid, SCAN_T, 0, st, db, d->cnt2, d->cnt2, ++d->plan_epoch, d->plan_agg, d->plan_flag,
-                  d->plan_flag + 1, d->cseg_off, d->cseg_mid, d->plan_tot, seg_cap, item_cap, d->items, PK ? 1 : 0, d->tplan));
+                  d->plan_flag + 1, d->cseg_off, d->cseg_mid, d->plan_tot, seg_cap, item_cap, d->items, PK ? 1 : 0, d->tplan,
+                  tlo, thi));
     if (stages) CK(cudaEventRecord(d->stage_ev[2], st));
     CK(launch_pdl(k_cseg_scatter<V, MODE>, nb, thr, 0, st, db, p.n, p.ctg, p.qs, p.qe, d->cnt2, d->qrank, d->cseg_off,
                   d->cseg_mid, d->plan_tot, seg_cap, item_cap, (void *)d->csegs));
@@ -1104,17 +1108,18 @@ int enqueue_count_t(igdb_dev *d, const igdb_dev::Pending &p)
         // the descriptors of k_count_rank (with the windows of the items): one thread per item, 8 or 32 per tile
         // a database of small tiles: most of them by k_windows_small, the others (many segments) by the general kernel
         const bool sparse = d->db_groups < 6 * (int64_t)d->T;       // groups per tile on average
+        const int64_t nt = std::max<int64_t>(thi - tlo, 1);
         if (sparse) {
-            CK(launch_pdl(k_windows_small, (unsigned)((d->T + 127) / 128), 128, 0, st, db, (const int4 *)d->tplan,
+            CK(launch_pdl(k_windows_small, (unsigned)((nt + 127) / 128), 128, 0, st, db, (const int4 *)d->tplan,
                           (const uint32_t *)(const void *)d->csegs, (const unsigned long long *)d->plan_tot, seg_cap,
-                          item_cap, d->items2));
+                          item_cap, d->items2, (uint32_t)tlo, (uint32_t)thi));
             d->launches += 1;
         }
         const int64_t tpc = sparse ? 256 : 8;                       // tiles per CTA and turn
-        const unsigned wgrid = (unsigned)std::min<int64_t>(((int64_t)d->T + tpc - 1) / tpc, (int64_t)d->sm_count * 64);
+        const unsigned wgrid = (unsigned)std::min<int64_t>((nt + tpc - 1) / tpc, (int64_t)d->sm_count * 64);
         CK(launch_pdl(k_windows<32>, wgrid, 256, 0, st, db, (const int4 *)d->tplan,
                       (const uint32_t *)(const void *)d->csegs, (const unsigned long long *)d->plan_tot, seg_cap, item_cap,
-                      d->items2, sparse ? 1 : 0));
+                      d->items2, sparse ? 1 : 0, (uint32_t)tlo, (uint32_t)thi));
         d->launches += 1;
     }
     if (stages) CK(cudaEventRecord(d->stage_ev[3], st));
@@ -1243,8 +1248,19 @@ void igdb_dev_last_plan(const igdb_dev *d, int64_t out[4])
     for (int k = 0; k < 4; ++k) out[k] = d->last_plan[k];
 }
 
+int igdb_dev_count_device_tiles(igdb_dev *d, int64_t n, const int32_t *d_ctg, const int32_t *d_qs, const int32_t *d_qe,
+                                int mode_v, int32_t v, uint64_t *d_hits, void *stream, int32_t tile_lo, int32_t tile_hi);
+
 int igdb_dev_count_device(igdb_dev *d, int64_t n, const int32_t *d_ctg, const int32_t *d_qs, const int32_t *d_qe,
                           int mode_v, int32_t v, uint64_t *d_hits, void *stream)
+{
+    return igdb_dev_count_device_tiles(d, n, d_ctg, d_qs, d_qe, mode_v, v, d_hits, stream, 0, 0x7fffffff);
+}
+
+// the same when the caller knows that no query touches a tile outside [tile_lo, tile_hi) (a shard of a multi-GPU
+// search): the plan and the descriptors then cover that range only
+int igdb_dev_count_device_tiles(igdb_dev *d, int64_t n, const int32_t *d_ctg, const int32_t *d_qs, const int32_t *d_qe,
+                                int mode_v, int32_t v, uint64_t *d_hits, void *stream, int32_t tile_lo, int32_t tile_hi)
 {
     g_err[0] = 0;
     CK(cudaSetDevice(d->device));
@@ -1258,6 +1274,7 @@ int igdb_dev_count_device(igdb_dev *d, int64_t n, const int32_t *d_ctg, const in
         p.mode_v = mode_v != 0, p.n = std::min(BATCH, n - a);
         p.ctg = d_ctg + a, p.qs = d_qs + a, p.qe = d_qe + a, p.v = v;
         p.hits = (unsigned long long *)d_hits, p.st = st;
+        p.tile_lo = tile_lo, p.tile_hi = tile_hi;
         p.mode = count_mode_for(d, p.mode_v, p.v);
         if (enqueue_count(d, p)) return -1;
         if (a + BATCH < n) {                        // the scratch buffers are reused by the next chunk

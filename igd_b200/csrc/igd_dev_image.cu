@@ -249,7 +249,7 @@ void igdb_dev_destroy(igdb_dev *d)
     void *ptrs[] = {d->tiles, d->d_toff, d->start, d->end, d->idx, d->value, d->tbase, d->q_ctg,
                     d->q_qs, d->q_qe, d->tile_cnt, d->tile_off, d->nseg, d->qseg_off, d->bsum, d->segs,
                     d->seg_hits, d->seg_out_off, d->d_hits, d->cnt2, d->cseg_off, d->cseg_mid,
-                    d->plan_agg, d->plan_flag, d->plan_tot, d->csegs, d->items, d->items2, d->tplan, d->qrank, d->rb, d->rv, d->gbase, d->gk,
+                    d->plan_agg, d->plan_flag, d->plan_tot, d->csegs, d->items, d->items2, d->tplan, d->qrank, d->shard_scratch, d->rb, d->rv, d->gbase, d->gk,
                     d->ctg_names, d->ctg_slots, d->d_text, d->d_starts};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -357,7 +357,7 @@ static int create_impl(igdb_dev *d, const int32_t *ntile, const int32_t *ncnt)
     CK(cudaMemset(d->tile_cnt, 0, ((size_t)d->T + 1) * 4));
     CK(cudaMemset(d->cnt2, 0, ((size_t)2 * d->T + 2) * 4));
     CK(cudaMemset(d->plan_flag, 0, (size_t)4 * d->sm_count * 4));
-    d->plan_grid = 0;                           // chosen at the first count batch (igd_dev_count.cu)
+    d->plan_grid = d->plan_grid_max = 0;        // chosen at the first count batch (igd_dev_count.cu)
     return 0;
 }
 

@@ -327,7 +327,7 @@ struct igdb_dev {
     uint32_t *cnt2 = nullptr, *cseg_off = nullptr, *cseg_mid = nullptr;   // [2T+2],[T+1],[T+1]
     PlanAgg *plan_agg = nullptr;                            // [plan_grid] per-CTA aggregates of k_plan
     uint32_t *plan_flag = nullptr, plan_epoch = 0;          // [plan_grid] = epoch of the batch that published
-    int plan_grid = 0;
+    int plan_grid = 0, plan_grid_max = 0;
     unsigned long long *plan_tot = nullptr;                 // device {segments, items} of the batch in flight
     volatile unsigned long long *h_plan = nullptr;          // pinned copy of plan_tot
     cudaEvent_t plan_ev = nullptr, plan_done = nullptr;
@@ -339,6 +339,7 @@ struct igdb_dev {
     int4 *items = nullptr;
     int64_t item_cap = 0;
     int4 *items2 = nullptr;                                 // k_count_rank's descriptors (2 x int4 per item), k_windows
+    unsigned long long *shard_scratch = nullptr;            // igd_dev_shard.cu: per-destination counters
     uint32_t *qrank = nullptr;                              // [n] per query: rank of its first-bin segment (k_cseg_count)
     int64_t qrank_cap = 0;
     int4 *tplan = nullptr;                                  // [2T] per tile {first segment, first later-bin one, end, first item}, {off8, n, ts, first group}
@@ -354,6 +355,7 @@ struct igdb_dev {
         int32_t v = 0;
         unsigned long long *hits = nullptr;
         cudaStream_t st = nullptr;
+        int32_t tile_lo = 0, tile_hi = 0x7fffffff;          // no query touches a tile outside [tile_lo, tile_hi)
     } pending;
     DbView view() const
     {

@@ -273,6 +273,37 @@ int igd_b200_count_device(igd_b200_t *h, int64_t n, const int32_t *d_ctg, const 
     return igdb_dev_count_device(h->dev, n, d_ctg, d_qs, d_qe, filter_on(h, v), v, d_hits, stream);
 }
 
+int igd_b200_count_device_tiles(igd_b200_t *h, int64_t n, const int32_t *d_ctg, const int32_t *d_qs,
+                                const int32_t *d_qe, int32_t v, uint64_t *d_hits, void *stream, int32_t tile_lo,
+                                int32_t tile_hi)
+{
+    g_err[0] = 0;
+    return igdb_dev_count_device_tiles(h->dev, n, d_ctg, d_qs, d_qe, filter_on(h, v), v, d_hits, stream, tile_lo, tile_hi);
+}
+
+/* K8: the shard plan of a multi-GPU search, on the device (igd_dev_shard.cu) */
+int igd_b200_shard_cost(igd_b200_t *h, int64_t n, const int32_t *d_ctg, const int32_t *d_qs, const int32_t *d_qe,
+                        uint64_t *d_tile_cost, void *stream)
+{
+    g_err[0] = 0;
+    return igdb_dev_shard_cost(h->dev, n, d_ctg, d_qs, d_qe, d_tile_cost, stream);
+}
+
+int igd_b200_shard_cuts(igd_b200_t *h, const uint64_t *d_tile_cost, int32_t n_parts, int32_t *d_cuts, void *stream)
+{
+    g_err[0] = 0;
+    return igdb_dev_shard_cuts(h->dev, d_tile_cost, n_parts, d_cuts, stream);
+}
+
+int igd_b200_shard_partition(igd_b200_t *h, int64_t n, const int32_t *d_ctg, const int32_t *d_qs, const int32_t *d_qe,
+                             const int32_t *d_cuts, int32_t n_parts, int32_t *d_out_ctg, int32_t *d_out_qs,
+                             int32_t *d_out_qe, int64_t *d_part_off, int32_t *d_reach, void *stream)
+{
+    g_err[0] = 0;
+    return igdb_dev_shard_partition(h->dev, n, d_ctg, d_qs, d_qe, d_cuts, n_parts, d_out_ctg, d_out_qs, d_out_qe,
+                                    d_part_off, d_reach, stream);
+}
+
 int igd_b200_count_device_finish(igd_b200_t *h)
 {
     g_err[0] = 0;

@@ -39,6 +39,55 @@ def tile_bounds(hdr: dict, n_parts: int) -> list[int]:
     return [int(x) for x in np.maximum.accumulate(b)]
 
 
+class DeviceSharder:
+    """K8 on the device (igd_dev_shard.cu through the C-ABI): every rank holds ANY 1/N of the query set in HBM;
+    ``shard`` leaves it holding the queries whose first bin lies in its contiguous tile range, the ranges balanced
+    by the prefix sum of estimated scan bytes.  Collectives (NCCL over NVLink): one all-reduce of the per-tile cost
+    (nTiles + 1 words), one of the per-destination reach, and the all-to-all of the queries themselves."""
+
+    def __init__(self, engine, dev, group=None):
+        import torch
+        import torch.distributed as dist
+        self.e, self.dev, self.group, self.dist, self.torch = engine, torch.device(dev), group, dist, torch
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.T = int(engine.ntiles)
+        self.cost = torch.zeros(self.T + 1, dtype=torch.int64, device=self.dev)
+        self.cuts = torch.zeros(self.world + 1, dtype=torch.int32, device=self.dev)
+        self.off = torch.zeros(self.world + 1, dtype=torch.int64, device=self.dev)
+        self.reach = torch.zeros(self.world, dtype=torch.int32, device=self.dev)
+        self.buf = None
+
+    def shard(self, d_ctg, d_qs, d_qe):
+        """torch int32 device tensors (this rank's slice, any order) -> (ctg, qs, qe, tile_lo, tile_hi) of its shard.
+        Runs on the current torch stream."""
+        torch, dist, W = self.torch, self.dist, self.world
+        n = int(d_ctg.shape[0])
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        self.cost.zero_()
+        self.e.shard_cost(n, d_ctg.data_ptr(), d_qs.data_ptr(), d_qe.data_ptr(), self.cost.data_ptr(), st)
+        dist.all_reduce(self.cost, group=self.group)
+        self.e.shard_cuts(self.cost.data_ptr(), W, self.cuts.data_ptr(), st)
+        if self.buf is None or self.buf.shape[1] < n:
+            self.buf = torch.empty((3, max(n, 1)), dtype=torch.int32, device=self.dev)
+        o = self.buf
+        self.e.shard_partition(n, d_ctg.data_ptr(), d_qs.data_ptr(), d_qe.data_ptr(), self.cuts.data_ptr(), W,
+                               o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), self.off.data_ptr(),
+                               self.reach.data_ptr(), st)
+        dist.all_reduce(self.reach, op=dist.ReduceOp.MAX, group=self.group)
+        send = (self.off[1:] - self.off[:-1]).contiguous()
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=self.group)
+        meta = torch.cat([send, recv, self.cuts.long(), self.reach.long()]).cpu().tolist()     # the one host sync
+        send_l, recv_l = meta[:W], meta[W:2 * W]
+        cuts, reach = meta[2 * W:3 * W + 1], meta[3 * W + 1:]
+        m = int(sum(recv_l))
+        out = torch.empty((3, max(m, 1)), dtype=torch.int32, device=self.dev)
+        for k in range(3):
+            dist.all_to_all_single(out[k, :m], o[k, :n], recv_l, send_l, group=self.group)
+        lo = int(cuts[self.rank])
+        return out[0, :m], out[1, :m], out[2, :m], lo, max(int(reach[self.rank]), lo)
+
+
 class ShardedSearch:
     def __init__(self, engine, hdr: dict, group=None, comm_device="cpu"):
         import torch.distributed as dist

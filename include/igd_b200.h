@@ -84,6 +84,33 @@ int64_t igd_b200_count(igd_b200_t *h, int64_t n, const int32_t *ctg, const int32
 int igd_b200_count_device(igd_b200_t *h, int64_t n, const int32_t *d_ctg, const int32_t *d_qs,
                           const int32_t *d_qe, int32_t v, uint64_t *d_hits, void *stream);
 int igd_b200_count_device_finish(igd_b200_t *h);
+/* The same when the caller knows that no query touches a tile outside [tile_lo, tile_hi) (global tile indices,
+ * contig-major: tile j of contig c is (sum of nTile of the contigs before c) + j) -- a shard of a multi-GPU search,
+ * below: the batch's plan then covers that range only. */
+int igd_b200_count_device_tiles(igd_b200_t *h, int64_t n, const int32_t *d_ctg, const int32_t *d_qs,
+                                const int32_t *d_qe, int32_t v, uint64_t *d_hits, void *stream, int32_t tile_lo,
+                                int32_t tile_hi);
+
+/* Sharding a query set over the ranks of a multi-GPU search, on the device (the reference is one process and has
+ * no counterpart; it implements north_star's "the sorted query set is sharded into contiguous ranges balanced by a
+ * prefix sum of estimated per-query scan bytes").  Rank r takes the queries whose FIRST bin is a tile of
+ * [cuts[r], cuts[r+1]): contiguous ranges of the (contig, start) order at tile granularity.  All pointers are
+ * device pointers; the calls are enqueued on `stream`.
+ *   shard_cost       d_tile_cost[nTiles + 1] += the estimated scan bytes of every query (the figure of
+ *                    igd_b200_query_cost), at its first tile's slot; slot nTiles takes the queries that reach no tile
+ *   (sum the slots over the ranks, e.g. one NCCL all-reduce)
+ *   shard_cuts       d_cuts[n_parts + 1]: cuts[0] = 0, cuts[n_parts] = nTiles, cuts[p] = the first tile at which the
+ *                    running sum reaches p / n_parts of the total
+ *   shard_partition  the n queries reordered by destination rank into d_out_*; d_part_off[n_parts + 1] (int64) = where
+ *                    each destination's run starts; d_reach[n_parts] (int32, may be NULL) = one past the last tile the
+ *                    queries of a destination touch (the tile_hi of igd_b200_count_device_tiles)
+ * n_parts <= 64.  0 on success. */
+int igd_b200_shard_cost(igd_b200_t *h, int64_t n, const int32_t *d_ctg, const int32_t *d_qs, const int32_t *d_qe,
+                        uint64_t *d_tile_cost, void *stream);
+int igd_b200_shard_cuts(igd_b200_t *h, const uint64_t *d_tile_cost, int32_t n_parts, int32_t *d_cuts, void *stream);
+int igd_b200_shard_partition(igd_b200_t *h, int64_t n, const int32_t *d_ctg, const int32_t *d_qs, const int32_t *d_qe,
+                             const int32_t *d_cuts, int32_t n_parts, int32_t *d_out_ctg, int32_t *d_out_qs,
+                             int32_t *d_out_qe, int64_t *d_part_off, int32_t *d_reach, void *stream);
 
 /* -f: the overlaps themselves, in the reference's order (get_overlaps_f1, src/igd_search.c:537-620:
  * per query, bin n1 from the last start < qe downwards, then later bins ascending).

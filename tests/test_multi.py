@@ -75,6 +75,28 @@ def _rank_main(rank, world, port, igd_path, out_dir, engine_kind):
     for v in (0, 500):
         out[f"hits_v{v}"] = sh.count(ctg, qs, qe, v)
         out[f"map_v{v}"] = sh.hitsmap(v)
+    if comm != "cpu":
+        # K8 on the devices: every rank starts from a 1/world slice of the unsorted queries (multi.DeviceSharder)
+        import torch
+        n = len(ctg)
+        a, b = n * rank // world, n * (rank + 1) // world
+        dev = torch.device(comm)
+        st = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(st):
+            shd = multi.DeviceSharder(eng, dev)
+            t = [torch.from_numpy(np.ascontiguousarray(x[a:b])).to(dev) for x in (ctg, qs, qe)]
+            c, s_, e_, lo, hi = shd.shard(*t)
+            hits = torch.zeros(eng.nfiles, dtype=torch.int64, device=dev)
+            if c.shape[0]:
+                eng.count_device_tiles(int(c.shape[0]), c.data_ptr(), s_.data_ptr(), e_.data_ptr(), 0, hits.data_ptr(),
+                                       st.cuda_stream, lo, hi)
+                eng.count_device_finish()
+            dist.all_reduce(hits)
+            got = torch.tensor([int(c.shape[0])], dtype=torch.int64, device=dev)
+            dist.all_reduce(got)
+            assert int(got.item()) == n
+            out["hits_sharded_on_device"] = hits.cpu().numpy()
+        st.synchronize()
     r = sh.full(ctg, qs, qe, dst=world - 1)
     assert (r is None) == (rank != world - 1)
     if r is not None:
@@ -100,6 +122,8 @@ def _check(workdir, world, engine_kind):
         for r in res:
             assert np.array_equal(r[f"hits_v{v}"], want)
             assert np.array_equal(r[f"map_v{v}"], wmap)
+            if v == 0 and "hits_sharded_on_device" in r.files:
+                assert np.array_equal(r["hits_sharded_on_device"], want)
     qoff, s, e, f = ref.full(ctg, qs, qe)                           # single engine, input order
     last = res[world - 1]
     assert np.array_equal(last["qoff"], qoff)
