@@ -476,6 +476,103 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_modes(args):
+    """--mode f | m: the other two sharded modes of the path as bench lines (cfg-4 / cfg-5 shapes on the cfg-2
+    database by default).  f: `value` = queries/s with queries and lists resident in HBM (igd_b200_full_device; N > 1:
+    shards, gather and order restoration on the devices), `e2e` = host arrays in, host lists out.  m: `value` =
+    overlapping record pairs/s of the whole self-join (N > 1: tile ranges + one uint32 all-reduce), matrix to the host
+    inside `e2e`."""
+    import torch
+    import torch.distributed as dist
+    from igd_b200 import api, multi
+    world, rank, local = env_int("WORLD_SIZE", 1), env_int("RANK", 0), env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the igd_b200 search path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    barrier = (lambda: dist.barrier()) if world > 1 else (lambda: None)
+    wl = args.workload if args.workload != "cfg3" else "cfg2"
+    if rank == 0:
+        workloads.build_db(wl, args.workdir)
+    barrier()
+    path = os.path.join(args.workdir, wl + ".igd")
+    igd = api.IGD(path, device=local)
+    q = workloads.queries(wl, args.queries or workloads.CONFIGS[wl]["n_queries"])
+    ctg = igd.resolve_names(synth.HG38_NAMES)[q.ctg].astype(np.int32)
+    qs, qe, n = q.start, q.end, len(q)
+    sh = multi.ShardedSearch(igd, workloads.read_igd_header(path), comm_device=str(dev)) if world > 1 else None
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = igd.launch_count()
+    side = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(side)
+
+    def timed(fn, steps, warm):
+        for _ in range(warm):
+            fn()
+        barrier()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(steps):
+            barrier()
+            t0 = time.perf_counter()
+            out = fn()
+            torch.cuda.synchronize()
+            ts.append(time.perf_counter() - t0)
+        return float(np.mean(ts)), out
+
+    steps, warm = args.steps, max(args.warmup, 3)
+    if args.mode == "f":
+        d = [torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (ctg, qs, qe)]
+        if world == 1:
+            dev_s, tot = timed(lambda: igd.full_device(n, d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), side.cuda_stream)[0],
+                               steps, warm)
+            e2e_s, res = timed(lambda: igd.full(ctg, qs, qe, copy=False), steps, warm)
+            total = int(res[0][-1])
+            assert tot == total
+        else:
+            e2e_s, res = timed(lambda: sh.full(ctg, qs, qe, dst=0), steps, warm)
+            dev_s, total = e2e_s, (int(res[0][-1]) if rank == 0 else 0)
+        unit, metric, units = UNIT, METRIC, n
+        extra = {"overlaps_per_step": total, "list_bytes_per_step": 12 * total}
+        d2h = 12 * total + 8 * (n + 1)
+    else:
+        v = 0
+        if world == 1:
+            m = torch.zeros(igd.nfiles * igd.nfiles, dtype=torch.int32, device=dev)
+            dev_s, _ = timed(lambda: igd.hitsmap_tiles_device(v, 0, igd.ntiles, m.data_ptr(), side.cuda_stream), steps, warm)
+            e2e_s, hm = timed(lambda: igd.hitsmap(v), steps, warm)
+        else:
+            e2e_s, hm = timed(lambda: sh.hitsmap(v), steps, warm)
+            dev_s = e2e_s
+        pairs = int(hm.astype(np.uint64).sum())
+        unit, metric, units = "record pairs/s", "hitsmap_pairs_per_s", pairs
+        extra = {"pairs_per_step": pairs, "matrix_bytes": 4 * igd.nfiles * igd.nfiles}
+        d2h = 4 * igd.nfiles * igd.nfiles
+    if world > 1:
+        t = torch.tensor([dev_s, e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_s, e2e_s = (float(x) for x in t.cpu())
+    sampler.stop_flag = True
+    sampler.join()
+    if rank == 0:
+        c = workloads.CONFIGS[wl]
+        emit({"metric": metric, "mode": "-" + args.mode, "value": units / dev_s, "unit": unit, "n_gpus": world, "steps": steps,
+              "warmup": warm, "ms_per_step": dev_s * 1e3, "higher_is_better": True, "scaling": "strong",
+              "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+              "config": {"workload": f"{wl}: {c['n_files']} files x {c['per_file']} intervals (hg38, -b 14), "
+                                     + (f"{n} queries, -f" if args.mode == "f" else "-m (database self-join)"),
+                         "timing": "host clock around the call + device synchronize (the calls end with the result in place)"},
+              "e2e": {"value": units / e2e_s, "unit": unit, "ms_per_step": e2e_s * 1e3,
+                      "h2d_bytes_per_step": 12 * n if args.mode == "f" else 0, "d2h_bytes_per_step": d2h},
+              "gpu_launches": int(igd.launch_count() - launches0), "clocks": sampler.summary(), **extra})
+    igd.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_reference(args):
     """The reference's own CPU implementation on the box's host cores (rank 0 only)."""
     if env_int("RANK", 0) != 0:
@@ -565,11 +662,15 @@ def main():
     ap.add_argument("--workdir", default=os.environ.get("IGD_B200_WORKDIR", default_workdir()))
     ap.add_argument("--cpu-sample", type=int, default=1_000_000, help="queries in the one-core cpu_baseline sample")
     ap.add_argument("--no-parity", action="store_true", help="skip the whole-set oracle run (profiling runs)")
+    ap.add_argument("--mode", default="count", choices=["count", "f", "m"],
+                    help="count (the contract line); f / m: the other sharded modes, on cfg2 unless --workload says otherwise")
     ap.add_argument("--ref-sample", type=int, default=1_000_000, help="queries per step of --impl reference")
     args = ap.parse_args()
     claim_stdout()
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode != "count":
+        run_modes(args)
     else:
         run_ours(args)
 

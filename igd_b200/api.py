@@ -107,10 +107,14 @@ def load_library():
     L.igd_b200_hitlist_free.argtypes = [C.POINTER(_HitList)]
     L.igd_b200_full_device.restype = C.c_int64
     L.igd_b200_full_device.argtypes = [vp, C.c_int64, vp, vp, vp, vp, C.POINTER(vp), C.POINTER(vp)]
+    L.igd_b200_full_restore.restype = C.c_int
+    L.igd_b200_full_restore.argtypes = [vp, C.c_int64, vp, vp, vp, C.c_int64, vp, vp, vp]
     L.igd_b200_hitsmap.restype = C.c_int64
     L.igd_b200_hitsmap.argtypes = [vp, C.c_int32, _u32p]
     L.igd_b200_hitsmap_tiles.restype = C.c_int64
     L.igd_b200_hitsmap_tiles.argtypes = [vp, C.c_int32, C.c_int64, C.c_int64, _u32p]
+    L.igd_b200_hitsmap_tiles_device.restype = C.c_int
+    L.igd_b200_hitsmap_tiles_device.argtypes = [vp, C.c_int32, C.c_int64, C.c_int64, vp, vp]
     L.igd_b200_read_bed.restype = C.POINTER(_Queries)
     L.igd_b200_read_bed.argtypes = [C.c_char_p]
     L.igd_b200_queries_free.argtypes = [C.POINTER(_Queries)]
@@ -481,6 +485,13 @@ class IGD:
             raise IGDError(last_error())
         return int(t), qoff.value or 0, lst.value or 0
 
+    def full_restore(self, n: int, d_order: int, d_cnt: int, d_lists_sorted: int, total: int, d_query_off: int,
+                     d_lists_out: int, stream: int = 0) -> None:
+        """multi-GPU -f, gathering rank: shard-ordered lists -> the caller's query order (device pointers)."""
+        if self._L.igd_b200_full_restore(self._need(), n, d_order, d_cnt, d_lists_sorted, total, d_query_off,
+                                         d_lists_out, stream):
+            raise IGDError(last_error())
+
     # -- -m / -s -----------------------------------------------------------------------------------------
     def hitsmap(self, v: int = 0, tiles: tuple[int, int] | None = None) -> np.ndarray:
         """-m; ``tiles=(lo, hi)`` restricts the self-join to that range of global tile indices (one rank's
@@ -493,6 +504,11 @@ class IGD:
         if r < 0:
             raise IGDError(last_error())
         return hm
+
+    def hitsmap_tiles_device(self, v: int, tile_lo: int, tile_hi: int, d_map: int, stream: int = 0) -> None:
+        """-m over a tile range into a uint32[nFiles*nFiles] matrix in device memory (incremented), enqueued."""
+        if self._L.igd_b200_hitsmap_tiles_device(self._need(), int(v), int(tile_lo), int(tile_hi), d_map, stream):
+            raise IGDError(last_error())
 
     def seq_overlaps(self, ctg, qs, qe):
         """seq_overlaps for a batch: (query_off[n+1], structured array of overlap_t records in scan order)"""

@@ -83,6 +83,11 @@ int64_t igdb_dev_full_host(igdb_dev *d, int64_t n, const int32_t *ctg, const int
 int64_t igdb_dev_full_device(igdb_dev *d, int64_t n, const int32_t *d_ctg, const int32_t *d_qs, const int32_t *d_qe,
                              void *stream, int64_t **d_query_off, int32_t **d_lists);
 
+/* multi-GPU -f on the gathering rank: the lists of the concatenated shards (d_cnt[i] overlaps of their i-th query,
+ * which is query d_order[i] of the caller's array) rearranged into the caller's query order */
+int igdb_dev_full_restore(igdb_dev *d, int64_t n, const int64_t *d_order, const int64_t *d_cnt, const int32_t *d_lists_sorted,
+                          int64_t total, int64_t *d_query_off, int32_t *d_lists_out, void *stream);
+
 /* -s: n queries grouped by query-file chrom (grp[] ascending) and start-sorted inside a group; grp_nq[g] =
  * queries of group g; acc[nfiles] = sum of matched similarities per file */
 int igdb_dev_seqpare(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_t *qs, const int32_t *qe,
@@ -93,8 +98,11 @@ int igdb_dev_seqpare(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_t *
 int64_t igdb_dev_seq_pairs_host(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_t *qs, const int32_t *qe,
                                 int64_t **query_off, void **pairs);
 
-/* -m restricted to the tiles [t0, t1) (global tile indices, contig-major): hitmap[nfiles*nfiles] is incremented */
-int64_t igdb_dev_hitsmap_host(igdb_dev *d, int32_t v, int64_t t0, int64_t t1, uint32_t *hitmap);
+/* -m restricted to the tiles [t0, t1) (global tile indices, contig-major): hitmap[nfiles*nfiles] is incremented.
+ * filter != 0: only pairs whose two values both exceed v (getMap_v, src/igd_search.c:856,872, for any v). */
+int64_t igdb_dev_hitsmap_host(igdb_dev *d, int filter, int32_t v, int64_t t0, int64_t t1, uint32_t *hitmap);
+/* the same into a DEVICE matrix, enqueued on stream (what a rank of a multi-GPU -m runs before the all-reduce) */
+int igdb_dev_hitsmap_device(igdb_dev *d, int filter, int32_t v, int64_t t0, int64_t t1, uint32_t *d_map, void *stream);
 
 /* Sharding a query set over n_parts ranks on the device (igd_dev_shard.cu): cost adds every query's estimated scan
  * bytes to its first tile's slot of d_tile_cost[nTiles + 1]; cuts turns the (all-reduced) slots into n_parts + 1

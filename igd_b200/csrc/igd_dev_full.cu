@@ -191,14 +191,63 @@ int build_segments(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_t *qs
 }
 
 
+// ---- multi-GPU -f: the lists of the (sorted) shards back into the order of the caller's query array ----------
+// order[i] = index, in the caller's array, of the i-th query of the concatenated shards; cnt[i] = its overlaps.
+__global__ void k_restore_counts(int64_t n, const long long *__restrict__ order, const long long *__restrict__ cnt,
+                                 unsigned long long *__restrict__ cnt_orig)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) cnt_orig[order[i]] = (unsigned long long)cnt[i];
+}
+
+// one warp per query: its run of overlaps from where the shards left it to where the caller's order wants it
+__global__ void __launch_bounds__(256) k_restore_copy(int64_t n, const long long *__restrict__ order,
+                                                       const unsigned long long *__restrict__ soff,
+                                                       const unsigned long long *__restrict__ qoff, int64_t total,
+                                                       const int32_t *__restrict__ in, int32_t *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += nw) {
+        const unsigned long long src = soff[i], c = soff[i + 1] - src, dst = qoff[order[i]];
+        for (unsigned long long k = lane; k < c; k += 32) {
+            out[dst + k] = in[src + k];
+            out[total + dst + k] = in[total + src + k];
+            out[2 * total + dst + k] = in[2 * total + src + k];
+        }
+    }
+}
+
 }  // namespace
 
 // -f core: the queries are in d->q_ctg/q_qs/q_qe (device).  Leaves query_off[n+1] (overlaps of query q are
 // [query_off[q], query_off[q+1])) in qoff and the overlaps, SoA, in out: start[total] | end[total] | file[total]
 // (| index within the tile [total] if with_g), in the reference's order.  Returns total.
+// qoff and out come from two buffers that the handle keeps and grows (a cudaMalloc / cudaFree of the lists per call
+// cost as much as the kernels): they are valid until the next -f / -s call on the handle.
+static int pool_take(void **pool, size_t *cap, size_t bytes, DevBuf &b)
+{
+    if (bytes > *cap) {
+        if (*pool) CK(cudaFree(*pool));
+        *pool = nullptr, *cap = 0;
+        const size_t want = bytes + (bytes >> 3) + 4096;
+        if (cudaMalloc(pool, want) != cudaSuccess) {
+            cudaGetLastError();
+            *pool = nullptr;
+            return -1;
+        }
+        *cap = want;
+    }
+    b.p = *pool, b.owned = false;
+    return 0;
+}
+
 int64_t igdb::full_device(igdb_dev *d, int64_t n, cudaStream_t st, bool with_g, DevBuf &qoff, DevBuf &out)
 {
-    if (qoff.alloc(((size_t)n + 1) * 8)) return -1;
+    if (pool_take(&d->fp_qoff, &d->fp_qoff_cap, ((size_t)n + 1) * 8, qoff)) {
+        snprintf(g_err, sizeof g_err, "-f: query offsets do not fit in device memory");
+        return -1;
+    }
     uint32_t nsegs = 0;
     if (build_segments(d, n, d->q_ctg, d->q_qs, d->q_qe, st, &nsegs)) return -1;
     if (nsegs == 0) {
@@ -223,9 +272,7 @@ int64_t igdb::full_device(igdb_dev *d, int64_t n, cudaStream_t st, bool with_g, 
     k_query_off<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(n, d->qseg_off, d->seg_out_off, qoff.as<int64_t>());
     d->launches += 1;
     if (total > 0) {
-        if (cudaMalloc(&out.p, (size_t)total * (with_g ? 16 : 12)) != cudaSuccess) {
-            out.p = nullptr;
-            cudaGetLastError();
+        if (pool_take(&d->fp_out, &d->fp_out_cap, (size_t)total * (with_g ? 16 : 12), out)) {
             snprintf(g_err, sizeof g_err, "%lld overlaps do not fit in device memory", (long long)total);
             return -1;
         }
@@ -317,13 +364,11 @@ int64_t igdb_dev_full_device(igdb_dev *d, int64_t n, const int32_t *d_ctg, const
         return -1;
     }
     cudaStream_t st = stream ? (cudaStream_t)stream : d->stream;
-    if (d->dres_qoff) cudaFree(d->dres_qoff);
-    if (d->dres_out) cudaFree(d->dres_out);
     d->dres_qoff = d->dres_out = nullptr;
     DevBuf qoff, out;
     int64_t total = 0;
     if (n == 0 || d->T == 0) {
-        if (qoff.alloc(((size_t)n + 1) * 8)) return -1;
+        if (pool_take(&d->fp_qoff, &d->fp_qoff_cap, ((size_t)n + 1) * 8, qoff)) return -1;
         CK(cudaMemsetAsync(qoff.p, 0, ((size_t)n + 1) * 8, st));
     } else {
         if (ensure_query_cap(d, n)) return -1;
@@ -334,11 +379,44 @@ int64_t igdb_dev_full_device(igdb_dev *d, int64_t n, const int32_t *d_ctg, const
         if (total < 0) return -1;
     }
     CK(cudaStreamSynchronize(st));
-    d->dres_qoff = qoff.p, d->dres_out = out.p;
-    qoff.p = out.p = nullptr;                                   // ownership moves to the handle
+    d->dres_qoff = qoff.p, d->dres_out = out.p;                 // (memory of the handle's pools)
     *d_query_off = (int64_t *)d->dres_qoff;
     *d_lists = (int32_t *)d->dres_out;
     return total;
+}
+
+// multi-GPU -f, on the gathering rank: d_lists_sorted = start | end | file [total] of the queries in SHARD order,
+// d_cnt[i] = overlaps of the i-th of them, d_order[i] = its index in the caller's query array.  Writes the caller's
+// order: d_query_off[n + 1] and d_lists_out (same layout).  Enqueued on stream; temporaries are stream-ordered.
+int igdb_dev_full_restore(igdb_dev *d, int64_t n, const int64_t *d_order, const int64_t *d_cnt, const int32_t *d_lists_sorted,
+                          int64_t total, int64_t *d_query_off, int32_t *d_lists_out, void *stream)
+{
+    g_err[0] = 0;
+    CK(cudaSetDevice(d->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : d->stream;
+    if (n <= 0) {
+        CK(cudaMemsetAsync(d_query_off, 0, 8, st));
+        return 0;
+    }
+    DevBuf corig, soff;
+    if (corig.alloc(((size_t)n + 1) * 8) || soff.alloc(((size_t)n + 1) * 8)) return -1;
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    k_restore_counts<<<nb, 256, 0, st>>>(n, (const long long *)d_order, (const long long *)d_cnt,
+                                        corig.as<unsigned long long>());
+    if (exclusive_scan<unsigned long long, unsigned long long>(d, corig.as<unsigned long long>(),
+                                                                (unsigned long long *)d_query_off, n, st))
+        return -1;
+    if (exclusive_scan<unsigned long long, unsigned long long>(d, (const unsigned long long *)d_cnt,
+                                                                soff.as<unsigned long long>(), n, st))
+        return -1;
+    if (total > 0)
+        k_restore_copy<<<d->sm_count * 8, 256, 0, st>>>(n, (const long long *)d_order, soff.as<unsigned long long>(),
+                                                        (const unsigned long long *)d_query_off, total, d_lists_sorted,
+                                                        d_lists_out);
+    d->launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));                              // the temporaries go out of scope
+    return 0;
 }
 
 }  // extern "C"

@@ -249,7 +249,7 @@ void igdb_dev_destroy(igdb_dev *d)
     void *ptrs[] = {d->tiles, d->d_toff, d->start, d->end, d->idx, d->value, d->tbase, d->q_ctg,
                     d->q_qs, d->q_qe, d->tile_cnt, d->tile_off, d->nseg, d->qseg_off, d->bsum, d->segs,
                     d->seg_hits, d->seg_out_off, d->d_hits, d->cnt2, d->cseg_off, d->cseg_mid,
-                    d->plan_agg, d->plan_flag, d->plan_tot, d->csegs, d->items, d->items2, d->tplan, d->qrank, d->shard_scratch, d->rb, d->rv, d->gbase, d->gk,
+                    d->plan_agg, d->plan_flag, d->plan_tot, d->csegs, d->items, d->items2, d->tplan, d->qrank, d->shard_scratch, d->hm_rt, d->hm_pmax, d->hm_half, d->hm_map, d->hm_n, d->hm_frec, d->hm_fstart, d->seq_pool, d->seq_tab, d->rb, d->rv, d->gbase, d->gk,
                     d->ctg_names, d->ctg_slots, d->d_text, d->d_starts};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -258,8 +258,8 @@ void igdb_dev_destroy(igdb_dev *d)
         if (d->up_ev[k]) cudaEventDestroy(d->up_ev[k]);
     }
     if (d->bad_idx) cudaFree(d->bad_idx);
-    if (d->dres_qoff) cudaFree(d->dres_qoff);
-    if (d->dres_out) cudaFree(d->dres_out);
+    if (d->fp_qoff) cudaFree(d->fp_qoff);
+    if (d->fp_out) cudaFree(d->fp_out);
     if (d->pinned) cudaFreeHost(d->pinned);
     if (d->arena) cudaFreeHost(d->arena);
     if (d->h_scalar) cudaFreeHost(d->h_scalar);

@@ -291,7 +291,9 @@ struct igdb_dev {
     uint32_t ctg_mask = 0;
     void *arena = nullptr;                  // pinned host arena of the -f result lists
     size_t arena_cap = 0;
-    void *dres_qoff = nullptr, *dres_out = nullptr;     // device-resident -f result of the last igdb_dev_full_device
+    void *dres_qoff = nullptr, *dres_out = nullptr;     // device-resident -f result of the last igdb_dev_full_device (in the pools)
+    void *fp_qoff = nullptr, *fp_out = nullptr;         // -f: pooled query_off / list buffers (grown to the high-water mark)
+    size_t fp_qoff_cap = 0, fp_out_cap = 0;
     char *d_text = nullptr;                 // query text staging
     size_t d_text_cap = 0;
     uint32_t *d_starts = nullptr;                           // ingest: offsets of the candidate lines of a chunk
@@ -339,6 +341,15 @@ struct igdb_dev {
     int4 *items = nullptr;
     int64_t item_cap = 0;
     int4 *items2 = nullptr;                                 // k_count_rank's descriptors (2 x int4 per item), k_windows
+    int32_t *hm_rt = nullptr, *hm_pmax = nullptr;           // -m: per record slot its tile / the prefix maximum of end (made once)
+    uint32_t *hm_half = nullptr, *hm_map = nullptr;         // -m: half matrix (zero between calls), result matrix of the host entry
+    size_t hm_map_cells = 0;
+    uint32_t *hm_frec = nullptr;                            // -m: the record slots grouped by file
+    unsigned long long *hm_fstart = nullptr;                // -m: [nfiles + 1] where each file's slots start in hm_frec
+    bool hm_rows = false;                                   // -m: a file's row of counters fits in shared memory
+    unsigned long long *hm_n = nullptr;                     // -m: pairs counted by the last call
+    void *seq_pool = nullptr, *seq_tab = nullptr;           // -s: the temporaries of a call, the matching tables
+    size_t seq_pool_cap = 0, seq_tab_cap = 0;
     unsigned long long *shard_scratch = nullptr;            // igd_dev_shard.cu: per-destination counters
     uint32_t *qrank = nullptr;                              // [n] per query: rank of its first-bin segment (k_cseg_count)
     int64_t qrank_cap = 0;
@@ -413,9 +424,10 @@ int exclusive_scan(igdb_dev *d, const Tin *in, Tout *out, int64_t n, cudaStream_
     return 0;
 }
 
-struct DevBuf {                             // cudaFree on scope exit
+struct DevBuf {                             // cudaFree on scope exit (unless the memory belongs to a pool of the handle)
     void *p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
+    bool owned = true;
+    ~DevBuf() { if (p && owned) cudaFree(p); }
     template <class T>
     T *as() const { return (T *)p; }
     int alloc(size_t bytes)

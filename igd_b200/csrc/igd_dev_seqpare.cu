@@ -1,7 +1,15 @@
 // igd_b200 CUDA layer -- -s: Seqpare similarity.
 #include "igd_dev_impl.cuh"
 
-#include <cub/device/device_radix_sort.cuh>
+#include "igd_dev_sort.cuh"
+
+namespace {
+struct Slice {                              // a piece of the handle's pooled temporaries
+    void *p = nullptr;
+    template <class T>
+    T *as() const { return (T *)p; }
+};
+}  // namespace
 
 namespace {
 
@@ -314,11 +322,32 @@ int igdb_dev_seqpare(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_t *
         snprintf(g_err, sizeof g_err, "Seqpare: %lld candidate pairs exceed one pass (2^31)", (long long)total);
         return -1;
     }
-    DevBuf b_grp, b_gnq, b_key, b_key2, b_val, b_val2, b_row, b_col, b_tmp;
-    if (b_grp.alloc((size_t)n * 4) || b_gnq.alloc((size_t)ngroups * 4) || b_key.alloc((size_t)total * 8) ||
-        b_key2.alloc((size_t)total * 8) || b_val.alloc((size_t)total * 4) || b_val2.alloc((size_t)total * 4) ||
-        b_row.alloc((size_t)total * 4) || b_col.alloc((size_t)total * 8))
-        return -1;
+    // the temporaries of a call come out of ONE buffer that the handle keeps (grown to the high-water mark): a
+    // cudaMalloc / cudaFree pair per multi-GB array and call was a sizeable part of the call
+    Slice b_grp, b_gnq, b_key, b_key2, b_val, b_val2, b_row, b_col, b_tmp, b_pstart, b_tsize, b_toff, b_pick, b_npick, b_acc;
+    {
+        struct Want { Slice *s; size_t bytes; };
+        const Want want[] = {{&b_grp, (size_t)n * 4}, {&b_gnq, (size_t)ngroups * 4}, {&b_key, (size_t)total * 8},
+                             {&b_key2, (size_t)total * 8}, {&b_val, (size_t)total * 4}, {&b_val2, (size_t)total * 4},
+                             {&b_row, (size_t)total * 4}, {&b_col, (size_t)total * 8},
+                             {&b_tmp, radix_sort_tmp_bytes(total)}, {&b_pstart, (size_t)(nprob + 1) * 8},
+                             {&b_tsize, (size_t)(nprob + 1) * 4}, {&b_toff, (size_t)(nprob + 1) * 8},
+                             {&b_pick, (size_t)total * 4}, {&b_npick, (size_t)nprob * 4}, {&b_acc, (size_t)d->nfiles * 8}};
+        size_t need = 0;
+        for (const Want &w : want) need += (w.bytes + 255) & ~(size_t)255;
+        if (need > d->seq_pool_cap) {
+            if (d->seq_pool) CK(cudaFree(d->seq_pool));
+            d->seq_pool = nullptr, d->seq_pool_cap = 0;
+            if (cudaMalloc(&d->seq_pool, need + (need >> 3)) != cudaSuccess) {
+                cudaGetLastError();
+                snprintf(g_err, sizeof g_err, "Seqpare: %zu bytes of temporaries do not fit in device memory", need);
+                return -1;
+            }
+            d->seq_pool_cap = need + (need >> 3);
+        }
+        char *p = (char *)d->seq_pool;
+        for (const Want &w : want) w.s->p = p, p += (w.bytes + 255) & ~(size_t)255;
+    }
     CK(cudaMemcpyAsync(b_grp.p, grp, (size_t)n * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(b_gnq.p, grp_nq, (size_t)ngroups * 4, cudaMemcpyHostToDevice, st));
     const int32_t *o = out.as<int32_t>();
@@ -328,23 +357,15 @@ int igdb_dev_seqpare(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_t *
         b_col.as<unsigned long long>());
     CK(cudaGetLastError());
     mark(2);
-    // stable LSD radix sort (CUB, a library primitive) on the used key bits only
+    // stable LSD radix sort (igd_dev_sort.cuh) on the used key bits only
     int end_bit = 32;
     while (end_bit < 64 && (nprob >> (end_bit - 32)) != 0) ++end_bit;
-    size_t tmp_bytes = 0;
-    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, b_key.as<unsigned long long>(),
-                                       b_key2.as<unsigned long long>(), b_val.as<uint32_t>(), b_val2.as<uint32_t>(),
-                                       (int)total, 0, end_bit, st));
-    if (b_tmp.alloc(tmp_bytes)) return -1;
-    CK(cub::DeviceRadixSort::SortPairs(b_tmp.p, tmp_bytes, b_key.as<unsigned long long>(),
-                                       b_key2.as<unsigned long long>(), b_val.as<uint32_t>(), b_val2.as<uint32_t>(),
-                                       (int)total, 0, end_bit, st));
-    mark(3);
-    DevBuf b_pstart, b_tsize, b_toff, b_tab, b_pick, b_npick, b_acc;
-    if (b_pstart.alloc((size_t)(nprob + 1) * 8) || b_tsize.alloc((size_t)(nprob + 1) * 4) ||
-        b_toff.alloc((size_t)(nprob + 1) * 8) || b_pick.alloc((size_t)total * 4) ||
-        b_npick.alloc((size_t)nprob * 4) || b_acc.alloc((size_t)d->nfiles * 8))
+    int where = 0;
+    if (radix_sort_pairs(d, b_key.as<unsigned long long>(), b_key2.as<unsigned long long>(), b_val.as<uint32_t>(),
+                         b_val2.as<uint32_t>(), total, end_bit, b_tmp.p, st, &where))
         return -1;
+    if (where == 0) std::swap(b_key.p, b_key2.p), std::swap(b_val.p, b_val2.p);     // sorted pairs: (b_key2, b_val2)
+    mark(3);
     k_seq_ranges<<<(unsigned)((nprob + 1 + 255) / 256), 256, 0, st>>>(
         b_key2.as<unsigned long long>(), total, nprob, d->nfiles, b_gnq.as<int32_t>(), b_pstart.as<int64_t>(),
         b_tsize.as<uint32_t>());
@@ -356,10 +377,18 @@ int igdb_dev_seqpare(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_t *
     CK(cudaMemcpyAsync(h_total, b_toff.as<unsigned long long>() + nprob, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const size_t slots = (size_t)*h_total;
-    if (b_tab.alloc(slots * 8)) {
-        snprintf(g_err, sizeof g_err, "Seqpare: matching tables (%zu slots) do not fit in device memory", slots);
-        return -1;
+    Slice b_tab;
+    if (slots * 8 + 16 > d->seq_tab_cap) {
+        if (d->seq_tab) CK(cudaFree(d->seq_tab));
+        d->seq_tab = nullptr, d->seq_tab_cap = 0;
+        if (cudaMalloc(&d->seq_tab, slots * 8 + (slots >> 1) + 16) != cudaSuccess) {
+            cudaGetLastError();
+            snprintf(g_err, sizeof g_err, "Seqpare: matching tables (%zu slots) do not fit in device memory", slots);
+            return -1;
+        }
+        d->seq_tab_cap = slots * 8 + (slots >> 1) + 16;
     }
+    b_tab.p = d->seq_tab;
     CK(cudaMemsetAsync(b_tab.p, 0, std::max<size_t>(slots * 8, 16), st));
     static const bool thread_sweep = getenv("IGD_B200_SEQ_THREAD_SWEEP") != nullptr;    // the one-thread-per-problem form
     if (thread_sweep)

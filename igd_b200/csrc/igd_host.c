@@ -372,16 +372,31 @@ void igd_b200_hitlist_free(igd_b200_hitlist *l)
     memset(l, 0, sizeof *l);
 }
 
+int igd_b200_full_restore(igd_b200_t *h, int64_t n, const int64_t *d_order, const int64_t *d_cnt,
+                          const int32_t *d_lists_sorted, int64_t total, int64_t *d_query_off, int32_t *d_lists_out,
+                          void *stream)
+{
+    g_err[0] = 0;
+    return igdb_dev_full_restore(h->dev, n, d_order, d_cnt, d_lists_sorted, total, d_query_off, d_lists_out, stream);
+}
+
 int64_t igd_b200_hitsmap(igd_b200_t *h, int32_t v, uint32_t *hitmap)
 {
     g_err[0] = 0;
-    return igdb_dev_hitsmap_host(h->dev, v, 0, h->ntiles, hitmap);
+    return igdb_dev_hitsmap_host(h->dev, v > 0, v, 0, h->ntiles, hitmap);
 }
 
 int64_t igd_b200_hitsmap_tiles(igd_b200_t *h, int32_t v, int64_t tile_lo, int64_t tile_hi, uint32_t *hitmap)
 {
     g_err[0] = 0;
-    return igdb_dev_hitsmap_host(h->dev, v, tile_lo, tile_hi, hitmap);
+    return igdb_dev_hitsmap_host(h->dev, v > 0, v, tile_lo, tile_hi, hitmap);
+}
+
+int igd_b200_hitsmap_tiles_device(igd_b200_t *h, int32_t v, int64_t tile_lo, int64_t tile_hi, uint32_t *d_hitmap,
+                                  void *stream)
+{
+    g_err[0] = 0;
+    return igdb_dev_hitsmap_device(h->dev, v > 0, v, tile_lo, tile_hi, d_hitmap, stream);
 }
 
 /* estimated scan bytes per query: 4 * sum of nCnt over the bins the query touches */
@@ -682,15 +697,20 @@ int64_t getOverlaps_v(char *qFile, int64_t *hits, int32_t v)
 int32_t get_overlaps0(char *chrm, int32_t qs, int32_t qe, int64_t *hits) { return get_overlaps(chrm, qs, qe, hits); }
 int64_t getOverlaps0(char *qFile, int64_t *hits) { return getOverlaps(qFile, hits); }
 
-int64_t getMap(uint32_t **hitmap) { return getMap_v(hitmap, 0); }
+static int64_t get_map(uint32_t **hitmap, int filter, int32_t v);
+int64_t getMap(uint32_t **hitmap) { return get_map(hitmap, 0, 0); }
+/* getMap_v keeps the pairs whose two values exceed v for ANY v (src/igd_search.c:856,872); it is the CLI that calls
+ * it only when v > 0 (:1000) */
+int64_t getMap_v(uint32_t **hitmap, int32_t v) { return get_map(hitmap, 1, v); }
 
-int64_t getMap_v(uint32_t **hitmap, int32_t v)
+static int64_t get_map(uint32_t **hitmap, int filter, int32_t v)
 {
     if (!g_current) return 0;
     int32_t n = g_current->nfiles;
     uint32_t *dense = malloc(sizeof(uint32_t) * (size_t)n * (size_t)n + 4);
     for (int i = 0; i < n; i++) memcpy(dense + (size_t)i * n, hitmap[i], sizeof(uint32_t) * (size_t)n);
-    int64_t r = igd_b200_hitsmap(g_current, v, dense);
+    g_err[0] = 0;
+    int64_t r = igdb_dev_hitsmap_host(g_current->dev, filter, v, 0, g_current->ntiles, dense);
     if (r >= 0)
         for (int i = 0; i < n; i++) memcpy(hitmap[i], dense + (size_t)i * n, sizeof(uint32_t) * (size_t)n);
     free(dense);

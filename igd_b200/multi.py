@@ -226,23 +226,30 @@ class ShardedSearch:
             if sizes[r]:
                 dist.recv(p, r, group=self.group)
             cnts.append(c), pays.append(p)
-        cnt_sorted, pay = torch.cat(cnts), torch.cat(pays, dim=1)
-        nq = len(order)
-        pos = torch.empty(nq, dtype=torch.int64, device=dev)
-        pos[torch.from_numpy(order).to(dev)] = torch.arange(nq, device=dev)
-        soff = torch.cumsum(cnt_sorted, 0) - cnt_sorted
-        cnt_orig = cnt_sorted[pos]
-        qoff_o = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(cnt_orig, 0)])
-        tot = int(qoff_o[-1].item())
-        src = (torch.repeat_interleave(soff[pos] - qoff_o[:-1], cnt_orig, output_size=tot)
-               + torch.arange(tot, device=dev))
-        out = pay[:, src]
+        cnt_sorted, pay = torch.cat(cnts).contiguous(), torch.cat(pays, dim=1).contiguous()
+        nq, tot = len(order), int(pay.shape[1])
+        # the caller's query order, restored by the library's kernels (igd_b200_full_restore)
+        d_order = torch.from_numpy(np.ascontiguousarray(order, np.int64)).to(dev)
+        qoff_o = torch.empty(nq + 1, dtype=torch.int64, device=dev)
+        out = torch.empty((3, max(tot, 1)), dtype=torch.int32, device=dev)
+        self.e.full_restore(nq, d_order.data_ptr(), cnt_sorted.data_ptr(), pay.data_ptr(), tot, qoff_o.data_ptr(),
+                            out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+        out = out[:, :tot]
         return (qoff_o.cpu().numpy(), out[0].cpu().numpy(), out[1].cpu().numpy(), out[2].cpu().numpy())
 
     # ---- -m --------------------------------------------------------------------------------------
     def hitsmap(self, v: int = 0) -> np.ndarray:
         """uint32[nFiles, nFiles] of the whole database, on every rank."""
         b = tile_bounds(self.hdr, self.world)
+        if str(self.dev) != "cpu" and hasattr(self.e, "hitsmap_tiles_device"):
+            # the rank's matrix stays in HBM: self-join of its tiles, all-reduce (NCCL over NVLink), one D2H
+            import torch
+            nf = self.e.nfiles
+            t = torch.zeros(nf * nf, dtype=torch.int32, device=self.dev)
+            self.e.hitsmap_tiles_device(v, b[self.rank], b[self.rank + 1], t.data_ptr(),
+                                        torch.cuda.current_stream(self.dev).cuda_stream)
+            self.dist.all_reduce(t, group=self.group)
+            return t.cpu().numpy().view(np.uint32).reshape(nf, nf)
         hm = self.e.hitsmap(v, tiles=(b[self.rank], b[self.rank + 1]))
         t = self._t(hm.view(np.int32))
         self.dist.all_reduce(t, group=self.group)

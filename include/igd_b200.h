@@ -137,6 +137,15 @@ void igd_b200_hitlist_free(igd_b200_hitlist *l);
 int64_t igd_b200_full_device(igd_b200_t *h, int64_t n, const int32_t *d_ctg, const int32_t *d_qs, const int32_t *d_qe,
                              void *stream, int64_t **d_query_off, int32_t **d_lists);
 
+/* The last step of a multi-GPU -f, on the rank that gathers (device pointers, enqueued on `stream`, returns when
+ * done): d_lists_sorted = start[total] | end[total] | file[total] of the queries in the order the shards were
+ * gathered, d_cnt[i] = overlaps of the i-th of them, d_order[i] = its index in the caller's query array.  Writes the
+ * lists in the CALLER's query order -- each query's run unchanged, i.e. in the reference's order -- into d_lists_out
+ * (same layout) and d_query_off[n + 1]: what a single-GPU igd_b200_full_device returns for the unsharded input. */
+int igd_b200_full_restore(igd_b200_t *h, int64_t n, const int64_t *d_order, const int64_t *d_cnt,
+                          const int32_t *d_lists_sorted, int64_t total, int64_t *d_query_off, int32_t *d_lists_out,
+                          void *stream);
+
 /* -m: getMap / getMap_v (src/igd_search.c:772-886) as one dense row-major uint32[nFiles*nFiles],
  * incremented (wraps mod 2^32 like the reference).  v > 0 selects the strict `value > v` filter.
  * Returns the number of pairs counted or a negative error code. */
@@ -146,6 +155,10 @@ int64_t igd_b200_hitsmap(igd_b200_t *h, int32_t v, uint32_t *hitmap);
  * disjoint ranges add up to the whole map: this is what one rank of a multi-GPU -m computes before the
  * uint32 allreduce. */
 int64_t igd_b200_hitsmap_tiles(igd_b200_t *h, int32_t v, int64_t tile_lo, int64_t tile_hi, uint32_t *hitmap);
+/* the same into a matrix in DEVICE memory (uint32[nFiles*nFiles], incremented), enqueued on `stream`: the matrix of a
+ * rank stays in HBM through the all-reduce of a multi-GPU -m and comes to the host once.  0 or a negative error code. */
+int igd_b200_hitsmap_tiles_device(igd_b200_t *h, int32_t v, int64_t tile_lo, int64_t tile_hi, uint32_t *d_hitmap,
+                                  void *stream);
 
 /* Query ingest: the accepted lines of a BED(.gz) file by parse_bed's rule (src/igd_base.c:53-72: >= 3
  * tab-separated fields, contig starts with "chr", shorter than 40 chars, end > 0), read like
