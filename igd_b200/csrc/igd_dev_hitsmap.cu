@@ -18,16 +18,18 @@ namespace {
 // against the reference's committed hitsmaps.)
 // work items = padded record slots, so a flat grid-stride loop over P records needs no extra index.
 // ------------------------------------------------------------------------------------------------
+// Eight lanes per record, four records per warp: with the early exit a record looks at 32-64 predecessors, not at
+// hundreds (a whole warp per record spent 204 warp instructions per record, most of its lanes idle).
 template <bool V>
 __global__ void __launch_bounds__(256) k_hitsmap(DbView db, const int32_t *__restrict__ rec_tile,
                                                   const int32_t *__restrict__ pmax, int64_t r0, int64_t P, int32_t v,
                                                   uint32_t *__restrict__ half, uint32_t *__restrict__ hitmap,
                                                   unsigned long long *__restrict__ nols)
 {
-    const int lane = threadIdx.x & 31;
-    const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int lane = threadIdx.x & 31, l8 = lane & 7;
+    const int64_t nsub = (int64_t)gridDim.x * (blockDim.x >> 3);
     unsigned long long mine = 0;
-    for (int64_t r = r0 + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < P; r += nw) {
+    for (int64_t r = r0 + (int64_t)blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3); r < P; r += nsub) {
         const int t = __ldg(&rec_tile[r]);
         if (t < 0) continue;                                 // pad slot
         const int4 tm = __ldg(reinterpret_cast<const int4 *>(&db.tiles[t]));
@@ -38,16 +40,16 @@ __global__ void __launch_bounds__(256) k_hitsmap(DbView db, const int32_t *__res
         const int qs = __ldg(&db.start[r]);
         const int jj = __ldg(&db.idx[r]);
         uint32_t *row = half + (int64_t)jj * db.nfiles;
-        if (lane == 0) {                                     // (j, j)
+        if (l8 == 0) {                                       // (j, j)
             atomicAdd(&hitmap[(int64_t)jj * db.nfiles + jj], 1u);
             ++mine;
         }
-        // the records before j in start order, nearest first, 128 at a time; pmax[i] = the largest end among
+        // the records before j in start order, nearest first, 32 at a time; pmax[i] = the largest end among
         // records 0 .. i of the tile (k_hm_prepare), so once pmax[b1 - 1] <= start_j nobody in [0, b1) reaches j --
         // the reference's own early exit (src/igd_search.c:797-800), which leaves the result as it is
         for (int b1 = j; b1 > 0;) {
             if (__ldg(&pmax[off + b1 - 1]) <= qs) break;
-            const int b0 = (b1 - 1) & ~127, b = b0 + lane * 4;
+            const int b0 = (b1 - 1) & ~31, b = b0 + l8 * 4;
             if (b < b1) {
                 const int4 e = ldg4(db.end + off + b);
                 int4 val = make_int4(0, 0, 0, 0);

@@ -220,8 +220,9 @@ int igdb_dev_count_text(igdb_dev *d, const char *text, size_t len, int mode_v, i
         CK(cudaMalloc((void **)&d->d_starts, (tcap / 2 + 2) * sizeof(uint32_t)));
         d->d_text_cap = tcap;
     }
-    // an accepted line has at least 8 characters ("chr" + tab + digit + tab + digit + newline)
-    const int64_t cap = (int64_t)(len / 8 + 1);
+    // an accepted line has at least 6 characters before its newline: "chr", tab, an EMPTY start field (atol("") = 0 is
+    // accepted by parse_bed), tab, one digit -- and the last line of a chunk may come without a newline
+    const int64_t cap = (int64_t)(len / 6 + 2);
     if (ensure_query_cap(d, cap)) return -1;
     CK(cudaMemcpyAsync(d->d_text, text, len, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(d->plan_tot + 4, 0, 8, st));
@@ -239,7 +240,11 @@ int igdb_dev_count_text(igdb_dev *d, const char *text, size_t len, int mode_v, i
     unsigned long long *h_n = (unsigned long long *)(d->h_scalar + 4);
     CK(cudaMemcpyAsync(h_n, d->plan_tot + 4, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    const int64_t n = (int64_t)std::min<unsigned long long>(*h_n, (unsigned long long)cap);
+    if (*h_n > (unsigned long long)cap) {                   // cannot happen (see cap); never drop queries silently
+        snprintf(g_err, sizeof g_err, "count_text: %llu accepted lines in %zu bytes", *h_n, len);
+        return -1;
+    }
+    const int64_t n = (int64_t)*h_n;
     if (n_queries) *n_queries = n;
     if (n == 0) return 0;
     igdb_dev::Pending p;

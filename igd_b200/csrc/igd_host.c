@@ -57,12 +57,16 @@ static int read_index_tsv(igd_b200_t *h, const char *igd_path)
     int cap = 64, n = 0;
     h->fname = malloc(sizeof(char *) * cap);
     h->fnr = malloc(sizeof(int32_t) * cap);
+    if (!h->fname || !h->fnr) { fclose(f); set_err("%s: out of memory reading the file table", igd_path); return -1; }
     if (!fgets(buf, sizeof buf, f)) { fclose(f); h->nfiles = 0; return 0; }
     while (fgets(buf, sizeof buf, f)) {
         if (n == cap) {
             cap *= 2;
-            h->fname = realloc(h->fname, sizeof(char *) * cap);
-            h->fnr = realloc(h->fnr, sizeof(int32_t) * cap);
+            char **fn = realloc(h->fname, sizeof(char *) * cap);
+            int32_t *fr = realloc(h->fnr, sizeof(int32_t) * cap);
+            if (fn) h->fname = fn;
+            if (fr) h->fnr = fr;
+            if (!fn || !fr) { fclose(f); h->nfiles = n; set_err("%s: out of memory reading the file table", igd_path); return -1; }
         }
         char *save = NULL;
         strtok_r(buf, "\t", &save);
@@ -132,9 +136,12 @@ igd_b200_t *igd_b200_open(const char *igd_path, int device)
     if (h->gtype != 0 && h->gtype != 1) { set_err("%s: unknown gType (0 and 1 are supported)", igd_path); goto fail; }
     if (h->nbp <= 0 || h->nctg < 0) { set_err("%s: corrupt header", igd_path); goto fail; }
     int32_t m = h->nctg;
-    h->ntile = malloc(sizeof(int32_t) * (size_t)(m + 1));
+    /* the table sizes come from the file: a corrupt header must end in an error, not in a NULL dereference */
+    h->ntile = malloc(sizeof(int32_t) * ((size_t)m + 1));
+    h->tbase = malloc(sizeof(int64_t) * ((size_t)m + 1));
+    h->cname = malloc(40 * ((size_t)m + 1));
+    if (!h->ntile || !h->tbase || !h->cname) { set_err("%s: corrupt header", igd_path); goto fail; }
     if (m && fread(h->ntile, 4, m, f) != (size_t)m) { set_err("%s: truncated header", igd_path); goto fail; }
-    h->tbase = malloc(sizeof(int64_t) * (size_t)(m + 1));
     h->tbase[0] = 0;
     for (int i = 0; i < m; i++) {
         if (h->ntile[i] < 0) { set_err("%s: corrupt header", igd_path); goto fail; }
@@ -143,11 +150,11 @@ igd_b200_t *igd_b200_open(const char *igd_path, int device)
     h->ntiles = h->tbase[m];
     if (h->ntiles >= 0x7fffffff) { set_err("%s: too many tiles", igd_path); goto fail; }
     h->ncnt = malloc(sizeof(int32_t) * (size_t)(h->ntiles + 1));
+    if (!h->ncnt) { set_err("%s: corrupt header", igd_path); goto fail; }
     if (h->ntiles && fread(h->ncnt, 4, h->ntiles, f) != (size_t)h->ntiles) {
         set_err("%s: truncated header", igd_path);
         goto fail;
     }
-    h->cname = malloc(40 * (size_t)(m + 1));
     if (m && fread(h->cname, 40, m, f) != (size_t)m) { set_err("%s: truncated header", igd_path); goto fail; }
     for (int i = 0; i < m; i++) h->cname[i][39] = 0;
     for (int64_t t = 0; t < h->ntiles; t++) {
@@ -607,7 +614,11 @@ static int64_t search_mode(igd_b200_t *h, const char *qFile, int mode_v, int32_t
         size_t use = have;                          /* end of the last whole line */
         if (!eof) {
             while (use > from && buf[use - 1] != '\n') use--;
-            if (use == from && have - from == CH) { /* no newline in a full chunk: its head is the line */
+            /* no newline in a full chunk: the chunk is the HEAD of one line and stands for it, the rest is skipped up
+             * to its newline.  Same hits as the reference as long as the line's first three fields end inside these
+             * 16 MiB (the reference itself sees lines through kseq's growing buffer and has no such limit; a contig
+             * name of < 40 characters and two integers do). */
+            if (use == from && have - from == CH) {
                 use = have;
                 skipping = 1;
             }

@@ -35,7 +35,13 @@ int64_t igdb_dev_full_host(igdb_dev *d, int64_t n, const int32_t *a, const int32
 int64_t igdb_dev_full_device(igdb_dev *d, int64_t n, const int32_t *a, const int32_t *b, const int32_t *c, void *st, int64_t **q, int32_t **l) { (void)d; (void)n; (void)a; (void)b; (void)c; (void)st; (void)q; (void)l; return -1; }
 int64_t igdb_dev_seq_pairs_host(igdb_dev *d, int64_t n, const int32_t *a, const int32_t *b, const int32_t *c, int64_t **q, void **p) { (void)d; (void)n; (void)a; (void)b; (void)c; (void)q; (void)p; return -1; }
 int igdb_dev_seqpare(igdb_dev *d, int64_t n, const int32_t *a, const int32_t *b, const int32_t *c, const int32_t *g, int32_t ng, const int32_t *gn, double *acc) { (void)d; (void)n; (void)a; (void)b; (void)c; (void)g; (void)ng; (void)gn; (void)acc; return -1; }
-int64_t igdb_dev_hitsmap_host(igdb_dev *d, int32_t v, int64_t t0, int64_t t1, uint32_t *h) { (void)d; (void)v; (void)t0; (void)t1; (void)h; return -1; }
+int64_t igdb_dev_hitsmap_host(igdb_dev *d, int f, int32_t v, int64_t t0, int64_t t1, uint32_t *h) { (void)d; (void)f; (void)v; (void)t0; (void)t1; (void)h; return -1; }
+int igdb_dev_hitsmap_device(igdb_dev *d, int f, int32_t v, int64_t t0, int64_t t1, uint32_t *h, void *s) { (void)d; (void)f; (void)v; (void)t0; (void)t1; (void)h; (void)s; return -1; }
+int igdb_dev_count_device_tiles(igdb_dev *d, int64_t n, const int32_t *a, const int32_t *b, const int32_t *c, int m, int32_t v, uint64_t *h, void *s, int32_t lo, int32_t hi) { (void)d; (void)n; (void)a; (void)b; (void)c; (void)m; (void)v; (void)h; (void)s; (void)lo; (void)hi; return -1; }
+int igdb_dev_shard_cost(igdb_dev *d, int64_t n, const int32_t *a, const int32_t *b, const int32_t *c, uint64_t *t, void *s) { (void)d; (void)n; (void)a; (void)b; (void)c; (void)t; (void)s; return -1; }
+int igdb_dev_shard_cuts(igdb_dev *d, const uint64_t *t, int32_t n, int32_t *c, void *s) { (void)d; (void)t; (void)n; (void)c; (void)s; return -1; }
+int igdb_dev_shard_partition(igdb_dev *d, int64_t n, const int32_t *a, const int32_t *b, const int32_t *c, const int32_t *cu, int32_t np, int32_t *oa, int32_t *ob, int32_t *oc, int64_t *off, int32_t *r, void *s) { (void)d; (void)n; (void)a; (void)b; (void)c; (void)cu; (void)np; (void)oa; (void)ob; (void)oc; (void)off; (void)r; (void)s; return -1; }
+int igdb_dev_full_restore(igdb_dev *d, int64_t n, const int64_t *o, const int64_t *c, const int32_t *l, int64_t t, int64_t *q, int32_t *lo, void *s) { (void)d; (void)n; (void)o; (void)c; (void)l; (void)t; (void)q; (void)lo; (void)s; return -1; }
 igdb_reducer *igdb_reducer_create(int d, int r, int w, int32_t n) { (void)d; (void)r; (void)w; (void)n; return NULL; }
 int igdb_reducer_handle(igdb_reducer *r, void *o) { (void)r; (void)o; return -1; }
 int igdb_reducer_connect(igdb_reducer *r, const void *h) { (void)r; (void)h; return -1; }

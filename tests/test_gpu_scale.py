@@ -100,3 +100,72 @@ def test_count_properties_at_1m_queries(handles):
     v1, _ = g.count(ctg, q.start, q.end, 1)
     v1001, _ = g.count(ctg, q.start, q.end, 1001)
     assert v1001.sum() == 0 and v1.sum() >= whole.sum() * 0.99
+
+
+# ---- parity at the benchmark's own scale -------------------------------------------------------------------------
+# cfg3s = BASELINE config 3's per-tile statistics (10,000 files, ~5,500 records and ~53 queries per tile, lognormal
+# lengths) on a genome 1/10 the size: every tile is DENSE (21 groups of 256 entries, START and END halves), most
+# chunks hold > 32 segments, windows go through the home-group kernel.  cfg2 = BASELINE config 2 itself.
+
+def _big_dir(tmp_path_factory, name):
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.statvfs("/dev/shm").f_bavail * os.statvfs("/dev/shm").f_frsize > (8 << 30) else None
+    return str(tmp_path_factory.mktemp(name)) if base is None else __import__("tempfile").mkdtemp(prefix=f"igd_{name}_", dir=base)
+
+
+def _oracle_count_all_cores(o, ctg, qs, qe, v):
+    from concurrent.futures import ThreadPoolExecutor
+    cores = os.cpu_count() or 1
+    cuts = [len(ctg) * k // (2 * cores) for k in range(2 * cores + 1)]
+    with ThreadPoolExecutor(cores) as ex:
+        parts = list(ex.map(lambda ab: o.count(np.ascontiguousarray(ctg[ab[0]:ab[1]]), np.ascontiguousarray(qs[ab[0]:ab[1]]),
+                                               np.ascontiguousarray(qe[ab[0]:ab[1]]), v)[0], zip(cuts[:-1], cuts[1:])))
+    return np.sum(parts, axis=0).astype(np.int64)
+
+
+def test_cfg3s_count_against_the_oracle(tmp_path_factory):
+    import shutil
+    from igd_b200 import api
+    from oracle import oracle as O
+    d = _big_dir(tmp_path_factory, "cfg3s")
+    try:
+        path = workloads.build_db("cfg3s", d)
+        q = workloads.queries("cfg3s")
+        with api.IGD(path) as g:
+            assert g.nrecords / g.ntiles > 2048            # dense tiles
+            names = [n for n in synth.HG38_NAMES]
+            ctg = g.resolve_names(names)[q.ctg].astype(np.int32)
+            o = O.OracleDB(path)
+            for v in (0, 500):
+                want = _oracle_count_all_cores(o, ctg, q.start, q.end, v)
+                got, n = g.count(ctg, q.start, q.end, v)
+                assert np.array_equal(got, want), v
+                assert want.sum() > 1e8
+            plan = g.last_plan()
+            assert plan["items"] > 2 * g.ntiles * 20       # START and END items of ~21 groups per tile
+            o.close()
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+def test_cfg2_hitsmap_tile_ranges_against_the_oracle(tmp_path_factory):
+    """-m at BASELINE config 2 scale (1,905 files, 1e8 records): the oracle's self-join of the whole database takes
+    minutes, so the comparison is on sampled tile ranges (tiles are independent: src/igd_search.c:780-782), plus
+    the symmetry of the whole map and its total."""
+    import shutil
+    from igd_b200 import api
+    from oracle import oracle as O
+    d = _big_dir(tmp_path_factory, "cfg2")
+    try:
+        path = workloads.build_db("cfg2", d)
+        with api.IGD(path) as g:
+            o = O.OracleDB(path)
+            T = g.ntiles
+            for v in (0, 500):
+                for lo in (0, T // 3, T - 150):
+                    hi = min(T, lo + 150)
+                    assert np.array_equal(g.hitsmap(v, tiles=(lo, hi)), o.hitsmap(v, tiles=(lo, hi))), (v, lo)
+            whole = g.hitsmap(0)
+            assert np.array_equal(whole, whole.T) and int(whole.sum(dtype=np.uint64)) > 3_000_000_000
+            o.close()
+    finally:
+        shutil.rmtree(d, ignore_errors=True)

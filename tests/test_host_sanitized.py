@@ -29,6 +29,8 @@ def probe(workdir):
                         os.path.join(ROOT, "igd_b200", "csrc", "igd_host.c"), "-lz", "-lpthread"],
                        capture_output=True, text=True)
     if r.returncode != 0:
+        # a missing sanitizer runtime is a reason to skip; a stub that no longer matches igd_dev.h is a failure
+        assert "sanitize" in r.stderr or "asan" in r.stderr.lower() or "cannot find" in r.stderr, r.stderr[-1500:]
         pytest.skip("no sanitizer runtime here: " + r.stderr[-300:])
     return exe
 
