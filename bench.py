@@ -352,6 +352,8 @@ def run_ours(args):
     total_ms = float(sum(step_ms))
 
     # ---- timed: end to end from host buffers --------------------------------------------------------
+    # one call at a time: H2D, then the search, then D2H, each step on its own (N = 1: also reported as
+    # e2e.single_call, the latency of one igd_b200_count)
     for _ in range(3):
         hits_e2e = step_e2e()
     barrier()
@@ -365,6 +367,30 @@ def run_ours(args):
         hits_e2e = step_e2e()
         e2e_s += time.perf_counter() - t0
     e2e_split = igd.last_timing() if world == 1 else None
+    # N = 1: the same K batches as a STREAM through igd_b200_count_submit / _wait -- two in flight, the H2D of batch
+    # k + 1 under the search of batch k; every step still copies its 12 B per query in and its hits[] out inside the
+    # timed region (no L2 flush between the steps: each one reads several GB of the database, far beyond the L2)
+    e2e_single = None
+    if world == 1:
+        def stream_steps(k):
+            outs = [np.zeros(igd.nfiles, np.int64) for _ in range(k)]
+            ptrs = (n_local, h_ctg.data_ptr(), h_qs.data_ptr(), h_qe.data_ptr(), 0)
+            igd.count_submit(0, *ptrs)
+            for j in range(1, k):
+                igd.count_submit(j & 1, *ptrs)
+                igd.count_wait((j - 1) & 1, outs[j - 1])
+            igd.count_wait((k - 1) & 1, outs[k - 1])
+            return outs
+        stream_steps(3)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        outs = stream_steps(args.steps)
+        e2e_stream_s = time.perf_counter() - t0
+        for o in outs:
+            assert np.array_equal(o, hits_e2e), "pipelined and one-call end-to-end paths disagree"
+        e2e_single = {"value": n_total / (e2e_s / args.steps), "unit": UNIT, "ms_per_step": e2e_s / args.steps * 1e3,
+                      "api": "igd_b200_count (one synchronous call per step)"}
+        e2e_s = e2e_stream_s
     sampler.stop_flag = True
     sampler.join()
 
@@ -435,13 +461,15 @@ def run_ours(args):
                     "parity_seconds": orc.get("full_seconds"), "parity_cores": orc.get("full_cores")},
             "e2e": {"value": n_total / (e2e_s / args.steps), "unit": UNIT, "ms_per_step": e2e_s / args.steps * 1e3,
                     "h2d_bytes_per_step": 12 * n_total, "d2h_bytes_per_step": 8 * igd.nfiles * world,
+                    "single_call": e2e_single,
                     "device_split_ms_last_step": e2e_split,
                     # the H2D leg runs at whatever the box's PCIe path gives at that moment: 16 to 54 GB/s were
                     # seen on this pool's boxes for the same pinned buffers (profiles/microbench/h2d_*.py)
                     "h2d_gbs_last_step": (12 * n_total / (e2e_split["h2d_ms"] * 1e-3) / 1e9
                                           if e2e_split and e2e_split["h2d_ms"] > 0 else None),
                     "cpu_binding": numa,
-                    "api": "igd_b200_count (C-ABI, host buffers)" if world == 1 else
+                    "api": "igd_b200_count_submit / igd_b200_count_wait (C-ABI, pinned host buffers; the K steps as a stream, "
+                           "two batches in flight: H2D of step k + 1 under the search of step k)" if world == 1 else
                            "pinned H2D of this rank's 1/N of the queries + igd_b200_shard_* (cost, all-reduce, cuts, partition, "
                            "all-to-all) + igd_b200_count_device_tiles + hits[] exchange + D2H"},
             "file_ingest": None if file_s is None else {

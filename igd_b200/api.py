@@ -90,6 +90,10 @@ def load_library():
     L.create_iGD.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
     L.igd_b200_count.restype = C.c_int64
     L.igd_b200_count.argtypes = [vp, C.c_int64, vp, vp, vp, C.c_int32, _i64p]
+    L.igd_b200_count_submit.restype = C.c_int
+    L.igd_b200_count_submit.argtypes = [vp, C.c_int, C.c_int64, vp, vp, vp, C.c_int32]
+    L.igd_b200_count_wait.restype = C.c_int64
+    L.igd_b200_count_wait.argtypes = [vp, C.c_int, _i64p]
     L.igd_b200_count_device.restype = C.c_int
     L.igd_b200_count_device.argtypes = [vp, C.c_int64, vp, vp, vp, C.c_int32, vp, vp]
     L.igd_b200_count_device_finish.restype = C.c_int
@@ -372,6 +376,19 @@ class IGD:
     def count_ptr(self, n: int, ctg_ptr: int, qs_ptr: int, qe_ptr: int, v: int, hits: np.ndarray) -> int:
         """Same, on raw host pointers (e.g. pinned torch tensors)."""
         r = self._L.igd_b200_count(self._need(), n, ctg_ptr, qs_ptr, qe_ptr, int(v), hits)
+        if r < 0:
+            raise IGDError(last_error())
+        return int(r)
+
+    def count_submit(self, slot: int, n: int, ctg_ptr: int, qs_ptr: int, qe_ptr: int, v: int = 0) -> None:
+        """Pipelined count: enqueue H2D + search of one batch in slot 0 / 1 (raw host pointers, pinned for full PCIe
+        speed; they must stay untouched until count_wait(slot) returns)."""
+        if self._L.igd_b200_count_submit(self._need(), int(slot), int(n), ctg_ptr, qs_ptr, qe_ptr, int(v)) != 0:
+            raise IGDError(last_error())
+
+    def count_wait(self, slot: int, hits: np.ndarray) -> int:
+        """Result of the batch submitted in `slot` (hits[] incremented); waits come in submission order."""
+        r = self._L.igd_b200_count_wait(self._need(), int(slot), hits)
         if r < 0:
             raise IGDError(last_error())
         return int(r)

@@ -52,6 +52,11 @@ void igdb_host_free(void *p);
  * kernels, D2H (may be NULL). */
 int igdb_dev_count_host(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_t *qs, const int32_t *qe,
                         int mode_v, int32_t v, uint64_t *hits_delta, float *t_ms);
+/* the same for a stream of batches, two in flight (slot 0 / 1): submit enqueues H2D (on a copy stream) + search +
+ * D2H of the counts; wait settles the batch and hands out its counts.  Waits come in submission order. */
+int igdb_dev_count_submit(igdb_dev *d, int slot, int64_t n, const int32_t *ctg, const int32_t *qs, const int32_t *qe,
+                          int mode_v, int32_t v);
+int igdb_dev_count_wait(igdb_dev *d, int slot, uint64_t *hits_delta);
 /* device buffers, enqueued on stream; d_hits[nfiles] incremented.  Pair with igdb_dev_count_finish. */
 int igdb_dev_count_device(igdb_dev *d, int64_t n, const int32_t *d_ctg, const int32_t *d_qs,
                           const int32_t *d_qe, int mode_v, int32_t v, uint64_t *d_hits, void *stream);

@@ -1085,8 +1085,10 @@ int enqueue_count_t(igdb_dev *d, const igdb_dev::Pending &p)
     }
     d->plan_grid = std::max(1, std::min(d->plan_grid_max, (thi - tlo + SCAN_T - 1) / SCAN_T));
     const bool stages = d->stage_timing && MODE != M_ABN32;
-    if (stages) CK(cudaEventRecord(d->stage_ev[0], st));
     if (grow(&d->qrank, &d->qrank_cap, p.n)) return -1;
+    // plan_tot is about to be rewritten: the readback of the previous batch's totals (side stream) must have read it
+    if (d->last_plan_ev) CK(cudaStreamWaitEvent(st, d->last_plan_ev, 0));
+    if (stages) CK(cudaEventRecord(d->stage_ev[0], st));
     CK(launch_pdl(k_cseg_count<V, MODE>, nb, thr, 0, st, db, p.n, p.ctg, p.qs, p.qe, d->cnt2, d->qrank));
     if (stages) CK(cudaEventRecord(d->stage_ev[1], st));
     // (the plan reads the later-bin counters that the scatter counts back down to zero)
@@ -1099,8 +1101,9 @@ int enqueue_count_t(igdb_dev *d, const igdb_dev::Pending &p)
     // the plan's totals go back to the host on a side stream, so that the copy does not sit between the kernels
     CK(cudaEventRecord(d->plan_done, st));
     CK(cudaStreamWaitEvent(d->side, d->plan_done, 0));
-    CK(cudaMemcpyAsync((void *)d->h_plan, d->plan_tot, 32, cudaMemcpyDeviceToHost, d->side));
-    CK(cudaEventRecord(d->plan_ev, d->side));
+    CK(cudaMemcpyAsync((void *)(d->h_plan + 4 * p.slot), d->plan_tot, 32, cudaMemcpyDeviceToHost, d->side));
+    CK(cudaEventRecord(d->plan_ev[p.slot], d->side));
+    d->last_plan_ev = d->plan_ev[p.slot];
     CountArgs a{};
     a.db = db, a.items = d->items, a.desc = d->items2, a.segs = d->csegs, a.tot = d->plan_tot;
     a.seg_cap = seg_cap, a.item_cap = item_cap, a.v = p.v, a.hits = p.hits;
@@ -1156,6 +1159,17 @@ int igdb::enqueue_count(igdb_dev *d, const igdb_dev::Pending &p)
     }
 }
 
+// the one-call entry points and the pipelined one (igdb_dev_count_submit) do not mix on a handle
+int igdb::slots_idle(const igdb_dev *d, const char *who)
+{
+    for (const auto &s : d->slot)
+        if (s.active) {
+            snprintf(g_err, sizeof g_err, "%s: submitted count batches are still in flight (igd_b200_count_wait them first)", who);
+            return -1;
+        }
+    return 0;
+}
+
 namespace {
 
 // wait for the plan of the enqueued batch p; make sure it ran (see above)
@@ -1164,8 +1178,9 @@ int settle_count(igdb_dev *d, const igdb_dev::Pending &p)
     if (p.n <= 0) return 0;
     const bool pk = p.mode == M_PACKED;
     for (;;) {
-        CK(cudaEventSynchronize(d->plan_ev));
-        const unsigned long long nsegs = d->h_plan[0], nitems = d->h_plan[1], nrec = d->h_plan[2], nabn = d->h_plan[3];
+        CK(cudaEventSynchronize(d->plan_ev[p.slot]));
+        const volatile unsigned long long *hp = d->h_plan + 4 * p.slot;
+        const unsigned long long nsegs = hp[0], nitems = hp[1], nrec = hp[2], nabn = hp[3];
         if (getenv("IGD_B200_DEBUG"))
             fprintf(stderr, "[igd_b200] count batch (mode %d): n=%lld segments=%llu items=%llu left=%llu (caps %lld / %lld)\n",
                     p.mode, (long long)p.n, nsegs, nitems, nabn, (long long)d->cseg_cap, (long long)d->item_cap);
@@ -1186,6 +1201,7 @@ int settle_count(igdb_dev *d, const igdb_dev::Pending &p)
             return 0;
         }
         // none of this batch's kernels wrote anything, but its segment counters were not counted back down
+        ++d->misfits;
         CK(cudaStreamSynchronize(p.st));
         CK(cudaMemsetAsync(d->cnt2, 0, ((size_t)2 * d->T + 2) * 4, p.st));
         if (nsegs >= 0x7fffffffull || nitems > (unsigned long long)lim) {
@@ -1264,6 +1280,7 @@ int igdb_dev_count_device_tiles(igdb_dev *d, int64_t n, const int32_t *d_ctg, co
 {
     g_err[0] = 0;
     CK(cudaSetDevice(d->device));
+    if (slots_idle(d, "count_device")) return -1;
     if (finish_pending(d)) return -1;
     if (n <= 0) return 0;
     if (d->T == 0) return 0;
@@ -1299,6 +1316,7 @@ int igdb_dev_count_host(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_
 {
     g_err[0] = 0;
     CK(cudaSetDevice(d->device));
+    if (slots_idle(d, "count")) return -1;
     if (finish_pending(d)) return -1;
     cudaStream_t st = d->stream;
     CK(cudaMemsetAsync(d->d_hits, 0, (size_t)d->nfiles * 8, st));
@@ -1349,6 +1367,106 @@ int igdb_dev_count_host(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_
     }
     CK(cudaStreamSynchronize(st));
     if (t_ms) CK(cudaEventElapsedTime(&t_ms[2], d->ev[2], d->ev[3]));
+    return 0;
+}
+
+}  // extern "C"
+
+// ---- the pipelined host entry: a STREAM of batches, two in flight -----------------------------------------
+// End to end a count call is PCIe first and HBM second: 12 B per query cross the bus before a search that needs the
+// whole batch for its plan (BASELINE config 3: 2.2 ms of H2D in front of 2.0 ms of kernels).  One call cannot
+// overlap the two -- cutting a batch into sub-batches would read the database once per sub-batch -- but a caller
+// with more than one batch can: submit(k + 1) copies on d->copy while batch k searches on d->stream.
+namespace {
+
+// everything behind the search of slot s: the counts to the pinned result, the event wait() sleeps on
+int slot_tail(igdb_dev *d, igdb_dev::CountSlot &s)
+{
+    CK(cudaMemcpyAsync(s.h_hits, s.d_hits, (size_t)d->nfiles * 8, cudaMemcpyDeviceToHost, d->stream));
+    CK(cudaEventRecord(s.done, d->stream));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int igdb_dev_count_submit(igdb_dev *d, int slot, int64_t n, const int32_t *ctg, const int32_t *qs, const int32_t *qe,
+                          int mode_v, int32_t v)
+{
+    g_err[0] = 0;
+    CK(cudaSetDevice(d->device));
+    if (slot < 0 || slot > 1) {
+        snprintf(g_err, sizeof g_err, "count_submit: slot must be 0 or 1");
+        return -1;
+    }
+    igdb_dev::CountSlot &s = d->slot[slot];
+    if (s.active) {
+        snprintf(g_err, sizeof g_err, "count_submit: slot %d holds a batch that has not been waited for", slot);
+        return -1;
+    }
+    if (n > ((int64_t)1 << 26)) {
+        snprintf(g_err, sizeof g_err, "count_submit: at most 2^26 queries per batch");
+        return -1;
+    }
+    if (finish_pending(d)) return -1;
+    if (!d->copy) CK(cudaStreamCreateWithFlags(&d->copy, cudaStreamNonBlocking));
+    if (!s.d_hits) {
+        CK(cudaMalloc((void **)&s.d_hits, std::max<size_t>((size_t)d->nfiles, 1) * 8));
+        CK(cudaMallocHost((void **)&s.h_hits, std::max<size_t>((size_t)d->nfiles, 1) * 8));
+        CK(cudaEventCreateWithFlags(&s.h2d, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    }
+    n = std::max<int64_t>(n, 0);
+    if (d->T == 0) n = 0;
+    if (grow(&s.q, &s.q_cap, 3 * std::max<int64_t>(n, 1))) return -1;
+    const int64_t cap = s.q_cap / 3;
+    int32_t *d_ctg = s.q, *d_qs = s.q + cap, *d_qe = s.q + 2 * cap;
+    if (n > 0) {
+        CK(cudaMemcpyAsync(d_ctg, ctg, (size_t)n * 4, cudaMemcpyHostToDevice, d->copy));
+        CK(cudaMemcpyAsync(d_qs, qs, (size_t)n * 4, cudaMemcpyHostToDevice, d->copy));
+        CK(cudaMemcpyAsync(d_qe, qe, (size_t)n * 4, cudaMemcpyHostToDevice, d->copy));
+    }
+    CK(cudaEventRecord(s.h2d, d->copy));
+    CK(cudaStreamWaitEvent(d->stream, s.h2d, 0));
+    CK(cudaMemsetAsync(s.d_hits, 0, (size_t)d->nfiles * 8, d->stream));
+    igdb_dev::Pending p;
+    p.mode_v = mode_v != 0, p.n = n, p.ctg = d_ctg, p.qs = d_qs, p.qe = d_qe, p.v = v;
+    p.hits = s.d_hits, p.st = d->stream, p.slot = slot;
+    p.mode = count_mode_for(d, p.mode_v, p.v);
+    if (enqueue_count(d, p)) return -1;
+    if (slot_tail(d, s)) return -1;
+    s.p = p, s.active = true, s.seq = ++d->submit_seq;
+    return 0;
+}
+
+// hits_delta[nfiles] receives the counts of the batch in `slot`.  Batches are waited for in the order they were
+// submitted.  A batch whose plan did not fit the scratch buffers is run again here (settle_count) -- and so is the
+// batch submitted behind it, which planned on segment counters the first one had left behind.
+int igdb_dev_count_wait(igdb_dev *d, int slot, uint64_t *hits_delta)
+{
+    g_err[0] = 0;
+    CK(cudaSetDevice(d->device));
+    if (slot < 0 || slot > 1 || !d->slot[slot].active) {
+        snprintf(g_err, sizeof g_err, "count_wait: no batch was submitted in slot %d", slot);
+        return -1;
+    }
+    igdb_dev::CountSlot &s = d->slot[slot], &o = d->slot[slot ^ 1];
+    if (o.active && o.seq < s.seq) {
+        snprintf(g_err, sizeof g_err, "count_wait: the batch in slot %d was submitted first; wait for it first", slot ^ 1);
+        return -1;
+    }
+    s.active = false;
+    const int64_t launches0 = d->launches;
+    const uint64_t misfits0 = d->misfits;
+    if (settle_count(d, s.p)) return -1;
+    if (d->launches != launches0 && slot_tail(d, s)) return -1;        // it ran again (or its second pipeline ran)
+    if (d->misfits != misfits0 && o.active) {
+        CK(cudaMemsetAsync(o.d_hits, 0, (size_t)d->nfiles * 8, d->stream));
+        if (enqueue_count(d, o.p) || slot_tail(d, o)) return -1;
+    }
+    CK(cudaEventSynchronize(s.done));
+    memcpy(hits_delta, s.h_hits, (size_t)d->nfiles * 8);
     return 0;
 }
 

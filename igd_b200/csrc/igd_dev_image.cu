@@ -263,9 +263,18 @@ void igdb_dev_destroy(igdb_dev *d)
     if (d->pinned) cudaFreeHost(d->pinned);
     if (d->arena) cudaFreeHost(d->arena);
     if (d->h_scalar) cudaFreeHost(d->h_scalar);
-    if (d->plan_ev) cudaEventDestroy(d->plan_ev);
+    for (auto &e : d->plan_ev)
+        if (e) cudaEventDestroy(e);
     if (d->plan_done) cudaEventDestroy(d->plan_done);
     if (d->side) cudaStreamDestroy(d->side);
+    for (auto &s : d->slot) {
+        if (s.q) cudaFree(s.q);
+        if (s.d_hits) cudaFree(s.d_hits);
+        if (s.h_hits) cudaFreeHost(s.h_hits);
+        if (s.h2d) cudaEventDestroy(s.h2d);
+        if (s.done) cudaEventDestroy(s.done);
+    }
+    if (d->copy) cudaStreamDestroy(d->copy);
     for (auto &e : d->ev)
         if (e) cudaEventDestroy(e);
     for (auto &e : d->kev)
@@ -286,9 +295,9 @@ static int create_impl(igdb_dev *d, const int32_t *ntile, const int32_t *ncnt)
     for (auto &e : d->ev) CK(cudaEventCreate(&e));
     for (auto &e : d->kev) CK(cudaEventCreate(&e));
     for (auto &e : d->stage_ev) CK(cudaEventCreate(&e));
-    CK(cudaMallocHost((void **)&d->h_scalar, 64));
-    d->h_plan = reinterpret_cast<volatile unsigned long long *>(d->h_scalar + 8);
-    CK(cudaEventCreateWithFlags(&d->plan_ev, cudaEventDisableTiming));
+    CK(cudaMallocHost((void **)&d->h_scalar, 128));
+    d->h_plan = reinterpret_cast<volatile unsigned long long *>(d->h_scalar + 8);      // 2 slots x 4 words
+    for (auto &e : d->plan_ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&d->plan_done, cudaEventDisableTiming));
     CK(cudaStreamCreateWithFlags(&d->side, cudaStreamNonBlocking));
 

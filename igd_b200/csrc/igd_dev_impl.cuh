@@ -331,8 +331,9 @@ struct igdb_dev {
     uint32_t *plan_flag = nullptr, plan_epoch = 0;          // [plan_grid] = epoch of the batch that published
     int plan_grid = 0, plan_grid_max = 0;
     unsigned long long *plan_tot = nullptr;                 // device {segments, items} of the batch in flight
-    volatile unsigned long long *h_plan = nullptr;          // pinned copy of plan_tot
-    cudaEvent_t plan_ev = nullptr, plan_done = nullptr;
+    volatile unsigned long long *h_plan = nullptr;          // pinned copies of plan_tot, 4 words per slot (Pending::slot)
+    cudaEvent_t plan_ev[2] = {nullptr, nullptr}, plan_done = nullptr;   // plan_ev[slot]: that slot's copy has landed
+    cudaEvent_t last_plan_ev = nullptr;                     // the plan readback enqueued last (the next k_plan waits for it)
     cudaEvent_t stage_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // around the 4 launches (diagnostics)
     bool stage_timing = false, stage_valid = false;
     cudaStream_t side = nullptr;                            // carries the plan readback
@@ -367,7 +368,22 @@ struct igdb_dev {
         unsigned long long *hits = nullptr;
         cudaStream_t st = nullptr;
         int32_t tile_lo = 0, tile_hi = 0x7fffffff;          // no query touches a tile outside [tile_lo, tile_hi)
+        int slot = 0;                                       // which h_plan / plan_ev carries this batch's plan back
     } pending;
+    // The pipelined host entry (igdb_dev_count_submit / _wait): two batches in flight.  A slot owns what must outlive
+    // the next batch's copy -- its queries in HBM, its hits[] on both sides, its events; the plan scratch is shared,
+    // because the batches run one after the other on d->stream and only the H2D of the next one (d->copy) overlaps.
+    struct CountSlot {
+        bool active = false;
+        uint64_t seq = 0;                                   // order of submission
+        Pending p;
+        int32_t *q = nullptr;                               // ctg[cap] | qs[cap] | qe[cap]
+        int64_t q_cap = 0;
+        unsigned long long *d_hits = nullptr, *h_hits = nullptr;    // [nfiles] device / pinned host
+        cudaEvent_t h2d = nullptr, done = nullptr;
+    } slot[2];
+    cudaStream_t copy = nullptr;                            // carries the H2D of submitted batches
+    uint64_t submit_seq = 0, misfits = 0;                   // misfits: batches whose plan did not fit (settle_count)
     DbView view() const
     {
         DbView v;
@@ -444,6 +460,7 @@ int upload_queries(igdb_dev *d, int64_t n, const int32_t *ctg, const int32_t *qs
                    cudaStream_t st);                                               // igd_dev_image.cu
 int enqueue_count(igdb_dev *d, const igdb_dev::Pending &p);                        // igd_dev_count.cu
 int finish_pending(igdb_dev *d);                                                   // igd_dev_count.cu
+int slots_idle(const igdb_dev *d, const char *who);                                // igd_dev_count.cu
 int count_mode_for(const igdb_dev *d, bool mode_v, int32_t v);                     // igd_dev_count.cu
 int64_t full_device(igdb_dev *d, int64_t n, cudaStream_t st, bool with_g, DevBuf &qoff, DevBuf &out);   // igd_dev_full.cu
 

@@ -181,7 +181,7 @@ int igdb_dev_hits_begin(igdb_dev *d)
 {
     g_err[0] = 0;
     CK(cudaSetDevice(d->device));
-    if (finish_pending(d)) return -1;
+    if (slots_idle(d, "search") || finish_pending(d)) return -1;
     CK(cudaMemsetAsync(d->d_hits, 0, (size_t)d->nfiles * 8, d->stream));
     return 0;
 }

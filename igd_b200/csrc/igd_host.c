@@ -273,6 +273,25 @@ int64_t igd_b200_count(igd_b200_t *h, int64_t n, const int32_t *ctg, const int32
     return count_mode(h, n, ctg, qs, qe, filter_on(h, v), v, hits);
 }
 
+int igd_b200_count_submit(igd_b200_t *h, int slot, int64_t n, const int32_t *ctg, const int32_t *qs,
+                          const int32_t *qe, int32_t v)
+{
+    g_err[0] = 0;
+    return igdb_dev_count_submit(h->dev, slot, n, ctg, qs, qe, filter_on(h, v), v);
+}
+
+int64_t igd_b200_count_wait(igd_b200_t *h, int slot, int64_t *hits)
+{
+    g_err[0] = 0;
+    if (igdb_dev_count_wait(h->dev, slot, h->delta)) return -1;
+    int64_t total = 0;
+    for (int i = 0; i < h->nfiles; i++) {
+        hits[i] += (int64_t)h->delta[i];
+        total += (int64_t)h->delta[i];
+    }
+    return total;
+}
+
 int igd_b200_count_device(igd_b200_t *h, int64_t n, const int32_t *d_ctg, const int32_t *d_qs,
                           const int32_t *d_qe, int32_t v, uint64_t *d_hits, void *stream)
 {

@@ -72,6 +72,20 @@ int64_t get_overlaps_n32(igd_b200_t *h, int64_t n, const char *const *chrm, cons
 /* same, contig ids already resolved with igd_b200_ctg_id (-1 = unknown chrom: contributes nothing) */
 int64_t igd_b200_count(igd_b200_t *h, int64_t n, const int32_t *ctg, const int32_t *qs,
                        const int32_t *qe, int32_t v, int64_t *hits);
+/* The same for a STREAM of batches, two in flight (no counterpart in the reference, whose search_nr is one
+ * synchronous loop, IGDr/src/igd_search.c:340-355).  End to end a batch is PCIe first and HBM second -- 12 B per query
+ * cross the bus before a search that needs the whole batch for its plan -- so one call cannot overlap the two, but a
+ * caller with several batches can:
+ *     igd_b200_count_submit(h, 0, n0, ...);
+ *     igd_b200_count_submit(h, 1, n1, ...);  igd_b200_count_wait(h, 0, hits);     -- batch 1 copies while batch 0 searches
+ *     igd_b200_count_submit(h, 0, n2, ...);  igd_b200_count_wait(h, 1, hits);  ...
+ * submit: slot is 0 or 1 and must be free; n <= 2^26; the host arrays (pinned memory for full PCIe speed) must stay
+ * untouched until the wait for that slot returns.  Returns 0 once copy and search are enqueued.
+ * wait: batches are waited for in submission order; hits[nFiles] is INCREMENTED like igd_b200_count's; returns the
+ * overlaps of the batch or a negative error code.  The one-call entry points fail while a slot is busy. */
+int igd_b200_count_submit(igd_b200_t *h, int slot, int64_t n, const int32_t *ctg, const int32_t *qs,
+                          const int32_t *qe, int32_t v);
+int64_t igd_b200_count_wait(igd_b200_t *h, int slot, int64_t *hits);
 /* same, but every buffer is a DEVICE pointer on the handle's device and the work is enqueued on
  * `stream` (a cudaStream_t, may be NULL) without any host round trip.  d_hits is uint64[nFiles],
  * incremented.  Returns 0 once the work is enqueued.  This is the entry point the multi-GPU driver uses,

@@ -27,6 +27,8 @@ void igdb_host_free(void *p) { free(p); }
 int igdb_dev_count_host(igdb_dev *d, int64_t n, const int32_t *a, const int32_t *b, const int32_t *c, int m, int32_t v, uint64_t *h, float *t) { (void)d; (void)n; (void)a; (void)b; (void)c; (void)m; (void)v; (void)h; (void)t; return -1; }
 int igdb_dev_count_device(igdb_dev *d, int64_t n, const int32_t *a, const int32_t *b, const int32_t *c, int m, int32_t v, uint64_t *h, void *s) { (void)d; (void)n; (void)a; (void)b; (void)c; (void)m; (void)v; (void)h; (void)s; return -1; }
 int igdb_dev_count_finish(igdb_dev *d) { (void)d; return -1; }
+int igdb_dev_count_submit(igdb_dev *d, int s, int64_t n, const int32_t *a, const int32_t *b, const int32_t *c, int m, int32_t v) { (void)d; (void)s; (void)n; (void)a; (void)b; (void)c; (void)m; (void)v; return -1; }
+int igdb_dev_count_wait(igdb_dev *d, int s, uint64_t *h) { (void)d; (void)s; (void)h; return -1; }
 int igdb_dev_set_contigs(igdb_dev *d, const char *n) { (void)d; (void)n; return -1; }
 int igdb_dev_hits_begin(igdb_dev *d) { (void)d; return -1; }
 int igdb_dev_count_text(igdb_dev *d, const char *t, size_t l, int m, int32_t v, int64_t *n) { (void)d; (void)t; (void)l; (void)m; (void)v; (void)n; return -1; }
