@@ -321,6 +321,10 @@ class IGD:
     def ntile(self, ctg: int) -> int:
         return self._L.igd_b200_ntile(self._need(), ctg)
 
+    def ncnt(self, ctg: int, tile: int) -> int:
+        """iGD_t.nCnt[ctg][tile]: records of one tile."""
+        return self._L.igd_b200_ncnt(self._need(), ctg, tile)
+
     def device_bytes(self) -> int:
         return self._L.igd_b200_device_bytes(self._need())
 

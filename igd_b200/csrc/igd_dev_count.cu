@@ -628,7 +628,8 @@ __global__ void __launch_bounds__(256, 4) k_windows(DbView db, const int4 *__res
                                                   const uint32_t *__restrict__ segs,
                                                   const unsigned long long *__restrict__ tot,
                                                   unsigned long long seg_cap, unsigned long long item_cap,
-                                                  int4 *__restrict__ out, int small_done, uint32_t tlo, uint32_t thi)
+                                                  int4 *__restrict__ out, int small_done, uint32_t tlo, uint32_t thi,
+                                                  uint32_t min_groups)
 {
     constexpr int NSUB = 256 / LPT, NGT = 4 * LPT;          // NGT: groups of a tile whose key ranges are staged in shared memory
     __shared__ uint32_t s_cnt[NSUB][LPT + 1], s_m0[NSUB][LPT], s_m1[NSUB][LPT], s_x[NSUB][SMAX], s_gk[NSUB][2][NGT];
@@ -649,7 +650,7 @@ __global__ void __launch_bounds__(256, 4) k_windows(DbView db, const int4 *__res
           tp_l = __ldg(&tplan[2 * (tb + l)]);
           if (tp_l.z != tp_l.x) tm_l = __ldg(&tplan[2 * (tb + l) + 1]);
       }
-      bool need = tp_l.z != tp_l.x;
+      bool need = tp_l.z != tp_l.x && ((uint32_t)tm_l.y + GROUP - 1) / GROUP >= min_groups;   // (fewer: k_windows_warp's)
       if (need && small_done && windows_small_tile((uint32_t)(tp_l.z - tp_l.x), ((uint32_t)tm_l.y + GROUP - 1) / GROUP))
           need = false;                                     // k_windows_small has done this tile
       unsigned todo = __ballot_sync(FULL, need);
@@ -731,6 +732,135 @@ __global__ void __launch_bounds__(256, 4) k_windows(DbView db, const int4 *__res
             }
         }
         __syncwarp(lmask);
+      }
+    }
+}
+
+// The descriptors of the tiles of a dense database (BASELINE config 3: ~22 groups and ~56 segments per tile), one
+// WARP per tile, tiles of fewer than W2_NG groups (the others: k_windows<32> above, launched only for a database
+// that has such tiles).  Same result as k_windows<32>, a third of its instructions:
+//   * the groups' thresholds (largest key + 0x8000 padded with +inf to a power of two P, smallest key + 0x8000) are
+//     staged once per tile, so a segment's HOME group -- the number of groups whose largest key it is past -- is a
+//     branch-free search of log2(P) steps of 4 instructions;
+//   * a lane searches for segments `lane` and `lane + 32` of the chunk at once (two independent chains), and both
+//     kinds (START: x = qe', END: x = qs') use the same two loaded words;
+//   * ONE shared-memory atomic per segment leaves both counts at its home group -- segments (low half) and segments
+//     inside the window (high half); its return value is the slot of the segment's x among the <= RK_INL values
+//     that travel in the descriptor, so the group phase reads them back with one load instead of walking a mask.
+constexpr uint32_t W2_NG = 128;
+
+__global__ void __launch_bounds__(256) k_windows_warp(DbView db, const int4 *__restrict__ tplan,
+                                                       const uint32_t *__restrict__ segs,
+                                                       const unsigned long long *__restrict__ tot,
+                                                       unsigned long long seg_cap, unsigned long long item_cap,
+                                                       int4 *__restrict__ out, int small_done, uint32_t tpw, uint32_t tlo,
+                                                       uint32_t thi)
+{
+    __shared__ uint32_t s_hi[8][2][W2_NG], s_lo[8][2][W2_NG];
+    __shared__ uint32_t s_cw[8][W2_NG], s_m0[8][W2_NG], s_m1[8][W2_NG];
+    __shared__ uint2 s_wv[8][W2_NG];
+    pdl_launch_dependents();
+    pdl_wait();                                             // the plan, the segments
+    if (tot[0] > seg_cap || tot[1] > item_cap) return;
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    uint32_t *cw = s_cw[wib], *m0 = s_m0[wib], *m1 = s_m1[wib];
+    uint16_t *wv = reinterpret_cast<uint16_t *>(s_wv[wib]);
+    // `tpw` tiles per warp and turn (32 in a database of small tiles, most of which k_windows_small has done; else 8):
+    // lane i looks at tile tb + i, then the warp works through the ones that are its to describe
+    for (uint32_t tb = tlo + (blockIdx.x * 8 + wib) * tpw; tb < thi; tb += gridDim.x * 8 * tpw) {
+      bool need = false;
+      if (lane < tpw && tb + lane < thi) {
+          const int4 tp_l = __ldg(&tplan[2 * (tb + lane)]);
+          if (tp_l.z != tp_l.x) {                           // (else: no query reached this tile)
+              const uint32_t ng_l = ((uint32_t)__ldg(&tplan[2 * (tb + lane) + 1]).y + GROUP - 1) / GROUP;
+              need = ng_l < W2_NG &&                        // (else: k_windows<32>)
+                     !(small_done && windows_small_tile((uint32_t)(tp_l.z - tp_l.x), ng_l));   // (else: k_windows_small)
+          }
+      }
+      unsigned todo = __ballot_sync(FULL, need);
+      while (todo) {
+        const uint32_t t = tb + (uint32_t)__ffs(todo) - 1;
+        todo &= todo - 1;
+        const int4 tp = __ldg(&tplan[2 * t]), tm = __ldg(&tplan[2 * t + 1]);      // {segments .. first item}, {off8, n, ts, first group}
+        const uint32_t a = (uint32_t)tp.x, m = (uint32_t)tp.y, e = (uint32_t)tp.z, i0 = (uint32_t)tp.w;
+        const uint32_t gb = (uint32_t)tm.w, n = (uint32_t)tm.y, ng = (n + GROUP - 1) / GROUP;
+        const uint32_t P = ng < 32 ? 32u : (ng < 64 ? 64u : 128u);     // > ng: the search can answer "past all groups"
+        const uint32_t ch = (e - a + SMAX - 1) / SMAX, chF = (m - a + SMAX - 1) / SMAX;
+        __syncwarp();
+        for (uint32_t g = lane; g < P; g += 32) {
+            const uint32_t ks = g < ng ? __ldg(&db.gk[gb + g]) : 0u, ke = g < ng ? __ldg(&db.gk[gb + db.ngroups + g]) : 0u;
+            s_hi[wib][0][g] = g < ng ? (ks >> 16) + 0x8000u : 0xffffffffu, s_lo[wib][0][g] = (ks & 0xffffu) + 0x8000u;
+            s_hi[wib][1][g] = g < ng ? (ke >> 16) + 0x8000u : 0xffffffffu, s_lo[wib][1][g] = (ke & 0xffffu) + 0x8000u;
+        }
+        for (uint32_t c = 0; c < ch; ++c) {
+            const uint32_t sa = a + c * SMAX, ns_all = min(sa + (uint32_t)SMAX, e) - sa;
+            const uint32_t nf = min(max(m, sa), sa + ns_all) - sa;         // first-bin segments of the chunk
+            const uint32_t w0 = lane < ns_all ? __ldg(&segs[sa + lane]) : 0u;
+            const uint32_t w1 = lane + 32 < ns_all ? __ldg(&segs[sa + 32 + lane]) : 0u;
+            for (uint32_t kind = 0; kind < (c < chF ? 2u : 1u); ++kind) {
+                const uint32_t ns = kind ? nf : ns_all, sh = kind ? 0u : 16u;
+                const uint32_t *hi = s_hi[wib][kind], *lo = s_lo[wib][kind];
+                for (uint32_t g = lane; g < P; g += 32) cw[g] = 0, m0[g] = 0, m1[g] = 0;
+                __syncwarp();
+                const uint32_t x0 = (w0 >> sh) & 0xffffu, x1 = (w1 >> sh) & 0xffffu;
+                uint32_t h0 = 0, h1 = 0;                    // home = #groups whose largest key x is past
+                if (P == 32) {                              // (the common depth, unrolled: 4 instructions per step)
+#pragma unroll
+                    for (uint32_t step = 16; step; step >>= 1) {
+                        if (x0 >= hi[h0 + step - 1]) h0 += step;
+                        if (x1 >= hi[h1 + step - 1]) h1 += step;
+                    }
+                } else {
+                    for (uint32_t step = P >> 1; step; step >>= 1) {
+                        if (x0 >= hi[h0 + step - 1]) h0 += step;
+                        if (x1 >= hi[h1 + step - 1]) h1 += step;
+                    }
+                }
+                if (lane < ns) {
+                    const bool in = h0 < ng && x0 >= lo[h0];        // past the home group's smallest key: in its window
+                    const uint32_t slot = atomicAdd(&cw[h0], in ? 0x10001u : 1u) >> 16;
+                    if (in) {
+                        atomicOr(&m0[h0], 1u << lane);
+                        if (slot < RK_INL) wv[h0 * 4 + slot] = (uint16_t)x0;
+                    }
+                }
+                if (lane + 32 < ns) {
+                    const bool in = h1 < ng && x1 >= lo[h1];
+                    const uint32_t slot = atomicAdd(&cw[h1], in ? 0x10001u : 1u) >> 16;
+                    if (in) {
+                        atomicOr(&m1[h1], 1u << lane);
+                        if (slot < RK_INL) wv[h1 * 4 + slot] = (uint16_t)x1;
+                    }
+                }
+                __syncwarp();
+                // lane <-> group g0 + lane, from the window that holds slot ng (the segments past every group) down:
+                // an item's base count = the segments whose home lies behind its group
+                uint32_t carry = 0;
+                for (int g0 = (int)(ng & ~31u); g0 >= 0; g0 -= 32) {
+                    const uint32_t g = (uint32_t)g0 + lane;
+                    const uint32_t cwg = g < P ? cw[g] : 0u, cnt = cwg & 0xffffu, nin = cwg >> 16;
+                    uint32_t suf = cnt;                     // inclusive suffix sum over the window
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t o = __shfl_down_sync(FULL, suf, d);
+                        if (lane + d < 32) suf += o;
+                    }
+                    const uint32_t base = suf - cnt + carry;
+                    carry += __shfl_sync(FULL, suf, 0);
+                    if (g < ng) {
+                        const uint2 v = s_wv[wib][g];
+                        const int r0 = (int)(g * GROUP);
+                        const uint32_t nv = (uint32_t)min((int)n - r0, GROUP), tsr = (uint32_t)min(max(tm.z - r0, 0), GROUP);
+                        const uint32_t nl = kind ? 0u : ns_all - nf, fix = !kind && tsr > 0 && nl > 0;
+                        const size_t k = (size_t)i0 + (kind ? ng * ch + g * chF + c : g * ch + c);
+                        out[2 * k] = make_int4((int)((uint32_t)tm.x + g * (GROUP / 8) + (kind ? db.eoff8 : 0u)), (int)sa,
+                                               (int)(nv | ns << 9 | base << 16 | nl << 23 | kind << 30 | fix << 31), (int)m0[g]);
+                        out[2 * k + 1] = make_int4((int)m1[g], (int)v.x, (int)v.y, (int)nin);
+                    }
+                }
+                __syncwarp();
+            }
+        }
       }
     }
 }
@@ -1118,12 +1248,21 @@ int enqueue_count_t(igdb_dev *d, const igdb_dev::Pending &p)
                           item_cap, d->items2, (uint32_t)tlo, (uint32_t)thi));
             d->launches += 1;
         }
-        const int64_t tpc = sparse ? 256 : 8;                       // tiles per CTA and turn
-        const unsigned wgrid = (unsigned)std::min<int64_t>((nt + tpc - 1) / tpc, (int64_t)d->sm_count * 64);
-        CK(launch_pdl(k_windows<32>, wgrid, 256, 0, st, db, (const int4 *)d->tplan,
+        // the others: a warp per tile; tiles of W2_NG groups or more (none in the BASELINE configurations) by the
+        // general kernel
+        const int64_t tpw = sparse ? 32 : 8;                        // tiles per warp and turn
+        const unsigned wgrid = (unsigned)std::min<int64_t>((nt + 8 * tpw - 1) / (8 * tpw), (int64_t)d->sm_count * 48);
+        CK(launch_pdl(k_windows_warp, wgrid, 256, 0, st, db, (const int4 *)d->tplan,
                       (const uint32_t *)(const void *)d->csegs, (const unsigned long long *)d->plan_tot, seg_cap, item_cap,
-                      d->items2, sparse ? 1 : 0, (uint32_t)tlo, (uint32_t)thi));
+                      d->items2, sparse ? 1 : 0, (uint32_t)tpw, (uint32_t)tlo, (uint32_t)thi));
         d->launches += 1;
+        if (d->max_tile_groups >= (int64_t)W2_NG) {
+            const unsigned ggrid = (unsigned)std::min<int64_t>((nt + 255) / 256, (int64_t)d->sm_count * 64);
+            CK(launch_pdl(k_windows<32>, ggrid, 256, 0, st, db, (const int4 *)d->tplan,
+                          (const uint32_t *)(const void *)d->csegs, (const unsigned long long *)d->plan_tot, seg_cap,
+                          item_cap, d->items2, 1, (uint32_t)tlo, (uint32_t)thi, W2_NG));
+            d->launches += 1;
+        }
     }
     if (stages) CK(cudaEventRecord(d->stage_ev[3], st));
     if (MODE != M_ABN32) CK(cudaEventRecord(d->kev[0], st));

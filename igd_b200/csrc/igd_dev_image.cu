@@ -319,6 +319,7 @@ static int create_impl(igdb_dev *d, const int32_t *ntile, const int32_t *ncnt)
             d->toff[t + 1] = d->toff[t] + n;
             gbase[t] = (uint32_t)d->db_groups;
             d->db_groups += (n + GROUP - 1) / GROUP;
+            d->max_tile_groups = std::max<int64_t>(d->max_tile_groups, (n + GROUP - 1) / GROUP);
             p8 += (n + 7) / 8;
         }
     if (p8 >= (int64_t)0x7ffffff0) {             // the END half of the count-mode copy starts at p8 + 1

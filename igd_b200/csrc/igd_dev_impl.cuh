@@ -357,6 +357,7 @@ struct igdb_dev {
     int4 *tplan = nullptr;                                  // [2T] per tile {first segment, first later-bin one, end, first item}, {off8, n, ts, first group}
     int64_t item2_cap = 0;
     int64_t db_groups = 0;                                  // sum over tiles of ceil(n / GROUP)
+    int64_t max_tile_groups = 0;                            // the most groups any tile has
     int count_grid[2][2] = {{0, 0}, {0, 0}};                // CTAs of the search kernel [packed][V] (0 = not set up)
     int64_t last_plan[4] = {0, 0, 0, 0};                    // segments, items, records, bytes of the last batch
     struct Pending {                                        // count batch enqueued but not yet settled

@@ -102,6 +102,41 @@ def test_dense_tiles_long_tailed_lengths(workdir, v):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("v", [0, 500])
+def test_very_dense_tiles_every_windows_kernel(workdir, v):
+    """tiles of ~12, ~36, ~71, ~110 and ~164 groups of 256 records: the descriptor kernel's three search depths (32,
+    64, 128 staged groups: k_windows_warp) and the tiles beyond them (k_windows<32>), with ~1000 segments (16 chunks)
+    per tile"""
+    from igd_b200 import api
+    from oracle import oracle as O
+    names = ["chrP", "chrQ", "chrR", "chrS", "chrT"]
+    sizes = np.full(5, 4 * 16384, dtype=np.int64)
+    stem = os.path.join(workdir, "very_dense")
+    if not os.path.exists(stem + ".igd"):
+        files = []
+        for i in range(8):
+            rng = np.random.default_rng(81000 + i)
+            n = 50000
+            ctg = rng.choice(5, size=n, p=[0.03, 0.09, 0.18, 0.28, 0.42]).astype(np.int32)
+            ln = np.clip(np.exp(rng.normal(5.5, 1.2, n)), 1, 60000).astype(np.int64)
+            start = np.floor(rng.random(n) * np.maximum(sizes[ctg] - ln, 1)).astype(np.int64)
+            end = np.minimum(start + ln, sizes[ctg])
+            files.append(synth.Intervals(ctg, start.astype(np.int32), end.astype(np.int32),
+                                         rng.integers(0, 1001, size=n, dtype=np.int32)))
+        synth.write_igd_direct(stem, files, names=names)
+    odb = O.OracleDB(stem + ".igd")
+    qa = synth.gen_intervals(82, 20000, ("lognormal", 6.0, 1.2), sizes)
+    qb = synth.gen_intervals(83, 500, ("fixed", 40000), sizes)
+    ctg = np.concatenate([qa.ctg, qb.ctg])
+    qs, qe = np.concatenate([qa.start, qb.start]), np.concatenate([qa.end, qb.end])
+    want, _ = odb.count(ctg, qs, qe, v)
+    with api.IGD(stem + ".igd") as g:
+        most = max(g.ncnt(c, t) for c in range(5) for t in range(g.ntile(c)))
+        assert most >= 128 * 256                        # a tile beyond the staged kernel's reach is in there
+        got, _ = g.count(ctg, qs, qe, v)
+    assert want.sum() > 0 and np.array_equal(got, want)
+
+
 def test_item_boundary_tiles_full_hitsmap_seqpare(db, workdir):
     """the same tiles (1, 2, 15, 16, 17, 31, 32, 33 ... records, duplicate starts) through the query-centric
     kernels: -f (the 32-ary ballot search and the descending scan), -m, -m -v, and Seqpare's candidate lists"""
