@@ -228,13 +228,27 @@ def run_ours(args):
         from igd_b200.multi import DeviceSharder
         a, b = n_total * rank // world, n_total * (rank + 1) // world
         ctg_l, qs_l, qe_l = ctg_all[a:b], qs_all[a:b], qe_all[a:b]
-        sharder = DeviceSharder(igd, dev)
+        # the query exchange by the library's own kernels over NVLink peer memory (igd_b200_dispatcher_*: partition
+        # fused with its all-to-all); IGD_B200_NCCL_SHARD=1 keeps the partition + NCCL all-to-all
+        sharder = DeviceSharder(igd, dev, peer_cap=0 if os.environ.get("IGD_B200_NCCL_SHARD") else n_total)
         u_ctg, u_qs, u_qe = (torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (ctg_l, qs_l, qe_l))
         d_ctg, d_qs, d_qe, tile_lo, tile_hi = sharder.shard(u_ctg, u_qs, u_qe)
         d_ctg, d_qs, d_qe = d_ctg.clone(), d_qs.clone(), d_qe.clone()
         torch.cuda.synchronize()
     else:
         ctg_l, qs_l, qe_l = ctg_all, qs_all, qe_all
+        if args.shard_of > 1:
+            # profiling aid: the work of ONE rank of an N-GPU run on a single GPU (the shard cut on the host like
+            # tests/test_gpu_shard.py's reference) -- what ncu can look at, since it must not run multi-rank commands
+            hdr = workloads.read_igd_header(path)
+            s_ctg, s_qs, s_qe, bounds = workloads.sort_and_shard(hdr, ctg_all, qs_all, qe_all, args.shard_of)
+            a, b = bounds[args.shard_rank], bounds[args.shard_rank + 1]
+            ctg_l, qs_l, qe_l = s_ctg[a:b], s_qs[a:b], s_qe[a:b]
+            nbp, tb = hdr["nbp"], hdr["tbase"]
+            first = tb[ctg_l] + qs_l // nbp
+            last = tb[ctg_l] + np.minimum((qe_l.astype(np.int64) - 1) // nbp, hdr["ntile"][ctg_l] - 1)
+            tile_lo, tile_hi = int(first.min()), int(max(last.max(), first.max())) + 1
+            args.no_parity = True
         d_ctg = torch.from_numpy(np.ascontiguousarray(ctg_l)).to(dev)
         d_qs = torch.from_numpy(np.ascontiguousarray(qs_l)).to(dev)
         d_qe = torch.from_numpy(np.ascontiguousarray(qe_l)).to(dev)
@@ -261,16 +275,23 @@ def run_ours(args):
             reducer.close()
             reducer = None
 
+    # N > 1: a rank counts into d_part, and the exchange kernel writes the sum to d_hits and leaves d_part zeroed for
+    # the next step (igd_b200_reducer_allreduce_into) -- no separate launch to clear the counters
+    d_part = torch.zeros(igd.nfiles, dtype=torch.int64, device=dev) if world > 1 else d_hits
+
     def combine():
         if reducer is not None:
-            reducer.allreduce(d_hits.data_ptr(), stream)
+            reducer.allreduce_into(d_part.data_ptr(), d_hits.data_ptr(), stream)
         else:
+            d_hits.copy_(d_part)
+            d_part.zero_()
             dist.all_reduce(d_hits)
 
     def step_device():
-        d_hits.zero_()
+        if world == 1:
+            d_hits.zero_()
         if n_local:
-            igd.count_device_tiles(n_local, d_ctg.data_ptr(), d_qs.data_ptr(), d_qe.data_ptr(), 0, d_hits.data_ptr(),
+            igd.count_device_tiles(n_local, d_ctg.data_ptr(), d_qs.data_ptr(), d_qe.data_ptr(), 0, d_part.data_ptr(),
                                    stream, tile_lo, tile_hi)
             igd.count_device_finish()
         if world > 1:
@@ -294,10 +315,9 @@ def run_ours(args):
         e_qs.copy_(h_qs, non_blocking=True)
         e_qe.copy_(h_qe, non_blocking=True)
         s_ctg, s_qs, s_qe, lo, hi = sharder.shard(e_ctg, e_qs, e_qe)
-        d_hits.zero_()
         if s_ctg.shape[0]:
             igd.count_device_tiles(int(s_ctg.shape[0]), s_ctg.data_ptr(), s_qs.data_ptr(), s_qe.data_ptr(), 0,
-                                   d_hits.data_ptr(), stream, lo, hi)
+                                   d_part.data_ptr(), stream, lo, hi)
             igd.count_device_finish()
         combine()
         h_hits.copy_(d_hits, non_blocking=True)
@@ -370,7 +390,60 @@ def run_ours(args):
     # N = 1: the same K batches as a STREAM through igd_b200_count_submit / _wait -- two in flight, the H2D of batch
     # k + 1 under the search of batch k; every step still copies its 12 B per query in and its hits[] out inside the
     # timed region (no L2 flush between the steps: each one reads several GB of the database, far beyond the L2)
-    e2e_single = None
+    e2e_single, e2e_phases = None, None
+    if world > 1:
+        # N > 1: the same K steps as a stream -- the H2D of step k + 1 (this rank's 1/N of the queries, on a copy stream
+        # into the other of two input buffers) under the shard plan, exchange and search of step k
+        copy_st = torch.cuda.Stream(device=dev)
+        e_in = [[torch.empty(n_slice, dtype=torch.int32, device=dev) for _ in range(3)] for _ in range(2)]
+        h_out = [torch.zeros(igd.nfiles, dtype=torch.int64).pin_memory() for _ in range(2)]
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+
+        def upload(k):
+            with torch.cuda.stream(copy_st):
+                for dst, src in zip(e_in[k & 1], (h_ctg, h_qs, h_qe)):
+                    dst.copy_(src, non_blocking=True)
+                ev_in[k & 1].record(copy_st)
+
+        def stream_steps(k_steps):
+            upload(0)
+            for k in range(k_steps):
+                if k + 1 < k_steps:
+                    upload(k + 1)                       # (its buffers were last read by step k - 1, which has completed)
+                side.wait_event(ev_in[k & 1])
+                s_ctg, s_qs, s_qe, lo, hi = sharder.shard(*e_in[k & 1])
+                if s_ctg.shape[0]:
+                    igd.count_device_tiles(int(s_ctg.shape[0]), s_ctg.data_ptr(), s_qs.data_ptr(), s_qe.data_ptr(), 0,
+                                           d_part.data_ptr(), stream, lo, hi)
+                    igd.count_device_finish()
+                combine()
+                h_out[k & 1].copy_(d_hits, non_blocking=True)
+                side.synchronize()                      # the step's result is on the host
+            return h_out[(k_steps - 1) & 1].numpy()
+
+        stream_steps(3)
+        # one more (untimed) step, one at a time, with CUDA events at the phase boundaries
+        sharder.marks = []
+        for _ in range(2):
+            sharder.marks.clear()
+            torch.cuda.synchronize()
+            barrier()
+            sharder._mark("h2d_begin")
+            step_e2e()
+            sharder._mark("end")
+        torch.cuda.synchronize()
+        mk = sharder.marks
+        e2e_phases = {mk[i + 1][0]: round(mk[i][1].elapsed_time(mk[i + 1][1]), 4) for i in range(len(mk) - 1)}
+        sharder.marks = None
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out_last = stream_steps(args.steps)
+        e2e_stream_s = time.perf_counter() - t0
+        assert np.array_equal(out_last, np.asarray(hits_e2e)), "pipelined and step-by-step end-to-end paths disagree"
+        e2e_single = {"value": None, "unit": UNIT, "ms_per_step": e2e_s / args.steps * 1e3,
+                      "api": "the same steps one at a time (H2D, then shard + search + exchange, then D2H)"}
+        e2e_s = e2e_stream_s
     if world == 1:
         def stream_steps(k):
             outs = [np.zeros(igd.nfiles, np.int64) for _ in range(k)]
@@ -414,9 +487,10 @@ def run_ours(args):
         file_n = nf
 
     if world > 1:
-        t = torch.tensor([total_ms, e2e_s, float(np.mean(kernel_ms))], dtype=torch.float64, device=dev)
+        t = torch.tensor([total_ms, e2e_s, float(np.mean(kernel_ms)), e2e_single["ms_per_step"]], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_s, kmean = (float(x) for x in t.cpu())
+        total_ms, e2e_s, kmean, e2e_single["ms_per_step"] = (float(x) for x in t.cpu())
+        e2e_single["value"] = n_total / (e2e_single["ms_per_step"] * 1e-3)
         ln = torch.tensor([launches], dtype=torch.int64, device=dev)
         dist.all_reduce(ln)
         launches = int(ln.item())
@@ -424,6 +498,15 @@ def run_ours(args):
         kmean = float(np.mean(kernel_ms))
     assert np.array_equal(np.asarray(hits_e2e), hits_dev), "e2e and device-resident paths disagree"
 
+    per_rank = None
+    if world > 1:
+        mine = torch.tensor([float(np.mean(kernel_ms)), float(np.mean(step_ms)), float(n_local), float(plan["items"])]
+                            + [float(stages[k]) for k in ("seg_count", "plan", "seg_scatter", "search")],
+                            dtype=torch.float64, device=dev)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {k: [round(float(t[i]), 4) for t in allr] for i, k in enumerate(
+            ("kernel_ms", "step_ms", "queries", "items", "seg_count_ms", "plan_ms", "seg_scatter_windows_ms", "search_ms"))}
     if world > 1:
         pl = torch.tensor([plan["own_bytes"]], dtype=torch.float64, device=dev)
         dist.all_reduce(pl, op=dist.ReduceOp.MAX)
@@ -439,6 +522,8 @@ def run_ours(args):
         parity = None
         if orc.get("hits_full") is not None:
             parity = bool(np.array_equal(np.array(orc["hits_full"], np.int64), hits_dev))
+        if args.shard_of > 1:
+            n_total = n_local
         achieved = own_bytes / (kmean * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
@@ -446,6 +531,9 @@ def run_ours(args):
             tr = json.load(open(tp)).get(args.workload)
             traffic = tr.get(str(world)) if isinstance(tr, dict) else None
         cfg = config_of(args, n_total, world)
+        if args.shard_of > 1:
+            cfg["parallelism"] = (f"PROFILING AID: the shard of rank {args.shard_rank} of {args.shard_of} on one GPU "
+                                  f"({n_local} queries, tiles [{tile_lo}, {tile_hi})); not a benchmark line")
         if world > 1:
             cfg["parallelism"] += (" kernel per rank over NVLink peer memory (igd_b200_reducer)" if reducer is not None
                                    else " NCCL int64 allreduce")
@@ -461,7 +549,7 @@ def run_ours(args):
                     "parity_seconds": orc.get("full_seconds"), "parity_cores": orc.get("full_cores")},
             "e2e": {"value": n_total / (e2e_s / args.steps), "unit": UNIT, "ms_per_step": e2e_s / args.steps * 1e3,
                     "h2d_bytes_per_step": 12 * n_total, "d2h_bytes_per_step": 8 * igd.nfiles * world,
-                    "single_call": e2e_single,
+                    "single_call": e2e_single, "phases_ms_rank0_one_step": e2e_phases,
                     "device_split_ms_last_step": e2e_split,
                     # the H2D leg runs at whatever the box's PCIe path gives at that moment: 16 to 54 GB/s were
                     # seen on this pool's boxes for the same pinned buffers (profiles/microbench/h2d_*.py)
@@ -470,8 +558,10 @@ def run_ours(args):
                     "cpu_binding": numa,
                     "api": "igd_b200_count_submit / igd_b200_count_wait (C-ABI, pinned host buffers; the K steps as a stream, "
                            "two batches in flight: H2D of step k + 1 under the search of step k)" if world == 1 else
-                           "pinned H2D of this rank's 1/N of the queries + igd_b200_shard_* (cost, all-reduce, cuts, partition, "
-                           "all-to-all) + igd_b200_count_device_tiles + hits[] exchange + D2H"},
+                           "pinned H2D of this rank's 1/N of the queries + igd_b200_shard_* (cost, all-reduce, cuts) + "
+                           "igd_b200_dispatch (partition fused with its all-to-all over NVLink peer memory) + "
+                           "igd_b200_count_device_tiles + hits[] exchange + D2H; the K steps as a stream: "
+                           "the H2D of step k + 1 on a copy stream under step k"},
             "file_ingest": None if file_s is None else {
                 "value": file_n / file_s, "unit": UNIT, "ms": file_s * 1e3, "file_bytes": file_bytes, "n_queries": file_n,
                 "api": "search(igd, qFile) -- BED text (warm page cache) -> pinned chunks -> H2D -> parsed on the "
@@ -480,7 +570,7 @@ def run_ours(args):
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "k_count_rank (count-mode search, 16-bit START / END entries)",
-                         "kernel_ms": kmean, "stages_ms_rank0": stages,
+                         "kernel_ms": kmean, "stages_ms_rank0": stages, "per_rank": per_rank,
                          "bytes_per_launch": own_bytes,
                          "bytes_definition": "what the search kernel reads per launch: 32 B per item descriptor + 4 B per "
                                              "(entry, item) + 4 B per segment, counted by the planner on the device "
@@ -499,6 +589,9 @@ def run_ours(args):
     if reducer is not None:
         dist.barrier()
         reducer.close()
+    if world > 1:
+        dist.barrier()
+        sharder.close()
     igd.close()
     if world > 1:
         dist.destroy_process_group()
@@ -692,6 +785,8 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the whole-set oracle run (profiling runs)")
     ap.add_argument("--mode", default="count", choices=["count", "f", "m"],
                     help="count (the contract line); f / m: the other sharded modes, on cfg2 unless --workload says otherwise")
+    ap.add_argument("--shard-of", type=int, default=1, help="profiling aid (N = 1 only): run the shard one rank of this many would get")
+    ap.add_argument("--shard-rank", type=int, default=0)
     ap.add_argument("--ref-sample", type=int, default=1_000_000, help="queries per step of --impl reference")
     args = ap.parse_args()
     claim_stdout()

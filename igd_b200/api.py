@@ -141,11 +141,19 @@ def load_library():
     L.igd_b200_stage_timing.argtypes = [vp, C.c_int]
     L.igd_b200_last_stage_ms.restype = C.c_int
     L.igd_b200_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float * 4)]
+    L.igd_b200_dispatcher_create.restype = vp
+    L.igd_b200_dispatcher_create.argtypes = [vp, C.c_int, C.c_int, C.c_int64]
+    L.igd_b200_dispatcher_handle.argtypes = [vp, vp]
+    L.igd_b200_dispatcher_connect.argtypes = [vp, vp]
+    L.igd_b200_dispatch.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),
+                                    C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.igd_b200_dispatcher_destroy.argtypes = [vp]
     L.igd_b200_reducer_create.restype = vp
     L.igd_b200_reducer_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int32]
     L.igd_b200_reducer_handle.argtypes = [vp, vp]
     L.igd_b200_reducer_connect.argtypes = [vp, vp]
     L.igd_b200_reducer_allreduce.argtypes = [vp, vp, vp]
+    L.igd_b200_reducer_allreduce_into.argtypes = [vp, vp, vp, vp]
     L.igd_b200_reducer_status.restype = C.c_int
     L.igd_b200_reducer_status.argtypes = [vp]
     L.igd_b200_reducer_destroy.argtypes = [vp]
@@ -230,6 +238,11 @@ class HitsReducer:
         if self._L.igd_b200_reducer_allreduce(self._r, d_hits_ptr, stream):
             raise IGDError(last_error())
 
+    def allreduce_into(self, d_in_ptr: int, d_out_ptr: int, stream: int = 0) -> None:
+        """d_out = sum over the ranks of d_in; d_in is left zeroed (ready for the next batch's counts)."""
+        if self._L.igd_b200_reducer_allreduce_into(self._r, d_in_ptr, d_out_ptr, stream):
+            raise IGDError(last_error())
+
     def status(self) -> int:
         """0 = every exchange so far met all its peers (waits for the device)."""
         return int(self._L.igd_b200_reducer_status(self._r))
@@ -238,6 +251,63 @@ class HitsReducer:
         if getattr(self, "_r", None):
             self._L.igd_b200_reducer_destroy(self._r)
             self._r = None
+
+
+def _exchange_ipc_handles(mine_bytes, group, on):
+    """all ranks' 64-byte CUDA IPC handles, rank-major, exchanged with torch.distributed"""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(list(mine_bytes), dtype=torch.uint8, device=on)
+    allh = [torch.zeros_like(t) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(allh, t, group=group)
+    return bytes(torch.cat(allh).cpu().tolist())
+
+
+class QueryDispatcher:
+    """The query exchange of a multi-GPU search over NVLink peer memory (igd_b200_dispatcher_*, igd_dev_shard.cu): the
+    partition by destination rank fused with its all-to-all -- every query is stored straight into the receive buffer
+    of the rank that will search it.  ``cap`` = queries a receive buffer holds (the whole query set is always enough)."""
+
+    def __init__(self, igd: "IGD", device: int, cap: int, group=None):
+        import torch
+        import torch.distributed as dist
+        self._L = load_library()
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        on = torch.device("cuda", device) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+
+        def everybody(ok: bool) -> bool:
+            f = torch.tensor([1 if ok else 0], dtype=torch.int32, device=on)
+            dist.all_reduce(f, op=dist.ReduceOp.MIN, group=group)
+            return bool(f.item())
+
+        err = ""
+        mine = (C.c_uint8 * 64)()
+        self._x = self._L.igd_b200_dispatcher_create(igd._need(), self.rank, self.world, int(cap))
+        if not self._x or self._L.igd_b200_dispatcher_handle(self._x, mine):
+            err = last_error() or "igd_b200_dispatcher_create failed"
+        blob = _exchange_ipc_handles(mine, group, on)
+        good = everybody(not err)
+        if good and self.world > 1:
+            if self._L.igd_b200_dispatcher_connect(self._x, C.c_char_p(blob)):
+                err = last_error() or "igd_b200_dispatcher_connect failed"
+            good = everybody(not err)           # also: every block is mapped everywhere before the first store
+        if not good:
+            self.close()
+            raise IGDError(err or "the peer-memory query exchange could not be set up on another rank")
+
+    def dispatch(self, n: int, d_ctg: int, d_qs: int, d_qe: int, d_cuts: int, stream: int = 0):
+        """-> (m, ctg_ptr, qs_ptr, qe_ptr, tile_lo, tile_hi): this rank's shard, device pointers into its receive buffer"""
+        o = [C.c_void_p() for _ in range(3)]
+        m, lo, hi = C.c_int64(), C.c_int32(), C.c_int32()
+        if self._L.igd_b200_dispatch(self._x, int(n), d_ctg, d_qs, d_qe, d_cuts, stream, C.byref(o[0]), C.byref(o[1]),
+                                     C.byref(o[2]), C.byref(m), C.byref(lo), C.byref(hi)):
+            raise IGDError(last_error())
+        return int(m.value), o[0].value, o[1].value, o[2].value, int(lo.value), int(hi.value)
+
+    def close(self) -> None:
+        if getattr(self, "_x", None):
+            self._L.igd_b200_dispatcher_destroy(self._x)
+            self._x = None
 
 
 class QuerySet:

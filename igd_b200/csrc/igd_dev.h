@@ -120,6 +120,19 @@ int igdb_dev_shard_partition(igdb_dev *d, int64_t n, const int32_t *d_ctg, const
                              const int32_t *d_cuts, int32_t n_parts, int32_t *o_ctg, int32_t *o_qs, int32_t *o_qe,
                              int64_t *d_part_off, int32_t *d_reach, void *stream);
 
+/* The partition fused with its all-to-all over peer memory (igd_dev_shard.cu): a rank's queries go straight into the
+ * receive buffers (cap queries each) of the ranks that own their first tile.  create -> handle (64-byte CUDA IPC
+ * handle of this rank's block) -> connect (all ranks' handles, rank-major) -> dispatch any number of times, the same
+ * number on every rank, each followed on the same stream by the search of the shard it returned. */
+typedef struct igdb_dispatcher igdb_dispatcher;
+igdb_dispatcher *igdb_dispatcher_create(igdb_dev *d, int rank, int world, int64_t cap);
+int igdb_dispatcher_handle(igdb_dispatcher *x, void *out64);
+int igdb_dispatcher_connect(igdb_dispatcher *x, const void *handles);
+int igdb_dispatch(igdb_dispatcher *x, int64_t n, const int32_t *d_ctg, const int32_t *d_qs, const int32_t *d_qe,
+                  const int32_t *d_cuts, void *stream, int32_t **o_ctg, int32_t **o_qs, int32_t **o_qe, int64_t *m,
+                  int32_t *tile_lo, int32_t *tile_hi);
+void igdb_dispatcher_destroy(igdb_dispatcher *x);
+
 /* The exchange step of the multi-GPU count path (igd_dev_p2p.cu): hits[] summed over the ranks by one kernel per
  * rank over peer memory.  create -> handle (64-byte CUDA IPC handle of this rank's mailbox) -> connect (all ranks'
  * handles, rank-major) -> allreduce any number of times, the same number on every rank. */
@@ -128,6 +141,8 @@ igdb_reducer *igdb_reducer_create(int device, int rank, int world, int32_t nfile
 int igdb_reducer_handle(igdb_reducer *r, void *out64);
 int igdb_reducer_connect(igdb_reducer *r, const void *handles);
 int igdb_reducer_allreduce(igdb_reducer *r, unsigned long long *d_hits, void *stream);
+/* out of place: d_out = the sum over the ranks of their d_in, and d_in is left zeroed */
+int igdb_reducer_allreduce_into(igdb_reducer *r, unsigned long long *d_in, unsigned long long *d_out, void *stream);
 int igdb_reducer_status(igdb_reducer *r);       /* 0 ok; k > 0: a wait for rank k - 1 timed out; < 0: CUDA error */
 void igdb_reducer_destroy(igdb_reducer *r);
 

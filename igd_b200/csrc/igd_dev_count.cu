@@ -36,12 +36,15 @@ __device__ __forceinline__ void cseg_walk(const DbView &db, int64_t n, const int
         __syncthreads();
     }
     const int nbp = db.nbp;
-    const int64_t q0 = (int64_t)blockIdx.x * (CSEG_T * CSEG_Q) + threadIdx.x;
     pdl_wait();                                             // the queries / counters of the previous launch
+    int nabn = 0;
+    // grid-stride over blocks of CSEG_T * CSEG_Q queries: the grid is one resident wave at most, so a batch a little
+    // larger than what the GPU holds at once does not pay for a second, nearly empty wave
+    for (int64_t q0 = (int64_t)blockIdx.x * (CSEG_T * CSEG_Q) + threadIdx.x; q0 - threadIdx.x < n;
+         q0 += (int64_t)gridDim.x * (CSEG_T * CSEG_Q)) {
     int c[CSEG_Q], s[CSEG_Q], e[CSEG_Q], tile[CSEG_Q], nlast[CSEG_Q], bd[CSEG_Q];
     uint32_t r[CSEG_Q];
     bool ok[CSEG_Q];
-    int nabn = 0;
 #pragma unroll
     for (int k = 0; k < CSEG_Q; ++k) {
         const int64_t q = q0 + (int64_t)k * CSEG_T;
@@ -85,7 +88,6 @@ __device__ __forceinline__ void cseg_walk(const DbView &db, int64_t n, const int
             if (ok[k] && r[k] != Q_NOSEG) first(tile[k], s[k], e[k], bd[k], r[k]);
         }
     }
-    if (MODE == M_PACKED && nabn) atomicAdd(abn, (uint32_t)(abn_sign * nabn));   // left to the M_ABN32 pipeline
 #pragma unroll
     for (int k = 0; k < CSEG_Q; ++k) {
         if (!ok[k]) continue;
@@ -94,6 +96,8 @@ __device__ __forceinline__ void cseg_walk(const DbView &db, int64_t n, const int
             if (mm.y > 0 && e[k] > mm.w) later(t, s[k], e[k], bd[k] + (t - tile[k]) * nbp);
         }
     }
+    }
+    if (MODE == M_PACKED && nabn) atomicAdd(abn, (uint32_t)(abn_sign * nabn));   // left to the M_ABN32 pipeline
 }
 
 template <bool V, int MODE>
@@ -1131,7 +1135,11 @@ __global__ void __launch_bounds__(RK_MAXW * 32, 1) k_count_rank(const CountArgs 
     cp_async_wait<0>();
     if (SMEM) {
         __syncthreads();
-        for (int f = threadIdx.x; f < db.nfiles; f += blockDim.x) {
+        // every CTA starts at its own place of the file range: the CTAs finish together, and the same counter from
+        // all of them at once is one L2 atomic unit serving 148 requests while the others idle
+        const int off = (int)(((long long)blockIdx.x * db.nfiles) / gridDim.x);
+        for (int i = threadIdx.x; i < db.nfiles; i += blockDim.x) {
+            const int f = i + off < db.nfiles ? i + off : i + off - db.nfiles;
             const uint32_t c = hist[f];                                 // a sum modulo 2^32 of +H and -K: signed
             if (c) atomicAdd(&a.hits[f], (unsigned long long)(long long)(int32_t)c);
         }
@@ -1203,7 +1211,7 @@ int enqueue_count_t(igdb_dev *d, const igdb_dev::Pending &p)
     const unsigned long long item_cap =
         (unsigned long long)std::min<int64_t>(d->item_cap - CAP_SLACK, item_limit(d, grid));
     const int thr = CSEG_T;
-    const int nb = (int)((p.n + CSEG_T * CSEG_Q - 1) / (CSEG_T * CSEG_Q));
+    const int nb = (int)std::min<int64_t>((p.n + CSEG_T * CSEG_Q - 1) / (CSEG_T * CSEG_Q), (int64_t)d->sm_count * (2048 / CSEG_T));
     const int32_t tlo = std::max(0, std::min(p.tile_lo, d->T)), thi = std::max(tlo, std::min(p.tile_hi, d->T));
     if (d->plan_grid_max == 0) {
         // k_plan's CTAs wait for each other, so all of them must be resident at once: never more than the
@@ -1250,7 +1258,8 @@ int enqueue_count_t(igdb_dev *d, const igdb_dev::Pending &p)
         }
         // the others: a warp per tile; tiles of W2_NG groups or more (none in the BASELINE configurations) by the
         // general kernel
-        const int64_t tpw = sparse ? 32 : 8;                        // tiles per warp and turn
+        // tiles per warp and turn: few enough that a small tile range (a shard of a multi-GPU search) still fills the GPU
+        const int64_t tpw = sparse ? 32 : std::max<int64_t>(1, std::min<int64_t>(8, nt / ((int64_t)d->sm_count * 40)));
         const unsigned wgrid = (unsigned)std::min<int64_t>((nt + 8 * tpw - 1) / (8 * tpw), (int64_t)d->sm_count * 48);
         CK(launch_pdl(k_windows_warp, wgrid, 256, 0, st, db, (const int4 *)d->tplan,
                       (const uint32_t *)(const void *)d->csegs, (const unsigned long long *)d->plan_tot, seg_cap, item_cap,

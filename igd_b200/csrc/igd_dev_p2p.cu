@@ -1,9 +1,9 @@
 // igd_b200 CUDA layer -- the one exchange step of the multi-GPU count path: the sum of the per-rank hits[] over
 // all ranks, done by ONE small kernel over NVLink peer memory instead of an NCCL all-reduce.
 //
-// One process per GPU.  Every rank owns a mailbox in its HBM -- recv[2][world][nfiles] (uint64) and flag[2][world]
-// -- exported to the other processes as a CUDA IPC handle.  An all-reduce of epoch e is one launch of
-// k_hits_exchange per rank:
+// One process per GPU.  Every rank owns a mailbox in its HBM -- recv[2][world][nfiles] (uint64) and
+// flag[2][world][slices] -- exported to the other processes as a CUDA IPC handle.  An all-reduce of epoch e is one
+// launch of k_hits_exchange per rank, the file range cut into slices of 512 files, one CTA each; per slice:
 //   1. push: the rank stores its hits[] into slot [e & 1][rank] of EVERY rank's mailbox (its own included) --
 //      plain coalesced stores, a few KB per peer, travelling over NVLink / NVSwitch -- then fences (system scope)
 //      and raises flag[e & 1][rank] = e in each mailbox with a release store;
@@ -42,32 +42,40 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 }
 
 constexpr unsigned long long EXCHANGE_TIMEOUT_NS = 20ull * 1000 * 1000 * 1000;
+constexpr int EX_MAXCTA = 32;               // the file range is cut into at most this many slices, one CTA each
 
-__global__ void __launch_bounds__(1024) k_hits_exchange(unsigned long long *__restrict__ hits, int32_t nfiles, int rank,
-                                                         int world, unsigned long long epoch,
-                                                         unsigned long long *const *__restrict__ peer)
+// CTA c of every rank handles slice c of the files -- push, flag[.][rank][c], wait for flag[.][q][c] of all ranks q,
+// sum -- so the slices are exchanged side by side and no CTA waits for another CTA of its own GPU.
+// in == out: the classic in-place all-reduce.  in != out: out = the sum and `in` is left ZEROED, ready to take the
+// next batch's counts (what a search step otherwise spends one more launch on).
+__global__ void __launch_bounds__(512) k_hits_exchange(const unsigned long long *in, unsigned long long *out, int zero_in,
+                                                        int32_t nfiles, int rank, int world, unsigned long long epoch,
+                                                        unsigned long long *const *__restrict__ peer)
 {
+    const int G = gridDim.x, c = blockIdx.x;
+    const int per = (nfiles + G - 1) / G, f0 = min(c * per, nfiles), f1 = min(f0 + per, nfiles);
     const size_t slot = (size_t)(epoch & 1) * (size_t)world * (size_t)nfiles;
-    const size_t flags = (size_t)2 * (size_t)world * (size_t)nfiles + (size_t)(epoch & 1) * (size_t)world;
+    const size_t flags = (size_t)2 * (size_t)world * (size_t)nfiles + (size_t)(epoch & 1) * (size_t)world * EX_MAXCTA;
     // 1. push
-    for (int p = 0; p < world; ++p) {
-        unsigned long long *dst = peer[p] + slot + (size_t)rank * (size_t)nfiles;
-        for (int f = threadIdx.x; f < nfiles; f += blockDim.x) dst[f] = hits[f];
+    for (int f = f0 + threadIdx.x; f < f1; f += blockDim.x) {
+        const unsigned long long v = in[f];
+        for (int p = 0; p < world; ++p) peer[p][slot + (size_t)rank * (size_t)nfiles + f] = v;
+        if (zero_in) const_cast<unsigned long long *>(in)[f] = 0;
     }
     __threadfence_system();
     __syncthreads();
-    if ((int)threadIdx.x < world) st_release_sys(peer[threadIdx.x] + flags + rank, epoch);
-    // 2. wait for everybody's push into MY mailbox (a peer that never arrives must not hang the GPU: after
-    //    EXCHANGE_TIMEOUT_NS the wait gives up and leaves a mark that igdb_reducer_status reports)
+    if ((int)threadIdx.x < world) st_release_sys(peer[threadIdx.x] + flags + (size_t)rank * EX_MAXCTA + c, epoch);
+    // 2. wait for everybody's push of this slice into MY mailbox (a peer that never arrives must not hang the GPU:
+    //    after EXCHANGE_TIMEOUT_NS the wait gives up and leaves a mark that igdb_reducer_status reports)
     if ((int)threadIdx.x < world) {
-        const unsigned long long *fl = peer[rank] + flags + threadIdx.x;
+        const unsigned long long *fl = peer[rank] + flags + (size_t)threadIdx.x * EX_MAXCTA + c;
         unsigned long long t0 = 0, now = 0;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
         while (ld_acquire_sys(fl) != epoch) {
-            __nanosleep(100);
+            __nanosleep(64);
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
             if (now - t0 > EXCHANGE_TIMEOUT_NS) {
-                peer[rank][(size_t)2 * world * nfiles + (size_t)2 * world] = 1ull + threadIdx.x;    // status word
+                peer[rank][(size_t)2 * world * nfiles + (size_t)2 * world * EX_MAXCTA] = 1ull + threadIdx.x;    // status word
                 break;
             }
         }
@@ -75,15 +83,15 @@ __global__ void __launch_bounds__(1024) k_hits_exchange(unsigned long long *__re
     __syncthreads();
     // 3. sum in rank order
     const unsigned long long *mine = peer[rank] + slot;
-    for (int f = threadIdx.x; f < nfiles; f += blockDim.x) {
+    for (int f = f0 + threadIdx.x; f < f1; f += blockDim.x) {
         unsigned long long s = 0;
         for (int q = 0; q < world; ++q) s += mine[(size_t)q * (size_t)nfiles + f];
-        hits[f] = s;
+        out[f] = s;
     }
 }
 
-// recv[2][world][nfiles], flag[2][world], one status word
-size_t mailbox_words(int world, int32_t nfiles) { return (size_t)2 * world * nfiles + (size_t)2 * world + 1; }
+// recv[2][world][nfiles], flag[2][world][EX_MAXCTA], one status word
+size_t mailbox_words(int world, int32_t nfiles) { return (size_t)2 * world * nfiles + (size_t)2 * world * EX_MAXCTA + 1; }
 
 }  // namespace
 
@@ -139,22 +147,40 @@ int igdb_reducer_connect(igdb_reducer *r, const void *handles)
     return 0;
 }
 
-// d_hits[nfiles] (uint64, on this rank's device) becomes the sum over all ranks; enqueued on `stream`.
-// Every rank must call it the same number of times.
-int igdb_reducer_allreduce(igdb_reducer *r, unsigned long long *d_hits, void *stream)
+// d_out[nfiles] (uint64, on this rank's device) = the sum over all ranks of their d_in[]; enqueued on `stream`.
+// d_in == d_out: in place.  Otherwise d_in is left zeroed.  Every rank must call it the same number of times.
+static int reducer_launch(igdb_reducer *r, unsigned long long *d_in, unsigned long long *d_out, void *stream)
 {
     g_err[0] = 0;
     if (!r->connected && r->world > 1) {
         snprintf(g_err, sizeof g_err, "reducer: not connected");
         return -1;
     }
-    if (r->world == 1 || r->nfiles == 0) return 0;
+    if (r->nfiles == 0) return 0;
     CK(cudaSetDevice(r->device));
+    if (r->world == 1) {
+        if (d_in != d_out) {
+            CK(cudaMemcpyAsync(d_out, d_in, (size_t)r->nfiles * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+            CK(cudaMemsetAsync(d_in, 0, (size_t)r->nfiles * 8, (cudaStream_t)stream));
+        }
+        return 0;
+    }
     ++r->epoch;
-    const int threads = std::max(64, std::min(1024, (r->nfiles + 31) / 32 * 32));
-    k_hits_exchange<<<1, threads, 0, (cudaStream_t)stream>>>(d_hits, r->nfiles, r->rank, r->world, r->epoch, r->d_peer);
+    const int grid = std::max(1, std::min(EX_MAXCTA, (r->nfiles + 511) / 512));
+    k_hits_exchange<<<grid, 512, 0, (cudaStream_t)stream>>>(d_in, d_out, d_in != d_out, r->nfiles, r->rank, r->world,
+                                                            r->epoch, r->d_peer);
     CK(cudaGetLastError());
     return 0;
+}
+
+int igdb_reducer_allreduce(igdb_reducer *r, unsigned long long *d_hits, void *stream)
+{
+    return reducer_launch(r, d_hits, d_hits, stream);
+}
+
+int igdb_reducer_allreduce_into(igdb_reducer *r, unsigned long long *d_in, unsigned long long *d_out, void *stream)
+{
+    return reducer_launch(r, d_in, d_out, stream);
 }
 
 // 0 = every exchange so far met all its peers; k > 0 = a wait for rank k - 1 timed out (results are then invalid).

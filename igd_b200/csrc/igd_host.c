@@ -670,6 +670,23 @@ int64_t search(igd_b200_t *h, const char *qFile, int32_t v, int64_t *hits)
 }
 
 /* ---- the multi-GPU exchange step (igd_dev_p2p.cu) ---------------------------------------------------------- */
+/* the partition fused with its all-to-all over peer memory (igd_dev_shard.cu) */
+igd_b200_dispatcher *igd_b200_dispatcher_create(igd_b200_t *h, int rank, int world, int64_t cap)
+{
+    g_err[0] = 0;
+    return igdb_dispatcher_create(h->dev, rank, world, cap);
+}
+int igd_b200_dispatcher_handle(igd_b200_dispatcher *x, void *out64) { g_err[0] = 0; return igdb_dispatcher_handle(x, out64); }
+int igd_b200_dispatcher_connect(igd_b200_dispatcher *x, const void *handles) { g_err[0] = 0; return igdb_dispatcher_connect(x, handles); }
+int igd_b200_dispatch(igd_b200_dispatcher *x, int64_t n, const int32_t *d_ctg, const int32_t *d_qs, const int32_t *d_qe,
+                      const int32_t *d_cuts, void *stream, int32_t **d_out_ctg, int32_t **d_out_qs, int32_t **d_out_qe,
+                      int64_t *m, int32_t *tile_lo, int32_t *tile_hi)
+{
+    g_err[0] = 0;
+    return igdb_dispatch(x, n, d_ctg, d_qs, d_qe, d_cuts, stream, d_out_ctg, d_out_qs, d_out_qe, m, tile_lo, tile_hi);
+}
+void igd_b200_dispatcher_destroy(igd_b200_dispatcher *x) { igdb_dispatcher_destroy(x); }
+
 igd_b200_reducer *igd_b200_reducer_create(int device, int rank, int world, int32_t nfiles)
 {
     g_err[0] = 0;
@@ -681,6 +698,11 @@ int igd_b200_reducer_allreduce(igd_b200_reducer *r, uint64_t *d_hits, void *stre
 {
     g_err[0] = 0;
     return igdb_reducer_allreduce(r, (unsigned long long *)d_hits, stream);
+}
+int igd_b200_reducer_allreduce_into(igd_b200_reducer *r, uint64_t *d_in, uint64_t *d_out, void *stream)
+{
+    g_err[0] = 0;
+    return igdb_reducer_allreduce_into(r, (unsigned long long *)d_in, (unsigned long long *)d_out, stream);
 }
 int igd_b200_reducer_status(igd_b200_reducer *r) { g_err[0] = 0; return igdb_reducer_status(r); }
 void igd_b200_reducer_destroy(igd_b200_reducer *r) { igdb_reducer_destroy(r); }

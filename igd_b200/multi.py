@@ -43,9 +43,13 @@ class DeviceSharder:
     """K8 on the device (igd_dev_shard.cu through the C-ABI): every rank holds ANY 1/N of the query set in HBM;
     ``shard`` leaves it holding the queries whose first bin lies in its contiguous tile range, the ranges balanced
     by the prefix sum of estimated scan bytes.  Collectives (NCCL over NVLink): one all-reduce of the per-tile cost
-    (nTiles + 1 words), one of the per-destination reach, and the all-to-all of the queries themselves."""
+    (nTiles + 1 words), one all-gather of the per-destination counts and reach, and ONE all-to-all of the queries
+    themselves, as (ctg, qs, qe) rows."""
 
-    def __init__(self, engine, dev, group=None):
+    def __init__(self, engine, dev, group=None, peer_cap: int = 0):
+        """peer_cap > 0: the queries travel through the library's own exchange over NVLink peer memory
+        (api.QueryDispatcher, receive buffers of peer_cap queries -- the size of the whole query set is always
+        enough) instead of an NCCL all-to-all."""
         import torch
         import torch.distributed as dist
         self.e, self.dev, self.group, self.dist, self.torch = engine, torch.device(dev), group, dist, torch
@@ -56,6 +60,22 @@ class DeviceSharder:
         self.off = torch.zeros(self.world + 1, dtype=torch.int64, device=self.dev)
         self.reach = torch.zeros(self.world, dtype=torch.int32, device=self.dev)
         self.buf = None
+        self.marks = None           # diagnostics: set to [] to collect (label, CUDA event) at the phase boundaries
+        self.peer = None
+        if peer_cap > 0:
+            from .api import QueryDispatcher
+            self.peer = QueryDispatcher(engine, self.dev.index or 0, peer_cap, group)
+
+    def close(self):
+        if self.peer is not None:
+            self.peer.close()
+            self.peer = None
+
+    def _mark(self, label):
+        if self.marks is not None:
+            ev = self.torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.marks.append((label, ev))
 
     def shard(self, d_ctg, d_qs, d_qe):
         """torch int32 device tensors (this rank's slice, any order) -> (ctg, qs, qe, tile_lo, tile_hi) of its shard.
@@ -63,27 +83,50 @@ class DeviceSharder:
         torch, dist, W = self.torch, self.dist, self.world
         n = int(d_ctg.shape[0])
         st = torch.cuda.current_stream(self.dev).cuda_stream
+        self._mark("start")
         self.cost.zero_()
         self.e.shard_cost(n, d_ctg.data_ptr(), d_qs.data_ptr(), d_qe.data_ptr(), self.cost.data_ptr(), st)
+        self._mark("cost")
         dist.all_reduce(self.cost, group=self.group)
+        self._mark("cost_allreduce")
         self.e.shard_cuts(self.cost.data_ptr(), W, self.cuts.data_ptr(), st)
+        if self.peer is not None:
+            # partition + all-to-all in the library's kernels: the shard arrives in this rank's receive buffer
+            from .api import device_view
+            m, p_c, p_s, p_e, lo, hi = self.peer.dispatch(n, d_ctg.data_ptr(), d_qs.data_ptr(), d_qe.data_ptr(),
+                                                          self.cuts.data_ptr(), st)
+            self._mark("dispatch")
+            if m == 0:
+                z = torch.empty(0, dtype=torch.int32, device=self.dev)
+                return z, z, z, lo, hi
+            return tuple(torch.as_tensor(device_view(p, m, "<i4"), device=self.dev) for p in (p_c, p_s, p_e)) + (lo, hi)
         if self.buf is None or self.buf.shape[1] < n:
             self.buf = torch.empty((3, max(n, 1)), dtype=torch.int32, device=self.dev)
         o = self.buf
         self.e.shard_partition(n, d_ctg.data_ptr(), d_qs.data_ptr(), d_qe.data_ptr(), self.cuts.data_ptr(), W,
                                o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), self.off.data_ptr(),
                                self.reach.data_ptr(), st)
-        dist.all_reduce(self.reach, op=dist.ReduceOp.MAX, group=self.group)
-        send = (self.off[1:] - self.off[:-1]).contiguous()
-        recv = torch.empty_like(send)
-        dist.all_to_all_single(recv, send, group=self.group)
-        meta = torch.cat([send, recv, self.cuts.long(), self.reach.long()]).cpu().tolist()     # the one host sync
-        send_l, recv_l = meta[:W], meta[W:2 * W]
-        cuts, reach = meta[2 * W:3 * W + 1], meta[3 * W + 1:]
+        self._mark("cuts_partition")
+        # what every rank must know about every other one -- how many queries go where, how far each destination's
+        # queries reach -- in ONE all-gather (with this rank's copy of the cuts riding along), then the one host sync
+        mine = torch.cat([self.off[1:] - self.off[:-1], self.reach.long(), self.cuts.long()])
+        meta = torch.empty((W, mine.numel()), dtype=torch.int64, device=self.dev)
+        dist.all_gather_into_tensor(meta, mine, group=self.group)
+        self._mark("meta_gather")
+        meta = meta.cpu()
+        send_l, recv_l = meta[self.rank, :W].tolist(), meta[:, self.rank].tolist()
+        reach = meta[:, W:2 * W].max(dim=0).values.tolist()
+        cuts = meta[self.rank, 2 * W:].tolist()
         m = int(sum(recv_l))
-        out = torch.empty((3, max(m, 1)), dtype=torch.int32, device=self.dev)
-        for k in range(3):
-            dist.all_to_all_single(out[k, :m], o[k, :n], recv_l, send_l, group=self.group)
+        # the queries themselves: one all-to-all of (ctg, qs, qe) rows
+        rows = torch.stack((o[0, :n], o[1, :n], o[2, :n]), dim=1)
+        got = torch.empty((max(m, 1), 3), dtype=torch.int32, device=self.dev)
+        dist.all_to_all_single(got[:m], rows, recv_l, send_l, group=self.group)
+        self._mark("all_to_all")
+        out = got[:m].t().contiguous()
+        self._mark("transpose")
+        if m == 0:
+            out = torch.empty((3, 1), dtype=torch.int32, device=self.dev)
         lo = int(cuts[self.rank])
         return out[0, :m], out[1, :m], out[2, :m], lo, max(int(reach[self.rank]), lo)
 
@@ -151,10 +194,10 @@ class ShardedSearch:
         the reference's order -- what a single GPU returns.  None elsewhere."""
         import torch
         dist = self.dist
+        if str(self.dev) != "cpu" and hasattr(self.e, "full_device"):
+            return self._full_on_device(ctg, qs, qe, dst)
         order, cs, ss, es, b = self._plan(ctg, qs, qe)
         lo, hi = b[self.rank], b[self.rank + 1]
-        if str(self.dev) != "cpu" and hasattr(self.e, "full_device"):
-            return self._full_on_device(order, cs[lo:hi], ss[lo:hi], es[lo:hi], b, dst)
         qoff, s, e, f = self.e.full(cs[lo:hi], ss[lo:hi], es[lo:hi])
         mine = torch.tensor([int(qoff[-1])], dtype=torch.int64, device=self.dev)
         sizes = [torch.zeros_like(mine) for _ in range(self.world)]
@@ -192,50 +235,94 @@ class ShardedSearch:
         src = np.repeat(soff[pos], cnt_orig) + (np.arange(total) - np.repeat(qoff_o[:-1], cnt_orig))
         return qoff_o, pay[0][src], pay[1][src], pay[2][src]
 
-    def _full_on_device(self, order, cs, ss, es, b, dst):
-        """-f with the lists resident in HBM from the search to the restored order (one D2H at the very end)."""
+    def _pinned(self, name, n, dtype):
+        """a page-locked host buffer kept between calls (the lists come back at PCIe speed, like a single GPU's arena)"""
+        import torch
+        bufs = self.__dict__.setdefault("_pin", {})
+        t = bufs.get(name)
+        if t is None or t.numel() < n or t.dtype != dtype:
+            t = torch.empty(max(int(n * 1.25), 1024), dtype=dtype).pin_memory()
+            bufs[name] = t
+        return t[:n]
+
+    def _full_on_device(self, ctg, qs, qe, dst):
+        """-f with everything after the upload on the devices: the shard plan (per-tile cost of the whole set by the
+        library's kernels, cuts, each query's destination = the range its first tile falls in), the search
+        (igd_b200_full_device: lists left in HBM), the gather over NCCL, the caller's order restored by
+        igd_b200_full_restore, and ONE D2H of the result into page-locked buffers kept by this object (the arrays
+        returned are views of them, valid until the next call)."""
         import torch
 
         from .api import device_view
-        dist, dev = self.dist, self.dev
-        n = len(cs)
-        d_c, d_s, d_e = self._t(cs), self._t(ss), self._t(es)
-        stream = torch.cuda.current_stream().cuda_stream
-        total, p_qoff, p_lists = self.e.full_device(n, d_c.data_ptr(), d_s.data_ptr(), d_e.data_ptr(), stream)
-        qoff = torch.as_tensor(device_view(p_qoff, n + 1, "<i8"), device=dev)
+        dist, dev, W, e, hdr = self.dist, self.dev, self.world, self.e, self.hdr
+        n = len(ctg)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        d = [self._t(np.ascontiguousarray(x, np.int32)) for x in (ctg, qs, qe)]
+        T = int(e.ntiles)
+        if getattr(self, "_tb", None) is None:
+            self._tb = torch.from_numpy(np.ascontiguousarray(hdr["tbase"], np.int64)).to(dev)
+            self._nt = torch.from_numpy(np.ascontiguousarray(hdr["ntile"], np.int64)).to(dev)
+        cost = torch.zeros(T + 1, dtype=torch.int64, device=dev)
+        cuts = torch.zeros(W + 1, dtype=torch.int32, device=dev)
+        e.shard_cost(n, d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), cost.data_ptr(), st)
+        e.shard_cuts(cost.data_ptr(), W, cuts.data_ptr(), st)
+        c = d[0].long()
+        ok = (c >= 0) & (c < hdr["nctg"])
+        c0 = torch.where(ok, c, torch.zeros_like(c))
+        n1 = torch.div(d[1].long(), hdr["nbp"], rounding_mode="floor")
+        ok &= (d[1] >= 0) & (n1 < self._nt[c0])
+        tile = torch.where(ok, self._tb[c0] + n1, torch.full_like(c, T))
+        dest = torch.where(ok, torch.bucketize(tile, cuts[1:-1].long().contiguous(), right=True),
+                           torch.full_like(c, W - 1))
+        perm = torch.argsort(dest, stable=True)         # concatenated shard order -> index in the caller's arrays
+        off = [0] + torch.cumsum(torch.bincount(dest, minlength=W), 0).tolist()       # (host sync)
+        mine = perm[off[self.rank]:off[self.rank + 1]]
+        m = int(mine.numel())
+        sc, ss, se = (x[mine].contiguous() for x in d)
+        total, p_qoff, p_lists = e.full_device(m, sc.data_ptr(), ss.data_ptr(), se.data_ptr(), st)
+        qoff = torch.as_tensor(device_view(p_qoff, m + 1, "<i8"), device=dev)
         cnt = (qoff[1:] - qoff[:-1]).contiguous()
         pay = (torch.as_tensor(device_view(p_lists, 3 * total, "<i4"), device=dev).view(3, total) if total
                else torch.zeros((3, 0), dtype=torch.int32, device=dev))
-        mine = torch.tensor([total], dtype=torch.int64, device=dev)
-        sizes = [torch.zeros_like(mine) for _ in range(self.world)]
-        dist.all_gather(sizes, mine, group=self.group)
-        sizes = [int(x.item()) for x in sizes]
+        tot_t = torch.tensor([total], dtype=torch.int64, device=dev)
+        sizes = torch.empty(W, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(sizes, tot_t, group=self.group)
+        sizes = sizes.tolist()
         if self.rank != dst:
-            dist.send(cnt, dst, group=self.group)
+            ops = [dist.P2POp(dist.isend, cnt, dst, group=self.group)] if m else []
             if total:
-                dist.send(pay.contiguous(), dst, group=self.group)
+                ops.append(dist.P2POp(dist.isend, pay.contiguous(), dst, group=self.group))
+            for w in (dist.batch_isend_irecv(ops) if ops else []):
+                w.wait()
+            torch.cuda.current_stream(dev).synchronize()    # the handle's list buffers are reused by the next call
             return None
-        cnts, pays = [], []
-        for r in range(self.world):
+        cnts, pays, ops = [], [], []
+        for r in range(W):
             if r == dst:
                 cnts.append(cnt), pays.append(pay)
                 continue
-            c = torch.empty(b[r + 1] - b[r], dtype=torch.int64, device=dev)
-            dist.recv(c, r, group=self.group)
-            p = torch.empty((3, sizes[r]), dtype=torch.int32, device=dev)
+            cr = torch.empty(off[r + 1] - off[r], dtype=torch.int64, device=dev)
+            pr = torch.empty((3, sizes[r]), dtype=torch.int32, device=dev)
+            if cr.numel():
+                ops.append(dist.P2POp(dist.irecv, cr, r, group=self.group))
             if sizes[r]:
-                dist.recv(p, r, group=self.group)
-            cnts.append(c), pays.append(p)
-        cnt_sorted, pay = torch.cat(cnts).contiguous(), torch.cat(pays, dim=1).contiguous()
-        nq, tot = len(order), int(pay.shape[1])
+                ops.append(dist.P2POp(dist.irecv, pr, r, group=self.group))
+            cnts.append(cr), pays.append(pr)
+        for w in (dist.batch_isend_irecv(ops) if ops else []):
+            w.wait()
+        cnt_sorted, pay_all = torch.cat(cnts).contiguous(), torch.cat(pays, dim=1).contiguous()
+        tot = int(pay_all.shape[1])
         # the caller's query order, restored by the library's kernels (igd_b200_full_restore)
-        d_order = torch.from_numpy(np.ascontiguousarray(order, np.int64)).to(dev)
-        qoff_o = torch.empty(nq + 1, dtype=torch.int64, device=dev)
+        qoff_o = torch.empty(n + 1, dtype=torch.int64, device=dev)
         out = torch.empty((3, max(tot, 1)), dtype=torch.int32, device=dev)
-        self.e.full_restore(nq, d_order.data_ptr(), cnt_sorted.data_ptr(), pay.data_ptr(), tot, qoff_o.data_ptr(),
-                            out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
-        out = out[:, :tot]
-        return (qoff_o.cpu().numpy(), out[0].cpu().numpy(), out[1].cpu().numpy(), out[2].cpu().numpy())
+        e.full_restore(n, perm.data_ptr(), cnt_sorted.data_ptr(), pay_all.data_ptr(), tot, qoff_o.data_ptr(),
+                       out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+        h_qoff, h_out = self._pinned("qoff", n + 1, torch.int64), self._pinned("lists", 3 * max(tot, 1), torch.int32)
+        h_qoff.copy_(qoff_o, non_blocking=True)
+        h_out.copy_(out.view(-1), non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        h = h_out.numpy().reshape(3, max(tot, 1))
+        return (h_qoff.numpy(), h[0, :tot], h[1, :tot], h[2, :tot])
 
     # ---- -m --------------------------------------------------------------------------------------
     def hitsmap(self, v: int = 0) -> np.ndarray:

@@ -126,6 +126,27 @@ int igd_b200_shard_partition(igd_b200_t *h, int64_t n, const int32_t *d_ctg, con
                              const int32_t *d_cuts, int32_t n_parts, int32_t *d_out_ctg, int32_t *d_out_qs,
                              int32_t *d_out_qe, int64_t *d_part_off, int32_t *d_reach, void *stream);
 
+/* shard_partition FUSED with the all-to-all that follows it, over NVLink peer memory: the scatter pass stores every
+ * query straight into the receive buffer (cap queries) of the rank that will search it, so the query exchange of a
+ * multi-GPU search is three launches per rank and no library collective (igd_dev_shard.cu: per-destination counts
+ * pushed to every rank -> every rank knows the whole source x destination matrix, hence every slot range -> stores
+ * into the peers' buffers -> flags).  One process per GPU:
+ *   x = igd_b200_dispatcher_create(h, rank, world, cap);       -- cap >= the largest shard (the whole query set is safe)
+ *   igd_b200_dispatcher_handle(x, h64);  ... exchange the 64-byte CUDA IPC handles ...  igd_b200_dispatcher_connect(x, all);
+ *   per batch: shard_cost, (sum over the ranks), shard_cuts, then
+ *   igd_b200_dispatch(x, n, d_ctg, d_qs, d_qe, d_cuts, stream, &ctg, &qs, &qe, &m, &lo, &hi);
+ *   igd_b200_count_device_tiles(h, m, ctg, qs, qe, v, d_hits, stream, lo, hi);   -- SAME stream, before the next dispatch
+ * dispatch returns when this rank's shard (m queries, device pointers into its receive buffer) is complete; every rank
+ * must call it the same number of times.  0 on success; a peer that does not arrive within 20 s is an error. */
+typedef struct igdb_dispatcher igd_b200_dispatcher;
+igd_b200_dispatcher *igd_b200_dispatcher_create(igd_b200_t *h, int rank, int world, int64_t cap);
+int igd_b200_dispatcher_handle(igd_b200_dispatcher *x, void *out64);
+int igd_b200_dispatcher_connect(igd_b200_dispatcher *x, const void *handles);
+int igd_b200_dispatch(igd_b200_dispatcher *x, int64_t n, const int32_t *d_ctg, const int32_t *d_qs, const int32_t *d_qe,
+                      const int32_t *d_cuts, void *stream, int32_t **d_out_ctg, int32_t **d_out_qs, int32_t **d_out_qe,
+                      int64_t *m, int32_t *tile_lo, int32_t *tile_hi);
+void igd_b200_dispatcher_destroy(igd_b200_dispatcher *x);
+
 /* -f: the overlaps themselves, in the reference's order (get_overlaps_f1, src/igd_search.c:537-620:
  * per query, bin n1 from the last start < qe downwards, then later bins ascending).
  * The arrays live in a pinned host arena owned by the handle (so that the lists come back at PCIe speed): they
@@ -227,6 +248,9 @@ igd_b200_reducer *igd_b200_reducer_create(int device, int rank, int world, int32
 int igd_b200_reducer_handle(igd_b200_reducer *r, void *out64);
 int igd_b200_reducer_connect(igd_b200_reducer *r, const void *handles);
 int igd_b200_reducer_allreduce(igd_b200_reducer *r, uint64_t *d_hits, void *stream);
+/* out of place: d_out = the sum over the ranks of their d_in, and d_in is left ZEROED -- ready to take the next batch's
+ * counts, so a search step needs no separate launch to clear its counters */
+int igd_b200_reducer_allreduce_into(igd_b200_reducer *r, uint64_t *d_in, uint64_t *d_out, void *stream);
 /* waits for the device; 0 = every exchange so far met all its peers, k > 0 = the wait for rank k - 1 gave up after
  * 20 s (a rank died or skipped a call: the sums are then invalid), negative = CUDA error */
 int igd_b200_reducer_status(igd_b200_reducer *r);

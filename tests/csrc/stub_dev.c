@@ -44,9 +44,15 @@ int igdb_dev_shard_cost(igdb_dev *d, int64_t n, const int32_t *a, const int32_t 
 int igdb_dev_shard_cuts(igdb_dev *d, const uint64_t *t, int32_t n, int32_t *c, void *s) { (void)d; (void)t; (void)n; (void)c; (void)s; return -1; }
 int igdb_dev_shard_partition(igdb_dev *d, int64_t n, const int32_t *a, const int32_t *b, const int32_t *c, const int32_t *cu, int32_t np, int32_t *oa, int32_t *ob, int32_t *oc, int64_t *off, int32_t *r, void *s) { (void)d; (void)n; (void)a; (void)b; (void)c; (void)cu; (void)np; (void)oa; (void)ob; (void)oc; (void)off; (void)r; (void)s; return -1; }
 int igdb_dev_full_restore(igdb_dev *d, int64_t n, const int64_t *o, const int64_t *c, const int32_t *l, int64_t t, int64_t *q, int32_t *lo, void *s) { (void)d; (void)n; (void)o; (void)c; (void)l; (void)t; (void)q; (void)lo; (void)s; return -1; }
+igdb_dispatcher *igdb_dispatcher_create(igdb_dev *d, int r, int w, int64_t c) { (void)d; (void)r; (void)w; (void)c; return NULL; }
+int igdb_dispatcher_handle(igdb_dispatcher *x, void *o) { (void)x; (void)o; return -1; }
+int igdb_dispatcher_connect(igdb_dispatcher *x, const void *h) { (void)x; (void)h; return -1; }
+int igdb_dispatch(igdb_dispatcher *x, int64_t n, const int32_t *a, const int32_t *b, const int32_t *c, const int32_t *k, void *s, int32_t **oa, int32_t **ob, int32_t **oc, int64_t *m, int32_t *lo, int32_t *hi) { (void)x; (void)n; (void)a; (void)b; (void)c; (void)k; (void)s; (void)oa; (void)ob; (void)oc; (void)m; (void)lo; (void)hi; return -1; }
+void igdb_dispatcher_destroy(igdb_dispatcher *x) { (void)x; }
 igdb_reducer *igdb_reducer_create(int d, int r, int w, int32_t n) { (void)d; (void)r; (void)w; (void)n; return NULL; }
 int igdb_reducer_handle(igdb_reducer *r, void *o) { (void)r; (void)o; return -1; }
 int igdb_reducer_connect(igdb_reducer *r, const void *h) { (void)r; (void)h; return -1; }
 int igdb_reducer_allreduce(igdb_reducer *r, unsigned long long *h, void *s) { (void)r; (void)h; (void)s; return -1; }
+int igdb_reducer_allreduce_into(igdb_reducer *r, unsigned long long *i, unsigned long long *o, void *s) { (void)r; (void)i; (void)o; (void)s; return -1; }
 void igdb_reducer_destroy(igdb_reducer *r) { (void)r; }
 int igdb_reducer_status(igdb_reducer *r) { (void)r; return -1; }

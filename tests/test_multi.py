@@ -185,7 +185,7 @@ def _reducer_rank(rank, world, port, out_dir):
                                 device_id=torch.device("cuda", dev))
     else:
         dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
-    nfiles = 1905
+    nfiles = 1905 if world == 2 else 10000              # 4 and 20 slices (CTAs) of the file range
     red = api.HitsReducer(dev, nfiles)
     stream = torch.cuda.Stream(device=dev)
     ok = True
@@ -195,9 +195,15 @@ def _reducer_rank(rank, world, port, out_dir):
             mine = torch.randint(0, 2**40, (nfiles,), generator=g, dtype=torch.int64).to(f"cuda:{dev}")
             want = sum(torch.randint(0, 2**40, (nfiles,), generator=torch.Generator().manual_seed(1000 * epoch + q),
                                      dtype=torch.int64) for q in range(world))
-            red.allreduce(mine.data_ptr(), stream.cuda_stream)
-            stream.synchronize()
-            ok = ok and bool(torch.equal(mine.cpu(), want))
+            if epoch & 1:                               # out of place: the input is left zeroed
+                out = torch.full((nfiles,), -1, dtype=torch.int64, device=f"cuda:{dev}")
+                red.allreduce_into(mine.data_ptr(), out.data_ptr(), stream.cuda_stream)
+                stream.synchronize()
+                ok = ok and bool(torch.equal(out.cpu(), want)) and int(mine.abs().sum()) == 0
+            else:
+                red.allreduce(mine.data_ptr(), stream.cuda_stream)
+                stream.synchronize()
+                ok = ok and bool(torch.equal(mine.cpu(), want))
     ok = ok and red.status() == 0
     red.close()
     open(os.path.join(out_dir, f"reducer{rank}.txt"), "w").write("ok" if ok else "MISMATCH")
@@ -217,3 +223,104 @@ def test_peer_memory_hits_reducer(workdir, world):
     mp.spawn(_reducer_rank, args=(world, _free_port(), out_dir), nprocs=world, join=True)
     for r in range(world):
         assert open(os.path.join(out_dir, f"reducer{r}.txt")).read() == "ok"
+
+
+def _dispatch_rank(rank, world, port, igd_path, out_dir):
+    import signal
+    import torch
+    import torch.distributed as dist
+    from igd_b200 import api
+    signal.alarm(200)                                   # a lost flag would spin (20 s, then an error): die instead
+    ndev = torch.cuda.device_count()
+    dev = rank if ndev >= world else 0                  # one GPU: the ranks share it
+    torch.cuda.set_device(dev)
+    if ndev >= world:
+        dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                                device_id=torch.device("cuda", dev))
+    else:
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    g = api.IGD(igd_path, device=dev)
+    hdr = workloads.read_igd_header(igd_path)
+    T, tdev = g.ntiles, torch.device("cuda", dev)
+    ok = True
+    stream = torch.cuda.Stream(device=tdev)
+    with torch.cuda.stream(stream):
+        st = stream.cuda_stream
+        disp = api.QueryDispatcher(g, dev, 40000)
+        res = {}
+        for epoch, (seed, n) in enumerate([(301, 30000), (302, 7), (303, 40000), (304, 0), (305, 20000)]):
+            q = make_queries(seed, n, ("lognormal", 7.0, 1.5))
+            ctg, qs, qe = q.ctg.copy(), q.start.copy(), q.end.copy()
+            if n > 100:
+                ctg[:20] = -1                           # unknown contigs go to the last rank and count nothing
+            a, b = n * rank // world, n * (rank + 1) // world
+            full = [torch.from_numpy(np.ascontiguousarray(x)).to(tdev) for x in (ctg, qs, qe)]
+            mine = [x[a:b].contiguous() for x in full]
+            cost = torch.zeros(T + 1, dtype=torch.int64, device=tdev)
+            cuts = torch.zeros(world + 1, dtype=torch.int32, device=tdev)
+            if n:
+                g.shard_cost(n, full[0].data_ptr(), full[1].data_ptr(), full[2].data_ptr(), cost.data_ptr(), st)
+            g.shard_cuts(cost.data_ptr(), world, cuts.data_ptr(), st)
+            m, pc, ps, pe, lo, hi = disp.dispatch(b - a, mine[0].data_ptr(), mine[1].data_ptr(), mine[2].data_ptr(),
+                                                  cuts.data_ptr(), st)
+            got = [torch.as_tensor(api.device_view(p, m, "<i4"), device=tdev).cpu().numpy() if m else np.zeros(0, np.int32)
+                   for p in (pc, ps, pe)]
+            # the numpy model of the plan (tests/test_gpu_shard.py): destination = the cut range of the first tile
+            cu = cuts.cpu().numpy()
+            okq = (ctg >= 0) & (ctg < hdr["nctg"])
+            c0 = np.where(okq, ctg, 0)
+            n1 = qs // hdr["nbp"]
+            okq &= (qs >= 0) & (n1 < hdr["ntile"][c0])
+            tile = np.where(okq, hdr["tbase"][c0] + n1, T)
+            dest = np.where(okq, np.searchsorted(cu[1:-1], tile, side="right"), world - 1)
+            src = np.minimum(np.searchsorted(np.array([n * r // world for r in range(1, world)]), np.arange(n), side="right"),
+                             world - 1) if n else np.zeros(0, np.int64)
+            pos = 0
+            for s_ in range(world):                     # rank-major by source; inside a source any order
+                sel = (dest == rank) & (src == s_)
+                k = int(sel.sum())
+                want = sorted(zip(ctg[sel].tolist(), qs[sel].tolist(), qe[sel].tolist()))
+                have = sorted(zip(got[0][pos:pos + k].tolist(), got[1][pos:pos + k].tolist(), got[2][pos:pos + k].tolist()))
+                ok = ok and want == have
+                pos += k
+            ok = ok and pos == m and lo == int(cu[rank])
+            hits = torch.zeros(g.nfiles, dtype=torch.int64, device=tdev)
+            if m:
+                g.count_device_tiles(m, pc, ps, pe, 0, hits.data_ptr(), st, lo, hi)
+                g.count_device_finish()
+            stream.synchronize()
+            h = hits if ndev >= world else hits.cpu()   # (NCCL reduces device tensors, gloo host tensors)
+            dist.all_reduce(h)
+            res[f"hits{epoch}"] = h.cpu().numpy()
+        disp.close()
+    g.close()
+    np.savez(os.path.join(out_dir, f"dispatch{rank}.npz"), ok=np.array([ok]), **res)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3])
+def test_peer_memory_query_dispatch(workdir, world):
+    """igd_b200_dispatcher_*: the partition by destination rank fused with its all-to-all over peer memory, five
+    epochs in a row (both matrix slots and the one receive buffer reused; a tiny batch, an empty one), against the
+    numpy model of the plan, and the shards searched over their tile ranges against the oracle.  On a one-GPU box
+    the ranks share the device."""
+    import torch.multiprocessing as mp
+    stem = os.path.join(workdir, f"dispatch_db{world}")
+    make_dense_db(stem, n_files=11, n_per_file=1500, seed=33)
+    out_dir = os.path.join(workdir, f"dispatch_out{world}")
+    os.makedirs(out_dir, exist_ok=True)
+    mp.spawn(_dispatch_rank, args=(world, _free_port(), stem + ".igd", out_dir), nprocs=world, join=True)
+    ref = OracleEngine(stem + ".igd")
+    for r in range(world):
+        z = np.load(os.path.join(out_dir, f"dispatch{r}.npz"))
+        assert bool(z["ok"][0])
+        for epoch, (seed, n) in enumerate([(301, 30000), (302, 7), (303, 40000), (304, 0), (305, 20000)]):
+            q = make_queries(seed, n, ("lognormal", 7.0, 1.5))
+            ctg = q.ctg.copy()
+            if n > 100:
+                ctg[:20] = -1
+            known = ctg >= 0
+            want, _ = ref.count(ctg[known], q.start[known], q.end[known], 0)
+            assert np.array_equal(z[f"hits{epoch}"], want), (r, epoch)
