@@ -411,11 +411,17 @@ def run_ours(args):
                 if k + 1 < k_steps:
                     upload(k + 1)                       # (its buffers were last read by step k - 1, which has completed)
                 side.wait_event(ev_in[k & 1])
-                s_ctg, s_qs, s_qe, lo, hi = sharder.shard(*e_in[k & 1])
-                if s_ctg.shape[0]:
-                    igd.count_device_tiles(int(s_ctg.shape[0]), s_ctg.data_ptr(), s_qs.data_ptr(), s_qe.data_ptr(), 0,
-                                           d_part.data_ptr(), stream, lo, hi)
+                if sharder.peer is not None:
+                    # no host round trip between the exchange and the search: the shard's shape stays on the device
+                    p_c, p_s, p_e, p_shape = sharder.shard_async(*e_in[k & 1])
+                    igd.count_device_shaped(n_total, p_shape, p_c, p_s, p_e, 0, d_part.data_ptr(), stream)
                     igd.count_device_finish()
+                else:
+                    s_ctg, s_qs, s_qe, lo, hi = sharder.shard(*e_in[k & 1])
+                    if s_ctg.shape[0]:
+                        igd.count_device_tiles(int(s_ctg.shape[0]), s_ctg.data_ptr(), s_qs.data_ptr(), s_qe.data_ptr(), 0,
+                                               d_part.data_ptr(), stream, lo, hi)
+                        igd.count_device_finish()
                 combine()
                 h_out[k & 1].copy_(d_hits, non_blocking=True)
                 side.synchronize()                      # the step's result is on the host
@@ -441,6 +447,8 @@ def run_ours(args):
         out_last = stream_steps(args.steps)
         e2e_stream_s = time.perf_counter() - t0
         assert np.array_equal(out_last, np.asarray(hits_e2e)), "pipelined and step-by-step end-to-end paths disagree"
+        if sharder.peer is not None:
+            sharder.peer.status()                       # every dispatch met all its peers, no receive buffer overflowed
         e2e_single = {"value": None, "unit": UNIT, "ms_per_step": e2e_s / args.steps * 1e3,
                       "api": "the same steps one at a time (H2D, then shard + search + exchange, then D2H)"}
         e2e_s = e2e_stream_s

@@ -147,7 +147,11 @@ def load_library():
     L.igd_b200_dispatcher_connect.argtypes = [vp, vp]
     L.igd_b200_dispatch.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),
                                     C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.igd_b200_dispatch_async.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),
+                                          C.POINTER(vp)]
+    L.igd_b200_dispatcher_status.argtypes = [vp]
     L.igd_b200_dispatcher_destroy.argtypes = [vp]
+    L.igd_b200_count_device_shaped.argtypes = [vp, C.c_int64, vp, vp, vp, vp, C.c_int32, vp, vp]
     L.igd_b200_reducer_create.restype = vp
     L.igd_b200_reducer_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int32]
     L.igd_b200_reducer_handle.argtypes = [vp, vp]
@@ -303,6 +307,20 @@ class QueryDispatcher:
                                      C.byref(o[2]), C.byref(m), C.byref(lo), C.byref(hi)):
             raise IGDError(last_error())
         return int(m.value), o[0].value, o[1].value, o[2].value, int(lo.value), int(hi.value)
+
+    def dispatch_async(self, n: int, d_ctg: int, d_qs: int, d_qe: int, d_cuts: int, stream: int = 0):
+        """-> (ctg_ptr, qs_ptr, qe_ptr, shape_ptr): nothing is read back; shape_ptr -> device {queries, tile_lo, tile_hi}
+        for IGD.count_device_shaped on the same stream"""
+        o = [C.c_void_p() for _ in range(4)]
+        if self._L.igd_b200_dispatch_async(self._x, int(n), d_ctg, d_qs, d_qe, d_cuts, stream, C.byref(o[0]),
+                                           C.byref(o[1]), C.byref(o[2]), C.byref(o[3])):
+            raise IGDError(last_error())
+        return o[0].value, o[1].value, o[2].value, o[3].value
+
+    def status(self) -> None:
+        """waits for the device; raises if a dispatch did not complete (a peer missing, a receive buffer too small)"""
+        if self._L.igd_b200_dispatcher_status(self._x):
+            raise IGDError(last_error())
 
     def close(self) -> None:
         if getattr(self, "_x", None):
@@ -537,6 +555,12 @@ class IGD:
                         o_qe: int, d_part_off: int, d_reach: int = 0, stream: int = 0) -> None:
         if self._L.igd_b200_shard_partition(self._need(), n, d_ctg, d_qs, d_qe, d_cuts, int(n_parts), o_ctg, o_qs, o_qe,
                                             d_part_off, d_reach, stream):
+            raise IGDError(last_error())
+
+    def count_device_shaped(self, n_max: int, d_shape: int, d_ctg: int, d_qs: int, d_qe: int, v: int, d_hits: int,
+                            stream: int = 0) -> None:
+        """count_device_tiles for a batch whose shape {queries, tile_lo, tile_hi} is in device memory (QueryDispatcher)"""
+        if self._L.igd_b200_count_device_shaped(self._need(), int(n_max), d_shape, d_ctg, d_qs, d_qe, int(v), d_hits, stream):
             raise IGDError(last_error())
 
     def count_device_finish(self) -> None:

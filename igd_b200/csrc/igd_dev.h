@@ -64,6 +64,10 @@ int igdb_dev_count_device(igdb_dev *d, int64_t n, const int32_t *d_ctg, const in
  * cover that range only */
 int igdb_dev_count_device_tiles(igdb_dev *d, int64_t n, const int32_t *d_ctg, const int32_t *d_qs, const int32_t *d_qe,
                                 int mode_v, int32_t v, uint64_t *d_hits, void *stream, int32_t tile_lo, int32_t tile_hi);
+/* the same for a batch whose shape is in device memory: d_dyn = {queries, tile_lo, tile_hi} (uint64), written earlier on
+ * the stream (igdb_dispatch_async); n_max bounds the number of queries */
+int igdb_dev_count_device_dyn(igdb_dev *d, int64_t n_max, const uint64_t *d_dyn, const int32_t *d_ctg, const int32_t *d_qs,
+                              const int32_t *d_qe, int mode_v, int32_t v, uint64_t *d_hits, void *stream);
 /* waits until the batch enqueued by igdb_dev_count_device has been planned; if its plan did not fit the
  * scratch buffers (nothing was added to d_hits then) grows them and runs it again.  0 = d_hits is valid
  * in stream order. */
@@ -131,6 +135,13 @@ int igdb_dispatcher_connect(igdb_dispatcher *x, const void *handles);
 int igdb_dispatch(igdb_dispatcher *x, int64_t n, const int32_t *d_ctg, const int32_t *d_qs, const int32_t *d_qe,
                   const int32_t *d_cuts, void *stream, int32_t **o_ctg, int32_t **o_qs, int32_t **o_qe, int64_t *m,
                   int32_t *tile_lo, int32_t *tile_hi);
+/* the same without waiting: the shard's shape -- {queries, tile_lo, tile_hi}, uint64 -- stays in device memory at *d_dyn
+ * for igdb_dev_count_device_dyn; the pointers into the receive buffer are fixed for the life of the dispatcher */
+int igdb_dispatch_async(igdb_dispatcher *x, int64_t n, const int32_t *d_ctg, const int32_t *d_qs, const int32_t *d_qe,
+                        const int32_t *d_cuts, void *stream, int32_t **o_ctg, int32_t **o_qs, int32_t **o_qe,
+                        const uint64_t **d_dyn);
+/* waits for the device; 0 = every dispatch so far completed, < 0 = a peer did not arrive or a receive buffer was too small */
+int igdb_dispatcher_status(igdb_dispatcher *x);
 void igdb_dispatcher_destroy(igdb_dispatcher *x);
 
 /* The exchange step of the multi-GPU count path (igd_dev_p2p.cu): hits[] summed over the ranks by one kernel per

@@ -26,7 +26,7 @@ template <bool V, int MODE, bool SCATTER, class F1, class FL>
 __device__ __forceinline__ void cseg_walk(const DbView &db, int64_t n, const int32_t *__restrict__ ctg,
                                           const int32_t *__restrict__ qs, const int32_t *__restrict__ qe,
                                           uint32_t *__restrict__ qrank, uint32_t *__restrict__ abn, int abn_sign,
-                                          F1 first, FL later)
+                                          const unsigned long long *__restrict__ dyn, F1 first, FL later)
 {
     __shared__ int32_t tb_s[CSEG_MAXCTG + 1];
     const bool in_smem = db.nctg <= CSEG_MAXCTG;
@@ -37,6 +37,7 @@ __device__ __forceinline__ void cseg_walk(const DbView &db, int64_t n, const int
     }
     const int nbp = db.nbp;
     pdl_wait();                                             // the queries / counters of the previous launch
+    if (dyn) n = min(n, (int64_t)dyn[0]);                   // the batch's size lives on the device (a dispatched shard)
     int nabn = 0;
     // grid-stride over blocks of CSEG_T * CSEG_Q queries: the grid is one resident wave at most, so a batch a little
     // larger than what the GPU holds at once does not pay for a second, nearly empty wave
@@ -103,12 +104,21 @@ __device__ __forceinline__ void cseg_walk(const DbView &db, int64_t n, const int
 template <bool V, int MODE>
 __global__ void __launch_bounds__(CSEG_T) k_cseg_count(DbView db, int64_t n, const int32_t *__restrict__ ctg,
                                                         const int32_t *__restrict__ qs, const int32_t *__restrict__ qe,
-                                                        uint32_t *__restrict__ cnt2, uint32_t *__restrict__ qrank)
+                                                        uint32_t *__restrict__ cnt2, uint32_t *__restrict__ qrank,
+                                                        const unsigned long long *__restrict__ dyn)
 {
     cseg_walk<V, MODE, false>(
-        db, n, ctg, qs, qe, qrank, &cnt2[2 * db.ntiles], +1,
+        db, n, ctg, qs, qe, qrank, &cnt2[2 * db.ntiles], +1, dyn,
         [&](int tile, int, int, int, uint32_t) { return atomicAdd(&cnt2[2 * tile], 1u); },
         [&](int tile, int, int, int) { atomicAdd(&cnt2[2 * tile + 1], 1u); });
+}
+
+// the tile range of a batch whose shape lives on the device: dyn = {queries, tile_lo, tile_hi}
+__device__ __forceinline__ void dyn_range(const unsigned long long *__restrict__ dyn, int32_t T, int32_t &tlo, int32_t &thi)
+{
+    if (!dyn) return;
+    tlo = (int32_t)min(dyn[1], (unsigned long long)T);
+    thi = max(tlo, (int32_t)min(dyn[2], (unsigned long long)T));
 }
 
 constexpr uint32_t RK_END = 0x1ff;      // an END item of k_count_rank carries this in the tsr field of its descriptor
@@ -152,17 +162,19 @@ __global__ void __launch_bounds__(SCAN_T) k_plan(DbView db, const uint32_t *cnt2
                                                   uint32_t *ticket, uint32_t *__restrict__ seg_off, uint32_t *__restrict__ seg_mid,
                                                   unsigned long long *__restrict__ tot, unsigned long long seg_cap,
                                                   unsigned long long item_cap, int4 *__restrict__ items, int rank,
-                                                  int4 *__restrict__ tplan, int32_t tlo, int32_t thi)
+                                                  int4 *__restrict__ tplan, int32_t tlo, int32_t thi,
+                                                  const unsigned long long *__restrict__ dyn)
 {
     __shared__ unsigned long long red[3][SCAN_T / 32];
     __shared__ unsigned long long sh_prefix[2], sh_total[3];
     __shared__ bool sh_last;
     const int32_t T = db.ntiles;
     const int G = gridDim.x, b = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    // only the tiles [tlo, thi) can have segments (a shard of a multi-GPU search: igd_dev_shard.cu; else all of them)
-    const int32_t per = (thi - tlo + G - 1) / G, t0 = min(tlo + b * per, thi), t1 = min(t0 + per, thi);
     pdl_launch_dependents();
     pdl_wait();                                             // the segment counters
+    // only the tiles [tlo, thi) can have segments (a shard of a multi-GPU search: igd_dev_shard.cu; else all of them)
+    dyn_range(dyn, T, tlo, thi);
+    const int32_t per = (thi - tlo + G - 1) / G, t0 = min(tlo + b * per, thi), t1 = min(t0 + per, thi);
 
     // 1. aggregate of this CTA's range
     unsigned long long segs = 0, its = 0, recs = 0;
@@ -303,7 +315,7 @@ __global__ void __launch_bounds__(CSEG_T) k_cseg_scatter(DbView db, int64_t n, c
                                                           const uint32_t *__restrict__ seg_mid,
                                                           const unsigned long long *__restrict__ tot,
                                                           unsigned long long seg_cap, unsigned long long item_cap,
-                                                          void *__restrict__ segs)
+                                                          void *__restrict__ segs, const unsigned long long *__restrict__ dyn)
 {
     pdl_wait();                                             // the plan
     if (tot[0] > seg_cap || tot[1] > item_cap) return;
@@ -317,7 +329,7 @@ __global__ void __launch_bounds__(CSEG_T) k_cseg_scatter(DbView db, int64_t n, c
     };
     // (the queries left to the M_ABN32 pipeline are counted back down too)
     cseg_walk<V, MODE, true>(
-        db, n, ctg, qs, qe, qrank, &cnt2[2 * db.ntiles], -1,
+        db, n, ctg, qs, qe, qrank, &cnt2[2 * db.ntiles], -1, dyn,
         [&](int tile, int s, int e, int bd, uint32_t rank) {
             put(__ldg(&seg_off[tile]) + rank, s, e, bd);
             return 0u;
@@ -633,13 +645,18 @@ __global__ void __launch_bounds__(256, 4) k_windows(DbView db, const int4 *__res
                                                   const unsigned long long *__restrict__ tot,
                                                   unsigned long long seg_cap, unsigned long long item_cap,
                                                   int4 *__restrict__ out, int small_done, uint32_t tlo, uint32_t thi,
-                                                  uint32_t min_groups)
+                                                  uint32_t min_groups, const unsigned long long *__restrict__ dyn)
 {
     constexpr int NSUB = 256 / LPT, NGT = 4 * LPT;          // NGT: groups of a tile whose key ranges are staged in shared memory
     __shared__ uint32_t s_cnt[NSUB][LPT + 1], s_m0[NSUB][LPT], s_m1[NSUB][LPT], s_x[NSUB][SMAX], s_gk[NSUB][2][NGT];
     pdl_launch_dependents();
     pdl_wait();                                             // the plan, the segments
     if (tot[0] > seg_cap || tot[1] > item_cap) return;
+    {
+        int32_t lo_ = (int32_t)tlo, hi_ = (int32_t)thi;
+        dyn_range(dyn, db.ntiles, lo_, hi_);
+        tlo = (uint32_t)lo_, thi = (uint32_t)hi_;
+    }
     static_assert(LPT == 32, "a warp per tile: the tiles are taken 32 at a time, one per lane, to see which need work");
     const uint32_t l = threadIdx.x % LPT, sub = threadIdx.x / LPT;
     const unsigned lmask = FULL;
@@ -758,7 +775,7 @@ __global__ void __launch_bounds__(256) k_windows_warp(DbView db, const int4 *__r
                                                        const unsigned long long *__restrict__ tot,
                                                        unsigned long long seg_cap, unsigned long long item_cap,
                                                        int4 *__restrict__ out, int small_done, uint32_t tpw, uint32_t tlo,
-                                                       uint32_t thi)
+                                                       uint32_t thi, const unsigned long long *__restrict__ dyn)
 {
     __shared__ uint32_t s_hi[8][2][W2_NG], s_lo[8][2][W2_NG];
     __shared__ uint32_t s_cw[8][W2_NG], s_m0[8][W2_NG], s_m1[8][W2_NG];
@@ -766,6 +783,11 @@ __global__ void __launch_bounds__(256) k_windows_warp(DbView db, const int4 *__r
     pdl_launch_dependents();
     pdl_wait();                                             // the plan, the segments
     if (tot[0] > seg_cap || tot[1] > item_cap) return;
+    {
+        int32_t lo_ = (int32_t)tlo, hi_ = (int32_t)thi;
+        dyn_range(dyn, db.ntiles, lo_, hi_);
+        tlo = (uint32_t)lo_, thi = (uint32_t)hi_;
+    }
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     uint32_t *cw = s_cw[wib], *m0 = s_m0[wib], *m1 = s_m1[wib];
     uint16_t *wv = reinterpret_cast<uint16_t *>(s_wv[wib]);
@@ -877,11 +899,17 @@ __global__ void __launch_bounds__(128) k_windows_small(DbView db, const int4 *__
                                                         const uint32_t *__restrict__ segs,
                                                         const unsigned long long *__restrict__ tot,
                                                         unsigned long long seg_cap, unsigned long long item_cap,
-                                                        int4 *__restrict__ out, uint32_t tlo, uint32_t thi)
+                                                        int4 *__restrict__ out, uint32_t tlo, uint32_t thi,
+                                                        const unsigned long long *__restrict__ dyn)
 {
     pdl_launch_dependents();
     pdl_wait();                                             // the plan, the segments
     if (tot[0] > seg_cap || tot[1] > item_cap) return;
+    {
+        int32_t lo_ = (int32_t)tlo, hi_ = (int32_t)thi;
+        dyn_range(dyn, db.ntiles, lo_, hi_);
+        tlo = (uint32_t)lo_, thi = (uint32_t)hi_;
+    }
     const uint32_t t = tlo + blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= thi) return;
     const int4 tp = __ldg(&tplan[2 * t]);
@@ -1227,15 +1255,15 @@ int enqueue_count_t(igdb_dev *d, const igdb_dev::Pending &p)
     // plan_tot is about to be rewritten: the readback of the previous batch's totals (side stream) must have read it
     if (d->last_plan_ev) CK(cudaStreamWaitEvent(st, d->last_plan_ev, 0));
     if (stages) CK(cudaEventRecord(d->stage_ev[0], st));
-    CK(launch_pdl(k_cseg_count<V, MODE>, nb, thr, 0, st, db, p.n, p.ctg, p.qs, p.qe, d->cnt2, d->qrank));
+    CK(launch_pdl(k_cseg_count<V, MODE>, nb, thr, 0, st, db, p.n, p.ctg, p.qs, p.qe, d->cnt2, d->qrank, p.dyn));
     if (stages) CK(cudaEventRecord(d->stage_ev[1], st));
     // (the plan reads the later-bin counters that the scatter counts back down to zero)
     CK(launch_pdl(k_plan, d->plan_grid, SCAN_T, 0, st, db, d->cnt2, d->cnt2, ++d->plan_epoch, d->plan_agg, d->plan_flag,
                   d->plan_flag + 1, d->cseg_off, d->cseg_mid, d->plan_tot, seg_cap, item_cap, d->items, PK ? 1 : 0, d->tplan,
-                  tlo, thi));
+                  tlo, thi, p.dyn));
     if (stages) CK(cudaEventRecord(d->stage_ev[2], st));
     CK(launch_pdl(k_cseg_scatter<V, MODE>, nb, thr, 0, st, db, p.n, p.ctg, p.qs, p.qe, d->cnt2, d->qrank, d->cseg_off,
-                  d->cseg_mid, d->plan_tot, seg_cap, item_cap, (void *)d->csegs));
+                  d->cseg_mid, d->plan_tot, seg_cap, item_cap, (void *)d->csegs, p.dyn));
     // the plan's totals go back to the host on a side stream, so that the copy does not sit between the kernels
     CK(cudaEventRecord(d->plan_done, st));
     CK(cudaStreamWaitEvent(d->side, d->plan_done, 0));
@@ -1253,23 +1281,23 @@ int enqueue_count_t(igdb_dev *d, const igdb_dev::Pending &p)
         if (sparse) {
             CK(launch_pdl(k_windows_small, (unsigned)((nt + 127) / 128), 128, 0, st, db, (const int4 *)d->tplan,
                           (const uint32_t *)(const void *)d->csegs, (const unsigned long long *)d->plan_tot, seg_cap,
-                          item_cap, d->items2, (uint32_t)tlo, (uint32_t)thi));
+                          item_cap, d->items2, (uint32_t)tlo, (uint32_t)thi, p.dyn));
             d->launches += 1;
         }
         // the others: a warp per tile; tiles of W2_NG groups or more (none in the BASELINE configurations) by the
         // general kernel
         // tiles per warp and turn: few enough that a small tile range (a shard of a multi-GPU search) still fills the GPU
-        const int64_t tpw = sparse ? 32 : std::max<int64_t>(1, std::min<int64_t>(8, nt / ((int64_t)d->sm_count * 40)));
+        const int64_t tpw = sparse ? 32 : (p.dyn ? 2 : std::max<int64_t>(1, std::min<int64_t>(8, nt / ((int64_t)d->sm_count * 40))));
         const unsigned wgrid = (unsigned)std::min<int64_t>((nt + 8 * tpw - 1) / (8 * tpw), (int64_t)d->sm_count * 48);
         CK(launch_pdl(k_windows_warp, wgrid, 256, 0, st, db, (const int4 *)d->tplan,
                       (const uint32_t *)(const void *)d->csegs, (const unsigned long long *)d->plan_tot, seg_cap, item_cap,
-                      d->items2, sparse ? 1 : 0, (uint32_t)tpw, (uint32_t)tlo, (uint32_t)thi));
+                      d->items2, sparse ? 1 : 0, (uint32_t)tpw, (uint32_t)tlo, (uint32_t)thi, p.dyn));
         d->launches += 1;
         if (d->max_tile_groups >= (int64_t)W2_NG) {
             const unsigned ggrid = (unsigned)std::min<int64_t>((nt + 255) / 256, (int64_t)d->sm_count * 64);
             CK(launch_pdl(k_windows<32>, ggrid, 256, 0, st, db, (const int4 *)d->tplan,
                           (const uint32_t *)(const void *)d->csegs, (const unsigned long long *)d->plan_tot, seg_cap,
-                          item_cap, d->items2, 1, (uint32_t)tlo, (uint32_t)thi, W2_NG));
+                          item_cap, d->items2, 1, (uint32_t)tlo, (uint32_t)thi, W2_NG, p.dyn));
             d->launches += 1;
         }
     }
@@ -1353,8 +1381,9 @@ int settle_count(igdb_dev *d, const igdb_dev::Pending &p)
         CK(cudaStreamSynchronize(p.st));
         CK(cudaMemsetAsync(d->cnt2, 0, ((size_t)2 * d->T + 2) * 4, p.st));
         if (nsegs >= 0x7fffffffull || nitems > (unsigned long long)lim) {
-            if (p.n <= 1) {
-                snprintf(g_err, sizeof g_err, "a single query expands to too many (query, tile) segments");
+            if (p.n <= 1 || p.dyn) {
+                snprintf(g_err, sizeof g_err, p.dyn ? "a dispatched shard expands to too many (query, tile) segments for one batch"
+                                                    : "a single query expands to too many (query, tile) segments");
                 return -1;
             }
             igdb_dev::Pending a = p, b = p;
@@ -1449,6 +1478,33 @@ int igdb_dev_count_device_tiles(igdb_dev *d, int64_t n, const int32_t *d_ctg, co
             d->pending = p;
         }
     }
+    return 0;
+}
+
+// the same for a batch whose shape lives in device memory -- d_dyn = {queries, tile_lo, tile_hi} (uint64), written by
+// an earlier kernel on the stream (igdb_dispatch_async): n_max bounds the number of queries (it sizes the scratch and
+// the grids), nothing is read back before the launches, so the host never waits between the query exchange of a
+// multi-GPU step and its search
+int igdb_dev_count_device_dyn(igdb_dev *d, int64_t n_max, const uint64_t *d_dyn, const int32_t *d_ctg, const int32_t *d_qs,
+                              const int32_t *d_qe, int mode_v, int32_t v, uint64_t *d_hits, void *stream)
+{
+    g_err[0] = 0;
+    CK(cudaSetDevice(d->device));
+    if (slots_idle(d, "count_device")) return -1;
+    if (finish_pending(d)) return -1;
+    if (n_max <= 0 || d->T == 0) return 0;
+    if (n_max > ((int64_t)1 << 26)) {
+        snprintf(g_err, sizeof g_err, "count_device_dyn: at most 2^26 queries per batch");
+        return -1;
+    }
+    igdb_dev::Pending p;
+    p.mode_v = mode_v != 0, p.n = n_max, p.ctg = d_ctg, p.qs = d_qs, p.qe = d_qe, p.v = v;
+    p.hits = (unsigned long long *)d_hits, p.st = stream ? (cudaStream_t)stream : d->stream;
+    p.dyn = (const unsigned long long *)d_dyn;
+    p.mode = count_mode_for(d, p.mode_v, p.v);
+    if (enqueue_count(d, p)) return -1;
+    p.active = true;
+    d->pending = p;
     return 0;
 }
 

@@ -370,6 +370,7 @@ struct igdb_dev {
         cudaStream_t st = nullptr;
         int32_t tile_lo = 0, tile_hi = 0x7fffffff;          // no query touches a tile outside [tile_lo, tile_hi)
         int slot = 0;                                       // which h_plan / plan_ev carries this batch's plan back
+        const unsigned long long *dyn = nullptr;            // device {queries, tile_lo, tile_hi}: n and the tile range above are upper bounds then
     } pending;
     // The pipelined host entry (igdb_dev_count_submit / _wait): two batches in flight.  A slot owns what must outlive
     // the next batch's copy -- its queries in HBM, its hits[] on both sides, its events; the plan scratch is shared,

@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(SH_T) k_dispatch_scatter(DbView db, int64_t n,
             m += *(volatile unsigned long long *)&mine[dc_cnt(v, s, src, v.rank)];
             far = max(far, *(volatile unsigned long long *)&mine[dc_reach(v, s, src, v.rank)]);
         }
-        meta[0] = m, meta[1] = far, meta[2] = (unsigned long long)cut_s[v.rank];
+        meta[0] = m, meta[1] = (unsigned long long)cut_s[v.rank], meta[2] = far;     // {queries, tile_lo, tile_hi}: igdb_dev_count_device_dyn's d_dyn
         ticket[1] = 0;
     }
 }
@@ -544,18 +544,14 @@ int igdb_dispatcher_connect(igdb_dispatcher *x, const void *handles)
 // (*o_ctg / *o_qs / *o_qe point into it) and touches the tiles [*tile_lo, *tile_hi) only.  Enqueued on `stream`; the
 // call waits for the three launches (the host needs m).  Every rank must call it the same number of times, and the
 // search of the shard must be queued on the same stream before the next dispatch.
-int igdb_dispatch(igdb_dispatcher *x, int64_t n, const int32_t *d_ctg, const int32_t *d_qs, const int32_t *d_qe,
-                  const int32_t *d_cuts, void *stream, int32_t **o_ctg, int32_t **o_qs, int32_t **o_qe, int64_t *m,
-                  int32_t *tile_lo, int32_t *tile_hi)
+static int dispatch_enqueue(igdb_dispatcher *x, int64_t n, const int32_t *d_ctg, const int32_t *d_qs, const int32_t *d_qe,
+                            const int32_t *d_cuts, cudaStream_t st)
 {
-    g_err[0] = 0;
     igdb_dev *d = x->dev;
     if (!x->connected) {
         snprintf(g_err, sizeof g_err, "dispatcher: not connected");
         return -1;
     }
-    CK(cudaSetDevice(d->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : d->stream;
     ++x->epoch;
     DispatchView v;
     v.peer = x->d_peer, v.rank = x->rank, v.world = x->world, v.epoch = x->epoch, v.cap = x->cap, v.ctrl_words = x->ctrl_words;
@@ -569,25 +565,65 @@ int igdb_dispatch(igdb_dispatcher *x, int64_t n, const int32_t *d_ctg, const int
     k_dispatch_wait<<<1, 64, 0, st>>>(v, x->scratch);
     d->launches += 3;
     CK(cudaGetLastError());
+    return 0;
+}
+
+static int dispatch_check(igdb_dispatcher *x)
+{
+    if (x->h_meta[3] == 0) return 0;
+    if (x->h_meta[3] == 0x100)
+        snprintf(g_err, sizeof g_err, "dispatcher: a receive buffer (%lld queries) is too small for its shard", (long long)x->cap);
+    else
+        snprintf(g_err, sizeof g_err, "dispatcher: the wait for rank %llu timed out", x->h_meta[3] - 1);
+    return -1;
+}
+
+int igdb_dispatch(igdb_dispatcher *x, int64_t n, const int32_t *d_ctg, const int32_t *d_qs, const int32_t *d_qe,
+                  const int32_t *d_cuts, void *stream, int32_t **o_ctg, int32_t **o_qs, int32_t **o_qe, int64_t *m,
+                  int32_t *tile_lo, int32_t *tile_hi)
+{
+    g_err[0] = 0;
+    igdb_dev *d = x->dev;
+    CK(cudaSetDevice(d->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : d->stream;
+    if (dispatch_enqueue(x, n, d_ctg, d_qs, d_qe, d_cuts, st)) return -1;
     CK(cudaMemcpyAsync(x->h_meta, x->scratch + 3 * SH_MAXP + 2, 32, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    if (x->h_meta[3] != 0) {
-        if (x->h_meta[3] == 0x100)
-            snprintf(g_err, sizeof g_err, "dispatcher: a receive buffer (%lld queries) is too small for its shard", (long long)x->cap);
-        else
-            snprintf(g_err, sizeof g_err, "dispatcher: the wait for rank %llu timed out", x->h_meta[3] - 1);
-        return -1;
-    }
+    if (dispatch_check(x)) return -1;
     int32_t *recv = reinterpret_cast<int32_t *>(x->block + x->ctrl_words);
     *o_ctg = recv, *o_qs = recv + x->cap, *o_qe = recv + 2 * x->cap;
     *m = (int64_t)x->h_meta[0];
-    *tile_lo = (int32_t)x->h_meta[2];
-    *tile_hi = std::max(*tile_lo, (int32_t)x->h_meta[1]);
+    *tile_lo = (int32_t)x->h_meta[1];
+    *tile_hi = std::max(*tile_lo, (int32_t)x->h_meta[2]);
     if (*m > x->cap) {
         snprintf(g_err, sizeof g_err, "dispatcher: shard of %lld queries, receive buffer of %lld", (long long)*m, (long long)x->cap);
         return -1;
     }
     return 0;
+}
+
+int igdb_dispatch_async(igdb_dispatcher *x, int64_t n, const int32_t *d_ctg, const int32_t *d_qs, const int32_t *d_qe,
+                        const int32_t *d_cuts, void *stream, int32_t **o_ctg, int32_t **o_qs, int32_t **o_qe,
+                        const uint64_t **d_dyn)
+{
+    g_err[0] = 0;
+    igdb_dev *d = x->dev;
+    CK(cudaSetDevice(d->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : d->stream;
+    if (dispatch_enqueue(x, n, d_ctg, d_qs, d_qe, d_cuts, st)) return -1;
+    int32_t *recv = reinterpret_cast<int32_t *>(x->block + x->ctrl_words);
+    *o_ctg = recv, *o_qs = recv + x->cap, *o_qe = recv + 2 * x->cap;
+    *d_dyn = reinterpret_cast<const uint64_t *>(x->scratch + 3 * SH_MAXP + 2);
+    return 0;
+}
+
+int igdb_dispatcher_status(igdb_dispatcher *x)
+{
+    g_err[0] = 0;
+    CK(cudaSetDevice(x->dev->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(x->h_meta, x->scratch + 3 * SH_MAXP + 2, 32, cudaMemcpyDeviceToHost));
+    return dispatch_check(x);
 }
 
 void igdb_dispatcher_destroy(igdb_dispatcher *x)

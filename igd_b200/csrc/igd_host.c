@@ -330,6 +330,13 @@ int igd_b200_shard_partition(igd_b200_t *h, int64_t n, const int32_t *d_ctg, con
                                     d_part_off, d_reach, stream);
 }
 
+int igd_b200_count_device_shaped(igd_b200_t *h, int64_t n_max, const uint64_t *d_shape, const int32_t *d_ctg,
+                                 const int32_t *d_qs, const int32_t *d_qe, int32_t v, uint64_t *d_hits, void *stream)
+{
+    g_err[0] = 0;
+    return igdb_dev_count_device_dyn(h->dev, n_max, d_shape, d_ctg, d_qs, d_qe, filter_on(h, v), v, d_hits, stream);
+}
+
 int igd_b200_count_device_finish(igd_b200_t *h)
 {
     g_err[0] = 0;
@@ -685,6 +692,14 @@ int igd_b200_dispatch(igd_b200_dispatcher *x, int64_t n, const int32_t *d_ctg, c
     g_err[0] = 0;
     return igdb_dispatch(x, n, d_ctg, d_qs, d_qe, d_cuts, stream, d_out_ctg, d_out_qs, d_out_qe, m, tile_lo, tile_hi);
 }
+int igd_b200_dispatch_async(igd_b200_dispatcher *x, int64_t n, const int32_t *d_ctg, const int32_t *d_qs, const int32_t *d_qe,
+                            const int32_t *d_cuts, void *stream, int32_t **d_out_ctg, int32_t **d_out_qs,
+                            int32_t **d_out_qe, const uint64_t **d_shape)
+{
+    g_err[0] = 0;
+    return igdb_dispatch_async(x, n, d_ctg, d_qs, d_qe, d_cuts, stream, d_out_ctg, d_out_qs, d_out_qe, d_shape);
+}
+int igd_b200_dispatcher_status(igd_b200_dispatcher *x) { g_err[0] = 0; return igdb_dispatcher_status(x); }
 void igd_b200_dispatcher_destroy(igd_b200_dispatcher *x) { igdb_dispatcher_destroy(x); }
 
 igd_b200_reducer *igd_b200_reducer_create(int device, int rank, int world, int32_t nfiles)

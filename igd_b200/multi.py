@@ -77,6 +77,18 @@ class DeviceSharder:
             ev.record()
             self.marks.append((label, ev))
 
+    def shard_async(self, d_ctg, d_qs, d_qe):
+        """The same with the host out of the loop (peer mode only): -> (ctg_ptr, qs_ptr, qe_ptr, shape_ptr), raw device
+        pointers -- the shard lands in this rank's receive buffer and its shape {queries, tile_lo, tile_hi} in device
+        memory, for ``engine.count_device_shaped`` on the same stream; nothing is read back."""
+        n = int(d_ctg.shape[0])
+        st = self.torch.cuda.current_stream(self.dev).cuda_stream
+        self.cost.zero_()
+        self.e.shard_cost(n, d_ctg.data_ptr(), d_qs.data_ptr(), d_qe.data_ptr(), self.cost.data_ptr(), st)
+        self.dist.all_reduce(self.cost, group=self.group)
+        self.e.shard_cuts(self.cost.data_ptr(), self.world, self.cuts.data_ptr(), st)
+        return self.peer.dispatch_async(n, d_ctg.data_ptr(), d_qs.data_ptr(), d_qe.data_ptr(), self.cuts.data_ptr(), st)
+
     def shard(self, d_ctg, d_qs, d_qe):
         """torch int32 device tensors (this rank's slice, any order) -> (ctg, qs, qe, tile_lo, tile_hi) of its shard.
         Runs on the current torch stream."""

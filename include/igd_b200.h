@@ -105,6 +105,12 @@ int igd_b200_count_device_tiles(igd_b200_t *h, int64_t n, const int32_t *d_ctg, 
                                 const int32_t *d_qe, int32_t v, uint64_t *d_hits, void *stream, int32_t tile_lo,
                                 int32_t tile_hi);
 
+/* igd_b200_count_device_tiles for a batch whose shape is only known on the device: d_shape = {queries, tile_lo, tile_hi}
+ * (uint64[3], device), written by earlier work on `stream` (igd_b200_dispatch_async); n_max >= queries sizes the scratch
+ * buffers and the grids (<= 2^26, and <= the capacity of the arrays).  Pair with igd_b200_count_device_finish. */
+int igd_b200_count_device_shaped(igd_b200_t *h, int64_t n_max, const uint64_t *d_shape, const int32_t *d_ctg,
+                                 const int32_t *d_qs, const int32_t *d_qe, int32_t v, uint64_t *d_hits, void *stream);
+
 /* Sharding a query set over the ranks of a multi-GPU search, on the device (the reference is one process and has
  * no counterpart; it implements north_star's "the sorted query set is sharded into contiguous ranges balanced by a
  * prefix sum of estimated per-query scan bytes").  Rank r takes the queries whose FIRST bin is a tile of
@@ -145,6 +151,14 @@ int igd_b200_dispatcher_connect(igd_b200_dispatcher *x, const void *handles);
 int igd_b200_dispatch(igd_b200_dispatcher *x, int64_t n, const int32_t *d_ctg, const int32_t *d_qs, const int32_t *d_qe,
                       const int32_t *d_cuts, void *stream, int32_t **d_out_ctg, int32_t **d_out_qs, int32_t **d_out_qe,
                       int64_t *m, int32_t *tile_lo, int32_t *tile_hi);
+/* The same without the host in the loop: nothing is read back, the shard's shape -- {queries, tile_lo, tile_hi}, uint64
+ * -- stays in device memory at *d_shape for igd_b200_count_device_shaped (same stream).  The output pointers are the
+ * same for the life of the dispatcher.  igd_b200_dispatcher_status (waits for the device) tells afterwards whether every
+ * dispatch completed: 0, or negative when a peer did not arrive or a receive buffer was too small. */
+int igd_b200_dispatch_async(igd_b200_dispatcher *x, int64_t n, const int32_t *d_ctg, const int32_t *d_qs, const int32_t *d_qe,
+                            const int32_t *d_cuts, void *stream, int32_t **d_out_ctg, int32_t **d_out_qs,
+                            int32_t **d_out_qe, const uint64_t **d_shape);
+int igd_b200_dispatcher_status(igd_b200_dispatcher *x);
 void igd_b200_dispatcher_destroy(igd_b200_dispatcher *x);
 
 /* -f: the overlaps themselves, in the reference's order (get_overlaps_f1, src/igd_search.c:537-620:

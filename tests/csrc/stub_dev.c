@@ -27,6 +27,7 @@ void igdb_host_free(void *p) { free(p); }
 int igdb_dev_count_host(igdb_dev *d, int64_t n, const int32_t *a, const int32_t *b, const int32_t *c, int m, int32_t v, uint64_t *h, float *t) { (void)d; (void)n; (void)a; (void)b; (void)c; (void)m; (void)v; (void)h; (void)t; return -1; }
 int igdb_dev_count_device(igdb_dev *d, int64_t n, const int32_t *a, const int32_t *b, const int32_t *c, int m, int32_t v, uint64_t *h, void *s) { (void)d; (void)n; (void)a; (void)b; (void)c; (void)m; (void)v; (void)h; (void)s; return -1; }
 int igdb_dev_count_finish(igdb_dev *d) { (void)d; return -1; }
+int igdb_dev_count_device_dyn(igdb_dev *d, int64_t n, const uint64_t *y, const int32_t *a, const int32_t *b, const int32_t *c, int m, int32_t v, uint64_t *h, void *s) { (void)d; (void)n; (void)y; (void)a; (void)b; (void)c; (void)m; (void)v; (void)h; (void)s; return -1; }
 int igdb_dev_count_submit(igdb_dev *d, int s, int64_t n, const int32_t *a, const int32_t *b, const int32_t *c, int m, int32_t v) { (void)d; (void)s; (void)n; (void)a; (void)b; (void)c; (void)m; (void)v; return -1; }
 int igdb_dev_count_wait(igdb_dev *d, int s, uint64_t *h) { (void)d; (void)s; (void)h; return -1; }
 int igdb_dev_set_contigs(igdb_dev *d, const char *n) { (void)d; (void)n; return -1; }
@@ -48,6 +49,8 @@ igdb_dispatcher *igdb_dispatcher_create(igdb_dev *d, int r, int w, int64_t c) { 
 int igdb_dispatcher_handle(igdb_dispatcher *x, void *o) { (void)x; (void)o; return -1; }
 int igdb_dispatcher_connect(igdb_dispatcher *x, const void *h) { (void)x; (void)h; return -1; }
 int igdb_dispatch(igdb_dispatcher *x, int64_t n, const int32_t *a, const int32_t *b, const int32_t *c, const int32_t *k, void *s, int32_t **oa, int32_t **ob, int32_t **oc, int64_t *m, int32_t *lo, int32_t *hi) { (void)x; (void)n; (void)a; (void)b; (void)c; (void)k; (void)s; (void)oa; (void)ob; (void)oc; (void)m; (void)lo; (void)hi; return -1; }
+int igdb_dispatch_async(igdb_dispatcher *x, int64_t n, const int32_t *a, const int32_t *b, const int32_t *c, const int32_t *k, void *s, int32_t **oa, int32_t **ob, int32_t **oc, const uint64_t **dy) { (void)x; (void)n; (void)a; (void)b; (void)c; (void)k; (void)s; (void)oa; (void)ob; (void)oc; (void)dy; return -1; }
+int igdb_dispatcher_status(igdb_dispatcher *x) { (void)x; return -1; }
 void igdb_dispatcher_destroy(igdb_dispatcher *x) { (void)x; }
 igdb_reducer *igdb_reducer_create(int d, int r, int w, int32_t n) { (void)d; (void)r; (void)w; (void)n; return NULL; }
 int igdb_reducer_handle(igdb_reducer *r, void *o) { (void)r; (void)o; return -1; }

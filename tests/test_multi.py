@@ -289,9 +289,20 @@ def _dispatch_rank(rank, world, port, igd_path, out_dir):
                 g.count_device_tiles(m, pc, ps, pe, 0, hits.data_ptr(), st, lo, hi)
                 g.count_device_finish()
             stream.synchronize()
+            # the same exchange with the host out of the loop: the shape of the shard stays on the device
+            qc, qs_, qe_, shape = disp.dispatch_async(b - a, mine[0].data_ptr(), mine[1].data_ptr(), mine[2].data_ptr(),
+                                                      cuts.data_ptr(), st)
+            hits2 = torch.zeros(g.nfiles, dtype=torch.int64, device=tdev)
+            g.count_device_shaped(40000, shape, qc, qs_, qe_, 0, hits2.data_ptr(), st)
+            g.count_device_finish()
+            stream.synchronize()
+            sh = torch.as_tensor(api.device_view(shape, 3, "<i8"), device=tdev).cpu().numpy()
+            ok = ok and (qc, qs_, qe_) == (pc, ps, pe) and [int(sh[0]), int(sh[1]), max(int(sh[1]), int(sh[2]))] == [m, lo, hi] \
+                and bool(torch.equal(hits, hits2))
             h = hits if ndev >= world else hits.cpu()   # (NCCL reduces device tensors, gloo host tensors)
             dist.all_reduce(h)
             res[f"hits{epoch}"] = h.cpu().numpy()
+        disp.status()
         disp.close()
     g.close()
     np.savez(os.path.join(out_dir, f"dispatch{rank}.npz"), ok=np.array([ok]), **res)
