@@ -390,19 +390,28 @@ def run_ours(args):
     # N = 1: the same K batches as a STREAM through igd_b200_count_submit / _wait -- two in flight, the H2D of batch
     # k + 1 under the search of batch k; every step still copies its 12 B per query in and its hits[] out inside the
     # timed region (no L2 flush between the steps: each one reads several GB of the database, far beyond the L2)
-    e2e_single, e2e_phases = None, None
+    e2e_single, e2e_phases, h2d_under = None, None, None
     if world > 1:
         # N > 1: the same K steps as a stream -- the H2D of step k + 1 (this rank's 1/N of the queries, on a copy stream
         # into the other of two input buffers) under the shard plan, exchange and search of step k
         copy_st = torch.cuda.Stream(device=dev)
+        step_c = None
+        if reducer is not None and sharder.peer is not None and not os.environ.get("IGD_B200_PY_STEP"):
+            step_c = api.ShardedCounter(igd, local, n_total)
         e_in = [[torch.empty(n_slice, dtype=torch.int32, device=dev) for _ in range(3)] for _ in range(2)]
         h_out = [torch.zeros(igd.nfiles, dtype=torch.int64).pin_memory() for _ in range(2)]
         ev_in = [torch.cuda.Event() for _ in range(2)]
 
+        h2d_ev = []                                     # (begin, end) of every upload, on the copy stream
+
         def upload(k):
             with torch.cuda.stream(copy_st):
+                a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a_.record(copy_st)
                 for dst, src in zip(e_in[k & 1], (h_ctg, h_qs, h_qe)):
                     dst.copy_(src, non_blocking=True)
+                b_.record(copy_st)
+                h2d_ev.append((a_, b_))
                 ev_in[k & 1].record(copy_st)
 
         def stream_steps(k_steps):
@@ -411,6 +420,14 @@ def run_ours(args):
                 if k + 1 < k_steps:
                     upload(k + 1)                       # (its buffers were last read by step k - 1, which has completed)
                 side.wait_event(ev_in[k & 1])
+                if step_c is not None:
+                    # the whole step as ONE C call (igd_b200_sharded_count): cost, its sum over the ranks, cuts, query
+                    # exchange, search, sum of hits[] -- the library's kernels over peer memory, no host round trip
+                    x = e_in[k & 1]
+                    step_c.count(n_slice, x[0].data_ptr(), x[1].data_ptr(), x[2].data_ptr(), 0, d_hits.data_ptr(), stream)
+                    h_out[k & 1].copy_(d_hits, non_blocking=True)
+                    side.synchronize()
+                    continue
                 if sharder.peer is not None:
                     # no host round trip between the exchange and the search: the shard's shape stays on the device
                     p_c, p_s, p_e, p_shape = sharder.shard_async(*e_in[k & 1])
@@ -444,11 +461,18 @@ def run_ours(args):
         barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
+        h2d_ev.clear()
         out_last = stream_steps(args.steps)
         e2e_stream_s = time.perf_counter() - t0
+        torch.cuda.synchronize()
+        h2d_under = float(np.median([a_.elapsed_time(b_) for a_, b_ in h2d_ev[1:]])) if len(h2d_ev) > 1 else None
         assert np.array_equal(out_last, np.asarray(hits_e2e)), "pipelined and step-by-step end-to-end paths disagree"
         if sharder.peer is not None:
             sharder.peer.status()                       # every dispatch met all its peers, no receive buffer overflowed
+        if step_c is not None:
+            step_c.status()
+            barrier()
+            step_c.close()
         e2e_single = {"value": None, "unit": UNIT, "ms_per_step": e2e_s / args.steps * 1e3,
                       "api": "the same steps one at a time (H2D, then shard + search + exchange, then D2H)"}
         e2e_s = e2e_stream_s
@@ -558,6 +582,7 @@ def run_ours(args):
             "e2e": {"value": n_total / (e2e_s / args.steps), "unit": UNIT, "ms_per_step": e2e_s / args.steps * 1e3,
                     "h2d_bytes_per_step": 12 * n_total, "d2h_bytes_per_step": 8 * igd.nfiles * world,
                     "single_call": e2e_single, "phases_ms_rank0_one_step": e2e_phases,
+                    "h2d_ms_under_the_previous_step_rank0": h2d_under,
                     "device_split_ms_last_step": e2e_split,
                     # the H2D leg runs at whatever the box's PCIe path gives at that moment: 16 to 54 GB/s were
                     # seen on this pool's boxes for the same pinned buffers (profiles/microbench/h2d_*.py)
@@ -568,7 +593,8 @@ def run_ours(args):
                            "two batches in flight: H2D of step k + 1 under the search of step k)" if world == 1 else
                            "pinned H2D of this rank's 1/N of the queries + igd_b200_shard_* (cost, all-reduce, cuts) + "
                            "igd_b200_dispatch (partition fused with its all-to-all over NVLink peer memory) + "
-                           "igd_b200_count_device_tiles + hits[] exchange + D2H; the K steps as a stream: "
+                           "igd_b200_count_device_shaped + hits[] exchange -- as ONE C call per step, igd_b200_sharded_count -- "
+                           "+ D2H; the K steps as a stream: "
                            "the H2D of step k + 1 on a copy stream under step k"},
             "file_ingest": None if file_s is None else {
                 "value": file_n / file_s, "unit": UNIT, "ms": file_s * 1e3, "file_bytes": file_bytes, "n_queries": file_n,

@@ -152,6 +152,13 @@ def load_library():
     L.igd_b200_dispatcher_status.argtypes = [vp]
     L.igd_b200_dispatcher_destroy.argtypes = [vp]
     L.igd_b200_count_device_shaped.argtypes = [vp, C.c_int64, vp, vp, vp, vp, C.c_int32, vp, vp]
+    L.igd_b200_sharded_create.restype = vp
+    L.igd_b200_sharded_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int64]
+    L.igd_b200_sharded_handles.argtypes = [vp, vp]
+    L.igd_b200_sharded_connect.argtypes = [vp, vp]
+    L.igd_b200_sharded_count.argtypes = [vp, C.c_int64, vp, vp, vp, C.c_int32, vp, vp]
+    L.igd_b200_sharded_status.argtypes = [vp]
+    L.igd_b200_sharded_destroy.argtypes = [vp]
     L.igd_b200_reducer_create.restype = vp
     L.igd_b200_reducer_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int32]
     L.igd_b200_reducer_handle.argtypes = [vp, vp]
@@ -326,6 +333,54 @@ class QueryDispatcher:
         if getattr(self, "_x", None):
             self._L.igd_b200_dispatcher_destroy(self._x)
             self._x = None
+
+
+class ShardedCounter:
+    """One multi-GPU count step as one C call (igd_b200_sharded_*): per-tile cost, its sum over the ranks, cuts, the
+    query exchange, the search of the shard and the sum of hits[] -- the library's own kernels over NVLink peer memory,
+    no host round trip in between.  ``cap`` >= queries of the whole set.  torch.distributed only carries the 192-byte
+    IPC handles at set-up."""
+
+    def __init__(self, igd: "IGD", device: int, cap: int, group=None):
+        import torch
+        import torch.distributed as dist
+        self._L = load_library()
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        on = torch.device("cuda", device) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+
+        def everybody(ok: bool) -> bool:
+            f = torch.tensor([1 if ok else 0], dtype=torch.int32, device=on)
+            dist.all_reduce(f, op=dist.ReduceOp.MIN, group=group)
+            return bool(f.item())
+
+        err = ""
+        mine = (C.c_uint8 * 192)()
+        self._s = self._L.igd_b200_sharded_create(igd._need(), device, self.rank, self.world, int(cap))
+        if not self._s or self._L.igd_b200_sharded_handles(self._s, mine):
+            err = last_error() or "igd_b200_sharded_create failed"
+        blob = _exchange_ipc_handles(mine, group, on)
+        good = everybody(not err)
+        if good:
+            if self._L.igd_b200_sharded_connect(self._s, C.c_char_p(blob)):
+                err = last_error() or "igd_b200_sharded_connect failed"
+            good = everybody(not err)
+        if not good:
+            self.close()
+            raise IGDError(err or "the sharded count step could not be set up on another rank")
+
+    def count(self, n: int, d_ctg: int, d_qs: int, d_qe: int, v: int, d_hits: int, stream: int = 0) -> None:
+        """d_hits[nFiles] (device uint64) = hits[] of all ranks' queries (overwritten); enqueued on ``stream``"""
+        if self._L.igd_b200_sharded_count(self._s, int(n), d_ctg, d_qs, d_qe, int(v), d_hits, stream):
+            raise IGDError(last_error())
+
+    def status(self) -> None:
+        if self._L.igd_b200_sharded_status(self._s):
+            raise IGDError(last_error())
+
+    def close(self) -> None:
+        if getattr(self, "_s", None):
+            self._L.igd_b200_sharded_destroy(self._s)
+            self._s = None
 
 
 class QuerySet:

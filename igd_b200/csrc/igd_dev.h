@@ -46,6 +46,9 @@ int igdb_dev_last_stages(igdb_dev *d, float out[4]);
 void *igdb_dev_pinned(igdb_dev *d, size_t bytes);   /* reusable pinned staging buffer (upload) */
 void *igdb_host_alloc(size_t bytes);                /* zeroed page-locked host memory (small result buffers) */
 void igdb_host_free(void *p);
+void *igdb_dev_malloc(igdb_dev *d, size_t bytes);   /* zeroed device memory on the handle's device (NULL on failure) */
+void igdb_dev_free(igdb_dev *d, void *p);
+int igdb_dev_memset_async(igdb_dev *d, void *p, size_t bytes, void *stream);    /* zeroes; NULL stream = the handle's */
 
 /* count (mode_v = 0: get_overlaps control flow) / -v (mode_v = 1: get_overlaps_v control flow and the
  * value >= v predicate).  Host buffers; hits_delta[nfiles] receives the counts of THIS call. t_ms[3] = H2D,

@@ -394,6 +394,31 @@ void *igdb_host_alloc(size_t bytes)
     memset(p, 0, bytes);
     return p;
 }
+// plain device memory for the host C layer (the sharded step's cost / cuts / partial-count buffers)
+void *igdb_dev_malloc(igdb_dev *d, size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaSetDevice(d->device) != cudaSuccess || cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    if (cudaMemset(p, 0, bytes ? bytes : 1) != cudaSuccess) {
+        cudaFree(p);
+        return nullptr;
+    }
+    return p;
+}
+void igdb_dev_free(igdb_dev *d, void *p)
+{
+    if (!p) return;
+    cudaSetDevice(d->device);
+    cudaFree(p);
+}
+int igdb_dev_memset_async(igdb_dev *d, void *p, size_t bytes, void *stream)
+{
+    g_err[0] = 0;
+    CK(cudaSetDevice(d->device));
+    CK(cudaMemsetAsync(p, 0, bytes, stream ? (cudaStream_t)stream : d->stream));
+    return 0;
+}
+
 void igdb_host_free(void *p)
 {
     if (p) cudaFreeHost(p);

@@ -702,6 +702,111 @@ int igd_b200_dispatch_async(igd_b200_dispatcher *x, int64_t n, const int32_t *d_
 int igd_b200_dispatcher_status(igd_b200_dispatcher *x) { g_err[0] = 0; return igdb_dispatcher_status(x); }
 void igd_b200_dispatcher_destroy(igd_b200_dispatcher *x) { igdb_dispatcher_destroy(x); }
 
+/* ---- one multi-GPU count step as ONE call (no counterpart in the reference, which is one process): everything
+ * between "this rank's 1/N of the queries is in its HBM" and "hits[] of the whole query set is in its HBM" queued on
+ * one stream with no host round trip and no library collective -- per-tile cost, its sum over the ranks (the
+ * reducer's kernel on nTiles + 1 words), cuts, the query exchange (igd_b200_dispatch_async), the search on the shard
+ * (igd_b200_count_device_shaped), the sum of hits[] over the ranks. ------------------------------------------- */
+struct igd_b200_sharded {
+    igd_b200_t *h;
+    int rank, world;
+    int64_t cap;
+    igdb_dispatcher *disp;
+    igdb_reducer *red_hits, *red_cost;
+    uint64_t *d_cost, *d_part;      /* [ntiles + 1], [nfiles] */
+    int32_t *d_cuts;                /* [world + 1] */
+};
+
+void igd_b200_sharded_destroy(igd_b200_sharded *s)
+{
+    if (!s) return;
+    if (s->disp) igdb_dispatcher_destroy(s->disp);
+    if (s->red_hits) igdb_reducer_destroy(s->red_hits);
+    if (s->red_cost) igdb_reducer_destroy(s->red_cost);
+    igdb_dev_free(s->h->dev, s->d_cost);
+    igdb_dev_free(s->h->dev, s->d_part);
+    igdb_dev_free(s->h->dev, s->d_cuts);
+    free(s);
+}
+
+igd_b200_sharded *igd_b200_sharded_create(igd_b200_t *h, int device, int rank, int world, int64_t cap)
+{
+    g_err[0] = 0;
+    if (h->ntiles + 1 > 0x7fffffff) { set_err("%s", "sharded: too many tiles"); return NULL; }
+    igd_b200_sharded *s = calloc(1, sizeof *s);
+    if (!s) return NULL;
+    s->h = h, s->rank = rank, s->world = world, s->cap = cap;
+    s->disp = igdb_dispatcher_create(h->dev, rank, world, cap);
+    s->red_hits = igdb_reducer_create(device, rank, world, h->nfiles);
+    s->red_cost = igdb_reducer_create(device, rank, world, (int32_t)(h->ntiles + 1));
+    s->d_cost = igdb_dev_malloc(h->dev, (size_t)(h->ntiles + 1) * 8);
+    s->d_part = igdb_dev_malloc(h->dev, ((size_t)h->nfiles + 1) * 8);
+    s->d_cuts = igdb_dev_malloc(h->dev, ((size_t)world + 1) * 4);
+    if (!s->disp || !s->red_hits || !s->red_cost || !s->d_cost || !s->d_part || !s->d_cuts) {
+        if (!g_err[0] && !igdb_dev_error()[0]) set_err("%s", "sharded: out of device memory");
+        igd_b200_sharded_destroy(s);
+        return NULL;
+    }
+    return s;
+}
+
+/* 3 x 64 bytes: the CUDA IPC handles of this rank's dispatcher block, hits[] mailbox and cost mailbox */
+int igd_b200_sharded_handles(igd_b200_sharded *s, void *out192)
+{
+    g_err[0] = 0;
+    char *o = out192;
+    return igdb_dispatcher_handle(s->disp, o) || igdb_reducer_handle(s->red_hits, o + 64) ||
+           igdb_reducer_handle(s->red_cost, o + 128) ? -1 : 0;
+}
+
+/* handles: world x 192 bytes, rank-major */
+int igd_b200_sharded_connect(igd_b200_sharded *s, const void *handles)
+{
+    g_err[0] = 0;
+    if (s->world == 1) return 0;
+    char *t = malloc((size_t)s->world * 64);
+    if (!t) return -1;
+    int rc = 0;
+    for (int k = 0; k < 3 && !rc; k++) {
+        for (int p = 0; p < s->world; p++) memcpy(t + 64 * (size_t)p, (const char *)handles + 192 * (size_t)p + 64 * k, 64);
+        rc = k == 0 ? igdb_dispatcher_connect(s->disp, t)
+                    : igdb_reducer_connect(k == 1 ? s->red_hits : s->red_cost, t);
+    }
+    free(t);
+    return rc ? -1 : 0;
+}
+
+/* d_hits[nFiles] (device, uint64) = hits[] of ALL ranks' queries (overwritten, not incremented); the n queries are this
+ * rank's part of the set, device arrays in any order.  Enqueued on `stream`; returns once the search has been planned
+ * (igd_b200_count_device_finish's rule).  Every rank must call it the same number of times. */
+int igd_b200_sharded_count(igd_b200_sharded *s, int64_t n, const int32_t *d_ctg, const int32_t *d_qs, const int32_t *d_qe,
+                           int32_t v, uint64_t *d_hits, void *stream)
+{
+    g_err[0] = 0;
+    igdb_dev *dev = s->h->dev;
+    int32_t *c, *qs, *qe;
+    const uint64_t *shape;
+    if (n > s->cap) { set_err("%s", "sharded_count: more queries than the receive buffers hold"); return -1; }
+    if (igdb_dev_memset_async(dev, s->d_cost, (size_t)(s->h->ntiles + 1) * 8, stream)) return -1;
+    if (igdb_dev_shard_cost(dev, n, d_ctg, d_qs, d_qe, s->d_cost, stream)) return -1;
+    if (igdb_reducer_allreduce(s->red_cost, (unsigned long long *)s->d_cost, stream)) return -1;
+    if (igdb_dev_shard_cuts(dev, s->d_cost, s->world, s->d_cuts, stream)) return -1;
+    if (igdb_dispatch_async(s->disp, n, d_ctg, d_qs, d_qe, s->d_cuts, stream, &c, &qs, &qe, &shape)) return -1;
+    if (igdb_dev_count_device_dyn(dev, s->cap, shape, c, qs, qe, filter_on(s->h, v), v, s->d_part, stream)) return -1;
+    if (igdb_dev_count_finish(dev)) return -1;
+    return igdb_reducer_allreduce_into(s->red_hits, (unsigned long long *)s->d_part, (unsigned long long *)d_hits, stream);
+}
+
+/* waits for the device; 0 = every step so far met all its peers and fitted its buffers */
+int igd_b200_sharded_status(igd_b200_sharded *s)
+{
+    g_err[0] = 0;
+    if (igdb_dispatcher_status(s->disp)) return -1;
+    int a = igdb_reducer_status(s->red_hits), b = igdb_reducer_status(s->red_cost);
+    if (a || b) { set_err("%s", "sharded: an exchange of hits[] or of the tile costs missed a peer"); return -1; }
+    return 0;
+}
+
 igd_b200_reducer *igd_b200_reducer_create(int device, int rank, int world, int32_t nfiles)
 {
     g_err[0] = 0;

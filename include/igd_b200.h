@@ -161,6 +161,24 @@ int igd_b200_dispatch_async(igd_b200_dispatcher *x, int64_t n, const int32_t *d_
 int igd_b200_dispatcher_status(igd_b200_dispatcher *x);
 void igd_b200_dispatcher_destroy(igd_b200_dispatcher *x);
 
+/* One multi-GPU count step as ONE call: from "this rank's part of the query set is in its HBM, any order" to "hits[] of
+ * the whole set is in its HBM", queued on one stream with no host round trip and no library collective -- shard_cost,
+ * its sum over the ranks (the reducer's kernel over nTiles + 1 words), shard_cuts, igd_b200_dispatch_async,
+ * igd_b200_count_device_shaped, igd_b200_reducer_allreduce_into.  One process per GPU:
+ *   s = igd_b200_sharded_create(h, device, rank, world, cap);   -- cap >= queries of the whole set (receive buffers)
+ *   igd_b200_sharded_handles(s, h192);  ... exchange the 192 bytes between the ranks ...  igd_b200_sharded_connect(s, all);
+ *   igd_b200_sharded_count(s, n, d_ctg, d_qs, d_qe, v, d_hits, stream);    -- d_hits[nFiles] (uint64) is OVERWRITTEN
+ * Every rank must call sharded_count the same number of times.  igd_b200_sharded_status waits for the device and
+ * returns 0 when every step met all its peers and fitted its buffers. */
+typedef struct igd_b200_sharded igd_b200_sharded;
+igd_b200_sharded *igd_b200_sharded_create(igd_b200_t *h, int device, int rank, int world, int64_t cap);
+int igd_b200_sharded_handles(igd_b200_sharded *s, void *out192);
+int igd_b200_sharded_connect(igd_b200_sharded *s, const void *handles);
+int igd_b200_sharded_count(igd_b200_sharded *s, int64_t n, const int32_t *d_ctg, const int32_t *d_qs, const int32_t *d_qe,
+                           int32_t v, uint64_t *d_hits, void *stream);
+int igd_b200_sharded_status(igd_b200_sharded *s);
+void igd_b200_sharded_destroy(igd_b200_sharded *s);
+
 /* -f: the overlaps themselves, in the reference's order (get_overlaps_f1, src/igd_search.c:537-620:
  * per query, bin n1 from the last start < qe downwards, then later bins ascending).
  * The arrays live in a pinned host arena owned by the handle (so that the lists come back at PCIe speed): they

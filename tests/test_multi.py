@@ -304,6 +304,18 @@ def _dispatch_rank(rank, world, port, igd_path, out_dir):
             res[f"hits{epoch}"] = h.cpu().numpy()
         disp.status()
         disp.close()
+        # the whole step as ONE C call (igd_b200_sharded_*): cost, its sum over the ranks, cuts, exchange, search, sum
+        sc = api.ShardedCounter(g, dev, 40000)
+        for epoch, (seed, n) in enumerate([(311, 25000), (312, 0), (313, 40000), (314, 3)]):
+            q = make_queries(seed, n, ("lognormal", 7.0, 1.5))
+            a, b = n * rank // world, n * (rank + 1) // world
+            mine = [torch.from_numpy(np.ascontiguousarray(x[a:b])).to(tdev) for x in (q.ctg, q.start, q.end)]
+            out = torch.full((g.nfiles,), -7, dtype=torch.int64, device=tdev)
+            sc.count(b - a, mine[0].data_ptr(), mine[1].data_ptr(), mine[2].data_ptr(), 0, out.data_ptr(), st)
+            stream.synchronize()
+            res[f"step{epoch}"] = out.cpu().numpy()
+        sc.status()
+        sc.close()
     g.close()
     np.savez(os.path.join(out_dir, f"dispatch{rank}.npz"), ok=np.array([ok]), **res)
     dist.barrier()
@@ -335,3 +347,7 @@ def test_peer_memory_query_dispatch(workdir, world):
             known = ctg >= 0
             want, _ = ref.count(ctg[known], q.start[known], q.end[known], 0)
             assert np.array_equal(z[f"hits{epoch}"], want), (r, epoch)
+        for epoch, (seed, n) in enumerate([(311, 25000), (312, 0), (313, 40000), (314, 3)]):
+            q = make_queries(seed, n, ("lognormal", 7.0, 1.5))
+            want, _ = ref.count(q.ctg, q.start, q.end, 0)
+            assert np.array_equal(z[f"step{epoch}"], want), (r, "one-call step", epoch)
