@@ -467,6 +467,10 @@ def run_ours(args):
         torch.cuda.synchronize()
         h2d_under = float(np.median([a_.elapsed_time(b_) for a_, b_ in h2d_ev[1:]])) if len(h2d_ev) > 1 else None
         assert np.array_equal(out_last, np.asarray(hits_e2e)), "pipelined and step-by-step end-to-end paths disagree"
+        hh = torch.tensor([h2d_under or 0.0], dtype=torch.float64, device=dev)
+        hall = [torch.empty_like(hh) for _ in range(world)]
+        dist.all_gather(hall, hh)
+        h2d_under = [round(float(x.item()), 4) for x in hall]     # every rank's: the slowest upload paces the stream
         if sharder.peer is not None:
             sharder.peer.status()                       # every dispatch met all its peers, no receive buffer overflowed
         if step_c is not None:
@@ -582,7 +586,7 @@ def run_ours(args):
             "e2e": {"value": n_total / (e2e_s / args.steps), "unit": UNIT, "ms_per_step": e2e_s / args.steps * 1e3,
                     "h2d_bytes_per_step": 12 * n_total, "d2h_bytes_per_step": 8 * igd.nfiles * world,
                     "single_call": e2e_single, "phases_ms_rank0_one_step": e2e_phases,
-                    "h2d_ms_under_the_previous_step_rank0": h2d_under,
+                    "h2d_ms_per_rank_under_the_previous_step": h2d_under,
                     "device_split_ms_last_step": e2e_split,
                     # the H2D leg runs at whatever the box's PCIe path gives at that moment: 16 to 54 GB/s were
                     # seen on this pool's boxes for the same pinned buffers (profiles/microbench/h2d_*.py)
