@@ -39,8 +39,7 @@ __device__ __forceinline__ void cseg_walk(const DbView &db, int64_t n, const int
     pdl_wait();                                             // the queries / counters of the previous launch
     if (dyn) n = min(n, (int64_t)dyn[0]);                   // the batch's size lives on the device (a dispatched shard)
     int nabn = 0;
-    // grid-stride over blocks of CSEG_T * CSEG_Q queries: the grid is one resident wave at most, so a batch a little
-    // larger than what the GPU holds at once does not pay for a second, nearly empty wave
+    // (grid-stride: the launch may bring fewer CTAs than blocks of CSEG_T * CSEG_Q queries)
     for (int64_t q0 = (int64_t)blockIdx.x * (CSEG_T * CSEG_Q) + threadIdx.x; q0 - threadIdx.x < n;
          q0 += (int64_t)gridDim.x * (CSEG_T * CSEG_Q)) {
     int c[CSEG_Q], s[CSEG_Q], e[CSEG_Q], tile[CSEG_Q], nlast[CSEG_Q], bd[CSEG_Q];
@@ -970,6 +969,30 @@ __device__ __forceinline__ void sts128(uint32_t addr, const int4 v)
     asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// ---- bulk asynchronous copies (cp.async.bulk -> UBLKCP, the TMA unit) completing on an mbarrier --------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\tLAB_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t@P1 bra DONE;\n\t"
+        "bra LAB_WAIT;\n\tDONE:\n\t}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+
 constexpr int RK_K = 3;                 // stages of a warp's entry ring
 
 template <bool V>
@@ -977,7 +1000,8 @@ struct RankSmem {
     static constexpr uint32_t DESC = 2 * 32 * 32;                       // a warp's ring of 64 descriptors
     static constexpr uint32_t ARR = GROUP * 2;                          // one 16-bit array of a stage
     static constexpr uint32_t STAGE = (V ? 3 : 2) * ARR;                // keys | files | (values)
-    static constexpr uint32_t WARP = DESC + RK_K * STAGE;
+    static constexpr uint32_t BARS = 32;                                // RK_K mbarriers of 8 bytes (bulk-copy variant)
+    static constexpr uint32_t WARP = DESC + RK_K * STAGE + BARS;
     static size_t hist_bytes(int nfiles) { return ((size_t)(nfiles + 1) * 4 + 127) / 128 * 128; }   // + the pads' slot
     static int warps(int nfiles, bool smem_hist)
     {
@@ -999,7 +1023,10 @@ struct RankSmem {
 // covers exactly the bytes it is about to read.  (Loading straight into registers two items ahead was tried: the
 // hardware's six scoreboards per warp are shared between the slots, and a use of the oldest slot then waits for
 // the loads issued just before it.)
-template <bool V, bool SMEM>
+// PRE4: the file fields hold 4 * file (DbView::fshift == 2).  BULK: an item's entries arrive by ONE bulk copy (the TMA
+// unit, issued by lane 0, completing on the stage's mbarrier) instead of two 16-byte cp.async per lane -- the kernel's
+// busiest unit is the shared-memory / L1 pipe, and a bulk copy's writes do not pass through it.
+template <bool V, bool SMEM, bool PRE4 = false, bool BULK = false>
 __global__ void __launch_bounds__(RK_MAXW * 32, 1) k_count_rank(const CountArgs a)
 {
     using L = RankSmem<V>;
@@ -1015,6 +1042,16 @@ __global__ void __launch_bounds__(RK_MAXW * 32, 1) k_count_rank(const CountArgs 
     const int lane = threadIdx.x & 31, W = blockDim.x >> 5, wib = threadIdx.x >> 5;
     const uint32_t ring = hist_s + hist_bytes + (uint32_t)wib * L::WARP;       // descriptors
     const uint32_t lslot = ring + L::DESC + lane * 16;                          // this lane's column of the stages
+    const uint32_t bars = ring + L::DESC + RK_K * L::STAGE;                     // BULK: one mbarrier per stage
+    uint32_t par = 0;                                                           // BULK: the phase of each stage's barrier
+    if (BULK) {
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < RK_K; ++k) mbar_init(bars + 8 * k, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
     pdl_wait();                                             // the plan, the descriptors, the segments
     const unsigned long long nseg = a.tot[0], nit = a.tot[1];
     const uint32_t n_items = (nseg > a.seg_cap || nit > a.item_cap) ? 0u : (uint32_t)nit;
@@ -1047,13 +1084,29 @@ __global__ void __launch_bounds__(RK_MAXW * 32, 1) k_count_rank(const CountArgs 
     const uint16_t *const pB = db.rb + lane * 8;
     const uint16_t *const pV = db.rv + lane * 8;
 
-    // issue the copies of item slot n into stage n % K
-    auto issue = [&](uint32_t n) {
+    // issue the copies of item slot n into stage `stg` = n % K (kept by the caller: a modulo by 3 per item is five
+    // instructions of a kernel that is bound by its issue slots)
+    auto issue = [&](uint32_t n, uint32_t stg) {
+        if (BULK) {
+            // (every lane has taken the entries of the slot that used this stage out of shared memory: __syncwarp
+            // in the loop below)
+            if (lane == 0 && n < N) {
+                const uint32_t nv = lds32(ring + (n & 63) * 32 + 8) & 0x1ffu;
+                if (nv) {
+                    const uint32_t x = lds32(ring + (n & 63) * 32), nvp = (nv + 7) & ~7u;
+                    const uint32_t dst = ring + L::DESC + stg * L::STAGE, bar = bars + 8 * stg;
+                    mbar_expect_tx(bar, nvp * (V ? 6u : 4u));
+                    bulk_g2s(dst, db.rb + (size_t)x * 16, nvp * 4, bar);        // keys[nvp] | files[nvp]
+                    if (V) bulk_g2s(dst + 2 * L::ARR, db.rv + (size_t)x * 8, nvp * 2, bar);
+                }
+            }
+            return;
+        }
         if (n < N) {
             const int2 xz = lds64(ring + (n & 63) * 32);                // A.x, A.y
             const uint32_t z = lds32(ring + (n & 63) * 32 + 8), nv = z & 0x1ffu;
             if ((uint32_t)lane * 8 < nv) {
-                const uint32_t so = lslot + (n % RK_K) * L::STAGE, nvp = (nv + 7) & ~7u;
+                const uint32_t so = lslot + stg * L::STAGE, nvp = (nv + 7) & ~7u;
                 const uint16_t *p = pB + (size_t)(uint32_t)xz.x * 16;
                 cp_async16(so, p);
                 cp_async16(so + L::ARR, p + nvp);
@@ -1063,15 +1116,20 @@ __global__ void __launch_bounds__(RK_MAXW * 32, 1) k_count_rank(const CountArgs 
         cp_async_commit();
     };
 
-    // evaluate item slot n
-    auto eval = [&](uint32_t n) {
+    // evaluate item slot n (in stage `stg` = n % K)
+    auto eval = [&](uint32_t n, uint32_t stg) {
         const int4 A = lds128(ring + (n & 63) * 32);
         const uint32_t z = (uint32_t)A.z, nv = z & 0x1ffu;
         if (nv == 0) return;
         const int4 B = lds128(ring + (n & 63) * 32 + 16);
         const bool endk = z >> 30 & 1;
-        const uint32_t so = lslot + (n % RK_K) * L::STAGE;
-        const int4 k_ = lds128(so), f_ = lds128(so + L::ARR);
+        const uint32_t so = lslot + stg * L::STAGE;
+        if (BULK) {
+            mbar_wait(bars + 8 * stg, (par >> stg) & 1u);
+            par ^= 1u << stg;
+        }
+        // (BULK: the files follow the nvp keys of the group directly)
+        const int4 k_ = lds128(so), f_ = lds128(so + (BULK ? ((nv + 7) & ~7u) * 2 : L::ARR));
         const uint32_t K[4] = {(uint32_t)k_.x, (uint32_t)k_.y, (uint32_t)k_.z, (uint32_t)k_.w};
         const uint32_t F[4] = {(uint32_t)f_.x, (uint32_t)f_.y, (uint32_t)f_.z, (uint32_t)f_.w};
         const uint32_t base2 = ((z >> 16) & 0x7fu) * 0x10001u;
@@ -1127,16 +1185,26 @@ __global__ void __launch_bounds__(RK_MAXW * 32, 1) k_count_rank(const CountArgs 
         // hits[file] += count (START) or -= count (END): one shared-memory atomic per entry; the pads of a tile's
         // last group carry file = nfiles, the histogram's trash slot
         if ((uint32_t)lane * 8 < nv) {
+            // byte offsets of the two counters of a pair of entries
+            auto off0 = [&](uint32_t f2) { return PRE4 ? f2 & 0xffffu : (f2 << 2) & 0x3fffcu; };
+            auto off1 = [&](uint32_t f2) { return PRE4 ? f2 >> 16 : (f2 >> 14) & 0x3fffcu; };
+            if (SMEM && !endk) {                                        // (warp-uniform: START items add as they are)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(hist_s + off0(F[k])), "r"(c[k] & 0xffffu) : "memory");
+                    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(hist_s + off1(F[k])), "r"(c[k] >> 16) : "memory");
+                }
+                return;
+            }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 uint32_t c0 = c[k] & 0xffffu, c1 = c[k] >> 16;
                 if (endk) c0 = 0u - c0, c1 = 0u - c1;
                 if (SMEM) {
-                    const uint32_t a0 = hist_s + ((F[k] << 2) & 0x3fffcu), a1 = hist_s + ((F[k] >> 14) & 0x3fffcu);
-                    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a0), "r"(c0) : "memory");
-                    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a1), "r"(c1) : "memory");
+                    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(hist_s + off0(F[k])), "r"(c0) : "memory");
+                    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(hist_s + off1(F[k])), "r"(c1) : "memory");
                 } else {
-                    const uint32_t f0 = F[k] & 0xffffu, f1 = F[k] >> 16;
+                    const uint32_t f0 = (F[k] & 0xffffu) >> db.fshift, f1 = (F[k] >> 16) >> db.fshift;
                     if (c0 && f0 < (uint32_t)db.nfiles) atomicAdd(&a.hits[f0], (unsigned long long)(long long)(int32_t)c0);
                     if (c1 && f1 < (uint32_t)db.nfiles) atomicAdd(&a.hits[f1], (unsigned long long)(long long)(int32_t)c1);
                 }
@@ -1145,11 +1213,15 @@ __global__ void __launch_bounds__(RK_MAXW * 32, 1) k_count_rank(const CountArgs 
     };
 
 #pragma unroll
-    for (int n = 0; n < RK_K - 1; ++n) issue(n);                        // prologue: slots 0 .. K-2
+    for (int n = 0; n < RK_K - 1; ++n) issue(n, n);                     // prologue: slots 0 .. K-2
+    uint32_t stg = 0;                                                   // n % K
     for (uint32_t n = 0; n < N; ++n) {
-        issue(n + RK_K - 1);                                            // goes into the stage slot n - 1 released
-        cp_async_wait<RK_K - 1>();                                      // slot n has landed (this lane's bytes)
-        eval(n);
+        const uint32_t prev = stg == 0 ? RK_K - 1 : stg - 1;            // (n + K - 1) % K: the stage slot n - 1 released
+        if (BULK) __syncwarp();                                         // ... by every lane
+        issue(n + RK_K - 1, prev);
+        if (!BULK) cp_async_wait<RK_K - 1>();                           // slot n has landed (this lane's bytes)
+        eval(n, stg);
+        stg = stg == RK_K - 1 ? 0 : stg + 1;
         // every 32 items the descriptors of the quad-block after next move into the half of the ring that the one
         // just finished has left (items n + 1 .. n + K - 1 -- already issued -- are in the other half)
         if ((n & 31) == 31) {
@@ -1160,7 +1232,7 @@ __global__ void __launch_bounds__(RK_MAXW * 32, 1) k_count_rank(const CountArgs 
             load_desc(g + 1, nA, nB);
         }
     }
-    cp_async_wait<0>();
+    if (!BULK) cp_async_wait<0>();
     if (SMEM) {
         __syncthreads();
         // every CTA starts at its own place of the file range: the CTAs finish together, and the same counter from
@@ -1204,7 +1276,9 @@ int count_geometry(igdb_dev *d, int *grid, int *threads, size_t *shm, bool *smem
     *shm = PK ? LP::cta_bytes(d->nfiles, *smem, nw) : L32::cta_bytes(d->nfiles, *smem, nw);
     *threads = nw * 32;
     if (d->count_grid[PK][V] == 0) {
-        const void *k = PK ? (*smem ? (const void *)k_count_rank<V, true> : (const void *)k_count_rank<V, false>)
+        const void *k = PK ? (*smem ? (d->fshift == 2 ? (d->bulk ? (const void *)k_count_rank<V, true, true, true> : (const void *)k_count_rank<V, true, true>)
+                                                      : (d->bulk ? (const void *)k_count_rank<V, true, false, true> : (const void *)k_count_rank<V, true>))
+                                    : (const void *)k_count_rank<V, false>)
                            : (*smem ? (const void *)k_count_items<V, true> : (const void *)k_count_items<V, false>);
         CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*shm));
         d->count_grid[PK][V] = d->sm_count;
@@ -1239,7 +1313,9 @@ int enqueue_count_t(igdb_dev *d, const igdb_dev::Pending &p)
     const unsigned long long item_cap =
         (unsigned long long)std::min<int64_t>(d->item_cap - CAP_SLACK, item_limit(d, grid));
     const int thr = CSEG_T;
-    const int nb = (int)std::min<int64_t>((p.n + CSEG_T * CSEG_Q - 1) / (CSEG_T * CSEG_Q), (int64_t)d->sm_count * (2048 / CSEG_T));
+    // (one block of queries per CTA: a resident wave that strides over the batch was measured slower at 10 M queries --
+    // 0.121 + 0.18 ms against 0.113 + 0.135 -- the hardware's CTA scheduler balances the tail better than a fixed stride)
+    const int nb = (int)((p.n + CSEG_T * CSEG_Q - 1) / (CSEG_T * CSEG_Q));
     const int32_t tlo = std::max(0, std::min(p.tile_lo, d->T)), thi = std::max(tlo, std::min(p.tile_hi, d->T));
     if (d->plan_grid_max == 0) {
         // k_plan's CTAs wait for each other, so all of them must be resident at once: never more than the
@@ -1304,7 +1380,10 @@ int enqueue_count_t(igdb_dev *d, const igdb_dev::Pending &p)
     if (stages) CK(cudaEventRecord(d->stage_ev[3], st));
     if (MODE != M_ABN32) CK(cudaEventRecord(d->kev[0], st));
     if (PK) {
-        if (smem) CK(launch_pdl(k_count_rank<V, true>, grid, threads, shm, st, a));
+        if (smem && d->fshift == 2 && d->bulk) CK(launch_pdl(k_count_rank<V, true, true, true>, grid, threads, shm, st, a));
+        else if (smem && d->fshift == 2) CK(launch_pdl(k_count_rank<V, true, true>, grid, threads, shm, st, a));
+        else if (smem && d->bulk) CK(launch_pdl(k_count_rank<V, true, false, true>, grid, threads, shm, st, a));
+        else if (smem) CK(launch_pdl(k_count_rank<V, true>, grid, threads, shm, st, a));
         else CK(launch_pdl(k_count_rank<V, false>, grid, threads, shm, st, a));
     } else {
         if (smem) k_count_items<V, true><<<grid, threads, shm, st>>>(a);

@@ -55,7 +55,7 @@ __device__ __forceinline__ int64_t rb_key_index(int64_t base16, int32_t n, int32
 __global__ void __launch_bounds__(256) k_pack_start(const TileMeta *__restrict__ tiles, int32_t T,
                                                      const int32_t *__restrict__ start, const int32_t *__restrict__ idx,
                                                      const int32_t *__restrict__ value, int32_t nbp, int32_t nfiles,
-                                                     uint16_t *__restrict__ rb, uint16_t *__restrict__ rv)
+                                                     int fshift, uint16_t *__restrict__ rb, uint16_t *__restrict__ rv)
 {
     const int32_t t = (int32_t)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(256) k_pack_start(const TileMeta *__restrict__
         const int64_t k = rb_key_index(base * 2, n, i, &nvp);
         const bool real = i < n;
         rb[k] = real ? (uint16_t)(pk_rel(start[base + i], bd, nbp) + 1) : (uint16_t)0x8000;
-        rb[k + nvp] = real ? (uint16_t)idx[base + i] : (uint16_t)nfiles;
+        rb[k + nvp] = (uint16_t)((real ? idx[base + i] : nfiles) << fshift);
         rv[base + i] = real ? (uint16_t)(min(max(value[base + i], 0), 32767) + 0x8000) : (uint16_t)0x8000;
     }
 }
@@ -79,7 +79,8 @@ __global__ void __launch_bounds__(256) k_pack_start(const TileMeta *__restrict__
 __global__ void __launch_bounds__(SCAN_T) k_pack_end(const TileMeta *__restrict__ tiles, int32_t T,
                                                       const int32_t *__restrict__ end, const int32_t *__restrict__ idx,
                                                       const int32_t *__restrict__ value, int32_t nbp, int32_t nfiles,
-                                                      int64_t eo, uint16_t *__restrict__ rb, uint16_t *__restrict__ rv)
+                                                      int fshift, int64_t eo, uint16_t *__restrict__ rb,
+                                                      uint16_t *__restrict__ rv)
 {
     extern __shared__ uint32_t bucket[];                        // [nbp + 2]
     const int32_t nb = nbp + 2, per = (nb + SCAN_T - 1) / SCAN_T;
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(SCAN_T) k_pack_end(const TileMeta *__restrict_
             int32_t nvp;
             const int64_t k = rb_key_index((eo + base) * 2, n, pos, &nvp);
             rb[k] = (uint16_t)e;
-            rb[k + nvp] = real ? (uint16_t)idx[base + i] : (uint16_t)nfiles;
+            rb[k + nvp] = (uint16_t)((real ? idx[base + i] : nfiles) << fshift);
             rv[eo + base + pos] = real ? (uint16_t)(min(max(value[base + i], 0), 32767) + 0x8000) : (uint16_t)0x8000;
         }
         __syncthreads();
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(SCAN_T) k_pack_end(const TileMeta *__restrict_
 // per bank (measured on B200: 3.6 -> ~2 wavefronts per ATOMS).  One warp per tile.
 __global__ void __launch_bounds__(256) k_group_banksort(const TileMeta *__restrict__ tiles, int32_t T, int64_t eo,
                                                          const uint32_t *__restrict__ gbase, uint32_t ngroups,
-                                                         uint16_t *__restrict__ rb, uint16_t *__restrict__ rv,
+                                                         int fshift, uint16_t *__restrict__ rb, uint16_t *__restrict__ rv,
                                                          uint32_t *__restrict__ gk)
 {
     __shared__ uint16_t sk[8][GROUP], sf[8][GROUP], sv[8][GROUP];
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(256) k_group_banksort(const TileMeta *__restri
             for (int32_t i = lane; i < nv; i += 32) {
                 const uint32_t k = kb[i];
                 kmin = min(kmin, k), kmax = max(kmax, k);
-                atomicAdd(&cnt[w][fb[i] & 31], 1u);
+                atomicAdd(&cnt[w][(fb[i] >> fshift) & 31], 1u);
             }
             kmin = __reduce_min_sync(FULL, kmin), kmax = __reduce_max_sync(FULL, kmax);
             __syncwarp();
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(256) k_group_banksort(const TileMeta *__restri
             __syncwarp();
             for (int32_t i = lane; i < nv; i += 32) {
                 const uint16_t f = fb[i];
-                const uint32_t pos = atomicAdd(&cnt[w][f & 31], 1u);
+                const uint32_t pos = atomicAdd(&cnt[w][(f >> fshift) & 31], 1u);
                 sk[w][pos] = kb[i], sf[w][pos] = f, sv[w][pos] = vb[i];
             }
             __syncwarp();
@@ -340,6 +341,10 @@ static int create_impl(igdb_dev *d, const int32_t *ntile, const int32_t *ncnt)
         return -1;
     // packed count-mode copies: tile-relative coordinates need nbp + 1 < 2^15, file indices 16 bits
     d->packed = d->nbp <= 16384 && d->nfiles <= 65535 && !getenv("IGD_B200_NO_PACKED");
+    // with few enough files the count-mode copy keeps 4 * file -- the byte offset of the file's counter in the shared
+    // histogram -- so the search kernel spends one instruction per entry on the address instead of two
+    d->bulk = getenv("IGD_B200_BULK") ? atoi(getenv("IGD_B200_BULK")) != 0 : false;
+    d->fshift = d->nfiles + 1 <= 16383 && !getenv("IGD_B200_NO_PRESCALE") ? 2 : 0;
     const size_t half = (size_t)d->P + 8;       // START half, END half (igd_dev_impl.cuh)
     if (d->db_groups >= (int64_t)0x7fffffff) {
         snprintf(g_err, sizeof g_err, "database too large for 32-bit group numbers");
@@ -492,13 +497,13 @@ int igdb_dev_finalize(igdb_dev *d)
     if (d->T > 0) {
         if (d->packed) {
             k_pack_start<<<(unsigned)(((int64_t)d->T * 32 + 255) / 256), 256, 0, d->stream>>>(
-                d->tiles, d->T, d->start, d->idx, d->value, d->nbp, d->nfiles, d->rb, d->rv);
+                d->tiles, d->T, d->start, d->idx, d->value, d->nbp, d->nfiles, d->fshift, d->rb, d->rv);
             const size_t shm = ((size_t)d->nbp + 2) * 4;
             CK(cudaFuncSetAttribute(k_pack_end, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
             k_pack_end<<<(unsigned)std::min<int64_t>(d->T, (int64_t)d->sm_count * 16), SCAN_T, shm, d->stream>>>(
-                d->tiles, d->T, d->end, d->idx, d->value, d->nbp, d->nfiles, (int64_t)d->P + 8, d->rb, d->rv);
+                d->tiles, d->T, d->end, d->idx, d->value, d->nbp, d->nfiles, d->fshift, (int64_t)d->P + 8, d->rb, d->rv);
             k_group_banksort<<<(unsigned)(((int64_t)d->T * 32 + 255) / 256), 256, 0, d->stream>>>(
-                d->tiles, d->T, (int64_t)d->P + 8, d->gbase, (uint32_t)d->db_groups, d->rb, d->rv, d->gk);
+                d->tiles, d->T, (int64_t)d->P + 8, d->gbase, (uint32_t)d->db_groups, d->fshift, d->rb, d->rv, d->gk);
             d->launches += 3;
         }
         k_tile_meta<<<(d->T + 255) / 256, 256, 0, d->stream>>>(d->tiles, d->T, d->start);

@@ -30,6 +30,7 @@
 //                       rv = clamp(value, 0, 32767) + 0x8000 per entry (exact for the -v thresholds 1 .. 32767;
 //                       any other threshold runs on the int32 arrays).
 //                       Pads: START key 0x8000, END key 0x7fff (past every real key), file = nFiles (a trash slot).
+//                       With nFiles + 1 <= 16383 the file fields hold 4 * file, the byte offset of hist[file] (fshift).
 //   tbase[nctg+1]     global tile index of each contig's tile 0.
 //
 // Query batches are turned into (query, tile) SEGMENTS -- one per non-empty, non-gated tile the reference
@@ -85,6 +86,7 @@ struct DbView {
     uint32_t eoff8;                         // first entry of the END half, in units of 8 entries
     const uint32_t *gbase, *gk;             // first group of each tile; per group smallest | largest << 16 real key (END half: + ngroups)
     uint32_t ngroups;
+    int32_t fshift;                         // rb's file fields are file << fshift
     const int32_t *tbase;
     int32_t nctg, nbp, nfiles, ntiles;
 };
@@ -298,6 +300,8 @@ struct igdb_dev {
     size_t d_text_cap = 0;
     uint32_t *d_starts = nullptr;                           // ingest: offsets of the candidate lines of a chunk
     bool packed = false;
+    bool bulk = false;                      // the search kernel stages an item's entries by one bulk copy (TMA) instead of cp.async
+    int fshift = 0;                         // the count-mode copy stores file << fshift (2: the byte offset of hist[file])
     int64_t bytes = 0;
     int64_t launches = 0;
     cudaStream_t stream = nullptr;
@@ -390,7 +394,7 @@ struct igdb_dev {
     {
         DbView v;
         v.tiles = tiles, v.start = start, v.end = end, v.idx = idx, v.value = value, v.tbase = tbase;
-        v.rb = rb, v.rv = rv, v.eoff8 = (uint32_t)((P + 8) / 8), v.gbase = gbase, v.gk = gk, v.ngroups = (uint32_t)db_groups;
+        v.rb = rb, v.rv = rv, v.eoff8 = (uint32_t)((P + 8) / 8), v.gbase = gbase, v.gk = gk, v.ngroups = (uint32_t)db_groups, v.fshift = fshift;
         v.nctg = nctg, v.nbp = nbp, v.nfiles = nfiles, v.ntiles = T;
         return v;
     }
