@@ -66,10 +66,17 @@ __device__ __forceinline__ void cseg_walk(const DbView &db, int64_t n, const int
         }
     }
     if (!SCATTER) {
+        // A query that stays inside ONE bin (most do) needs no look at its tile here: if the tile is empty, or the
+        // query ends before the tile's first start (the gate of :477), its segment finds nothing -- an empty tile has
+        // no work items, a gated query is past no start -- so it is simply counted; the first-bin-empty rule (:468)
+        // only matters to a query that would go on to later bins.
         int4 m[CSEG_Q];
+        bool one[CSEG_Q];
 #pragma unroll
-        for (int k = 0; k < CSEG_Q; ++k)
-            m[k] = ok[k] ? __ldg(reinterpret_cast<const int4 *>(&db.tiles[tile[k]])) : make_int4(0, 0, 0, 0);
+        for (int k = 0; k < CSEG_Q; ++k) {
+            one[k] = MODE == M_PACKED && nlast[k] == tile[k];
+            m[k] = ok[k] && !one[k] ? __ldg(reinterpret_cast<const int4 *>(&db.tiles[tile[k]])) : make_int4(0, 1, 0, IMIN);
+        }
 #pragma unroll
         for (int k = 0; k < CSEG_Q; ++k) {
             if (!V && m[k].y == 0) ok[k] = false;                           // first-bin-empty quirk (:468)
