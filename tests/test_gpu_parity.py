@@ -208,6 +208,46 @@ def test_count_int32_layout(dense_db, O, api, v, monkeypatch):
     g.close()
 
 
+@pytest.mark.parametrize("env", ["IGD_B200_NO_PRESCALE", "IGD_B200_BULK"])
+@pytest.mark.parametrize("v", [0, 500])
+def test_count_search_kernel_variants(dense_db, O, api, v, env, monkeypatch):
+    """The other instantiations of the search kernel: file indices kept unscaled in the count-mode copy (what a database
+    of 16 383 .. 65 535 files uses) and the bulk-copy (TMA) staging of the entries -- same hits[] as the default."""
+    monkeypatch.setenv(env, "1")
+    g = api.IGD(dense_db)
+    odb = O.OracleDB(dense_db)
+    for ctg, qs, qe in ((lambda q: (q.ctg, q.start, q.end))(_queries("short")), _abnormal_mix(8000)):
+        want, _ = odb.count(ctg, qs, qe, v)
+        got, _ = g.count(ctg, qs, qe, v)
+        assert np.array_equal(got, want)
+    g.close()
+
+
+def test_count_more_files_than_a_shared_histogram_holds(workdir, O, api):
+    """50 000 files: the per-CTA histogram (200 KB) leaves no room for the warps' rings, so the search kernel adds
+    to hits[] in global memory, and the file indices are too large to be kept pre-scaled."""
+    stem = os.path.join(workdir, "manyfiles")
+    rng = np.random.default_rng(97)
+    n_files, per = 50000, 12
+    ctg = rng.choice(3, size=n_files * per, p=SMALL_SIZES / SMALL_SIZES.sum()).astype(np.int32)
+    ln = np.clip(np.exp(rng.normal(6.0, 1.2, n_files * per)), 1, 50000).astype(np.int64)
+    start = np.floor(rng.random(n_files * per) * np.maximum(SMALL_SIZES[ctg] - ln, 1)).astype(np.int64)
+    end = np.minimum(start + ln, SMALL_SIZES[ctg])
+    val = rng.integers(0, 1001, size=n_files * per, dtype=np.int32)
+    files = [synth.Intervals(ctg[i * per:(i + 1) * per], start[i * per:(i + 1) * per].astype(np.int32),
+                             end[i * per:(i + 1) * per].astype(np.int32), val[i * per:(i + 1) * per]) for i in range(n_files)]
+    synth.write_igd_direct(stem, files, names=SMALL_NAMES)
+    odb = O.OracleDB(stem + ".igd")
+    g = api.IGD(stem + ".igd")
+    assert g.nfiles == n_files
+    q = _queries("short")
+    for v in (0, 500):
+        want, _ = odb.count(q.ctg, q.start, q.end, v)
+        got, _ = g.count(q.ctg, q.start, q.end, v)
+        assert want.sum() > 0 and np.array_equal(got, want), v
+    g.close()
+
+
 @pytest.mark.parametrize("b", [9, 12, 15])
 def test_count_other_bin_sizes(workdir, O, api, b):
     """igd create -b: nbp = 2^b.  b <= 14 runs on the packed layout, b = 15 on int32."""
