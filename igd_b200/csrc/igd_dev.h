@@ -46,6 +46,7 @@ int igdb_dev_last_stages(igdb_dev *d, float out[4]);
 void *igdb_dev_pinned(igdb_dev *d, size_t bytes);   /* reusable pinned staging buffer (upload) */
 void *igdb_host_alloc(size_t bytes);                /* zeroed page-locked host memory (small result buffers) */
 void igdb_host_free(void *p);
+void *igdb_dev_stream(igdb_dev *d);                 /* the handle's own cudaStream_t (what a NULL stream argument means) */
 void *igdb_dev_malloc(igdb_dev *d, size_t bytes);   /* zeroed device memory on the handle's device (NULL on failure) */
 void igdb_dev_free(igdb_dev *d, void *p);
 int igdb_dev_memset_async(igdb_dev *d, void *p, size_t bytes, void *stream);    /* zeroes; NULL stream = the handle's */

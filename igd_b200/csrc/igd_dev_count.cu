@@ -1701,12 +1701,11 @@ int igdb_dev_count_submit(igdb_dev *d, int slot, int64_t n, const int32_t *ctg, 
     }
     if (finish_pending(d)) return -1;
     if (!d->copy) CK(cudaStreamCreateWithFlags(&d->copy, cudaStreamNonBlocking));
-    if (!s.d_hits) {
-        CK(cudaMalloc((void **)&s.d_hits, std::max<size_t>((size_t)d->nfiles, 1) * 8));
-        CK(cudaMallocHost((void **)&s.h_hits, std::max<size_t>((size_t)d->nfiles, 1) * 8));
-        CK(cudaEventCreateWithFlags(&s.h2d, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
-    }
+    // (each piece on its own: a failure half way leaves the slot usable for the next attempt)
+    if (!s.d_hits) CK(cudaMalloc((void **)&s.d_hits, std::max<size_t>((size_t)d->nfiles, 1) * 8));
+    if (!s.h_hits) CK(cudaMallocHost((void **)&s.h_hits, std::max<size_t>((size_t)d->nfiles, 1) * 8));
+    if (!s.h2d) CK(cudaEventCreateWithFlags(&s.h2d, cudaEventDisableTiming));
+    if (!s.done) CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
     n = std::max<int64_t>(n, 0);
     if (d->T == 0) n = 0;
     if (grow(&s.q, &s.q_cap, 3 * std::max<int64_t>(n, 1))) return -1;

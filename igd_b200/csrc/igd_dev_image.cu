@@ -399,6 +399,8 @@ void *igdb_host_alloc(size_t bytes)
     memset(p, 0, bytes);
     return p;
 }
+void *igdb_dev_stream(igdb_dev *d) { return (void *)d->stream; }
+
 // plain device memory for the host C layer (the sharded step's cost / cuts / partial-count buffers)
 void *igdb_dev_malloc(igdb_dev *d, size_t bytes)
 {

@@ -733,6 +733,7 @@ igd_b200_sharded *igd_b200_sharded_create(igd_b200_t *h, int device, int rank, i
 {
     g_err[0] = 0;
     if (h->ntiles + 1 > 0x7fffffff) { set_err("%s", "sharded: too many tiles"); return NULL; }
+    if (cap < 1 || cap > ((int64_t)1 << 26)) { set_err("%s", "sharded: receive buffers of 1 .. 2^26 queries"); return NULL; }
     igd_b200_sharded *s = calloc(1, sizeof *s);
     if (!s) return NULL;
     s->h = h, s->rank = rank, s->world = world, s->cap = cap;
@@ -787,6 +788,7 @@ int igd_b200_sharded_count(igd_b200_sharded *s, int64_t n, const int32_t *d_ctg,
     int32_t *c, *qs, *qe;
     const uint64_t *shape;
     if (n > s->cap) { set_err("%s", "sharded_count: more queries than the receive buffers hold"); return -1; }
+    if (!stream) stream = igdb_dev_stream(dev);             /* one stream for every launch of the step */
     if (igdb_dev_memset_async(dev, s->d_cost, (size_t)(s->h->ntiles + 1) * 8, stream)) return -1;
     if (igdb_dev_shard_cost(dev, n, d_ctg, d_qs, d_qe, s->d_cost, stream)) return -1;
     if (igdb_reducer_allreduce(s->red_cost, (unsigned long long *)s->d_cost, stream)) return -1;

@@ -24,6 +24,7 @@ int igdb_dev_last_stages(igdb_dev *d, float out[4]) { (void)d; (void)out; return
 void *igdb_dev_pinned(igdb_dev *d, size_t bytes) { (void)d; (void)bytes; return NULL; }
 void *igdb_host_alloc(size_t bytes) { return calloc(1, bytes ? bytes : 1); }
 void igdb_host_free(void *p) { free(p); }
+void *igdb_dev_stream(igdb_dev *d) { (void)d; return NULL; }
 void *igdb_dev_malloc(igdb_dev *d, size_t b) { (void)d; (void)b; return NULL; }
 void igdb_dev_free(igdb_dev *d, void *p) { (void)d; (void)p; }
 int igdb_dev_memset_async(igdb_dev *d, void *p, size_t b, void *s) { (void)d; (void)p; (void)b; (void)s; return -1; }
