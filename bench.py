@@ -404,8 +404,14 @@ def run_ours(args):
 
         h2d_ev = []                                     # (begin, end) of every upload, on the copy stream
 
+        d_out2 = [torch.zeros(igd.nfiles, dtype=torch.int64, device=dev) for _ in range(2)]
+        ev_done = [torch.cuda.Event() for _ in range(2)]
+        done_valid = [False, False]
+
         def upload(k):
             with torch.cuda.stream(copy_st):
+                if step_c is not None and k >= 2 and done_valid[k & 1]:
+                    copy_st.wait_event(ev_done[k & 1])  # step k - 2 (the last reader of these buffers) has finished
                 a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a_.record(copy_st)
                 for dst, src in zip(e_in[k & 1], (h_ctg, h_qs, h_qe)):
@@ -418,15 +424,22 @@ def run_ours(args):
             upload(0)
             for k in range(k_steps):
                 if k + 1 < k_steps:
-                    upload(k + 1)                       # (its buffers were last read by step k - 1, which has completed)
+                    upload(k + 1)                       # (its buffers were last read by step k - 1)
                 side.wait_event(ev_in[k & 1])
                 if step_c is not None:
                     # the whole step as ONE C call (igd_b200_sharded_count): cost, its sum over the ranks, cuts, query
-                    # exchange, search, sum of hits[] -- the library's kernels over peer memory, no host round trip
+                    # exchange, search, sum of hits[] -- the library's kernels over peer memory, no host round trip.
+                    # The host reads a step's result one step late (two result buffers), so step k + 1 is enqueued
+                    # while step k still runs and the GPU goes from one step straight into the next.
                     x = e_in[k & 1]
-                    step_c.count(n_slice, x[0].data_ptr(), x[1].data_ptr(), x[2].data_ptr(), 0, d_hits.data_ptr(), stream)
-                    h_out[k & 1].copy_(d_hits, non_blocking=True)
-                    side.synchronize()
+                    step_c.count(n_slice, x[0].data_ptr(), x[1].data_ptr(), x[2].data_ptr(), 0, d_out2[k & 1].data_ptr(), stream)
+                    h_out[k & 1].copy_(d_out2[k & 1], non_blocking=True)
+                    ev_done[k & 1].record(side)
+                    done_valid[k & 1] = True
+                    if k >= 1:
+                        ev_done[(k - 1) & 1].synchronize()      # the result of step k - 1 is on the host
+                    if k + 1 == k_steps:
+                        ev_done[k & 1].synchronize()
                     continue
                 if sharder.peer is not None:
                     # no host round trip between the exchange and the search: the shard's shape stays on the device
