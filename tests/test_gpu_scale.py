@@ -74,6 +74,22 @@ def test_cfg5_hotspot_1mb_queries(handles, mini):
     assert np.array_equal(sm, sm_want)
 
 
+def test_cfg5_seqpare_10k_hotspot_queries(handles, mini):
+    """BASELINE config 5 at its own query count: 10 000 hotspot 1 Mb queries (31 M candidate pairs on this database)
+    through -s -- the same doubles as the oracle, file by file (tolerance stated: 1e-9 relative)."""
+    from oracle import oracle as O
+    g, o = handles
+    _, d = mini
+    q = synth.gen_hotspot_queries(synth.seed_for(5, synth.QUERY_FILE_INDEX), 10000, 1_000_000)
+    qbed = os.path.join(d, "hot10k.bed")
+    synth.write_bed(qbed, q)
+    sm_want = o.seqpare(O.Queries(qbed))
+    sm = g.seqpare(qbed)
+    assert sm_want.max() > 0
+    np.testing.assert_allclose(sm, sm_want, rtol=1e-9, atol=0)
+    assert np.array_equal(sm, sm_want)
+
+
 def test_cfg5_hitsmap_self_join(handles):
     g, o = handles
     for v in (0, 500):
