@@ -4,6 +4,7 @@
  * stdout is kept byte-compatible with the reference; anything new goes to stderr. */
 #define _GNU_SOURCE
 #include "igd_b200.h"
+#include "igd_fmt.h"
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -73,12 +74,36 @@ static int64_t print_full_batch(igd_b200_t *h, int64_t n, char *const *names, co
         fprintf(stderr, "igd: %s\n", igd_b200_last_error());
         return 0;
     }
-    for (int64_t q = 0; q < n; q++) {
-        if (!banner_applies(h, ctg[q], qs[q])) continue;
-        printf("Query %s, %i, %i: \n", names[name_id ? name_id[q] : q], qs[q], qe[q]);
-        int32_t k = 0;
-        for (int64_t i = L.query_off[q]; i < L.query_off[q + 1]; i++)
-            printf("%i\t %i\t %i\t %s\n", k++, L.start[i], L.end[i], igd_b200_file_name(h, L.file[i]));
+    /* the reference's printf calls (src/igd_search.c:545,565,592), byte for byte, through one buffer (igd_fmt.h);
+     * IGD_B200_CLI_PRINTF=1 keeps printf itself */
+    static char *obuf = NULL;
+    const size_t ocap = 4u << 20;
+    if (!obuf && !getenv("IGD_B200_CLI_PRINTF")) obuf = malloc(ocap);
+    if (!obuf) {
+        for (int64_t q = 0; q < n; q++) {
+            if (!banner_applies(h, ctg[q], qs[q])) continue;
+            printf("Query %s, %i, %i: \n", names[name_id ? name_id[q] : q], qs[q], qe[q]);
+            int32_t k = 0;
+            for (int64_t i = L.query_off[q]; i < L.query_off[q + 1]; i++)
+                printf("%i\t %i\t %i\t %s\n", k++, L.start[i], L.end[i], igd_b200_file_name(h, L.file[i]));
+        }
+    } else {
+        const int32_t nf = igd_b200_nfiles(h);
+        size_t *flen = malloc(sizeof(size_t) * (size_t)(nf > 0 ? nf : 1));
+        for (int32_t f = 0; flen && f < nf; f++) flen[f] = strlen(igd_b200_file_name(h, f));
+        fmt_sink S = {obuf, obuf, ocap, stdout};
+        for (int64_t q = 0; q < n; q++) {
+            if (!banner_applies(h, ctg[q], qs[q])) continue;
+            fmt_banner(&S, names[name_id ? name_id[q] : q], qs[q], qe[q]);
+            int32_t k = 0;
+            for (int64_t i = L.query_off[q]; i < L.query_off[q + 1]; i++) {
+                const int32_t f = L.file[i];
+                const char *fn = igd_b200_file_name(h, f);
+                fmt_hit(&S, k++, L.start[i], L.end[i], fn, flen && f >= 0 && f < nf ? flen[f] : strlen(fn));
+            }
+        }
+        fmt_flush(&S);
+        free(flen);
     }
     int64_t total = L.total;
     igd_b200_hitlist_free(&L);
