@@ -620,7 +620,11 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "k_count_rank (count-mode search, 16-bit START / END entries)",
+                         "traffic": traffic,
+                         # the counted bytes include re-reads that the L2 serves (the second chunk of a tile with more than
+                         # 64 segments reads its entries again), so `frac` can pass 1; by DRAM traffic (ncu, same kernel):
+                         "frac_by_dram_traffic": (traffic / (kmean * 1e-3) / 1e9 / peak) if traffic else None,
+                         "kernel": "k_count_rank (count-mode search, 16-bit START / END entries)",
                          "kernel_ms": kmean, "stages_ms_rank0": stages, "per_rank": per_rank,
                          "bytes_per_launch": own_bytes,
                          "bytes_definition": "what the search kernel reads per launch: 32 B per item descriptor + 4 B per "
